@@ -1,0 +1,126 @@
+/*
+ * wdr.h — C ABI of libwdr_b200: the B200-native (CUDA sm_100a) replacement for the native compute
+ * that tmoroney/whisper-diarize-rs reaches through whisper-rs (whisper.cpp) and pyannote-rs
+ * (ONNX Runtime + kaldi-native-fbank) behind Engine::transcribe_audio (reference src/engine.rs:65-200).
+ *
+ * Every entry point names the reference interface it replaces (reference file:line = the call site in
+ * the crate; "whisper.h"/"pyannote-rs" = the un-vendored upstream symbol that call resolves to).
+ * Plain pointers and sizes only.  Return convention: 0 (or a non-negative count) = ok, negative = error
+ * (see WDR_ERR_*); constructors return NULL on failure and never abort (the crate wraps them in
+ * catch_unwind, src/transcribe.rs:153).  There is no CPU fallback: without a CUDA device every compute
+ * call returns WDR_ERR_NO_DEVICE.
+ *
+ * Pointer residency: functions without a suffix take HOST pointers and do their own H2D/D2H on the
+ * library's stream; functions ending in _dev take DEVICE pointers plus a cudaStream_t (passed as
+ * void*) and never synchronise — those are the ones bench.py times with inputs resident in HBM.
+ */
+#ifndef WDR_H
+#define WDR_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WDR_OK 0
+#define WDR_ERR_INVALID (-1)     /* bad argument */
+#define WDR_ERR_NO_DEVICE (-2)   /* no CUDA device / driver: there is no CPU path */
+#define WDR_ERR_CUDA (-3)        /* a CUDA runtime call or kernel failed; see wdr_last_error() */
+#define WDR_ERR_OOM (-4)
+#define WDR_ERR_ABORTED (-5)     /* abort callback returned true (src/transcribe.rs:348-350) */
+#define WDR_ERR_TOO_SHORT (-6)   /* e.g. fbank yields 0 frames (src/transcribe.rs:466-476 maps it to speaker "?") */
+#define WDR_ERR_UNSUPPORTED (-7)
+
+#define WDR_SAMPLE_RATE 16000
+#define WDR_N_FFT 400
+#define WDR_HOP 160
+#define WDR_CHUNK_SAMPLES 480000 /* 30 s */
+#define WDR_CHUNK_FRAMES 3000    /* mel frames per 30 s window */
+#define WDR_AUDIO_CTX 1500       /* encoder positions per window */
+#define WDR_TEXT_CTX 448
+
+/* ---- library-wide ---------------------------------------------------------------------------- */
+const char* wdr_version(void);
+/* Thread-local description of the last error on this thread ("" if none). */
+const char* wdr_last_error(void);
+/* Number of CUDA devices visible (0 if none; never negative). */
+int wdr_device_count(void);
+/* Replaces whisper_log_set (whisper_rs::install_logging_hooks, reference examples/test.rs:6). */
+typedef void (*wdr_log_callback)(int level, const char* text, void* user_data);
+void wdr_log_set(wdr_log_callback cb, void* user_data);
+/* Count of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t wdr_launch_count(void);
+
+/* ---- audio (reference src/audio.rs:4-24, src/transcribe.rs:380-381, src/vad.rs:11-12) ---------- */
+/* whisper_rs::convert_integer_to_float_audio: out[i] = in[i] / 32768.0f, exact. Device kernel. */
+int wdr_convert_integer_to_float_audio(const int16_t* pcm, int n, float* out);
+
+/* ---- log-mel (whisper.cpp log_mel_spectrogram inside state.full, src/transcribe.rs:389) --------- */
+/* Mel front end: holds the [n_mel][201] filterbank (read from the ggml model file upstream), the
+ * Hann window and the twiddle tables on the device.  n_mel = 80 or 128. */
+typedef struct wdr_mel wdr_mel;
+wdr_mel* wdr_mel_init(const float* filters /* [n_mel][201] host */, int n_mel, int device);
+void wdr_mel_free(wdr_mel*);
+/* n_len whisper.cpp computes for an n-sample buffer: (n + 480000) / 160. */
+int wdr_mel_n_len(int n_samples);
+/* Whole-buffer log-mel exactly as whisper.cpp lays it out: out[n_mel][n_len], mel-major, normalised
+ * with the buffer-global max (clamp to max-8, (x+4)/4) when normalize != 0, raw log10 otherwise.
+ * Host pointers.  Returns n_len. */
+int wdr_log_mel_f32(wdr_mel*, const float* pcm, int n, int normalize, float* out);
+int wdr_log_mel_i16(wdr_mel*, const int16_t* pcm, int n, int normalize, float* out);
+/* Batched 30 s windows, the sharded mode of SURVEY §0.4: chunk b = pcm[b*chunk_stride ..][0..n_valid[b])
+ * (n_valid NULL => all 480000 valid); produces out[b][n_mel][3000] (the frames the encoder consumes,
+ * per-chunk max normalisation == whisper.cpp on that chunk alone) and, if out_max != NULL, the raw
+ * per-chunk max.  DEVICE pointers, asynchronous on `stream`. */
+int wdr_log_mel_batch_f32_dev(wdr_mel*, const float* pcm, int64_t chunk_stride, const int32_t* n_valid, int n_chunks,
+                              int normalize, float* out, float* out_max, void* stream);
+int wdr_log_mel_batch_i16_dev(wdr_mel*, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid, int n_chunks,
+                              int normalize, float* out, float* out_max, void* stream);
+/* Same, HOST pointers (H2D + kernel + D2H inside the call; pcm may be pinned or pageable). */
+int wdr_log_mel_batch_i16(wdr_mel*, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid, int n_chunks,
+                          int normalize, float* out);
+
+/* ---- DTW word alignment (whisper.cpp whisper_exp_compute_token_level_timestamps_dtw; enabled by
+ *      create_context, src/transcribe.rs:115-136; consumed at src/transcribe.rs:272-282) ---------- */
+/* median_filter custom op: w[H][N][M] -> out, odd width <= 31, reflect indexing along M. Host ptrs. */
+int wdr_median_filter(const float* w, int H, int N, int M, int width, float* out);
+/* Steps 4-6 of SURVEY A.6: alignment-head weights w[H][n_tokens][n_audio] -> normalise over tokens
+ * (eps 1e-9) -> median(width) over audio -> mean over heads -> negate -> drop the first sot_len rows and
+ * the last row.  out[(n_tokens-sot_len-1)][n_audio]. Host ptrs. */
+int wdr_dtw_cost(const float* w, int H, int n_tokens, int n_audio, int sot_len, int width, float* out);
+/* dtw_and_backtrace: cost x[N][M] -> monotone path; text_idx/time_idx hold >= N+M entries; *path_len
+ * receives the length.  Anti-diagonal wavefront on the device + serial integer backtrace.  Optional
+ * cost_out/trace_out ((N+1)*(M+1) each, may be NULL) return the accumulated-cost and trace matrices. Host ptrs. */
+int wdr_dtw(const float* x, int N, int M, int32_t* text_idx, int32_t* time_idx, int* path_len,
+            float* cost_out, int32_t* trace_out);
+/* Batched form over independent windows: x[b] is [N[b]][M[b]] at x + x_offset[b]; outputs at stride
+ * max_path per window.  DEVICE pointers for x / outputs; N, M, x_offset are HOST arrays. */
+int wdr_dtw_batch_dev(const float* x, const int64_t* x_offset, const int32_t* N, const int32_t* M, int n_windows,
+                      int32_t* text_idx, int32_t* time_idx, int32_t* path_len, int max_path, void* stream);
+
+/* ---- Kaldi fbank (knf-rs compute_fbank inside EmbeddingExtractor::compute, src/transcribe.rs:466) */
+/* Frames for an n-sample segment with snip_edges: 0 if n < 400 else 1 + (n-400)/160. */
+int wdr_fbank_frames(int n_samples);
+/* 25 ms / 10 ms povey-window, preemph 0.97, DC removal, 512-pt power spectrum, n_bins HTK-mel bins
+ * 20 Hz..Nyquist, log(max(e, FLT_EPSILON)); subtract_mean != 0 applies pyannote-rs' per-column mean
+ * subtraction.  pcm is int16 (cast to float WITHOUT scaling, as pyannote-rs does).  out[T][n_bins].
+ * Host pointers.  Returns T, or WDR_ERR_TOO_SHORT. */
+int wdr_kaldi_fbank_i16(const int16_t* pcm, int n, int n_bins, int subtract_mean, float* out);
+/* DEVICE pointers, batched over segments laid out back to back: segment s = pcm[seg_offset[s] ..
+ * seg_offset[s+1]); features of segment s start at frame feat_offset[s] of out.  seg_offset /
+ * feat_offset are DEVICE int64 arrays of n_segments+1 entries (feat_offset = prefix sum of
+ * wdr_fbank_frames).  total_frames = feat_offset[n_segments] (host value). */
+int wdr_kaldi_fbank_batch_i16_dev(const int16_t* pcm, const int64_t* seg_offset, const int64_t* feat_offset,
+                                  int n_segments, int64_t total_frames, int n_bins, int subtract_mean,
+                                  float* out, void* stream);
+
+/* ---- get_signal_energy (whisper.cpp, used by the token-timestamp heuristic) --------- */
+int wdr_signal_energy(const float* pcm, int n, int half_window, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WDR_H */

@@ -271,7 +271,8 @@ int oracle_dtw_cost(const float *w, int H, int n_tokens, int n_audio, int sot_le
  * log(max(e, FLT_EPSILON)); then per-column mean subtraction over frames (pyannote-rs).
  * in: raw int16-scale samples as fp32.  out [T][n_bins].  Returns T (0 if too short).
  * ------------------------------------------------------------------------------------------ */
-static inline double mel_htk(double f) { return 1127.0 * log(1.0 + f / 700.0); }
+/* kaldi-native-fbank MelScale: float arithmetic (mel-computations.h) */
+static inline float mel_htk(float f) { return 1127.0f * logf(1.0f + f / 700.0f); }
 
 int oracle_fbank_frames(int n) { return n < 400 ? 0 : 1 + (n - 400) / 160; }
 
@@ -286,18 +287,18 @@ int oracle_kaldi_fbank(const float *wave, int n, int n_bins, int subtract_mean, 
         win[i] = (float)pow(0.5 - 0.5 * cos(a * i), 0.85);
     }
     /* mel banks (kaldi MelBanks): low 20, high nyquist, no vtln */
-    const double nyq = 8000.0, low = 20.0, high = nyq;
-    const double fft_bin_w = (double)WDR_SAMPLE_RATE / nfft;
-    const double mlow = mel_htk(low), mhigh = mel_htk(high);
-    const double mdelta = (mhigh - mlow) / (n_bins + 1);
+    const float nyq = 8000.0f, low = 20.0f, high = nyq;
+    const float fft_bin_w = (float)WDR_SAMPLE_RATE / nfft;
+    const float mlow = mel_htk(low), mhigh = mel_htk(high);
+    const float mdelta = (mhigh - mlow) / (n_bins + 1);
     float *bank = (float *)calloc((size_t)n_bins * nb, sizeof(float));
     for (int b = 0; b < n_bins; b++) {
-        double lm = mlow + b * mdelta, cm = mlow + (b + 1) * mdelta, rm = mlow + (b + 2) * mdelta;
+        float lm = mlow + b * mdelta, cm = mlow + (b + 1) * mdelta, rm = mlow + (b + 2) * mdelta;
         for (int i = 0; i < nb; i++) {
-            double mel = mel_htk(fft_bin_w * i);
+            float mel = mel_htk(fft_bin_w * i);
             if (mel > lm && mel < rm) {
-                double wgt = mel <= cm ? (mel - lm) / (cm - lm) : (rm - mel) / (rm - cm);
-                bank[(size_t)b * nb + i] = (float)wgt;
+                float wgt = mel <= cm ? (mel - lm) / (cm - lm) : (rm - mel) / (rm - cm);
+                bank[(size_t)b * nb + i] = wgt;
             }
         }
     }

@@ -1,0 +1,191 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(libwdr_b200.so via the ctypes binding) and is compared with the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for DTW cost/trace/path, median filter, signal energy (integer / order-preserving fp work);
+log-mel within 1e-4 absolute (BASELINE.json north_star); Kaldi fbank within 2e-3 absolute on log energies
+of int16-scale audio (values ~5..25).
+"""
+import numpy as np
+import pytest
+
+from conftest import synth_audio
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-4  # north_star: "log-mel within 1e-4 absolute"
+FBANK_TOL = 2e-3
+
+
+@pytest.mark.parametrize("n_mel", [80, 128])
+@pytest.mark.parametrize("seconds", [0.0, 0.011, 1.0, 7.3, 30.0])
+def test_log_mel_whole_buffer(wdr, oracle, filters80, filters128, n_mel, seconds):
+    filt = filters80 if n_mel == 80 else filters128
+    pcm = synth_audio(100 + int(seconds * 10), seconds) if seconds > 0 else np.zeros(0, np.int16)
+    x = pcm.astype(np.float32) / 32768.0
+    ref = oracle.log_mel(x, filt, normalize=True)
+    fe = wdr.MelFrontend(filt)
+    got_f = fe.log_mel(x, normalize=True)
+    got_i = fe.log_mel(pcm, normalize=True)
+    assert got_f.shape == ref.shape
+    assert np.abs(got_f - ref).max() < MEL_TOL
+    assert np.array_equal(got_f, got_i)  # int16 decode (x/32768) is exact
+    raw_ref = oracle.log_mel(x, filt, normalize=False)
+    raw = fe.log_mel(x, normalize=False)
+    # raw log10 only compared where the oracle is above the clamp (below it rounding noise dominates)
+    mask = raw_ref > raw_ref.max() - 8.0
+    assert np.abs(raw - raw_ref)[mask].max() < 4 * MEL_TOL if mask.any() else True
+    fe.close()
+
+
+def test_log_mel_kats(wdr, filters80):
+    fe = wdr.MelFrontend(filters80)
+    assert np.all(fe.log_mel(np.zeros(16000, np.float32)) == np.float32(-1.5))
+    imp = np.zeros(4000, np.float32)
+    imp[1000] = 1.0
+    raw = fe.log_mel(imp, normalize=False)
+    w = 0.5 * (1 - np.cos(2 * np.pi * 240 / 400))
+    expect = np.log10(np.maximum(w * w * filters80.sum(1), 1e-10))
+    assert np.abs(raw[:, 6] - expect).max() < 1e-4
+    fe.close()
+
+
+def test_log_mel_batch_matches_per_chunk(wdr, oracle, filters80):
+    """Sharded mode: each 30 s chunk == whisper.cpp on that chunk alone, first 3000 frames."""
+    B = 3
+    pcm = np.stack([synth_audio(2000 + i, 30.0) for i in range(B)])
+    n_valid = np.array([480000, 480000, 123457], np.int32)
+    pcm[2, n_valid[2]:] = 0
+    fe = wdr.MelFrontend(filters80)
+    got = fe.log_mel_batch(pcm, n_valid=n_valid)
+    assert got.shape == (B, 80, 3000)
+    for b in range(B):
+        x = pcm[b, : n_valid[b]].astype(np.float32) / 32768.0
+        ref = oracle.log_mel(x, filters80)[:, :3000]
+        assert np.abs(got[b] - ref).max() < MEL_TOL
+    fe.close()
+
+
+def test_convert_integer_to_float_audio(wdr):
+    x = np.array([-32768, -1, 0, 1, 12345, 32767], np.int16)
+    assert np.array_equal(wdr.convert_integer_to_float_audio(x), x.astype(np.float32) / np.float32(32768.0))
+
+
+@pytest.mark.parametrize("shape,width", [((1, 1, 4), 7), ((3, 17, 120), 7), ((10, 60, 1500), 7), ((2, 5, 33), 3), ((1, 2, 64), 31)])
+def test_median_filter_bit_exact(wdr, oracle, shape, width):
+    rng = np.random.default_rng(sum(shape))
+    w = rng.standard_normal(shape).astype(np.float32)
+    assert np.array_equal(wdr.median_filter(w, width), oracle.median_filter(w, width))
+
+
+def test_median_filter_rejects_short_rows(wdr):
+    with pytest.raises(wdr.WdrError):
+        wdr.median_filter(np.zeros((1, 1, 3), np.float32), 7)
+    with pytest.raises(wdr.WdrError):
+        wdr.median_filter(np.zeros((1, 1, 30), np.float32), 4)
+
+
+@pytest.mark.parametrize("H,T,A,sot", [(5, 12, 50, 1), (10, 40, 1500, 2), (8, 3, 9, 1), (6, 226, 700, 2)])
+def test_dtw_cost_bit_exact(wdr, oracle, H, T, A, sot):
+    rng = np.random.default_rng(H * T + A)
+    w = rng.random((H, T, A)).astype(np.float32)
+    w /= w.sum(2, keepdims=True)  # rows look like softmaxed attention
+    assert np.array_equal(wdr.dtw_cost(w, sot, 7), oracle.dtw_cost(w, sot, 7))
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (1, 9), (9, 1), (3, 4), (5, 7), (40, 300), (224, 1500), (300, 40), (1100, 64), (4200, 37)])
+def test_dtw_bit_exact(wdr, oracle, n, m):
+    rng = np.random.default_rng(n * 7919 + m)
+    x = rng.standard_normal((n, m)).astype(np.float32)
+    ti, tj, cost, trace = wdr.dtw(x, want_matrices=True)
+    rti, rtj, rcost, rtrace = oracle.dtw(x, want_matrices=True)
+    assert np.array_equal(cost, rcost)
+    assert np.array_equal(trace, rtrace)
+    assert np.array_equal(ti, rti) and np.array_equal(tj, rtj)
+    ti2, tj2 = wdr.dtw(x)
+    assert np.array_equal(ti2, rti) and np.array_equal(tj2, rtj)
+
+
+def test_dtw_ties_and_infinities(wdr, oracle):
+    cases = [np.zeros((3, 4), np.float32), np.ones((6, 6), np.float32)]
+    x = np.zeros((2, 3), np.float32)
+    x[0, 1] = np.inf
+    cases.append(x)
+    rng = np.random.default_rng(9)
+    cases.append(rng.integers(0, 3, (30, 90)).astype(np.float32))  # many exact ties
+    y = rng.standard_normal((20, 50)).astype(np.float32)
+    y[rng.random((20, 50)) < 0.2] = np.inf
+    cases.append(y)
+    for x in cases:
+        ti, tj, cost, trace = wdr.dtw(x, want_matrices=True)
+        rti, rtj, rcost, rtrace = oracle.dtw(x, want_matrices=True)
+        assert np.array_equal(cost, rcost) and np.array_equal(trace, rtrace)
+        assert np.array_equal(ti, rti) and np.array_equal(tj, rtj)
+    ti, tj = wdr.dtw(np.zeros((0, 5), np.float32))
+    assert len(ti) == 0 and len(tj) == 0
+
+
+def test_dtw_batch_dev(wdr, oracle):
+    import torch
+    rng = np.random.default_rng(4)
+    shapes = [(17, 300), (224, 1500), (1, 40), (60, 750), (0, 10)]
+    xs = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    offs = np.cumsum([0] + [x.size for x in xs])[:-1].astype(np.int64)
+    flat = torch.from_numpy(np.concatenate([x.ravel() for x in xs])).cuda()
+    max_path = 1800
+    ti = torch.full((len(xs), max_path), -7, dtype=torch.int32, device="cuda")
+    tj = torch.full((len(xs), max_path), -7, dtype=torch.int32, device="cuda")
+    ln = torch.zeros(len(xs), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    wdr.dtw_batch_dev(flat.data_ptr(), offs, [s[0] for s in shapes], [s[1] for s in shapes], ti.data_ptr(), tj.data_ptr(),
+                      ln.data_ptr(), max_path, st)
+    torch.cuda.synchronize()
+    for b, x in enumerate(xs):
+        L = int(ln[b])
+        if x.shape[0] == 0:
+            assert L == 0
+            continue
+        rti, rtj = oracle.dtw(x)
+        assert L == len(rti)
+        assert np.array_equal(ti[b, :L].cpu().numpy(), rti) and np.array_equal(tj[b, :L].cpu().numpy(), rtj)
+
+
+@pytest.mark.parametrize("n", [400, 559, 560, 16000, 5 * 16000 + 123, 37 * 16000])
+def test_kaldi_fbank(wdr, oracle, n):
+    pcm = synth_audio(300 + n % 97, n / 16000.0 + 0.01)[:n]
+    ref = oracle.kaldi_fbank(pcm.astype(np.float32), 80, subtract_mean=False)
+    got = wdr.kaldi_fbank(pcm, 80, subtract_mean=False)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < FBANK_TOL
+    refc = oracle.kaldi_fbank(pcm.astype(np.float32), 80, subtract_mean=True)
+    gotc = wdr.kaldi_fbank(pcm, 80, subtract_mean=True)
+    assert np.abs(gotc - refc).max() < FBANK_TOL
+
+
+def test_kaldi_fbank_too_short(wdr):
+    with pytest.raises(wdr.WdrError) as e:
+        wdr.kaldi_fbank(np.zeros(399, np.int16))
+    assert e.value.code == -6
+
+
+def test_kaldi_fbank_batch_dev(wdr, oracle):
+    import torch
+    segs = [synth_audio(500 + i, s) for i, s in enumerate((0.5, 3.2, 0.02, 1.0))]  # third one yields 0 frames
+    seg_off = np.cumsum([0] + [len(s) for s in segs]).astype(np.int64)
+    frames = [wdr.fbank_frames(len(s)) for s in segs]
+    feat_off = np.cumsum([0] + frames).astype(np.int64)
+    pcm = torch.from_numpy(np.concatenate(segs)).cuda()
+    out = torch.zeros((int(feat_off[-1]), 80), dtype=torch.float32, device="cuda")
+    so, fo = torch.from_numpy(seg_off).cuda(), torch.from_numpy(feat_off).cuda()
+    rc = wdr.load().wdr_kaldi_fbank_batch_i16_dev(pcm.data_ptr(), so.data_ptr(), fo.data_ptr(), len(segs), int(feat_off[-1]), 80, 1,
+                                                  out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    for i, s in enumerate(segs):
+        ref = oracle.kaldi_fbank(s.astype(np.float32), 80, subtract_mean=True)
+        assert np.abs(o[feat_off[i]:feat_off[i + 1]] - ref).max(initial=0) < FBANK_TOL
+
+
+def test_signal_energy_bit_exact(wdr, oracle):
+    x = synth_audio(77, 1.0).astype(np.float32) / 32768.0
+    assert np.array_equal(wdr.signal_energy(x, 32), oracle.signal_energy(x, 32))

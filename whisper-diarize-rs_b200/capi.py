@@ -1,0 +1,219 @@
+"""ctypes binding of libwdr_b200.so — one Python function per C entry point of include/wdr.h."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_SO = os.path.join(_CSRC, "libwdr_b200.so")
+_lib = None
+
+f32p, i16p, i32p, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int16), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+
+WDR_ERR_NO_DEVICE = -2
+WDR_ERR_TOO_SHORT = -6
+
+
+class WdrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"wdr error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _SO
+
+
+def build(force=False):
+    """Compile csrc/*.cu for sm_100a into csrc/libwdr_b200.so (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.check_call(["make", "-C", _CSRC, "clean"], stdout=subprocess.DEVNULL)
+    subprocess.check_call(["make", "-C", _CSRC, "-j8", "-s"])
+    return _SO
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise WdrError(-100, f"{_SO} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(_SO)
+    L.wdr_version.restype = C.c_char_p
+    L.wdr_last_error.restype = C.c_char_p
+    L.wdr_launch_count.restype = C.c_uint64
+    L.wdr_mel_init.restype = C.c_void_p
+    L.wdr_mel_init.argtypes = [f32p, C.c_int, C.c_int]
+    L.wdr_mel_free.argtypes = [C.c_void_p]
+    L.wdr_mel_n_len.argtypes = [C.c_int]
+    L.wdr_log_mel_f32.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, f32p]
+    L.wdr_log_mel_i16.argtypes = [C.c_void_p, i16p, C.c_int, C.c_int, f32p]
+    L.wdr_log_mel_batch_f32_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.wdr_log_mel_batch_i16_dev.argtypes = L.wdr_log_mel_batch_f32_dev.argtypes
+    L.wdr_log_mel_batch_i16.argtypes = [C.c_void_p, i16p, C.c_int64, i32p, C.c_int, C.c_int, f32p]
+    L.wdr_convert_integer_to_float_audio.argtypes = [i16p, C.c_int, f32p]
+    L.wdr_median_filter.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+    L.wdr_dtw_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+    L.wdr_dtw.argtypes = [f32p, C.c_int, C.c_int, i32p, i32p, C.POINTER(C.c_int), f32p, i32p]
+    L.wdr_dtw_batch_dev.argtypes = [C.c_void_p, i64p, i32p, i32p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.wdr_fbank_frames.argtypes = [C.c_int]
+    L.wdr_kaldi_fbank_i16.argtypes = [i16p, C.c_int, C.c_int, C.c_int, f32p]
+    L.wdr_kaldi_fbank_batch_i16_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.wdr_signal_energy.argtypes = [f32p, C.c_int, C.c_int, f32p]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc < 0:
+        raise WdrError(rc, load().wdr_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _p(a, ptype):
+    return a.ctypes.data_as(ptype)
+
+
+def version():
+    return load().wdr_version().decode()
+
+
+def device_count():
+    return load().wdr_device_count()
+
+
+def launch_count():
+    return int(load().wdr_launch_count())
+
+
+def mel_n_len(n):
+    return load().wdr_mel_n_len(int(n))
+
+
+class MelFrontend:
+    """wdr_mel handle: whisper.cpp log_mel_spectrogram on the device (reference src/transcribe.rs:389)."""
+
+    def __init__(self, filters, device=0):
+        f = _np(filters, np.float32)
+        assert f.ndim == 2 and f.shape[1] == 201
+        self.n_mel = f.shape[0]
+        self._h = load().wdr_mel_init(_p(f, f32p), self.n_mel, device)
+        if not self._h:
+            raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, load().wdr_last_error().decode())
+
+    def close(self):
+        if self._h:
+            load().wdr_mel_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def log_mel(self, pcm, normalize=True):
+        """Whole buffer, whisper.cpp layout: returns mel[n_mel, n_len]."""
+        pcm = np.asarray(pcm)
+        n_len = mel_n_len(len(pcm))
+        out = np.empty((self.n_mel, n_len), np.float32)
+        if pcm.dtype == np.int16:
+            x = _np(pcm, np.int16)
+            _check(load().wdr_log_mel_i16(self._h, _p(x, i16p), len(x), int(normalize), _p(out, f32p)))
+        else:
+            x = _np(pcm, np.float32)
+            _check(load().wdr_log_mel_f32(self._h, _p(x, f32p), len(x), int(normalize), _p(out, f32p)))
+        return out
+
+    def log_mel_batch(self, pcm_i16, n_valid=None, normalize=True):
+        """pcm_i16[B, 480000] host array -> mel[B, n_mel, 3000] (H2D + kernel + D2H inside the call)."""
+        x = _np(pcm_i16, np.int16)
+        assert x.ndim == 2 and x.shape[1] == 480000
+        out = np.empty((x.shape[0], self.n_mel, 3000), np.float32)
+        nv = None if n_valid is None else _np(n_valid, np.int32)
+        _check(load().wdr_log_mel_batch_i16(self._h, _p(x, i16p), x.shape[1], None if nv is None else _p(nv, i32p),
+                                            x.shape[0], int(normalize), _p(out, f32p)))
+        return out
+
+    def log_mel_batch_dev(self, pcm_ptr, is_i16, chunk_stride, n_chunks, out_ptr, n_valid_ptr=None, out_max_ptr=None,
+                          normalize=True, stream=0):
+        """Device pointers (ints), asynchronous on `stream` (a cudaStream_t value)."""
+        fn = load().wdr_log_mel_batch_i16_dev if is_i16 else load().wdr_log_mel_batch_f32_dev
+        _check(fn(self._h, pcm_ptr, chunk_stride, n_valid_ptr, n_chunks, int(normalize), out_ptr, out_max_ptr, stream))
+
+
+def log_mel(pcm, filters, normalize=True, device=0):
+    m = MelFrontend(filters, device)
+    try:
+        return m.log_mel(pcm, normalize)
+    finally:
+        m.close()
+
+
+def convert_integer_to_float_audio(pcm_i16):
+    x = _np(pcm_i16, np.int16)
+    out = np.empty(len(x), np.float32)
+    _check(load().wdr_convert_integer_to_float_audio(_p(x, i16p), len(x), _p(out, f32p)))
+    return out
+
+
+def median_filter(w, width=7):
+    w3 = _np(w, np.float32)
+    H, N, M = w3.shape
+    out = np.empty_like(w3)
+    _check(load().wdr_median_filter(_p(w3, f32p), H, N, M, width, _p(out, f32p)))
+    return out
+
+
+def dtw_cost(w, sot_len, width=7):
+    w3 = _np(w, np.float32)
+    H, T, A = w3.shape
+    out = np.empty((T - sot_len - 1, A), np.float32)
+    _check(load().wdr_dtw_cost(_p(w3, f32p), H, T, A, sot_len, width, _p(out, f32p)))
+    return out
+
+
+def dtw(x, want_matrices=False):
+    x2 = _np(x, np.float32)
+    N, M = x2.shape
+    ti = np.empty(N + M + 2, np.int32)
+    tj = np.empty(N + M + 2, np.int32)
+    n = C.c_int(0)
+    cost = trace = None
+    cp, tp = f32p(), i32p()
+    if want_matrices:
+        cost = np.empty((N + 1, M + 1), np.float32)
+        trace = np.empty((N + 1, M + 1), np.int32)
+        cp, tp = _p(cost, f32p), _p(trace, i32p)
+    _check(load().wdr_dtw(_p(x2, f32p), N, M, _p(ti, i32p), _p(tj, i32p), C.byref(n), cp, tp))
+    if want_matrices:
+        return ti[: n.value].copy(), tj[: n.value].copy(), cost, trace
+    return ti[: n.value].copy(), tj[: n.value].copy()
+
+
+def dtw_batch_dev(x_ptr, x_offset, N, M, text_ptr, time_ptr, len_ptr, max_path, stream=0):
+    xo, n_, m_ = _np(x_offset, np.int64), _np(N, np.int32), _np(M, np.int32)
+    _check(load().wdr_dtw_batch_dev(x_ptr, _p(xo, i64p), _p(n_, i32p), _p(m_, i32p), len(n_), text_ptr, time_ptr, len_ptr,
+                                    max_path, stream))
+
+
+def fbank_frames(n):
+    return load().wdr_fbank_frames(int(n))
+
+
+def kaldi_fbank(pcm_i16, n_bins=80, subtract_mean=True):
+    x = _np(pcm_i16, np.int16)
+    T = fbank_frames(len(x))
+    out = np.empty((max(T, 0), n_bins), np.float32)
+    rc = _check(load().wdr_kaldi_fbank_i16(_p(x, i16p), len(x), n_bins, int(subtract_mean), _p(out, f32p)))
+    assert rc == T
+    return out
+
+
+def signal_energy(pcm_f32, hw=32):
+    x = _np(pcm_f32, np.float32)
+    out = np.empty_like(x)
+    _check(load().wdr_signal_energy(_p(x, f32p), len(x), hw, _p(out, f32p)))
+    return out

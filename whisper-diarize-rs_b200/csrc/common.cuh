@@ -1,0 +1,85 @@
+// common.cuh — error plumbing, launch accounting and small device helpers shared by every kernel file.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/wdr.h"
+
+namespace wdr {
+
+// thread-local last-error text (wdr_last_error)
+void set_error(const char* fmt, ...);
+void clear_error();
+void log_msg(int level, const char* fmt, ...);
+
+extern std::atomic<uint64_t> g_launches;
+inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Returns WDR_OK if a usable device exists (and makes `device` current), WDR_ERR_NO_DEVICE otherwise.
+int ensure_device(int device);
+
+#define WDR_CUDA_TRY(expr)                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            ::wdr::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? WDR_ERR_OOM : WDR_ERR_CUDA;                  \
+        }                                                                                           \
+    } while (0)
+
+#define WDR_LAUNCH_CHECK()                                                                                 \
+    do {                                                                                                   \
+        ::wdr::count_launch();                                                                             \
+        cudaError_t _e = cudaGetLastError();                                                               \
+        if (_e != cudaSuccess) {                                                                           \
+            ::wdr::set_error("%s:%d: kernel launch failed -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return WDR_ERR_CUDA;                                                                           \
+        }                                                                                                  \
+    } while (0)
+
+#define WDR_REQUIRE(cond, msg)                   \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::wdr::set_error("%s: %s", __func__, msg); \
+            return WDR_ERR_INVALID;              \
+        }                                        \
+    } while (0)
+
+// RAII device buffer for the host-pointer entry points.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t count) {
+        n = count;
+        return cudaMalloc(reinterpret_cast<void**>(&p), (count ? count : 1) * sizeof(T));
+    }
+};
+
+// Monotone float <-> uint key (for atomicMax over floats of either sign).
+__device__ __forceinline__ unsigned float_to_key(float f) {
+    unsigned b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace wdr
