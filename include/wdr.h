@@ -120,6 +120,19 @@ int wdr_kaldi_fbank_batch_i16_dev(const int16_t* pcm, const int64_t* seg_offset,
 /* ---- get_signal_energy (whisper.cpp, used by the token-timestamp heuristic) --------- */
 int wdr_signal_energy(const float* pcm, int n, int half_window, float* out);
 
+/* ---- stage-level kernels (not in whisper.h; for parity tests and roofline measurement) -------------- */
+/* tcgen05 bf16 GEMM: D[M][N] = A[M][K] * W[N][K]^T with a fused epilogue (the ggml mul_mat / ONNX Gemm of the
+ * encoder, decoder and embedding nets).  bf16 values are passed as uint16_t.  A rows are n_batch groups of
+ * rows_per_batch rows (row stride lda, batch stride a_batch_stride, elements).  kb_per_tap > 0 selects the
+ * implicit-GEMM (conv1d) addressing: K is cut into taps of kb_per_tap*64 columns, tap t reads A rows r + t.
+ * epilogue: 0 bias->bf16, 1 bias+GELU->bf16, 2 resid+bias->f32 (resid_or_pos = resid[M][ldc]),
+ * 3 GELU(bias)+pos->f32 (resid_or_pos = pos[rows_per_batch][N]), 4 QKV (columns >= n_split stored transposed
+ * into out_t[n - n_split][row], row stride ldt), 5 bias->f32.  DEVICE pointers, asynchronous on stream. */
+int wdr_gemm_bf16_dev(const uint16_t* A, int64_t lda, int rows_per_batch, int n_batch, int64_t a_batch_stride,
+                      const uint16_t* W, int64_t ldw, int N, int K, int kb_per_tap, int a_cols, const float* bias,
+                      int epilogue, void* out, int64_t ldc, const float* resid_or_pos, uint16_t* out_t, int64_t ldt,
+                      int n_split, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,5 +12,5 @@ or through the `wdr_b200` alias module at the repo root.
 from .capi import (  # noqa: F401
     WdrError, load, lib_path, build, version, device_count, launch_count,
     MelFrontend, log_mel, median_filter, dtw_cost, dtw, dtw_batch_dev, kaldi_fbank, fbank_frames,
-    signal_energy, convert_integer_to_float_audio, mel_n_len,
+    signal_energy, convert_integer_to_float_audio, mel_n_len, gemm_bf16_dev,
 )

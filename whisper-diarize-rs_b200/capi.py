@@ -62,6 +62,9 @@ def load():
     L.wdr_kaldi_fbank_i16.argtypes = [i16p, C.c_int, C.c_int, C.c_int, f32p]
     L.wdr_kaldi_fbank_batch_i16_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.wdr_signal_energy.argtypes = [f32p, C.c_int, C.c_int, f32p]
+    L.wdr_gemm_bf16_dev.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                    C.c_int, C.c_void_p]
     _lib = L
     return L
 
@@ -217,3 +220,10 @@ def signal_energy(pcm_f32, hw=32):
     out = np.empty_like(x)
     _check(load().wdr_signal_energy(_p(x, f32p), len(x), hw, _p(out, f32p)))
     return out
+
+
+def gemm_bf16_dev(A_ptr, lda, rows_per_batch, n_batch, a_batch_stride, W_ptr, ldw, N, K, out_ptr, ldc, epilogue=0, bias_ptr=None,
+                  extra_ptr=None, out_t_ptr=None, ldt=0, n_split=0, kb_per_tap=0, a_cols=0, stream=0):
+    """tcgen05 GEMM on device pointers (ints); see wdr_gemm_bf16_dev in include/wdr.h."""
+    _check(load().wdr_gemm_bf16_dev(A_ptr, lda, rows_per_batch, n_batch, a_batch_stride, W_ptr, ldw, N, K, kb_per_tap, a_cols,
+                                    bias_ptr, epilogue, out_ptr, ldc, extra_ptr, out_t_ptr, ldt, n_split, stream))

@@ -1,0 +1,350 @@
+// gemm.cu — persistent, warp-specialised bf16 GEMM on tcgen05 tensor cores for sm_100a.
+//
+// The Whisper encoder/decoder linear layers, the conv stem (as implicit GEMM over strided row views) and
+// the WeSpeaker/pyannote dense layers all run through this kernel.  It replaces ggml's mul_mat (whisper.cpp
+// `whisper_encode_internal`, reached from reference src/transcribe.rs:389) and ONNX Runtime's Gemm/Conv.
+//
+//   D[M x N] = A[M x K] * W[N x K]^T, bf16 operands (both K-major), fp32 accumulation in TMEM.
+//
+// CTA = 8 warps: warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, kStages-deep mbarrier ring),
+// warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1 128 x BN x 16, tcgen05.commit frees the
+// shared-memory stage / publishes the accumulator), warp 2 = TMEM allocator, warps 4..7 = epilogue
+// (tcgen05.ld 32 lanes x 32 columns per warp, fused bias / GELU / residual / positional embedding /
+// transposed store).  Two accumulator stages in TMEM let the epilogue of tile i overlap the MMAs of tile i+1.
+// One CTA per SM, persistent over a (m-tile, n-tile) list with n fastest so that concurrently running CTAs
+// share the same A tile through L2.
+#include <cuda.h>
+#include <mutex>
+#include "common.cuh"
+#include "gemm.cuh"
+#include "sm100.cuh"
+
+namespace wdr {
+
+using namespace sm100;
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kGemmThreads = 256;
+
+struct GemmParams {
+    int rows_per_batch, n_batch, N, K;
+    int kb_per_tap;
+    int tiles_per_batch, n_tiles, total_tiles;
+    void* out;
+    int64_t ldc;
+    const float* bias;
+    const float* resid;
+    const float* pos;
+    __nv_bfloat16* out_t;
+    int64_t ldt;
+    int n_split;
+};
+
+__device__ __forceinline__ float gelu_tanh(float x) {
+    // 0.5 x (1 + tanh(u)) == x * sigmoid(2u),  u = sqrt(2/pi) * x * (1 + 0.044715 x^2)   (ggml_gelu_f32)
+    const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
+    return __fdividef(x, 1.0f + __expf(-2.0f * u));
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+    constexpr int kABytes = kBM * kBK * 2;
+    constexpr int kBBytes = BN * kBK * 2;
+    constexpr uint32_t kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+    static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "BN");
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + STAGES * kABytes;
+    __shared__ __align__(8) uint64_t bar_full[STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[STAGES];
+    __shared__ __align__(8) uint64_t bar_tfull[2];
+    __shared__ __align__(8) uint64_t bar_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + kBK - 1) / kBK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tma_a);
+        tma_prefetch_desc(&tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(&bar_full[s], 1);
+            mbar_init(&bar_empty[s], 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(&bar_tfull[s], 1);
+            mbar_init(&bar_tempty[s], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        tmem_alloc(&s_tmem_base, kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+                const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(&bar_empty[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&bar_full[s], kABytes + kBBytes);
+                    const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                    tma_load_3d(sA + s * kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
+                    tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                mbar_wait(&bar_tempty[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BN;
+                for (int kb = 0; kb < num_kb; kb++) {
+                    mbar_wait(&bar_full[s], ph);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * kABytes));
+                    const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; k++) {
+                        // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&bar_empty[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&bar_tfull[as]);
+                as ^= 1;
+                if (as == 0) aph ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int q = warp & 3;  // TMEM lane group this warp may access
+        int as = 0;
+        uint32_t aph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+            const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
+            const int r_in_batch = mt * kBM + q * 32 + lane;
+            const bool row_ok = r_in_batch < p.rows_per_batch;
+            const int64_t grow = (int64_t)batch * p.rows_per_batch + r_in_batch;
+            mbar_wait(&bar_tfull[as], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                const int n0 = n_tile * BN + c * 32;
+                if (n0 >= p.N) break;  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n0 + j < p.N) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                        }
+                    }
+                }
+                if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = gelu_tanh(v[j]);
+                }
+                if (!row_ok) continue;
+                if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || (EPI == EPI_QKV_BF16 && n0 < p.n_split)) {
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + n0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (n0 + j < p.N) {
+                            uint4 w;
+                            w.x = pack_bf16(v[j], v[j + 1]);
+                            w.y = pack_bf16(v[j + 2], v[j + 3]);
+                            w.z = pack_bf16(v[j + 4], v[j + 5]);
+                            w.w = pack_bf16(v[j + 6], v[j + 7]);
+                            *reinterpret_cast<uint4*>(o + j) = w;
+                        }
+                    }
+                } else if (EPI == EPI_QKV_BF16) {
+                    // transposed store: lanes hold consecutive rows -> 64 B coalesced per column
+                    __nv_bfloat16* o = p.out_t + (int64_t)(n0 - p.n_split) * p.ldt + grow;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (n0 + j < p.N) o[(int64_t)j * p.ldt] = __float2bfloat16_rn(v[j]);
+                } else {
+                    float* o = reinterpret_cast<float*>(p.out) + grow * p.ldc + n0;
+                    const float* rs = (EPI == EPI_BIAS_RESID_F32) ? p.resid + grow * p.ldc + n0
+                                      : (EPI == EPI_BIAS_GELU_POS_F32) ? p.pos + (int64_t)r_in_batch * p.N + n0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (n0 + j < p.N) {
+                            float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                            if (rs) {
+                                const float4 a = *reinterpret_cast<const float4*>(rs + j);
+                                w.x += a.x; w.y += a.y; w.z += a.z; w.w += a.w;
+                            }
+                            *reinterpret_cast<float4*>(o + j) = w;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar_tempty[as]);
+            as ^= 1;
+            if (as == 0) aph ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+static PFN_encodeTiled get_encode() {
+    std::call_once(g_encode_once, [] {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    });
+    return g_encode;
+}
+
+// bf16 tensor map with 128-byte swizzle; dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return WDR_ERR_CUDA; }
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; i++) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) gstr[i] = strides_bytes[i];
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu] stride0 %llu base %p", (int)r, rank,
+                  (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), (unsigned long long)(rank > 2 ? dims[2] : 0),
+                  (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), base);
+        return WDR_ERR_CUDA;
+    }
+    return WDR_OK;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int BN, int STAGES, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
+    static bool attr_done = false;
+    if (!attr_done) {
+        WDR_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    gemm_bf16_kernel<BN, STAGES, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+    WDR_LAUNCH_CHECK();
+    return WDR_OK;
+}
+
+int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
+    WDR_REQUIRE(d.A && d.W && d.out && d.rows_per_batch > 0 && d.n_batch > 0 && d.N > 0 && d.K > 0, "bad arguments");
+    WDR_REQUIRE(d.N % 8 == 0 && d.K % 8 == 0, "N and K must be multiples of 8");
+    WDR_REQUIRE(d.a_row_stride % 8 == 0 && d.a_batch_stride % 8 == 0 && d.ldw % 8 == 0, "operand strides must be multiples of 8 elements");
+    WDR_REQUIRE((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0, "operands must be 16-byte aligned");
+    WDR_REQUIRE(d.ldc % 8 == 0, "ldc must be a multiple of 8");
+    if (d.epilogue == EPI_QKV_BF16) WDR_REQUIRE(d.out_t && d.n_split % 32 == 0, "QKV epilogue needs out_t and n_split % 32 == 0");
+    constexpr int BN = 128;
+    CUtensorMap ta, tb;
+    {
+        // in tap mode the last tap reads rows up to rows_per_batch - 1 + (taps - 1): the caller's buffer holds them
+        const int num_kb = (d.K + kBK - 1) / kBK;
+        const int taps = d.kb_per_tap > 0 ? (num_kb + d.kb_per_tap - 1) / d.kb_per_tap : 1;
+        const uint64_t dims[3] = {(uint64_t)(d.a_cols > 0 ? d.a_cols : d.K), (uint64_t)(d.rows_per_batch + taps - 1), (uint64_t)d.n_batch};
+        const uint64_t str[2] = {(uint64_t)d.a_row_stride * 2, (uint64_t)(d.n_batch > 1 ? d.a_batch_stride : d.a_row_stride * d.rows_per_batch) * 2};
+        const uint32_t box[3] = {kBK, kBM, 1};
+        int rc = make_tmap_bf16(&ta, d.A, 3, dims, str, box);
+        if (rc != WDR_OK) return rc;
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.N};
+        const uint64_t str[1] = {(uint64_t)d.ldw * 2};
+        const uint32_t box[2] = {kBK, BN};
+        int rc = make_tmap_bf16(&tb, d.W, 2, dims, str, box);
+        if (rc != WDR_OK) return rc;
+    }
+    GemmParams p;
+    p.rows_per_batch = d.rows_per_batch; p.n_batch = d.n_batch; p.N = d.N; p.K = d.K;
+    p.kb_per_tap = d.kb_per_tap > 0 ? d.kb_per_tap : (d.K + kBK - 1) / kBK;
+    p.tiles_per_batch = (d.rows_per_batch + kBM - 1) / kBM;
+    p.n_tiles = (d.N + BN - 1) / BN;
+    p.total_tiles = p.tiles_per_batch * d.n_batch * p.n_tiles;
+    p.out = d.out; p.ldc = d.ldc; p.bias = d.bias; p.resid = d.resid; p.pos = d.pos;
+    p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
+    switch (d.epilogue) {
+        case EPI_BIAS_BF16: return launch_gemm<BN, 6, EPI_BIAS_BF16>(ta, tb, p, st);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<BN, 6, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
+        case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<BN, 6, EPI_BIAS_RESID_F32>(ta, tb, p, st);
+        case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<BN, 6, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
+        case EPI_QKV_BF16: return launch_gemm<BN, 6, EPI_QKV_BF16>(ta, tb, p, st);
+        case EPI_F32: return launch_gemm<BN, 6, EPI_F32>(ta, tb, p, st);
+    }
+    set_error("unknown epilogue %d", d.epilogue);
+    return WDR_ERR_INVALID;
+}
+
+}  // namespace wdr

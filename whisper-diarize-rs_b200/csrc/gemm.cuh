@@ -1,0 +1,48 @@
+// gemm.cuh — host-side interface of the tcgen05 bf16 GEMM (gemm.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wdr {
+
+enum GemmEpilogue {
+    EPI_BIAS_BF16 = 0,          // out_bf16 = acc + bias
+    EPI_BIAS_GELU_BF16 = 1,     // out_bf16 = gelu(acc + bias)
+    EPI_BIAS_RESID_F32 = 2,     // out_f32 = resid + acc + bias            (resid may alias out)
+    EPI_BIAS_GELU_POS_F32 = 3,  // out_f32 = gelu(acc + bias) + pos[row_in_batch][n]
+    EPI_QKV_BF16 = 4,           // n < n_split: out_bf16[row][n] = acc + bias;  n >= n_split: out_t[n - n_split][row] = acc + bias
+    EPI_F32 = 5,                // out_f32 = acc + bias
+};
+
+// D[M x N] = A[M x K] * W[N x K]^T.  A rows are organised as n_batch groups of rows_per_batch rows (row r of
+// batch b lives at A + b*a_batch_stride + r*a_row_stride elements); tiles never straddle a batch, so strided
+// (overlapping) row views — the implicit-GEMM form of conv1d — are expressed by the strides alone.
+// Output row index = b*rows_per_batch + r.
+struct GemmDesc {
+    const __nv_bfloat16* A = nullptr;
+    int64_t a_row_stride = 0;    // elements; multiple of 8
+    int64_t a_batch_stride = 0;  // elements; multiple of 8
+    int rows_per_batch = 0;
+    int n_batch = 1;
+    const __nv_bfloat16* W = nullptr;  // [N][ldw] K-major
+    int64_t ldw = 0;
+    int N = 0, K = 0;
+    // Implicit-GEMM (conv1d) addressing: the K axis is cut into "taps" of kb_per_tap 64-element blocks; tap t reads
+    // columns [0, kb_per_tap*64) of A rows shifted by t (row r + t).  0 = plain GEMM (one tap spanning all of K).
+    int kb_per_tap = 0;
+    int a_cols = 0;  // inner extent of the A tensor (defaults to K); columns beyond it read as zero
+    int epilogue = EPI_BIAS_BF16;
+    void* out = nullptr;
+    int64_t ldc = 0;
+    const float* bias = nullptr;   // [N] or null
+    const float* resid = nullptr;  // fp32 [M][ldc]
+    const float* pos = nullptr;    // fp32 [rows_per_batch][N]
+    __nv_bfloat16* out_t = nullptr;
+    int64_t ldt = 0;
+    int n_split = 0;
+};
+
+int gemm_bf16(const GemmDesc& d, cudaStream_t st);
+
+}  // namespace wdr
