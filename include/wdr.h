@@ -120,6 +120,56 @@ int wdr_kaldi_fbank_batch_i16_dev(const int16_t* pcm, const int64_t* seg_offset,
 /* ---- get_signal_energy (whisper.cpp, used by the token-timestamp heuristic) --------- */
 int wdr_signal_energy(const float* pcm, int n, int half_window, float* out);
 
+/* ---- context / state (whisper_context, whisper_state) ------------------------------------------- */
+typedef struct wdr_context wdr_context;
+typedef struct wdr_state wdr_state;
+/* == whisper_alignment_heads_preset; the crate maps model names to these (src/transcribe.rs:117-129). */
+enum wdr_aheads_preset {
+    WDR_AHEADS_NONE = -1, WDR_AHEADS_TINY_EN = 0, WDR_AHEADS_TINY, WDR_AHEADS_BASE_EN, WDR_AHEADS_BASE, WDR_AHEADS_SMALL_EN,
+    WDR_AHEADS_SMALL, WDR_AHEADS_MEDIUM_EN, WDR_AHEADS_MEDIUM, WDR_AHEADS_LARGE_V3, WDR_AHEADS_LARGE_V3_TURBO
+};
+/* == whisper_context_params (WhisperContextParameters, src/transcribe.rs:102-136), plus the seeded-weights
+ * extension (no model file can exist here): arch_name selects the architecture, seed the weights. */
+typedef struct wdr_context_params {
+    int use_gpu;               /* false is refused: there is no CPU path */
+    int gpu_device;
+    int flash_attn;            /* accepted; the encoder attention is always the fused tcgen05 kernel */
+    int dtw_token_timestamps;
+    int dtw_aheads_preset;     /* enum wdr_aheads_preset */
+    size_t dtw_mem_size;       /* accepted (src/utils.rs:3-49); workspaces are sized from the batch instead */
+    const char* arch_name;     /* "tiny.en" ... "large-v3-turbo" */
+    uint64_t seed;
+} wdr_context_params;
+typedef struct wdr_model_dims {
+    int n_audio_state, n_audio_head, n_audio_layer, n_text_layer, n_mels, n_vocab, n_audio_ctx, n_text_ctx, is_multilingual;
+    int64_t weight_bytes;
+} wdr_model_dims;
+wdr_context_params wdr_context_default_params(void);                                         /* whisper_context_default_params */
+/* whisper_init_from_file_with_params (WhisperContext::new_with_params, src/transcribe.rs:154).  path == NULL:
+ * seeded weights of params.arch_name.  Returns NULL on failure, never aborts. */
+wdr_context* wdr_init_from_file_with_params(const char* path, wdr_context_params params);
+void wdr_free(wdr_context* ctx);                                                             /* whisper_free */
+int wdr_model_info(const wdr_context* ctx, wdr_model_dims* out);                             /* whisper_model_n_* getters */
+wdr_state* wdr_init_state(wdr_context* ctx);                 /* whisper_init_state (ctx.create_state(), src/transcribe.rs:335) */
+void wdr_free_state(wdr_state* state);                       /* whisper_free_state */
+/* librosa slaney filterbank [n_mel][201] that whisper.cpp reads from the model file. Host pointer. */
+int wdr_mel_filters(int n_mel, float* out);
+
+/* ---- encoder (whisper_encode / the encoder half of whisper_full_with_state, src/transcribe.rs:389) --- */
+/* whisper_encode semantics: normalised mel[n_mel][n_len] (host), window at frame mel_offset, zero-extended to
+ * 3000 frames -> hidden[1500][n_audio_state] fp32 (host). */
+int wdr_encode(wdr_context* ctx, wdr_state* state, const float* mel, int n_len, int mel_offset, float* out_hidden);
+/* Sharded mode: B independent 30 s windows of int16 PCM -> log-mel -> encoder -> hidden[B][1500][d].
+ * _dev: DEVICE pointers, asynchronous on stream.  Without suffix: HOST pointers, copies inside the call. */
+int wdr_encode_chunks_i16_dev(wdr_context* ctx, wdr_state* state, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid,
+                              int n_chunks, float* out_hidden, void* stream);
+int wdr_encode_chunks_i16(wdr_context* ctx, wdr_state* state, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid,
+                          int n_chunks, float* out_hidden);
+/* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] (V transposed over all tokens)
+ * -> out bf16 [B*T][d].  DEVICE pointers. */
+int wdr_encoder_attention_dev(const uint16_t* qk, const uint16_t* vt, int64_t ldt, int n_chunks, int T, int n_head, int d_model,
+                              uint16_t* out, void* stream);
+
 /* ---- stage-level kernels (not in whisper.h; for parity tests and roofline measurement) -------------- */
 /* tcgen05 bf16 GEMM: D[M][N] = A[M][K] * W[N][K]^T with a fused epilogue (the ggml mul_mat / ONNX Gemm of the
  * encoder, decoder and embedding nets).  bf16 values are passed as uint16_t.  A rows are n_batch groups of

@@ -32,6 +32,7 @@ def lib():
         _lib.oracle_kaldi_fbank.argtypes = [f32p, C.c_int, C.c_int, C.c_int, f32p]
         _lib.oracle_signal_energy.argtypes = [f32p, C.c_int, C.c_int, f32p]
         _lib.oracle_signal_energy.restype = None
+        _lib.oracle_whisper_encode.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, f32p]
     return _lib
 
 
@@ -113,4 +114,17 @@ def signal_energy(signal, hw=32):
     s, sp = _f32(signal)
     out = np.empty_like(s)
     lib().oracle_signal_energy(sp, len(s), hw, out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
+def whisper_encode(mel, arch, packed_weights):
+    """whisper.cpp encoder on one window: mel[n_mel, 3000] normalised -> hidden[1500, d]."""
+    from . import weights as W
+    a = W.ARCHS[arch]
+    m, mp = _f32(mel)
+    assert m.shape == (a["n_mel"], 3000)
+    pw, pp = _f32(packed_weights)
+    out = np.empty((1500, a["d"]), np.float32)
+    rc = lib().oracle_whisper_encode(mp, a["n_mel"], a["d"], a["n_head"], a["n_enc"], pp, out.ctypes.data_as(C.POINTER(C.c_float)))
+    assert rc == 0
     return out

@@ -361,3 +361,166 @@ void oracle_signal_energy(const float *signal, int n, int hw, float *out) {
         out[i] = sum / (2 * hw + 1);
     }
 }
+
+/* ==========================================================================================
+ * A.2 Whisper encoder (whisper.cpp whisper_encode_internal): conv1d(k3,s1,p1)+GELU ->
+ * conv1d(k3,s2,p1)+GELU -> + sinusoidal positions -> n_layer x {LN, MHA (key has no bias),
+ * +res, LN, MLP(4x, GELU), +res} -> ln_post.  fp32 throughout; GELU = ggml's tanh form
+ * (the f16 lookup table ggml uses on CPU is not reproduced; the 1e-2 tolerance absorbs it).
+ * Weights arrive as one flat fp32 array in the order documented in oracle/weights.py.
+ * ========================================================================================== */
+static inline float gelu_tanh_f(float x) {
+    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
+}
+
+/* C[M][N] (ldc) = A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] (bias may be NULL); accumulate==1 adds into C. */
+static void gemm_nt(const float *A, int lda, const float *W, int ldw, const float *bias, float *C, int ldc,
+                    int M, int N, int K, int accumulate) {
+#pragma omp parallel for schedule(static)
+    for (int i0 = 0; i0 < M; i0 += 4) {
+        const int im = (M - i0) < 4 ? (M - i0) : 4;
+        for (int j = 0; j < N; j++) {
+            const float *w = W + (size_t)j * ldw;
+            float acc[4] = {0, 0, 0, 0};
+            for (int ii = 0; ii < im; ii++) {
+                const float *a = A + (size_t)(i0 + ii) * lda;
+                float s = 0.0f;
+#pragma omp simd reduction(+ : s)
+                for (int k = 0; k < K; k++) s += a[k] * w[k];
+                acc[ii] = s;
+            }
+            for (int ii = 0; ii < im; ii++) {
+                float v = acc[ii] + (bias ? bias[j] : 0.0f);
+                float *c = C + (size_t)(i0 + ii) * ldc + j;
+                *c = accumulate ? *c + v : v;
+            }
+        }
+    }
+}
+
+static void layer_norm_rows(const float *x, const float *g, const float *b, float *y, int rows, int d) {
+#pragma omp parallel for schedule(static)
+    for (int r = 0; r < rows; r++) {
+        const float *xr = x + (size_t)r * d;
+        float *yr = y + (size_t)r * d;
+        double s = 0.0;
+        for (int i = 0; i < d; i++) s += xr[i];
+        const float mean = (float)(s / d);
+        double q = 0.0;
+        for (int i = 0; i < d; i++) { const float v = xr[i] - mean; q += (double)v * v; }
+        const float rstd = 1.0f / sqrtf((float)(q / d) + 1e-5f);
+        for (int i = 0; i < d; i++) yr[i] = (xr[i] - mean) * rstd * g[i] + b[i];
+    }
+}
+
+/* softmax(Q K^T * scale) V for one head; q,k,v,o are [T][ld] slices. */
+static void attention_head(const float *q, const float *k, const float *v, float *o, int Tq, int Tk, int dh, int ld, int ldo,
+                           float scale, float *probs_out /* optional [Tq][Tk] */) {
+#pragma omp parallel
+    {
+        float *s = (float *)malloc(sizeof(float) * (size_t)Tk);
+#pragma omp for schedule(static)
+        for (int i = 0; i < Tq; i++) {
+            const float *qi = q + (size_t)i * ld;
+            float mx = -INFINITY;
+            for (int j = 0; j < Tk; j++) {
+                const float *kj = k + (size_t)j * ld;
+                float d = 0.0f;
+#pragma omp simd reduction(+ : d)
+                for (int c = 0; c < dh; c++) d += qi[c] * kj[c];
+                s[j] = d * scale;
+                if (s[j] > mx) mx = s[j];
+            }
+            float sum = 0.0f;
+            for (int j = 0; j < Tk; j++) { s[j] = expf(s[j] - mx); sum += s[j]; }
+            const float inv = 1.0f / sum;
+            float *oi = o + (size_t)i * ldo;
+            for (int c = 0; c < dh; c++) oi[c] = 0.0f;
+            for (int j = 0; j < Tk; j++) {
+                const float p = s[j] * inv;
+                if (probs_out) probs_out[(size_t)i * Tk + j] = p;
+                const float *vj = v + (size_t)j * ld;
+#pragma omp simd
+                for (int c = 0; c < dh; c++) oi[c] += p * vj[c];
+            }
+        }
+        free(s);
+    }
+}
+
+/* mel: [n_mel][3000] normalised.  wts: flat weights (oracle/weights.py: pack_encoder).  out: [1500][d]. */
+int oracle_whisper_encode(const float *mel, int n_mel, int d, int n_head, int n_layer, const float *wts, float *out) {
+    const int T0 = 3000, T = 1500, dh = d / n_head;
+    const float *p = wts;
+    const float *c1w = p; p += (size_t)d * n_mel * 3;
+    const float *c1b = p; p += d;
+    const float *c2w = p; p += (size_t)d * d * 3;
+    const float *c2b = p; p += d;
+    const float *pos = p; p += (size_t)T * d;
+    float *a1 = (float *)calloc((size_t)T0 * d, sizeof(float));
+    float *x = (float *)calloc((size_t)T * d, sizeof(float));
+    float *h = (float *)malloc(sizeof(float) * (size_t)T * d);
+    float *qkv = (float *)malloc(sizeof(float) * (size_t)T * 3 * d);
+    float *att = (float *)malloc(sizeof(float) * (size_t)T * d);
+    float *ff = (float *)malloc(sizeof(float) * (size_t)T * 4 * d);
+    /* conv1: out[t][o] = gelu(b[o] + sum_c sum_k w[o][c][k] * mel[c][t + k - 1]) */
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < T0; t++)
+        for (int o = 0; o < d; o++) {
+            float s = c1b[o];
+            for (int c = 0; c < n_mel; c++)
+                for (int k = 0; k < 3; k++) {
+                    const int tt = t + k - 1;
+                    if (tt >= 0 && tt < T0) s += c1w[((size_t)o * n_mel + c) * 3 + k] * mel[(size_t)c * T0 + tt];
+                }
+            a1[(size_t)t * d + o] = gelu_tanh_f(s);
+        }
+    /* conv2 (stride 2): out[j][o] = gelu(b[o] + sum_c sum_k w[o][c][k] * a1[2j + k - 1][c]) + pos[j][o] */
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < T; j++)
+        for (int o = 0; o < d; o++) {
+            float s = c2b[o];
+            for (int k = 0; k < 3; k++) {
+                const int tt = 2 * j + k - 1;
+                if (tt < 0 || tt >= T0) continue;
+                const float *ar = a1 + (size_t)tt * d;
+                const float *wr = c2w + (size_t)o * d * 3 + k;
+                float acc = 0.0f;
+                for (int c = 0; c < d; c++) acc += wr[(size_t)c * 3] * ar[c];
+                s += acc;
+            }
+            x[(size_t)j * d + o] = gelu_tanh_f(s) + pos[(size_t)j * d + o];
+        }
+    const float scale = 1.0f / sqrtf((float)dh);
+    for (int l = 0; l < n_layer; l++) {
+        const float *ln1g = p; p += d;
+        const float *ln1b = p; p += d;
+        const float *qw = p; p += (size_t)d * d;
+        const float *qb = p; p += d;
+        const float *kw = p; p += (size_t)d * d;
+        const float *vw = p; p += (size_t)d * d;
+        const float *vb = p; p += d;
+        const float *ow = p; p += (size_t)d * d;
+        const float *ob = p; p += d;
+        const float *ln2g = p; p += d;
+        const float *ln2b = p; p += d;
+        const float *f1w = p; p += (size_t)4 * d * d;
+        const float *f1b = p; p += 4 * d;
+        const float *f2w = p; p += (size_t)4 * d * d;
+        const float *f2b = p; p += d;
+        layer_norm_rows(x, ln1g, ln1b, h, T, d);
+        gemm_nt(h, d, qw, d, qb, qkv, 3 * d, T, d, d, 0);
+        gemm_nt(h, d, kw, d, NULL, qkv + d, 3 * d, T, d, d, 0);
+        gemm_nt(h, d, vw, d, vb, qkv + 2 * d, 3 * d, T, d, d, 0);
+        for (int hh = 0; hh < n_head; hh++)
+            attention_head(qkv + hh * dh, qkv + d + hh * dh, qkv + 2 * d + hh * dh, att + hh * dh, T, T, dh, 3 * d, d, scale, NULL);
+        gemm_nt(att, d, ow, d, ob, x, d, T, d, d, 1);
+        layer_norm_rows(x, ln2g, ln2b, h, T, d);
+        gemm_nt(h, d, f1w, d, f1b, ff, 4 * d, T, 4 * d, d, 0);
+        for (size_t i = 0; i < (size_t)T * 4 * d; i++) ff[i] = gelu_tanh_f(ff[i]);
+        gemm_nt(ff, 4 * d, f2w, 4 * d, f2b, x, d, T, d, 4 * d, 1);
+    }
+    layer_norm_rows(x, p, p + d, out, T, d);
+    free(a1); free(x); free(h); free(qkv); free(att); free(ff);
+    return 0;
+}

@@ -13,4 +13,5 @@ from .capi import (  # noqa: F401
     WdrError, load, lib_path, build, version, device_count, launch_count,
     MelFrontend, log_mel, median_filter, dtw_cost, dtw, dtw_batch_dev, kaldi_fbank, fbank_frames,
     signal_energy, convert_integer_to_float_audio, mel_n_len, gemm_bf16_dev,
+    Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
 )

@@ -16,6 +16,17 @@ WDR_ERR_NO_DEVICE = -2
 WDR_ERR_TOO_SHORT = -6
 
 
+class ContextParams(C.Structure):
+    """== wdr_context_params (whisper_context_params + arch_name/seed)."""
+    _fields_ = [("use_gpu", C.c_int), ("gpu_device", C.c_int), ("flash_attn", C.c_int), ("dtw_token_timestamps", C.c_int),
+                ("dtw_aheads_preset", C.c_int), ("dtw_mem_size", C.c_size_t), ("arch_name", C.c_char_p), ("seed", C.c_uint64)]
+
+
+class ModelDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_audio_state", "n_audio_head", "n_audio_layer", "n_text_layer", "n_mels", "n_vocab",
+                                       "n_audio_ctx", "n_text_ctx", "is_multilingual")] + [("weight_bytes", C.c_int64)]
+
+
 class WdrError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"wdr error {code}: {msg}")
@@ -65,6 +76,19 @@ def load():
     L.wdr_gemm_bf16_dev.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_int, C.c_void_p]
+    L.wdr_context_default_params.restype = ContextParams
+    L.wdr_init_from_file_with_params.restype = C.c_void_p
+    L.wdr_init_from_file_with_params.argtypes = [C.c_char_p, ContextParams]
+    L.wdr_free.argtypes = [C.c_void_p]
+    L.wdr_model_info.argtypes = [C.c_void_p, C.POINTER(ModelDims)]
+    L.wdr_init_state.restype = C.c_void_p
+    L.wdr_init_state.argtypes = [C.c_void_p]
+    L.wdr_free_state.argtypes = [C.c_void_p]
+    L.wdr_mel_filters.argtypes = [C.c_int, f32p]
+    L.wdr_encode.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, C.c_int, f32p]
+    L.wdr_encode_chunks_i16_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.wdr_encode_chunks_i16.argtypes = [C.c_void_p, C.c_void_p, i16p, C.c_int64, i32p, C.c_int, f32p]
+    L.wdr_encoder_attention_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -227,3 +251,89 @@ def gemm_bf16_dev(A_ptr, lda, rows_per_batch, n_batch, a_batch_stride, W_ptr, ld
     """tcgen05 GEMM on device pointers (ints); see wdr_gemm_bf16_dev in include/wdr.h."""
     _check(load().wdr_gemm_bf16_dev(A_ptr, lda, rows_per_batch, n_batch, a_batch_stride, W_ptr, ldw, N, K, kb_per_tap, a_cols,
                                     bias_ptr, epilogue, out_ptr, ldc, extra_ptr, out_t_ptr, ldt, n_split, stream))
+
+
+def mel_filters(n_mel):
+    out = np.empty((n_mel, 201), np.float32)
+    _check(load().wdr_mel_filters(n_mel, _p(out, f32p)))
+    return out
+
+
+DTW_PRESETS = {"tiny.en": 0, "tiny": 1, "base.en": 2, "base": 3, "small.en": 4, "small": 5, "medium.en": 6, "medium": 7,
+               "large-v3": 8, "large-v3-turbo": 9}
+
+
+class Context:
+    """wdr_context: WhisperContext::new_with_params (reference src/transcribe.rs:89-166)."""
+
+    def __init__(self, arch_name, seed=1234, gpu_device=0, enable_dtw=False, flash_attn=False, dtw_mem_size=0):
+        L = load()
+        p = L.wdr_context_default_params()
+        p.gpu_device = gpu_device
+        p.arch_name = arch_name.encode()
+        p.seed = seed
+        if enable_dtw:  # create_context: DTW on => flash attention off, preset by model name, unknown names -> small
+            p.flash_attn = 0
+            p.dtw_token_timestamps = 1
+            p.dtw_aheads_preset = DTW_PRESETS.get(arch_name, DTW_PRESETS["small"])
+            p.dtw_mem_size = dtw_mem_size
+        else:
+            p.flash_attn = int(flash_attn)
+        self._h = L.wdr_init_from_file_with_params(None, p)
+        if not self._h:
+            raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, L.wdr_last_error().decode())
+        self.arch_name = arch_name
+        md = ModelDims()
+        _check(L.wdr_model_info(self._h, C.byref(md)))
+        self.dims = md
+
+    def close(self):
+        if self._h:
+            load().wdr_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def create_state(self):
+        return State(self)
+
+
+class State:
+    """wdr_state: ctx.create_state() (reference src/transcribe.rs:335)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self._h = load().wdr_init_state(ctx._h)
+        if not self._h:
+            raise WdrError(-3, load().wdr_last_error().decode())
+
+    def close(self):
+        if self._h:
+            load().wdr_free_state(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def encode(self, mel, mel_offset=0):
+        """whisper_encode: normalised mel[n_mel, n_len] -> hidden[1500, d]."""
+        m = _np(mel, np.float32)
+        out = np.empty((1500, self.ctx.dims.n_audio_state), np.float32)
+        _check(load().wdr_encode(self.ctx._h, self._h, _p(m, f32p), m.shape[1], mel_offset, _p(out, f32p)))
+        return out
+
+    def encode_chunks(self, pcm_i16, n_valid=None):
+        """pcm_i16[B, 480000] (host) -> hidden[B, 1500, d]; H2D/D2H inside the call."""
+        x = _np(pcm_i16, np.int16)
+        assert x.ndim == 2 and x.shape[1] == 480000
+        out = np.empty((x.shape[0], 1500, self.ctx.dims.n_audio_state), np.float32)
+        nv = None if n_valid is None else _np(n_valid, np.int32)
+        _check(load().wdr_encode_chunks_i16(self.ctx._h, self._h, _p(x, i16p), x.shape[1], None if nv is None else _p(nv, i32p),
+                                            x.shape[0], _p(out, f32p)))
+        return out
+
+    def encode_chunks_dev(self, pcm_ptr, chunk_stride, n_chunks, out_ptr, n_valid_ptr=None, stream=0):
+        _check(load().wdr_encode_chunks_i16_dev(self.ctx._h, self._h, pcm_ptr, chunk_stride, n_valid_ptr, n_chunks, out_ptr, stream))
+
+
+def encoder_attention_dev(qk_ptr, vt_ptr, ldt, n_chunks, T, n_head, d_model, out_ptr, stream=0):
+    _check(load().wdr_encoder_attention_dev(qk_ptr, vt_ptr, ldt, n_chunks, T, n_head, d_model, out_ptr, stream))

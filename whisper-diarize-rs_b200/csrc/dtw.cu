@@ -283,6 +283,9 @@ int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int
         int dev = 0, v = 0;
         WDR_CUDA_TRY(cudaGetDevice(&dev));
         WDR_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        cudaFuncAttributes fa;
+        WDR_CUDA_TRY(cudaFuncGetAttributes(&fa, dtw_wavefront_kernel));
+        v -= (int)fa.sharedSizeBytes;  // the opt-in limit covers static + dynamic shared memory
         WDR_CUDA_TRY(cudaFuncSetAttribute(dtw_wavefront_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, v));
         g_dtw_smem_max = v;
     }

@@ -33,6 +33,7 @@ struct GemmParams {
     int tiles_per_batch, n_tiles, total_tiles;
     void* out;
     int64_t ldc;
+    int64_t c_batch_stride;
     const float* bias;
     const float* resid;
     const float* pos;
@@ -156,7 +157,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
             const int r_in_batch = mt * kBM + q * 32 + lane;
             const bool row_ok = r_in_batch < p.rows_per_batch;
-            const int64_t grow = (int64_t)batch * p.rows_per_batch + r_in_batch;
+            const int64_t grow = (int64_t)batch * p.rows_per_batch + r_in_batch;       // logical output row
+            const int64_t c_off = (int64_t)batch * p.c_batch_stride + (int64_t)r_in_batch * p.ldc;  // its element offset
             mbar_wait(&bar_tfull[as], aph);
             tc_fence_after();
 #pragma unroll 1
@@ -184,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 }
                 if (!row_ok) continue;
                 if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || (EPI == EPI_QKV_BF16 && n0 < p.n_split)) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + grow * p.ldc + n0;
+                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + c_off + n0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         if (n0 + j < p.N) {
@@ -203,8 +205,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     for (int j = 0; j < 32; j++)
                         if (n0 + j < p.N) o[(int64_t)j * p.ldt] = __float2bfloat16_rn(v[j]);
                 } else {
-                    float* o = reinterpret_cast<float*>(p.out) + grow * p.ldc + n0;
-                    const float* rs = (EPI == EPI_BIAS_RESID_F32) ? p.resid + grow * p.ldc + n0
+                    float* o = reinterpret_cast<float*>(p.out) + c_off + n0;
+                    const float* rs = (EPI == EPI_BIAS_RESID_F32) ? p.resid + c_off + n0
                                       : (EPI == EPI_BIAS_GELU_POS_F32) ? p.pos + (int64_t)r_in_batch * p.N + n0 : nullptr;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -333,7 +335,8 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.tiles_per_batch = (d.rows_per_batch + kBM - 1) / kBM;
     p.n_tiles = (d.N + BN - 1) / BN;
     p.total_tiles = p.tiles_per_batch * d.n_batch * p.n_tiles;
-    p.out = d.out; p.ldc = d.ldc; p.bias = d.bias; p.resid = d.resid; p.pos = d.pos;
+    p.out = d.out; p.ldc = d.ldc; p.bias = d.bias;
+    p.c_batch_stride = d.c_batch_stride > 0 ? d.c_batch_stride : (int64_t)d.rows_per_batch * d.ldc; p.resid = d.resid; p.pos = d.pos;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     switch (d.epilogue) {
         case EPI_BIAS_BF16: return launch_gemm<BN, 6, EPI_BIAS_BF16>(ta, tb, p, st);

@@ -35,6 +35,7 @@ struct GemmDesc {
     int epilogue = EPI_BIAS_BF16;
     void* out = nullptr;
     int64_t ldc = 0;
+    int64_t c_batch_stride = 0;  // elements between batches of the output (and resid); 0 = rows_per_batch * ldc
     const float* bias = nullptr;   // [N] or null
     const float* resid = nullptr;  // fp32 [M][ldc]
     const float* pos = nullptr;    // fp32 [rows_per_batch][N]
