@@ -30,7 +30,7 @@ const WhisperArch* find_arch(const char* name) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// counter-based weight synthesis (bit-identical in oracle/weights.py)
+// counter-based weight synthesis (the CPU checker in the test tree restates it bit for bit)
 // ---------------------------------------------------------------------------------------------------
 __host__ __device__ inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ULL;
@@ -60,10 +60,10 @@ __global__ void synth_kernel(T* __restrict__ dst, int rows, int cols, int64_t ld
         const int r = (int)(e / cols), c = (int)(e % cols);
         float v;
         if (mode == 0) {
-            v = offset + synth_unit(key, (uint64_t)e) * scale;
+            v = __fadd_rn(offset, __fmul_rn(synth_unit(key, (uint64_t)e), scale));  // no FMA contraction: matches the checker
         } else {
             const int t = c / cpad, ci = c % cpad;
-            v = (ci < cin) ? offset + synth_unit(key, ((uint64_t)r * cin + ci) * 3 + t) * scale : 0.0f;
+            v = (ci < cin) ? __fadd_rn(offset, __fmul_rn(synth_unit(key, ((uint64_t)r * cin + ci) * 3 + t), scale)) : 0.0f;
         }
         if (sizeof(T) == 2) {
             // matrices are bf16 "checkpoints": round-to-nearest-even once
