@@ -165,8 +165,8 @@ int wdr_encode_chunks_i16_dev(wdr_context* ctx, wdr_state* state, const int16_t*
                               int n_chunks, float* out_hidden, void* stream);
 int wdr_encode_chunks_i16(wdr_context* ctx, wdr_state* state, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid,
                           int n_chunks, float* out_hidden);
-/* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] (V transposed over all tokens)
- * -> out bf16 [B*T][d].  DEVICE pointers. */
+/* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] = V transposed, window b's tokens at
+ * columns b*round_up(T,8) + t (pad columns zero) -> out bf16 [B*T][d].  DEVICE pointers. */
 int wdr_encoder_attention_dev(const uint16_t* qk, const uint16_t* vt, int64_t ldt, int n_chunks, int T, int n_head, int d_model,
                               uint16_t* out, void* stream);
 
@@ -177,11 +177,12 @@ int wdr_encoder_attention_dev(const uint16_t* qk, const uint16_t* vt, int64_t ld
  * implicit-GEMM (conv1d) addressing: K is cut into taps of kb_per_tap*64 columns, tap t reads A rows r + t.
  * epilogue: 0 bias->bf16, 1 bias+GELU->bf16, 2 resid+bias->f32 (resid_or_pos = resid[M][ldc]),
  * 3 GELU(bias)+pos->f32 (resid_or_pos = pos[rows_per_batch][N]), 4 QKV (columns >= n_split stored transposed
- * into out_t[n - n_split][row], row stride ldt), 5 bias->f32.  DEVICE pointers, asynchronous on stream. */
+ * into out_t[n - n_split][batch * t_batch_stride + row_in_batch], row stride ldt; t_batch_stride 0 = rows_per_batch),
+ * 5 bias->f32.  DEVICE pointers, asynchronous on stream. */
 int wdr_gemm_bf16_dev(const uint16_t* A, int64_t lda, int rows_per_batch, int n_batch, int64_t a_batch_stride,
                       const uint16_t* W, int64_t ldw, int N, int K, int kb_per_tap, int a_cols, const float* bias,
                       int epilogue, void* out, int64_t ldc, const float* resid_or_pos, uint16_t* out_t, int64_t ldt,
-                      int n_split, void* stream);
+                      int n_split, int64_t t_batch_stride, void* stream);
 
 #ifdef __cplusplus
 }

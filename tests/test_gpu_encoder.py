@@ -13,22 +13,23 @@ pytestmark = pytest.mark.gpu
 ENC_RTOL = 1e-2
 
 
-@pytest.mark.parametrize("B,T,H", [(1, 128, 1), (2, 300, 2), (3, 1500, 6), (1, 1500, 20)])
+@pytest.mark.parametrize("B,T,H", [(1, 128, 1), (2, 300, 2), (3, 301, 1), (3, 1500, 6), (1, 1500, 20)])
 def test_encoder_attention_kernel(wdr, B, T, H):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T + H)
     d = 64 * H
     M = B * T
-    ldt = (M + 7) // 8 * 8
+    T_pad = (T + 7) // 8 * 8
+    ldt = B * T_pad
     qkv = torch.randn(M, 3 * d, device="cuda", generator=g) * 1.5
     qk = qkv[:, : 2 * d].contiguous().bfloat16()
-    vt = torch.zeros(d, ldt, device="cuda", dtype=torch.bfloat16)
-    vt[:, :M] = qkv[:, 2 * d:].T.bfloat16()
+    vt = torch.zeros(d, B, T_pad, device="cuda", dtype=torch.bfloat16)
+    vt[:, :, :T] = qkv[:, 2 * d:].bfloat16().view(B, T, d).permute(2, 0, 1)
     out = torch.full((M, d), float("nan"), device="cuda", dtype=torch.bfloat16)
     wdr.encoder_attention_dev(qk.data_ptr(), vt.data_ptr(), ldt, B, T, H, d, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     q = qk[:, :d].float().view(B, T, H, 64).transpose(1, 2)
     k = qk[:, d:].float().view(B, T, H, 64).transpose(1, 2)
-    v = vt[:, :M].float().T.reshape(B, T, H, 64).transpose(1, 2)
+    v = vt[:, :, :T].float().permute(1, 2, 0).reshape(B, T, H, 64).transpose(1, 2)
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(M, d)
     assert torch.isfinite(out.float()).all()
     err = (out.float() - ref).abs().max().item()

@@ -23,7 +23,7 @@ def run(wdr, A, W, epilogue=0, bias=None, extra=None, rows_per_batch=None, n_bat
     out_t = torch.full((max(N - n_split, 1), M), float("nan"), dtype=torch.bfloat16, device="cuda") if epilogue == 4 else None
     wdr.gemm_bf16_dev(A.data_ptr(), lda or A.stride(-2), rows_per_batch, n_batch, a_batch_stride, W.data_ptr(), W.stride(0), N, K,
                       out.data_ptr(), N, epilogue, None if bias is None else bias.data_ptr(), None if extra is None else extra.data_ptr(),
-                      None if out_t is None else out_t.data_ptr(), M, n_split, kb_per_tap, a_cols, torch.cuda.current_stream().cuda_stream)
+                      None if out_t is None else out_t.data_ptr(), M, n_split, kb_per_tap, a_cols, 0, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
     return out, out_t
 

@@ -75,7 +75,7 @@ def load():
     L.wdr_signal_energy.argtypes = [f32p, C.c_int, C.c_int, f32p]
     L.wdr_gemm_bf16_dev.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
-                                    C.c_int, C.c_void_p]
+                                    C.c_int, C.c_int64, C.c_void_p]
     L.wdr_context_default_params.restype = ContextParams
     L.wdr_init_from_file_with_params.restype = C.c_void_p
     L.wdr_init_from_file_with_params.argtypes = [C.c_char_p, ContextParams]
@@ -247,10 +247,10 @@ def signal_energy(pcm_f32, hw=32):
 
 
 def gemm_bf16_dev(A_ptr, lda, rows_per_batch, n_batch, a_batch_stride, W_ptr, ldw, N, K, out_ptr, ldc, epilogue=0, bias_ptr=None,
-                  extra_ptr=None, out_t_ptr=None, ldt=0, n_split=0, kb_per_tap=0, a_cols=0, stream=0):
+                  extra_ptr=None, out_t_ptr=None, ldt=0, n_split=0, kb_per_tap=0, a_cols=0, t_batch_stride=0, stream=0):
     """tcgen05 GEMM on device pointers (ints); see wdr_gemm_bf16_dev in include/wdr.h."""
     _check(load().wdr_gemm_bf16_dev(A_ptr, lda, rows_per_batch, n_batch, a_batch_stride, W_ptr, ldw, N, K, kb_per_tap, a_cols,
-                                    bias_ptr, epilogue, out_ptr, ldc, extra_ptr, out_t_ptr, ldt, n_split, stream))
+                                    bias_ptr, epilogue, out_ptr, ldc, extra_ptr, out_t_ptr, ldt, n_split, t_batch_stride, stream))
 
 
 def mel_filters(n_mel):

@@ -32,6 +32,7 @@ constexpr uint32_t kAttTmemCols = 256;
 
 struct AttParams {
     int T;          // tokens per chunk (1500)
+    int T_pad;      // per-chunk column stride of V^T (multiple of 8: TMA box starts must be 16-byte aligned)
     int n_kt;       // key tiles per chunk
     int d_model;
     __nv_bfloat16* out;  // [B*T][d_model]
@@ -86,7 +87,7 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tma_qk, const __gri
                 tma_load_3d(sK + s * kKBytes, &tma_qk, &bar_kfull[s], p.d_model + h * kAttD, j * kAttK, b);
                 mbar_wait(&bar_vempty, (j & 1) ^ 1);
                 mbar_arrive_expect_tx(&bar_vfull, kVBytes);
-                const int tok0 = b * p.T + j * kAttK;
+                const int tok0 = b * p.T_pad + j * kAttK;
                 tma_load_2d(sV, &tma_vt, &bar_vfull, tok0, h * kAttD);
                 tma_load_2d(sV + kVBytes / 2, &tma_vt, &bar_vfull, tok0 + 64, h * kAttD);
             }
@@ -235,11 +236,13 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tma_qk, const __gri
     }
 }
 
-// qk: bf16 [B*T][2*d_model] (q | k), vt: bf16 [d_model][ldt] (V^T over all tokens), out: bf16 [B*T][d_model]
+// qk: bf16 [B*T][2*d_model] (q | k); vt: bf16 [d_model][ldt], chunk b's tokens at columns b*T_pad .. b*T_pad+T-1 with
+// T_pad = round_up(T, 8) (pad columns zero); out: bf16 [B*T][d_model]
 int encoder_attention(const __nv_bfloat16* qk, const __nv_bfloat16* vt, int64_t ldt, int B, int T, int n_head, int d_model,
                       __nv_bfloat16* out, cudaStream_t st) {
     WDR_REQUIRE(d_model == n_head * kAttD, "d_head must be 64");
-    WDR_REQUIRE(ldt % 8 == 0 && ldt >= (int64_t)B * T, "ldt must be a multiple of 8 covering all tokens");
+    const int T_pad = (T + 7) / 8 * 8;
+    WDR_REQUIRE(ldt % 8 == 0 && ldt >= (int64_t)B * T_pad, "ldt must be a multiple of 8 covering B * round_up(T, 8) columns");
     CUtensorMap tqk, tvt;
     {
         const uint64_t dims[3] = {(uint64_t)2 * d_model, (uint64_t)T, (uint64_t)B};
@@ -249,7 +252,7 @@ int encoder_attention(const __nv_bfloat16* qk, const __nv_bfloat16* vt, int64_t 
         if (rc != WDR_OK) return rc;
     }
     {
-        const uint64_t dims[2] = {(uint64_t)B * T, (uint64_t)d_model};
+        const uint64_t dims[2] = {(uint64_t)B * T_pad, (uint64_t)d_model};
         const uint64_t str[1] = {(uint64_t)ldt * 2};
         const uint32_t box[2] = {64, kAttD};
         int rc = make_tmap_bf16(&tvt, vt, 2, dims, str, box);
@@ -262,6 +265,7 @@ int encoder_attention(const __nv_bfloat16* qk, const __nv_bfloat16* vt, int64_t 
     }
     AttParams p;
     p.T = T;
+    p.T_pad = T_pad;
     p.n_kt = (T + kAttK - 1) / kAttK;
     p.d_model = d_model;
     p.out = out;

@@ -22,6 +22,8 @@
 
 namespace wdr {
 
+constexpr int kTPad = (WDR_AUDIO_CTX + 7) / 8 * 8;  // 1504: V^T column stride per window
+
 int encoder_attention(const __nv_bfloat16* qk, const __nv_bfloat16* vt, int64_t ldt, int B, int T, int n_head, int d_model,
                       __nv_bfloat16* out, cudaStream_t st);
 template <typename In>
@@ -132,7 +134,7 @@ int EncoderWorkspace::reserve(const WhisperArch& a, int B) {
     release();
     const int64_t M = (int64_t)B * WDR_AUDIO_CTX;
     const int d = a.d;
-    ldt = (M + 7) / 8 * 8;
+    ldt = (int64_t)B * kTPad;
     WDR_CUDA_TRY(cudaMalloc(&mel_raw, sizeof(float) * (size_t)B * a.n_mel * WDR_CHUNK_FRAMES));
     WDR_CUDA_TRY(cudaMalloc(&chunk_max, sizeof(float) * B));
     WDR_CUDA_TRY(cudaMalloc(&frames, sizeof(__nv_bfloat16) * (size_t)B * 3002 * kConv1CPad));
@@ -185,9 +187,11 @@ int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* m
         if ((rc = layernorm<__nv_bfloat16>(ws.x, e.ln1_g, e.ln1_b, M, d, ws.h, st)) != WDR_OK) return rc;
         {
             GemmDesc g;
-            g.A = ws.h; g.a_row_stride = d; g.rows_per_batch = (int)M; g.n_batch = 1;
+            // per-window batches so that V^T columns can be laid out at a 16-byte aligned per-window stride
+            g.A = ws.h; g.a_row_stride = d; g.a_batch_stride = (int64_t)T * d; g.rows_per_batch = T; g.n_batch = B;
             g.W = e.w_qkv; g.ldw = d; g.N = 3 * d; g.K = d;
-            g.epilogue = EPI_QKV_BF16; g.out = ws.qk; g.ldc = 2 * d; g.bias = e.b_qkv; g.out_t = ws.vt; g.ldt = ws.ldt; g.n_split = 2 * d;
+            g.epilogue = EPI_QKV_BF16; g.out = ws.qk; g.ldc = 2 * d; g.bias = e.b_qkv;
+            g.out_t = ws.vt; g.ldt = ws.ldt; g.t_batch_stride = kTPad; g.n_split = 2 * d;
             if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
         if ((rc = encoder_attention(ws.qk, ws.vt, ws.ldt, B, T, a.n_head, d, ws.att, st)) != WDR_OK) return rc;

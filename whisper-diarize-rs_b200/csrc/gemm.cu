@@ -39,6 +39,7 @@ struct GemmParams {
     const float* pos;
     __nv_bfloat16* out_t;
     int64_t ldt;
+    int64_t t_batch_stride;
     int n_split;
 };
 
@@ -157,7 +158,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
             const int r_in_batch = mt * kBM + q * 32 + lane;
             const bool row_ok = r_in_batch < p.rows_per_batch;
-            const int64_t grow = (int64_t)batch * p.rows_per_batch + r_in_batch;       // logical output row
             const int64_t c_off = (int64_t)batch * p.c_batch_stride + (int64_t)r_in_batch * p.ldc;  // its element offset
             mbar_wait(&bar_tfull[as], aph);
             tc_fence_after();
@@ -200,7 +200,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                 } else if (EPI == EPI_QKV_BF16) {
                     // transposed store: lanes hold consecutive rows -> 64 B coalesced per column
-                    __nv_bfloat16* o = p.out_t + (int64_t)(n0 - p.n_split) * p.ldt + grow;
+                    __nv_bfloat16* o = p.out_t + (int64_t)(n0 - p.n_split) * p.ldt + (int64_t)batch * p.t_batch_stride + r_in_batch;
 #pragma unroll
                     for (int j = 0; j < 32; j++)
                         if (n0 + j < p.N) o[(int64_t)j * p.ldt] = __float2bfloat16_rn(v[j]);
@@ -338,6 +338,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.out = d.out; p.ldc = d.ldc; p.bias = d.bias;
     p.c_batch_stride = d.c_batch_stride > 0 ? d.c_batch_stride : (int64_t)d.rows_per_batch * d.ldc; p.resid = d.resid; p.pos = d.pos;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
+    p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     switch (d.epilogue) {
         case EPI_BIAS_BF16: return launch_gemm<BN, 6, EPI_BIAS_BF16>(ta, tb, p, st);
         case EPI_BIAS_GELU_BF16: return launch_gemm<BN, 6, EPI_BIAS_GELU_BF16>(ta, tb, p, st);

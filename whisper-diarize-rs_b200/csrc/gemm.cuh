@@ -41,6 +41,7 @@ struct GemmDesc {
     const float* pos = nullptr;    // fp32 [rows_per_batch][N]
     __nv_bfloat16* out_t = nullptr;
     int64_t ldt = 0;
+    int64_t t_batch_stride = 0;  // column distance between batches in out_t; 0 = rows_per_batch
     int n_split = 0;
 };
 

@@ -8,7 +8,7 @@ using namespace wdr;
 extern "C" int wdr_gemm_bf16_dev(const uint16_t* A, int64_t lda, int rows_per_batch, int n_batch, int64_t a_batch_stride,
                                  const uint16_t* W, int64_t ldw, int N, int K, int kb_per_tap, int a_cols, const float* bias,
                                  int epilogue, void* out, int64_t ldc, const float* resid_or_pos, uint16_t* out_t, int64_t ldt,
-                                 int n_split, void* stream) {
+                                 int n_split, int64_t t_batch_stride, void* stream) {
     clear_error();
     int rc = ensure_device(-1);
     if (rc != WDR_OK) return rc;
@@ -33,5 +33,6 @@ extern "C" int wdr_gemm_bf16_dev(const uint16_t* A, int64_t lda, int rows_per_ba
     d.out_t = reinterpret_cast<__nv_bfloat16*>(out_t);
     d.ldt = ldt;
     d.n_split = n_split;
+    d.t_batch_stride = t_batch_stride;
     return gemm_bf16(d, (cudaStream_t)stream);
 }
