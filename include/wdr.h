@@ -164,7 +164,15 @@ int wdr_encode(wdr_context* ctx, wdr_state* state, const float* mel, int n_len, 
 int wdr_encode_chunks_i16_dev(wdr_context* ctx, wdr_state* state, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid,
                               int n_chunks, float* out_hidden, void* stream);
 int wdr_encode_chunks_i16(wdr_context* ctx, wdr_state* state, const int16_t* pcm, int64_t chunk_stride, const int32_t* n_valid,
-                          int n_chunks, float* out_hidden);
+                          int n_chunks, float* out_hidden /* may be NULL: the result stays in the state, as whisper_encode leaves it */);
+/* Per-window mean |hidden| of the encoder output held in the state (n <= windows of the last encode call): a
+ * 4-byte-per-window device->host read that proves the encode finished without moving the hidden states. */
+int wdr_state_hidden_digest(wdr_state* state, float* out, int n);
+/* Per-kernel-class CUDA-event timing on the launching stream.  Classes: 0 mel, 1 mel re-layout, 2 tcgen05 GEMM,
+ * 3 attention, 4 layernorm, 5 decoder, 6 dtw, 7 other.  collect() sums the finished records (caller has synchronised)
+ * into ms[] / launches[] (>= 8 entries each) and returns the number of classes. */
+int wdr_profile_enable(wdr_state* state, int enable);
+int wdr_profile_collect(wdr_state* state, double* ms, int32_t* launches, int n_classes);
 /* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] = V transposed, window b's tokens at
  * columns b*round_up(T,8) + t (pad columns zero) -> out bf16 [B*T][d].  DEVICE pointers. */
 int wdr_encoder_attention_dev(const uint16_t* qk, const uint16_t* vt, int64_t ldt, int n_chunks, int T, int n_head, int d_model,

@@ -88,6 +88,9 @@ def load():
     L.wdr_encode.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, C.c_int, f32p]
     L.wdr_encode_chunks_i16_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.wdr_encode_chunks_i16.argtypes = [C.c_void_p, C.c_void_p, i16p, C.c_int64, i32p, C.c_int, f32p]
+    L.wdr_state_hidden_digest.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.wdr_profile_enable.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_profile_collect.argtypes = [C.c_void_p, C.POINTER(C.c_double), i32p, C.c_int]
     L.wdr_encoder_attention_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = L
     return L
@@ -330,6 +333,25 @@ class State:
         _check(load().wdr_encode_chunks_i16(self.ctx._h, self._h, _p(x, i16p), x.shape[1], None if nv is None else _p(nv, i32p),
                                             x.shape[0], _p(out, f32p)))
         return out
+
+    def encode_chunks_resident(self, pcm_host_ptr, n_chunks, chunk_stride=480000):
+        """Host PCM pointer (int; pinned memory recommended) -> encoder output kept in the state on the device."""
+        _check(load().wdr_encode_chunks_i16(self.ctx._h, self._h, C.cast(pcm_host_ptr, i16p), chunk_stride, None, n_chunks, None))
+
+    def hidden_digest(self, n):
+        out = np.empty(n, np.float32)
+        _check(load().wdr_state_hidden_digest(self._h, _p(out, f32p), n))
+        return out
+
+    def profile_enable(self, on=True):
+        _check(load().wdr_profile_enable(self._h, int(on)))
+
+    def profile_collect(self):
+        ms = (C.c_double * 8)()
+        ln = (C.c_int32 * 8)()
+        _check(load().wdr_profile_collect(self._h, ms, ln, 8))
+        names = ["mel", "mel_aux", "gemm", "attention", "layernorm", "decoder", "dtw", "other"]
+        return {n: {"ms": ms[i], "records": ln[i]} for i, n in enumerate(names)}
 
     def encode_chunks_dev(self, pcm_ptr, chunk_stride, n_chunks, out_ptr, n_valid_ptr=None, stream=0):
         _check(load().wdr_encode_chunks_i16_dev(self.ctx._h, self._h, pcm_ptr, chunk_stride, n_valid_ptr, n_chunks, out_ptr, stream))

@@ -19,6 +19,7 @@
 #include "encoder.cuh"
 #include "gemm.cuh"
 #include "model.cuh"
+#include "profile.cuh"
 
 namespace wdr {
 
@@ -155,13 +156,15 @@ int EncoderWorkspace::reserve(const WhisperArch& a, int B) {
 
 // mel (raw or already normalised) -> hidden states.  mel: [B][n_mel][n_frames] device.
 int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* mel, int n_frames, int mel_offset,
-                    const float* chunk_max, int normalized_input, int B, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st) {
+                    const float* chunk_max, int normalized_input, int B, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st,
+                    Profiler* prof) {
     const WhisperArch& a = ctx->arch;
     const WhisperWeights& w = ctx->w;
     const int d = a.d, T = WDR_AUDIO_CTX;
     const int64_t M = (int64_t)B * T;
     int rc;
     {
+        ProfScope ps(prof, KC_MEL_AUX, st);
         dim3 grid((WDR_CHUNK_FRAMES + 31) / 32, kConv1CPad / 32, B);
         mel_to_frames_kernel<<<grid, dim3(32, 8), 0, st>>>(mel, a.n_mel, n_frames, mel_offset, chunk_max, normalized_input, ws.frames);
         WDR_LAUNCH_CHECK();
@@ -172,6 +175,7 @@ int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* m
         g.rows_per_batch = WDR_CHUNK_FRAMES; g.n_batch = B;
         g.W = w.conv1_w; g.ldw = 3 * kConv1CPad; g.N = d; g.K = 3 * kConv1CPad; g.kb_per_tap = kConv1CPad / 64; g.a_cols = kConv1CPad;
         g.epilogue = EPI_BIAS_GELU_BF16; g.out = ws.conv1 + d; g.ldc = d; g.c_batch_stride = (int64_t)3002 * d; g.bias = w.conv1_b;
+        ProfScope ps(prof, KC_GEMM, st);
         if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
     }
     {   // conv2: k=3, stride 2, pad 1 over row pairs: output j reads pair rows j (taps 0,1) and j+1 (tap 2)
@@ -180,11 +184,15 @@ int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* m
         g.rows_per_batch = T; g.n_batch = B;
         g.W = w.conv2_w; g.ldw = 3 * d; g.N = d; g.K = 3 * d; g.kb_per_tap = 2 * d / 64; g.a_cols = 2 * d;
         g.epilogue = EPI_BIAS_GELU_POS_F32; g.out = ws.x; g.ldc = d; g.bias = w.conv2_b; g.pos = w.enc_pos;
+        ProfScope ps(prof, KC_GEMM, st);
         if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
     }
     for (int l = 0; l < a.n_enc_layer; l++) {
         const EncLayerW& e = w.enc[l];
-        if ((rc = layernorm<__nv_bfloat16>(ws.x, e.ln1_g, e.ln1_b, M, d, ws.h, st)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_LAYERNORM, st);
+            if ((rc = layernorm<__nv_bfloat16>(ws.x, e.ln1_g, e.ln1_b, M, d, ws.h, st)) != WDR_OK) return rc;
+        }
         {
             GemmDesc g;
             // per-window batches so that V^T columns can be laid out at a 16-byte aligned per-window stride
@@ -192,32 +200,43 @@ int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* m
             g.W = e.w_qkv; g.ldw = d; g.N = 3 * d; g.K = d;
             g.epilogue = EPI_QKV_BF16; g.out = ws.qk; g.ldc = 2 * d; g.bias = e.b_qkv;
             g.out_t = ws.vt; g.ldt = ws.ldt; g.t_batch_stride = kTPad; g.n_split = 2 * d;
-            if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
+            ProfScope ps(prof, KC_GEMM, st);
+        if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
-        if ((rc = encoder_attention(ws.qk, ws.vt, ws.ldt, B, T, a.n_head, d, ws.att, st)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_ATTENTION, st);
+            if ((rc = encoder_attention(ws.qk, ws.vt, ws.ldt, B, T, a.n_head, d, ws.att, st)) != WDR_OK) return rc;
+        }
         {
             GemmDesc g;
             g.A = ws.att; g.a_row_stride = d; g.rows_per_batch = (int)M; g.n_batch = 1;
             g.W = e.w_o; g.ldw = d; g.N = d; g.K = d;
             g.epilogue = EPI_BIAS_RESID_F32; g.out = ws.x; g.ldc = d; g.bias = e.b_o; g.resid = ws.x;
-            if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
+            ProfScope ps(prof, KC_GEMM, st);
+        if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
-        if ((rc = layernorm<__nv_bfloat16>(ws.x, e.ln2_g, e.ln2_b, M, d, ws.h, st)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_LAYERNORM, st);
+            if ((rc = layernorm<__nv_bfloat16>(ws.x, e.ln2_g, e.ln2_b, M, d, ws.h, st)) != WDR_OK) return rc;
+        }
         {
             GemmDesc g;
             g.A = ws.h; g.a_row_stride = d; g.rows_per_batch = (int)M; g.n_batch = 1;
             g.W = e.w_fc1; g.ldw = d; g.N = 4 * d; g.K = d;
             g.epilogue = EPI_BIAS_GELU_BF16; g.out = ws.ff; g.ldc = 4 * d; g.bias = e.b_fc1;
-            if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
+            ProfScope ps(prof, KC_GEMM, st);
+        if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
         {
             GemmDesc g;
             g.A = ws.ff; g.a_row_stride = 4 * d; g.rows_per_batch = (int)M; g.n_batch = 1;
             g.W = e.w_fc2; g.ldw = 4 * d; g.N = d; g.K = 4 * d;
             g.epilogue = EPI_BIAS_RESID_F32; g.out = ws.x; g.ldc = d; g.bias = e.b_fc2; g.resid = ws.x;
-            if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
+            ProfScope ps(prof, KC_GEMM, st);
+        if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
     }
+    ProfScope ps_post(prof, KC_LAYERNORM, st);
     if (out_f32 && (rc = layernorm<float>(ws.x, w.enc_lnpost_g, w.enc_lnpost_b, M, d, out_f32, st)) != WDR_OK) return rc;
     if (out_bf16 && (rc = layernorm<__nv_bfloat16>(ws.x, w.enc_lnpost_g, w.enc_lnpost_b, M, d, out_bf16, st)) != WDR_OK) return rc;
     return WDR_OK;
@@ -226,14 +245,17 @@ int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* m
 // PCM windows -> hidden states (mel + encoder), everything on `st`.
 template <typename In>
 int encode_chunks(const wdr_context* ctx, EncoderWorkspace& ws, const In* pcm, int64_t chunk_stride, const int32_t* n_valid_dev, int B,
-                  float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st) {
+                  float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st, Profiler* prof) {
     int rc = ws.reserve(ctx->arch, B);
     if (rc != WDR_OK) return rc;
-    rc = mel_launch<In>(ctx->mel, pcm, chunk_stride, n_valid_dev, WDR_CHUNK_SAMPLES, B, WDR_CHUNK_FRAMES, 0, ws.mel_raw, ws.chunk_max, st);
-    if (rc != WDR_OK) return rc;
-    return encoder_forward(ctx, ws, ws.mel_raw, WDR_CHUNK_FRAMES, 0, ws.chunk_max, 0, B, out_f32, out_bf16, st);
+    {
+        ProfScope ps(prof, KC_MEL, st);
+        rc = mel_launch<In>(ctx->mel, pcm, chunk_stride, n_valid_dev, WDR_CHUNK_SAMPLES, B, WDR_CHUNK_FRAMES, 0, ws.mel_raw, ws.chunk_max, st);
+        if (rc != WDR_OK) return rc;
+    }
+    return encoder_forward(ctx, ws, ws.mel_raw, WDR_CHUNK_FRAMES, 0, ws.chunk_max, 0, B, out_f32, out_bf16, st, prof);
 }
-template int encode_chunks<int16_t>(const wdr_context*, EncoderWorkspace&, const int16_t*, int64_t, const int32_t*, int, float*, __nv_bfloat16*, cudaStream_t);
-template int encode_chunks<float>(const wdr_context*, EncoderWorkspace&, const float*, int64_t, const int32_t*, int, float*, __nv_bfloat16*, cudaStream_t);
+template int encode_chunks<int16_t>(const wdr_context*, EncoderWorkspace&, const int16_t*, int64_t, const int32_t*, int, float*, __nv_bfloat16*, cudaStream_t, Profiler*);
+template int encode_chunks<float>(const wdr_context*, EncoderWorkspace&, const float*, int64_t, const int32_t*, int, float*, __nv_bfloat16*, cudaStream_t, Profiler*);
 
 }  // namespace wdr

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "model.cuh"
+#include "profile.cuh"
 
 namespace wdr {
 
@@ -25,10 +26,10 @@ struct EncoderWorkspace {
 };
 
 int encoder_forward(const wdr_context* ctx, EncoderWorkspace& ws, const float* mel, int n_frames, int mel_offset, const float* chunk_max,
-                    int normalized_input, int B, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st);
+                    int normalized_input, int B, float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st, Profiler* prof = nullptr);
 template <typename In>
 int encode_chunks(const wdr_context* ctx, EncoderWorkspace& ws, const In* pcm, int64_t chunk_stride, const int32_t* n_valid_dev, int B,
-                  float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st);
+                  float* out_f32, __nv_bfloat16* out_bf16, cudaStream_t st, Profiler* prof = nullptr);
 template <typename Out>
 int layernorm(const float* x, const float* g, const float* b, int64_t rows, int d, Out* out, cudaStream_t st);
 
