@@ -39,6 +39,72 @@ struct AttParams {
     float scale_log2e;   // (1/sqrt(64)) * log2(e)
 };
 
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
+// pass 1 over the S tile in TMEM: row max of the first n_valid columns (MASK = tile has padding keys)
+template <bool MASK>
+__device__ __forceinline__ float att_row_max(uint32_t taddr, int n_valid) {
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < kAttK / 32; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float x0 = __uint_as_float(r[i]), x1 = __uint_as_float(r[i + 1]);
+            if (MASK) {
+                if (c * 32 + i >= n_valid) x0 = -INFINITY;
+                if (c * 32 + i + 1 >= n_valid) x1 = -INFINITY;
+            }
+            m = max3(m, x0, x1);
+        }
+    }
+    return m;
+}
+
+// pass 2: p = 2^(s*scale - m_scaled) -> bf16 P in shared memory (128-byte-swizzled K-major rows), returns the row sum
+template <bool MASK>
+__device__ __forceinline__ float att_row_probs(uint32_t taddr, int n_valid, float scale, float m_scaled, unsigned char* p_row, int sw) {
+    float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < kAttK / 32; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c * 32, r);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(r[i]), scale, -m_scaled));
+            float p1 = ex2_approx(fmaf(__uint_as_float(r[i + 1]), scale, -m_scaled));
+            if (MASK) {
+                if (c * 32 + i >= n_valid) p0 = 0.0f;
+                if (c * 32 + i + 1 >= n_valid) p1 = 0.0f;
+            }
+            l0 += p0;
+            l1 += p1;
+            __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
+            packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
+        }
+        unsigned char* blk = p_row + (c >> 1) * (kPBytes / 2);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int chunk = (c & 1) * 4 + g;  // 16-byte chunk within the 128-byte row
+            *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
+        }
+    }
+    return l0 + l1;
+}
+
 __global__ void __launch_bounds__(kAttThreads, 2)
 encoder_attention_kernel(const __grid_constant__ CUtensorMap tma_qk, const __grid_constant__ CUtensorMap tma_vt, const AttParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -138,18 +204,10 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tma_qk, const __gri
             mbar_wait(&bar_s, j & 1);
             tc_fence_after();
             // pass 1: row max
-            float m_tile = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < kAttK / 32; c++) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if (c * 32 + i < n_valid) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
-            }
+            const bool full = (n_valid == kAttK);
+            const float m_tile = full ? att_row_max<false>(tmem_s + lane_addr, n_valid) : att_row_max<true>(tmem_s + lane_addr, n_valid);
             const float m_new = fmaxf(m_run, m_tile);
-            const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // m_run = -inf on the first tile -> 0
+            const float alpha = ex2_approx((m_run - m_new) * p.scale_log2e);  // m_run = -inf on the first tile -> 0
             const float m_scaled = m_new * p.scale_log2e;
             // previous tile's P V must be finished before sP is overwritten and before O_part is consumed
             if (j > 0) {
@@ -165,30 +223,8 @@ encoder_attention_kernel(const __grid_constant__ CUtensorMap tma_qk, const __gri
                 }
             }
             // pass 2: probabilities -> bf16 P in shared memory (swizzled K-major), row sum
-            float l_tile = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < kAttK / 32; c++) {
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_s + lane_addr + c * 32, r);
-                tmem_ld_wait();
-                uint32_t packed[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = (c * 32 + i < n_valid) ? exp2f(fmaf(__uint_as_float(r[i]), p.scale_log2e, -m_scaled)) : 0.0f;
-                    float p1 = (c * 32 + i + 1 < n_valid) ? exp2f(fmaf(__uint_as_float(r[i + 1]), p.scale_log2e, -m_scaled)) : 0.0f;
-                    __nv_bfloat162 pk = __floats2bfloat162_rn(p0, p1);
-                    // the row sum uses the rounded values the MMA will see, so that sum(P)/l is consistent
-                    l_tile += __low2float(pk) + __high2float(pk);
-                    packed[i >> 1] = *reinterpret_cast<uint32_t*>(&pk);
-                }
-                unsigned char* blk = p_row + (c >> 1) * (kPBytes / 2);
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int chunk = (c & 1) * 4 + g;  // 16-byte chunk within the 128-byte row
-                    *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) =
-                        make_uint4(packed[4 * g], packed[4 * g + 1], packed[4 * g + 2], packed[4 * g + 3]);
-                }
-            }
+            const float l_tile = full ? att_row_probs<false>(tmem_s + lane_addr, n_valid, p.scale_log2e, m_scaled, p_row, sw)
+                                      : att_row_probs<true>(tmem_s + lane_addr, n_valid, p.scale_log2e, m_scaled, p_row, sw);
             // rescale the running state for the new max
 #pragma unroll
             for (int i = 0; i < kAttD; i++) o_acc[i] *= alpha;

@@ -72,6 +72,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __shared__ __align__(8) uint64_t bar_tfull[2];
     __shared__ __align__(8) uint64_t bar_tempty[2];
     __shared__ uint32_t s_tmem_base;
+    __shared__ __align__(16) float4 s_stage[4][32 * 8];  // per epilogue warp: 32 rows x 32 fp32
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + kBK - 1) / kBK;
@@ -151,6 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int q = warp & 3;  // TMEM lane group this warp may access
+        float4* stage = s_stage[q];
         int as = 0;
         uint32_t aph = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -158,7 +160,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
             const int r_in_batch = mt * kBM + q * 32 + lane;
             const bool row_ok = r_in_batch < p.rows_per_batch;
-            const int64_t c_off = (int64_t)batch * p.c_batch_stride + (int64_t)r_in_batch * p.ldc;  // its element offset
             mbar_wait(&bar_tfull[as], aph);
             tc_fence_after();
 #pragma unroll 1
@@ -168,58 +169,58 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
                 tmem_ld_wait();
-                float v[32];
+                if (EPI == EPI_QKV_BF16 && n0 >= p.n_split) {
+                    // transposed store (V^T): lanes hold consecutive rows -> 64 B coalesced per column, straight from registers
+                    if (row_ok) {
+                        __nv_bfloat16* o = p.out_t + (int64_t)(n0 - p.n_split) * p.ldt + (int64_t)batch * p.t_batch_stride + r_in_batch;
 #pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = __uint_as_float(r[j]);
-                if (p.bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (n0 + j < p.N) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
-                            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                        }
+                        for (int j = 0; j < 32; j++)
+                            if (n0 + j < p.N) o[(int64_t)j * p.ldt] = __float2bfloat16_rn(__uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.0f));
                     }
+                    continue;
                 }
-                if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
+                // stage the 32 x 32 fp32 block (lane = row) in shared memory, 16-byte groups XOR-swizzled by row, then
+                // re-read it with 8 lanes per row so that every global access is a contiguous 128 B (fp32) / 64 B (bf16) row segment
+                float4* srow = stage + lane * 8;
 #pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = gelu_tanh(v[j]);
-                }
-                if (!row_ok) continue;
-                if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || (EPI == EPI_QKV_BF16 && n0 < p.n_split)) {
-                    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + c_off + n0;
+                for (int g = 0; g < 8; g++)
+                    srow[g ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
+                                                       __uint_as_float(r[4 * g + 3]));
+                __syncwarp();
+                const int g = lane & 7, rsub = lane >> 3;
+                const int n = n0 + 4 * g;
+                const bool col_ok = n < p.N;
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        if (n0 + j < p.N) {
-                            uint4 w;
-                            w.x = pack_bf16(v[j], v[j + 1]);
-                            w.y = pack_bf16(v[j + 2], v[j + 3]);
-                            w.z = pack_bf16(v[j + 4], v[j + 5]);
-                            w.w = pack_bf16(v[j + 6], v[j + 7]);
-                            *reinterpret_cast<uint4*>(o + j) = w;
+                for (int it = 0; it < 8; it++) {
+                    const int row = it * 4 + rsub;
+                    const int rib = mt * kBM + q * 32 + row;
+                    float4 v = stage[row * 8 + (g ^ (row & 7))];
+                    if (rib < p.rows_per_batch && col_ok) {
+                        v.x += bias4.x; v.y += bias4.y; v.z += bias4.z; v.w += bias4.w;
+                        if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
+                            v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); v.z = gelu_tanh(v.z); v.w = gelu_tanh(v.w);
                         }
-                    }
-                } else if (EPI == EPI_QKV_BF16) {
-                    // transposed store: lanes hold consecutive rows -> 64 B coalesced per column
-                    __nv_bfloat16* o = p.out_t + (int64_t)(n0 - p.n_split) * p.ldt + (int64_t)batch * p.t_batch_stride + r_in_batch;
-#pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (n0 + j < p.N) o[(int64_t)j * p.ldt] = __float2bfloat16_rn(v[j]);
-                } else {
-                    float* o = reinterpret_cast<float*>(p.out) + c_off + n0;
-                    const float* rs = (EPI == EPI_BIAS_RESID_F32) ? p.resid + c_off + n0
-                                      : (EPI == EPI_BIAS_GELU_POS_F32) ? p.pos + (int64_t)r_in_batch * p.N + n0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        if (n0 + j < p.N) {
-                            float4 w = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                            if (rs) {
-                                const float4 a = *reinterpret_cast<const float4*>(rs + j);
-                                w.x += a.x; w.y += a.y; w.z += a.z; w.w += a.w;
+                        const int64_t off = (int64_t)batch * p.c_batch_stride + (int64_t)rib * p.ldc + n;
+                        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16) {
+                            uint2 w;
+                            w.x = pack_bf16(v.x, v.y);
+                            w.y = pack_bf16(v.z, v.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = w;
+                        } else {
+                            if (EPI == EPI_BIAS_RESID_F32) {
+                                const float4 a = *reinterpret_cast<const float4*>(p.resid + off);
+                                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                            } else if (EPI == EPI_BIAS_GELU_POS_F32) {
+                                const float4 a = __ldg(reinterpret_cast<const float4*>(p.pos + (int64_t)rib * p.N + n));
+                                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
                             }
-                            *reinterpret_cast<float4*>(o + j) = w;
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
                         }
                     }
                 }
+                __syncwarp();  // the staging block is reused by the next chunk
             }
             tc_fence_before();
             __syncwarp();
