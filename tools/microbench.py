@@ -46,9 +46,17 @@ def main():
         W = (torch.randn(N, K, device="cuda") * 0.05).bfloat16()
         b = torch.randn(N, device="cuda")
         out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
-        med, best = time_it(lambda: w.gemm_bf16_dev(A.data_ptr(), K, M, 1, 0, W.data_ptr(), K, N, K, out.data_ptr(), N, 0, b.data_ptr(), stream=st))
+        out32 = torch.randn(M, N, device="cuda", dtype=torch.float32)
+        entry = {}
+        for name, epi, o, extra in (("bias_bf16", 0, out, None), ("gelu_bf16", 1, out, None), ("resid_f32", 2, out32, out32)):
+            med, best = time_it(lambda: w.gemm_bf16_dev(A.data_ptr(), K, M, 1, 0, W.data_ptr(), K, N, K, o.data_ptr(), N, epi, b.data_ptr(),
+                                                        None if extra is None else extra.data_ptr(), stream=st))
+            entry[name] = {"ms": med, "TFLOPs": 2 * M * N * K / med / 1e9}
         tmed, _ = time_it(lambda: torch.matmul(A, W.T))
-        res[f"gemm_{M}x{N}x{K}"] = {"ms": med, "TFLOPs": 2 * M * N * K / med / 1e9, "cublas_ms": tmed, "cublas_TFLOPs": 2 * M * N * K / tmed / 1e9}
+        entry["cublas"] = {"ms": tmed, "TFLOPs": 2 * M * N * K / tmed / 1e9}
+        res[f"gemm_{M}x{N}x{K}"] = entry
+    if len(sys.argv) > 1 and sys.argv[1] == "att":
+        pass
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)

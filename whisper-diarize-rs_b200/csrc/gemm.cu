@@ -25,7 +25,7 @@ using namespace sm100;
 
 constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 384;  // 4 control warps + 8 epilogue warps
 
 struct GemmParams {
     int rows_per_batch, n_batch, N, K;
@@ -44,9 +44,12 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-    // 0.5 x (1 + tanh(u)) == x * sigmoid(2u),  u = sqrt(2/pi) * x * (1 + 0.044715 x^2)   (ggml_gelu_f32)
+    // 0.5 x (1 + tanh(u)),  u = sqrt(2/pi) * x * (1 + 0.044715 x^2)   (ggml_gelu_f32); one MUFU (tanh.approx, abs err 2^-11)
     const float u = 0.7978845608028654f * x * fmaf(0.044715f * x, x, 1.0f);
-    return __fdividef(x, 1.0f + __expf(-2.0f * u));
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -72,7 +75,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     __shared__ __align__(8) uint64_t bar_tfull[2];
     __shared__ __align__(8) uint64_t bar_tempty[2];
     __shared__ uint32_t s_tmem_base;
-    __shared__ __align__(16) float4 s_stage[4][32 * 8];  // per epilogue warp: 32 rows x 32 fp32
+    __shared__ __align__(16) float4 s_stage[8][32 * 8];  // per epilogue warp: 32 rows x 32 fp32
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + kBK - 1) / kBK;
@@ -88,7 +91,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&bar_tfull[s], 1);
-            mbar_init(&bar_tempty[s], 4);
+            mbar_init(&bar_tempty[s], 8);
         }
         mbar_fence_init();
     }
@@ -150,9 +153,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             }
         }
     } else if (warp >= 4) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;  // TMEM lane group this warp may access
-        float4* stage = s_stage[q];
+        // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
+        const int q = warp & 3;           // TMEM lane group this warp may access
+        const int half = (warp - 4) >> 2;  // which half of the tile's columns
+        float4* stage = s_stage[warp - 4];
+        const int g = lane & 7, rsub = lane >> 3;
         int as = 0;
         uint32_t aph = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -160,12 +165,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
             const int r_in_batch = mt * kBM + q * 32 + lane;
             const bool row_ok = r_in_batch < p.rows_per_batch;
-            mbar_wait(&bar_tfull[as], aph);
-            tc_fence_after();
+            const int64_t c_base = (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32) * p.ldc;
+            bool waited = false;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
                 const int n0 = n_tile * BN + c * 32;
                 if (n0 >= p.N) break;  // warp-uniform
+                const int n = n0 + 4 * g;
+                const bool col_ok = n < p.N;
+                // operands that do not depend on the accumulator are fetched before waiting for it
+                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                float4 extra[8];
+                if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32) {
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int row = it * 4 + rsub;
+                        const int rib = mt * kBM + q * 32 + row;
+                        extra[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rib < p.rows_per_batch && col_ok) {
+                            if (EPI == EPI_BIAS_RESID_F32) extra[it] = *reinterpret_cast<const float4*>(p.resid + c_base + (int64_t)row * p.ldc + n);
+                            else extra[it] = __ldg(reinterpret_cast<const float4*>(p.pos + (int64_t)rib * p.N + n));
+                        }
+                    }
+                }
+                if (!waited) {
+                    mbar_wait(&bar_tfull[as], aph);
+                    tc_fence_after();
+                    waited = true;
+                }
                 uint32_t r[32];
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
                 tmem_ld_wait();
@@ -183,15 +211,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 // re-read it with 8 lanes per row so that every global access is a contiguous 128 B (fp32) / 64 B (bf16) row segment
                 float4* srow = stage + lane * 8;
 #pragma unroll
-                for (int g = 0; g < 8; g++)
-                    srow[g ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * g]), __uint_as_float(r[4 * g + 1]), __uint_as_float(r[4 * g + 2]),
-                                                       __uint_as_float(r[4 * g + 3]));
+                for (int gg = 0; gg < 8; gg++)
+                    srow[gg ^ (lane & 7)] = make_float4(__uint_as_float(r[4 * gg]), __uint_as_float(r[4 * gg + 1]),
+                                                        __uint_as_float(r[4 * gg + 2]), __uint_as_float(r[4 * gg + 3]));
                 __syncwarp();
-                const int g = lane & 7, rsub = lane >> 3;
-                const int n = n0 + 4 * g;
-                const bool col_ok = n < p.N;
-                float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
 #pragma unroll
                 for (int it = 0; it < 8; it++) {
                     const int row = it * 4 + rsub;
@@ -202,25 +225,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         if (EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_GELU_POS_F32) {
                             v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); v.z = gelu_tanh(v.z); v.w = gelu_tanh(v.w);
                         }
-                        const int64_t off = (int64_t)batch * p.c_batch_stride + (int64_t)rib * p.ldc + n;
+                        const int64_t off = c_base + (int64_t)row * p.ldc + n;
                         if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16) {
                             uint2 w;
                             w.x = pack_bf16(v.x, v.y);
                             w.y = pack_bf16(v.z, v.w);
                             *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off) = w;
                         } else {
-                            if (EPI == EPI_BIAS_RESID_F32) {
-                                const float4 a = *reinterpret_cast<const float4*>(p.resid + off);
-                                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                            } else if (EPI == EPI_BIAS_GELU_POS_F32) {
-                                const float4 a = __ldg(reinterpret_cast<const float4*>(p.pos + (int64_t)rib * p.N + n));
-                                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                            if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32) {
+                                v.x += extra[it].x; v.y += extra[it].y; v.z += extra[it].z; v.w += extra[it].w;
                             }
                             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + off) = v;
                         }
                     }
                 }
                 __syncwarp();  // the staging block is reused by the next chunk
+            }
+            if (!waited) {  // this warp's column half lies beyond N: still take part in the accumulator hand-shake
+                mbar_wait(&bar_tfull[as], aph);
+                tc_fence_after();
             }
             tc_fence_before();
             __syncwarp();
@@ -341,12 +364,12 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     switch (d.epilogue) {
-        case EPI_BIAS_BF16: return launch_gemm<BN, 6, EPI_BIAS_BF16>(ta, tb, p, st);
-        case EPI_BIAS_GELU_BF16: return launch_gemm<BN, 6, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
-        case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<BN, 6, EPI_BIAS_RESID_F32>(ta, tb, p, st);
-        case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<BN, 6, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
-        case EPI_QKV_BF16: return launch_gemm<BN, 6, EPI_QKV_BF16>(ta, tb, p, st);
-        case EPI_F32: return launch_gemm<BN, 6, EPI_F32>(ta, tb, p, st);
+        case EPI_BIAS_BF16: return launch_gemm<BN, 5, EPI_BIAS_BF16>(ta, tb, p, st);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<BN, 5, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
+        case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<BN, 5, EPI_BIAS_RESID_F32>(ta, tb, p, st);
+        case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<BN, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
+        case EPI_QKV_BF16: return launch_gemm<BN, 5, EPI_QKV_BF16>(ta, tb, p, st);
+        case EPI_F32: return launch_gemm<BN, 5, EPI_F32>(ta, tb, p, st);
     }
     set_error("unknown epilogue %d", d.epilogue);
     return WDR_ERR_INVALID;
