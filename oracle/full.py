@@ -1,0 +1,76 @@
+"""whisper_full_with_state as the reference drives it, composed from the oracle's C pieces, for ONE
+buffer of <= 30 s (the sharded mode of SURVEY §0.4: single_segment, no prompt carry, per-chunk mel max).  Test
+infrastructure only."""
+import numpy as np
+
+from . import native, vocab as V, weights as W, filters
+
+
+def prompt_tokens(n_vocab, lang_id=0, translate=False):
+    v = V.special_ids(n_vocab)
+    p = [v["sot"]]
+    if v["multilingual"]:
+        p += [v["lang0"] + lang_id, v["translate"] if translate else v["transcribe"]]
+    return p
+
+
+def dtw_sequence(n_vocab, text_ids, lang_id=0):
+    v = V.special_ids(n_vocab)
+    seq = [v["sot"]]
+    if v["multilingual"]:
+        seq.append(v["lang0"] + lang_id)
+    sot_len = len(seq)
+    seq.append(v["not_"])
+    seq += [int(t) for t in text_ids]
+    seq.append(v["eot"])
+    return seq, sot_len
+
+
+def n_len_org(n_samples):
+    return 1 + (n_samples + 200 - 400) // 160
+
+
+def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10):
+    """dec: native.Decoder; enc_out [1500, d] (encoder output for this window); pcm_f32: the window's samples (<= 480000).
+    Returns dict(segments=[dict(t0, t1, text, tokens=[TokenData])], seek_delta, no_speech_prob, margins, ...)."""
+    nv = dec.a["n_vocab"]
+    v = V.special_ids(nv)
+    seek, seek_end = 0, n_len_org(len(pcm_f32))
+    out = dict(segments=[], seek_end=seek_end)
+    if seek_end < seek + delta_min or seek + delta_min >= seek_end:
+        return out
+    dec.set_audio(enc_out)
+    r = dec.decode_window(prompt_tokens(nv), seek, seek_end, True, delta_min)
+    out.update(r)
+    toks = r["tokens"]
+    if r["failed"]:
+        avg_logprob = -np.inf
+    else:
+        avg_logprob = sum(float(t.plog) for t in toks) / max(1, r["result_len"]) if r["result_len"] else -np.inf
+    is_no_speech = r["no_speech_prob"] > 0.6 and avg_logprob < -1.0
+    out["is_no_speech"] = bool(is_no_speech)
+    if not toks or is_no_speech:
+        return out
+    seek_delta = r["seek_delta"]
+    t0 = seek + 2 * (toks[0].tid - v["beg"])
+    text = "".join(V.token_text(t.id, nv) for t in toks if t.id < v["eot"])
+    if text:
+        t1 = seek + seek_delta
+        if token_timestamps:
+            energy = native.signal_energy(pcm_f32, 32)
+            vlen = [V.voice_length(V.token_text(t.id, nv)) for t in toks]
+            st3 = np.zeros(3, np.int64)
+            toks = native.token_timestamps(toks, t0, t1, vlen, energy, v["beg"], v["eot"], st3)
+        if dtw:
+            n_frames = min(3000, seek_delta, seek_end - seek)
+            n_audio = n_frames // 2
+            text_ids = [t.id for t in toks if t.id < v["eot"]]
+            seq, sot_len = dtw_sequence(nv, text_ids)
+            aheads = W.ALIGNMENT_HEADS[dec.arch]
+            w = dec.dtw_attention(seq, aheads, n_audio)
+            cost = native.dtw_cost(w, sot_len, 7)
+            ti, tj = native.dtw(cost)
+            toks = native.dtw_stamp(toks, v["eot"], ti, tj, seek)
+            out.update(dtw_w=w, dtw_cost=cost, dtw_path=(ti, tj))
+        out["segments"].append(dict(t0=t0, t1=t1, text=text, tokens=toks))
+    return out

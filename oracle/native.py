@@ -128,3 +128,165 @@ def whisper_encode(mel, arch, packed_weights):
     rc = lib().oracle_whisper_encode(mp, a["n_mel"], a["d"], a["n_head"], a["n_enc"], pp, out.ctypes.data_as(C.POINTER(C.c_float)))
     assert rc == 0
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# decoder half (oracle/wdr_oracle_full.c)
+# ---------------------------------------------------------------------------------------------------
+class TokenData(C.Structure):
+    """== whisper_token_data"""
+    _fields_ = [("id", C.c_int32), ("tid", C.c_int32), ("p", C.c_float), ("plog", C.c_float), ("pt", C.c_float), ("ptsum", C.c_float),
+                ("t0", C.c_int64), ("t1", C.c_int64), ("t_dtw", C.c_int64), ("vlen", C.c_float)]
+
+    def as_tuple(self):
+        return (self.id, self.tid, self.p, self.plog, self.pt, self.ptsum, self.t0, self.t1, self.t_dtw, self.vlen)
+
+
+class Vocab(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n_vocab", "eot", "sot", "translate", "transcribe", "solm", "prev", "nosp", "not_", "beg",
+                                       "lang0", "n_langs", "space")]
+
+
+class LogitParams(C.Structure):
+    _fields_ = [("suppress_blank", C.c_int), ("no_timestamps", C.c_int), ("suppress_nst", C.c_int), ("max_initial_ts", C.c_float)]
+
+
+def make_vocab(n_vocab):
+    from . import vocab as V
+    s = V.special_ids(n_vocab)
+    return Vocab(**{k: s[k] for k, _ in Vocab._fields_})
+
+
+_full_ready = False
+
+
+def _full():
+    global _full_ready
+    L = lib()
+    if not _full_ready:
+        f32p, i32p, i64p = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_int64)
+        L.oracle_dec_create.restype = C.c_void_p
+        L.oracle_dec_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int]
+        L.oracle_dec_free.argtypes = [C.c_void_p]
+        L.oracle_dec_set_audio.argtypes = [C.c_void_p, f32p]
+        L.oracle_dec_step.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, i32p, C.c_int, f32p]
+        L.oracle_process_logits.argtypes = [f32p, C.POINTER(Vocab), C.POINTER(LogitParams), C.POINTER(TokenData), C.c_int, C.c_int, C.c_int,
+                                            f32p, f32p]
+        L.oracle_process_logits.restype = None
+        L.oracle_sample_greedy.argtypes = [f32p, f32p, C.POINTER(Vocab)]
+        L.oracle_sample_greedy.restype = TokenData
+        L.oracle_no_speech_prob.argtypes = [f32p, C.POINTER(Vocab), f32p]
+        L.oracle_no_speech_prob.restype = C.c_float
+        L.oracle_decode_window.argtypes = [C.c_void_p, C.POINTER(Vocab), C.POINTER(LogitParams), i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                           C.c_int, C.POINTER(TokenData), i32p, f32p, f32p]
+        L.oracle_token_timestamps.argtypes = [C.POINTER(TokenData), C.c_int, C.c_int64, C.c_int64, f32p, f32p, C.c_int, C.c_int, C.c_int,
+                                              C.c_float, C.c_float, i64p]
+        L.oracle_token_timestamps.restype = None
+        L.oracle_dtw_attention.argtypes = [C.c_void_p, i32p, C.c_int, i32p, C.c_int, C.c_int, f32p]
+        L.oracle_dtw_stamp.argtypes = [C.POINTER(TokenData), C.c_int, C.c_int, i32p, i32p, C.c_int, C.c_int]
+        L.oracle_dtw_stamp.restype = None
+        _full_ready = True
+    return L
+
+
+class Decoder:
+    """KV-cached Whisper decoder for ONE window.  bf16=True applies libwdr_b200's storage precision."""
+
+    def __init__(self, arch, packed_weights, bf16=False):
+        from . import weights as W
+        self.a = W.ARCHS[arch]
+        self.arch = arch
+        self.w = np.ascontiguousarray(packed_weights, np.float32)  # keep alive: the C side borrows it
+        self.h = _full().oracle_dec_create(self.a["d"], self.a["n_head"], self.a["n_dec"], self.a["n_vocab"],
+                                           self.w.ctypes.data_as(C.POINTER(C.c_float)), int(bf16))
+        self.vocab = make_vocab(self.a["n_vocab"])
+
+    def close(self):
+        if self.h:
+            _full().oracle_dec_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_audio(self, enc):
+        e, ep = _f32(enc)
+        assert e.shape == (1500, self.a["d"])
+        _full().oracle_dec_set_audio(self.h, ep)
+
+    def step(self, token, pos, aheads=None, want_logits=True):
+        logits = np.empty(self.a["n_vocab"], np.float32) if want_logits else None
+        lp = logits.ctypes.data_as(C.POINTER(C.c_float)) if want_logits else C.POINTER(C.c_float)()
+        if aheads:
+            ah = np.ascontiguousarray(np.array(aheads, np.int32).reshape(-1))
+            pr = np.empty((len(aheads), 1500), np.float32)
+            rc = _full().oracle_dec_step(self.h, int(token), int(pos), lp, ah.ctypes.data_as(C.POINTER(C.c_int32)), len(aheads),
+                                         pr.ctypes.data_as(C.POINTER(C.c_float)))
+            assert rc == 0
+            return logits, pr
+        rc = _full().oracle_dec_step(self.h, int(token), int(pos), lp, C.POINTER(C.c_int32)(), 0, C.POINTER(C.c_float)())
+        assert rc == 0
+        return logits
+
+    def decode_window(self, prompt, seek=0, seek_end=2999, single_segment=True, delta_min=10, suppress_blank=True, max_initial_ts=1.0):
+        """One seek iteration of whisper_full (greedy, T=0).  Returns dict(tokens=[TokenData...], seek_delta, failed, completed,
+        n_sampled, result_len, no_speech_prob, margins)."""
+        pr = np.ascontiguousarray(np.array(prompt, np.int32))
+        toks = (TokenData * 224)()
+        info = np.zeros(8, np.int32)
+        nsp = C.c_float(0)
+        margins = np.zeros(224, np.float32)
+        lp = LogitParams(int(suppress_blank), 0, 0, float(max_initial_ts))
+        n = _full().oracle_decode_window(self.h, C.byref(self.vocab), C.byref(lp), pr.ctypes.data_as(C.POINTER(C.c_int32)), len(pr),
+                                         int(seek), int(seek_end), int(single_segment), int(delta_min), toks,
+                                         info.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(nsp), margins.ctypes.data_as(C.POINTER(C.c_float)))
+        return dict(tokens=[toks[i] for i in range(n)], seek_delta=int(info[0]), failed=bool(info[1]), completed=bool(info[2]),
+                    n_sampled=int(info[3]), result_len=int(info[5]), no_speech_prob=float(nsp.value), margins=margins[: int(info[3])].copy())
+
+    def dtw_attention(self, seq, aheads, n_audio):
+        sq = np.ascontiguousarray(np.array(seq, np.int32))
+        ah = np.ascontiguousarray(np.array(aheads, np.int32).reshape(-1))
+        out = np.empty((len(aheads), len(sq), n_audio), np.float32)
+        rc = _full().oracle_dtw_attention(self.h, sq.ctypes.data_as(C.POINTER(C.c_int32)), len(sq), ah.ctypes.data_as(C.POINTER(C.c_int32)),
+                                          len(aheads), int(n_audio), out.ctypes.data_as(C.POINTER(C.c_float)))
+        assert rc == 0
+        return out
+
+
+def process_logits(logits, n_vocab, tokens_cur, has_ts, seek_delta, suppress_blank=True, max_initial_ts=1.0):
+    """whisper_process_logits + greedy whisper_sample_token on one logits row. tokens_cur: list of token ids sampled so far."""
+    v = make_vocab(n_vocab)
+    lg = np.ascontiguousarray(logits, np.float32).copy()
+    lpb = np.empty(n_vocab, np.float32)
+    pb = np.empty(n_vocab, np.float32)
+    cur = (TokenData * max(1, len(tokens_cur)))()
+    for i, t in enumerate(tokens_cur):
+        cur[i].id = int(t)
+    lp = LogitParams(int(suppress_blank), 0, 0, float(max_initial_ts))
+    f32p = C.POINTER(C.c_float)
+    _full().oracle_process_logits(lg.ctypes.data_as(f32p), C.byref(v), C.byref(lp), cur, len(tokens_cur), int(has_ts), int(seek_delta),
+                                  lpb.ctypes.data_as(f32p), pb.ctypes.data_as(f32p))
+    tok = _full().oracle_sample_greedy(pb.ctypes.data_as(f32p), lpb.ctypes.data_as(f32p), C.byref(v))
+    return tok, lg, lpb, pb
+
+
+def token_timestamps(tokens, t0, t1, vlen, energy, token_beg, token_eot, state3, thold_pt=0.01, thold_ptsum=0.01):
+    """whisper_exp_compute_token_level_timestamps on a list of TokenData (modified in place). state3: int64[3] carried."""
+    n = len(tokens)
+    arr = (TokenData * max(1, n))(*tokens)
+    vl = np.ascontiguousarray(vlen, np.float32)
+    en = np.ascontiguousarray(energy, np.float32)
+    _full().oracle_token_timestamps(arr, n, int(t0), int(t1), vl.ctypes.data_as(C.POINTER(C.c_float)), en.ctypes.data_as(C.POINTER(C.c_float)),
+                                    len(en), int(token_beg), int(token_eot), float(thold_pt), float(thold_ptsum),
+                                    state3.ctypes.data_as(C.POINTER(C.c_int64)))
+    return [arr[i] for i in range(n)]
+
+
+def dtw_stamp(tokens, token_eot, text_idx, time_idx, seek):
+    n = len(tokens)
+    arr = (TokenData * max(1, n))(*tokens)
+    ti = np.ascontiguousarray(text_idx, np.int32)
+    tj = np.ascontiguousarray(time_idx, np.int32)
+    _full().oracle_dtw_stamp(arr, n, int(token_eot), ti.ctypes.data_as(C.POINTER(C.c_int32)), tj.ctypes.data_as(C.POINTER(C.c_int32)), len(ti),
+                             int(seek))
+    return [arr[i] for i in range(n)]

@@ -144,3 +144,36 @@ def pack_encoder(arch, w):
             parts.append(w[p + n])
     parts += [w["encoder.ln_post.weight"], w["encoder.ln_post.bias"]]
     return np.concatenate([np.ravel(x) for x in parts]).astype(np.float32)
+
+
+def pack_decoder(arch, w):
+    """Flat fp32 array in the order oracle_dec_create walks (oracle/wdr_oracle_full.c)."""
+    a = ARCHS[arch]
+    parts = [w["decoder.token_embedding.weight"], w["decoder.positional_embedding"]]
+    for l in range(a["n_dec"]):
+        p = f"decoder.blocks.{l}."
+        for n in ("attn_ln.weight", "attn_ln.bias", "attn.query.weight", "attn.query.bias", "attn.key.weight", "attn.value.weight",
+                  "attn.value.bias", "attn.out.weight", "attn.out.bias", "cross_attn_ln.weight", "cross_attn_ln.bias",
+                  "cross_attn.query.weight", "cross_attn.query.bias", "cross_attn.key.weight", "cross_attn.value.weight",
+                  "cross_attn.value.bias", "cross_attn.out.weight", "cross_attn.out.bias", "mlp_ln.weight", "mlp_ln.bias",
+                  "mlp.0.weight", "mlp.0.bias", "mlp.2.weight", "mlp.2.bias"):
+            parts.append(w[p + n])
+    parts += [w["decoder.ln.weight"], w["decoder.ln.bias"]]
+    return np.concatenate([np.ravel(x) for x in parts]).astype(np.float32)
+
+
+# (layer, head) alignment heads per DTW preset (SURVEY B.2; OpenAI _ALIGNMENT_HEADS)
+ALIGNMENT_HEADS = {
+    "tiny.en": [(1, 0), (2, 0), (2, 5), (3, 0), (3, 1), (3, 2), (3, 3), (3, 4)],
+    "tiny": [(2, 2), (3, 0), (3, 2), (3, 3), (3, 4), (3, 5)],
+    "base.en": [(3, 3), (4, 7), (5, 1), (5, 5), (5, 7)],
+    "base": [(3, 1), (4, 2), (4, 3), (4, 7), (5, 1), (5, 2), (5, 4), (5, 6)],
+    "small.en": [(6, 6), (7, 0), (7, 3), (7, 8), (8, 2), (8, 5), (8, 7), (9, 0), (9, 4), (9, 8), (9, 10), (10, 0), (10, 1), (10, 2),
+                 (10, 3), (10, 6), (10, 11), (11, 2), (11, 4)],
+    "small": [(5, 3), (5, 9), (8, 0), (8, 4), (8, 7), (8, 8), (9, 0), (9, 7), (9, 9), (10, 5)],
+    "medium.en": [(11, 4), (14, 1), (14, 12), (14, 14), (15, 4), (16, 0), (16, 4), (16, 9), (17, 12), (17, 14), (18, 7), (18, 10),
+                  (18, 15), (20, 0), (20, 3), (20, 9), (20, 14), (21, 12)],
+    "medium": [(13, 15), (15, 4), (15, 15), (16, 1), (20, 0), (23, 4)],
+    "large-v3": [(7, 0), (10, 17), (12, 18), (13, 12), (16, 1), (17, 14), (19, 11), (21, 4), (24, 1), (25, 6)],
+    "large-v3-turbo": [(2, 4), (2, 11), (3, 3), (3, 6), (3, 11), (3, 14)],
+}
