@@ -178,6 +178,84 @@ int wdr_profile_collect(wdr_state* state, double* ms, int32_t* launches, int n_c
 int wdr_encoder_attention_dev(const uint16_t* qk, const uint16_t* vt, int64_t ldt, int n_chunks, int T, int n_head, int d_model,
                               uint16_t* out, void* stream);
 
+/* ---- full transcription (whisper_full_with_state: state.full, src/transcribe.rs:389; results :393-412, :252-282) -- */
+/* == whisper_token_data (WhisperToken::token_data(), src/transcribe.rs:272-282). t0/t1/t_dtw in centiseconds relative
+ * to the start of the buffer passed to the call; t_dtw = -1 when DTW did not reach the token. */
+typedef struct wdr_token_data {
+    int32_t id, tid;
+    float p, plog, pt, ptsum;
+    int64_t t0, t1, t_dtw;
+    float vlen;
+} wdr_token_data;
+enum wdr_sampling_strategy { WDR_SAMPLING_GREEDY = 0, WDR_SAMPLING_BEAM_SEARCH = 1 };
+/* == whisper_full_params, the fields the crate sets (setup_params, src/transcribe.rs:20-87) plus whisper.cpp's defaults
+ * for the rest.  Supported decoding: greedy at temperature 0 without temperature fallback (temperature_inc defaults to 0
+ * here; beam search and the fallback ladder are SURVEY §8f-4 rows and are refused with WDR_ERR_UNSUPPORTED), language given
+ * (no auto-detect), single_segment = 1 as the crate always sets (src/transcribe.rs:46).  Strings are borrowed for the call. */
+typedef struct wdr_full_params {
+    int strategy;            /* enum wdr_sampling_strategy */
+    int n_threads;           /* accepted, unused */
+    int n_max_text_ctx;
+    int offset_ms, duration_ms;
+    int translate, no_context, no_timestamps, single_segment;
+    int print_special, print_progress, print_realtime, print_timestamps;
+    int token_timestamps;    /* heuristic t0/t1 per token */
+    float thold_pt, thold_ptsum;
+    int max_len, split_on_word, max_tokens;
+    int audio_ctx;
+    const char* initial_prompt;      /* needs a tokenizer file: refused when non-empty */
+    const int32_t* prompt_tokens;    /* ids appended to the text context ([PREV] + tokens + sot sequence) */
+    int prompt_n_tokens;
+    const char* language;            /* "en", "de", ...; NULL = "en" */
+    int detect_language;
+    int suppress_blank, suppress_nst;
+    float temperature, max_initial_ts, length_penalty;
+    float temperature_inc, entropy_thold, logprob_thold, no_speech_thold;
+    int greedy_best_of, beam_size;
+    float beam_patience;
+    void (*progress_callback)(wdr_context* ctx, wdr_state* state, int progress, void* user_data);
+    void* progress_callback_user_data;
+    bool (*abort_callback)(void* user_data);   /* polled between decoder steps; true -> WDR_ERR_ABORTED (src/transcribe.rs:348-350) */
+    void* abort_callback_user_data;
+} wdr_full_params;
+wdr_full_params wdr_full_default_params(int strategy);                                     /* whisper_full_default_params */
+/* state.full(params, &samples): one buffer of <= 30 s (what the crate submits per SpeechSegment, src/transcribe.rs:376-389).
+ * 0 = ok; results stay in the state until the next call.  Host pointers. */
+int wdr_full_with_state(wdr_context* ctx, wdr_state* state, wdr_full_params params, const float* pcm, int n);
+int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* state, wdr_full_params params, const int16_t* pcm, int n);
+/* Sharded mode: n_chunks independent buffers of <= 30 s each (chunk b = pcm[b*chunk_stride ..][0..n_valid[b]),
+ * n_valid NULL = 480000), each treated exactly as its own wdr_full_with_state call; mel + encoder + cross-KV + greedy decode +
+ * token timestamps + DTW run batched on the device.  Results: segments of all chunks in chunk order. */
+int wdr_full_batch_i16(wdr_context* ctx, wdr_state* state, wdr_full_params params, const int16_t* pcm, int64_t chunk_stride,
+                       const int32_t* n_valid, int n_chunks);
+int wdr_full_n_segments_from_state(wdr_state* state);                                      /* state.full_n_segments(), :397 */
+int wdr_full_get_segment_chunk_from_state(wdr_state* state, int i_segment);                /* chunk the segment belongs to (batch calls) */
+int64_t wdr_full_get_segment_t0_from_state(wdr_state* state, int i_segment);               /* start_timestamp(), cs */
+int64_t wdr_full_get_segment_t1_from_state(wdr_state* state, int i_segment);               /* end_timestamp(), cs */
+const char* wdr_full_get_segment_text_from_state(wdr_state* state, int i_segment);         /* to_str(); owned by the state */
+float wdr_full_get_segment_no_speech_prob_from_state(wdr_state* state, int i_segment);
+int wdr_full_n_tokens_from_state(wdr_state* state, int i_segment);                         /* n_tokens(), :252 */
+int32_t wdr_full_get_token_id_from_state(wdr_state* state, int i_segment, int i_token);
+const char* wdr_full_get_token_text_from_state(wdr_context* ctx, wdr_state* state, int i_segment, int i_token);  /* to_str_lossy(), :257 */
+wdr_token_data wdr_full_get_token_data_from_state(wdr_state* state, int i_segment, int i_token);                /* token_data(), :272 */
+int wdr_full_lang_id_from_state(wdr_state* state);                                         /* full_lang_id_from_state(), :393 */
+const char* wdr_lang_str(int id);                                                          /* whisper_rs::get_lang_str, :394 */
+int wdr_lang_id(const char* lang);                                                         /* whisper_lang_id */
+const char* wdr_token_to_str(wdr_context* ctx, int32_t token);                             /* whisper_token_to_str */
+/* Per-chunk decoder summary of the last full call: info[8] = {seek_delta, failed, completed, n_sampled, has_ts, result_len,
+ * seek_end, n_segments}; *no_speech_prob optional.  For parity tests. */
+int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* info, float* no_speech_prob);
+/* Stage-level decoder access for parity tests: teacher-forced pass of `n_seq` tokens over window 0.. of the last encode/full call.
+ * enc: optional HOST encoder output [n_chunks][1500][d] to install first (NULL = keep the state's).  seq: HOST [n_chunks][n_seq].
+ * logits_out: HOST [n_chunks][n_seq][n_vocab] or NULL.  aheads_out: HOST [n_chunks][n_aheads][n_seq][1500] or NULL (needs a DTW
+ * context). */
+int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* state, const float* enc, int n_chunks, const int32_t* seq, int n_seq,
+                              float* logits_out, float* aheads_out);
+
+/* Bring-up aid: copies a decoder workspace buffer of the last step to the host as fp32 (0 x, 1 h, 2 att, 3 ff, 4 layer-0 cross K|V,
+ * 5 split-K partials). */
+int wdr_debug_decoder_read(wdr_state* state, int which, float* out, int64_t count);
+
 /* ---- stage-level kernels (not in whisper.h; for parity tests and roofline measurement) -------------- */
 /* tcgen05 bf16 GEMM: D[M][N] = A[M][K] * W[N][K]^T with a fused epilogue (the ggml mul_mat / ONNX Gemm of the
  * encoder, decoder and embedding nets).  bf16 values are passed as uint16_t.  A rows are n_batch groups of

@@ -22,19 +22,20 @@ def special_ids(n_vocab):
 
 
 def voice_length(text):
-    r = 0.0
+    import numpy as np
+    r = np.float32(0.0)
     for c in text:
         if c == " ":
-            r += 0.01
+            r = np.float32(r + np.float32(0.01))
         elif c == ",":
-            r += 2.0
+            r = np.float32(r + np.float32(2.0))
         elif c in ".!?":
-            r += 3.0
+            r = np.float32(r + np.float32(3.0))
         elif "0" <= c <= "9":
-            r += 3.0
+            r = np.float32(r + np.float32(3.0))
         else:
-            r += 1.0
-    return r
+            r = np.float32(r + np.float32(1.0))
+    return float(r)
 
 
 def token_text(i, n_vocab):

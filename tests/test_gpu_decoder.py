@@ -1,0 +1,144 @@
+"""GPU parity of the decoder half of state.full (reference src/transcribe.rs:389) through the C ABI.
+
+* teacher-forced logits and alignment-head cross-attention against the CPU oracle at the library's storage precision
+  (oracle bf16 policy = bf16 encoder output and cross-KV cache; the library's activations carry 16 mantissa bits: tolerance
+  3e-5 of max|logit|) and against the all-fp32 oracle (1e-3 of max|logit|; north-star class is 1e-2 relative);
+* the whole sharded-mode call (mel -> encoder -> cross-KV -> greedy decode -> token timestamps -> DTW): greedy token ids,
+  segment times, heuristic t0/t1 and DTW t_dtw must be IDENTICAL to the oracle run on the same encoder output."""
+import numpy as np
+import pytest
+
+from conftest import synth_audio
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tiny_w():
+    from oracle import weights as W
+    return W.whisper_weights("tiny.en", seed=1234)
+
+
+def test_vocab_strings_match_checker(wdr):
+    from oracle import vocab as V
+    import ctypes as C
+    ctx = wdr.Context("tiny.en", seed=1234)
+    L = wdr.load()
+    nv = ctx.dims.n_vocab
+    for i in list(range(0, 600)) + [1300, 27377, 50255, 50256, 50257, 50258, 50300, 50357, 50358, 50359, 50360, 50361, 50362, 50363, 50364, 51863]:
+        assert L.wdr_token_to_str(ctx._h, i).decode() == V.token_text(i, nv), i
+    ctx.close()
+    assert wdr.lang_str(0) == "en" and wdr.lang_id("de") == 2 and wdr.lang_str(99) == "yue"
+
+
+@pytest.mark.parametrize("arch", ["tiny.en", "base"])
+def test_teacher_forced_logits_and_alignment_heads(wdr, oracle, arch):
+    from oracle import weights as W, vocab as V
+    w = W.whisper_weights(arch, seed=1234)
+    a = W.ARCHS[arch]
+    v = V.special_ids(a["n_vocab"])
+    rng = np.random.default_rng(11)
+    B = 3
+    enc = rng.standard_normal((B, 1500, a["d"])).astype(np.float32)
+    seqs = np.array([[v["sot"], v["not_"], 1300, 220, 17, v["beg"] + 40, 901, v["eot"]],
+                     [v["sot"], v["not_"], 5, 6, 7, 8, 9, v["eot"]],
+                     [v["sot"], v["beg"], 4000, 4001, v["beg"] + 700, v["beg"] + 700, 31, v["eot"]]], np.int32)
+    aheads = W.ALIGNMENT_HEADS[arch]
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    logits, ah = st.decode_teacher_forced(seqs, enc=enc, want_logits=True, want_aheads=True, n_aheads=len(aheads))
+    pw = W.pack_decoder(arch, w)
+    for bf16, tol in ((True, 3e-5), (False, 1e-3)):
+        for b in range(B):
+            dec = oracle.Decoder(arch, pw, bf16=bf16)
+            dec.set_audio(enc[b])
+            for i, t in enumerate(seqs[b]):
+                lg, pr = dec.step(int(t), i, aheads=aheads)
+                scale = np.abs(lg).max()
+                assert np.abs(lg - logits[b, i]).max() <= tol * scale, (arch, bf16, b, i)
+                assert np.abs(pr - ah[b, :, i, :]).max() <= (1e-6 if bf16 else 1e-5), (arch, bf16, b, i)
+            dec.close()
+    st.close()
+    ctx.close()
+
+
+def _oracle_full(oracle, arch, w, enc, pcm_f32):
+    from oracle import weights as W, full
+    dec = oracle.Decoder(arch, W.pack_decoder(arch, w), bf16=True)
+    r = full.full_window(dec, enc, pcm_f32)
+    dec.close()
+    return r
+
+
+def test_full_batch_matches_oracle(wdr, oracle, tiny_w):
+    arch = "tiny.en"
+    B = 4
+    pcm = np.zeros((B, 480000), np.int16)
+    nv = np.array([480000, 480000, 200000, 64000], np.int32)
+    for b in range(B):
+        a = synth_audio(2000 + b, nv[b] / 16000.0)
+        pcm[b, : len(a)] = a[: nv[b]]
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    hid = st.encode_chunks(pcm, nv)
+    segs = st.full_batch(pcm, nv)
+    by_chunk = {}
+    for s in segs:
+        by_chunk.setdefault(s["chunk"], []).append(s)
+    n_identical = 0
+    for b in range(B):
+        x = pcm[b, : nv[b]].astype(np.float32) / np.float32(32768.0)
+        ref = _oracle_full(oracle, arch, tiny_w, hid[b], x)
+        info = st.chunk_info(b)
+        assert info["seek_end"] == ref["seek_end"]
+        got = by_chunk.get(b, [])
+        assert len(got) == len(ref["segments"]), (b, info, ref.get("failed"))
+        if not got:
+            continue
+        assert info["seek_delta"] == ref["seek_delta"] and info["failed"] == int(ref["failed"]) and info["n_sampled"] == ref["n_sampled"], (b, info)
+        assert abs(info["no_speech_prob"] - ref["no_speech_prob"]) <= 1e-3 * ref["no_speech_prob"] + 1e-9
+        g, r = got[0], ref["segments"][0]
+        ids_g, ids_r = [t.id for t in g["tokens"]], [t.id for t in r["tokens"]]
+        assert ids_g == ids_r, (b, ids_g, ids_r, ref["margins"])
+        n_identical += 1
+        assert (g["t0"], g["t1"], g["text"]) == (r["t0"], r["t1"], r["text"])
+        for tg, tr in zip(g["tokens"], r["tokens"]):
+            assert tg.tid == tr.tid
+            assert abs(tg.p - tr.p) <= 1e-3 * tr.p + 1e-9 and abs(tg.plog - tr.plog) <= 2e-3
+            assert abs(tg.pt - tr.pt) <= 1e-3 * tr.pt + 1e-9 and abs(tg.ptsum - tr.ptsum) <= 1e-3 * tr.ptsum + 1e-9
+            assert (tg.t0, tg.t1) == (tr.t0, tr.t1), (b, tg.id)
+            assert abs(tg.vlen - tr.vlen) < 1e-6
+            assert tg.t_dtw == tr.t_dtw, (b, tg.id, tg.t_dtw, tr.t_dtw)
+        assert g["token_text"] == [__import__("oracle.vocab", fromlist=["x"]).token_text(i, ctx.dims.n_vocab) for i in ids_g]
+    assert n_identical >= 3
+    st.close()
+    ctx.close()
+
+
+def test_full_single_buffer_f32_equals_i16(wdr):
+    ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    a = synth_audio(5, 9.0)
+    s1 = st.full(a)
+    s2 = st.full(a.astype(np.float32) / np.float32(32768.0))
+    assert [t.id for s in s1 for t in s["tokens"]] == [t.id for s in s2 for t in s["tokens"]]
+    assert [(s["t0"], s["t1"]) for s in s1] == [(s["t0"], s["t1"]) for s in s2]
+    assert st.lang_id() == 0
+    # too short (< 100 ms): nothing is decoded, as whisper.cpp returns early
+    assert st.full(np.zeros(800, np.int16)) == []
+    st.close()
+    ctx.close()
+
+
+def test_unsupported_params_fail_loudly(wdr):
+    ctx = wdr.Context("tiny.en", seed=1234)
+    st = ctx.create_state()
+    with pytest.raises(wdr.WdrError) as e:
+        st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=5))
+    assert e.value.code == -7
+    with pytest.raises(wdr.WdrError):
+        st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2))
+    with pytest.raises(wdr.WdrError):
+        st.full(np.zeros(16000, np.int16), st.full_params(language="auto"))
+    st.close()
+    ctx.close()

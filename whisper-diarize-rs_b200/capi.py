@@ -27,6 +27,31 @@ class ModelDims(C.Structure):
                                        "n_audio_ctx", "n_text_ctx", "is_multilingual")] + [("weight_bytes", C.c_int64)]
 
 
+class TokenData(C.Structure):
+    """== wdr_token_data == whisper_token_data (reference src/transcribe.rs:272-282)."""
+    _fields_ = [("id", C.c_int32), ("tid", C.c_int32), ("p", C.c_float), ("plog", C.c_float), ("pt", C.c_float), ("ptsum", C.c_float),
+                ("t0", C.c_int64), ("t1", C.c_int64), ("t_dtw", C.c_int64), ("vlen", C.c_float)]
+
+
+PROGRESS_CB = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+ABORT_CB = C.CFUNCTYPE(C.c_bool, C.c_void_p)
+
+
+class FullParams(C.Structure):
+    """== wdr_full_params (FullParams, reference src/transcribe.rs:20-87)."""
+    _fields_ = [("strategy", C.c_int), ("n_threads", C.c_int), ("n_max_text_ctx", C.c_int), ("offset_ms", C.c_int), ("duration_ms", C.c_int),
+                ("translate", C.c_int), ("no_context", C.c_int), ("no_timestamps", C.c_int), ("single_segment", C.c_int),
+                ("print_special", C.c_int), ("print_progress", C.c_int), ("print_realtime", C.c_int), ("print_timestamps", C.c_int),
+                ("token_timestamps", C.c_int), ("thold_pt", C.c_float), ("thold_ptsum", C.c_float), ("max_len", C.c_int),
+                ("split_on_word", C.c_int), ("max_tokens", C.c_int), ("audio_ctx", C.c_int), ("initial_prompt", C.c_char_p),
+                ("prompt_tokens", C.POINTER(C.c_int32)), ("prompt_n_tokens", C.c_int), ("language", C.c_char_p), ("detect_language", C.c_int),
+                ("suppress_blank", C.c_int), ("suppress_nst", C.c_int), ("temperature", C.c_float), ("max_initial_ts", C.c_float),
+                ("length_penalty", C.c_float), ("temperature_inc", C.c_float), ("entropy_thold", C.c_float), ("logprob_thold", C.c_float),
+                ("no_speech_thold", C.c_float), ("greedy_best_of", C.c_int), ("beam_size", C.c_int), ("beam_patience", C.c_float),
+                ("progress_callback", PROGRESS_CB), ("progress_callback_user_data", C.c_void_p), ("abort_callback", ABORT_CB),
+                ("abort_callback_user_data", C.c_void_p)]
+
+
 class WdrError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"wdr error {code}: {msg}")
@@ -92,6 +117,32 @@ def load():
     L.wdr_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.wdr_profile_collect.argtypes = [C.c_void_p, C.POINTER(C.c_double), i32p, C.c_int]
     L.wdr_encoder_attention_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.wdr_full_default_params.restype = FullParams
+    L.wdr_full_default_params.argtypes = [C.c_int]
+    L.wdr_full_with_state.argtypes = [C.c_void_p, C.c_void_p, FullParams, f32p, C.c_int]
+    L.wdr_full_with_state_i16.argtypes = [C.c_void_p, C.c_void_p, FullParams, i16p, C.c_int]
+    L.wdr_full_batch_i16.argtypes = [C.c_void_p, C.c_void_p, FullParams, C.c_void_p, C.c_int64, i32p, C.c_int]
+    L.wdr_full_n_segments_from_state.argtypes = [C.c_void_p]
+    for fn in ("chunk", "t0", "t1", "text", "no_speech_prob"):
+        getattr(L, f"wdr_full_get_segment_{fn}_from_state").argtypes = [C.c_void_p, C.c_int]
+    L.wdr_full_get_segment_t0_from_state.restype = C.c_int64
+    L.wdr_full_get_segment_t1_from_state.restype = C.c_int64
+    L.wdr_full_get_segment_text_from_state.restype = C.c_char_p
+    L.wdr_full_get_segment_no_speech_prob_from_state.restype = C.c_float
+    L.wdr_full_n_tokens_from_state.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_full_get_token_id_from_state.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.wdr_full_get_token_text_from_state.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.wdr_full_get_token_text_from_state.restype = C.c_char_p
+    L.wdr_full_get_token_data_from_state.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.wdr_full_get_token_data_from_state.restype = TokenData
+    L.wdr_full_lang_id_from_state.argtypes = [C.c_void_p]
+    L.wdr_lang_str.argtypes = [C.c_int]
+    L.wdr_lang_str.restype = C.c_char_p
+    L.wdr_lang_id.argtypes = [C.c_char_p]
+    L.wdr_token_to_str.argtypes = [C.c_void_p, C.c_int32]
+    L.wdr_token_to_str.restype = C.c_char_p
+    L.wdr_full_get_chunk_info_from_state.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
+    L.wdr_decode_teacher_forced.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, i32p, C.c_int, f32p, f32p]
     _lib = L
     return L
 
@@ -353,9 +404,99 @@ class State:
         names = ["mel", "mel_aux", "gemm", "attention", "layernorm", "decoder", "dtw", "other"]
         return {n: {"ms": ms[i], "records": ln[i]} for i, n in enumerate(names)}
 
+    # ---- full transcription (state.full, reference src/transcribe.rs:389; accessors :393-412, :252-282) ----
+    def full_params(self, strategy=0, **kw):
+        """FullParams as setup_params builds them (src/transcribe.rs:20-87): suppress_blank, token_timestamps, single_segment."""
+        p = load().wdr_full_default_params(strategy)
+        p.print_special = 0
+        p.print_progress = 1
+        p.print_realtime = 0
+        p.print_timestamps = 0
+        p.suppress_blank = 1
+        p.token_timestamps = 1
+        p.single_segment = 1
+        for k, v in kw.items():
+            setattr(p, k, v.encode() if isinstance(v, str) else v)
+        return p
+
+    def full(self, pcm, params=None):
+        """state.full on ONE buffer of <= 30 s (float32 in [-1,1) or int16)."""
+        p = params if params is not None else self.full_params()
+        pcm = np.asarray(pcm)
+        if pcm.dtype == np.int16:
+            x = _np(pcm, np.int16)
+            _check(load().wdr_full_with_state_i16(self.ctx._h, self._h, p, _p(x, i16p), len(x)))
+        else:
+            x = _np(pcm, np.float32)
+            _check(load().wdr_full_with_state(self.ctx._h, self._h, p, _p(x, f32p), len(x)))
+        return self.segments()
+
+    def full_batch(self, pcm_i16, n_valid=None, params=None):
+        """Sharded mode: pcm_i16[B, stride] host array (or a host pointer + (n_chunks, stride)) -> segments of all chunks."""
+        p = params if params is not None else self.full_params()
+        x = _np(pcm_i16, np.int16)
+        assert x.ndim == 2
+        nv = None if n_valid is None else _np(n_valid, np.int32)
+        _check(load().wdr_full_batch_i16(self.ctx._h, self._h, p, x.ctypes.data, x.shape[1], None if nv is None else _p(nv, i32p), x.shape[0]))
+        return self.segments()
+
+    def full_batch_ptr(self, pcm_host_ptr, n_chunks, chunk_stride=480000, params=None):
+        p = params if params is not None else self.full_params()
+        _check(load().wdr_full_batch_i16(self.ctx._h, self._h, p, pcm_host_ptr, chunk_stride, None, n_chunks))
+        return load().wdr_full_n_segments_from_state(self._h)
+
+    def n_segments(self):
+        return load().wdr_full_n_segments_from_state(self._h)
+
+    def segments(self):
+        L = load()
+        out = []
+        for i in range(L.wdr_full_n_segments_from_state(self._h)):
+            n = L.wdr_full_n_tokens_from_state(self._h, i)
+            toks = [L.wdr_full_get_token_data_from_state(self._h, i, j) for j in range(n)]
+            texts = [L.wdr_full_get_token_text_from_state(self.ctx._h, self._h, i, j).decode("utf-8", "replace") for j in range(n)]
+            out.append(dict(chunk=L.wdr_full_get_segment_chunk_from_state(self._h, i), t0=L.wdr_full_get_segment_t0_from_state(self._h, i),
+                            t1=L.wdr_full_get_segment_t1_from_state(self._h, i),
+                            text=L.wdr_full_get_segment_text_from_state(self._h, i).decode("utf-8", "replace"),
+                            no_speech_prob=L.wdr_full_get_segment_no_speech_prob_from_state(self._h, i), tokens=toks, token_text=texts))
+        return out
+
+    def chunk_info(self, i):
+        info = np.zeros(8, np.int32)
+        nsp = C.c_float(0)
+        _check(load().wdr_full_get_chunk_info_from_state(self._h, i, _p(info, i32p), C.byref(nsp)))
+        keys = ["seek_delta", "failed", "completed", "n_sampled", "has_ts", "result_len", "seek_end", "n_segments"]
+        d = {k: int(v) for k, v in zip(keys, info)}
+        d["no_speech_prob"] = float(nsp.value)
+        return d
+
+    def lang_id(self):
+        return load().wdr_full_lang_id_from_state(self._h)
+
+    def decode_teacher_forced(self, seq, enc=None, want_logits=True, want_aheads=False, n_aheads=0):
+        """Stage-level: teacher-forced decoder pass. seq[B, n_seq]; enc[B,1500,d] host (None = keep the state's encoder output)."""
+        sq = _np(seq, np.int32)
+        B, n_seq = sq.shape
+        nv = self.ctx.dims.n_vocab
+        e = None if enc is None else _np(enc, np.float32)
+        logits = np.empty((B, n_seq, nv), np.float32) if want_logits else None
+        ah = np.empty((B, n_aheads, n_seq, 1500), np.float32) if want_aheads else None
+        _check(load().wdr_decode_teacher_forced(self.ctx._h, self._h, None if e is None else _p(e, f32p), B, _p(sq, i32p), n_seq,
+                                                None if logits is None else _p(logits, f32p), None if ah is None else _p(ah, f32p)))
+        return logits, ah
+
     def encode_chunks_dev(self, pcm_ptr, chunk_stride, n_chunks, out_ptr, n_valid_ptr=None, stream=0):
         _check(load().wdr_encode_chunks_i16_dev(self.ctx._h, self._h, pcm_ptr, chunk_stride, n_valid_ptr, n_chunks, out_ptr, stream))
 
 
 def encoder_attention_dev(qk_ptr, vt_ptr, ldt, n_chunks, T, n_head, d_model, out_ptr, stream=0):
     _check(load().wdr_encoder_attention_dev(qk_ptr, vt_ptr, ldt, n_chunks, T, n_head, d_model, out_ptr, stream))
+
+
+def lang_str(i):
+    r = load().wdr_lang_str(int(i))
+    return r.decode() if r else None
+
+
+def lang_id(s):
+    return load().wdr_lang_id(s.encode())

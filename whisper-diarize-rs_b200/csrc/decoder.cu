@@ -1,0 +1,651 @@
+// decoder.cu — the KV-cached Whisper text decoder, batched over 30 s windows (one token per window per step).
+//
+// Replaces whisper.cpp `whisper_build_graph_cross` / `whisper_decode_internal` / `whisper_process_logits` /
+// `whisper_sample_token`, which `state.full` runs per window (reference src/transcribe.rs:389,
+// configured by setup_params src/transcribe.rs:20-87).
+//
+// A step advances all B <= 128 windows by one token, so every linear layer is a weight-streaming GEMM with a single
+// 128-row M tile: the tcgen05 GEMM runs with BN = 64 tiles and split-K so that >= ~148 CTAs stream the weights, writing
+// fp32 partial sums that the consumer kernel reduces in a fixed order (deterministic):
+//   dec_ln        x += bias + sum(partials); h = bf16(LayerNorm(x))                      one CTA per window
+//   dec_self_attn q|k|v = sum(partials) + bias; append k,v (bf16) to the self cache; softmax(q K^T) V over <= 448 positions
+//   dec_cross_attn q = sum(partials) + bias; streams K_c / V_c (2 x 1500 x 64 bf16 per (window, head)) with 128-bit loads —
+//                 the HBM-bound kernel of the decoder; optionally stores the alignment heads' probabilities (DTW pass)
+//   dec_bias_gelu ff = bf16(gelu(sum(partials) + bias))
+//   dec_sample    logit rules, log-softmax, timestamp-mass rule, greedy argmax, token statistics, per-window bookkeeping
+// Precision: weights and the cross-KV cache are bf16 (whisper.cpp: f16).  Activations that feed a GEMM (LayerNorm, attention and
+// GELU outputs) are stored as a (hi, lo) bf16 pair = 16 mantissa bits and both halves multiply the same weight tile (dual-A
+// GEMM: weights are read once, so the weight-streaming cost is unchanged); the self-KV cache, the residual stream, softmax and
+// LayerNorm statistics are fp32.  A single-bf16 activation path decorrelates from an fp32 decoder within a few layers (every
+// rounding flip is a 2^-8 kick that the next rounding amplifies), which makes greedy argmax flip on ~3 % of the tokens of a
+// random-weight model; at 16 bits the logits agree with the fp32 restatement to ~1e-5 and token sequences match.
+#include <math.h>
+#include <stdlib.h>
+#include <algorithm>
+#include "common.cuh"
+#include "decoder.cuh"
+#include "gemm.cuh"
+
+namespace wdr {
+
+constexpr int kT = WDR_AUDIO_CTX;
+
+// ---------------------------------------------------------------------------------------------------
+// block-wide reductions (blockDim.x multiple of 32, <= 1024)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < nw) ? red[l] : 0.0f;
+    t = warp_sum(t);
+    return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    v = warp_max(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = (l < nw) ? red[l] : -INFINITY;
+    t = warp_max(t);
+    return t;
+}
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long* red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = u > v ? u : v;
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    unsigned long long t = (l < nw) ? red[l] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long u = __shfl_xor_sync(0xffffffffu, t, o);
+        t = u > t ? u : t;
+    }
+    return t;
+}
+
+__device__ __forceinline__ float gelu_tanh_exact(float x) {
+    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
+}
+
+// activation v as a (hi, lo) bf16 pair: hi at dst[idx], lo at dst[idx + lo_off]
+__device__ __forceinline__ void store_split(__nv_bfloat16* __restrict__ dst, int64_t lo_off, int64_t idx, float v) {
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    dst[idx] = hi;
+    dst[idx + lo_off] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// sum of the split-K partials of element (row, col), in split order
+__device__ __forceinline__ float part_sum(const float* __restrict__ part, int n_splits, int64_t split_stride, int64_t idx) {
+    float a = part[idx];
+    for (int s = 1; s < n_splits; s++) a += part[(int64_t)s * split_stride + idx];
+    return a;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void dec_embed_kernel(const int32_t* __restrict__ seq, int pos, const __nv_bfloat16* __restrict__ tok_emb,
+                                 const float* __restrict__ pos_emb, int d, int n_vocab, float* __restrict__ x) {
+    const int b = blockIdx.x;
+    int tok = seq[b * kDecSeqCap + pos];
+    if (tok < 0 || tok >= n_vocab) tok = 0;
+    for (int i = threadIdx.x; i < d; i += blockDim.x)
+        x[(int64_t)b * d + i] = __bfloat162float(tok_emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
+}
+
+// x (+= bias + partials) -> h = bf16(LN(x)).  One CTA (256 threads) per window row; d <= 1280.
+__global__ void __launch_bounds__(256)
+dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_splits, int64_t split_stride, int ldp,
+              const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ bta, __nv_bfloat16* __restrict__ h, int64_t lo_off,
+              int d) {
+    __shared__ float red[32];
+    const int row = blockIdx.x, tid = threadIdx.x;
+    float v[5];
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int i = tid + k * 256;
+        v[k] = 0.0f;
+        if (i < d) {
+            float a = x[(int64_t)row * d + i];
+            if (part) {
+                const float add = part_sum(part, n_splits, split_stride, (int64_t)row * ldp + i) + bias[i];
+                a += add;
+                x[(int64_t)row * d + i] = a;
+            }
+            v[k] = a;
+            s += a;
+        }
+    }
+    const float mean = block_sum(s, red) / (float)d;
+    float q = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int i = tid + k * 256;
+        if (i < d) { const float c = v[k] - mean; q += c * c; }
+    }
+    const float var = block_sum(q, red) / (float)d;
+    const float rstd = 1.0f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const int i = tid + k * 256;
+        if (i < d) store_split(h, lo_off, (int64_t)row * d + i, (v[k] - mean) * rstd * g[i] + bta[i]);
+    }
+}
+
+// self-attention of one (head, window) at position pos.  part: [S][B][3d] partials of the fused QKV GEMM.
+__global__ void __launch_bounds__(128)
+dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
+                     float* __restrict__ sk, float* __restrict__ sv, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off) {
+    __shared__ float q[64];
+    __shared__ float p[kDecSeqCap];
+    __shared__ float red[32];
+    __shared__ float acc2[2][64];
+    const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    float* K = sk + (int64_t)b * kDecSeqCap * d + hh * 64;
+    float* V = sv + (int64_t)b * kDecSeqCap * d + hh * 64;
+    if (tid < 64) {
+        const int64_t base = (int64_t)b * 3 * d + hh * 64 + tid;
+        q[tid] = part_sum(part, n_splits, split_stride, base) + b_qkv[hh * 64 + tid];
+        const float kv = part_sum(part, n_splits, split_stride, base + d) + b_qkv[d + hh * 64 + tid];
+        const float vv = part_sum(part, n_splits, split_stride, base + 2 * d) + b_qkv[2 * d + hh * 64 + tid];
+        K[(int64_t)pos * d + tid] = kv;
+        V[(int64_t)pos * d + tid] = vv;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    for (int t = tid; t <= pos; t += 128) {
+        const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)t * d);
+        float a = 0.0f;
+#pragma unroll
+        for (int c4 = 0; c4 < 16; c4++) {
+            const float4 f = kr[c4];
+            a = fmaf(q[c4 * 4], f.x, a);
+            a = fmaf(q[c4 * 4 + 1], f.y, a);
+            a = fmaf(q[c4 * 4 + 2], f.z, a);
+            a = fmaf(q[c4 * 4 + 3], f.w, a);
+        }
+        a *= 0.125f;
+        p[t] = a;
+        mx = fmaxf(mx, a);
+    }
+    mx = block_max(mx, red);
+    float sum = 0.0f;
+    for (int t = tid; t <= pos; t += 128) {
+        const float e = expf(p[t] - mx);
+        p[t] = e;
+        sum += e;
+    }
+    sum = block_sum(sum, red);
+    const float inv = 1.0f / sum;
+    __syncthreads();
+    const int c = tid & 63, half = tid >> 6;
+    float a = 0.0f;
+    for (int t = half; t <= pos; t += 2) a = fmaf(p[t] * inv, V[(int64_t)t * d + c], a);
+    acc2[half][c] = a;
+    __syncthreads();
+    if (tid < 64) store_split(att, lo_off, (int64_t)b * d + hh * 64 + tid, acc2[0][tid] + acc2[1][tid]);
+}
+
+// cross-attention of one (head, window): q from the cross-query GEMM partials; K_c/V_c rows are 64 bf16 (128 B) at row
+// stride 2d.  8 lanes x 16 B cover one row; a warp covers 4 rows per load, the CTA (8 warps) 32 rows.
+__global__ void __launch_bounds__(256)
+dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
+                      const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
+                      const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
+                      float* __restrict__ aw, const int64_t* __restrict__ aw_off, const int32_t* __restrict__ aw_T,
+                      const int32_t* __restrict__ aw_A, int pos) {
+    __shared__ float q[64];
+    __shared__ float p[kT + 4];
+    __shared__ float red[32];
+    __shared__ float accs[8][64];
+    const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5, g = lane & 7, r = lane >> 3;
+    if (tid < 64) q[tid] = part_sum(part, n_splits, split_stride, (int64_t)b * d + hh * 64 + tid) + b_q[hh * 64 + tid];
+    __syncthreads();
+    float q8[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) q8[j] = q[g * 8 + j];
+    const __nv_bfloat16* Kb = ckv + (int64_t)b * kT * 2 * d + hh * 64 + g * 8;
+    const __nv_bfloat16* Vb = Kb + d;
+    const int64_t rs = 2 * (int64_t)d;
+    // ---- scores ----
+    float mx = -INFINITY;
+    for (int t0 = warp * 4 + r; t0 < kT; t0 += 128) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = t0 + k * 32;
+            u[k] = (t < kT) ? __ldg(reinterpret_cast<const uint4*>(Kb + (int64_t)t * rs)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = t0 + k * 32;
+            const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __bfloat1622float2(e[j]);
+                a = fmaf(q8[2 * j], f.x, a);
+                a = fmaf(q8[2 * j + 1], f.y, a);
+            }
+            a += __shfl_xor_sync(0xffffffffu, a, 1);
+            a += __shfl_xor_sync(0xffffffffu, a, 2);
+            a += __shfl_xor_sync(0xffffffffu, a, 4);
+            a *= 0.125f;
+            if (t < kT) {
+                if (g == 0) p[t] = a;
+                mx = fmaxf(mx, a);
+            }
+        }
+    }
+    mx = block_max(mx, red);
+    float sum = 0.0f;
+    for (int t = tid; t < kT; t += 256) {
+        const float e = expf(p[t] - mx);
+        p[t] = e;
+        sum += e;
+    }
+    sum = block_sum(sum, red);
+    const float inv = 1.0f / sum;
+    for (int t = tid; t < kT; t += 256) p[t] *= inv;
+    __syncthreads();
+    const int ahead = ahead_map ? ahead_map[hh] : -1;
+    if (ahead >= 0) {
+        const int T_b = aw_T[b], A_b = aw_A[b];
+        if (pos < T_b) {
+            float* dst = aw + aw_off[b] + ((int64_t)ahead * T_b + pos) * A_b;
+            for (int t = tid; t < A_b; t += 256) dst[t] = p[t];
+        }
+    }
+    // ---- P V ----
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = 0.0f;
+    for (int t0 = warp * 4 + r; t0 < kT; t0 += 128) {
+        uint4 u[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = t0 + k * 32;
+            u[k] = (t < kT) ? __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)t * rs)) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = t0 + k * 32;
+            const float pt = (t < kT) ? p[t] : 0.0f;
+            const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&u[k]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __bfloat1622float2(e[j]);
+                acc[2 * j] = fmaf(pt, f.x, acc[2 * j]);
+                acc[2 * j + 1] = fmaf(pt, f.y, acc[2 * j + 1]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (r == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) accs[warp][g * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float a = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) a += accs[w][tid];
+        store_split(att, lo_off, (int64_t)b * d + hh * 64 + tid, a);
+    }
+}
+
+__global__ void dec_bias_gelu_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ bias,
+                                     int n, int64_t total, __nv_bfloat16* __restrict__ out, int64_t lo_off) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(e % n);
+        store_split(out, lo_off, e, gelu_tanh_exact(part_sum(part, n_splits, split_stride, e) + bias[j]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// whisper_process_logits + whisper_sample_token(best) + the decoder bookkeeping of whisper_full's inner loop
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSampThreads = 1024;
+constexpr int kSampPer = 51;  // 51 * 1024 = 52224 >= n_vocab
+
+__global__ void __launch_bounds__(kSampThreads, 1)
+dec_sample_kernel(const float* __restrict__ logits, int64_t ldv, DecWinState* __restrict__ win, wdr_token_data* __restrict__ tokens,
+                  int32_t* __restrict__ seq, int pos, const SampleParams sp, int32_t* __restrict__ done_count) {
+    __shared__ float red[32];
+    __shared__ unsigned long long red64[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    DecWinState st = win[b];
+    if (st.completed || st.failed) return;
+    const int n = sp.n_vocab;
+    const int n_cur = st.n_cur;
+    const bool is_initial = n_cur == 0;
+    const wdr_token_data* tk = tokens + (int64_t)b * kDecMaxTokens;
+    const bool last_was_ts = n_cur > 0 && tk[n_cur - 1].id >= sp.beg;
+    const bool penult_was_ts = n_cur < 2 || tk[n_cur - 2].id >= sp.beg;
+    const float* lg = logits + (int64_t)b * ldv;
+    float v[kSampPer];
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        v[k] = (i < n) ? lg[i] : -INFINITY;
+    }
+    // no_speech_prob: softmax over the unfiltered logits, taken after the prompt (whisper_full)
+    if (is_initial) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kSampPer; k++) m = fmaxf(m, v[k]);
+        m = block_max(m, red);
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) s += expf(v[k] - m);
+        s = block_sum(s, red);
+        if (tid == 0) st.no_speech_prob = expf(lg[sp.nosp] - (logf(s) + m));
+    }
+    // ---- logit rules ----
+    const int ts_floor = st.has_ts ? sp.beg + st.seek_delta / 2 : sp.beg;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        bool mask = false;
+        if (sp.suppress_blank && is_initial && (i == sp.eot || i == sp.space)) mask = true;
+        if (i == sp.not_ || i == sp.sot || i == sp.nosp || i == sp.solm || i == sp.translate || i == sp.transcribe || i == sp.prev) mask = true;
+        if (sp.no_timestamps && i >= sp.beg) mask = true;
+        if (i >= sp.lang0 && i < sp.lang0 + sp.n_langs) mask = true;
+        if (last_was_ts) {
+            if (penult_was_ts) { if (i >= sp.beg) mask = true; }
+            else { if (i < sp.eot) mask = true; }
+        }
+        if (is_initial && sp.initial_tid0 >= 0 && i >= sp.beg + sp.initial_tid0 + 1) mask = true;
+        if (i >= sp.beg && i < ts_floor) mask = true;
+        if (mask) v[k] = -INFINITY;
+    }
+    // ---- log-softmax ----
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) m = fmaxf(m, v[k]);
+    m = block_max(m, red);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) s += expf(v[k] - m);
+    s = block_sum(s, red);
+    const float lse = logf(s) + m;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) v[k] -= lse;  // v = logprobs
+    // ---- if the probability mass on timestamps beats every text token, sample a timestamp ----
+    float tmax = -INFINITY, xmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        if (i >= sp.beg) tmax = fmaxf(tmax, v[k]); else xmax = fmaxf(xmax, v[k]);
+    }
+    tmax = block_max(tmax, red);
+    xmax = block_max(xmax, red);
+    float tsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        if (i >= sp.beg && v[k] > -INFINITY) tsum += expf(v[k] - tmax);
+    }
+    tsum = block_sum(tsum, red);
+    const float ts_logprob = tsum > 0.0f ? logf(tsum) + tmax : -INFINITY;
+    const bool mask_text = ts_logprob > xmax;
+    // ---- probabilities, timestamp statistics, greedy argmax (first maximum wins) ----
+    float sum_ts = 0.0f;
+    unsigned long long best_ts = 0ull, best_all = 0ull;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        if (mask_text && i < sp.beg) v[k] = -INFINITY;
+        const float pr = v[k] > -INFINITY ? expf(v[k]) : 0.0f;
+        if (pr > 0.0f) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(pr) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+            if (i >= sp.beg) { sum_ts += pr; best_ts = key > best_ts ? key : best_ts; }
+            best_all = key > best_all ? key : best_all;
+        }
+    }
+    sum_ts = block_sum(sum_ts, red);
+    best_ts = block_max_u64(best_ts, red64);
+    best_all = block_max_u64(best_all, red64);
+    if (tid != 0) return;
+    wdr_token_data td;
+    td.id = 0; td.tid = 0; td.p = 0.0f; td.plog = 0.0f; td.pt = 0.0f; td.ptsum = 0.0f; td.t0 = -1; td.t1 = -1; td.t_dtw = -1; td.vlen = 0.0f;
+    {
+        double max_ts = 0.0;
+        if (best_ts) { td.tid = (int)(0xFFFFFFFFu - (unsigned)(best_ts & 0xFFFFFFFFull)); max_ts = (double)__uint_as_float((unsigned)(best_ts >> 32)); }
+        td.pt = (float)(max_ts / ((double)sum_ts + 1e-10));
+        td.ptsum = sum_ts;
+    }
+    if (best_all) {
+        td.id = (int)(0xFFFFFFFFu - (unsigned)(best_all & 0xFFFFFFFFull));
+        td.p = __uint_as_float((unsigned)(best_all >> 32));
+        td.plog = logf(td.p);  // replaced below by the exact logprob
+    }
+    // plog is logprobs[id]; recompute it from the logit (thread 0 does not hold that element): logit - lse (masking never selects a masked id)
+    td.plog = lg[td.id] - lse;
+    if (td.id >= sp.beg) { td.tid = td.id; td.pt = td.p; }
+    // ---- decoder bookkeeping (whisper_full inner loop, one decoder, T = 0) ----
+    const int i = n_cur;
+    tokens[(int64_t)b * kDecMaxTokens + n_cur] = td;
+    st.n_cur = n_cur + 1;
+    bool done = false;
+    if (td.id > sp.beg) {
+        const int sd_new = 2 * (td.id - sp.beg);
+        if (st.has_ts && st.seek_delta > sd_new && st.result_len < i) { st.failed = 1; done = true; }
+        else { st.seek_delta = sd_new; st.result_len = i + 1; st.has_ts = 1; }
+    }
+    if (!done && (td.id == sp.eot || (st.has_ts && st.seek + st.seek_delta + sp.delta_min >= st.seek_end))) {
+        bool fail = false;
+        if (st.result_len == 0 && !sp.no_timestamps) {
+            if (st.seek + st.seek_delta + sp.delta_min >= st.seek_end) st.result_len = i + 1;
+            else fail = true;
+        }
+        if (fail) st.failed = 1;
+        else {
+            if (sp.single_segment || sp.no_timestamps) { st.result_len = i + 1; st.seek_delta = 100 * 30; }
+            st.completed = 1;
+        }
+        done = true;
+    }
+    if (!done && i == sp.n_max - 1 && (st.result_len == 0 || st.seek_delta < 100 * 30 / 2)) { st.failed = 1; done = true; }
+    if (!done && pos + 1 < kDecSeqCap) seq[b * kDecSeqCap + pos + 1] = td.id;
+    win[b] = st;
+    if (done) atomicAdd(done_count, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+void DecoderWorkspace::release() {
+    for (void* p : {(void*)enc_bf16, (void*)sk, (void*)sv, (void*)x, (void*)h, (void*)att, (void*)ff, (void*)part, (void*)logits, (void*)seq,
+                    (void*)tokens, (void*)win, (void*)done_count, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
+        if (p) cudaFree(p);
+    for (auto p : ckv) if (p) cudaFree(p);
+    *this = DecoderWorkspace();
+}
+
+int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
+    if (B <= cap_B) return WDR_OK;
+    WDR_REQUIRE(B <= kDecMaxBatch, "decode batch exceeds 128 windows");
+    release();
+    const WhisperArch& a = ctx->arch;
+    d = a.d; n_layer = a.n_dec_layer; n_head = a.n_head;
+    ldv = (a.n_vocab + 7) / 8 * 8;
+    WDR_CUDA_TRY(cudaMalloc(&enc_bf16, sizeof(__nv_bfloat16) * (size_t)B * kT * d));
+    ckv.assign(n_layer, nullptr);
+    for (int l = 0; l < n_layer; l++) WDR_CUDA_TRY(cudaMalloc(&ckv[l], sizeof(__nv_bfloat16) * (size_t)B * kT * 2 * d));
+    const size_t skv = (size_t)n_layer * B * kDecSeqCap * d;
+    WDR_CUDA_TRY(cudaMalloc(&sk, sizeof(float) * skv));
+    WDR_CUDA_TRY(cudaMalloc(&sv, sizeof(float) * skv));
+    WDR_CUDA_TRY(cudaMalloc(&x, sizeof(float) * (size_t)B * d));
+    WDR_CUDA_TRY(cudaMalloc(&h, sizeof(__nv_bfloat16) * (size_t)2 * B * d));    // (hi, lo) planes
+    WDR_CUDA_TRY(cudaMalloc(&att, sizeof(__nv_bfloat16) * (size_t)2 * B * d));
+    WDR_CUDA_TRY(cudaMalloc(&ff, sizeof(__nv_bfloat16) * (size_t)2 * B * 4 * d));
+    part_elems = (size_t)32 * B * 4 * d;
+    WDR_CUDA_TRY(cudaMalloc(&part, sizeof(float) * part_elems));
+    WDR_CUDA_TRY(cudaMalloc(&logits, sizeof(float) * (size_t)B * ldv));
+    WDR_CUDA_TRY(cudaMalloc(&seq, sizeof(int32_t) * (size_t)B * kDecSeqCap));
+    WDR_CUDA_TRY(cudaMalloc(&tokens, sizeof(wdr_token_data) * (size_t)B * kDecMaxTokens));
+    WDR_CUDA_TRY(cudaMalloc(&win, sizeof(DecWinState) * B));
+    WDR_CUDA_TRY(cudaMalloc(&done_count, sizeof(int32_t)));
+    WDR_CUDA_TRY(cudaMalloc(&ahead_map, sizeof(int32_t) * n_layer * n_head));
+    WDR_CUDA_TRY(cudaMalloc(&aw_off, sizeof(int64_t) * B));
+    WDR_CUDA_TRY(cudaMalloc(&aw_T, sizeof(int32_t) * B));
+    WDR_CUDA_TRY(cudaMalloc(&aw_A, sizeof(int32_t) * B));
+    {
+        std::vector<int32_t> map((size_t)n_layer * n_head, -1);
+        n_aheads = (int)ctx->aheads.size();
+        for (int i = 0; i < n_aheads; i++) {
+            const int l = ctx->aheads[i].first, hd = ctx->aheads[i].second;
+            if (l < n_layer && hd < n_head) map[(size_t)l * n_head + hd] = i;
+        }
+        WDR_CUDA_TRY(cudaMemcpy(ahead_map, map.data(), sizeof(int32_t) * map.size(), cudaMemcpyHostToDevice));
+    }
+    cap_B = B;
+    return WDR_OK;
+}
+
+int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaStream_t st, Profiler* prof) {
+    const int d = ctx->arch.d;
+    for (int l = 0; l < ctx->arch.n_dec_layer; l++) {
+        const DecLayerW& e = ctx->w.dec[l];
+        GemmDesc g;
+        g.A = ws.enc_bf16; g.a_row_stride = d; g.rows_per_batch = B * kT; g.n_batch = 1;
+        g.W = e.w_ckv; g.ldw = d; g.N = 2 * d; g.K = d;
+        g.epilogue = EPI_BIAS_BF16; g.out = ws.ckv[l]; g.ldc = 2 * d; g.bias = e.b_ckv;
+        ProfScope ps(prof, KC_GEMM, st);
+        int rc = gemm_bf16(g, st);
+        if (rc != WDR_OK) return rc;
+    }
+    return WDR_OK;
+}
+
+// splits so that tiles * splits covers the SMs, every split owning the same number (>= 1) of 64-wide k-blocks
+static int pick_split(int K, int N) {
+    const int num_kb = (K + 63) / 64, tiles = (N + 63) / 64;
+    int want = (148 + tiles - 1) / tiles;
+    if (want > 16) want = 16;
+    if (want > num_kb) want = num_kb;
+    for (int s = want; s >= 1; s--) {
+        const int per = (num_kb + s - 1) / s;
+        if ((num_kb + per - 1) / per == s) return s;
+    }
+    return 1;
+}
+
+struct SkinnyGemm {
+    int splits;
+    int64_t split_stride;
+};
+
+// part[s][B][N] = A[B][K] * W[N][K]^T over K-slice s
+static int skinny_gemm(const __nv_bfloat16* A, int B, const __nv_bfloat16* W, int N, int K, DecoderWorkspace& ws, SkinnyGemm* out,
+                       cudaStream_t st, Profiler* prof) {
+    GemmDesc g;
+    g.A = A; g.a_row_stride = K; g.rows_per_batch = B; g.n_batch = 1;
+    g.W = W; g.ldw = K; g.N = N; g.K = K;
+    g.epilogue = EPI_F32; g.out = ws.part; g.ldc = N; g.bn = 64;
+    g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * K;
+    g.split_k = pick_split(K, N);
+    g.split_stride = (int64_t)B * N;
+    if ((size_t)g.split_k * B * N > ws.part_elems) { set_error("decoder: split-K workspace too small"); return WDR_ERR_INVALID; }
+    out->splits = g.split_k;
+    out->split_stride = g.split_stride;
+    ProfScope ps(prof, KC_DECODER, st);
+    return gemm_bf16(g, st);
+}
+
+int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, bool capture, cudaStream_t st, Profiler* prof) {
+    const WhisperArch& a = ctx->arch;
+    const WhisperWeights& w = ctx->w;
+    const int d = a.d, H = a.n_head, L = a.n_dec_layer;
+    WDR_REQUIRE(pos >= 0 && pos < kDecSeqCap && B > 0 && B <= ws.cap_B, "decoder_step: bad position or batch");
+    int rc;
+    SkinnyGemm sg{1, 0};
+    const float* pend_bias = nullptr;  // bias of the GEMM whose partials the next dec_ln folds into x
+    bool pending = false;
+    {
+        ProfScope ps(prof, KC_DECODER, st);
+        dec_embed_kernel<<<B, 128, 0, st>>>(ws.seq, pos, w.tok_emb, w.dec_pos, d, a.n_vocab, ws.x);
+        WDR_LAUNCH_CHECK();
+    }
+    auto ln = [&](const float* g, const float* b) -> int {
+        ProfScope ps(prof, KC_DECODER, st);
+        dec_ln_kernel<<<B, 256, 0, st>>>(ws.x, pending ? ws.part : nullptr, sg.splits, sg.split_stride, d, pend_bias, g, b, ws.h, (int64_t)ws.cap_B * d, d);
+        WDR_LAUNCH_CHECK();
+        pending = false;
+        return WDR_OK;
+    };
+    static const int dbg_layers = getenv("WDR_DEBUG_DEC_LAYERS") ? atoi(getenv("WDR_DEBUG_DEC_LAYERS")) : 1 << 30;  // bring-up aid: truncate the stack
+    for (int l = 0; l < L && l < dbg_layers; l++) {
+        const DecLayerW& e = w.dec[l];
+        if ((rc = ln(e.ln1_g, e.ln1_b)) != WDR_OK) return rc;
+        if ((rc = skinny_gemm(ws.h, B, e.w_qkv, 3 * d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_DECODER, st);
+            dec_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_qkv,
+                                                               ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos, d, ws.att,
+                                                               (int64_t)ws.cap_B * d);
+            WDR_LAUNCH_CHECK();
+        }
+        if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
+        pending = true; pend_bias = e.b_o;
+        if ((rc = ln(e.ln2_g, e.ln2_b)) != WDR_OK) return rc;
+        if ((rc = skinny_gemm(ws.h, B, e.w_cq, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_DECODER, st);
+            dec_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d,
+                                                                capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T,
+                                                                ws.aw_A, pos);
+            WDR_LAUNCH_CHECK();
+        }
+        if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
+        pending = true; pend_bias = e.b_co;
+        if ((rc = ln(e.ln3_g, e.ln3_b)) != WDR_OK) return rc;
+        if ((rc = skinny_gemm(ws.h, B, e.w_fc1, 4 * d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_DECODER, st);
+            const int64_t total = (int64_t)B * 4 * d;
+            dec_bias_gelu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_fc1, 4 * d, total, ws.ff,
+                                                                                    (int64_t)ws.cap_B * 4 * d);
+            WDR_LAUNCH_CHECK();
+        }
+        if ((rc = skinny_gemm(ws.ff, B, e.w_fc2, d, 4 * d, ws, &sg, st, prof)) != WDR_OK) return rc;
+        pending = true; pend_bias = e.b_fc2;
+    }
+    if (want_logits) {
+        if ((rc = ln(w.dec_ln_g, w.dec_ln_b)) != WDR_OK) return rc;
+        GemmDesc g;
+        g.A = ws.h; g.a_row_stride = d; g.rows_per_batch = B; g.n_batch = 1;
+        g.W = w.tok_emb; g.ldw = d; g.N = (int)ws.ldv; g.K = d;
+        g.epilogue = EPI_F32; g.out = ws.logits; g.ldc = ws.ldv; g.bn = 64;
+        g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * d;
+        ProfScope ps(prof, KC_DECODER, st);
+        if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
+    }
+    return WDR_OK;
+}
+
+int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof) {
+    WDR_REQUIRE(sp.n_vocab <= kSampThreads * kSampPer, "vocabulary larger than the sampler's register tile");
+    ProfScope ps(prof, KC_DECODER, st);
+    dec_sample_kernel<<<B, kSampThreads, 0, st>>>(ws.logits, ws.ldv, ws.win, ws.tokens, ws.seq, pos, sp, ws.done_count);
+    WDR_LAUNCH_CHECK();
+    return WDR_OK;
+}
+
+}  // namespace wdr

@@ -1,0 +1,69 @@
+// decoder.cuh — KV-cached Whisper decoder over a batch of windows: workspace and entry points (decoder.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <vector>
+#include "model.cuh"
+#include "profile.cuh"
+#include "vocab.cuh"
+
+namespace wdr {
+
+constexpr int kDecMaxBatch = 128;   // windows per decode batch = one 128-row M tile of the tcgen05 GEMM
+constexpr int kDecMaxTokens = 224;  // sampled tokens kept per window (n_text_ctx/2)
+constexpr int kDecSeqCap = WDR_TEXT_CTX;
+
+// per-window decoder state (whisper_decoder + whisper_sequence fields the loop needs), device resident
+struct DecWinState {
+    int32_t n_cur, has_ts, seek_delta, result_len, failed, completed, seek, seek_end;
+    float no_speech_prob;
+    int32_t pad[3];
+};
+
+struct SampleParams {
+    int n_vocab, eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, lang0, n_langs, space;
+    int suppress_blank, no_timestamps, single_segment, delta_min, n_max;
+    int initial_tid0;  // round(max_initial_ts / 0.02), or -1 when max_initial_ts <= 0
+};
+
+struct DecoderWorkspace {
+    int cap_B = 0;
+    int d = 0, n_layer = 0, n_head = 0;
+    int64_t ldv = 0;                   // logits row stride (n_vocab rounded up to 8)
+    __nv_bfloat16* enc_bf16 = nullptr; // [B][1500][d]   ln_post output, the cross-KV GEMM's A operand
+    std::vector<__nv_bfloat16*> ckv;   // per layer [B*1500][2d]  (key | value), bf16
+    float* sk = nullptr;               // [L][B][448][d]  self-attention keys / values, fp32
+    float* sv = nullptr;
+    float* x = nullptr;                // [B][d]  residual stream
+    __nv_bfloat16* h = nullptr;        // [2][B][d]   (hi, lo) planes of the LayerNorm output
+    __nv_bfloat16* att = nullptr;      // [2][B][d]
+    __nv_bfloat16* ff = nullptr;       // [2][B][4d]
+    float* part = nullptr;             // split-K partial sums
+    size_t part_elems = 0;
+    float* logits = nullptr;           // [B][ldv]
+    int32_t* seq = nullptr;            // [B][448] tokens fed to the decoder (prompt, then sampled / teacher-forced)
+    wdr_token_data* tokens = nullptr;  // [B][224]
+    DecWinState* win = nullptr;        // [B]
+    int32_t* done_count = nullptr;
+    int32_t* ahead_map = nullptr;      // [L*H] -> alignment-head index or -1
+    int n_aheads = 0;
+    // alignment-head capture of the DTW pass: window b's w[H_a][T_b][A_b] starts at aw + aw_off[b]
+    float* aw = nullptr;
+    size_t aw_cap = 0;
+    int64_t* aw_off = nullptr;
+    int32_t* aw_T = nullptr;
+    int32_t* aw_A = nullptr;
+    int reserve(const wdr_context* ctx, int B);
+    void release();
+};
+
+// cross-KV projection of all decoder layers from ws.enc_bf16 (B windows)
+int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaStream_t st, Profiler* prof);
+// one decoder step at position pos for all B windows (token = ws.seq[b][pos]).  want_logits: final LN + logits GEMM.
+// capture: write alignment-head cross-attention rows to ws.aw (DTW pass).
+int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, bool capture, cudaStream_t st, Profiler* prof);
+// whisper_process_logits + greedy whisper_sample_token + decoder bookkeeping on ws.logits; appends to ws.tokens / ws.seq[pos+1]
+int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof);
+
+}  // namespace wdr

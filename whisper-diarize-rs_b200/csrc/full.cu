@@ -1,0 +1,657 @@
+// full.cu — whisper_full_with_state as the reference drives it, batched over independent <= 30 s buffers.
+//
+// Replaces `state.full(params, &samples)` (reference src/transcribe.rs:389, parameters from setup_params :20-87) and the
+// result accessors (`full_n_segments`, segment text/t0/t1, `n_tokens`, `get_token`, `token_data`; :393-412, :252-282).
+// Device work: log-mel -> encoder -> cross-KV -> greedy decode (decoder.cu) -> DTW pass (teacher-forced decoder steps that
+// capture the alignment heads, dtw.cu).  Host work (scalar, data dependent, restated from SURVEY A.4-A.6): segment assembly,
+// whisper_exp_compute_token_level_timestamps, stamping t_dtw from the DTW path.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "decoder.cuh"
+#include "encoder.cuh"
+#include "state.cuh"
+#include "vocab.cuh"
+
+namespace wdr {
+
+int dtw_cost_dev(const float* w, int H, int T, int A, int sot_len, int width, float* mean, float* scale, float* out, cudaStream_t st);
+struct DtwWindow { int64_t x_off; int32_t N, M; int64_t tr_off; };
+int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int32_t* time_idx, int32_t* path_len, int max_path,
+            float* cost_out, int32_t* trace_out, cudaStream_t st);
+
+constexpr int kDeltaMin = 10;  // whisper.cpp v1.7.x: "if only 100 ms left, then stop" (delta_min = 10 mel frames)
+
+// get_signal_energy: moving average of |x| over [i-hw, i+hw] clipped to the buffer, summed in index order
+template <typename In>
+__global__ void energy_kernel(const In* __restrict__ pcm, int64_t chunk_stride, const int32_t* __restrict__ n_valid, int n_fixed, int hw,
+                              float* __restrict__ out, int64_t out_stride) {
+    const int b = blockIdx.y;
+    const int n = n_valid ? n_valid[b] : n_fixed;
+    const In* x = pcm + (int64_t)b * chunk_stride;
+    float* o = out + (int64_t)b * out_stride;
+    const float den = (float)(2 * hw + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float s = 0.0f;
+        const int lo = max(0, i - hw), hi = min(n - 1, i + hw);
+        for (int j = lo; j <= hi; j++) {
+            float v;
+            if (sizeof(In) == 2) v = (float)x[j] * (1.0f / 32768.0f); else v = (float)x[j];
+            s += fabsf(v);
+        }
+        o[i] = s / den;
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+static int timestamp_to_sample(int64_t t, int n_samples) {
+    int64_t s = (t * WDR_SAMPLE_RATE) / 100;
+    if (s > n_samples - 1) s = n_samples - 1;
+    if (s < 0) s = 0;
+    return (int)s;
+}
+static int64_t sample_to_timestamp(int i) { return (100ll * i) / WDR_SAMPLE_RATE; }
+
+// whisper_exp_compute_token_level_timestamps for one segment; st3 = {t_beg, t_last, tid_last}
+static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t t0, int64_t t1, const Vocab& v, const float* energy,
+                                   int n_samples, float thold_pt, float thold_ptsum, int64_t* st3) {
+    const int n = (int)tokens.size();
+    if (n_samples == 0 || n == 0) return;
+    if (n == 1) { tokens[0].t0 = t0; tokens[0].t1 = t1; return; }
+    int64_t &t_beg = st3[0], &t_last = st3[1], &tid_last = st3[2];
+    for (int j = 0; j < n; j++) {
+        wdr_token_data& tk = tokens[j];
+        if (j == 0) {
+            if (tk.id == v.beg) {
+                tokens[j].t0 = t0; tokens[j].t1 = t0; tokens[j + 1].t0 = t0;
+                t_beg = t0; t_last = t0; tid_last = v.beg;
+            } else {
+                tokens[j].t0 = t_last;
+            }
+        }
+        const int64_t tt = t_beg + 2 * (tk.tid - v.beg);
+        tk.vlen = voice_length(token_text(v, tk.id));
+        if (tk.pt > thold_pt && tk.ptsum > thold_ptsum && tk.tid > tid_last && tt <= t1) {
+            if (j > 0) tokens[j - 1].t1 = tt;
+            tokens[j].t0 = tt;
+            tid_last = tk.tid;
+        }
+    }
+    tokens[n - 2].t1 = t1; tokens[n - 1].t0 = t1; tokens[n - 1].t1 = t1;
+    t_last = t1;
+    {
+        int p0 = 0, p1 = 0;
+        while (true) {
+            while (p1 < n && tokens[p1].t1 < 0) p1++;
+            if (p1 >= n) p1--;
+            if (p1 > p0) {
+                double psum = 0.0;
+                for (int j = p0; j <= p1; j++) psum += tokens[j].vlen;
+                const double dt = (double)(tokens[p1].t1 - tokens[p0].t0);
+                for (int j = p0 + 1; j <= p1; j++) {
+                    const double ct = tokens[j - 1].t0 + dt * tokens[j - 1].vlen / psum;
+                    tokens[j - 1].t1 = (int64_t)ct;
+                    tokens[j].t0 = (int64_t)ct;
+                }
+            }
+            p1++;
+            p0 = p1;
+            if (p1 >= n) break;
+        }
+    }
+    for (int j = 0; j < n - 1; j++) {
+        if (tokens[j].t1 < 0) tokens[j + 1].t0 = tokens[j].t1;
+        if (j > 0 && tokens[j - 1].t1 > tokens[j].t0) {
+            tokens[j].t0 = tokens[j - 1].t1;
+            tokens[j].t1 = std::max(tokens[j].t0, tokens[j].t1);
+        }
+    }
+    const int hw = WDR_SAMPLE_RATE / 8;
+    for (int j = 0; j < n; j++) {
+        if (tokens[j].id >= v.eot) continue;
+        int s0 = timestamp_to_sample(tokens[j].t0, n_samples);
+        int s1 = timestamp_to_sample(tokens[j].t1, n_samples);
+        const int ss0 = std::max(s0 - hw, 0);
+        const int ss1 = std::min(s1 + hw, n_samples);
+        const int ns = ss1 - ss0;
+        float sum = 0.0f;
+        for (int k = ss0; k < ss1; k++) sum += energy[k];
+        const float thold = 0.5f * sum / ns;
+        {
+            int k = s0;
+            if (energy[k] > thold && j > 0) {
+                while (k > 0 && energy[k] > thold) k--;
+                tokens[j].t0 = sample_to_timestamp(k);
+                if (tokens[j].t0 < tokens[j - 1].t1) tokens[j].t0 = tokens[j - 1].t1;
+                else s0 = k;
+            } else {
+                while (energy[k] < thold && k < s1) k++;
+                s0 = k;
+                tokens[j].t0 = sample_to_timestamp(k);
+            }
+        }
+        {
+            int k = s1;
+            if (energy[k] > thold) {
+                while (k < n_samples - 1 && energy[k] > thold) k++;
+                tokens[j].t1 = sample_to_timestamp(k);
+                if (j < ns - 1 && j + 1 < n && tokens[j].t1 > tokens[j + 1].t0) tokens[j].t1 = tokens[j + 1].t0;
+                else s1 = k;
+            } else {
+                while (energy[k] < thold && k > s0) k--;
+                s1 = k;
+                tokens[j].t1 = sample_to_timestamp(k);
+            }
+        }
+    }
+}
+
+static SampleParams make_sample_params(const Vocab& v, const wdr_full_params& p) {
+    SampleParams sp;
+    sp.n_vocab = v.n_vocab; sp.eot = v.eot; sp.sot = v.sot; sp.translate = v.translate; sp.transcribe = v.transcribe; sp.solm = v.solm;
+    sp.prev = v.prev; sp.nosp = v.nosp; sp.not_ = v.not_; sp.beg = v.beg; sp.lang0 = v.lang0; sp.n_langs = v.n_langs; sp.space = v.space;
+    sp.suppress_blank = p.suppress_blank; sp.no_timestamps = p.no_timestamps; sp.single_segment = p.single_segment;
+    sp.delta_min = kDeltaMin;
+    sp.n_max = WDR_TEXT_CTX / 2 - 4;
+    sp.initial_tid0 = p.max_initial_ts > 0.0f ? (int)roundf(p.max_initial_ts / (30.0f / 1500.0f)) : -1;
+    return sp;
+}
+
+static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int* lang_id) {
+    if (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) { set_error("beam search (beam_size %d) is not implemented yet: use WDR_SAMPLING_GREEDY", p.beam_size); return WDR_ERR_UNSUPPORTED; }
+    if (p.temperature != 0.0f || p.temperature_inc != 0.0f) { set_error("only temperature 0 without fallback is implemented (temperature %g, temperature_inc %g)", p.temperature, p.temperature_inc); return WDR_ERR_UNSUPPORTED; }
+    if (!p.single_segment) { set_error("single_segment = 0 is not implemented (the crate always sets it, src/transcribe.rs:46)"); return WDR_ERR_UNSUPPORTED; }
+    if (p.no_timestamps) { set_error("no_timestamps = 1 is not implemented"); return WDR_ERR_UNSUPPORTED; }
+    if (p.detect_language || (p.language && strcmp(p.language, "auto") == 0)) { set_error("language auto-detection is not implemented: pass the language"); return WDR_ERR_UNSUPPORTED; }
+    if (p.initial_prompt && p.initial_prompt[0]) { set_error("initial_prompt needs a tokenizer file; pass prompt_tokens instead"); return WDR_ERR_UNSUPPORTED; }
+    if (p.offset_ms || p.duration_ms || p.max_len || p.max_tokens || p.audio_ctx || p.suppress_nst) { set_error("offset/duration/max_len/max_tokens/audio_ctx/suppress_nst are not implemented"); return WDR_ERR_UNSUPPORTED; }
+    if (p.translate && !ctx->arch.multilingual) { set_error("translate needs a multilingual model"); return WDR_ERR_INVALID; }
+    int id = lang_id_from_str(p.language ? p.language : "en");
+    if (id < 0) { set_error("unknown language '%s'", p.language); return WDR_ERR_INVALID; }
+    *lang_id = id;
+    return WDR_OK;
+}
+
+template <typename T>
+static int grow_dev(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return WDR_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    WDR_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), need * sizeof(T)));
+    *cap = need;
+    return WDR_OK;
+}
+template <typename T>
+static int grow_pinned(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return WDR_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(p), need * sizeof(T)));
+    *cap = need;
+    return WDR_OK;
+}
+
+// One group of B <= 128 windows whose PCM is already on the device (In = int16_t or float).
+template <typename In>
+static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, int lang_id, const In* pcm_dev, int64_t chunk_stride,
+                      const int32_t* n_valid_host, int chunk0, int B) {
+    FullScratch& fs = st->full;
+    DecoderWorkspace& ws = st->dec;
+    const WhisperArch& a = ctx->arch;
+    const Vocab v = make_vocab(a.n_vocab);
+    cudaStream_t s = st->stream;
+    int rc;
+    if ((rc = ws.reserve(ctx, B)) != WDR_OK) return rc;
+    // ---- n_valid on the device ----
+    if ((rc = grow_dev(&fs.nvalid_dev, &fs.nvalid_cap, (size_t)B)) != WDR_OK) return rc;
+    std::vector<int32_t> nv(B);
+    for (int b = 0; b < B; b++) nv[b] = n_valid_host ? n_valid_host[chunk0 + b] : WDR_CHUNK_SAMPLES;
+    WDR_CUDA_TRY(cudaMemcpyAsync(fs.nvalid_dev, nv.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    // ---- mel + encoder -> bf16 hidden states ----
+    if ((rc = encode_chunks<In>(ctx, st->enc, pcm_dev, chunk_stride, fs.nvalid_dev, B, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
+    // ---- energy for the token-timestamp heuristic (D2H overlaps the decode) ----
+    if (p.token_timestamps) {
+        if ((rc = grow_dev(&fs.energy_dev, &fs.energy_cap, (size_t)B * WDR_CHUNK_SAMPLES)) != WDR_OK) return rc;
+        if ((rc = grow_pinned(&fs.energy_host, &fs.energy_host_cap, (size_t)B * WDR_CHUNK_SAMPLES)) != WDR_OK) return rc;
+        ProfScope ps(&st->prof, KC_OTHER, s);
+        energy_kernel<In><<<dim3(256, B), 256, 0, s>>>(pcm_dev, chunk_stride, fs.nvalid_dev, WDR_CHUNK_SAMPLES, 32, fs.energy_dev, WDR_CHUNK_SAMPLES);
+        WDR_LAUNCH_CHECK();
+        WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy, s));
+        WDR_CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, fs.ev_energy, 0));
+        for (int b = 0; b < B; b++)
+            if (nv[b] > 0)
+                WDR_CUDA_TRY(cudaMemcpyAsync(fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, fs.energy_dev + (size_t)b * WDR_CHUNK_SAMPLES,
+                                             sizeof(float) * nv[b], cudaMemcpyDeviceToHost, st->copy_stream));
+        WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy_done, st->copy_stream));
+    }
+    if ((rc = decoder_cross_kv(ctx, ws, B, s, &st->prof)) != WDR_OK) return rc;
+    // ---- prompt + decoder state ----
+    std::vector<int32_t> prompt;
+    if (p.prompt_tokens && p.prompt_n_tokens > 0 && p.n_max_text_ctx > 0) {
+        const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), p.prompt_n_tokens);
+        prompt.push_back(v.prev);
+        for (int i = p.prompt_n_tokens - n_take; i < p.prompt_n_tokens; i++) prompt.push_back(p.prompt_tokens[i]);
+    }
+    prompt.push_back(v.sot);
+    if (v.multilingual) {
+        prompt.push_back(v.lang0 + lang_id);
+        prompt.push_back(p.translate ? v.translate : v.transcribe);
+    }
+    const int n_prompt = (int)prompt.size();
+    const int n_max = WDR_TEXT_CTX / 2 - 4;
+    WDR_REQUIRE(n_prompt + n_max <= kDecSeqCap, "prompt too long");
+    std::vector<int32_t> seq((size_t)B * kDecSeqCap, v.eot);
+    std::vector<DecWinState> win(B);
+    int n_skip = 0;
+    for (int b = 0; b < B; b++) {
+        for (int i = 0; i < n_prompt; i++) seq[(size_t)b * kDecSeqCap + i] = prompt[i];
+        DecWinState w;
+        memset(&w, 0, sizeof(w));
+        w.seek_delta = 100 * 30;
+        w.seek = 0;
+        w.seek_end = 1 + (nv[b] + 200 - WDR_N_FFT) / WDR_HOP;  // mel.n_len_org
+        if (nv[b] <= 0 || w.seek_end < w.seek + kDeltaMin || w.seek + kDeltaMin >= w.seek_end) { w.completed = 1; w.seek_delta = 0; n_skip++; }  // too short: no decode
+        win[b] = w;
+    }
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.win, win.data(), sizeof(DecWinState) * B, cudaMemcpyHostToDevice, s));
+    WDR_CUDA_TRY(cudaMemsetAsync(ws.done_count, 0, sizeof(int32_t), s));
+    WDR_CUDA_TRY(cudaMemsetAsync(ws.tokens, 0, sizeof(wdr_token_data) * (size_t)B * kDecMaxTokens, s));
+    const SampleParams sp = make_sample_params(v, p);
+    // ---- greedy decode ----
+    int steps_run = 0;
+    if (n_skip < B) {
+        for (int i = 0; i < n_prompt; i++)
+            if ((rc = decoder_step(ctx, ws, B, i, i == n_prompt - 1, false, s, &st->prof)) != WDR_OK) return rc;
+        int32_t* done_host = fs.done_host;
+        for (int i = 0; i < n_max; i++) {
+            if ((rc = decoder_sample(ctx, ws, B, n_prompt - 1 + i, sp, s, &st->prof)) != WDR_OK) return rc;
+            steps_run = i + 1;
+            if ((i & 3) == 3 || i == n_max - 1) {
+                WDR_CUDA_TRY(cudaMemcpyAsync(done_host, ws.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                WDR_CUDA_TRY(cudaStreamSynchronize(s));
+                if (*done_host + n_skip >= B) break;
+                if (p.abort_callback && p.abort_callback(p.abort_callback_user_data)) { set_error("aborted by callback"); return WDR_ERR_ABORTED; }
+            }
+            if (i == n_max - 1) break;
+            if ((rc = decoder_step(ctx, ws, B, n_prompt + i, true, false, s, &st->prof)) != WDR_OK) return rc;
+        }
+    }
+    fs.last_decode_steps = steps_run;
+    // ---- results to the host ----
+    std::vector<wdr_token_data> toks((size_t)B * kDecMaxTokens);
+    WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
+    WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
+    WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    if (p.token_timestamps) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
+
+    struct Pending { int seg; int b; int n_frames; std::vector<int32_t> dtw_seq; int sot_len; };
+    std::vector<Pending> pend;
+    for (int b = 0; b < B; b++) {
+        const DecWinState& w = win[b];
+        ChunkInfo ci;
+        ci.seek_delta = w.seek_delta; ci.failed = w.failed; ci.completed = w.completed; ci.n_sampled = w.n_cur; ci.has_ts = w.has_ts;
+        ci.result_len = w.result_len; ci.seek_end = w.seek_end; ci.n_segments = 0; ci.no_speech_prob = w.no_speech_prob;
+        const int n_keep = w.failed ? w.n_cur : w.result_len;
+        std::vector<wdr_token_data> cur(toks.begin() + (size_t)b * kDecMaxTokens, toks.begin() + (size_t)b * kDecMaxTokens + n_keep);
+        double avg_logprob = -INFINITY;
+        if (!w.failed && w.result_len > 0) {
+            double sum = 0.0;
+            for (int i = 0; i < w.result_len; i++) sum += cur[i].plog;
+            avg_logprob = sum / w.result_len;
+        }
+        const bool is_no_speech = w.no_speech_prob > p.no_speech_thold && avg_logprob < p.logprob_thold;
+        if (!cur.empty() && !is_no_speech) {
+            const int seek = w.seek;
+            const int64_t t0 = seek + 2 * (cur.front().tid - v.beg);
+            std::string text;
+            for (auto& t : cur)
+                if (p.print_special || t.id < v.eot) text += token_text(v, t.id);
+            if (!text.empty()) {
+                ResultSegment seg;
+                seg.chunk = chunk0 + b;
+                seg.t0 = t0;
+                seg.t1 = seek + w.seek_delta;
+                seg.text = text;
+                seg.no_speech_prob = w.no_speech_prob;
+                seg.tokens = cur;
+                if (p.token_timestamps) {
+                    int64_t st3[3] = {0, 0, 0};
+                    token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, nv[b], p.thold_pt, p.thold_ptsum, st3);
+                }
+                for (auto& t : seg.tokens) seg.token_text.push_back(token_text(v, t.id));
+                st->results.push_back(std::move(seg));
+                ci.n_segments = 1;
+                if (ctx->dtw_enabled) {
+                    Pending pd;
+                    pd.seg = (int)st->results.size() - 1;
+                    pd.b = b;
+                    pd.n_frames = std::min(std::min(100 * 30, w.seek_delta), w.seek_end - seek);
+                    pd.dtw_seq.push_back(v.sot);
+                    if (v.multilingual) pd.dtw_seq.push_back(v.lang0 + lang_id);
+                    pd.sot_len = (int)pd.dtw_seq.size();
+                    pd.dtw_seq.push_back(v.not_);
+                    for (auto& t : st->results[pd.seg].tokens)
+                        if (t.id < v.eot) pd.dtw_seq.push_back(t.id);
+                    pd.dtw_seq.push_back(v.eot);
+                    pend.push_back(std::move(pd));
+                }
+            }
+        }
+        st->chunk_info.push_back(ci);
+    }
+    // ---- DTW token timestamps: teacher-forced pass capturing the alignment heads, then cost + wavefront + backtrace ----
+    if (!pend.empty()) {
+        const int Ha = (int)ctx->aheads.size();
+        std::vector<int64_t> aw_off(B, 0), x_off(B, 0);
+        std::vector<int32_t> aw_T(B, 0), aw_A(B, 0);
+        std::fill(seq.begin(), seq.end(), v.eot);
+        size_t aw_total = 0, x_total = 0, stat_max = 0;
+        int max_T = 0, max_path = 1;
+        for (auto& pd : pend) {
+            const int T_b = (int)pd.dtw_seq.size(), A_b = pd.n_frames / 2;
+            aw_T[pd.b] = T_b; aw_A[pd.b] = A_b;
+            aw_off[pd.b] = (int64_t)aw_total;
+            aw_total += (size_t)Ha * T_b * A_b;
+            x_off[pd.b] = (int64_t)x_total;
+            x_total += (size_t)(T_b - pd.sot_len - 1) * A_b;
+            stat_max = std::max(stat_max, (size_t)Ha * A_b);
+            max_T = std::max(max_T, T_b);
+            max_path = std::max(max_path, T_b + A_b);
+            for (int i = 0; i < T_b; i++) seq[(size_t)pd.b * kDecSeqCap + i] = pd.dtw_seq[i];
+        }
+        if (aw_total > ws.aw_cap) {
+            if (ws.aw) cudaFree(ws.aw);
+            ws.aw = nullptr; ws.aw_cap = 0;
+            WDR_CUDA_TRY(cudaMalloc(&ws.aw, sizeof(float) * aw_total));
+            ws.aw_cap = aw_total;
+        }
+        if ((rc = grow_dev(&fs.dtw_x, &fs.dtw_x_cap, std::max<size_t>(x_total, 1))) != WDR_OK) return rc;
+        if ((rc = grow_dev(&fs.dtw_stat, &fs.dtw_stat_cap, 2 * std::max<size_t>(stat_max, 1))) != WDR_OK) return rc;
+        if ((rc = grow_dev(&fs.dtw_path, &fs.dtw_path_cap, (size_t)(2 * max_path + 1) * B)) != WDR_OK) return rc;
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_off, aw_off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_T, aw_T.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_A, aw_A.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+        for (int i = 0; i < max_T; i++)
+            if ((rc = decoder_step(ctx, ws, B, i, false, true, s, &st->prof)) != WDR_OK) return rc;
+        std::vector<DtwWindow> wins;
+        std::vector<int> win_b;
+        for (auto& pd : pend) {
+            const int T_b = aw_T[pd.b], A_b = aw_A[pd.b], N = T_b - pd.sot_len - 1;
+            if (N <= 0 || A_b <= 3) continue;
+            {
+                ProfScope ps(&st->prof, KC_DTW, s);
+                if ((rc = dtw_cost_dev(ws.aw + aw_off[pd.b], Ha, T_b, A_b, pd.sot_len, 7, fs.dtw_stat, fs.dtw_stat + stat_max, fs.dtw_x + x_off[pd.b], s)) != WDR_OK) return rc;
+            }
+            DtwWindow dw;
+            dw.x_off = x_off[pd.b]; dw.N = N; dw.M = A_b; dw.tr_off = 0;
+            wins.push_back(dw);
+            win_b.push_back((int)(&pd - &pend[0]));
+        }
+        if (!wins.empty()) {
+            int32_t* ti = fs.dtw_path;
+            int32_t* tj = ti + (size_t)max_path * B;
+            int32_t* pl = tj + (size_t)max_path * B;
+            {
+                ProfScope ps(&st->prof, KC_DTW, s);
+                if ((rc = dtw_run(fs.dtw_x, wins, ti, tj, pl, max_path, nullptr, nullptr, s)) != WDR_OK) return rc;
+            }
+            const size_t nw = wins.size();
+            std::vector<int32_t> h_ti(nw * max_path), h_tj(nw * max_path), h_pl(nw);
+            WDR_CUDA_TRY(cudaMemcpyAsync(h_ti.data(), ti, sizeof(int32_t) * h_ti.size(), cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaMemcpyAsync(h_tj.data(), tj, sizeof(int32_t) * h_tj.size(), cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaMemcpyAsync(h_pl.data(), pl, sizeof(int32_t) * nw, cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaStreamSynchronize(s));
+            for (size_t k = 0; k < nw; k++) {
+                const Pending& pd = pend[win_b[k]];
+                ResultSegment& seg = st->results[pd.seg];
+                const int seek = 0;
+                const int32_t* a_ti = h_ti.data() + k * max_path;
+                const int32_t* a_tj = h_tj.data() + k * max_path;
+                if (h_pl[k] < 0) { set_error("dtw backtrace did not terminate"); return WDR_ERR_CUDA; }
+                int last_v = 0;
+                size_t tix = 0;
+                for (int i = 0; i < h_pl[k]; i++) {
+                    const int vv = a_ti[i];
+                    if (vv != last_v) {
+                        const int64_t ts = (int64_t)a_tj[i] * 2 + seek;
+                        last_v = vv;
+                        while (tix < seg.tokens.size() && !(seg.tokens[tix].id < v.eot)) tix++;
+                        if (tix >= seg.tokens.size()) break;
+                        seg.tokens[tix].t_dtw = ts;
+                        tix++;
+                    }
+                }
+            }
+        } else {
+            WDR_CUDA_TRY(cudaStreamSynchronize(s));
+        }
+    }
+    return WDR_OK;
+}
+
+template <typename In>
+static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, const In* pcm, int64_t chunk_stride,
+                           const int32_t* n_valid, int n_chunks) {
+    clear_error();
+    WDR_REQUIRE(ctx && st && st->ctx == ctx && n_chunks >= 0, "bad arguments");
+    WDR_REQUIRE(n_chunks == 0 || (pcm && chunk_stride >= 0), "bad arguments");
+    int rc = ensure_device(ctx->device);
+    if (rc != WDR_OK) return rc;
+    int lang_id = 0;
+    if ((rc = validate_params(ctx, p, &lang_id)) != WDR_OK) return rc;
+    st->results.clear();
+    st->chunk_info.clear();
+    st->lang_id = lang_id;
+    FullScratch& fs = st->full;
+    if (!fs.ev_energy) {
+        WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy, cudaEventDisableTiming));
+        WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy_done, cudaEventDisableTiming));
+        WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_h2d, cudaEventDisableTiming));
+        WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.done_host), sizeof(int32_t)));
+    }
+    for (int b = 0; b < n_chunks; b++) {
+        const int n = n_valid ? n_valid[b] : WDR_CHUNK_SAMPLES;
+        WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "each buffer must hold 0..480000 samples (longer audio: split into 30 s chunks)");
+    }
+    for (int c0 = 0; c0 < n_chunks; c0 += kDecMaxBatch) {
+        const int B = std::min(kDecMaxBatch, n_chunks - c0);
+        // stage this group's PCM: rows of up to 480000 samples at a fixed device stride
+        size_t cap_bytes = fs.pcm_cap;
+        void* buf = fs.pcm_dev;
+        const size_t need = (size_t)B * WDR_CHUNK_SAMPLES * sizeof(In);
+        if (need > cap_bytes) {
+            if (buf) cudaFree(buf);
+            fs.pcm_dev = nullptr; fs.pcm_cap = 0;
+            WDR_CUDA_TRY(cudaMalloc(&fs.pcm_dev, need));
+            fs.pcm_cap = need;
+        }
+        In* pcm_dev = reinterpret_cast<In*>(fs.pcm_dev);
+        for (int b = 0; b < B; b++) {
+            const int n = n_valid ? n_valid[c0 + b] : WDR_CHUNK_SAMPLES;
+            if (n > 0)
+                WDR_CUDA_TRY(cudaMemcpyAsync(pcm_dev + (size_t)b * WDR_CHUNK_SAMPLES, pcm + (size_t)(c0 + b) * chunk_stride, sizeof(In) * (size_t)n,
+                                             cudaMemcpyHostToDevice, st->stream));
+        }
+        rc = full_group<In>(ctx, st, p, lang_id, pcm_dev, WDR_CHUNK_SAMPLES, n_valid, c0, B);
+        if (rc != WDR_OK) return rc;
+        if (p.progress_callback) p.progress_callback(ctx, st, (int)(100ll * (c0 + B) / n_chunks), p.progress_callback_user_data);
+    }
+    return WDR_OK;
+}
+
+}  // namespace wdr
+
+using namespace wdr;
+
+extern "C" wdr_full_params wdr_full_default_params(int strategy) {
+    wdr_full_params p;
+    memset(&p, 0, sizeof(p));
+    p.strategy = strategy;
+    p.n_threads = 4;
+    p.n_max_text_ctx = 16384;
+    p.no_context = 1;
+    p.print_progress = 1;
+    p.print_timestamps = 1;
+    p.thold_pt = 0.01f;
+    p.thold_ptsum = 0.01f;
+    p.language = "en";
+    p.suppress_blank = 1;
+    p.temperature = 0.0f;
+    p.max_initial_ts = 1.0f;
+    p.length_penalty = -1.0f;
+    p.temperature_inc = 0.0f;  // whisper.cpp: 0.2 — the fallback ladder is not implemented
+    p.entropy_thold = 2.4f;
+    p.logprob_thold = -1.0f;
+    p.no_speech_thold = 0.6f;
+    p.greedy_best_of = strategy == WDR_SAMPLING_GREEDY ? 5 : -1;
+    p.beam_size = strategy == WDR_SAMPLING_BEAM_SEARCH ? 5 : -1;
+    p.beam_patience = -1.0f;
+    return p;
+}
+
+extern "C" int wdr_full_with_state(wdr_context* ctx, wdr_state* st, wdr_full_params p, const float* pcm, int n) {
+    clear_error();
+    WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "wdr_full_with_state takes one buffer of <= 30 s; longer audio goes through wdr_full_batch_i16 in 30 s chunks");
+    const int32_t nv = n;
+    return full_batch_impl<float>(ctx, st, p, pcm, WDR_CHUNK_SAMPLES, &nv, 1);
+}
+extern "C" int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm, int n) {
+    clear_error();
+    WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "wdr_full_with_state_i16 takes one buffer of <= 30 s");
+    const int32_t nv = n;
+    return full_batch_impl<int16_t>(ctx, st, p, pcm, WDR_CHUNK_SAMPLES, &nv, 1);
+}
+extern "C" int wdr_full_batch_i16(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm, int64_t chunk_stride,
+                                  const int32_t* n_valid, int n_chunks) {
+    return full_batch_impl<int16_t>(ctx, st, p, pcm, chunk_stride, n_valid, n_chunks);
+}
+
+#define SEG_OR(ret)                                                                  \
+    if (!st || i < 0 || i >= (int)st->results.size()) { set_error("segment index out of range"); return ret; } \
+    const ResultSegment& seg = st->results[i];
+
+extern "C" int wdr_full_n_segments_from_state(wdr_state* st) { return st ? (int)st->results.size() : 0; }
+extern "C" int wdr_full_get_segment_chunk_from_state(wdr_state* st, int i) { SEG_OR(-1) return seg.chunk; }
+extern "C" int64_t wdr_full_get_segment_t0_from_state(wdr_state* st, int i) { SEG_OR(-1) return seg.t0; }
+extern "C" int64_t wdr_full_get_segment_t1_from_state(wdr_state* st, int i) { SEG_OR(-1) return seg.t1; }
+extern "C" const char* wdr_full_get_segment_text_from_state(wdr_state* st, int i) { SEG_OR(nullptr) return seg.text.c_str(); }
+extern "C" float wdr_full_get_segment_no_speech_prob_from_state(wdr_state* st, int i) { SEG_OR(0.0f) return seg.no_speech_prob; }
+extern "C" int wdr_full_n_tokens_from_state(wdr_state* st, int i) { SEG_OR(-1) return (int)seg.tokens.size(); }
+extern "C" int32_t wdr_full_get_token_id_from_state(wdr_state* st, int i, int j) {
+    SEG_OR(-1)
+    if (j < 0 || j >= (int)seg.tokens.size()) { set_error("token index out of range"); return -1; }
+    return seg.tokens[j].id;
+}
+extern "C" const char* wdr_full_get_token_text_from_state(wdr_context*, wdr_state* st, int i, int j) {
+    SEG_OR(nullptr)
+    if (j < 0 || j >= (int)seg.token_text.size()) { set_error("token index out of range"); return nullptr; }
+    return seg.token_text[j].c_str();
+}
+extern "C" wdr_token_data wdr_full_get_token_data_from_state(wdr_state* st, int i, int j) {
+    wdr_token_data z;
+    memset(&z, 0, sizeof(z));
+    z.t0 = z.t1 = z.t_dtw = -1;
+    SEG_OR(z)
+    if (j < 0 || j >= (int)seg.tokens.size()) { set_error("token index out of range"); return z; }
+    return seg.tokens[j];
+}
+extern "C" int wdr_full_lang_id_from_state(wdr_state* st) { return st ? st->lang_id : -1; }
+extern "C" const char* wdr_lang_str(int id) { return (id >= 0 && id < 100) ? kLangs[id] : nullptr; }
+extern "C" int wdr_lang_id(const char* lang) { return lang_id_from_str(lang); }
+extern "C" const char* wdr_token_to_str(wdr_context* ctx, int32_t token) {
+    static thread_local std::string buf;
+    if (!ctx || token < 0 || token >= ctx->arch.n_vocab) return nullptr;
+    buf = token_text(make_vocab(ctx->arch.n_vocab), token);
+    return buf.c_str();
+}
+extern "C" int wdr_full_get_chunk_info_from_state(wdr_state* st, int i, int32_t* info, float* nsp) {
+    clear_error();
+    WDR_REQUIRE(st && info && i >= 0 && i < (int)st->chunk_info.size(), "chunk index out of range");
+    const ChunkInfo& c = st->chunk_info[i];
+    info[0] = c.seek_delta; info[1] = c.failed; info[2] = c.completed; info[3] = c.n_sampled; info[4] = c.has_ts; info[5] = c.result_len;
+    info[6] = c.seek_end; info[7] = c.n_segments;
+    if (nsp) *nsp = c.no_speech_prob;
+    return WDR_OK;
+}
+
+extern "C" int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* st, const float* enc, int n_chunks, const int32_t* seq_in, int n_seq,
+                                         float* logits_out, float* aheads_out) {
+    clear_error();
+    WDR_REQUIRE(ctx && st && st->ctx == ctx && seq_in && n_chunks > 0 && n_chunks <= kDecMaxBatch && n_seq > 0 && n_seq <= kDecSeqCap, "bad arguments");
+    WDR_REQUIRE(!aheads_out || !ctx->aheads.empty(), "alignment heads need a context created with dtw_token_timestamps");
+    int rc = ensure_device(ctx->device);
+    if (rc != WDR_OK) return rc;
+    DecoderWorkspace& ws = st->dec;
+    const int B = n_chunks, d = ctx->arch.d, nv = ctx->arch.n_vocab;
+    cudaStream_t s = st->stream;
+    if (enc) {
+        if ((rc = ws.reserve(ctx, B)) != WDR_OK) return rc;
+        const size_t n = (size_t)B * WDR_AUDIO_CTX * d;
+        DevBuf<float> tmp;
+        WDR_CUDA_TRY(tmp.alloc(n));
+        WDR_CUDA_TRY(cudaMemcpyAsync(tmp.p, enc, sizeof(float) * n, cudaMemcpyHostToDevice, s));
+        f32_to_bf16_kernel<<<148 * 4, 256, 0, s>>>(tmp.p, ws.enc_bf16, (int64_t)n);
+        WDR_LAUNCH_CHECK();
+        if ((rc = decoder_cross_kv(ctx, ws, B, s, &st->prof)) != WDR_OK) return rc;
+        WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    WDR_REQUIRE(ws.cap_B >= B, "no encoder output in the state for that many windows");
+    const Vocab v = make_vocab(nv);
+    std::vector<int32_t> seq((size_t)B * kDecSeqCap, v.eot);
+    for (int b = 0; b < B; b++)
+        for (int i = 0; i < n_seq; i++) seq[(size_t)b * kDecSeqCap + i] = seq_in[(size_t)b * n_seq + i];
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
+    const int Ha = (int)ctx->aheads.size();
+    if (aheads_out) {
+        const size_t per = (size_t)Ha * n_seq * WDR_AUDIO_CTX;
+        if (per * B > ws.aw_cap) {
+            if (ws.aw) cudaFree(ws.aw);
+            ws.aw = nullptr; ws.aw_cap = 0;
+            WDR_CUDA_TRY(cudaMalloc(&ws.aw, sizeof(float) * per * B));
+            ws.aw_cap = per * B;
+        }
+        std::vector<int64_t> off(B);
+        std::vector<int32_t> T(B, n_seq), A(B, WDR_AUDIO_CTX);
+        for (int b = 0; b < B; b++) off[b] = (int64_t)(per * b);
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_off, off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_T, T.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_A, A.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    }
+    for (int i = 0; i < n_seq; i++) {
+        if ((rc = decoder_step(ctx, ws, B, i, logits_out != nullptr, aheads_out != nullptr, s, &st->prof)) != WDR_OK) return rc;
+        if (logits_out)
+            WDR_CUDA_TRY(cudaMemcpy2DAsync(logits_out + (size_t)i * nv, sizeof(float) * (size_t)n_seq * nv, ws.logits, sizeof(float) * ws.ldv,
+                                           sizeof(float) * nv, B, cudaMemcpyDeviceToHost, s));
+    }
+    if (aheads_out)
+        WDR_CUDA_TRY(cudaMemcpyAsync(aheads_out, ws.aw, sizeof(float) * (size_t)B * Ha * n_seq * WDR_AUDIO_CTX, cudaMemcpyDeviceToHost, s));
+    WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    return WDR_OK;
+}
+
+// Bring-up aid (not part of the reference surface): copies a decoder workspace buffer to the host as fp32.
+// which: 0 x [B][d] | 1 h | 2 att | 3 ff [B][4d] | 4 first `count` elements of layer-0 cross K|V | 5 split-K partial workspace
+extern "C" int wdr_debug_decoder_read(wdr_state* st, int which, float* out, int64_t count) {
+    clear_error();
+    WDR_REQUIRE(st && out && count > 0, "bad arguments");
+    DecoderWorkspace& ws = st->dec;
+    WDR_REQUIRE(ws.cap_B > 0, "no decoder workspace yet");
+    WDR_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    if (which == 0 || which == 5) {
+        WDR_CUDA_TRY(cudaMemcpy(out, which == 0 ? ws.x : ws.part, sizeof(float) * count, cudaMemcpyDeviceToHost));
+        return WDR_OK;
+    }
+    const __nv_bfloat16* src = which == 1 ? ws.h : which == 2 ? ws.att : which == 3 ? ws.ff : ws.ckv[0];
+    std::vector<__nv_bfloat16> tmp((size_t)count);
+    WDR_CUDA_TRY(cudaMemcpy(tmp.data(), src, sizeof(__nv_bfloat16) * count, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < count; i++) out[i] = __bfloat162float(tmp[i]);
+    return WDR_OK;
+}

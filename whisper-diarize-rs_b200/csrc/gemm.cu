@@ -31,6 +31,8 @@ struct GemmParams {
     int rows_per_batch, n_batch, N, K;
     int kb_per_tap;
     int tiles_per_batch, n_tiles, total_tiles;
+    int splits, kb_per_split;  // split-K: work item t -> (tile t / splits, split t % splits); split s covers k-blocks [s*kb_per_split, ...)
+    int64_t split_stride;      // elements between the partial outputs of consecutive splits
     void* out;
     int64_t ldc;
     int64_t c_batch_stride;
@@ -57,7 +59,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, bool DUAL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
     constexpr int kABytes = kBM * kBK * 2;
@@ -68,8 +70,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+    // DUAL: the A operand is a (hi, lo) bf16 pair (A = hi + lo to 16 mantissa bits); both halves multiply the same W tile
+    constexpr int kAStage = DUAL ? 2 * kABytes : kABytes;
     unsigned char* sA = smem;
-    unsigned char* sB = smem + STAGES * kABytes;
+    unsigned char* sB = smem + STAGES * kAStage;
     __shared__ __align__(8) uint64_t bar_full[STAGES];
     __shared__ __align__(8) uint64_t bar_empty[STAGES];
     __shared__ __align__(8) uint64_t bar_tfull[2];
@@ -109,14 +113,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
+                const int t = w / p.splits, sp = w - t * p.splits;
                 const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
                 const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
-                for (int kb = 0; kb < num_kb; kb++) {
+                const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&bar_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[s], kABytes + kBBytes);
+                    mbar_arrive_expect_tx(&bar_full[s], kAStage + kBBytes);
                     const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
-                    tma_load_3d(sA + s * kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
+                    tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
+                    if (DUAL) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
                     tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
@@ -130,19 +137,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
+                const int sp = w % p.splits;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 mbar_wait(&bar_tempty[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
-                for (int kb = 0; kb < num_kb; kb++) {
+                for (int kb = kb0; kb < kb1; kb++) {
                     mbar_wait(&bar_full[s], ph);
                     tc_fence_after();
-                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * kABytes));
+                    const uint64_t da = umma_desc_kmajor_sw128(smem_u32(sA + s * kAStage));
                     const uint64_t db = umma_desc_kmajor_sw128(smem_u32(sB + s * kBBytes));
 #pragma unroll
                     for (int k = 0; k < kBK / 16; k++) {
                         // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb != kb0) || (k != 0));
+                    }
+                    if (DUAL) {
+                        const uint64_t dl = umma_desc_kmajor_sw128(smem_u32(sA + s * kAStage + kABytes));
+#pragma unroll
+                        for (int k = 0; k < kBK / 16; k++) umma_bf16(tmem_d, dl + 2 * k, db + 2 * k, idesc, 1);
                     }
                     umma_commit(&bar_empty[s]);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -160,12 +174,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int g = lane & 7, rsub = lane >> 3;
         int as = 0;
         uint32_t aph = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
+            const int t = w / p.splits, sp = w - t * p.splits;
             const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
             const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
             const int r_in_batch = mt * kBM + q * 32 + lane;
             const bool row_ok = r_in_batch < p.rows_per_batch;
-            const int64_t c_base = (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32) * p.ldc;
+            const int64_t c_base = (int64_t)sp * p.split_stride + (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32) * p.ldc;
             bool waited = false;
 #pragma unroll 1
             for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
@@ -313,16 +328,16 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int BN, int STAGES, int EPI>
+template <int BN, int STAGES, int EPI, bool DUAL = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
+    constexpr size_t smem = (size_t)STAGES * ((DUAL ? 2 : 1) * kBM * kBK * 2 + BN * kBK * 2) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
-        WDR_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        WDR_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    gemm_bf16_kernel<BN, STAGES, EPI><<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+    gemm_bf16_kernel<BN, STAGES, EPI, DUAL><<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
     WDR_LAUNCH_CHECK();
     return WDR_OK;
 }
@@ -334,14 +349,18 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     WDR_REQUIRE((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0, "operands must be 16-byte aligned");
     WDR_REQUIRE(d.ldc % 8 == 0, "ldc must be a multiple of 8");
     if (d.epilogue == EPI_QKV_BF16) WDR_REQUIRE(d.out_t && d.n_split % 32 == 0, "QKV epilogue needs out_t and n_split % 32 == 0");
-    constexpr int BN = 128;
+    const int BN = d.bn == 64 ? 64 : 128;
+    WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
+    if (d.split_k > 1 || d.bn == 64) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 are plain fp32-partial GEMMs (EPI_F32, no bias)");
     CUtensorMap ta, tb;
     {
         // in tap mode the last tap reads rows up to rows_per_batch - 1 + (taps - 1): the caller's buffer holds them
         const int num_kb = (d.K + kBK - 1) / kBK;
         const int taps = d.kb_per_tap > 0 ? (num_kb + d.kb_per_tap - 1) / d.kb_per_tap : 1;
-        const uint64_t dims[3] = {(uint64_t)(d.a_cols > 0 ? d.a_cols : d.K), (uint64_t)(d.rows_per_batch + taps - 1), (uint64_t)d.n_batch};
-        const uint64_t str[2] = {(uint64_t)d.a_row_stride * 2, (uint64_t)(d.n_batch > 1 ? d.a_batch_stride : d.a_row_stride * d.rows_per_batch) * 2};
+        if (d.dual_a) WDR_REQUIRE(d.n_batch == 1 && d.bn == 64 && d.a_dual_stride > 0 && d.a_dual_stride % 8 == 0, "dual-A GEMMs are single-batch BN=64 GEMMs");
+        const uint64_t dims[3] = {(uint64_t)(d.a_cols > 0 ? d.a_cols : d.K), (uint64_t)(d.rows_per_batch + taps - 1), (uint64_t)(d.dual_a ? 2 : d.n_batch)};
+        const uint64_t str[2] = {(uint64_t)d.a_row_stride * 2,
+                                 (uint64_t)(d.dual_a ? d.a_dual_stride : d.n_batch > 1 ? d.a_batch_stride : d.a_row_stride * d.rows_per_batch) * 2};
         const uint32_t box[3] = {kBK, kBM, 1};
         int rc = make_tmap_bf16(&ta, d.A, 3, dims, str, box);
         if (rc != WDR_OK) return rc;
@@ -349,7 +368,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     {
         const uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.N};
         const uint64_t str[1] = {(uint64_t)d.ldw * 2};
-        const uint32_t box[2] = {kBK, BN};
+        const uint32_t box[2] = {kBK, (uint32_t)BN};
         int rc = make_tmap_bf16(&tb, d.W, 2, dims, str, box);
         if (rc != WDR_OK) return rc;
     }
@@ -358,18 +377,28 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.kb_per_tap = d.kb_per_tap > 0 ? d.kb_per_tap : (d.K + kBK - 1) / kBK;
     p.tiles_per_batch = (d.rows_per_batch + kBM - 1) / kBM;
     p.n_tiles = (d.N + BN - 1) / BN;
-    p.total_tiles = p.tiles_per_batch * d.n_batch * p.n_tiles;
+    {
+        const int num_kb = (d.K + kBK - 1) / kBK;
+        int splits = d.split_k < num_kb ? d.split_k : num_kb;
+        p.kb_per_split = (num_kb + splits - 1) / splits;
+        p.splits = (num_kb + p.kb_per_split - 1) / p.kb_per_split;  // every split owns at least one k-block
+        p.split_stride = d.split_stride;
+        if (p.splits != d.split_k && d.split_k > 1) { set_error("gemm: split_k %d does not divide %d k-blocks evenly enough (got %d)", d.split_k, num_kb, p.splits); return WDR_ERR_INVALID; }
+    }
+    p.total_tiles = p.tiles_per_batch * d.n_batch * p.n_tiles * p.splits;
     p.out = d.out; p.ldc = d.ldc; p.bias = d.bias;
     p.c_batch_stride = d.c_batch_stride > 0 ? d.c_batch_stride : (int64_t)d.rows_per_batch * d.ldc; p.resid = d.resid; p.pos = d.pos;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     switch (d.epilogue) {
-        case EPI_BIAS_BF16: return launch_gemm<BN, 5, EPI_BIAS_BF16>(ta, tb, p, st);
-        case EPI_BIAS_GELU_BF16: return launch_gemm<BN, 5, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
-        case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<BN, 5, EPI_BIAS_RESID_F32>(ta, tb, p, st);
-        case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<BN, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
-        case EPI_QKV_BF16: return launch_gemm<BN, 5, EPI_QKV_BF16>(ta, tb, p, st);
-        case EPI_F32: return launch_gemm<BN, 5, EPI_F32>(ta, tb, p, st);
+        case EPI_BIAS_BF16: return launch_gemm<128, 5, EPI_BIAS_BF16>(ta, tb, p, st);
+        case EPI_BIAS_GELU_BF16: return launch_gemm<128, 5, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
+        case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<128, 5, EPI_BIAS_RESID_F32>(ta, tb, p, st);
+        case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<128, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
+        case EPI_QKV_BF16: return launch_gemm<128, 5, EPI_QKV_BF16>(ta, tb, p, st);
+        case EPI_F32:
+            if (d.dual_a) return launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st);
+            return BN == 64 ? launch_gemm<64, 7, EPI_F32>(ta, tb, p, st) : launch_gemm<128, 5, EPI_F32>(ta, tb, p, st);
     }
     set_error("unknown epilogue %d", d.epilogue);
     return WDR_ERR_INVALID;

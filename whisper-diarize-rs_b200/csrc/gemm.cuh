@@ -43,6 +43,14 @@ struct GemmDesc {
     int64_t ldt = 0;
     int64_t t_batch_stride = 0;  // column distance between batches in out_t; 0 = rows_per_batch
     int n_split = 0;
+    // weight-streaming (decode) GEMMs: bn = 64 halves the tile width and split_k > 1 cuts K so that >= 148 CTAs stream W;
+    // both require EPI_F32 without bias — split s writes its fp32 partial to out + s*split_stride (consumer sums, in order)
+    int bn = 128;
+    int split_k = 1;
+    int64_t split_stride = 0;
+    // dual_a: A is a (hi, lo) bf16 pair, lo stored a_dual_stride elements after hi; D = (hi + lo) * W^T with W read once
+    bool dual_a = false;
+    int64_t a_dual_stride = 0;
 };
 
 int gemm_bf16(const GemmDesc& d, cudaStream_t st);

@@ -22,6 +22,23 @@ static const WhisperArch kArchs[] = {
     {"large-v3", 1280, 20, 32, 32, 128, 51866, true, 8}, {"large-v3-turbo", 1280, 20, 32, 4, 128, 51866, true, 9},
 };
 
+// (layer, head) alignment heads per DTW preset == whisper_alignment_heads_preset (OpenAI _ALIGNMENT_HEADS)
+static const std::vector<std::pair<int, int>> kAheads[10] = {
+    {{1, 0}, {2, 0}, {2, 5}, {3, 0}, {3, 1}, {3, 2}, {3, 3}, {3, 4}},
+    {{2, 2}, {3, 0}, {3, 2}, {3, 3}, {3, 4}, {3, 5}},
+    {{3, 3}, {4, 7}, {5, 1}, {5, 5}, {5, 7}},
+    {{3, 1}, {4, 2}, {4, 3}, {4, 7}, {5, 1}, {5, 2}, {5, 4}, {5, 6}},
+    {{6, 6}, {7, 0}, {7, 3}, {7, 8}, {8, 2}, {8, 5}, {8, 7}, {9, 0}, {9, 4}, {9, 8}, {9, 10}, {10, 0}, {10, 1}, {10, 2}, {10, 3}, {10, 6}, {10, 11}, {11, 2}, {11, 4}},
+    {{5, 3}, {5, 9}, {8, 0}, {8, 4}, {8, 7}, {8, 8}, {9, 0}, {9, 7}, {9, 9}, {10, 5}},
+    {{11, 4}, {14, 1}, {14, 12}, {14, 14}, {15, 4}, {16, 0}, {16, 4}, {16, 9}, {17, 12}, {17, 14}, {18, 7}, {18, 10}, {18, 15}, {20, 0}, {20, 3}, {20, 9}, {20, 14}, {21, 12}},
+    {{13, 15}, {15, 4}, {15, 15}, {16, 1}, {20, 0}, {23, 4}},
+    {{7, 0}, {10, 17}, {12, 18}, {13, 12}, {16, 1}, {17, 14}, {19, 11}, {21, 4}, {24, 1}, {25, 6}},
+    {{2, 4}, {2, 11}, {3, 3}, {3, 6}, {3, 11}, {3, 14}},
+};
+const std::vector<std::pair<int, int>>* aheads_for_preset(int preset) {
+    return (preset >= 0 && preset < 10) ? &kAheads[preset] : nullptr;
+}
+
 const WhisperArch* find_arch(const char* name) {
     if (!name) return nullptr;
     for (const auto& a : kArchs)
@@ -173,7 +190,12 @@ static int build_weights(wdr_context* ctx) {
     w.enc_lnpost_g = b.vec(d, "encoder.ln_post.weight", 1.0f, 0.1f);
     w.enc_lnpost_b = b.vec(d, "encoder.ln_post.bias", 0.0f, 0.1f);
     // ---- decoder ----
-    w.tok_emb = b.matrix(a.n_vocab, d, "decoder.token_embedding.weight", kWScale);
+    {
+        const int n_pad = (a.n_vocab + 7) / 8 * 8;
+        w.tok_emb = b.alloc<__nv_bfloat16>((size_t)n_pad * d);
+        if (w.tok_emb) cudaMemset(w.tok_emb, 0, sizeof(__nv_bfloat16) * (size_t)n_pad * d);
+        b.fill(w.tok_emb, a.n_vocab, d, d, "decoder.token_embedding.weight", 0.0f, kWScale);
+    }
     w.dec_pos = b.vec(WDR_TEXT_CTX * d, "decoder.positional_embedding", 0.0f, 0.017320508f);
     const float dec_out_scale = kWScale / sqrtf(2.0f * a.n_dec_layer);
     w.dec.resize(a.n_dec_layer);
@@ -291,6 +313,17 @@ extern "C" wdr_context* wdr_init_from_file_with_params(const char* path, wdr_con
     ctx->dtw_preset = params.dtw_aheads_preset;
     ctx->dtw_mem_size = params.dtw_mem_size;
     ctx->flash_attn = params.flash_attn;
+    if (params.dtw_token_timestamps) {
+        // WDR_AHEADS_NONE with DTW on: fall back to the architecture's own preset (the crate always passes a preset, src/transcribe.rs:117-129)
+        const int preset = params.dtw_aheads_preset >= 0 ? params.dtw_aheads_preset : a->dtw_preset;
+        const auto* ah = aheads_for_preset(preset);
+        if (!ah) { set_error("unknown alignment-head preset %d", preset); delete ctx; return nullptr; }
+        for (auto& lh : *ah) {
+            if (lh.first >= a->n_dec_layer || lh.second >= a->n_head) { set_error("alignment-head preset %d does not fit %s", preset, a->name); delete ctx; return nullptr; }
+            ctx->aheads.push_back(lh);
+        }
+        ctx->dtw_preset = preset;
+    }
     if (build_weights(ctx) != WDR_OK) { wdr_free(ctx); return nullptr; }
     ctx->mel_filters.resize((size_t)a->n_mel * 201);
     whisper_mel_filters(a->n_mel, ctx->mel_filters.data());

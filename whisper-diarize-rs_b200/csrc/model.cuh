@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 #include "../../include/wdr.h"
 
@@ -61,7 +62,7 @@ struct WhisperWeights {
     std::vector<EncLayerW> enc;
     float *enc_lnpost_g, *enc_lnpost_b;
     // decoder
-    __nv_bfloat16* tok_emb;  // [n_vocab][d]
+    __nv_bfloat16* tok_emb;  // [round_up(n_vocab, 8)][d], pad rows zero (tied logits GEMM reads whole 8-row groups)
     float* dec_pos;          // [448][d]
     std::vector<DecLayerW> dec;
     float *dec_ln_g, *dec_ln_b;
@@ -78,6 +79,7 @@ struct wdr_context {
     std::vector<void*> allocations;  // everything cudaMalloc'ed for the weights
     wdr_mel* mel = nullptr;
     std::vector<float> mel_filters;  // host copy [n_mel][201]
+    std::vector<std::pair<int, int>> aheads;  // (layer, head) alignment heads of the DTW preset
     int dtw_enabled = 0;
     int dtw_preset = -1;
     size_t dtw_mem_size = 0;

@@ -63,6 +63,8 @@ extern "C" void wdr_free_state(wdr_state* s) {
     cudaSetDevice(s->ctx->device);
     cudaDeviceSynchronize();
     s->enc.release();
+    s->dec.release();
+    s->full.release();
     cudaFree(s->pcm_dev);
     cudaFree(s->nvalid_dev);
     cudaFree(s->enc_out);

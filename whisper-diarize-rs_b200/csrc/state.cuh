@@ -1,14 +1,67 @@
 // state.cuh — wdr_state (whisper_state equivalent): stream, workspaces, device-resident results.
 #pragma once
+#include <string>
+#include <vector>
+#include "decoder.cuh"
 #include "encoder.cuh"
 #include "model.cuh"
 #include "profile.cuh"
+
+namespace wdr {
+// one result segment of the last full call (whisper_segment): times in centiseconds relative to its chunk's first sample
+struct ResultSegment {
+    int chunk = 0;
+    int64_t t0 = 0, t1 = 0;
+    std::string text;
+    float no_speech_prob = 0.0f;
+    std::vector<wdr_token_data> tokens;
+    std::vector<std::string> token_text;
+};
+struct ChunkInfo {
+    int seek_delta, failed, completed, n_sampled, has_ts, result_len, seek_end, n_segments;
+    float no_speech_prob;
+};
+// staging / scratch of the full pipeline (full.cu)
+struct FullScratch {
+    void* pcm_dev = nullptr;
+    size_t pcm_cap = 0;  // bytes
+    int32_t* nvalid_dev = nullptr;
+    size_t nvalid_cap = 0;
+    float* energy_dev = nullptr;
+    size_t energy_cap = 0;
+    float* energy_host = nullptr;  // pinned
+    size_t energy_host_cap = 0;
+    int32_t* done_host = nullptr;  // pinned
+    cudaEvent_t ev_energy = nullptr, ev_energy_done = nullptr, ev_h2d = nullptr;
+    float* dtw_x = nullptr;
+    size_t dtw_x_cap = 0;
+    float* dtw_stat = nullptr;
+    size_t dtw_stat_cap = 0;
+    int32_t* dtw_path = nullptr;
+    size_t dtw_path_cap = 0;
+    int last_decode_steps = 0;
+    void release() {
+        cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path);
+        if (energy_host) cudaFreeHost(energy_host);
+        if (done_host) cudaFreeHost(done_host);
+        if (ev_energy) cudaEventDestroy(ev_energy);
+        if (ev_energy_done) cudaEventDestroy(ev_energy_done);
+        if (ev_h2d) cudaEventDestroy(ev_h2d);
+        *this = FullScratch();
+    }
+};
+}  // namespace wdr
 
 struct wdr_state {
     wdr_context* ctx = nullptr;
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_stream = nullptr;  // H2D staging, overlapped with compute group by group
     wdr::EncoderWorkspace enc;
+    wdr::DecoderWorkspace dec;
+    wdr::FullScratch full;
+    std::vector<wdr::ResultSegment> results;  // segments of the last full call, chunk order
+    std::vector<wdr::ChunkInfo> chunk_info;
+    int lang_id = 0;
     wdr::Profiler prof;
     // device-resident staging / results of the last encode call
     int16_t* pcm_dev = nullptr;
