@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json metric on synthetic data: RTFx (audio-seconds per second) of the batched
-log-mel + Whisper-encoder hot path, tiny.en, 64 x 30 s windows per GPU (BASELINE.json configs[1]).
+"""bench.py — BASELINE.json metric on synthetic data: RTFx (audio-seconds per second).
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA sm_100a through the C ABI)
   python bench.py --impl reference --gpus N ...            the reference path's CPU restatement (oracle port) on the host cores
 
-One JSON line on stdout (rank 0).  `value` = whole-job RTFx with the PCM already resident in HBM; `e2e` = the same
-through the host-pointer C ABI call (pinned host PCM -> H2D -> mel -> encoder, result left in the state as
-whisper_encode leaves it, plus a per-window digest read back); `roofline` = the dominant kernel class, timed with CUDA
-events on the launching stream inside the timed region; `cpu_baseline` = the oracle port on a bounded sample.
+Workloads:
+  --workload transcribe (default)  BASELINE.json configs[2]: large-v3 (128 mel bins) full transcribe + DTW of 1 h of synthetic
+                                   audio = 120 x 30 s windows PER GPU, sharded by window (no data-path collective, weak scaling):
+                                   log-mel -> encoder -> cross-KV -> greedy decode -> token timestamps -> DTW, through wdr_full_batch_*.
+  --workload encoder               BASELINE.json configs[1]: tiny.en batched log-mel + encoder over 64 x 30 s windows on one GPU.
+
+One JSON line on stdout (rank 0).  `value` = whole-job RTFx with the PCM already resident in HBM (wdr_full_batch_i16_dev); `e2e` =
+the same through the host-pointer C ABI call (pinned host PCM -> H2D -> ... -> results read back through the whisper.h-style
+accessors); `roofline` = the dominant kernel class, timed with CUDA events on the launching stream inside the timed region;
+`cpu_baseline` = the oracle port on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -23,18 +28,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ARCH_DIMS = {"tiny.en": (384, 6, 4, 80), "base.en": (512, 8, 6, 80), "small": (768, 12, 12, 80), "large-v3": (1280, 20, 32, 128),
-             "large-v3-turbo": (1280, 20, 32, 128)}
+ARCH_DIMS = {"tiny.en": (384, 6, 4, 4, 80), "base.en": (512, 8, 6, 6, 80), "small": (768, 12, 12, 12, 80),
+             "large-v3": (1280, 20, 32, 32, 128), "large-v3-turbo": (1280, 20, 32, 4, 128)}
 
 
 def flops_per_window(arch):
     """Algorithmic FLOPs (2*M*N*K; softmax/LN/GELU excluded) of one 30 s window, split by kernel class."""
-    d, _, L, n_mel = ARCH_DIMS[arch]
+    d, _, L, Ld, n_mel = ARCH_DIMS[arch]
     T = 1500
     conv = 2 * 3000 * d * 3 * n_mel + 2 * T * d * 3 * d
     lin = L * 24 * T * d * d
     att = L * 4 * T * T * d
-    return {"gemm": conv + lin, "attention": att, "total": conv + lin + att}
+    cross = Ld * 2 * T * d * 2 * d
+    return {"gemm_enc": conv + lin, "attention": att, "cross_kv": cross, "total_enc": conv + lin + att}
 
 
 def synth_pcm(n_chunks, seed0=2000):
@@ -43,7 +49,7 @@ def synth_pcm(n_chunks, seed0=2000):
     from conftest import synth_audio
     base = [synth_audio(seed0 + i, 30.0) for i in range(min(n_chunks, 4))]
     out = np.empty((n_chunks, 480000), np.int16)
-    for i in range(n_chunks):  # 4 distinct windows, rolled so that no two of the 64 are identical
+    for i in range(n_chunks):  # 4 distinct windows, rolled so that no two windows are identical
         out[i] = np.roll(base[i % len(base)], 7919 * (i // len(base)))
     return out
 
@@ -96,21 +102,39 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_rtfx(arch, n_chunks, pcm):
-    """The oracle port (CPU restatement of the reference path: log-mel + encoder) on the host cores."""
-    from oracle import native, weights as W, filters
-    native.build()
-    a = W.ARCHS[arch]
-    w = W.whisper_weights(arch, seed=1234)
-    pw = W.pack_encoder(arch, w)
-    filt = filters.whisper_mel_filters(a["n_mel"])
-    t0 = time.perf_counter()
-    for i in range(n_chunks):
-        x = pcm[i].astype(np.float32) / np.float32(32768.0)
-        mel = native.log_mel(x, filt)[:, :3000]
-        native.whisper_encode(np.ascontiguousarray(mel), arch, pw)
-    dt = time.perf_counter() - t0
-    return n_chunks * 30.0 / dt, dt
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU port (the oracle) — the reported baseline and the --impl reference arm
+# ---------------------------------------------------------------------------------------------------------------------
+class CpuPort:
+    def __init__(self, arch, workload):
+        from oracle import native, weights as W, filters
+        native.build()
+        self.native, self.W = native, W
+        self.arch, self.workload = arch, workload
+        self.a = W.ARCHS[arch]
+        w = W.whisper_weights(arch, seed=1234)
+        self.enc_w = W.pack_encoder(arch, w)
+        self.filt = filters.whisper_mel_filters(self.a["n_mel"])
+        self.dec = native.Decoder(arch, W.pack_decoder(arch, w), bf16=True) if workload == "transcribe" else None
+
+    def run(self, pcm, n_chunks):
+        """Processes n_chunks windows; returns (RTFx, seconds, tokens)."""
+        from oracle import full
+        t0 = time.perf_counter()
+        n_tok = 0
+        for i in range(n_chunks):
+            x = pcm[i % len(pcm)].astype(np.float32) / np.float32(32768.0)
+            mel = self.native.log_mel(x, self.filt)[:, :3000]
+            enc = self.native.whisper_encode(np.ascontiguousarray(mel), self.arch, self.enc_w)
+            if self.dec is not None:
+                r = full.full_window(self.dec, enc, x)
+                n_tok += r.get("n_sampled", 0)
+        dt = time.perf_counter() - t0
+        return n_chunks * 30.0 / dt, dt, n_tok
+
+
+def metric_name(workload):
+    return "RTFx full transcribe+DTW" if workload == "transcribe" else "RTFx mel+encoder"
 
 
 def run_reference(args):
@@ -119,35 +143,52 @@ def run_reference(args):
         return
     cores = os.cpu_count()
     pcm = synth_pcm(4)
-    _, t1 = cpu_port_rtfx(args.arch, 1, pcm)  # warm (builds, page-in) and calibrates the sample size
+    port = CpuPort(args.arch, args.workload)
+    _, t1, _ = port.run(pcm, 1)  # warm (page-in) and calibrate the per-step sample
     per_step = max(1, min(4, int(8.0 / max(t1, 1e-3))))
     for _ in range(max(args.warmup - 1, 0)):
-        cpu_port_rtfx(args.arch, 1, pcm)
+        if t1 < 20.0:
+            port.run(pcm, 1)
+    steps = args.steps if t1 * per_step * args.steps < 240.0 else max(1, int(240.0 / (t1 * per_step)))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_port_rtfx(args.arch, per_step, pcm)
+    for _ in range(steps):
+        port.run(pcm, per_step)
     dt = time.perf_counter() - t0
-    val = args.steps * per_step * 30.0 / dt
-    line = {"impl": "reference", "metric": "RTFx mel+encoder", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    val = steps * per_step * 30.0 / dt
+    line = {"impl": "reference", "metric": metric_name(args.workload), "value": val, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.arch} log-mel + encoder, 30 s windows, seeded synthetic audio and weights", "chunks_per_step": per_step},
+            "config": {"workload": workload_name(args), "chunks_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} x 30 s windows per step on {cores} host threads (OpenMP), oracle/wdr_oracle.c"},
+                             "sample": f"{per_step} x 30 s window(s) per step x {steps} steps on {cores} host threads (OpenMP), oracle/wdr_oracle*.c"},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    if args.workload == "transcribe":
+        return (f"{args.arch} full transcribe (log-mel + encoder + cross-KV + greedy decode + token timestamps + DTW) of "
+                f"{args.chunks} x 30 s windows per GPU, sharded by window (BASELINE configs[2])")
+    return f"{args.arch} batched log-mel + encoder over {args.chunks} x 30 s windows per GPU (BASELINE configs[1])"
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--arch", default="tiny.en")
-    ap.add_argument("--chunks", type=int, default=64, help="30 s windows per GPU per step")
+    ap.add_argument("--workload", default="transcribe", choices=["transcribe", "encoder"])
+    ap.add_argument("--arch", default=None)
+    ap.add_argument("--chunks", type=int, default=None, help="30 s windows per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.arch is None:
+        args.arch = "large-v3" if args.workload == "transcribe" else "tiny.en"
+    if args.chunks is None:
+        args.chunks = 120 if args.workload == "transcribe" else 64
+    if args.steps is None:
+        args.steps = 5 if args.workload == "transcribe" else 40
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         return run_reference(args)
@@ -167,17 +208,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     B = args.chunks
-    ctx = w.Context(args.arch, seed=1234, gpu_device=local)
+    full = args.workload == "transcribe"
+    ctx = w.Context(args.arch, seed=1234, gpu_device=local, enable_dtw=full)
     st = ctx.create_state()
     d = ctx.dims.n_audio_state
     pcm_host = synth_pcm(B, seed0=2000 + 64 * rank)
     pcm_pin = torch.from_numpy(pcm_host).pin_memory()
     pcm_dev = pcm_pin.cuda(non_blocking=False)
-    hidden = torch.empty(B, 1500, d, device="cuda", dtype=torch.float32)
     stream = torch.cuda.current_stream().cuda_stream
+    params = st.full_params() if full else None
+    hidden = None if full else torch.empty(B, 1500, d, device="cuda", dtype=torch.float32)
+    stats = {"segments": 0, "tokens": 0}
 
     def step_resident():
-        st.encode_chunks_dev(pcm_dev.data_ptr(), 480000, B, hidden.data_ptr(), None, stream)
+        if full:
+            stats["segments"] = st.full_batch_dev(pcm_dev.data_ptr(), B, 480000, params)
+        else:
+            st.encode_chunks_dev(pcm_dev.data_ptr(), 480000, B, hidden.data_ptr(), None, stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,15 +261,27 @@ def main():
         ms = float(t.item())
     value = world * B * 30.0 * args.steps / (ms / 1e3)
 
-    # ---- end-to-end arm: host PCM through the C ABI, H2D inside the timed region, digest read back ----
-    for _ in range(2):
+    # ---- end-to-end arm: host PCM through the C ABI, H2D inside the timed region, results read back ----
+    def step_e2e():
+        if full:
+            n = st.full_batch_ptr(pcm_pin.data_ptr(), B, 480000, params)
+            L = w.load()
+            tok = 0
+            for i in range(n):  # whisper.h-style accessors, as the crate walks them (src/transcribe.rs:397-412, 252-282)
+                L.wdr_full_get_segment_t0_from_state(st._h, i)
+                L.wdr_full_get_segment_text_from_state(st._h, i)
+                tok += L.wdr_full_n_tokens_from_state(st._h, i)
+            stats["tokens"] = tok
+            return n
         st.encode_chunks_resident(pcm_pin.data_ptr(), B)
-        dig = st.hidden_digest(B)
+        return st.hidden_digest(B)
+
+    for _ in range(2):
+        res = step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st.encode_chunks_resident(pcm_pin.data_ptr(), B)
-        dig = st.hidden_digest(B)
+        res = step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -230,8 +289,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_val = world * B * 30.0 * args.steps / e2e_s
-    ref_dig = hidden.abs().mean(dim=(1, 2)).cpu().numpy()
-    digest_ok = bool(np.allclose(dig, ref_dig, rtol=1e-3))
+    if full:
+        check = {"segments_e2e": int(res), "segments_resident": int(stats["segments"]), "tokens": int(stats["tokens"]),
+                 "same_segment_count": bool(res == stats["segments"])}
+        d2h = int(B * 224 * 56 + B * 48 + B * 480000 * 4)  # token data + decoder state + energy for the timestamp heuristic
+    else:
+        ref_dig = hidden.abs().mean(dim=(1, 2)).cpu().numpy()
+        check = {"digest_matches_resident_arm": bool(np.allclose(res, ref_dig, rtol=1e-3))}
+        d2h = 4 * B
 
     if rank == 0:
         peaks = {}
@@ -241,46 +306,71 @@ def main():
             pass
         tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        peak_src = "measured (MEASURED_PEAKS.json, sustained)" if peaks else "fallback (B200_PROFILING.md)"
+        peak_src = "measured (MEASURED_PEAKS.json: sustained bf16, copy HBM)" if peaks else "fallback (B200_PROFILING.md)"
         fl = flops_per_window(args.arch)
+        dm, H, L_enc, L_dec, n_mel = ARCH_DIMS[args.arch]
+        total_ms = max(sum(v["ms"] for v in prof.values()), 1e-9)
         kern = {}
-        for name in ("gemm", "attention"):
-            t_ms = prof[name]["ms"]
-            if t_ms > 0:
-                ach = fl[name] * B * args.steps / (t_ms / 1e3) / 1e12
-                kern[name] = {"ms_per_step": t_ms / args.steps, "launches_per_step": prof[name]["records"] / args.steps,
-                              "achieved_tflops": ach, "frac": ach / tf_peak}
-        n_mel = ctx.dims.n_mels
+        # encoder-side GEMMs (conv stem + linears; plus the cross-KV projection in the transcribe workload)
+        gemm_flops = fl["gemm_enc"] + (fl["cross_kv"] if full else 0)
+        if prof["gemm"]["ms"] > 0:
+            ach = gemm_flops * B * args.steps / (prof["gemm"]["ms"] / 1e3) / 1e12
+            kern["gemm"] = {"ms_per_step": prof["gemm"]["ms"] / args.steps, "launches_per_step": prof["gemm"]["records"] / args.steps,
+                            "achieved_tflops": ach, "frac": ach / tf_peak, "algorithmic_gflop_per_window": gemm_flops / 1e9}
+        if prof["attention"]["ms"] > 0:
+            ach = fl["attention"] * B * args.steps / (prof["attention"]["ms"] / 1e3) / 1e12
+            kern["attention"] = {"ms_per_step": prof["attention"]["ms"] / args.steps, "launches_per_step": prof["attention"]["records"] / args.steps,
+                                 "achieved_tflops": ach, "frac": ach / tf_peak}
         mel_bytes = B * (480000 * 2 + n_mel * 3000 * 4)
         if prof["mel"]["ms"] > 0:
             gbs = mel_bytes * args.steps / (prof["mel"]["ms"] / 1e3) / 1e9
             kern["mel"] = {"ms_per_step": prof["mel"]["ms"] / args.steps, "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak,
                            "algorithmic_bytes_per_window": 480000 * 2 + n_mel * 3000 * 4}
-        for name in ("mel_aux", "layernorm"):
-            kern[name] = {"ms_per_step": prof[name]["ms"] / args.steps}
-        dom = max(("gemm", "attention"), key=lambda k: prof[k]["ms"])
-        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)" if dom == "gemm" else "encoder_attention_kernel (tcgen05)",
-                    "achieved": kern[dom]["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": kern[dom]["frac"],
-                    "traffic": None, "peak_source": peak_src,
-                    "share_of_step": prof[dom]["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
-        line = {"metric": "RTFx mel+encoder", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic",
-                "config": {"workload": f"{args.arch} batched log-mel + encoder over {B} x 30 s windows per GPU (BASELINE configs[1])",
-                           "windows_per_gpu": B, "weights": "seeded random-init, bf16 matrices", "pcm": "int16 16 kHz",
-                           "l2": "no explicit flush: each step rewrites ~1 GB of activations (x/h/qk/ff), far above the 126 MB L2"},
-                "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm_host.nbytes), "d2h_bytes_per_step": 4 * B,
-                        "ms_per_step": e2e_s / args.steps * 1e3, "api": "wdr_encode_chunks_i16 (pinned host PCM; result stays in the state) + wdr_state_hidden_digest",
-                        "digest_matches_resident_arm": digest_ok},
+        if prof["dec_cross"]["ms"] > 0:
+            # algorithmic bytes of one cross-attention launch: K_c and V_c of every (window, head): 2 x 1500 x d bf16 per window
+            per_launch = B * 2 * 1500 * dm * 2
+            gbs = per_launch * prof["dec_cross"]["records"] / (prof["dec_cross"]["ms"] / 1e3) / 1e9
+            kern["dec_cross_attention"] = {"ms_per_step": prof["dec_cross"]["ms"] / args.steps, "launches_per_step": prof["dec_cross"]["records"] / args.steps,
+                                           "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak, "algorithmic_bytes_per_launch": per_launch}
+        for name in ("mel_aux", "layernorm", "decoder", "dec_gemm", "dtw", "other"):
+            if prof[name]["ms"] > 0:
+                kern[name] = {"ms_per_step": prof[name]["ms"] / args.steps, "launches_per_step": prof[name]["records"] / args.steps}
+        cand = {k: prof[k]["ms"] for k in ("gemm", "attention", "dec_cross")}
+        dom = max(cand, key=cand.get)
+        if dom == "dec_cross":
+            k = kern["dec_cross_attention"]
+            roofline = {"bound": "hbm", "kernel": "dec_cross_attn_kernel", "achieved": k["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                        "frac": k["frac_hbm"], "traffic": None}
+        else:
+            k = kern[dom]
+            roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)" if dom == "gemm" else "encoder_attention_kernel (tcgen05)",
+                        "achieved": k["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": k["frac"], "traffic": None}
+        roofline["peak_source"] = peak_src
+        roofline["share_of_step"] = cand[dom] / total_ms
+        line = {"metric": metric_name(args.workload), "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": workload_name(args), "windows_per_gpu": B, "weights": "seeded random-init, bf16 matrices",
+                           "pcm": "int16 16 kHz", "decode": "greedy T=0, single_segment, token_timestamps, DTW (alignment-head preset)" if full else None,
+                           "l2": "no explicit flush: each step streams several GB of activations / KV cache, far above the 126 MB L2"},
+                "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm_host.nbytes), "d2h_bytes_per_step": d2h,
+                        "ms_per_step": e2e_s / args.steps * 1e3,
+                        "api": ("wdr_full_batch_i16 (pinned host PCM) + whisper.h-style result accessors" if full else
+                                "wdr_encode_chunks_i16 (pinned host PCM; result stays in the state) + wdr_state_hidden_digest"), **check},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
-                "encoder_tflops_overall": fl["total"] * B * args.steps / (ms / 1e3) / 1e12}
+                "kernel_ms_sum_per_step": total_ms / args.steps,
+                "encoder_tflops_overall": None if full else fl["total_enc"] * B * args.steps / (ms / 1e3) / 1e12}
         if not args.no_cpu_baseline:
             cores = os.cpu_count()
-            _, t1 = cpu_port_rtfx(args.arch, 1, pcm_host)
-            n = max(1, min(8, int(15.0 / max(t1, 1e-3))))
-            v, dt = cpu_port_rtfx(args.arch, n, pcm_host)
+            port = CpuPort(args.arch, args.workload)
+            _, t1, _ = port.run(pcm_host, 1)
+            n = max(1, min(8, int(15.0 / max(t1, 1e-3)))) if t1 < 15.0 else 0
+            if n:
+                v, dt, _ = port.run(pcm_host, n)
+            else:
+                n, v, dt = 1, 30.0 / t1, t1
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} of the {B} windows ({dt:.1f} s of CPU work) on {cores} host threads, oracle/wdr_oracle.c"}
+                                    "sample": f"{n} of the {B} windows ({dt:.1f} s of CPU work) on {cores} host threads, oracle/wdr_oracle*.c"}
         print(json.dumps(line), flush=True)
     st.close()
     ctx.close()

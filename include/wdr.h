@@ -168,9 +168,10 @@ int wdr_encode_chunks_i16(wdr_context* ctx, wdr_state* state, const int16_t* pcm
 /* Per-window mean |hidden| of the encoder output held in the state (n <= windows of the last encode call): a
  * 4-byte-per-window device->host read that proves the encode finished without moving the hidden states. */
 int wdr_state_hidden_digest(wdr_state* state, float* out, int n);
-/* Per-kernel-class CUDA-event timing on the launching stream.  Classes: 0 mel, 1 mel re-layout, 2 tcgen05 GEMM,
- * 3 attention, 4 layernorm, 5 decoder, 6 dtw, 7 other.  collect() sums the finished records (caller has synchronised)
- * into ms[] / launches[] (>= 8 entries each) and returns the number of classes. */
+/* Per-kernel-class CUDA-event timing on the launching stream.  Classes: 0 mel, 1 mel re-layout, 2 tcgen05 GEMM (encoder + cross-KV),
+ * 3 encoder attention, 4 layernorm, 5 decoder small kernels (embed / LN / self-attention / GELU / sampler), 6 dtw, 7 other,
+ * 8 decoder cross-attention (HBM-bound), 9 decoder weight-streaming GEMMs.  collect() sums the finished records (caller has
+ * synchronised) into ms[] / launches[] (>= 10 entries each) and returns the number of classes. */
 int wdr_profile_enable(wdr_state* state, int enable);
 int wdr_profile_collect(wdr_state* state, double* ms, int32_t* launches, int n_classes);
 /* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] = V transposed, window b's tokens at
@@ -228,6 +229,10 @@ int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* state, wdr_full_params 
  * token timestamps + DTW run batched on the device.  Results: segments of all chunks in chunk order. */
 int wdr_full_batch_i16(wdr_context* ctx, wdr_state* state, wdr_full_params params, const int16_t* pcm, int64_t chunk_stride,
                        const int32_t* n_valid, int n_chunks);
+/* Same with the PCM already resident in HBM (DEVICE pointer, chunk_stride >= 480000 elements; n_valid stays a HOST array):
+ * the arm bench.py times as `value`.  Results are still gathered into the state (host) before the call returns. */
+int wdr_full_batch_i16_dev(wdr_context* ctx, wdr_state* state, wdr_full_params params, const int16_t* pcm_dev, int64_t chunk_stride,
+                           const int32_t* n_valid, int n_chunks);
 int wdr_full_n_segments_from_state(wdr_state* state);                                      /* state.full_n_segments(), :397 */
 int wdr_full_get_segment_chunk_from_state(wdr_state* state, int i_segment);                /* chunk the segment belongs to (batch calls) */
 int64_t wdr_full_get_segment_t0_from_state(wdr_state* state, int i_segment);               /* start_timestamp(), cs */

@@ -376,24 +376,47 @@ static inline float gelu_tanh_f(float x) {
 /* C[M][N] (ldc) = A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] (bias may be NULL); accumulate==1 adds into C. */
 static void gemm_nt(const float *A, int lda, const float *W, int ldw, const float *bias, float *C, int ldc,
                     int M, int N, int K, int accumulate) {
+    /* 4 x 4 register tile of dot products along K (both operands are K-contiguous): 8 vector loads feed 16 multiply-adds */
 #pragma omp parallel for schedule(static)
     for (int i0 = 0; i0 < M; i0 += 4) {
         const int im = (M - i0) < 4 ? (M - i0) : 4;
-        for (int j = 0; j < N; j++) {
-            const float *w = W + (size_t)j * ldw;
-            float acc[4] = {0, 0, 0, 0};
-            for (int ii = 0; ii < im; ii++) {
-                const float *a = A + (size_t)(i0 + ii) * lda;
-                float s = 0.0f;
-#pragma omp simd reduction(+ : s)
-                for (int k = 0; k < K; k++) s += a[k] * w[k];
-                acc[ii] = s;
+        for (int j0 = 0; j0 < N; j0 += 4) {
+            const int jm = (N - j0) < 4 ? (N - j0) : 4;
+            float acc[4][4] = {{0}};
+            if (im == 4 && jm == 4) {
+                const float *a0 = A + (size_t)i0 * lda, *a1 = a0 + lda, *a2 = a1 + lda, *a3 = a2 + lda;
+                const float *w0 = W + (size_t)j0 * ldw, *w1 = w0 + ldw, *w2 = w1 + ldw, *w3 = w2 + ldw;
+                float s00 = 0, s01 = 0, s02 = 0, s03 = 0, s10 = 0, s11 = 0, s12 = 0, s13 = 0;
+                float s20 = 0, s21 = 0, s22 = 0, s23 = 0, s30 = 0, s31 = 0, s32 = 0, s33 = 0;
+#pragma omp simd reduction(+ : s00, s01, s02, s03, s10, s11, s12, s13, s20, s21, s22, s23, s30, s31, s32, s33)
+                for (int k = 0; k < K; k++) {
+                    const float x0 = a0[k], x1 = a1[k], x2 = a2[k], x3 = a3[k];
+                    const float y0 = w0[k], y1 = w1[k], y2 = w2[k], y3 = w3[k];
+                    s00 += x0 * y0; s01 += x0 * y1; s02 += x0 * y2; s03 += x0 * y3;
+                    s10 += x1 * y0; s11 += x1 * y1; s12 += x1 * y2; s13 += x1 * y3;
+                    s20 += x2 * y0; s21 += x2 * y1; s22 += x2 * y2; s23 += x2 * y3;
+                    s30 += x3 * y0; s31 += x3 * y1; s32 += x3 * y2; s33 += x3 * y3;
+                }
+                acc[0][0] = s00; acc[0][1] = s01; acc[0][2] = s02; acc[0][3] = s03;
+                acc[1][0] = s10; acc[1][1] = s11; acc[1][2] = s12; acc[1][3] = s13;
+                acc[2][0] = s20; acc[2][1] = s21; acc[2][2] = s22; acc[2][3] = s23;
+                acc[3][0] = s30; acc[3][1] = s31; acc[3][2] = s32; acc[3][3] = s33;
+            } else {
+                for (int ii = 0; ii < im; ii++)
+                    for (int jj = 0; jj < jm; jj++) {
+                        const float *a = A + (size_t)(i0 + ii) * lda, *w = W + (size_t)(j0 + jj) * ldw;
+                        float sum = 0.0f;
+#pragma omp simd reduction(+ : sum)
+                        for (int k = 0; k < K; k++) sum += a[k] * w[k];
+                        acc[ii][jj] = sum;
+                    }
             }
-            for (int ii = 0; ii < im; ii++) {
-                float v = acc[ii] + (bias ? bias[j] : 0.0f);
-                float *c = C + (size_t)(i0 + ii) * ldc + j;
-                *c = accumulate ? *c + v : v;
-            }
+            for (int ii = 0; ii < im; ii++)
+                for (int jj = 0; jj < jm; jj++) {
+                    const float v = acc[ii][jj] + (bias ? bias[j0 + jj] : 0.0f);
+                    float *c = C + (size_t)(i0 + ii) * ldc + j0 + jj;
+                    *c = accumulate ? *c + v : v;
+                }
         }
     }
 }
@@ -523,4 +546,34 @@ int oracle_whisper_encode(const float *mel, int n_mel, int d, int n_head, int n_
     layer_norm_rows(x, p, p + d, out, T, d);
     free(a1); free(x); free(h); free(qkv); free(att); free(ff);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Seeded weight synthesis (oracle/weights.py documents the generator): dst[i] = offset + u_i * scale with
+ * u_i = (int(splitmix64(key + i) >> 40) - 2^23) / 2^23, optionally rounded to bf16 (round-to-nearest-even).
+ * Same arithmetic as the numpy path in weights.py, in C so that large-v3 (1.5 G parameters) is generated in seconds.
+ * ------------------------------------------------------------------------------------------ */
+static inline uint64_t splitmix64_c(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+void oracle_synth_fill(float *dst, int64_t n, uint64_t key, float offset, float scale, int bf16) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) {
+        const uint64_t z = splitmix64_c(key + (uint64_t)i);
+        const int k = (int)(z >> 40);
+        const float u = (float)(k - 8388608) * (1.0f / 8388608.0f);
+        volatile float prod = u * scale; /* no FMA contraction: matches numpy's separate multiply and add */
+        float v = offset + prod;
+        if (bf16) {
+            uint32_t b;
+            memcpy(&b, &v, 4);
+            b = (b + 0x7fffu + ((b >> 16) & 1u)) & 0xffff0000u;
+            memcpy(&v, &b, 4);
+        }
+        dst[i] = v;
+    }
 }

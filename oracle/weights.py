@@ -52,9 +52,29 @@ def bf16_round(x):
     return ((u + r) & np.uint32(0xFFFF0000)).view(np.float32)
 
 
-def synth(seed, name, shape, offset=0.0, scale=W_SCALE, bf16=False):
+def _synth_native(key, n, offset, scale, bf16):
+    """C fast path (oracle_synth_fill, same arithmetic); None if the oracle library is not built."""
+    try:
+        import ctypes as C
+        from . import native
+        L = native.lib()
+        fn = L.oracle_synth_fill
+        fn.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_uint64, C.c_float, C.c_float, C.c_int]
+        fn.restype = None
+        out = np.empty(n, np.float32)
+        fn(out.ctypes.data_as(C.POINTER(C.c_float)), n, int(key), float(np.float32(offset)), float(np.float32(scale)), int(bf16))
+        return out
+    except Exception:
+        return None
+
+
+def synth(seed, name, shape, offset=0.0, scale=W_SCALE, bf16=False, native_ok=True):
     key = _splitmix64(_fnv1a(name) ^ _splitmix64(np.uint64(seed)))
     n = int(np.prod(shape))
+    if native_ok and n >= 65536:
+        v = _synth_native(key, n, offset, scale, bf16)
+        if v is not None:
+            return v.reshape(shape)
     with np.errstate(over="ignore"):
         z = _splitmix64((key + np.arange(n, dtype=np.uint64)) & M64)
     k = (z >> np.uint64(40)).astype(np.int64) - 8388608

@@ -122,6 +122,7 @@ def load():
     L.wdr_full_with_state.argtypes = [C.c_void_p, C.c_void_p, FullParams, f32p, C.c_int]
     L.wdr_full_with_state_i16.argtypes = [C.c_void_p, C.c_void_p, FullParams, i16p, C.c_int]
     L.wdr_full_batch_i16.argtypes = [C.c_void_p, C.c_void_p, FullParams, C.c_void_p, C.c_int64, i32p, C.c_int]
+    L.wdr_full_batch_i16_dev.argtypes = [C.c_void_p, C.c_void_p, FullParams, C.c_void_p, C.c_int64, i32p, C.c_int]
     L.wdr_full_n_segments_from_state.argtypes = [C.c_void_p]
     for fn in ("chunk", "t0", "t1", "text", "no_speech_prob"):
         getattr(L, f"wdr_full_get_segment_{fn}_from_state").argtypes = [C.c_void_p, C.c_int]
@@ -398,10 +399,10 @@ class State:
         _check(load().wdr_profile_enable(self._h, int(on)))
 
     def profile_collect(self):
-        ms = (C.c_double * 8)()
-        ln = (C.c_int32 * 8)()
-        _check(load().wdr_profile_collect(self._h, ms, ln, 8))
-        names = ["mel", "mel_aux", "gemm", "attention", "layernorm", "decoder", "dtw", "other"]
+        ms = (C.c_double * 16)()
+        ln = (C.c_int32 * 16)()
+        _check(load().wdr_profile_collect(self._h, ms, ln, 16))
+        names = ["mel", "mel_aux", "gemm", "attention", "layernorm", "decoder", "dtw", "other", "dec_cross", "dec_gemm"]
         return {n: {"ms": ms[i], "records": ln[i]} for i, n in enumerate(names)}
 
     # ---- full transcription (state.full, reference src/transcribe.rs:389; accessors :393-412, :252-282) ----
@@ -443,6 +444,13 @@ class State:
     def full_batch_ptr(self, pcm_host_ptr, n_chunks, chunk_stride=480000, params=None):
         p = params if params is not None else self.full_params()
         _check(load().wdr_full_batch_i16(self.ctx._h, self._h, p, pcm_host_ptr, chunk_stride, None, n_chunks))
+        return load().wdr_full_n_segments_from_state(self._h)
+
+    def full_batch_dev(self, pcm_dev_ptr, n_chunks, chunk_stride=480000, params=None, n_valid=None):
+        """PCM already in HBM (device pointer int); results gathered into the state.  Returns the number of segments."""
+        p = params if params is not None else self.full_params()
+        nv = None if n_valid is None else _np(n_valid, np.int32)
+        _check(load().wdr_full_batch_i16_dev(self.ctx._h, self._h, p, pcm_dev_ptr, chunk_stride, None if nv is None else _p(nv, i32p), n_chunks))
         return load().wdr_full_n_segments_from_state(self._h)
 
     def n_segments(self):

@@ -102,55 +102,50 @@ __global__ void dec_embed_kernel(const int32_t* __restrict__ seq, int pos, const
         x[(int64_t)b * d + i] = __bfloat162float(tok_emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
 }
 
-// x (+= bias + partials) -> h = bf16(LN(x)).  One CTA (256 threads) per window row; d <= 1280.
-__global__ void __launch_bounds__(256)
+// x (+= bias + partials) -> h = (hi, lo) bf16 of LN(x).  One CTA per window row, one float4 column group per thread
+// (blockDim.x = d / 4 <= 320): the n_splits partial loads of a thread are independent and issue back to back.
+__global__ void __launch_bounds__(320)
 dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_splits, int64_t split_stride, int ldp,
               const float* __restrict__ bias, const float* __restrict__ g, const float* __restrict__ bta, __nv_bfloat16* __restrict__ h, int64_t lo_off,
               int d) {
     __shared__ float red[32];
-    const int row = blockIdx.x, tid = threadIdx.x;
-    float v[5];
-    float s = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int i = tid + k * 256;
-        v[k] = 0.0f;
-        if (i < d) {
-            float a = x[(int64_t)row * d + i];
-            if (part) {
-                const float add = part_sum(part, n_splits, split_stride, (int64_t)row * ldp + i) + bias[i];
-                a += add;
-                x[(int64_t)row * d + i] = a;
-            }
-            v[k] = a;
-            s += a;
+    const int row = blockIdx.x, i = threadIdx.x * 4;
+    float4 a = *reinterpret_cast<const float4*>(x + (int64_t)row * d + i);
+    if (part) {
+        const float* pp = part + (int64_t)row * ldp + i;
+        float4 acc = *reinterpret_cast<const float4*>(pp);
+        for (int s = 1; s < n_splits; s++) {
+            const float4 t = *reinterpret_cast<const float4*>(pp + (int64_t)s * split_stride);
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
+        const float4 bb = *reinterpret_cast<const float4*>(bias + i);
+        a.x += acc.x + bb.x; a.y += acc.y + bb.y; a.z += acc.z + bb.z; a.w += acc.w + bb.w;
+        *reinterpret_cast<float4*>(x + (int64_t)row * d + i) = a;
     }
-    const float mean = block_sum(s, red) / (float)d;
-    float q = 0.0f;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int i = tid + k * 256;
-        if (i < d) { const float c = v[k] - mean; q += c * c; }
-    }
-    const float var = block_sum(q, red) / (float)d;
+    const float mean = block_sum(a.x + a.y + a.z + a.w, red) / (float)d;
+    const float c0 = a.x - mean, c1 = a.y - mean, c2 = a.z - mean, c3 = a.w - mean;
+    const float var = block_sum(c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3, red) / (float)d;
     const float rstd = 1.0f / sqrtf(var + 1e-5f);
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const int i = tid + k * 256;
-        if (i < d) store_split(h, lo_off, (int64_t)row * d + i, (v[k] - mean) * rstd * g[i] + bta[i]);
-    }
+    const float4 gg = *reinterpret_cast<const float4*>(g + i), bb = *reinterpret_cast<const float4*>(bta + i);
+    const int64_t o = (int64_t)row * d + i;
+    store_split(h, lo_off, o, c0 * rstd * gg.x + bb.x);
+    store_split(h, lo_off, o + 1, c1 * rstd * gg.y + bb.y);
+    store_split(h, lo_off, o + 2, c2 * rstd * gg.z + bb.z);
+    store_split(h, lo_off, o + 3, c3 * rstd * gg.w + bb.w);
 }
 
 // self-attention of one (head, window) at position pos.  part: [S][B][3d] partials of the fused QKV GEMM.
 __global__ void __launch_bounds__(128)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
-                     float* __restrict__ sk, float* __restrict__ sv, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off) {
+                     float* __restrict__ sk, float* __restrict__ sv, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
+                     const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */) {
     __shared__ float q[64];
     __shared__ float p[kDecSeqCap];
     __shared__ float red[32];
     __shared__ float acc2[2][64];
     const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    if (win && (win[b].completed | win[b].failed)) return;
+    if (t_limit && pos >= t_limit[b]) return;
     float* K = sk + (int64_t)b * kDecSeqCap * d + hh * 64;
     float* V = sv + (int64_t)b * kDecSeqCap * d + hh * 64;
     if (tid < 64) {
@@ -203,13 +198,15 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
                       const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                       const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
                       float* __restrict__ aw, const int64_t* __restrict__ aw_off, const int32_t* __restrict__ aw_T,
-                      const int32_t* __restrict__ aw_A, int pos) {
+                      const int32_t* __restrict__ aw_A, int pos, const DecWinState* __restrict__ win, const int32_t* __restrict__ t_limit) {
     __shared__ float q[64];
     __shared__ float p[kT + 4];
     __shared__ float red[32];
     __shared__ float accs[8][64];
     const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, g = lane & 7, r = lane >> 3;
+    if (win && (win[b].completed | win[b].failed)) return;  // finished windows stop streaming their K/V
+    if (t_limit && pos >= t_limit[b]) return;
     if (tid < 64) q[tid] = part_sum(part, n_splits, split_stride, (int64_t)b * d + hh * 64 + tid) + b_q[hh * 64 + tid];
     __syncthreads();
     float q8[8];
@@ -565,11 +562,11 @@ static int skinny_gemm(const __nv_bfloat16* A, int B, const __nv_bfloat16* W, in
     if ((size_t)g.split_k * B * N > ws.part_elems) { set_error("decoder: split-K workspace too small"); return WDR_ERR_INVALID; }
     out->splits = g.split_k;
     out->split_stride = g.split_stride;
-    ProfScope ps(prof, KC_DECODER, st);
+    ProfScope ps(prof, KC_DEC_GEMM, st);
     return gemm_bf16(g, st);
 }
 
-int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, bool capture, cudaStream_t st, Profiler* prof) {
+int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof) {
     const WhisperArch& a = ctx->arch;
     const WhisperWeights& w = ctx->w;
     const int d = a.d, H = a.n_head, L = a.n_dec_layer;
@@ -585,13 +582,21 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
     }
     auto ln = [&](const float* g, const float* b) -> int {
         ProfScope ps(prof, KC_DECODER, st);
-        dec_ln_kernel<<<B, 256, 0, st>>>(ws.x, pending ? ws.part : nullptr, sg.splits, sg.split_stride, d, pend_bias, g, b, ws.h, (int64_t)ws.cap_B * d, d);
+        dec_ln_kernel<<<B, d / 4, 0, st>>>(ws.x, pending ? ws.part : nullptr, sg.splits, sg.split_stride, d, pend_bias, g, b, ws.h, (int64_t)ws.cap_B * d, d);
         WDR_LAUNCH_CHECK();
         pending = false;
         return WDR_OK;
     };
     static const int dbg_layers = getenv("WDR_DEBUG_DEC_LAYERS") ? atoi(getenv("WDR_DEBUG_DEC_LAYERS")) : 1 << 30;  // bring-up aid: truncate the stack
-    for (int l = 0; l < L && l < dbg_layers; l++) {
+    const bool capture = mode == DEC_MODE_DTW;
+    const DecWinState* win = mode == DEC_MODE_DECODE ? ws.win : nullptr;
+    const int32_t* t_limit = mode == DEC_MODE_DTW ? ws.aw_T : nullptr;
+    int L_run = L;
+    if (capture && !want_logits) {  // the DTW pass only needs the layers up to the last alignment head
+        L_run = 0;
+        for (auto& lh : ctx->aheads) L_run = std::max(L_run, lh.first + 1);
+    }
+    for (int l = 0; l < L_run && l < dbg_layers; l++) {
         const DecLayerW& e = w.dec[l];
         if ((rc = ln(e.ln1_g, e.ln1_b)) != WDR_OK) return rc;
         if ((rc = skinny_gemm(ws.h, B, e.w_qkv, 3 * d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
@@ -599,7 +604,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             ProfScope ps(prof, KC_DECODER, st);
             dec_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_qkv,
                                                                ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos, d, ws.att,
-                                                               (int64_t)ws.cap_B * d);
+                                                               (int64_t)ws.cap_B * d, win, t_limit);
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
@@ -607,22 +612,24 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         if ((rc = ln(e.ln2_g, e.ln2_b)) != WDR_OK) return rc;
         if ((rc = skinny_gemm(ws.h, B, e.w_cq, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
         {
-            ProfScope ps(prof, KC_DECODER, st);
+            ProfScope ps(prof, KC_DEC_CROSS, st);
             dec_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d,
                                                                 capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T,
-                                                                ws.aw_A, pos);
+                                                                ws.aw_A, pos, win, t_limit);
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
         pending = true; pend_bias = e.b_co;
         if ((rc = ln(e.ln3_g, e.ln3_b)) != WDR_OK) return rc;
-        if ((rc = skinny_gemm(ws.h, B, e.w_fc1, 4 * d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
-        {
-            ProfScope ps(prof, KC_DECODER, st);
-            const int64_t total = (int64_t)B * 4 * d;
-            dec_bias_gelu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_fc1, 4 * d, total, ws.ff,
-                                                                                    (int64_t)ws.cap_B * 4 * d);
-            WDR_LAUNCH_CHECK();
+        {   // fc1 with the bias + GELU + (hi, lo) split fused into the epilogue (N = 4d gives >= 24 x 64-wide tiles; no split-K)
+            GemmDesc g;
+            g.A = ws.h; g.a_row_stride = d; g.rows_per_batch = B; g.n_batch = 1;
+            g.W = e.w_fc1; g.ldw = d; g.N = 4 * d; g.K = d;
+            g.epilogue = EPI_BIAS_GELU_SPLIT; g.out = ws.ff; g.ldc = 4 * d; g.bias = e.b_fc1; g.bn = 64;
+            g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * d;
+            g.split_stride = (int64_t)ws.cap_B * 4 * d;
+            ProfScope ps(prof, KC_DEC_GEMM, st);
+            if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
         if ((rc = skinny_gemm(ws.ff, B, e.w_fc2, d, 4 * d, ws, &sg, st, prof)) != WDR_OK) return rc;
         pending = true; pend_bias = e.b_fc2;
@@ -634,7 +641,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         g.W = w.tok_emb; g.ldw = d; g.N = (int)ws.ldv; g.K = d;
         g.epilogue = EPI_F32; g.out = ws.logits; g.ldc = ws.ldv; g.bn = 64;
         g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * d;
-        ProfScope ps(prof, KC_DECODER, st);
+        ProfScope ps(prof, KC_DEC_GEMM, st);
         if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
     }
     return WDR_OK;

@@ -61,8 +61,12 @@ struct DecoderWorkspace {
 // cross-KV projection of all decoder layers from ws.enc_bf16 (B windows)
 int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaStream_t st, Profiler* prof);
 // one decoder step at position pos for all B windows (token = ws.seq[b][pos]).  want_logits: final LN + logits GEMM.
-// capture: write alignment-head cross-attention rows to ws.aw (DTW pass).
-int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, bool capture, cudaStream_t st, Profiler* prof);
+// mode: DEC_MODE_DECODE = greedy decode (attention skips windows whose DecWinState is completed / failed);
+//       DEC_MODE_FORCED = teacher-forced, every window runs;
+//       DEC_MODE_DTW    = teacher-forced DTW pass: alignment-head cross-attention rows go to ws.aw, windows stop at their own
+//                         length ws.aw_T[b], and without logits only the layers up to the last alignment head run.
+enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2 };
+int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof);
 // whisper_process_logits + greedy whisper_sample_token + decoder bookkeeping on ws.logits; appends to ws.tokens / ws.seq[pos+1]
 int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof);
 

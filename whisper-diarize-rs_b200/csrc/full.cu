@@ -268,7 +268,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     int steps_run = 0;
     if (n_skip < B) {
         for (int i = 0; i < n_prompt; i++)
-            if ((rc = decoder_step(ctx, ws, B, i, i == n_prompt - 1, false, s, &st->prof)) != WDR_OK) return rc;
+            if ((rc = decoder_step(ctx, ws, B, i, i == n_prompt - 1, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
         int32_t* done_host = fs.done_host;
         for (int i = 0; i < n_max; i++) {
             if ((rc = decoder_sample(ctx, ws, B, n_prompt - 1 + i, sp, s, &st->prof)) != WDR_OK) return rc;
@@ -280,7 +280,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                 if (p.abort_callback && p.abort_callback(p.abort_callback_user_data)) { set_error("aborted by callback"); return WDR_ERR_ABORTED; }
             }
             if (i == n_max - 1) break;
-            if ((rc = decoder_step(ctx, ws, B, n_prompt + i, true, false, s, &st->prof)) != WDR_OK) return rc;
+            if ((rc = decoder_step(ctx, ws, B, n_prompt + i, true, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
         }
     }
     fs.last_decode_steps = steps_run;
@@ -380,7 +380,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_T, aw_T.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_A, aw_A.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
         for (int i = 0; i < max_T; i++)
-            if ((rc = decoder_step(ctx, ws, B, i, false, true, s, &st->prof)) != WDR_OK) return rc;
+            if ((rc = decoder_step(ctx, ws, B, i, false, DEC_MODE_DTW, s, &st->prof)) != WDR_OK) return rc;
         std::vector<DtwWindow> wins;
         std::vector<int> win_b;
         for (auto& pd : pend) {
@@ -439,7 +439,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
 
 template <typename In>
 static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, const In* pcm, int64_t chunk_stride,
-                           const int32_t* n_valid, int n_chunks) {
+                           const int32_t* n_valid, int n_chunks, bool pcm_on_device = false) {
     clear_error();
     WDR_REQUIRE(ctx && st && st->ctx == ctx && n_chunks >= 0, "bad arguments");
     WDR_REQUIRE(n_chunks == 0 || (pcm && chunk_stride >= 0), "bad arguments");
@@ -463,6 +463,13 @@ static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_param
     }
     for (int c0 = 0; c0 < n_chunks; c0 += kDecMaxBatch) {
         const int B = std::min(kDecMaxBatch, n_chunks - c0);
+        if (pcm_on_device) {
+            WDR_REQUIRE(chunk_stride >= WDR_CHUNK_SAMPLES, "device PCM needs chunk_stride >= 480000");
+            rc = full_group<In>(ctx, st, p, lang_id, pcm + (size_t)c0 * chunk_stride, chunk_stride, n_valid, c0, B);
+            if (rc != WDR_OK) return rc;
+            if (p.progress_callback) p.progress_callback(ctx, st, (int)(100ll * (c0 + B) / n_chunks), p.progress_callback_user_data);
+            continue;
+        }
         // stage this group's PCM: rows of up to 480000 samples at a fixed device stride
         size_t cap_bytes = fs.pcm_cap;
         void* buf = fs.pcm_dev;
@@ -532,6 +539,11 @@ extern "C" int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* st, wdr_full
 extern "C" int wdr_full_batch_i16(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm, int64_t chunk_stride,
                                   const int32_t* n_valid, int n_chunks) {
     return full_batch_impl<int16_t>(ctx, st, p, pcm, chunk_stride, n_valid, n_chunks);
+}
+
+extern "C" int wdr_full_batch_i16_dev(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm_dev, int64_t chunk_stride,
+                                      const int32_t* n_valid, int n_chunks) {
+    return full_batch_impl<int16_t>(ctx, st, p, pcm_dev, chunk_stride, n_valid, n_chunks, true);
 }
 
 #define SEG_OR(ret)                                                                  \
@@ -626,7 +638,7 @@ extern "C" int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* st, const 
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_A, A.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
     }
     for (int i = 0; i < n_seq; i++) {
-        if ((rc = decoder_step(ctx, ws, B, i, logits_out != nullptr, aheads_out != nullptr, s, &st->prof)) != WDR_OK) return rc;
+        if ((rc = decoder_step(ctx, ws, B, i, logits_out != nullptr, aheads_out ? DEC_MODE_DTW : DEC_MODE_FORCED, s, &st->prof)) != WDR_OK) return rc;
         if (logits_out)
             WDR_CUDA_TRY(cudaMemcpy2DAsync(logits_out + (size_t)i * nv, sizeof(float) * (size_t)n_seq * nv, ws.logits, sizeof(float) * ws.ldv,
                                            sizeof(float) * nv, B, cudaMemcpyDeviceToHost, s));

@@ -54,6 +54,10 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return fmaf(hx, t, hx);
 }
 
+__device__ __forceinline__ float gelu_tanh_precise(float x) {
+    return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -241,7 +245,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             v.x = gelu_tanh(v.x); v.y = gelu_tanh(v.y); v.z = gelu_tanh(v.z); v.w = gelu_tanh(v.w);
                         }
                         const int64_t off = c_base + (int64_t)row * p.ldc + n;
-                        if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16) {
+                        if (EPI == EPI_BIAS_GELU_SPLIT) {
+                            v.x = gelu_tanh_precise(v.x); v.y = gelu_tanh_precise(v.y); v.z = gelu_tanh_precise(v.z); v.w = gelu_tanh_precise(v.w);
+                            const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+                            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                            uint2 whi, wlo;
+                            whi.x = *reinterpret_cast<const uint32_t*>(&h0);
+                            whi.y = *reinterpret_cast<const uint32_t*>(&h1);
+                            wlo.x = pack_bf16(v.x - f0.x, v.y - f0.y);
+                            wlo.y = pack_bf16(v.z - f1.x, v.w - f1.y);
+                            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32 + row) * p.ldc + n;
+                            *reinterpret_cast<uint2*>(o) = whi;
+                            *reinterpret_cast<uint2*>(o + p.split_stride) = wlo;
+                        } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16) {
                             uint2 w;
                             w.x = pack_bf16(v.x, v.y);
                             w.y = pack_bf16(v.z, v.w);
@@ -351,7 +367,8 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     if (d.epilogue == EPI_QKV_BF16) WDR_REQUIRE(d.out_t && d.n_split % 32 == 0, "QKV epilogue needs out_t and n_split % 32 == 0");
     const int BN = d.bn == 64 ? 64 : 128;
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
-    if (d.split_k > 1 || d.bn == 64) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 are plain fp32-partial GEMMs (EPI_F32, no bias)");
+    if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
+    else if (d.split_k > 1 || d.bn == 64) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 are plain fp32-partial GEMMs (EPI_F32, no bias)");
     CUtensorMap ta, tb;
     {
         // in tap mode the last tap reads rows up to rows_per_batch - 1 + (taps - 1): the caller's buffer holds them
@@ -396,6 +413,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<128, 5, EPI_BIAS_RESID_F32>(ta, tb, p, st);
         case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<128, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
         case EPI_QKV_BF16: return launch_gemm<128, 5, EPI_QKV_BF16>(ta, tb, p, st);
+        case EPI_BIAS_GELU_SPLIT: return launch_gemm<64, 4, EPI_BIAS_GELU_SPLIT, true>(ta, tb, p, st);
         case EPI_F32:
             if (d.dual_a) return launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st);
             return BN == 64 ? launch_gemm<64, 7, EPI_F32>(ta, tb, p, st) : launch_gemm<128, 5, EPI_F32>(ta, tb, p, st);

@@ -13,6 +13,7 @@ enum GemmEpilogue {
     EPI_BIAS_GELU_POS_F32 = 3,  // out_f32 = gelu(acc + bias) + pos[row_in_batch][n]
     EPI_QKV_BF16 = 4,           // n < n_split: out_bf16[row][n] = acc + bias;  n >= n_split: out_t[n - n_split][row] = acc + bias
     EPI_F32 = 5,                // out_f32 = acc + bias
+    EPI_BIAS_GELU_SPLIT = 6,    // v = gelu_exact(acc + bias) stored as a (hi, lo) bf16 pair: out[.] = hi, out[. + split_stride] = lo (decoder fc1)
 };
 
 // D[M x N] = A[M x K] * W[N x K]^T.  A rows are organised as n_batch groups of rows_per_batch rows (row r of
