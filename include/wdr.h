@@ -257,6 +257,25 @@ int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* i
 int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* state, const float* enc, int n_chunks, const int32_t* seq, int n_seq,
                               float* logits_out, float* aheads_out);
 
+/* ---- speaker assignment (pyannote_rs::EmbeddingManager, src/transcribe.rs:342, 480-492) -------------------- */
+typedef struct wdr_spk wdr_spk;
+wdr_spk* wdr_spk_init(size_t max_speakers);            /* EmbeddingManager::new(max_speakers); SIZE_MAX = unlimited (src/engine.rs:108-111) */
+void wdr_spk_free(wdr_spk* m);
+int wdr_spk_count(wdr_spk* m);                         /* get_all_speakers().len() */
+/* search_speaker(embedding, threshold): best cosine match if sim > threshold (strict), else a new id while below the cap.
+ * Returns the speaker id (>= 1) or 0 for None (the crate renders "?", src/transcribe.rs:493-495). Host pointer. */
+int wdr_spk_search(wdr_spk* m, const float* emb, int dim, float threshold);
+/* get_best_speaker_match(embedding): best cosine match regardless of threshold; WDR_ERR_INVALID when no speaker is stored. */
+int wdr_spk_best_match(wdr_spk* m, const float* emb, int dim);
+/* Pairwise cosine similarity S[N][N] of embeddings emb[N][D] on the device (host pointers). */
+int wdr_cosine_matrix(const float* emb, int N, int D, float* S);
+/* The crate's per-segment policy (cap reached -> best match, else search/create) as a pure function of S, segments in time
+ * order; labels[i] = speaker id >= 1 or 0 for "?".  Returns the number of speakers.  Bit-exact given S. */
+int wdr_cluster_leader(const float* S, int N, float threshold, size_t max_speakers, int32_t* labels);
+/* Average-linkage agglomerative clustering of S on the device: merges the first maximal pair while its similarity > threshold.
+ * labels[i] = 1.. in order of each cluster's smallest member.  Returns the number of clusters.  Bit-exact given S. */
+int wdr_cluster_agglomerative(const float* S, int N, float threshold, int32_t* labels);
+
 /* Bring-up aid: copies a decoder workspace buffer of the last step to the host as fp32 (0 x, 1 h, 2 att, 3 ff, 4 layer-0 cross K|V,
  * 5 split-K partials). */
 int wdr_debug_decoder_read(wdr_state* state, int which, float* out, int64_t count);

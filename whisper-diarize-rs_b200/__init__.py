@@ -15,4 +15,5 @@ from .capi import (  # noqa: F401
     signal_energy, convert_integer_to_float_audio, mel_n_len, gemm_bf16_dev,
     Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
     FullParams, TokenData, lang_str, lang_id,
+    EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
 )

@@ -144,6 +144,15 @@ def load():
     L.wdr_token_to_str.restype = C.c_char_p
     L.wdr_full_get_chunk_info_from_state.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
     L.wdr_decode_teacher_forced.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, i32p, C.c_int, f32p, f32p]
+    L.wdr_spk_init.restype = C.c_void_p
+    L.wdr_spk_init.argtypes = [C.c_size_t]
+    L.wdr_spk_free.argtypes = [C.c_void_p]
+    L.wdr_spk_count.argtypes = [C.c_void_p]
+    L.wdr_spk_search.argtypes = [C.c_void_p, f32p, C.c_int, C.c_float]
+    L.wdr_spk_best_match.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.wdr_cosine_matrix.argtypes = [f32p, C.c_int, C.c_int, f32p]
+    L.wdr_cluster_leader.argtypes = [f32p, C.c_int, C.c_float, C.c_size_t, i32p]
+    L.wdr_cluster_agglomerative.argtypes = [f32p, C.c_int, C.c_float, i32p]
     _lib = L
     return L
 
@@ -508,3 +517,60 @@ def lang_str(i):
 
 def lang_id(s):
     return load().wdr_lang_id(s.encode())
+
+
+SIZE_MAX = (1 << 64) - 1
+
+
+class EmbeddingManager:
+    """wdr_spk: pyannote_rs::EmbeddingManager (reference src/transcribe.rs:342, 480-492).  Pure host logic."""
+
+    def __init__(self, max_speakers=SIZE_MAX):
+        self.max_speakers = max_speakers
+        self._h = load().wdr_spk_init(max_speakers)
+
+    def close(self):
+        if self._h:
+            load().wdr_spk_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def count(self):
+        return load().wdr_spk_count(self._h)
+
+    def search_speaker(self, emb, threshold):
+        e = _np(emb, np.float32)
+        r = _check(load().wdr_spk_search(self._h, _p(e, f32p), len(e), float(threshold)))
+        return r if r > 0 else None
+
+    def get_best_speaker_match(self, emb):
+        e = _np(emb, np.float32)
+        return _check(load().wdr_spk_best_match(self._h, _p(e, f32p), len(e)))
+
+    def assign(self, emb, threshold):
+        """The crate's policy (src/transcribe.rs:482-492): id, or None for "?"."""
+        if self.count() == self.max_speakers:
+            return self.get_best_speaker_match(emb)
+        return self.search_speaker(emb, threshold)
+
+
+def cosine_matrix(emb):
+    e = _np(emb, np.float32)
+    S = np.empty((e.shape[0], e.shape[0]), np.float32)
+    _check(load().wdr_cosine_matrix(_p(e, f32p), e.shape[0], e.shape[1], _p(S, f32p)))
+    return S
+
+
+def cluster_leader(S, threshold, max_speakers=SIZE_MAX):
+    s = _np(S, np.float32)
+    labels = np.empty(s.shape[0], np.int32)
+    _check(load().wdr_cluster_leader(_p(s, f32p), s.shape[0], float(threshold), max_speakers, _p(labels, i32p)))
+    return labels
+
+
+def cluster_agglomerative(S, threshold):
+    s = _np(S, np.float32)
+    labels = np.empty(s.shape[0], np.int32)
+    _check(load().wdr_cluster_agglomerative(_p(s, f32p), s.shape[0], float(threshold), _p(labels, i32p)))
+    return labels
