@@ -257,6 +257,34 @@ int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* i
 int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* state, const float* enc, int n_chunks, const int32_t* seq, int n_seq,
                               float* logits_out, float* aheads_out);
 
+/* ---- Silero VAD (WhisperVadContext, reference src/vad.rs:15-43; whisper.cpp whisper_vad_*) ----------------- */
+typedef struct wdr_vad wdr_vad;
+typedef struct wdr_vad_segments wdr_vad_segments;
+typedef struct wdr_vad_context_params { int n_threads, use_gpu, gpu_device; uint64_t seed; } wdr_vad_context_params;  /* + seed: synthetic weights */
+/* == whisper_vad_params (WhisperVadParams; the crate sets min_silence_duration_ms = 100, src/vad.rs:22) */
+typedef struct wdr_vad_params {
+    float threshold; int min_speech_duration_ms, min_silence_duration_ms; float max_speech_duration_s; int speech_pad_ms; float samples_overlap;
+} wdr_vad_params;
+wdr_vad_context_params wdr_vad_default_context_params(void);                     /* whisper_vad_default_context_params */
+wdr_vad_params wdr_vad_default_params(void);                                      /* whisper_vad_default_params */
+wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad_context_params params);  /* path NULL: seeded weights */
+void wdr_vad_free(wdr_vad* v);
+/* whisper_vad_detect_speech: one probability per 512-sample frame (last frame zero padded); LSTM state reset per call. Host ptr. */
+int wdr_vad_detect_speech(wdr_vad* v, const float* pcm, int n);
+int wdr_vad_n_probs(wdr_vad* v);
+const float* wdr_vad_probs(wdr_vad* v);
+/* Batched form over independent streams (files / shards) of int16 PCM: stream s = pcm[offsets[s] .. +n_samples[s]); probabilities of
+ * stream s land at probs_out[frame_offsets_out[s] ..).  frame_offsets_out has n_streams+1 entries.  Host pointers. */
+int wdr_vad_detect_speech_batch_i16(wdr_vad* v, const int16_t* pcm, const int64_t* offsets, const int32_t* n_samples, int n_streams,
+                                    float* probs_out, int64_t* frame_offsets_out);
+wdr_vad_segments* wdr_vad_segments_from_probs(wdr_vad* v, wdr_vad_params params);                         /* whisper_vad_segments_from_probs */
+wdr_vad_segments* wdr_vad_segments_from_probs_array(const float* probs, int n_probs, wdr_vad_params params);  /* same on a caller-supplied array (host logic only) */
+wdr_vad_segments* wdr_vad_segments_from_samples(wdr_vad* v, wdr_vad_params params, const float* pcm, int n);  /* vad.segments_from_samples, src/vad.rs:31 */
+int wdr_vad_segments_n(wdr_vad_segments* s);
+float wdr_vad_segments_get_segment_t0(wdr_vad_segments* s, int i);   /* centiseconds, as src/vad.rs:40-43 consumes them */
+float wdr_vad_segments_get_segment_t1(wdr_vad_segments* s, int i);
+void wdr_vad_free_segments(wdr_vad_segments* s);
+
 /* ---- speaker assignment (pyannote_rs::EmbeddingManager, src/transcribe.rs:342, 480-492) -------------------- */
 typedef struct wdr_spk wdr_spk;
 wdr_spk* wdr_spk_init(size_t max_speakers);            /* EmbeddingManager::new(max_speakers); SIZE_MAX = unlimited (src/engine.rs:108-111) */

@@ -15,5 +15,7 @@ from .capi import (  # noqa: F401
     signal_energy, convert_integer_to_float_audio, mel_n_len, gemm_bf16_dev,
     Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
     FullParams, TokenData, lang_str, lang_id,
+    VadContext, VadParams, vad_default_params, vad_segments_from_probs,
     EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
 )
+from . import host  # noqa: F401,E402  (host-side mirror of the reference's own Rust logic around the boundary)

@@ -52,6 +52,16 @@ class FullParams(C.Structure):
                 ("abort_callback_user_data", C.c_void_p)]
 
 
+class VadContextParams(C.Structure):
+    _fields_ = [("n_threads", C.c_int), ("use_gpu", C.c_int), ("gpu_device", C.c_int), ("seed", C.c_uint64)]
+
+
+class VadParams(C.Structure):
+    """== wdr_vad_params == whisper_vad_params (WhisperVadParams, reference src/vad.rs:21-27)."""
+    _fields_ = [("threshold", C.c_float), ("min_speech_duration_ms", C.c_int), ("min_silence_duration_ms", C.c_int),
+                ("max_speech_duration_s", C.c_float), ("speech_pad_ms", C.c_int), ("samples_overlap", C.c_float)]
+
+
 class WdrError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"wdr error {code}: {msg}")
@@ -144,6 +154,28 @@ def load():
     L.wdr_token_to_str.restype = C.c_char_p
     L.wdr_full_get_chunk_info_from_state.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
     L.wdr_decode_teacher_forced.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, i32p, C.c_int, f32p, f32p]
+    L.wdr_vad_default_context_params.restype = VadContextParams
+    L.wdr_vad_default_params.restype = VadParams
+    L.wdr_vad_init_from_file_with_params.restype = C.c_void_p
+    L.wdr_vad_init_from_file_with_params.argtypes = [C.c_char_p, VadContextParams]
+    L.wdr_vad_free.argtypes = [C.c_void_p]
+    L.wdr_vad_detect_speech.argtypes = [C.c_void_p, f32p, C.c_int]
+    L.wdr_vad_n_probs.argtypes = [C.c_void_p]
+    L.wdr_vad_probs.argtypes = [C.c_void_p]
+    L.wdr_vad_probs.restype = f32p
+    L.wdr_vad_detect_speech_batch_i16.argtypes = [C.c_void_p, i16p, i64p, i32p, C.c_int, f32p, i64p]
+    L.wdr_vad_segments_from_probs.restype = C.c_void_p
+    L.wdr_vad_segments_from_probs.argtypes = [C.c_void_p, VadParams]
+    L.wdr_vad_segments_from_probs_array.restype = C.c_void_p
+    L.wdr_vad_segments_from_probs_array.argtypes = [f32p, C.c_int, VadParams]
+    L.wdr_vad_segments_from_samples.restype = C.c_void_p
+    L.wdr_vad_segments_from_samples.argtypes = [C.c_void_p, VadParams, f32p, C.c_int]
+    L.wdr_vad_segments_n.argtypes = [C.c_void_p]
+    L.wdr_vad_segments_get_segment_t0.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_vad_segments_get_segment_t0.restype = C.c_float
+    L.wdr_vad_segments_get_segment_t1.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_vad_segments_get_segment_t1.restype = C.c_float
+    L.wdr_vad_free_segments.argtypes = [C.c_void_p]
     L.wdr_spk_init.restype = C.c_void_p
     L.wdr_spk_init.argtypes = [C.c_size_t]
     L.wdr_spk_free.argtypes = [C.c_void_p]
@@ -574,3 +606,66 @@ def cluster_agglomerative(S, threshold):
     labels = np.empty(s.shape[0], np.int32)
     _check(load().wdr_cluster_agglomerative(_p(s, f32p), s.shape[0], float(threshold), _p(labels, i32p)))
     return labels
+
+
+def vad_default_params(**kw):
+    p = load().wdr_vad_default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _collect_segments(h):
+    L = load()
+    if not h:
+        raise WdrError(-3, L.wdr_last_error().decode())
+    try:
+        return [(L.wdr_vad_segments_get_segment_t0(h, i), L.wdr_vad_segments_get_segment_t1(h, i)) for i in range(L.wdr_vad_segments_n(h))]
+    finally:
+        L.wdr_vad_free_segments(h)
+
+
+def vad_segments_from_probs(probs, params=None):
+    """whisper_vad_segments_from_probs on a caller-supplied probability array (host logic; no GPU needed) -> [(t0_cs, t1_cs)]."""
+    pr = _np(probs, np.float32)
+    return _collect_segments(load().wdr_vad_segments_from_probs_array(_p(pr, f32p), len(pr), params if params is not None else vad_default_params()))
+
+
+class VadContext:
+    """wdr_vad: WhisperVadContext (reference src/vad.rs:15-18)."""
+
+    def __init__(self, seed=1234, gpu_device=0):
+        L = load()
+        p = L.wdr_vad_default_context_params()
+        p.seed = seed
+        p.gpu_device = gpu_device
+        self._h = L.wdr_vad_init_from_file_with_params(None, p)
+        if not self._h:
+            raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, L.wdr_last_error().decode())
+
+    def close(self):
+        if self._h:
+            load().wdr_vad_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def detect_speech(self, pcm_f32):
+        x = _np(pcm_f32, np.float32)
+        _check(load().wdr_vad_detect_speech(self._h, _p(x, f32p), len(x)))
+        n = load().wdr_vad_n_probs(self._h)
+        return np.ctypeslib.as_array(load().wdr_vad_probs(self._h), shape=(n,)).copy() if n else np.zeros(0, np.float32)
+
+    def detect_speech_batch(self, pcm_i16, offsets, n_samples):
+        x = _np(pcm_i16, np.int16).reshape(-1)
+        off, n = _np(offsets, np.int64), _np(n_samples, np.int32)
+        nf = int(((n.astype(np.int64) + 511) // 512).sum())
+        probs = np.empty(max(nf, 1), np.float32)
+        foff = np.empty(len(n) + 1, np.int64)
+        _check(load().wdr_vad_detect_speech_batch_i16(self._h, _p(x, i16p), _p(off, i64p), _p(n, i32p), len(n), _p(probs, f32p), _p(foff, i64p)))
+        return [probs[foff[i]:foff[i + 1]].copy() for i in range(len(n))]
+
+    def segments_from_samples(self, pcm_f32, params=None):
+        """vad.segments_from_samples(params, &samples) -> [(start_cs, end_cs)] (reference src/vad.rs:31)."""
+        x = _np(pcm_f32, np.float32)
+        return _collect_segments(load().wdr_vad_segments_from_samples(self._h, params if params is not None else vad_default_params(), _p(x, f32p), len(x)))

@@ -1,0 +1,547 @@
+// vad.cu — Silero-VAD frame scoring on the device and whisper.cpp's segment extraction on the host.
+//
+// Replaces whisper_vad_init_from_file_with_params / whisper_vad_detect_speech / whisper_vad_segments_from_probs /
+// whisper_vad_segments_from_samples and the segment accessors, which the crate reaches through WhisperVadContext
+// (reference src/vad.rs:15-43).  No Silero model file can exist offline: the context synthesises seeded weights
+// with the documented shapes (the STFT basis is the true windowed DFT basis).
+//
+// Device work, batched over independent streams (files / shards):
+//   vad_frontend_kernel  8 frames per CTA: reflect pad 64 -> STFT conv (k 256, stride 128, 129 re + 129 im) -> magnitude ->
+//                        4 x (conv1d k3 + ReLU; strides 1,2,2,1) -> LSTM input projection W_ih x + b_ih + b_hh.  Every weight is
+//                        stored transposed ([k][out]) so that consecutive threads (= output channels) read consecutive words.
+//   vad_lstm_kernel      one persistent CTA per stream, 512 threads: thread r keeps row r of W_hh in registers, h lives in shared
+//                        memory; per frame one 128-long dot per thread, the cell update by 128 threads, ReLU -> 1x1 conv -> sigmoid.
+// Host work: the threshold / hysteresis state machine of whisper_vad_segments_from_probs (bit-exact given the probabilities).
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+namespace wdr {
+
+constexpr int kVadWin = 512, kVadPad = 64, kVadFramesPerCta = 8, kVadThreads = 256;
+constexpr int kVadPadded = kVadWin + 2 * kVadPad;  // 640
+constexpr size_t kVadSmemBytes = sizeof(float) * (kVadFramesPerCta * kVadPadded + kVadFramesPerCta * 258 * 4 + kVadFramesPerCta * 129 * 4);
+
+struct VadWeights {
+    float* basis_t;   // [256][258]
+    float* w_t[4];    // conv i: [C_in*3][C_out]
+    float* b[4];
+    float* wih_t;     // [128][512]
+    float* b_gates;   // [512] = b_ih + b_hh
+    float* whh;       // [512][128]
+    float* w_out;     // [128]
+    float b_out;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// pcm of stream s: x + off[s], n[s] samples; frames of stream s start at frame_off[s].  gates out: [total_frames][512].
+template <typename In>
+__global__ void __launch_bounds__(kVadThreads)
+vad_frontend_kernel(const In* __restrict__ pcm, const int64_t* __restrict__ off, const int32_t* __restrict__ n_samples,
+                    const int64_t* __restrict__ frame_off, int n_streams, VadWeights w, float* __restrict__ gates) {
+    // dynamic shared memory, regions reused once their producer stage is done:
+    //   xs  [8][640]      padded frames            -> later a1 [8][128][4]
+    //   st  [8][258][4]   raw STFT (re | im)       -> later a2 [8][64][2], a3 [8][64], a4 [8][128]
+    //   mag [8][129][4]
+    extern __shared__ float vad_sm[];
+    float (*xs)[kVadPadded] = reinterpret_cast<float (*)[kVadPadded]>(vad_sm);
+    float (*st)[258][4] = reinterpret_cast<float (*)[258][4]>(vad_sm + kVadFramesPerCta * kVadPadded);
+    float (*mag)[129][4] = reinterpret_cast<float (*)[129][4]>(vad_sm + kVadFramesPerCta * kVadPadded + kVadFramesPerCta * 258 * 4);
+    float (*a1)[128][4] = reinterpret_cast<float (*)[128][4]>(vad_sm);
+    float* st_base = vad_sm + kVadFramesPerCta * kVadPadded;
+    float (*a2)[64][2] = reinterpret_cast<float (*)[64][2]>(st_base);
+    float (*a3)[64] = reinterpret_cast<float (*)[64]>(st_base + kVadFramesPerCta * 64 * 2);
+    float (*a4)[128] = reinterpret_cast<float (*)[128]>(st_base + kVadFramesPerCta * 64 * 2 + kVadFramesPerCta * 64);
+    const int tid = threadIdx.x;
+    // which stream / frame range does this CTA cover?  blockIdx.x enumerates groups of 8 frames, stream by stream
+    int s = 0;
+    int64_t g = blockIdx.x;
+    for (; s < n_streams; s++) {
+        const int64_t nf = frame_off[s + 1] - frame_off[s];
+        const int64_t groups = (nf + kVadFramesPerCta - 1) / kVadFramesPerCta;
+        if (g < groups) break;
+        g -= groups;
+    }
+    if (s >= n_streams) return;
+    const int64_t nf = frame_off[s + 1] - frame_off[s];
+    const int f0 = (int)(g * kVadFramesPerCta);
+    const int nfr = (int)min((int64_t)kVadFramesPerCta, nf - f0);
+    const In* x = pcm + off[s];
+    const int n = n_samples[s];
+    // ---- stage: frames with reflect padding (frame j = samples [j*512, (j+1)*512), zero beyond n) ----
+    for (int i = tid; i < kVadFramesPerCta * kVadPadded; i += kVadThreads) {
+        const int f = i / kVadPadded, p = i % kVadPadded;
+        int q = p - kVadPad;                       // position inside the frame, reflected at both ends
+        if (q < 0) q = -q;
+        if (q >= kVadWin) q = 2 * (kVadWin - 1) - q;
+        const int64_t sidx = (int64_t)(f0 + f) * kVadWin + q;
+        float v = 0.0f;
+        if (f < nfr && sidx < n) v = sizeof(In) == 2 ? (float)x[sidx] * (1.0f / 32768.0f) : (float)x[sidx];
+        xs[f][p] = v;
+    }
+    __syncthreads();
+    // ---- STFT: channel c (258 over two rounds of threads) x 4 hops x 8 frames ----
+    for (int c = tid; c < 258; c += kVadThreads) {
+        float acc[kVadFramesPerCta][4];
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) acc[f][t] = 0.0f;
+        for (int k = 0; k < 256; k++) {
+            const float wv = __ldg(&w.basis_t[k * 258 + c]);
+#pragma unroll
+            for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+                for (int t = 0; t < 4; t++) acc[f][t] = fmaf(wv, xs[f][t * 128 + k], acc[f][t]);
+        }
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) st[f][c][t] = acc[f][t];
+    }
+    __syncthreads();
+    for (int i = tid; i < kVadFramesPerCta * 129 * 4; i += kVadThreads) {
+        const int f = i / (129 * 4), c = (i / 4) % 129, t = i & 3;
+        const float re = st[f][c][t], im = st[f][129 + c][t];
+        mag[f][c][t] = sqrtf(re * re + im * im);
+    }
+    __syncthreads();
+    // ---- conv1: 129 -> 128, k3, s1, p1 (T 4 -> 4) ----
+    if (tid < 128) {
+        float acc[kVadFramesPerCta][4];
+        const float bv = w.b[0][tid];
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) acc[f][t] = 0.0f;
+        for (int ic = 0; ic < 129; ic++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float wv = __ldg(&w.w_t[0][(ic * 3 + k) * 128 + tid]);
+#pragma unroll
+                for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const int ti = t + k - 1;
+                        if (ti >= 0 && ti < 4) acc[f][t] = fmaf(wv, mag[f][ic][ti], acc[f][t]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) a1[f][tid][t] = fmaxf(acc[f][t] + bv, 0.0f);
+    }
+    __syncthreads();
+    // ---- conv2: 128 -> 64, k3, s2, p1 (T 4 -> 2) ----
+    if (tid < 64) {
+        float acc[kVadFramesPerCta][2];
+        const float bv = w.b[1][tid];
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) { acc[f][0] = 0.0f; acc[f][1] = 0.0f; }
+        for (int ic = 0; ic < 128; ic++) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float wv = __ldg(&w.w_t[1][(ic * 3 + k) * 64 + tid]);
+#pragma unroll
+                for (int f = 0; f < kVadFramesPerCta; f++)
+#pragma unroll
+                    for (int t = 0; t < 2; t++) {
+                        const int ti = 2 * t + k - 1;
+                        if (ti >= 0 && ti < 4) acc[f][t] = fmaf(wv, a1[f][ic][ti], acc[f][t]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) { a2[f][tid][0] = fmaxf(acc[f][0] + bv, 0.0f); a2[f][tid][1] = fmaxf(acc[f][1] + bv, 0.0f); }
+    }
+    __syncthreads();
+    // ---- conv3: 64 -> 64, k3, s2, p1 (T 2 -> 1): taps k=1,2 hit positions 0,1 ----
+    if (tid < 64) {
+        float acc[kVadFramesPerCta];
+        const float bv = w.b[2][tid];
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) acc[f] = 0.0f;
+        for (int ic = 0; ic < 64; ic++) {
+            const float w1 = __ldg(&w.w_t[2][(ic * 3 + 1) * 64 + tid]), w2 = __ldg(&w.w_t[2][(ic * 3 + 2) * 64 + tid]);
+#pragma unroll
+            for (int f = 0; f < kVadFramesPerCta; f++) acc[f] = fmaf(w2, a2[f][ic][1], fmaf(w1, a2[f][ic][0], acc[f]));
+        }
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) a3[f][tid] = fmaxf(acc[f] + bv, 0.0f);
+    }
+    __syncthreads();
+    // ---- conv4: 64 -> 128, k3, s1, p1 (T 1 -> 1): only the centre tap sees data ----
+    if (tid < 128) {
+        float acc[kVadFramesPerCta];
+        const float bv = w.b[3][tid];
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) acc[f] = 0.0f;
+        for (int ic = 0; ic < 64; ic++) {
+            const float w1 = __ldg(&w.w_t[3][(ic * 3 + 1) * 128 + tid]);
+#pragma unroll
+            for (int f = 0; f < kVadFramesPerCta; f++) acc[f] = fmaf(w1, a3[f][ic], acc[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) a4[f][tid] = fmaxf(acc[f] + bv, 0.0f);
+    }
+    __syncthreads();
+    // ---- LSTM input projection: 512 gate rows over two rounds of threads ----
+    for (int r = tid; r < 512; r += kVadThreads) {
+        float acc[kVadFramesPerCta];
+        const float bv = w.b_gates[r];
+#pragma unroll
+        for (int f = 0; f < kVadFramesPerCta; f++) acc[f] = 0.0f;
+        for (int j = 0; j < 128; j++) {
+            const float wv = __ldg(&w.wih_t[j * 512 + r]);
+#pragma unroll
+            for (int f = 0; f < kVadFramesPerCta; f++) acc[f] = fmaf(wv, a4[f][j], acc[f]);
+        }
+        for (int f = 0; f < nfr; f++) gates[(frame_off[s] + f0 + f) * 512 + r] = acc[f] + bv;
+    }
+}
+
+__global__ void __launch_bounds__(512, 1)
+vad_lstm_kernel(const float* __restrict__ gates, const int64_t* __restrict__ frame_off, VadWeights w, float* __restrict__ probs) {
+    __shared__ float h[128];
+    __shared__ float gs[512];
+    __shared__ float part[4];
+    const int s = blockIdx.x, r = threadIdx.x;
+    float wr[128];
+#pragma unroll
+    for (int j = 0; j < 128; j++) wr[j] = w.whh[r * 128 + j];
+    float c = 0.0f;
+    const float wo = r < 128 ? w.w_out[r] : 0.0f;
+    if (r < 128) h[r] = 0.0f;
+    __syncthreads();
+    const int64_t f0 = frame_off[s], f1 = frame_off[s + 1];
+    float gnext = f0 < f1 ? gates[f0 * 512 + r] : 0.0f;
+    for (int64_t f = f0; f < f1; f++) {
+        float a = gnext;
+        if (f + 1 < f1) gnext = gates[(f + 1) * 512 + r];  // prefetch the next frame's input projection
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 128; j += 4) {
+            a0 = fmaf(wr[j], h[j], a0);
+            a1 = fmaf(wr[j + 1], h[j + 1], a1);
+            a2 = fmaf(wr[j + 2], h[j + 2], a2);
+            a3 = fmaf(wr[j + 3], h[j + 3], a3);
+        }
+        gs[r] = a + ((a0 + a1) + (a2 + a3));
+        __syncthreads();
+        if (r < 128) {
+            const float ig = sigmoidf_(gs[r]), fg = sigmoidf_(gs[128 + r]), gg = tanhf(gs[256 + r]), og = sigmoidf_(gs[384 + r]);
+            c = fg * c + ig * gg;
+            const float hn = og * tanhf(c);
+            h[r] = hn;
+            float y = wo * fmaxf(hn, 0.0f);
+            y = warp_sum(y);
+            if ((r & 31) == 0) part[r >> 5] = y;
+        }
+        __syncthreads();
+        if (r == 0) probs[f] = sigmoidf_(((part[0] + part[1]) + (part[2] + part[3])) + w.b_out);
+    }
+}
+
+// counter-based weight synthesis, identical to model.cu's generator (mode 0)
+__host__ __device__ inline uint64_t vad_splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+static uint64_t vad_fnv1a(const char* s) {
+    uint64_t h = 0xcbf29ce484222325ULL;
+    for (; *s; s++) { h ^= (unsigned char)*s; h *= 0x100000001b3ULL; }
+    return h;
+}
+static void vad_synth(std::vector<float>& out, size_t n, uint64_t seed, const char* name, float offset, float scale) {
+    const uint64_t key = vad_splitmix64(vad_fnv1a(name) ^ vad_splitmix64(seed));
+    out.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        const uint64_t z = vad_splitmix64(key + i);
+        const int k = (int)(z >> 40);
+        const float u = (float)(k - 8388608) * (1.0f / 8388608.0f);
+        volatile float prod = u * scale;
+        out[i] = offset + prod;
+    }
+}
+
+}  // namespace wdr
+
+using namespace wdr;
+
+struct wdr_vad {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    VadWeights w;
+    std::vector<void*> allocs;
+    std::vector<float> probs;  // of the last detect_speech call (whisper_vad_probs)
+};
+struct wdr_vad_segments {
+    std::vector<float> t0, t1;  // centiseconds
+};
+
+static float* vad_upload(wdr_vad* v, const std::vector<float>& h) {
+    float* d = nullptr;
+    if (cudaMalloc(&d, sizeof(float) * h.size()) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice);
+    v->allocs.push_back(d);
+    return d;
+}
+
+extern "C" wdr_vad_context_params wdr_vad_default_context_params(void) {
+    wdr_vad_context_params p;
+    p.n_threads = 4; p.use_gpu = 1; p.gpu_device = 0; p.seed = 1234;
+    return p;
+}
+extern "C" wdr_vad_params wdr_vad_default_params(void) {
+    wdr_vad_params p;
+    p.threshold = 0.5f; p.min_speech_duration_ms = 250; p.min_silence_duration_ms = 100; p.max_speech_duration_s = FLT_MAX;
+    p.speech_pad_ms = 30; p.samples_overlap = 0.1f;
+    return p;
+}
+
+extern "C" wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad_context_params params) {
+    clear_error();
+    if (path && path[0]) { set_error("wdr_vad_init: model files are not supported yet (pass NULL for seeded weights)"); return nullptr; }
+    if (ensure_device(params.gpu_device) != WDR_OK) return nullptr;
+    wdr_vad* v = new wdr_vad();
+    v->device = params.gpu_device;
+    if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream"); delete v; return nullptr; }
+    std::vector<float> t, tt;
+    {   // true windowed DFT basis, transposed to [k][c]
+        tt.resize(256 * 258);
+        for (int c = 0; c < 129; c++)
+            for (int k = 0; k < 256; k++) {
+                const double win = 0.5 * (1.0 - cos(2.0 * M_PI * k / 256.0)), ang = 2.0 * M_PI * c * k / 256.0;
+                tt[k * 258 + c] = (float)(cos(ang) * win);
+                tt[k * 258 + 129 + c] = (float)(-sin(ang) * win);
+            }
+        v->w.basis_t = vad_upload(v, tt);
+    }
+    const int chans[4][2] = {{129, 128}, {128, 64}, {64, 64}, {64, 128}};
+    for (int i = 0; i < 4; i++) {
+        const int ci = chans[i][0], co = chans[i][1];
+        const float s = (float)(1.0 / sqrt((double)ci * 3));
+        char name[64];
+        snprintf(name, sizeof(name), "vad.encoder.%d.weight", i);
+        vad_synth(t, (size_t)co * ci * 3, params.seed, name, 0.0f, s);
+        tt.resize(t.size());
+        for (int o = 0; o < co; o++)
+            for (int c = 0; c < ci; c++)
+                for (int k = 0; k < 3; k++) tt[((size_t)c * 3 + k) * co + o] = t[((size_t)o * ci + c) * 3 + k];
+        v->w.w_t[i] = vad_upload(v, tt);
+        snprintf(name, sizeof(name), "vad.encoder.%d.bias", i);
+        vad_synth(t, co, params.seed, name, 0.0f, s);
+        v->w.b[i] = vad_upload(v, t);
+    }
+    const float s = (float)(1.0 / sqrt(128.0));
+    vad_synth(t, 512 * 128, params.seed, "vad.lstm.weight_ih", 0.0f, s);
+    tt.resize(t.size());
+    for (int r = 0; r < 512; r++)
+        for (int j = 0; j < 128; j++) tt[(size_t)j * 512 + r] = t[(size_t)r * 128 + j];
+    v->w.wih_t = vad_upload(v, tt);
+    vad_synth(t, 512 * 128, params.seed, "vad.lstm.weight_hh", 0.0f, s);
+    v->w.whh = vad_upload(v, t);
+    std::vector<float> b1, b2;
+    vad_synth(b1, 512, params.seed, "vad.lstm.bias_ih", 0.0f, s);
+    vad_synth(b2, 512, params.seed, "vad.lstm.bias_hh", 0.0f, s);
+    for (int i = 0; i < 512; i++) b1[i] = b1[i] + b2[i];
+    v->w.b_gates = vad_upload(v, b1);
+    vad_synth(t, 128, params.seed, "vad.final_conv.weight", 0.0f, 0.5f);
+    v->w.w_out = vad_upload(v, t);
+    vad_synth(t, 1, params.seed, "vad.final_conv.bias", 0.0f, 0.1f);
+    v->w.b_out = t[0];
+    for (void* p : v->allocs)
+        if (!p) { set_error("wdr_vad_init: out of device memory"); wdr_vad_free(v); return nullptr; }
+    return v;
+}
+
+extern "C" void wdr_vad_free(wdr_vad* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    for (void* p : v->allocs) cudaFree(p);
+    if (v->stream) cudaStreamDestroy(v->stream);
+    delete v;
+}
+
+namespace wdr {
+// streams laid out by (off[s], n[s]); probs_out: [sum frames] device.  All device pointers except the descriptor arrays (host).
+template <typename In>
+static int vad_run(wdr_vad* v, const In* pcm_dev, const std::vector<int64_t>& off, const std::vector<int32_t>& n, float* probs_dev,
+                   std::vector<int64_t>* frame_off_out, cudaStream_t st) {
+    const int S = (int)n.size();
+    std::vector<int64_t> foff(S + 1, 0);
+    int64_t groups = 0;
+    for (int s = 0; s < S; s++) {
+        const int64_t nf = (n[s] + kVadWin - 1) / kVadWin;
+        foff[s + 1] = foff[s] + nf;
+        groups += (nf + kVadFramesPerCta - 1) / kVadFramesPerCta;
+    }
+    if (frame_off_out) *frame_off_out = foff;
+    if (foff[S] == 0) return WDR_OK;
+    DevBuf<int64_t> d_off, d_foff;
+    DevBuf<int32_t> d_n;
+    DevBuf<float> d_gates;
+    WDR_CUDA_TRY(d_off.alloc(S));
+    WDR_CUDA_TRY(d_foff.alloc(S + 1));
+    WDR_CUDA_TRY(d_n.alloc(S));
+    WDR_CUDA_TRY(d_gates.alloc((size_t)foff[S] * 512));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_off.p, off.data(), sizeof(int64_t) * S, cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_foff.p, foff.data(), sizeof(int64_t) * (S + 1), cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_n.p, n.data(), sizeof(int32_t) * S, cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaFuncSetAttribute(vad_frontend_kernel<In>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kVadSmemBytes));
+    vad_frontend_kernel<In><<<(unsigned)groups, kVadThreads, kVadSmemBytes, st>>>(pcm_dev, d_off.p, d_n.p, d_foff.p, S, v->w, d_gates.p);
+    WDR_LAUNCH_CHECK();
+    vad_lstm_kernel<<<S, 512, 0, st>>>(d_gates.p, d_foff.p, v->w, probs_dev);
+    WDR_LAUNCH_CHECK();
+    WDR_CUDA_TRY(cudaStreamSynchronize(st));  // DevBufs go out of scope
+    return WDR_OK;
+}
+}  // namespace wdr
+
+extern "C" int wdr_vad_detect_speech(wdr_vad* v, const float* pcm, int n) {
+    clear_error();
+    WDR_REQUIRE(v && n >= 0 && (pcm || n == 0), "bad arguments");
+    int rc = ensure_device(v->device);
+    if (rc != WDR_OK) return rc;
+    const int nf = (n + kVadWin - 1) / kVadWin;
+    v->probs.assign(nf, 0.0f);
+    if (nf == 0) return WDR_OK;
+    DevBuf<float> d_x, d_p;
+    WDR_CUDA_TRY(d_x.alloc(n));
+    WDR_CUDA_TRY(d_p.alloc(nf));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_x.p, pcm, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, v->stream));
+    rc = vad_run<float>(v, d_x.p, {0}, {n}, d_p.p, nullptr, v->stream);
+    if (rc != WDR_OK) return rc;
+    WDR_CUDA_TRY(cudaMemcpy(v->probs.data(), d_p.p, sizeof(float) * nf, cudaMemcpyDeviceToHost));
+    return WDR_OK;
+}
+
+extern "C" int wdr_vad_detect_speech_batch_i16(wdr_vad* v, const int16_t* pcm, const int64_t* offsets, const int32_t* n_samples, int n_streams,
+                                               float* probs_out, int64_t* frame_offsets_out) {
+    clear_error();
+    WDR_REQUIRE(v && pcm && offsets && n_samples && n_streams > 0 && probs_out && frame_offsets_out, "bad arguments");
+    int rc = ensure_device(v->device);
+    if (rc != WDR_OK) return rc;
+    std::vector<int64_t> off(offsets, offsets + n_streams);
+    std::vector<int32_t> n(n_samples, n_samples + n_streams);
+    int64_t total = 0;
+    for (int s = 0; s < n_streams; s++) { WDR_REQUIRE(n[s] >= 0 && off[s] >= 0, "bad stream descriptor"); total = std::max(total, off[s] + n[s]); }
+    DevBuf<int16_t> d_x;
+    DevBuf<float> d_p;
+    int64_t nf = 0;
+    for (int s = 0; s < n_streams; s++) nf += (n[s] + kVadWin - 1) / kVadWin;
+    WDR_CUDA_TRY(d_x.alloc((size_t)std::max<int64_t>(total, 1)));
+    WDR_CUDA_TRY(d_p.alloc((size_t)std::max<int64_t>(nf, 1)));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_x.p, pcm, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, v->stream));
+    std::vector<int64_t> foff;
+    rc = vad_run<int16_t>(v, d_x.p, off, n, d_p.p, &foff, v->stream);
+    if (rc != WDR_OK) return rc;
+    if (nf) WDR_CUDA_TRY(cudaMemcpy(probs_out, d_p.p, sizeof(float) * (size_t)nf, cudaMemcpyDeviceToHost));
+    for (int s = 0; s <= n_streams; s++) frame_offsets_out[s] = foff[s];
+    return WDR_OK;
+}
+
+extern "C" int wdr_vad_n_probs(wdr_vad* v) { return v ? (int)v->probs.size() : 0; }
+extern "C" const float* wdr_vad_probs(wdr_vad* v) { return v ? v->probs.data() : nullptr; }
+
+static int64_t samples_to_cs(int samples) { return (int64_t)((samples / (double)WDR_SAMPLE_RATE) * 100.0 + 0.5); }
+
+// whisper_vad_segments_from_probs, restated; probs: host array
+extern "C" wdr_vad_segments* wdr_vad_segments_from_probs_array(const float* probs, int n_probs, wdr_vad_params params) {
+    clear_error();
+    if (n_probs < 0 || (!probs && n_probs)) { set_error("bad arguments"); return nullptr; }
+    const int n_window = kVadWin, sample_rate = WDR_SAMPLE_RATE;
+    const float threshold = params.threshold;
+    const int min_silence_samples = sample_rate * params.min_silence_duration_ms / 1000;
+    const int audio_length_samples = n_probs * n_window;
+    const int min_speech_samples = sample_rate * params.min_speech_duration_ms / 1000;
+    const int speech_pad_samples = sample_rate * params.speech_pad_ms / 1000;
+    int max_speech_samples;
+    if (params.max_speech_duration_s > 100000.0f) max_speech_samples = INT_MAX / 2;
+    else {
+        const int64_t temp = (int64_t)sample_rate * (int64_t)(params.max_speech_duration_s) - n_window - 2 * speech_pad_samples;
+        max_speech_samples = (temp > INT_MAX) ? INT_MAX / 2 : (int)temp;
+        if (max_speech_samples < 0) max_speech_samples = INT_MAX / 2;
+    }
+    const int min_silence_samples_at_max_speech = sample_rate * 98 / 1000;
+    float neg_threshold = threshold - 0.15f;
+    if (neg_threshold < 0.01f) neg_threshold = 0.01f;
+    struct Sp { int start, end; };
+    std::vector<Sp> speeches;
+    bool is_speech = false, has_curr = false;
+    int temp_end = 0, prev_end = 0, next_start = 0, curr_start = 0;
+    for (int i = 0; i < n_probs; i++) {
+        const float pr = probs[i];
+        const int cs = n_window * i;
+        if (pr >= threshold && temp_end) {
+            temp_end = 0;
+            if (next_start < prev_end) next_start = cs;
+        }
+        if (pr >= threshold && !is_speech) { is_speech = true; curr_start = cs; has_curr = true; continue; }
+        if (is_speech && (cs - curr_start) > max_speech_samples) {
+            if (prev_end) {
+                speeches.push_back({curr_start, prev_end});
+                has_curr = true;
+                if (next_start < prev_end) { is_speech = false; has_curr = false; }
+                else curr_start = next_start;
+                prev_end = 0; next_start = 0; temp_end = 0;
+            } else {
+                speeches.push_back({curr_start, cs});
+                prev_end = 0; next_start = 0; temp_end = 0; is_speech = false; has_curr = false;
+                continue;
+            }
+        }
+        if (pr < neg_threshold && is_speech) {
+            if (!temp_end) temp_end = cs;
+            if ((cs - temp_end) > min_silence_samples_at_max_speech) prev_end = temp_end;
+            if ((cs - temp_end) < min_silence_samples) continue;
+            if ((temp_end - curr_start) > min_speech_samples) speeches.push_back({curr_start, temp_end});
+            prev_end = 0; next_start = 0; temp_end = 0; is_speech = false; has_curr = false;
+            continue;
+        }
+    }
+    if (has_curr && (audio_length_samples - curr_start) > min_speech_samples) speeches.push_back({curr_start, audio_length_samples});
+    const int ns = (int)speeches.size();
+    for (int i = 0; i < ns; i++) {
+        if (i == 0) speeches[i].start = speeches[i].start > speech_pad_samples ? speeches[i].start - speech_pad_samples : 0;
+        if (i < ns - 1) {
+            const int sil = speeches[i + 1].start - speeches[i].end;
+            if (sil < 2 * speech_pad_samples) {
+                speeches[i].end += sil / 2;
+                speeches[i + 1].start = speeches[i + 1].start > sil / 2 ? speeches[i + 1].start - sil / 2 : 0;
+            } else {
+                speeches[i].end = speeches[i].end + speech_pad_samples < audio_length_samples ? speeches[i].end + speech_pad_samples : audio_length_samples;
+                speeches[i + 1].start = speeches[i + 1].start > speech_pad_samples ? speeches[i + 1].start - speech_pad_samples : 0;
+            }
+        } else {
+            speeches[i].end = speeches[i].end + speech_pad_samples < audio_length_samples ? speeches[i].end + speech_pad_samples : audio_length_samples;
+        }
+    }
+    wdr_vad_segments* out = new wdr_vad_segments();
+    for (auto& s : speeches) {
+        out->t0.push_back((float)samples_to_cs(s.start));
+        out->t1.push_back((float)samples_to_cs(s.end));
+    }
+    return out;
+}
+
+extern "C" wdr_vad_segments* wdr_vad_segments_from_probs(wdr_vad* v, wdr_vad_params params) {
+    if (!v) { set_error("null vad context"); return nullptr; }
+    return wdr_vad_segments_from_probs_array(v->probs.data(), (int)v->probs.size(), params);
+}
+extern "C" wdr_vad_segments* wdr_vad_segments_from_samples(wdr_vad* v, wdr_vad_params params, const float* pcm, int n) {
+    if (wdr_vad_detect_speech(v, pcm, n) != WDR_OK) return nullptr;
+    return wdr_vad_segments_from_probs(v, params);
+}
+extern "C" int wdr_vad_segments_n(wdr_vad_segments* s) { return s ? (int)s->t0.size() : 0; }
+extern "C" float wdr_vad_segments_get_segment_t0(wdr_vad_segments* s, int i) { return (s && i >= 0 && i < (int)s->t0.size()) ? s->t0[i] : -1.0f; }
+extern "C" float wdr_vad_segments_get_segment_t1(wdr_vad_segments* s, int i) { return (s && i >= 0 && i < (int)s->t1.size()) ? s->t1[i] : -1.0f; }
+extern "C" void wdr_vad_free_segments(wdr_vad_segments* s) { delete s; }
