@@ -203,9 +203,14 @@ def main():
     if w.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: libwdr_b200 has no CPU path")
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE JSON line: anything libraries print while we run (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
 
     B = args.chunks
     full = args.workload == "transcribe"
@@ -371,6 +376,8 @@ def main():
                 n, v, dt = 1, 30.0 / t1, t1
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
                                     "sample": f"{n} of the {B} windows ({dt:.1f} s of CPU work) on {cores} host threads, oracle/wdr_oracle*.c"}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
     st.close()
     ctx.close()

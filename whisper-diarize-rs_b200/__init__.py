@@ -18,4 +18,5 @@ from .capi import (  # noqa: F401
     VadContext, VadParams, vad_default_params, vad_segments_from_probs,
     EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
 )
+from . import dist  # noqa: F401,E402
 from . import host  # noqa: F401,E402  (host-side mirror of the reference's own Rust logic around the boundary)
