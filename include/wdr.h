@@ -285,6 +285,26 @@ float wdr_vad_segments_get_segment_t0(wdr_vad_segments* s, int i);   /* centisec
 float wdr_vad_segments_get_segment_t1(wdr_vad_segments* s, int i);
 void wdr_vad_free_segments(wdr_vad_segments* s);
 
+/* ---- pyannote segmentation (pyannote_rs::get_segments, reference src/engine.rs:117-122) ------------------------- */
+typedef struct wdr_seg wdr_seg;
+typedef struct wdr_seg_result wdr_seg_result;
+wdr_seg* wdr_seg_init(const char* path /* NULL: seeded weights */, uint64_t seed, int device);
+void wdr_seg_free(wdr_seg* m);
+int wdr_seg_n_windows(int64_t n_samples);                              /* ceil(n / 160000) */
+/* PyanNet over every 10 s window (raw int16 values as f32, zero padded): scores[n_windows][589][7] log-probabilities. Host ptrs.
+ * Returns n_windows. */
+int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, float* scores);
+/* get_segments: windows -> scores -> per-frame argmax != 0 state machine (frame 270 samples, first frame at sample 721). */
+wdr_seg_result* wdr_seg_get_segments(wdr_seg* m, const int16_t* pcm, int64_t n);
+/* The state machine alone on caller-supplied scores (host logic; bit-exact given the scores). */
+wdr_seg_result* wdr_seg_segments_from_scores(const float* scores, int n_windows, int64_t n_samples_padded);
+int wdr_seg_result_n(wdr_seg_result* r);
+double wdr_seg_result_start(wdr_seg_result* r, int i);                 /* Segment.start, seconds (f64) */
+double wdr_seg_result_end(wdr_seg_result* r, int i);
+int64_t wdr_seg_result_sample_range(wdr_seg_result* r, int i, int64_t* i1);   /* [i0, i1) into the zero-padded input */
+const int16_t* wdr_seg_result_samples(wdr_seg_result* r, int i, int64_t* count);  /* Segment.samples (owned by the result) */
+void wdr_seg_result_free(wdr_seg_result* r);
+
 /* ---- speaker assignment (pyannote_rs::EmbeddingManager, src/transcribe.rs:342, 480-492) -------------------- */
 typedef struct wdr_spk wdr_spk;
 wdr_spk* wdr_spk_init(size_t max_speakers);            /* EmbeddingManager::new(max_speakers); SIZE_MAX = unlimited (src/engine.rs:108-111) */

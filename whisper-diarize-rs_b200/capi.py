@@ -176,6 +176,25 @@ def load():
     L.wdr_vad_segments_get_segment_t1.argtypes = [C.c_void_p, C.c_int]
     L.wdr_vad_segments_get_segment_t1.restype = C.c_float
     L.wdr_vad_free_segments.argtypes = [C.c_void_p]
+    L.wdr_seg_init.restype = C.c_void_p
+    L.wdr_seg_init.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
+    L.wdr_seg_free.argtypes = [C.c_void_p]
+    L.wdr_seg_n_windows.argtypes = [C.c_int64]
+    L.wdr_seg_scores_i16.argtypes = [C.c_void_p, i16p, C.c_int64, f32p]
+    L.wdr_seg_get_segments.restype = C.c_void_p
+    L.wdr_seg_get_segments.argtypes = [C.c_void_p, i16p, C.c_int64]
+    L.wdr_seg_segments_from_scores.restype = C.c_void_p
+    L.wdr_seg_segments_from_scores.argtypes = [f32p, C.c_int, C.c_int64]
+    L.wdr_seg_result_n.argtypes = [C.c_void_p]
+    L.wdr_seg_result_start.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_seg_result_start.restype = C.c_double
+    L.wdr_seg_result_end.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_seg_result_end.restype = C.c_double
+    L.wdr_seg_result_sample_range.argtypes = [C.c_void_p, C.c_int, i64p]
+    L.wdr_seg_result_sample_range.restype = C.c_int64
+    L.wdr_seg_result_samples.argtypes = [C.c_void_p, C.c_int, i64p]
+    L.wdr_seg_result_samples.restype = i16p
+    L.wdr_seg_result_free.argtypes = [C.c_void_p]
     L.wdr_spk_init.restype = C.c_void_p
     L.wdr_spk_init.argtypes = [C.c_size_t]
     L.wdr_spk_free.argtypes = [C.c_void_p]
@@ -669,3 +688,58 @@ class VadContext:
         """vad.segments_from_samples(params, &samples) -> [(start_cs, end_cs)] (reference src/vad.rs:31)."""
         x = _np(pcm_f32, np.float32)
         return _collect_segments(load().wdr_vad_segments_from_samples(self._h, params if params is not None else vad_default_params(), _p(x, f32p), len(x)))
+
+
+def _collect_seg_result(h, with_samples):
+    L = load()
+    if not h:
+        raise WdrError(-3, L.wdr_last_error().decode())
+    try:
+        out = []
+        for i in range(L.wdr_seg_result_n(h)):
+            i1 = C.c_int64(0)
+            i0 = L.wdr_seg_result_sample_range(h, i, C.byref(i1))
+            d = dict(start=L.wdr_seg_result_start(h, i), end=L.wdr_seg_result_end(h, i), i0=int(i0), i1=int(i1.value))
+            if with_samples:
+                cnt = C.c_int64(0)
+                p = L.wdr_seg_result_samples(h, i, C.byref(cnt))
+                d["samples"] = np.ctypeslib.as_array(p, shape=(cnt.value,)).copy() if cnt.value > 0 else np.zeros(0, np.int16)
+            out.append(d)
+        return out
+    finally:
+        L.wdr_seg_result_free(h)
+
+
+def seg_segments_from_scores(scores, n_samples_padded):
+    """pyannote-rs' speech state machine on scores[n_windows, 589, 7] (host logic; no GPU needed)."""
+    sc = _np(scores, np.float32)
+    return _collect_seg_result(load().wdr_seg_segments_from_scores(_p(sc, f32p), sc.shape[0], int(n_samples_padded)), False)
+
+
+class Segmenter:
+    """wdr_seg: the segmentation-3.0 session pyannote_rs::get_segments opens (reference src/engine.rs:117)."""
+
+    def __init__(self, seed=1234, device=0):
+        self._h = load().wdr_seg_init(None, seed, device)
+        if not self._h:
+            raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, load().wdr_last_error().decode())
+
+    def close(self):
+        if self._h:
+            load().wdr_seg_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def scores(self, pcm_i16):
+        x = _np(pcm_i16, np.int16)
+        W = load().wdr_seg_n_windows(len(x))
+        out = np.empty((W, 589, 7), np.float32)
+        if W:
+            _check(load().wdr_seg_scores_i16(self._h, _p(x, i16p), len(x), _p(out, f32p)))
+        return out
+
+    def get_segments(self, pcm_i16):
+        """pyannote_rs::get_segments(&samples, 16000, model) -> [dict(start, end, samples)]."""
+        x = _np(pcm_i16, np.int16)
+        return _collect_seg_result(load().wdr_seg_get_segments(self._h, _p(x, i16p), len(x)), True)
