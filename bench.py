@@ -238,11 +238,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident arm ----
+    # Timed region 1 (-> value): K steps exactly as a caller runs them (decode iterations replay as CUDA graphs, no per-kernel events).
+    # Timed region 2 (-> roofline / kernels): the same K steps again with a CUDA-event pair around every launch on the launching
+    # stream (wdr_profile_*); graphs are off there because events cannot bracket nodes of a replayed graph.
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    st.profile_enable(True)
-    st.profile_collect()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -257,9 +258,19 @@ def main():
     torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = w.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    phases = st.phase_ms() if full else None  # of the last timed step
+    st.profile_enable(True)
+    st.profile_collect()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(args.steps):
+        step_resident()
+    p1.record()
+    barrier()
+    ms_profiled = p0.elapsed_time(p1)
     prof = st.profile_collect()
     st.profile_enable(False)
-    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -337,7 +348,7 @@ def main():
             gbs = per_launch * prof["dec_cross"]["records"] / (prof["dec_cross"]["ms"] / 1e3) / 1e9
             kern["dec_cross_attention"] = {"ms_per_step": prof["dec_cross"]["ms"] / args.steps, "launches_per_step": prof["dec_cross"]["records"] / args.steps,
                                            "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak, "algorithmic_bytes_per_launch": per_launch}
-        for name in ("mel_aux", "layernorm", "decoder", "dec_gemm", "dtw", "other"):
+        for name in ("mel_aux", "layernorm", "decoder", "dec_gemm", "dec_cross_batched", "dtw", "other"):
             if prof[name]["ms"] > 0:
                 kern[name] = {"ms_per_step": prof[name]["ms"] / args.steps, "launches_per_step": prof[name]["records"] / args.steps}
         cand = {k: prof[k]["ms"] for k in ("gemm", "attention", "dec_cross")}
@@ -363,7 +374,8 @@ def main():
                         "api": ("wdr_full_batch_i16 (pinned host PCM) + whisper.h-style result accessors" if full else
                                 "wdr_encode_chunks_i16 (pinned host PCM; result stays in the state) + wdr_state_hidden_digest"), **check},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
-                "kernel_ms_sum_per_step": total_ms / args.steps,
+                "kernel_ms_sum_per_step": total_ms / args.steps, "profiled_pass_ms_per_step": ms_profiled / args.steps,
+                "lanes": int(os.environ.get("WDR_LANES", "3")) if full else 1, "phases_ms_last_step": phases,
                 "encoder_tflops_overall": None if full else fl["total_enc"] * B * args.steps / (ms / 1e3) / 1e12}
         if not args.no_cpu_baseline:
             cores = os.cpu_count()

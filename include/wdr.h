@@ -117,6 +117,23 @@ int wdr_kaldi_fbank_batch_i16_dev(const int16_t* pcm, const int64_t* seg_offset,
                                   int n_segments, int64_t total_frames, int n_bins, int subtract_mean,
                                   float* out, void* stream);
 
+/* ---- speaker embeddings (pyannote_rs::EmbeddingExtractor, src/transcribe.rs:343, 466-467) ---------------- */
+/* WeSpeaker ResNet34 (the north-star's model; the crate downloads the CAM++ export, same "feats" -> "embs" contract): int16
+ * samples cast to f32 without scaling -> Kaldi fbank (80 bins) -> per-column mean subtraction -> ResNet34 -> TSTP -> 256-d. */
+typedef struct wdr_emb wdr_emb;
+wdr_emb* wdr_emb_init(const char* path /* NULL: seeded weights */, uint64_t seed, int device);   /* EmbeddingExtractor::new(path) */
+void wdr_emb_free(wdr_emb* m);
+int wdr_emb_dim(wdr_emb* m);                                                                       /* 256 */
+/* compute(&samples): HOST pointers.  WDR_ERR_TOO_SHORT when the segment yields no fbank frame (< 400 samples): the crate maps
+ * that error to speaker "?" (src/transcribe.rs:468-476). */
+int wdr_emb_compute_i16(wdr_emb* m, const int16_t* pcm, int64_t n, float* out /* [256] */);
+/* All segments of a recording in one call: segment s = pcm[seg_offset[s] .. seg_offset[s+1]) (HOST arrays); out [n][256];
+ * status[s] = 0 or WDR_ERR_TOO_SHORT (that row of out is zero).  _dev: pcm / out are DEVICE pointers, offsets / status HOST. */
+int wdr_emb_compute_batch_i16(wdr_emb* m, const int16_t* pcm, const int64_t* seg_offset, int n_segments, float* out, int32_t* status);
+int wdr_emb_compute_batch_i16_dev(wdr_emb* m, const int16_t* pcm_dev, const int64_t* seg_offset_host, int n_segments, float* out_dev,
+                                  int32_t* status_host, void* stream);
+double wdr_emb_last_flops(wdr_emb* m);  /* algorithmic conv FLOPs (2*M*N*K) of the last compute call */
+
 /* ---- get_signal_energy (whisper.cpp, used by the token-timestamp heuristic) --------- */
 int wdr_signal_energy(const float* pcm, int n, int half_window, float* out);
 
@@ -170,10 +187,14 @@ int wdr_encode_chunks_i16(wdr_context* ctx, wdr_state* state, const int16_t* pcm
 int wdr_state_hidden_digest(wdr_state* state, float* out, int n);
 /* Per-kernel-class CUDA-event timing on the launching stream.  Classes: 0 mel, 1 mel re-layout, 2 tcgen05 GEMM (encoder + cross-KV),
  * 3 encoder attention, 4 layernorm, 5 decoder small kernels (embed / LN / self-attention / GELU / sampler), 6 dtw, 7 other,
- * 8 decoder cross-attention (HBM-bound), 9 decoder weight-streaming GEMMs.  collect() sums the finished records (caller has
- * synchronised) into ms[] / launches[] (>= 10 entries each) and returns the number of classes. */
+ * 8 decoder cross-attention (HBM-bound), 9 decoder weight-streaming GEMMs, 10 batched cross-attention of the DTW pass.  collect() sums the finished records (caller has
+ * synchronised) into ms[] / launches[] (>= 11 entries each) and returns the number of classes. */
 int wdr_profile_enable(wdr_state* state, int enable);
 int wdr_profile_collect(wdr_state* state, double* ms, int32_t* launches, int n_classes);
+/* B200 extension (no whisper.h equivalent): how many lanes wdr_full_batch_* cuts its windows into.  Each lane is a host thread
+ * with its own streams and workspaces, so one lane's latency-bound decode chain overlaps another's HBM-bound cross-attention and
+ * tensor-bound encoder.  0 = default (environment WDR_LANES, else 3); results do not depend on the lane count. */
+int wdr_state_set_lanes(wdr_state* state, int n_lanes);
 /* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] = V transposed, window b's tokens at
  * columns b*round_up(T,8) + t (pad columns zero) -> out bf16 [B*T][d].  DEVICE pointers. */
 int wdr_encoder_attention_dev(const uint16_t* qk, const uint16_t* vt, int64_t ldt, int n_chunks, int T, int n_head, int d_model,
@@ -249,6 +270,10 @@ int wdr_lang_id(const char* lang);                                              
 const char* wdr_token_to_str(wdr_context* ctx, int32_t token);                             /* whisper_token_to_str */
 /* Per-chunk decoder summary of the last full call: info[8] = {seek_delta, failed, completed, n_sampled, has_ts, result_len,
  * seek_end, n_segments}; *no_speech_prob optional.  For parity tests. */
+/* Device time (CUDA events on the compute stream) of the phases of the last full call, summed over its groups (and lanes):
+ * ms[5] = log-mel + encoder | cross-KV projection | greedy decode loop | batched DTW pass | DTW cost + wavefront + backtrace;
+ * decode_steps = greedy iterations run. */
+int wdr_full_get_phase_ms(wdr_state* state, double* ms, int32_t* decode_steps);
 int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* info, float* no_speech_prob);
 /* Stage-level decoder access for parity tests: teacher-forced pass of `n_seq` tokens over window 0.. of the last encode/full call.
  * enc: optional HOST encoder output [n_chunks][1500][d] to install first (NULL = keep the state's).  seq: HOST [n_chunks][n_seq].

@@ -142,3 +142,31 @@ def test_unsupported_params_fail_loudly(wdr):
         st.full(np.zeros(16000, np.int16), st.full_params(language="auto"))
     st.close()
     ctx.close()
+
+
+def test_lanes_do_not_change_results(wdr):
+    """wdr_state_set_lanes: 16 windows on 1 lane vs 2 concurrent lanes (host threads, own streams / workspaces) -> identical
+    segments, tokens, token statistics and DTW times, in chunk order."""
+    B = 16
+    pcm = np.zeros((B, 480000), np.int16)
+    nv = np.full(B, 480000, np.int32)
+    base = [synth_audio(2000 + b, 30.0) for b in range(3)]
+    for b in range(B):
+        pcm[b] = np.roll(base[b % 3], 7919 * (b // 3))
+    nv[5] = 100000
+    nv[11] = 0
+    ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    out = []
+    for lanes in (1, 2):
+        st.set_lanes(lanes)
+        segs = st.full_batch(pcm, nv)
+        out.append([(s["chunk"], s["t0"], s["t1"], s["text"], [(t.id, t.tid, t.p, t.plog, t.pt, t.ptsum, t.t0, t.t1, t.t_dtw, t.vlen) for t in s["tokens"]])
+                    for s in segs])
+        info = [st.chunk_info(b) for b in range(B)]
+        out[-1].append(info)
+    assert out[0] == out[1]
+    assert [s[0] for s in out[0][:-1]] == sorted(s[0] for s in out[0][:-1])
+    assert len(out[0]) - 1 >= 12
+    st.close()
+    ctx.close()

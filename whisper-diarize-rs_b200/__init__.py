@@ -16,7 +16,7 @@ from .capi import (  # noqa: F401
     Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
     FullParams, TokenData, lang_str, lang_id,
     VadContext, VadParams, vad_default_params, vad_segments_from_probs,
-    Segmenter, seg_segments_from_scores,
+    Segmenter, seg_segments_from_scores, EmbeddingExtractor,
     EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
 )
 from . import dist  # noqa: F401,E402

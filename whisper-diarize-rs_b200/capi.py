@@ -126,6 +126,7 @@ def load():
     L.wdr_state_hidden_digest.argtypes = [C.c_void_p, f32p, C.c_int]
     L.wdr_profile_enable.argtypes = [C.c_void_p, C.c_int]
     L.wdr_profile_collect.argtypes = [C.c_void_p, C.POINTER(C.c_double), i32p, C.c_int]
+    L.wdr_state_set_lanes.argtypes = [C.c_void_p, C.c_int]
     L.wdr_encoder_attention_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.wdr_full_default_params.restype = FullParams
     L.wdr_full_default_params.argtypes = [C.c_int]
@@ -195,6 +196,16 @@ def load():
     L.wdr_seg_result_samples.argtypes = [C.c_void_p, C.c_int, i64p]
     L.wdr_seg_result_samples.restype = i16p
     L.wdr_seg_result_free.argtypes = [C.c_void_p]
+    L.wdr_emb_init.restype = C.c_void_p
+    L.wdr_emb_init.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
+    L.wdr_emb_free.argtypes = [C.c_void_p]
+    L.wdr_emb_dim.argtypes = [C.c_void_p]
+    L.wdr_emb_compute_i16.argtypes = [C.c_void_p, i16p, C.c_int64, f32p]
+    L.wdr_emb_compute_batch_i16.argtypes = [C.c_void_p, i16p, i64p, C.c_int, f32p, i32p]
+    L.wdr_emb_compute_batch_i16_dev.argtypes = [C.c_void_p, C.c_void_p, i64p, C.c_int, C.c_void_p, i32p, C.c_void_p]
+    L.wdr_emb_last_flops.argtypes = [C.c_void_p]
+    L.wdr_emb_last_flops.restype = C.c_double
+    L.wdr_full_get_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), i32p]
     L.wdr_spk_init.restype = C.c_void_p
     L.wdr_spk_init.argtypes = [C.c_size_t]
     L.wdr_spk_free.argtypes = [C.c_void_p]
@@ -458,11 +469,15 @@ class State:
     def profile_enable(self, on=True):
         _check(load().wdr_profile_enable(self._h, int(on)))
 
+    def set_lanes(self, n):
+        """Lanes of full_batch (0 = library default); output is identical for any lane count."""
+        _check(load().wdr_state_set_lanes(self._h, int(n)))
+
     def profile_collect(self):
         ms = (C.c_double * 16)()
         ln = (C.c_int32 * 16)()
         _check(load().wdr_profile_collect(self._h, ms, ln, 16))
-        names = ["mel", "mel_aux", "gemm", "attention", "layernorm", "decoder", "dtw", "other", "dec_cross", "dec_gemm"]
+        names = ["mel", "mel_aux", "gemm", "attention", "layernorm", "decoder", "dtw", "other", "dec_cross", "dec_gemm", "dec_cross_batched"]
         return {n: {"ms": ms[i], "records": ln[i]} for i, n in enumerate(names)}
 
     # ---- full transcription (state.full, reference src/transcribe.rs:389; accessors :393-412, :252-282) ----
@@ -540,6 +555,15 @@ class State:
 
     def lang_id(self):
         return load().wdr_full_lang_id_from_state(self._h)
+
+    def phase_ms(self):
+        """Device time of the phases of the last full call (summed over groups and lanes) + greedy iterations run."""
+        ms = (C.c_double * 5)()
+        n = C.c_int32(0)
+        _check(load().wdr_full_get_phase_ms(self._h, ms, C.byref(n)))
+        d = dict(zip(["encode", "cross_kv", "decode", "dtw_pass", "dtw"], [float(v) for v in ms]))
+        d["decode_steps"] = int(n.value)
+        return d
 
     def decode_teacher_forced(self, seq, enc=None, want_logits=True, want_aheads=False, n_aheads=0):
         """Stage-level: teacher-forced decoder pass. seq[B, n_seq]; enc[B,1500,d] host (None = keep the state's encoder output)."""
@@ -743,3 +767,47 @@ class Segmenter:
         """pyannote_rs::get_segments(&samples, 16000, model) -> [dict(start, end, samples)]."""
         x = _np(pcm_i16, np.int16)
         return _collect_seg_result(load().wdr_seg_get_segments(self._h, _p(x, i16p), len(x)), True)
+
+
+class EmbeddingExtractor:
+    """wdr_emb: pyannote_rs::EmbeddingExtractor (reference src/transcribe.rs:343, 466-467) — WeSpeaker ResNet34, 256-d."""
+
+    def __init__(self, seed=1234, device=0):
+        self._h = load().wdr_emb_init(None, seed, device)
+        if not self._h:
+            raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, load().wdr_last_error().decode())
+        self.dim = load().wdr_emb_dim(self._h)
+
+    def close(self):
+        if self._h:
+            load().wdr_emb_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def compute(self, pcm_i16):
+        """compute(&samples) -> embedding [256]; raises WdrError(WDR_ERR_TOO_SHORT) when fbank yields no frame."""
+        x = _np(pcm_i16, np.int16)
+        out = np.empty(self.dim, np.float32)
+        _check(load().wdr_emb_compute_i16(self._h, _p(x, i16p), len(x), _p(out, f32p)))
+        return out
+
+    def compute_batch(self, pcm_i16, seg_offset):
+        """Segments pcm[seg_offset[s]:seg_offset[s+1]] -> (emb [n, 256], status [n] (0 or WDR_ERR_TOO_SHORT))."""
+        x = _np(pcm_i16, np.int16)
+        so = _np(seg_offset, np.int64)
+        n = len(so) - 1
+        out = np.zeros((n, self.dim), np.float32)
+        status = np.zeros(n, np.int32)
+        _check(load().wdr_emb_compute_batch_i16(self._h, _p(x, i16p), _p(so, i64p), n, _p(out, f32p), _p(status, i32p)))
+        return out, status
+
+    def compute_batch_dev(self, pcm_dev_ptr, seg_offset, out_dev_ptr, stream=None):
+        so = _np(seg_offset, np.int64)
+        n = len(so) - 1
+        status = np.zeros(n, np.int32)
+        _check(load().wdr_emb_compute_batch_i16_dev(self._h, pcm_dev_ptr, _p(so, i64p), n, out_dev_ptr, _p(status, i32p), stream))
+        return status
+
+    def last_flops(self):
+        return float(load().wdr_emb_last_flops(self._h))

@@ -93,8 +93,15 @@ __device__ __forceinline__ float part_sum(const float* __restrict__ part, int n_
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-__global__ void dec_embed_kernel(const int32_t* __restrict__ seq, int pos, const __nv_bfloat16* __restrict__ tok_emb,
+// Position arguments come as (pos_ptr, pos): a non-null pos_ptr (the workspace's device-resident step counter) wins, so that a
+// captured decode step replays as a CUDA graph without patching kernel arguments.
+__device__ __forceinline__ int load_pos(const int32_t* __restrict__ pos_ptr, int pos) { return pos_ptr ? *pos_ptr : pos; }
+
+__global__ void dec_advance_kernel(int32_t* pos_ptr) { *pos_ptr += 1; }
+
+__global__ void dec_embed_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ pos_ptr, int pos, const __nv_bfloat16* __restrict__ tok_emb,
                                  const float* __restrict__ pos_emb, int d, int n_vocab, float* __restrict__ x) {
+    pos = load_pos(pos_ptr, pos);
     const int b = blockIdx.x;
     int tok = seq[b * kDecSeqCap + pos];
     if (tok < 0 || tok >= n_vocab) tok = 0;
@@ -137,13 +144,14 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
 // self-attention of one (head, window) at position pos.  part: [S][B][3d] partials of the fused QKV GEMM.
 __global__ void __launch_bounds__(128)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
-                     float* __restrict__ sk, float* __restrict__ sv, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
+                     float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */) {
     __shared__ float q[64];
     __shared__ float p[kDecSeqCap];
     __shared__ float red[32];
     __shared__ float acc2[2][64];
     const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    pos = load_pos(pos_ptr, pos);
     if (win && (win[b].completed | win[b].failed)) return;
     if (t_limit && pos >= t_limit[b]) return;
     float* K = sk + (int64_t)b * kDecSeqCap * d + hh * 64;
@@ -198,13 +206,15 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
                       const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                       const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
                       float* __restrict__ aw, const int64_t* __restrict__ aw_off, const int32_t* __restrict__ aw_T,
-                      const int32_t* __restrict__ aw_A, int pos, const DecWinState* __restrict__ win, const int32_t* __restrict__ t_limit) {
+                      const int32_t* __restrict__ aw_A, const int32_t* __restrict__ pos_ptr, int pos, const DecWinState* __restrict__ win,
+                      const int32_t* __restrict__ t_limit) {
     __shared__ float q[64];
     __shared__ float p[kT + 4];
     __shared__ float red[32];
     __shared__ float accs[8][64];
     const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5, g = lane & 7, r = lane >> 3;
+    pos = load_pos(pos_ptr, pos);
     if (win && (win[b].completed | win[b].failed)) return;  // finished windows stop streaming their K/V
     if (t_limit && pos >= t_limit[b]) return;
     if (tid < 64) q[tid] = part_sum(part, n_splits, split_stride, (int64_t)b * d + hh * 64 + tid) + b_q[hh * 64 + tid];
@@ -314,6 +324,201 @@ __global__ void dec_bias_gelu_kernel(const float* __restrict__ part, int n_split
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// batched DTW pass: packed rows (window b, position pos), see decoder.cuh
+// ---------------------------------------------------------------------------------------------------
+__global__ void dtwp_embed_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ row_b, const int32_t* __restrict__ row_pos,
+                                  const __nv_bfloat16* __restrict__ tok_emb, const float* __restrict__ pos_emb, int d, int n_vocab,
+                                  float* __restrict__ x) {
+    const int row = blockIdx.x, b = row_b[row], pos = row_pos[row];
+    int tok = seq[b * kDecSeqCap + pos];
+    if (tok < 0 || tok >= n_vocab) tok = 0;
+    for (int i = threadIdx.x; i < d; i += blockDim.x)
+        x[(int64_t)row * d + i] = __bfloat162float(tok_emb[(int64_t)tok * d + i]) + pos_emb[(int64_t)pos * d + i];
+}
+
+constexpr int kDtwpMaxT = 256;  // longest teacher-forced sequence (sot, lang, not, <= 220 text tokens, eot)
+
+// causal self-attention of one (head, window) over all its T_b positions; K and V (+bias) staged in shared memory as fp32
+// (row stride 65: conflict-free for "lane = key" and "lane = column" accesses alike); one warp per query.
+__global__ void __launch_bounds__(256)
+dtwp_self_attn_kernel(const float* __restrict__ qkv /* [M][3d] */, const float* __restrict__ b_qkv, const int32_t* __restrict__ row_off,
+                      const int32_t* __restrict__ T, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off) {
+    extern __shared__ float sm[];
+    const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T_b = T[b];
+    if (T_b <= 0) return;
+    const int64_t r0 = row_off[b];
+    float* Ks = sm;                       // [T_b][65]
+    float* Vs = Ks + kDtwpMaxT * 65;      // [T_b][65]
+    float* qs = Vs + kDtwpMaxT * 65;      // [8][64]
+    float* ps = qs + 8 * 64;              // [8][kDtwpMaxT]
+    for (int e = tid; e < T_b * 64; e += 256) {
+        const int t = e >> 6, c = e & 63;
+        const float* src = qkv + (r0 + t) * 3 * (int64_t)d + hh * 64 + c;
+        Ks[t * 65 + c] = src[d] + b_qkv[d + hh * 64 + c];
+        Vs[t * 65 + c] = src[2 * d] + b_qkv[2 * d + hh * 64 + c];
+    }
+    __syncthreads();
+    float* q = qs + warp * 64;
+    float* p = ps + warp * kDtwpMaxT;
+    for (int i = warp; i < T_b; i += 8) {
+        const float* src = qkv + (r0 + i) * 3 * (int64_t)d + hh * 64;
+        q[lane] = src[lane] + b_qkv[hh * 64 + lane];
+        q[lane + 32] = src[lane + 32] + b_qkv[hh * 64 + lane + 32];
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j <= i; j += 32) {
+            const float* kr = Ks + j * 65;
+            float a = 0.0f;
+#pragma unroll 16
+            for (int c = 0; c < 64; c++) a = fmaf(q[c], kr[c], a);
+            a *= 0.125f;
+            p[j] = a;
+            mx = fmaxf(mx, a);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int j = lane; j <= i; j += 32) {
+            const float e = expf(p[j] - mx);
+            p[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        __syncwarp();
+        float a0 = 0.0f, a1 = 0.0f;
+        for (int j = 0; j <= i; j++) {
+            const float pj = p[j] * inv;
+            a0 = fmaf(pj, Vs[j * 65 + lane], a0);
+            a1 = fmaf(pj, Vs[j * 65 + lane + 32], a1);
+        }
+        const int64_t o = (r0 + i) * (int64_t)d + hh * 64;
+        store_split(att, lo_off, o + lane, a0);
+        store_split(att, lo_off, o + lane + 32, a1);
+        __syncwarp();
+    }
+}
+
+// cross-attention of 16 queries of one (window, head) against the window's 1500 K_c / V_c rows.  Scores: one key row
+// (64 bf16 -> fp32 registers) per thread, the 16 queries broadcast from shared memory; softmax per query by one warp;
+// P V with one warp per key slice (probabilities broadcast as float4, 8 FMAs per shared load).  Probabilities of the
+// alignment heads are stored to aw (same layout as dec_cross_attn_kernel).
+constexpr int kDtwpQB = 16;
+constexpr int kDtwpPStride = kT + 4;
+__global__ void __launch_bounds__(256)
+dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float* __restrict__ b_q, const __nv_bfloat16* __restrict__ ckv, int d,
+                       const int32_t* __restrict__ row_off, const int32_t* __restrict__ T, __nv_bfloat16* __restrict__ att, int64_t lo_off,
+                       const int32_t* __restrict__ ahead_map, float* __restrict__ aw, const int64_t* __restrict__ aw_off,
+                       const int32_t* __restrict__ aw_A) {
+    extern __shared__ float sm[];
+    const int hh = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * kDtwpQB, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T_b = T[b];
+    if (q0 >= T_b) return;
+    const int nq = min(kDtwpQB, T_b - q0);
+    const int64_t r0 = row_off[b] + q0;
+    float* qs = sm;                         // [16][64]
+    float* p = qs + kDtwpQB * 64;           // [16][1504]; reused as the P V reduction buffer [8][16][64]
+    for (int e = tid; e < kDtwpQB * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        qs[e] = qi < nq ? (qpart[(r0 + qi) * (int64_t)d + hh * 64 + c] + b_q[hh * 64 + c]) * 0.125f : 0.0f;
+    }
+    for (int e = tid; e < kDtwpQB * 4; e += 256) p[(e >> 2) * kDtwpPStride + kT + (e & 3)] = 0.0f;
+    __syncthreads();
+    const __nv_bfloat16* Kb = ckv + (int64_t)b * kT * 2 * d + hh * 64;
+    const __nv_bfloat16* Vb = Kb + d;
+    const int64_t rs = 2 * (int64_t)d;
+    // ---- scores ----
+    for (int t = tid; t < kT; t += 256) {
+        float k[64];
+        const uint4* kr = reinterpret_cast<const uint4*>(Kb + (int64_t)t * rs);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; c8++) {
+            const uint4 u = __ldg(kr + c8);
+            const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __bfloat1622float2(e[j]);
+                k[c8 * 8 + 2 * j] = f.x;
+                k[c8 * 8 + 2 * j + 1] = f.y;
+            }
+        }
+#pragma unroll 4
+        for (int qi = 0; qi < kDtwpQB; qi++) {
+            const float4* qv = reinterpret_cast<const float4*>(qs + qi * 64);
+            float a = 0.0f;
+#pragma unroll
+            for (int c4 = 0; c4 < 16; c4++) {
+                const float4 f = qv[c4];
+                a = fmaf(f.x, k[c4 * 4], a);
+                a = fmaf(f.y, k[c4 * 4 + 1], a);
+                a = fmaf(f.z, k[c4 * 4 + 2], a);
+                a = fmaf(f.w, k[c4 * 4 + 3], a);
+            }
+            p[qi * kDtwpPStride + t] = a;
+        }
+    }
+    __syncthreads();
+    // ---- softmax (warp w: queries w, w + 8) and alignment-head capture ----
+    const int ahead = ahead_map ? ahead_map[hh] : -1;
+    for (int qi = warp; qi < nq; qi += 8) {
+        float* pr = p + qi * kDtwpPStride;
+        float mx = -INFINITY;
+        for (int t = lane; t < kT; t += 32) mx = fmaxf(mx, pr[t]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int t = lane; t < kT; t += 32) {
+            const float e = expf(pr[t] - mx);
+            pr[t] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int t = lane; t < kT; t += 32) pr[t] *= inv;
+        if (ahead >= 0) {
+            __syncwarp();
+            const int A_b = aw_A[b];
+            float* dst = aw + aw_off[b] + ((int64_t)ahead * T_b + (q0 + qi)) * A_b;
+            for (int t = lane; t < A_b; t += 32) dst[t] = pr[t];
+        }
+    }
+    __syncthreads();
+    // ---- P V: warp = key slice (groups of 4 keys), lane = column pair ----
+    float acc[kDtwpQB][2];
+#pragma unroll
+    for (int qi = 0; qi < kDtwpQB; qi++) { acc[qi][0] = 0.0f; acc[qi][1] = 0.0f; }
+    for (int t4 = warp * 4; t4 < kT; t4 += 32) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            v[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vb + (int64_t)(t4 + j) * rs + 2 * lane));
+#pragma unroll
+        for (int qi = 0; qi < kDtwpQB; qi++) {
+            const float4 pv = *reinterpret_cast<const float4*>(p + qi * kDtwpPStride + t4);
+            acc[qi][0] = fmaf(pv.x, v[0].x, acc[qi][0]); acc[qi][1] = fmaf(pv.x, v[0].y, acc[qi][1]);
+            acc[qi][0] = fmaf(pv.y, v[1].x, acc[qi][0]); acc[qi][1] = fmaf(pv.y, v[1].y, acc[qi][1]);
+            acc[qi][0] = fmaf(pv.z, v[2].x, acc[qi][0]); acc[qi][1] = fmaf(pv.z, v[2].y, acc[qi][1]);
+            acc[qi][0] = fmaf(pv.w, v[3].x, acc[qi][0]); acc[qi][1] = fmaf(pv.w, v[3].y, acc[qi][1]);
+        }
+    }
+    __syncthreads();  // all warps are done reading p
+    float* red = p;   // [8][16][64]
+#pragma unroll
+    for (int qi = 0; qi < kDtwpQB; qi++) {
+        red[(warp * kDtwpQB + qi) * 64 + 2 * lane] = acc[qi][0];
+        red[(warp * kDtwpQB + qi) * 64 + 2 * lane + 1] = acc[qi][1];
+    }
+    __syncthreads();
+    for (int e = tid; e < nq * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        float a = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) a += red[(w * kDtwpQB + qi) * 64 + c];
+        store_split(att, lo_off, (r0 + qi) * (int64_t)d + hh * 64 + c, a);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // whisper_process_logits + whisper_sample_token(best) + the decoder bookkeeping of whisper_full's inner loop
 // ---------------------------------------------------------------------------------------------------
@@ -322,10 +527,11 @@ constexpr int kSampPer = 51;  // 51 * 1024 = 52224 >= n_vocab
 
 __global__ void __launch_bounds__(kSampThreads, 1)
 dec_sample_kernel(const float* __restrict__ logits, int64_t ldv, DecWinState* __restrict__ win, wdr_token_data* __restrict__ tokens,
-                  int32_t* __restrict__ seq, int pos, const SampleParams sp, int32_t* __restrict__ done_count) {
+                  int32_t* __restrict__ seq, const int32_t* __restrict__ pos_ptr, int pos, const SampleParams sp, int32_t* __restrict__ done_count) {
     __shared__ float red[32];
     __shared__ unsigned long long red64[32];
     const int b = blockIdx.x, tid = threadIdx.x;
+    pos = load_pos(pos_ptr, pos);
     DecWinState st = win[b];
     if (st.completed || st.failed) return;
     const int n = sp.n_vocab;
@@ -469,9 +675,10 @@ dec_sample_kernel(const float* __restrict__ logits, int64_t ldv, DecWinState* __
 // ---------------------------------------------------------------------------------------------------
 void DecoderWorkspace::release() {
     for (void* p : {(void*)enc_bf16, (void*)sk, (void*)sv, (void*)x, (void*)h, (void*)att, (void*)ff, (void*)part, (void*)logits, (void*)seq,
-                    (void*)tokens, (void*)win, (void*)done_count, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
+                    (void*)tokens, (void*)win, (void*)done_count, (void*)pos_dev, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
         if (p) cudaFree(p);
     for (auto p : ckv) if (p) cudaFree(p);
+    if (step_graph) cudaGraphExecDestroy(step_graph);
     *this = DecoderWorkspace();
 }
 
@@ -499,6 +706,7 @@ int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
     WDR_CUDA_TRY(cudaMalloc(&tokens, sizeof(wdr_token_data) * (size_t)B * kDecMaxTokens));
     WDR_CUDA_TRY(cudaMalloc(&win, sizeof(DecWinState) * B));
     WDR_CUDA_TRY(cudaMalloc(&done_count, sizeof(int32_t)));
+    WDR_CUDA_TRY(cudaMalloc(&pos_dev, sizeof(int32_t)));
     WDR_CUDA_TRY(cudaMalloc(&ahead_map, sizeof(int32_t) * n_layer * n_head));
     WDR_CUDA_TRY(cudaMalloc(&aw_off, sizeof(int64_t) * B));
     WDR_CUDA_TRY(cudaMalloc(&aw_T, sizeof(int32_t) * B));
@@ -566,7 +774,9 @@ static int skinny_gemm(const __nv_bfloat16* A, int B, const __nv_bfloat16* W, in
     return gemm_bf16(g, st);
 }
 
-int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof) {
+int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof,
+                 bool pos_on_device) {
+    const int32_t* pos_ptr = pos_on_device ? ws.pos_dev : nullptr;
     const WhisperArch& a = ctx->arch;
     const WhisperWeights& w = ctx->w;
     const int d = a.d, H = a.n_head, L = a.n_dec_layer;
@@ -577,7 +787,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
     bool pending = false;
     {
         ProfScope ps(prof, KC_DECODER, st);
-        dec_embed_kernel<<<B, 128, 0, st>>>(ws.seq, pos, w.tok_emb, w.dec_pos, d, a.n_vocab, ws.x);
+        dec_embed_kernel<<<B, 128, 0, st>>>(ws.seq, pos_ptr, pos, w.tok_emb, w.dec_pos, d, a.n_vocab, ws.x);
         WDR_LAUNCH_CHECK();
     }
     auto ln = [&](const float* g, const float* b) -> int {
@@ -603,7 +813,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         {
             ProfScope ps(prof, KC_DECODER, st);
             dec_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_qkv,
-                                                               ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos, d, ws.att,
+                                                               ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att,
                                                                (int64_t)ws.cap_B * d, win, t_limit);
             WDR_LAUNCH_CHECK();
         }
@@ -615,7 +825,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             ProfScope ps(prof, KC_DEC_CROSS, st);
             dec_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d,
                                                                 capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T,
-                                                                ws.aw_A, pos, win, t_limit);
+                                                                ws.aw_A, pos_ptr, pos, win, t_limit);
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
@@ -647,11 +857,160 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
     return WDR_OK;
 }
 
-int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof) {
+void DtwPassWorkspace::release() {
+    for (void* p : {(void*)x, (void*)h, (void*)att, (void*)ff, (void*)part, (void*)row_b, (void*)row_pos, (void*)row_off})
+        if (p) cudaFree(p);
+    *this = DtwPassWorkspace();
+}
+
+int DtwPassWorkspace::reserve(int64_t rows, int d_model) {
+    if (rows <= cap_rows && d_model == d) return WDR_OK;
+    release();
+    d = d_model;
+    const size_t M = (size_t)((rows + 127) / 128 * 128);
+    WDR_CUDA_TRY(cudaMalloc(&x, sizeof(float) * M * d));
+    WDR_CUDA_TRY(cudaMalloc(&h, sizeof(__nv_bfloat16) * 2 * M * d));
+    WDR_CUDA_TRY(cudaMalloc(&att, sizeof(__nv_bfloat16) * 2 * M * d));
+    WDR_CUDA_TRY(cudaMalloc(&ff, sizeof(__nv_bfloat16) * 2 * M * 4 * d));
+    WDR_CUDA_TRY(cudaMalloc(&part, sizeof(float) * M * 4 * d));
+    WDR_CUDA_TRY(cudaMalloc(&row_b, sizeof(int32_t) * M));
+    WDR_CUDA_TRY(cudaMalloc(&row_pos, sizeof(int32_t) * M));
+    WDR_CUDA_TRY(cudaMalloc(&row_off, sizeof(int32_t) * kDecMaxBatch));
+    cap_rows = (int64_t)M;
+    return WDR_OK;
+}
+
+// out[M][N] (fp32) = (hi, lo)[M][K] * W[N][K]^T, full-size tcgen05 GEMM over the packed rows
+static int packed_gemm(const __nv_bfloat16* A, int64_t M, int64_t M_cap, const __nv_bfloat16* W, int N, int K, float* out, cudaStream_t st, Profiler* prof) {
+    GemmDesc g;
+    g.A = A; g.a_row_stride = K; g.rows_per_batch = (int)M; g.n_batch = 1;
+    g.W = W; g.ldw = K; g.N = N; g.K = K;
+    g.epilogue = EPI_F32; g.out = out; g.ldc = N; g.bn = 64;
+    g.dual_a = true; g.a_dual_stride = M_cap * K;
+    ProfScope ps(prof, KC_DEC_GEMM, st);
+    return gemm_bf16(g, st);
+}
+
+int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorkspace& pw, int B, const int32_t* T_host, cudaStream_t st, Profiler* prof) {
+    const WhisperArch& a = ctx->arch;
+    const WhisperWeights& w = ctx->w;
+    const int d = a.d, H = a.n_head;
+    WDR_REQUIRE(B > 0 && B <= ws.cap_B && B <= kDecMaxBatch, "decoder_dtw_pass: bad batch");
+    std::vector<int32_t> row_b, row_pos, row_off(kDecMaxBatch, 0);
+    int max_T = 0;
+    for (int b = 0; b < B; b++) {
+        WDR_REQUIRE(T_host[b] >= 0 && T_host[b] <= kDtwpMaxT && T_host[b] <= kDecSeqCap, "decoder_dtw_pass: sequence too long");
+        row_off[b] = (int32_t)row_b.size();
+        for (int i = 0; i < T_host[b]; i++) { row_b.push_back(b); row_pos.push_back(i); }
+        max_T = std::max(max_T, T_host[b]);
+    }
+    const int64_t M = (int64_t)row_b.size();
+    if (M == 0) return WDR_OK;
+    int rc;
+    if ((rc = pw.reserve(M, d)) != WDR_OK) return rc;
+    const int64_t Mc = pw.cap_rows;
+    WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_b, row_b.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_pos, row_pos.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_off, row_off.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors die with this frame
+    static bool attr_done = false;
+    const int smem_self = (int)sizeof(float) * (2 * kDtwpMaxT * 65 + 8 * 64 + 8 * kDtwpMaxT);
+    const int smem_cross = (int)sizeof(float) * (kDtwpQB * 64 + kDtwpQB * kDtwpPStride);
+    if (!attr_done) {
+        WDR_CUDA_TRY(cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self));
+        WDR_CUDA_TRY(cudaFuncSetAttribute(dtwp_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross));
+        attr_done = true;
+    }
+    int L_run = 0;
+    for (auto& lh : ctx->aheads) L_run = std::max(L_run, lh.first + 1);
+    L_run = std::min(L_run, a.n_dec_layer);
+    {
+        ProfScope ps(prof, KC_DECODER, st);
+        dtwp_embed_kernel<<<(unsigned)M, 128, 0, st>>>(ws.seq, pw.row_b, pw.row_pos, w.tok_emb, w.dec_pos, d, a.n_vocab, pw.x);
+        WDR_LAUNCH_CHECK();
+    }
+    const float* pend_bias = nullptr;
+    bool pending = false;
+    auto ln = [&](const float* g, const float* bta) -> int {
+        ProfScope ps(prof, KC_DECODER, st);
+        dec_ln_kernel<<<(unsigned)M, d / 4, 0, st>>>(pw.x, pending ? pw.part : nullptr, 1, 0, d, pend_bias, g, bta, pw.h, Mc * d, d);
+        WDR_LAUNCH_CHECK();
+        pending = false;
+        return WDR_OK;
+    };
+    for (int l = 0; l < L_run; l++) {
+        const DecLayerW& e = w.dec[l];
+        if ((rc = ln(e.ln1_g, e.ln1_b)) != WDR_OK) return rc;
+        if ((rc = packed_gemm(pw.h, M, Mc, e.w_qkv, 3 * d, d, pw.part, st, prof)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_DECODER, st);
+            dtwp_self_attn_kernel<<<dim3(H, B), 256, smem_self, st>>>(pw.part, e.b_qkv, pw.row_off, ws.aw_T, d, pw.att, Mc * d);
+            WDR_LAUNCH_CHECK();
+        }
+        if ((rc = packed_gemm(pw.att, M, Mc, e.w_o, d, d, pw.part, st, prof)) != WDR_OK) return rc;
+        pending = true; pend_bias = e.b_o;
+        if ((rc = ln(e.ln2_g, e.ln2_b)) != WDR_OK) return rc;
+        if ((rc = packed_gemm(pw.h, M, Mc, e.w_cq, d, d, pw.part, st, prof)) != WDR_OK) return rc;
+        {
+            ProfScope ps(prof, KC_DEC_CROSS_BATCHED, st);
+            dtwp_cross_attn_kernel<<<dim3((max_T + kDtwpQB - 1) / kDtwpQB, H, B), 256, smem_cross, st>>>(
+                pw.part, e.b_cq, ws.ckv[l], d, pw.row_off, ws.aw_T, pw.att, Mc * d, ws.ahead_map + (size_t)l * H, ws.aw, ws.aw_off, ws.aw_A);
+            WDR_LAUNCH_CHECK();
+        }
+        if (l == L_run - 1) break;  // nothing after the last alignment head's probabilities is used
+        if ((rc = packed_gemm(pw.att, M, Mc, e.w_co, d, d, pw.part, st, prof)) != WDR_OK) return rc;
+        pending = true; pend_bias = e.b_co;
+        if ((rc = ln(e.ln3_g, e.ln3_b)) != WDR_OK) return rc;
+        {
+            GemmDesc g;
+            g.A = pw.h; g.a_row_stride = d; g.rows_per_batch = (int)M; g.n_batch = 1;
+            g.W = e.w_fc1; g.ldw = d; g.N = 4 * d; g.K = d;
+            g.epilogue = EPI_BIAS_GELU_SPLIT; g.out = pw.ff; g.ldc = 4 * d; g.bias = e.b_fc1; g.bn = 64;
+            g.dual_a = true; g.a_dual_stride = Mc * d;
+            g.split_stride = Mc * 4 * d;
+            ProfScope ps(prof, KC_DEC_GEMM, st);
+            if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
+        }
+        if ((rc = packed_gemm(pw.ff, M, Mc, e.w_fc2, d, 4 * d, pw.part, st, prof)) != WDR_OK) return rc;
+        pending = true; pend_bias = e.b_fc2;
+    }
+    return WDR_OK;
+}
+
+int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof,
+                   bool pos_on_device) {
     WDR_REQUIRE(sp.n_vocab <= kSampThreads * kSampPer, "vocabulary larger than the sampler's register tile");
     ProfScope ps(prof, KC_DECODER, st);
-    dec_sample_kernel<<<B, kSampThreads, 0, st>>>(ws.logits, ws.ldv, ws.win, ws.tokens, ws.seq, pos, sp, ws.done_count);
+    dec_sample_kernel<<<B, kSampThreads, 0, st>>>(ws.logits, ws.ldv, ws.win, ws.tokens, ws.seq, pos_on_device ? ws.pos_dev : nullptr, pos, sp, ws.done_count);
     WDR_LAUNCH_CHECK();
+    return WDR_OK;
+}
+
+// One greedy iteration as a replayable graph: sample at *pos_dev, advance the counter, decoder step (with logits) at the new
+// position.  Captured once per (batch, sampling parameters) on the caller's stream and cached in the workspace.
+int decoder_decode_graph(const wdr_context* ctx, DecoderWorkspace& ws, int B, const SampleParams& sp, cudaStream_t st, cudaGraphExec_t* out) {
+    if (ws.step_graph && ws.graph_B == B && memcmp(&ws.graph_sp, &sp, sizeof(sp)) == 0) { *out = ws.step_graph; return WDR_OK; }
+    if (ws.step_graph) { cudaGraphExecDestroy(ws.step_graph); ws.step_graph = nullptr; }
+    WDR_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = decoder_sample(ctx, ws, B, 0, sp, st, nullptr, true);
+    if (rc == WDR_OK) {
+        dec_advance_kernel<<<1, 1, 0, st>>>(ws.pos_dev);
+        count_launch();
+        rc = decoder_step(ctx, ws, B, 0, true, DEC_MODE_DECODE, st, nullptr, true);
+    }
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != WDR_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess || !graph) { set_error("decode graph capture failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return WDR_ERR_CUDA; }
+    size_t n_nodes = 0;
+    cudaGraphGetNodes(graph, nullptr, &n_nodes);
+    const cudaError_t e2 = cudaGraphInstantiate(&ws.step_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { ws.step_graph = nullptr; set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e2)); return WDR_ERR_CUDA; }
+    ws.graph_B = B;
+    ws.graph_sp = sp;
+    ws.graph_nodes = (int)n_nodes;
+    *out = ws.step_graph;
     return WDR_OK;
 }
 

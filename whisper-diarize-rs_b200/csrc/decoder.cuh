@@ -46,6 +46,10 @@ struct DecoderWorkspace {
     wdr_token_data* tokens = nullptr;  // [B][224]
     DecWinState* win = nullptr;        // [B]
     int32_t* done_count = nullptr;
+    int32_t* pos_dev = nullptr;        // device-resident step counter read by the graph-replayed decode step
+    cudaGraphExec_t step_graph = nullptr;  // one greedy iteration (sample, advance, step), see decoder_decode_graph
+    int graph_B = 0, graph_nodes = 0;
+    SampleParams graph_sp{};
     int32_t* ahead_map = nullptr;      // [L*H] -> alignment-head index or -1
     int n_aheads = 0;
     // alignment-head capture of the DTW pass: window b's w[H_a][T_b][A_b] starts at aw + aw_off[b]
@@ -58,6 +62,22 @@ struct DecoderWorkspace {
     void release();
 };
 
+// Workspace of the batched DTW pass (decoder_dtw_pass): all teacher-forced tokens of all windows as packed rows.
+struct DtwPassWorkspace {
+    int64_t cap_rows = 0;
+    int d = 0;
+    float* x = nullptr;            // [M][d] residual stream
+    __nv_bfloat16* h = nullptr;    // [2][M][d]  (hi, lo)
+    __nv_bfloat16* att = nullptr;  // [2][M][d]
+    __nv_bfloat16* ff = nullptr;   // [2][M][4d]
+    float* part = nullptr;         // [M][4d] GEMM output (fp32)
+    int32_t* row_b = nullptr;      // [M] window of each packed row
+    int32_t* row_pos = nullptr;    // [M] token position of each packed row
+    int32_t* row_off = nullptr;    // [kDecMaxBatch] first packed row of each window
+    int reserve(int64_t rows, int d_model);
+    void release();
+};
+
 // cross-KV projection of all decoder layers from ws.enc_bf16 (B windows)
 int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaStream_t st, Profiler* prof);
 // one decoder step at position pos for all B windows (token = ws.seq[b][pos]).  want_logits: final LN + logits GEMM.
@@ -66,8 +86,17 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 //       DEC_MODE_DTW    = teacher-forced DTW pass: alignment-head cross-attention rows go to ws.aw, windows stop at their own
 //                         length ws.aw_T[b], and without logits only the layers up to the last alignment head run.
 enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2 };
-int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof);
+int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof,
+                 bool pos_on_device = false);
+// The DTW pass in one shot: the teacher-forced sequences ws.seq[b][0 .. T_b) (T_b = ws.aw_T[b], host copy in T_host; 0 = window
+// not in the pass) of all B windows run through the decoder layers up to the last alignment head as ONE batch of sum(T_b) packed
+// rows — every linear layer is a full-size tcgen05 GEMM (weights read once, not once per token position) and the cross-attention
+// reads each window's K_c/V_c once per 16 queries instead of once per token.  Alignment-head probabilities land in ws.aw exactly as
+// in DEC_MODE_DTW of decoder_step (same layout, same fp32 softmax, same (hi, lo) bf16 activations).
+int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorkspace& pw, int B, const int32_t* T_host, cudaStream_t st, Profiler* prof);
 // whisper_process_logits + greedy whisper_sample_token + decoder bookkeeping on ws.logits; appends to ws.tokens / ws.seq[pos+1]
-int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof);
+int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof,
+                   bool pos_on_device = false);
+int decoder_decode_graph(const wdr_context* ctx, DecoderWorkspace& ws, int B, const SampleParams& sp, cudaStream_t st, cudaGraphExec_t* out);
 
 }  // namespace wdr

@@ -1,0 +1,475 @@
+// embedding.cu — WeSpeaker ResNet34 speaker embeddings on the device: Kaldi fbank -> 2-D ResNet34 (tcgen05 GEMMs) -> TSTP -> Linear.
+//
+// Replaces pyannote_rs::EmbeddingExtractor::{new, compute} (reference src/transcribe.rs:343, 466-467):
+// int16 samples cast to f32 without scaling -> knf fbank (fbank.cu) -> per-column mean subtraction -> ONNX model "feats" [1,T,80]
+// -> "embs" [1,D].  The crate ships the CAM++ export; the north-star names WeSpeaker ResNet34: D = 256.
+//
+// Segments are independent, so a call takes a batch of them.  Activations are bf16, channels innermost: level r holds
+// [segment][f < 80 >> r][t < T_r][C] as packed rows (segment s starts at row off_r[s]); every convolution is one GEMM
+//     out[rows][C_out] = im2col(in)[rows][k*k*C_in] * W[C_out][k*k*C_in]^T
+// on the tcgen05 kernel (gemm.cu) with the folded BatchNorm shift, the residual add and the ReLU in its epilogue.  The im2col
+// matrix is materialised in bf16 by a coalesced 16-byte gather (zero rows at the borders): 9x the activation bytes, HBM-trivial
+// next to the GEMM at these sizes.  TSTP (mean / unbiased std over time per (channel, frequency)) and the 5120 -> 256 linear
+// layer are fp32.
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "gemm.cuh"
+#include "nn_common.cuh"
+
+namespace wdr {
+
+int fbank_run(const int16_t* pcm, const int64_t* seg_offset_dev, const int64_t* feat_offset_dev, const std::vector<int64_t>& seg_offset_host,
+              int n_bins, int subtract_mean, float* out, cudaStream_t st);
+
+constexpr int kEmbDim = 256, kEmbBins = 80, kEmbPooled = 5120;
+constexpr int kEmbMaxFramesPerGroup = 8192;  // fbank frames per forward batch (bounds the im2col workspace: 80 * frames * 288 bf16)
+
+struct ConvW {
+    int c_in, c_out, k, stride, K;  // K = GEMM inner size (k*k*c_in, conv1: 16)
+    __nv_bfloat16* w;               // [c_out][K]
+    float* b;                       // [c_out]
+};
+struct BlockW { ConvW c1, c2, sc; bool has_sc; };
+
+static inline uint16_t f32_to_bf16_bits(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t r = ((u >> 16) & 1u) + 0x7FFFu;
+    return (uint16_t)((u + r) >> 16);
+}
+
+// fbank feats [t][80] fp32 -> conv1's im2col matrix [rows = (f, t)][16] bf16 (taps (ky, kx) over (f, t); columns 9..15 zero)
+__global__ void emb_im2col_feats_kernel(const float* __restrict__ feats, const int64_t* __restrict__ feat_off, const int32_t* __restrict__ T,
+                                        const int64_t* __restrict__ row_off, __nv_bfloat16* __restrict__ A) {
+    const int seg = blockIdx.y, Ts = T[seg];
+    const int64_t rows = (int64_t)kEmbBins * Ts;
+    const float* x = feats + feat_off[seg] * kEmbBins;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(row / Ts), t = (int)(row - (int64_t)f * Ts);
+        __align__(16) __nv_bfloat16 v[16];
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const int fi = f + tap / 3 - 1, ti = t + tap % 3 - 1;
+            const float a = (fi >= 0 && fi < kEmbBins && ti >= 0 && ti < Ts) ? x[(int64_t)ti * kEmbBins + fi] : 0.0f;
+            v[tap] = __float2bfloat16_rn(a);
+        }
+#pragma unroll
+        for (int tap = 9; tap < 16; tap++) v[tap] = __float2bfloat16_rn(0.0f);
+        uint4* dst = reinterpret_cast<uint4*>(A + (row_off[seg] + row) * 16);
+        dst[0] = *reinterpret_cast<const uint4*>(v);
+        dst[1] = *reinterpret_cast<const uint4*>(v + 8);
+    }
+}
+
+// in [rows_in][C] bf16 -> A [rows_out][KS*KS*C] bf16, one 16-byte vector (8 channels of one tap) per thread iteration
+template <int KS>
+__global__ void emb_im2col_kernel(const __nv_bfloat16* __restrict__ in, int C, int F_in, int F_out, int stride, const int32_t* __restrict__ T_in,
+                                  const int32_t* __restrict__ T_out, const int64_t* __restrict__ in_off, const int64_t* __restrict__ out_off,
+                                  __nv_bfloat16* __restrict__ A) {
+    const int seg = blockIdx.y, Ti = T_in[seg], To = T_out[seg];
+    const int cv_n = C >> 3, vec_per_row = KS * KS * cv_n;
+    const int64_t total = (int64_t)F_out * To * vec_per_row;
+    const uint4* src = reinterpret_cast<const uint4*>(in) + in_off[seg] * cv_n;
+    uint4* dst = reinterpret_cast<uint4*>(A) + out_off[seg] * vec_per_row;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = idx / vec_per_row;
+        const int v = (int)(idx - row * vec_per_row);
+        const int tap = v / cv_n, cv = v - tap * cv_n;
+        const int f = (int)(row / To), t = (int)(row - (int64_t)f * To);
+        const int fi = f * stride + tap / KS - KS / 2, ti = t * stride + tap % KS - KS / 2;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (fi >= 0 && fi < F_in && ti >= 0 && ti < Ti) val = __ldg(src + ((int64_t)fi * Ti + ti) * cv_n + cv);
+        dst[idx] = val;
+    }
+}
+
+// TSTP: x [rows][256] bf16 at level 3 (F = 10) -> stats[seg][c*10 + f] = mean_t, stats[seg][2560 + c*10 + f] = sqrt(unbiased var_t + 1e-7)
+__global__ void emb_tstp_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ T3, const int64_t* __restrict__ off3,
+                                float* __restrict__ stats) {
+    const int seg = blockIdx.y, f = blockIdx.x, c = threadIdx.x;  // 256 threads = channels
+    const int Ts = T3[seg];
+    const __nv_bfloat16* p = x + (off3[seg] + (int64_t)f * Ts) * 256 + c;
+    double s = 0.0, q = 0.0;
+    for (int t = 0; t < Ts; t++) {
+        const double v = (double)__bfloat162float(p[(int64_t)t * 256]);
+        s += v; q += v * v;
+    }
+    const double mean = s / Ts;
+    double var = (q - s * mean) / (Ts > 1 ? Ts - 1 : 1);
+    if (var < 0.0) var = 0.0;
+    stats[(int64_t)seg * kEmbPooled + c * 10 + f] = (float)mean;
+    stats[(int64_t)seg * kEmbPooled + 2560 + c * 10 + f] = (float)sqrt(var + 1e-7);
+}
+
+}  // namespace wdr
+
+using namespace wdr;
+
+struct wdr_emb {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<void*> allocs;
+    ConvW conv1{};
+    std::vector<BlockW> blocks;
+    float *lin_w = nullptr, *lin_b = nullptr;
+    // workspaces (grown on demand)
+    __nv_bfloat16 *act[4] = {nullptr, nullptr, nullptr, nullptr}, *col = nullptr;
+    size_t act_cap = 0, col_cap = 0;
+    double conv_flops = 0.0;  // of the last call (algorithmic, 2*M*N*K)
+};
+
+namespace wdr {
+
+static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, int ci, int co, int k, int stride, ConvW* out) {
+    const int fan = ci * k * k;
+    const std::string base = "resnet34." + name;
+    std::vector<float> w = nn_synth(seed, base + ".weight", (size_t)co * fan, 0.0f, (float)sqrt(6.0 / fan));
+    const bool tail = name.size() >= 5 && (name.compare(name.size() - 5, 5, "conv2") == 0 || name.compare(name.size() - 8 > name.size() ? 0 : name.size() - 8, 8, "shortcut") == 0);
+    std::vector<float> g = nn_synth(seed, base + ".bn.weight", co, tail ? 0.7f : 1.0f, 0.1f);
+    std::vector<float> beta = nn_synth(seed, base + ".bn.bias", co, 0.0f, 0.1f);
+    std::vector<float> mean = nn_synth(seed, base + ".bn.running_mean", co, 0.0f, 0.1f);
+    std::vector<float> var = nn_synth(seed, base + ".bn.running_var", co, 1.0f, 0.2f);
+    const int K = ci == 1 ? 16 : fan;
+    std::vector<uint16_t> wb((size_t)co * K, 0);
+    std::vector<float> bias(co);
+    for (int o = 0; o < co; o++) {
+        volatile float denom = sqrtf(var[o] + 1e-5f);
+        volatile float s = g[o] / denom;
+        volatile float ms = mean[o] * s;
+        bias[o] = beta[o] - ms;
+        // synthetic tensor layout is PyTorch's [co][ci][ky][kx]; the GEMM wants [co][(ky*k + kx)*ci + c]
+        for (int c = 0; c < ci; c++)
+            for (int t = 0; t < k * k; t++) {
+                volatile float prod = w[((size_t)o * ci + c) * k * k + t] * s;
+                wb[(size_t)o * K + (size_t)t * ci + c] = f32_to_bf16_bits(prod);
+            }
+    }
+    __nv_bfloat16* dw = nullptr;
+    float* db = nullptr;
+    WDR_CUDA_TRY(cudaMalloc(&dw, sizeof(uint16_t) * wb.size()));
+    m->allocs.push_back(dw);
+    WDR_CUDA_TRY(cudaMalloc(&db, sizeof(float) * co));
+    m->allocs.push_back(db);
+    WDR_CUDA_TRY(cudaMemcpy(dw, wb.data(), sizeof(uint16_t) * wb.size(), cudaMemcpyHostToDevice));
+    WDR_CUDA_TRY(cudaMemcpy(db, bias.data(), sizeof(float) * co, cudaMemcpyHostToDevice));
+    *out = ConvW{ci, co, k, stride, K, dw, db};
+    return WDR_OK;
+}
+
+static int emb_gemm(const __nv_bfloat16* A, int64_t rows, const ConvW& c, int epi, const __nv_bfloat16* resid, __nv_bfloat16* out, cudaStream_t st) {
+    GemmDesc g;
+    g.A = A; g.a_row_stride = c.K; g.rows_per_batch = (int)rows; g.n_batch = 1;
+    g.W = c.w; g.ldw = c.K; g.N = c.c_out; g.K = c.K;
+    g.epilogue = epi; g.out = out; g.ldc = c.c_out; g.bias = c.b; g.resid_bf16 = resid;
+    return gemm_bf16(g, st);
+}
+
+struct EmbLevel {
+    int F;
+    std::vector<int32_t> T;
+    std::vector<int64_t> off;  // n + 1
+    int32_t* d_T = nullptr;
+    int64_t* d_off = nullptr;
+    int64_t rows() const { return off.back(); }
+    int max_rows() const {
+        int64_t m = 0;
+        for (size_t i = 0; i + 1 < off.size(); i++) m = std::max(m, off[i + 1] - off[i]);
+        return (int)m;
+    }
+};
+
+template <typename T>
+static int emb_grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return WDR_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    WDR_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(p), need * sizeof(T)));
+    *cap = need;
+    return WDR_OK;
+}
+
+// One forward batch: feats (device, [frames][80], segment s at frame feat_off[s]) -> out_dev[n][256]
+static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t>& feat_off, float* out_dev, cudaStream_t st) {
+    const int n = (int)feat_off.size() - 1;
+    EmbLevel lv[4];
+    for (int r = 0; r < 4; r++) {
+        lv[r].F = kEmbBins >> r;
+        lv[r].T.resize(n);
+        lv[r].off.assign(n + 1, 0);
+        for (int s = 0; s < n; s++) {
+            const int T0 = (int)(feat_off[s + 1] - feat_off[s]);
+            int T = T0;
+            for (int k = 0; k < r; k++) T = (T + 1) / 2;
+            lv[r].T[s] = T;
+            lv[r].off[s + 1] = lv[r].off[s] + (int64_t)lv[r].F * T;
+        }
+    }
+    WDR_REQUIRE(lv[0].rows() < (int64_t)1 << 31, "embedding batch too large");
+    // level tables + feat offsets on the device
+    DevBuf<int32_t> d_T;
+    DevBuf<int64_t> d_off;
+    WDR_CUDA_TRY(d_T.alloc((size_t)4 * n));
+    WDR_CUDA_TRY(d_off.alloc((size_t)5 * (n + 1)));
+    for (int r = 0; r < 4; r++) {
+        lv[r].d_T = d_T.p + (size_t)r * n;
+        lv[r].d_off = d_off.p + (size_t)r * (n + 1);
+        WDR_CUDA_TRY(cudaMemcpyAsync(lv[r].d_T, lv[r].T.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
+        WDR_CUDA_TRY(cudaMemcpyAsync(lv[r].d_off, lv[r].off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    }
+    int64_t* d_feat_off = d_off.p + (size_t)4 * (n + 1);
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_feat_off, feat_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    // workspaces
+    const size_t rows0 = (size_t)lv[0].rows();
+    const size_t act_need = rows0 * 32 + 1024, col_need = rows0 * 288 + 1024;
+    if (act_need > m->act_cap) {
+        for (int i = 0; i < 4; i++) { if (m->act[i]) cudaFree(m->act[i]); m->act[i] = nullptr; }
+        m->act_cap = 0;
+        for (int i = 0; i < 4; i++) WDR_CUDA_TRY(cudaMalloc(&m->act[i], sizeof(__nv_bfloat16) * act_need));
+        m->act_cap = act_need;
+    }
+    int rc;
+    if ((rc = emb_grow(&m->col, &m->col_cap, col_need)) != WDR_OK) return rc;
+    auto blocks_for = [](int64_t work) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, 148 * 8)); };
+    double flops = 0.0;
+    // conv1
+    {
+        emb_im2col_feats_kernel<<<dim3(blocks_for(lv[0].max_rows()), n), 256, 0, st>>>(feats, d_feat_off, lv[0].d_T, lv[0].d_off, m->col);
+        WDR_LAUNCH_CHECK();
+        if ((rc = emb_gemm(m->col, lv[0].rows(), m->conv1, EPI_BIAS_RELU_BF16, nullptr, m->act[0], st)) != WDR_OK) return rc;
+        flops += 2.0 * lv[0].rows() * 32 * 9;
+    }
+    __nv_bfloat16 *x = m->act[0], *y1 = m->act[1], *sc = m->act[2], *x2 = m->act[3];
+    int level = 0;
+    auto im2col = [&](const __nv_bfloat16* in, const ConvW& c, int lin, int lout) -> int {
+        const int64_t work = (int64_t)lv[lout].max_rows() * c.k * c.k * (c.c_in / 8);
+        if (c.k == 3)
+            emb_im2col_kernel<3><<<dim3(blocks_for(work), n), 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lout].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off,
+                                                                           lv[lout].d_off, m->col);
+        else
+            emb_im2col_kernel<1><<<dim3(blocks_for(work), n), 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lout].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off,
+                                                                           lv[lout].d_off, m->col);
+        WDR_LAUNCH_CHECK();
+        flops += 2.0 * lv[lout].rows() * c.c_out * c.c_in * c.k * c.k;
+        return WDR_OK;
+    };
+    for (const BlockW& b : m->blocks) {
+        const int lout = level + (b.c1.stride == 2 ? 1 : 0);
+        if ((rc = im2col(x, b.c1, level, lout)) != WDR_OK) return rc;
+        if ((rc = emb_gemm(m->col, lv[lout].rows(), b.c1, EPI_BIAS_RELU_BF16, nullptr, y1, st)) != WDR_OK) return rc;
+        const __nv_bfloat16* resid = x;
+        if (b.has_sc) {
+            if (b.sc.stride == 1) {  // 1x1 stride 1: the activation matrix itself is the GEMM operand
+                if ((rc = emb_gemm(x, lv[lout].rows(), b.sc, EPI_BIAS_BF16, nullptr, sc, st)) != WDR_OK) return rc;
+                flops += 2.0 * lv[lout].rows() * b.sc.c_out * b.sc.c_in;
+            } else {
+                if ((rc = im2col(x, b.sc, level, lout)) != WDR_OK) return rc;
+                if ((rc = emb_gemm(m->col, lv[lout].rows(), b.sc, EPI_BIAS_BF16, nullptr, sc, st)) != WDR_OK) return rc;
+            }
+            resid = sc;
+        }
+        if ((rc = im2col(y1, b.c2, lout, lout)) != WDR_OK) return rc;
+        if ((rc = emb_gemm(m->col, lv[lout].rows(), b.c2, EPI_BIAS_ADD_RELU_BF16, resid, x2, st)) != WDR_OK) return rc;
+        std::swap(x, x2);
+        level = lout;
+    }
+    DevBuf<float> stats;
+    WDR_CUDA_TRY(stats.alloc((size_t)n * kEmbPooled));
+    emb_tstp_kernel<<<dim3(10, n), 256, 0, st>>>(x, lv[3].d_T, lv[3].d_off, stats.p);
+    WDR_LAUNCH_CHECK();
+    if ((rc = sgemm_nt(stats.p, kEmbPooled, m->lin_w, kEmbPooled, m->lin_b, out_dev, kEmbDim, n, kEmbDim, kEmbPooled, NN_ACT_NONE, st)) != WDR_OK) return rc;
+    WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the level tables and stats die with this frame
+    m->conv_flops += flops;
+    return WDR_OK;
+}
+
+}  // namespace wdr
+
+extern "C" wdr_emb* wdr_emb_init(const char* path, uint64_t seed, int device) {
+    clear_error();
+    if (path && path[0]) { set_error("wdr_emb_init: ONNX files are not supported yet (pass NULL for seeded weights)"); return nullptr; }
+    if (ensure_device(device) != WDR_OK) return nullptr;
+    wdr_emb* m = new wdr_emb();
+    m->device = device;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("wdr_emb_init: stream"); delete m; return nullptr; }
+    int rc = emb_upload_conv(m, seed, "conv1", 1, 32, 3, 1, &m->conv1);
+    static const int planes[4] = {32, 64, 128, 256}, nblocks[4] = {3, 4, 6, 3}, strides[4] = {1, 2, 2, 2};
+    int c_in = 32;
+    for (int li = 0; li < 4 && rc == WDR_OK; li++)
+        for (int bi = 0; bi < nblocks[li] && rc == WDR_OK; bi++) {
+            const int s = bi == 0 ? strides[li] : 1;
+            char nm[64];
+            BlockW b{};
+            snprintf(nm, sizeof(nm), "layer%d.%d.conv1", li + 1, bi);
+            rc = emb_upload_conv(m, seed, nm, c_in, planes[li], 3, s, &b.c1);
+            snprintf(nm, sizeof(nm), "layer%d.%d.conv2", li + 1, bi);
+            if (rc == WDR_OK) rc = emb_upload_conv(m, seed, nm, planes[li], planes[li], 3, 1, &b.c2);
+            b.has_sc = s != 1 || c_in != planes[li];
+            if (b.has_sc && rc == WDR_OK) {
+                snprintf(nm, sizeof(nm), "layer%d.%d.shortcut", li + 1, bi);
+                rc = emb_upload_conv(m, seed, nm, c_in, planes[li], 1, s, &b.sc);
+            }
+            m->blocks.push_back(b);
+            c_in = planes[li];
+        }
+    if (rc == WDR_OK) {
+        std::vector<float> lw = nn_synth(seed, "resnet34.seg_1.weight", (size_t)kEmbDim * kEmbPooled, 0.0f, (float)(1.0 / sqrt(5120.0)));
+        std::vector<float> lb = nn_synth(seed, "resnet34.seg_1.bias", kEmbDim, 0.0f, 0.05f);
+        if (cudaMalloc(&m->lin_w, sizeof(float) * lw.size()) != cudaSuccess || cudaMalloc(&m->lin_b, sizeof(float) * lb.size()) != cudaSuccess) rc = WDR_ERR_CUDA;
+        else {
+            cudaMemcpy(m->lin_w, lw.data(), sizeof(float) * lw.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(m->lin_b, lb.data(), sizeof(float) * lb.size(), cudaMemcpyHostToDevice);
+        }
+    }
+    if (rc != WDR_OK) {
+        if (!wdr_last_error()[0]) set_error("wdr_emb_init: device allocation failed");
+        wdr_emb_free(m);
+        return nullptr;
+    }
+    return m;
+}
+
+extern "C" void wdr_emb_free(wdr_emb* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (void* p : m->allocs) cudaFree(p);
+    cudaFree(m->lin_w);
+    cudaFree(m->lin_b);
+    for (int i = 0; i < 4; i++) cudaFree(m->act[i]);
+    cudaFree(m->col);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int wdr_emb_dim(wdr_emb* m) { return m ? kEmbDim : 0; }
+
+extern "C" double wdr_emb_last_flops(wdr_emb* m) { return m ? m->conv_flops : 0.0; }
+
+// pcm_dev: device int16, segment s = [seg_off[s], seg_off[s+1]) (host offsets).  out_dev [n][256]; status[s] = 0 or WDR_ERR_TOO_SHORT.
+static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector<int64_t>& seg_off, float* out_dev, int32_t* status, cudaStream_t st) {
+    const int n = (int)seg_off.size() - 1;
+    m->conv_flops = 0.0;
+    // segments that yield at least one frame, in order, cut into forward groups by total frames
+    std::vector<int> live;
+    for (int s = 0; s < n; s++) {
+        const int64_t len = seg_off[s + 1] - seg_off[s];
+        WDR_REQUIRE(len >= 0 && len < ((int64_t)1 << 31), "segment length out of range");
+        const int T = wdr_fbank_frames((int)len);
+        if (status) status[s] = T > 0 ? WDR_OK : WDR_ERR_TOO_SHORT;
+        if (T > 0) live.push_back(s);
+    }
+    size_t i0 = 0;
+    while (i0 < live.size()) {
+        size_t i1 = i0;
+        int64_t frames = 0;
+        while (i1 < live.size()) {
+            const int T = wdr_fbank_frames((int)(seg_off[live[i1] + 1] - seg_off[live[i1]]));
+            if (i1 > i0 && frames + T > kEmbMaxFramesPerGroup) break;
+            frames += T;
+            i1++;
+        }
+        const int g = (int)(i1 - i0);
+        // this group's segments are generally not contiguous in pcm (short ones are skipped): per-segment offsets for the fbank
+        std::vector<int64_t> so(2 * (size_t)g), fo((size_t)g + 1, 0);
+        bool contiguous = true;
+        for (int k = 0; k < g; k++) {
+            const int s = live[i0 + k];
+            if (k > 0 && seg_off[s] != seg_off[live[i0 + k - 1] + 1]) contiguous = false;
+            fo[k + 1] = fo[k] + wdr_fbank_frames((int)(seg_off[s + 1] - seg_off[s]));
+        }
+        DevBuf<float> feats, emb;
+        DevBuf<int64_t> d_so, d_fo;
+        WDR_CUDA_TRY(feats.alloc((size_t)frames * kEmbBins));
+        WDR_CUDA_TRY(emb.alloc((size_t)g * kEmbDim));
+        WDR_CUDA_TRY(d_fo.alloc((size_t)g + 1));
+        WDR_CUDA_TRY(cudaMemcpyAsync(d_fo.p, fo.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
+        int rc;
+        if (contiguous) {
+            std::vector<int64_t> s2((size_t)g + 1);
+            for (int k = 0; k < g; k++) s2[k] = seg_off[live[i0 + k]];
+            s2[g] = seg_off[live[i0 + g - 1] + 1];
+            WDR_CUDA_TRY(d_so.alloc((size_t)g + 1));
+            WDR_CUDA_TRY(cudaMemcpyAsync(d_so.p, s2.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
+            WDR_CUDA_TRY(cudaStreamSynchronize(st));
+            rc = fbank_run(pcm_dev, d_so.p, d_fo.p, s2, kEmbBins, 1, feats.p, st);
+            if (rc != WDR_OK) return rc;
+        } else {
+            // one fbank launch per contiguous run
+            WDR_CUDA_TRY(d_so.alloc((size_t)g + 2));
+            int k0 = 0;
+            while (k0 < g) {
+                int k1 = k0 + 1;
+                while (k1 < g && seg_off[live[i0 + k1]] == seg_off[live[i0 + k1 - 1] + 1]) k1++;
+                std::vector<int64_t> s2((size_t)(k1 - k0) + 1);
+                for (int k = k0; k < k1; k++) s2[k - k0] = seg_off[live[i0 + k]];
+                s2[k1 - k0] = seg_off[live[i0 + k1 - 1] + 1];
+                WDR_CUDA_TRY(cudaMemcpyAsync(d_so.p, s2.data(), sizeof(int64_t) * s2.size(), cudaMemcpyHostToDevice, st));
+                WDR_CUDA_TRY(cudaStreamSynchronize(st));
+                rc = fbank_run(pcm_dev, d_so.p, d_fo.p + k0, s2, kEmbBins, 1, feats.p, st);
+                if (rc != WDR_OK) return rc;
+                WDR_CUDA_TRY(cudaStreamSynchronize(st));  // d_so is reused by the next run
+                k0 = k1;
+            }
+        }
+        rc = emb_forward(m, feats.p, fo, emb.p, st);
+        if (rc != WDR_OK) return rc;
+        for (int k = 0; k < g; k++)
+            WDR_CUDA_TRY(cudaMemcpyAsync(out_dev + (size_t)live[i0 + k] * kEmbDim, emb.p + (size_t)k * kEmbDim, sizeof(float) * kEmbDim, cudaMemcpyDeviceToDevice, st));
+        WDR_CUDA_TRY(cudaStreamSynchronize(st));
+        i0 = i1;
+    }
+    return WDR_OK;
+}
+
+extern "C" int wdr_emb_compute_batch_i16(wdr_emb* m, const int16_t* pcm, const int64_t* seg_offset, int n_segments, float* out, int32_t* status) {
+    clear_error();
+    WDR_REQUIRE(m && n_segments >= 0, "bad arguments");
+    if (n_segments == 0) return WDR_OK;
+    WDR_REQUIRE(pcm && seg_offset && out, "null pointer");
+    int rc = ensure_device(m->device);
+    if (rc != WDR_OK) return rc;
+    std::vector<int64_t> so(seg_offset, seg_offset + n_segments + 1);
+    for (int s = 0; s < n_segments; s++) WDR_REQUIRE(so[s + 1] >= so[s], "segment offsets must ascend");
+    const int64_t base = so[0], total = so[n_segments] - base;
+    for (auto& v : so) v -= base;
+    DevBuf<int16_t> d_pcm;
+    DevBuf<float> d_out;
+    WDR_CUDA_TRY(d_pcm.alloc((size_t)std::max<int64_t>(total, 1)));
+    WDR_CUDA_TRY(d_out.alloc((size_t)n_segments * kEmbDim));
+    WDR_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, sizeof(float) * (size_t)n_segments * kEmbDim, m->stream));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_pcm.p, pcm + base, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, m->stream));
+    rc = emb_compute_dev(m, d_pcm.p, so, d_out.p, status, m->stream);
+    if (rc != WDR_OK) return rc;
+    WDR_CUDA_TRY(cudaMemcpyAsync(out, d_out.p, sizeof(float) * (size_t)n_segments * kEmbDim, cudaMemcpyDeviceToHost, m->stream));
+    WDR_CUDA_TRY(cudaStreamSynchronize(m->stream));
+    return WDR_OK;
+}
+
+extern "C" int wdr_emb_compute_batch_i16_dev(wdr_emb* m, const int16_t* pcm_dev, const int64_t* seg_offset_host, int n_segments, float* out_dev,
+                                             int32_t* status_host, void* stream) {
+    clear_error();
+    WDR_REQUIRE(m && n_segments >= 0, "bad arguments");
+    if (n_segments == 0) return WDR_OK;
+    WDR_REQUIRE(pcm_dev && seg_offset_host && out_dev, "null pointer");
+    int rc = ensure_device(m->device);
+    if (rc != WDR_OK) return rc;
+    std::vector<int64_t> so(seg_offset_host, seg_offset_host + n_segments + 1);
+    for (int s = 0; s < n_segments; s++) WDR_REQUIRE(so[s + 1] >= so[s], "segment offsets must ascend");
+    return emb_compute_dev(m, pcm_dev, so, out_dev, status_host, stream ? (cudaStream_t)stream : m->stream);
+}
+
+extern "C" int wdr_emb_compute_i16(wdr_emb* m, const int16_t* pcm, int64_t n, float* out) {
+    clear_error();
+    WDR_REQUIRE(m && n >= 0 && out, "bad arguments");
+    if (wdr_fbank_frames((int)std::min<int64_t>(n, 1 << 30)) == 0) {
+        set_error("segment of %lld samples is shorter than one 25 ms fbank frame", (long long)n);
+        return WDR_ERR_TOO_SHORT;
+    }
+    const int64_t off[2] = {0, n};
+    int32_t status = 0;
+    return wdr_emb_compute_batch_i16(m, pcm, off, 1, out, &status);
+}

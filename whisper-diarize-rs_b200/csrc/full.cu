@@ -6,9 +6,12 @@
 // capture the alignment heads, dtw.cu).  Host work (scalar, data dependent, restated from SURVEY A.4-A.6): segment assembly,
 // whisper_exp_compute_token_level_timestamps, stamping t_dtw from the DTW path.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 #include "decoder.cuh"
@@ -213,6 +216,9 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     std::vector<int32_t> nv(B);
     for (int b = 0; b < B; b++) nv[b] = n_valid_host ? n_valid_host[chunk0 + b] : WDR_CHUNK_SAMPLES;
     WDR_CUDA_TRY(cudaMemcpyAsync(fs.nvalid_dev, nv.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+    for (auto& e : fs.ev_phase)
+        if (!e) WDR_CUDA_TRY(cudaEventCreate(&e));
+    WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[0], s));
     // ---- mel + encoder -> bf16 hidden states ----
     if ((rc = encode_chunks<In>(ctx, st->enc, pcm_dev, chunk_stride, fs.nvalid_dev, B, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
     // ---- energy for the token-timestamp heuristic (D2H overlaps the decode) ----
@@ -230,7 +236,9 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                                              sizeof(float) * nv[b], cudaMemcpyDeviceToHost, st->copy_stream));
         WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy_done, st->copy_stream));
     }
+    WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[1], s));
     if ((rc = decoder_cross_kv(ctx, ws, B, s, &st->prof)) != WDR_OK) return rc;
+    WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[2], s));
     // ---- prompt + decoder state ----
     std::vector<int32_t> prompt;
     if (p.prompt_tokens && p.prompt_n_tokens > 0 && p.n_max_text_ctx > 0) {
@@ -270,20 +278,41 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         for (int i = 0; i < n_prompt; i++)
             if ((rc = decoder_step(ctx, ws, B, i, i == n_prompt - 1, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
         int32_t* done_host = fs.done_host;
+        // Greedy loop.  Iteration i = sample at position n_prompt-1+i, then the decoder step at n_prompt+i.  Unless per-kernel
+        // profiling is on, one iteration is a single CUDA-graph launch (the position lives in ws.pos_dev); the host looks at the
+        // finished-window counter every kDoneCheck iterations.
+        static const bool no_graph = getenv("WDR_NO_GRAPH") != nullptr;
+        const bool use_graph = !st->prof.enabled && !no_graph;
+        constexpr int kDoneCheck = 8;
+        cudaGraphExec_t graph = nullptr;
+        if (use_graph) {
+            if ((rc = decoder_decode_graph(ctx, ws, B, sp, s, &graph)) != WDR_OK) return rc;
+            const int32_t pos0 = n_prompt - 1;
+            WDR_CUDA_TRY(cudaMemcpyAsync(ws.pos_dev, &pos0, sizeof(int32_t), cudaMemcpyHostToDevice, s));
+            WDR_CUDA_TRY(cudaStreamSynchronize(s));  // pos0 is a stack variable
+        }
         for (int i = 0; i < n_max; i++) {
-            if ((rc = decoder_sample(ctx, ws, B, n_prompt - 1 + i, sp, s, &st->prof)) != WDR_OK) return rc;
+            const bool last = i == n_max - 1;
+            if (use_graph && !last) {
+                WDR_CUDA_TRY(cudaGraphLaunch(graph, s));
+                count_launch((uint64_t)ws.graph_nodes);
+            } else {
+                if ((rc = decoder_sample(ctx, ws, B, n_prompt - 1 + i, sp, s, &st->prof)) != WDR_OK) return rc;
+            }
             steps_run = i + 1;
-            if ((i & 3) == 3 || i == n_max - 1) {
+            if ((i % kDoneCheck) == kDoneCheck - 1 || last) {
                 WDR_CUDA_TRY(cudaMemcpyAsync(done_host, ws.done_count, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
                 WDR_CUDA_TRY(cudaStreamSynchronize(s));
                 if (*done_host + n_skip >= B) break;
                 if (p.abort_callback && p.abort_callback(p.abort_callback_user_data)) { set_error("aborted by callback"); return WDR_ERR_ABORTED; }
             }
-            if (i == n_max - 1) break;
-            if ((rc = decoder_step(ctx, ws, B, n_prompt + i, true, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
+            if (last) break;
+            if (!use_graph && (rc = decoder_step(ctx, ws, B, n_prompt + i, true, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
         }
     }
     fs.last_decode_steps = steps_run;
+    fs.decode_steps += steps_run;
+    WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[3], s));
     // ---- results to the host ----
     std::vector<wdr_token_data> toks((size_t)B * kDecMaxTokens);
     WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
@@ -379,8 +408,12 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_off, aw_off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_T, aw_T.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_A, aw_A.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
-        for (int i = 0; i < max_T; i++)
-            if ((rc = decoder_step(ctx, ws, B, i, false, DEC_MODE_DTW, s, &st->prof)) != WDR_OK) return rc;
+        static const bool stepwise = getenv("WDR_DTW_STEPWISE") != nullptr;  // bring-up aid: the one-token-per-launch pass
+        if (stepwise) {
+            for (int i = 0; i < max_T; i++)
+                if ((rc = decoder_step(ctx, ws, B, i, false, DEC_MODE_DTW, s, &st->prof)) != WDR_OK) return rc;
+        } else if ((rc = decoder_dtw_pass(ctx, ws, st->dtwp, B, aw_T.data(), s, &st->prof)) != WDR_OK) return rc;
+        WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[4], s));
         std::vector<DtwWindow> wins;
         std::vector<int> win_b;
         for (auto& pd : pend) {
@@ -434,48 +467,62 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             WDR_CUDA_TRY(cudaStreamSynchronize(s));
         }
     }
+    {   // phase times of this group (the stream is idle here: every branch above ended with a synchronize)
+        const bool dtw = !pend.empty();
+        if (!dtw) WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[4], s));
+        WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[5], s));
+        WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_phase[5]));
+        for (int i = 0; i < 5; i++) {
+            float t = 0.0f;
+            if (cudaEventElapsedTime(&t, fs.ev_phase[i], fs.ev_phase[i + 1]) == cudaSuccess) fs.phase_ms[i] += t;
+        }
+    }
     return WDR_OK;
 }
 
+// Shared progress accounting of one full call (lanes report under the mutex; the callback never runs concurrently).
+struct FullProgress {
+    std::mutex mu;
+    int done = 0, total = 0;
+    wdr_context* ctx = nullptr;
+    wdr_state* owner = nullptr;
+    void add(const wdr_full_params& p, int n) {
+        std::lock_guard<std::mutex> lk(mu);
+        done += n;
+        if (p.progress_callback && total > 0) p.progress_callback(ctx, owner, (int)(100ll * done / total), p.progress_callback_user_data);
+    }
+};
+
+// Chunks [c_begin, c_end) of the call on one lane (its own streams and workspaces), in groups of <= 128 windows.
 template <typename In>
-static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, const In* pcm, int64_t chunk_stride,
-                           const int32_t* n_valid, int n_chunks, bool pcm_on_device = false) {
-    clear_error();
-    WDR_REQUIRE(ctx && st && st->ctx == ctx && n_chunks >= 0, "bad arguments");
-    WDR_REQUIRE(n_chunks == 0 || (pcm && chunk_stride >= 0), "bad arguments");
-    int rc = ensure_device(ctx->device);
+static int full_range(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, int lang_id, const In* pcm, int64_t chunk_stride,
+                      const int32_t* n_valid, int c_begin, int c_end, bool pcm_on_device, FullProgress* prog) {
+    int rc = ensure_device(ctx->device);  // the current device is per host thread
     if (rc != WDR_OK) return rc;
-    int lang_id = 0;
-    if ((rc = validate_params(ctx, p, &lang_id)) != WDR_OK) return rc;
     st->results.clear();
     st->chunk_info.clear();
     st->lang_id = lang_id;
     FullScratch& fs = st->full;
+    for (auto& v : fs.phase_ms) v = 0.0;
+    fs.decode_steps = 0;
     if (!fs.ev_energy) {
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy_done, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_h2d, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.done_host), sizeof(int32_t)));
     }
-    for (int b = 0; b < n_chunks; b++) {
-        const int n = n_valid ? n_valid[b] : WDR_CHUNK_SAMPLES;
-        WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "each buffer must hold 0..480000 samples (longer audio: split into 30 s chunks)");
-    }
-    for (int c0 = 0; c0 < n_chunks; c0 += kDecMaxBatch) {
-        const int B = std::min(kDecMaxBatch, n_chunks - c0);
+    for (int c0 = c_begin; c0 < c_end; c0 += kDecMaxBatch) {
+        const int B = std::min(kDecMaxBatch, c_end - c0);
         if (pcm_on_device) {
-            WDR_REQUIRE(chunk_stride >= WDR_CHUNK_SAMPLES, "device PCM needs chunk_stride >= 480000");
             rc = full_group<In>(ctx, st, p, lang_id, pcm + (size_t)c0 * chunk_stride, chunk_stride, n_valid, c0, B);
             if (rc != WDR_OK) return rc;
-            if (p.progress_callback) p.progress_callback(ctx, st, (int)(100ll * (c0 + B) / n_chunks), p.progress_callback_user_data);
+            prog->add(p, B);
             continue;
         }
         // stage this group's PCM: rows of up to 480000 samples at a fixed device stride
-        size_t cap_bytes = fs.pcm_cap;
-        void* buf = fs.pcm_dev;
         const size_t need = (size_t)B * WDR_CHUNK_SAMPLES * sizeof(In);
-        if (need > cap_bytes) {
-            if (buf) cudaFree(buf);
+        if (need > fs.pcm_cap) {
+            if (fs.pcm_dev) cudaFree(fs.pcm_dev);
             fs.pcm_dev = nullptr; fs.pcm_cap = 0;
             WDR_CUDA_TRY(cudaMalloc(&fs.pcm_dev, need));
             fs.pcm_cap = need;
@@ -489,7 +536,80 @@ static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_param
         }
         rc = full_group<In>(ctx, st, p, lang_id, pcm_dev, WDR_CHUNK_SAMPLES, n_valid, c0, B);
         if (rc != WDR_OK) return rc;
-        if (p.progress_callback) p.progress_callback(ctx, st, (int)(100ll * (c0 + B) / n_chunks), p.progress_callback_user_data);
+        prog->add(p, B);
+    }
+    return WDR_OK;
+}
+
+// Lanes: the windows of one call are cut into contiguous ranges, each driven by its own host thread on its own streams and
+// workspaces.  A decode step is a chain of ~400 dependent, latency-bound kernels around one HBM-bound cross-attention per
+// layer; with several lanes in flight the SMs and HBM that one lane leaves idle between its dependent launches serve the
+// others (and one lane's tensor-bound encoder overlaps another's decode).  Windows are independent (sharded mode),
+// every kernel's result for a window is independent of which other windows share its launch, so the output is identical
+// for any lane count.
+static int default_lanes() {
+    static const int n = [] {
+        const char* e = getenv("WDR_LANES");
+        const int v = e ? atoi(e) : 3;
+        return v < 1 ? 1 : (v > 8 ? 8 : v);
+    }();
+    return n;
+}
+constexpr int kMinWindowsPerLane = 8;
+
+template <typename In>
+static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, const In* pcm, int64_t chunk_stride,
+                           const int32_t* n_valid, int n_chunks, bool pcm_on_device = false) {
+    clear_error();
+    WDR_REQUIRE(ctx && st && st->ctx == ctx && n_chunks >= 0, "bad arguments");
+    WDR_REQUIRE(n_chunks == 0 || (pcm && chunk_stride >= 0), "bad arguments");
+    int rc = ensure_device(ctx->device);
+    if (rc != WDR_OK) return rc;
+    int lang_id = 0;
+    if ((rc = validate_params(ctx, p, &lang_id)) != WDR_OK) return rc;
+    for (int b = 0; b < n_chunks; b++) {
+        const int n = n_valid ? n_valid[b] : WDR_CHUNK_SAMPLES;
+        WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "each buffer must hold 0..480000 samples (longer audio: split into 30 s chunks)");
+    }
+    if (pcm_on_device) WDR_REQUIRE(chunk_stride >= WDR_CHUNK_SAMPLES, "device PCM needs chunk_stride >= 480000");
+    FullProgress prog;
+    prog.total = n_chunks; prog.ctx = ctx; prog.owner = st;
+    const int want = st->n_lanes > 0 ? st->n_lanes : default_lanes();
+    const int G = std::max(1, std::min(want, n_chunks / kMinWindowsPerLane));
+    if (G == 1) return full_range<In>(ctx, st, p, lang_id, pcm, chunk_stride, n_valid, 0, n_chunks, pcm_on_device, &prog);
+    while ((int)st->lanes.size() < G - 1) {
+        wdr_state* ln = wdr_init_state(ctx);
+        if (!ln) return WDR_ERR_CUDA;
+        st->lanes.push_back(ln);
+    }
+    std::vector<int> bounds(G + 1);
+    for (int g = 0; g <= G; g++) bounds[g] = (int)((int64_t)n_chunks * g / G);
+    std::vector<int> rcs(G, WDR_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    auto run = [&](int g) {
+        wdr_state* ln = g == 0 ? st : st->lanes[g - 1];
+        ln->prof.enabled = st->prof.enabled;
+        clear_error();
+        rcs[g] = full_range<In>(ctx, ln, p, lang_id, pcm, chunk_stride, n_valid, bounds[g], bounds[g + 1], pcm_on_device, &prog);
+        if (rcs[g] != WDR_OK) errs[g] = wdr_last_error();
+    };
+    for (int g = 1; g < G; g++) th.emplace_back(run, g);
+    run(0);
+    for (auto& t : th) t.join();
+    for (int g = 0; g < G; g++)
+        if (rcs[g] != WDR_OK) {
+            st->results.clear();
+            st->chunk_info.clear();
+            set_error("%s", errs[g].c_str());
+            return rcs[g];
+        }
+    for (int g = 1; g < G; g++) {  // lane ranges are contiguous and ascending: appending keeps chunk order
+        wdr_state* ln = st->lanes[g - 1];
+        for (auto& r : ln->results) st->results.push_back(std::move(r));
+        st->chunk_info.insert(st->chunk_info.end(), ln->chunk_info.begin(), ln->chunk_info.end());
+        ln->results.clear();
+        ln->chunk_info.clear();
     }
     return WDR_OK;
 }
@@ -574,6 +694,18 @@ extern "C" wdr_token_data wdr_full_get_token_data_from_state(wdr_state* st, int 
     SEG_OR(z)
     if (j < 0 || j >= (int)seg.tokens.size()) { set_error("token index out of range"); return z; }
     return seg.tokens[j];
+}
+extern "C" int wdr_full_get_phase_ms(wdr_state* st, double* ms, int32_t* decode_steps) {
+    clear_error();
+    WDR_REQUIRE(st && ms, "bad arguments");
+    for (int i = 0; i < 5; i++) ms[i] = st->full.phase_ms[i];
+    int steps = st->full.decode_steps;
+    for (auto ln : st->lanes) {
+        for (int i = 0; i < 5; i++) ms[i] += ln->full.phase_ms[i];
+        steps += ln->full.decode_steps;
+    }
+    if (decode_steps) *decode_steps = steps;
+    return WDR_OK;
 }
 extern "C" int wdr_full_lang_id_from_state(wdr_state* st) { return st ? st->lang_id : -1; }
 extern "C" const char* wdr_lang_str(int id) { return (id >= 0 && id < 100) ? kLangs[id] : nullptr; }

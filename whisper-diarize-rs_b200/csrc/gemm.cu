@@ -38,6 +38,7 @@ struct GemmParams {
     int64_t c_batch_stride;
     const float* bias;
     const float* resid;
+    const __nv_bfloat16* resid_bf16;
     const float* pos;
     __nv_bfloat16* out_t;
     int64_t ldt;
@@ -257,7 +258,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32 + row) * p.ldc + n;
                             *reinterpret_cast<uint2*>(o) = whi;
                             *reinterpret_cast<uint2*>(o + p.split_stride) = wlo;
-                        } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16) {
+                        } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16 || EPI == EPI_BIAS_RELU_BF16 ||
+                                   EPI == EPI_BIAS_ADD_RELU_BF16) {
+                            if (EPI == EPI_BIAS_ADD_RELU_BF16) {
+                                const uint2 rr = *reinterpret_cast<const uint2*>(p.resid_bf16 + off);
+                                const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
+                                const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
+                                v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
+                            }
+                            if (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_ADD_RELU_BF16) {
+                                v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
+                            }
                             uint2 w;
                             w.x = pack_bf16(v.x, v.y);
                             w.y = pack_bf16(v.z, v.w);
@@ -405,6 +416,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.total_tiles = p.tiles_per_batch * d.n_batch * p.n_tiles * p.splits;
     p.out = d.out; p.ldc = d.ldc; p.bias = d.bias;
     p.c_batch_stride = d.c_batch_stride > 0 ? d.c_batch_stride : (int64_t)d.rows_per_batch * d.ldc; p.resid = d.resid; p.pos = d.pos;
+    p.resid_bf16 = d.resid_bf16;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     switch (d.epilogue) {
@@ -414,6 +426,8 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<128, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
         case EPI_QKV_BF16: return launch_gemm<128, 5, EPI_QKV_BF16>(ta, tb, p, st);
         case EPI_BIAS_GELU_SPLIT: return launch_gemm<64, 4, EPI_BIAS_GELU_SPLIT, true>(ta, tb, p, st);
+        case EPI_BIAS_RELU_BF16: return launch_gemm<128, 5, EPI_BIAS_RELU_BF16>(ta, tb, p, st);
+        case EPI_BIAS_ADD_RELU_BF16: WDR_REQUIRE(d.resid_bf16, "resid_bf16 missing"); return launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16>(ta, tb, p, st);
         case EPI_F32:
             if (d.dual_a) return launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st);
             return BN == 64 ? launch_gemm<64, 7, EPI_F32>(ta, tb, p, st) : launch_gemm<128, 5, EPI_F32>(ta, tb, p, st);

@@ -14,6 +14,8 @@ enum GemmEpilogue {
     EPI_QKV_BF16 = 4,           // n < n_split: out_bf16[row][n] = acc + bias;  n >= n_split: out_t[n - n_split][row] = acc + bias
     EPI_F32 = 5,                // out_f32 = acc + bias
     EPI_BIAS_GELU_SPLIT = 6,    // v = gelu_exact(acc + bias) stored as a (hi, lo) bf16 pair: out[.] = hi, out[. + split_stride] = lo (decoder fc1)
+    EPI_BIAS_RELU_BF16 = 7,     // out_bf16 = relu(acc + bias)                                  (ResNet34 conv + folded BN + ReLU)
+    EPI_BIAS_ADD_RELU_BF16 = 8, // out_bf16 = relu(acc + bias + resid_bf16[row][n])             (BasicBlock tail; resid_bf16 has the output's layout)
 };
 
 // D[M x N] = A[M x K] * W[N x K]^T.  A rows are organised as n_batch groups of rows_per_batch rows (row r of
@@ -39,6 +41,7 @@ struct GemmDesc {
     int64_t c_batch_stride = 0;  // elements between batches of the output (and resid); 0 = rows_per_batch * ldc
     const float* bias = nullptr;   // [N] or null
     const float* resid = nullptr;  // fp32 [M][ldc]
+    const __nv_bfloat16* resid_bf16 = nullptr;  // bf16 [M][ldc] (EPI_BIAS_ADD_RELU_BF16)
     const float* pos = nullptr;    // fp32 [rows_per_batch][N]
     __nv_bfloat16* out_t = nullptr;
     int64_t ldt = 0;

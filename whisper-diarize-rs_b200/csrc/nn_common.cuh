@@ -59,7 +59,7 @@ struct NnAllocs {
 enum { NN_ACT_NONE = 0, NN_ACT_LEAKY = 1, NN_ACT_RELU = 2 };
 
 // C[M][N] = act(A[M][K] * B[N][K]^T + bias[N]);  64 x 64 tile, 256 threads, 4 x 4 outputs per thread, K step 16.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 sgemm_nt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, const float* __restrict__ bias,
                 float* __restrict__ C, int ldc, int M, int N, int K, int act) {
     __shared__ float sA[16][64 + 4];
@@ -121,7 +121,7 @@ __device__ __forceinline__ float nn_sigmoid(float x) { return 1.0f / (1.0f + exp
 // One LSTM direction over one sequence per CTA (grid = (n_seq, n_dir)), hidden 128, 512 threads (thread r = gate row r,
 // PyTorch order i|f|g|o).  gates_in[(seq*T + t) * ld_g + dir*512 + r] = W_ih x_t + b_ih + b_hh (precomputed by an SGEMM);
 // out[(seq*T + t) * ld_o + dir*128 + j] = h_t[j].  dir 1 walks t = T-1 .. 0.
-__global__ void __launch_bounds__(512, 1)
+static __global__ void __launch_bounds__(512, 1)
 lstm_dir_kernel(const float* __restrict__ gates_in, int ld_g, const float* __restrict__ whh /* [n_dir][512][128] */, int T,
                 float* __restrict__ out, int ld_o) {
     __shared__ float h[128];

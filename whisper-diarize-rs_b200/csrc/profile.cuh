@@ -5,7 +5,7 @@
 
 namespace wdr {
 
-enum KernelClass { KC_MEL = 0, KC_MEL_AUX, KC_GEMM, KC_ATTENTION, KC_LAYERNORM, KC_DECODER, KC_DTW, KC_OTHER, KC_DEC_CROSS, KC_DEC_GEMM, KC_COUNT };
+enum KernelClass { KC_MEL = 0, KC_MEL_AUX, KC_GEMM, KC_ATTENTION, KC_LAYERNORM, KC_DECODER, KC_DTW, KC_OTHER, KC_DEC_CROSS, KC_DEC_GEMM, KC_DEC_CROSS_BATCHED, KC_COUNT };
 
 struct Profiler {
     bool enabled = false;

@@ -60,10 +60,13 @@ extern "C" wdr_state* wdr_init_state(wdr_context* ctx) {
 
 extern "C" void wdr_free_state(wdr_state* s) {
     if (!s) return;
+    for (auto ln : s->lanes) wdr_free_state(ln);
+    s->lanes.clear();
     cudaSetDevice(s->ctx->device);
     cudaDeviceSynchronize();
     s->enc.release();
     s->dec.release();
+    s->dtwp.release();
     s->full.release();
     cudaFree(s->pcm_dev);
     cudaFree(s->nvalid_dev);
@@ -180,6 +183,7 @@ extern "C" int wdr_profile_enable(wdr_state* st, int enable) {
     clear_error();
     WDR_REQUIRE(st, "null state");
     st->prof.enabled = enable != 0;
+    for (auto ln : st->lanes) ln->prof.enabled = st->prof.enabled;
     return WDR_OK;
 }
 
@@ -188,5 +192,13 @@ extern "C" int wdr_profile_collect(wdr_state* st, double* ms, int32_t* launches,
     WDR_REQUIRE(st && ms && launches && n_classes >= KC_COUNT, "need room for all kernel classes");
     for (int i = 0; i < n_classes; i++) { ms[i] = 0.0; launches[i] = 0; }
     st->prof.collect(ms, launches);
+    for (auto ln : st->lanes) ln->prof.collect(ms, launches);  // lanes overlap: class sums can exceed the wall time of the call
     return KC_COUNT;
+}
+
+extern "C" int wdr_state_set_lanes(wdr_state* st, int n_lanes) {
+    clear_error();
+    WDR_REQUIRE(st && n_lanes >= 0 && n_lanes <= 8, "lanes must be 0 (default) .. 8");
+    st->n_lanes = n_lanes;
+    return WDR_OK;
 }

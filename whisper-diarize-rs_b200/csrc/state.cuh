@@ -40,6 +40,10 @@ struct FullScratch {
     int32_t* dtw_path = nullptr;
     size_t dtw_path_cap = 0;
     int last_decode_steps = 0;
+    // phase boundaries of the last group on the compute stream: start | encoder | cross-KV | greedy decode | DTW pass | DTW
+    cudaEvent_t ev_phase[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double phase_ms[5] = {0, 0, 0, 0, 0};  // accumulated over the groups of the last full call
+    int decode_steps = 0;                  // greedy iterations of the last full call (summed over groups)
     void release() {
         cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path);
         if (energy_host) cudaFreeHost(energy_host);
@@ -47,6 +51,7 @@ struct FullScratch {
         if (ev_energy) cudaEventDestroy(ev_energy);
         if (ev_energy_done) cudaEventDestroy(ev_energy_done);
         if (ev_h2d) cudaEventDestroy(ev_h2d);
+        for (auto e : ev_phase) if (e) cudaEventDestroy(e);
         *this = FullScratch();
     }
 };
@@ -58,11 +63,15 @@ struct wdr_state {
     cudaStream_t copy_stream = nullptr;  // H2D staging, overlapped with compute group by group
     wdr::EncoderWorkspace enc;
     wdr::DecoderWorkspace dec;
+    wdr::DtwPassWorkspace dtwp;
     wdr::FullScratch full;
     std::vector<wdr::ResultSegment> results;  // segments of the last full call, chunk order
     std::vector<wdr::ChunkInfo> chunk_info;
     int lang_id = 0;
     wdr::Profiler prof;
+    // extra lanes of the full pipeline (full.cu): child states with their own streams / workspaces; lane 0 is this state
+    std::vector<wdr_state*> lanes;
+    int n_lanes = 0;  // 0 = library default (WDR_LANES, else 3)
     // device-resident staging / results of the last encode call
     int16_t* pcm_dev = nullptr;
     size_t pcm_cap = 0;
