@@ -9,6 +9,8 @@ Workloads:
                                    audio = 120 x 30 s windows PER GPU, sharded by window (no data-path collective, weak scaling):
                                    log-mel -> encoder -> cross-KV -> greedy decode -> token timestamps -> DTW, through wdr_full_batch_*.
   --workload encoder               BASELINE.json configs[1]: tiny.en batched log-mel + encoder over 64 x 30 s windows on one GPU.
+  --workload diarize               BASELINE.json configs[3]: segmentation-3.0 windows + WeSpeaker ResNet34 embeddings + cosine matrix +
+                                   clustering on a 10 min 4-speaker synthetic mix per GPU (one recording per rank).
 
 One JSON line on stdout (rank 0).  `value` = whole-job RTFx with the PCM already resident in HBM (wdr_full_batch_i16_dev); `e2e` =
 the same through the host-pointer C ABI call (pinned host PCM -> H2D -> ... -> results read back through the whisper.h-style
@@ -133,6 +135,160 @@ class CpuPort:
         return n_chunks * 30.0 / dt, dt, n_tok
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# diarization workload (BASELINE configs[3])
+# ---------------------------------------------------------------------------------------------------------------------
+def diar_cpu(pcm, n_windows, n_segments):
+    """Oracle port of the diarization path on a bounded sample: n_windows segmentation windows + n_segments embeddings (of the
+    segments the library found) + clustering.  Returns (seconds_seg_per_window, seconds_emb_per_frame)."""
+    from oracle import native, pyannet, resnet
+    native.build()
+    wseg = pyannet.pyannet_weights(1234)
+    wres = resnet.resnet_weights(1234)
+    t0 = time.perf_counter()
+    for i in range(n_windows):
+        pyannet.pyannet_forward(pcm[i * 160000:(i + 1) * 160000].astype(np.float32), wseg)
+    t_seg = (time.perf_counter() - t0) / max(n_windows, 1)
+    frames = 0
+    t0 = time.perf_counter()
+    for i in range(n_segments):
+        seg = pcm[i * 48000:(i + 1) * 48000]
+        resnet.compute(seg, wres, native.kaldi_fbank)
+        frames += 1 + (len(seg) - 400) // 160
+    t_emb = (time.perf_counter() - t0) / max(frames, 1)
+    return t_seg, t_emb
+
+
+def run_diarize(args):
+    """One step = one 10 min recording: pyannote_rs::get_segments -> EmbeddingExtractor::compute per segment -> cosine matrix ->
+    leader scan (the crate's EmbeddingManager policy) + agglomerative labels.  value: PCM already in HBM, stage calls through the
+    device-pointer C ABI; e2e: host PCM through whisper-diarize-rs_b200.host.diarize (the crate-shaped call)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import synth_audio
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    seconds = 600.0
+    pcm = synth_audio(4001 + rank, seconds, n_speakers=4)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count()
+        n_w, n_s = 2, 4
+        t0 = time.perf_counter()
+        steps = max(1, min(args.steps, 3))
+        for _ in range(steps):
+            t_seg, t_emb = diar_cpu(pcm, n_w, n_s)
+        dt = (time.perf_counter() - t0) / steps
+        audio_s = n_w * 10.0
+        val = audio_s / dt
+        line = {"impl": "reference", "metric": "RTFx diarization", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "diarization of a 10 min 4-speaker synthetic mix (BASELINE configs[3])"},
+                "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n_w} segmentation windows (20 s of audio) + {n_s} x 3 s segment embeddings per step, oracle/pyannet.py + oracle/resnet.py"},
+                "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import wdr_b200 as w
+    from wdr_b200 import host as H
+    if w.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: libwdr_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    seg = w.Segmenter(seed=1234, device=local)
+    emb = w.EmbeddingExtractor(seed=1234, device=local)
+    pcm_pin = torch.from_numpy(pcm).pin_memory()
+    out = {}
+
+    def step():
+        out["r"] = H.diarize(seg, emb, pcm_pin.numpy(), 0.5, w.SIZE_MAX, "leader")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = w.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = w.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # stage timings of one more step (host wall clock around each blocking C-ABI call)
+    stages = {}
+    t = time.perf_counter(); segs = seg.get_segments(pcm); stages["segmentation_ms"] = (time.perf_counter() - t) * 1e3
+    off = np.zeros(len(segs) + 1, np.int64)
+    for i, sgm in enumerate(segs):
+        off[i + 1] = off[i] + len(sgm["samples"])
+    cat = np.concatenate([sgm["samples"] for sgm in segs]).astype(np.int16) if len(segs) else np.zeros(0, np.int16)
+    t = time.perf_counter(); E, status = emb.compute_batch(cat, off); stages["embedding_ms"] = (time.perf_counter() - t) * 1e3
+    flops = emb.last_flops()
+    ok = np.flatnonzero(status == 0)
+    if not len(ok):
+        raise SystemExit("diarize workload: the segmenter emitted no embeddable segment")
+    t = time.perf_counter(); S = w.cosine_matrix(E[ok]); lab = w.cluster_leader(S, 0.5); agg = w.cluster_agglomerative(S, 0.5)
+    stages["cosine_cluster_ms"] = (time.perf_counter() - t) * 1e3
+    if world > 1:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    value = world * seconds * args.steps / dt
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        ach = flops / (stages["embedding_ms"] / 1e3) / 1e12 if stages["embedding_ms"] > 0 else 0.0
+        line = {"metric": "RTFx diarization", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16/f32", "data": "synthetic",
+                "config": {"workload": "diarization of a 10 min 4-speaker synthetic mix per GPU: segmentation-3.0 windows (fp32) + WeSpeaker ResNet34 "
+                                       "embeddings (bf16 tcgen05 GEMMs) + cosine matrix + leader scan (BASELINE configs[3])",
+                           "windows": int(w.load().wdr_seg_n_windows(len(pcm))), "segments": len(segs), "embedded": int(len(ok)),
+                           "speakers_leader": int(lab.max()) if len(lab) else 0, "clusters_agglomerative": int(agg.max()) if len(agg) else 0,
+                           "l2": "each step streams the whole recording's activations (> 126 MB L2)"},
+                "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm.nbytes + cat.nbytes), "d2h_bytes_per_step": int(E.nbytes + 60 * 589 * 7 * 4),
+                        "api": "host.diarize: wdr_seg_get_segments + wdr_emb_compute_batch_i16 + wdr_cosine_matrix + wdr_cluster_leader (host pointers)"},
+                "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
+                "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05) in the ResNet34 embedding stage (whole stage incl. fbank, im2col, H2D/D2H)",
+                             "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                             "algorithmic_gflop_per_step": flops / 1e9}}
+        if not args.no_cpu_baseline:
+            t_seg, t_emb = diar_cpu(pcm, 2, 4)
+            frames = sum(1 + (int(off[i + 1] - off[i]) - 400) // 160 for i in ok)
+            est = 60 * t_seg + frames * t_emb
+            line["cpu_baseline"] = {"value": seconds / est, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"2 of 60 segmentation windows ({t_seg:.2f} s each) + 4 x 3 s embeddings ({t_emb * 1e3:.2f} ms per fbank frame), "
+                                              f"extrapolated to the recording's 60 windows and {frames} frames; oracle/pyannet.py (numpy) + oracle/resnet.py (torch CPU)"}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+    seg.close()
+    emb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def metric_name(workload):
     return "RTFx full transcribe+DTW" if workload == "transcribe" else "RTFx mel+encoder"
 
@@ -178,7 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="transcribe", choices=["transcribe", "encoder"])
+    ap.add_argument("--workload", default="transcribe", choices=["transcribe", "encoder", "diarize"])
     ap.add_argument("--arch", default=None)
     ap.add_argument("--chunks", type=int, default=None, help="30 s windows per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -188,8 +344,12 @@ def main():
     if args.chunks is None:
         args.chunks = 120 if args.workload == "transcribe" else 64
     if args.steps is None:
-        args.steps = 5 if args.workload == "transcribe" else 40
+        args.steps = 5 if args.workload == "transcribe" else 40 if args.workload == "encoder" else 10
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.workload == "diarize":
+        if args.steps is None or args.steps > 40:
+            args.steps = 10
+        return run_diarize(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -375,7 +535,7 @@ def main():
                                 "wdr_encode_chunks_i16 (pinned host PCM; result stays in the state) + wdr_state_hidden_digest"), **check},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kern,
                 "kernel_ms_sum_per_step": total_ms / args.steps, "profiled_pass_ms_per_step": ms_profiled / args.steps,
-                "lanes": int(os.environ.get("WDR_LANES", "3")) if full else 1, "phases_ms_last_step": phases,
+                "lanes": int(os.environ.get("WDR_LANES", "1")) if full else 1, "phases_ms_last_step": phases,
                 "encoder_tflops_overall": None if full else fl["total_enc"] * B * args.steps / (ms / 1e3) / 1e12}
         if not args.no_cpu_baseline:
             cores = os.cpu_count()

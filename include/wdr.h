@@ -193,7 +193,7 @@ int wdr_profile_enable(wdr_state* state, int enable);
 int wdr_profile_collect(wdr_state* state, double* ms, int32_t* launches, int n_classes);
 /* B200 extension (no whisper.h equivalent): how many lanes wdr_full_batch_* cuts its windows into.  Each lane is a host thread
  * with its own streams and workspaces, so one lane's latency-bound decode chain overlaps another's HBM-bound cross-attention and
- * tensor-bound encoder.  0 = default (environment WDR_LANES, else 3); results do not depend on the lane count. */
+ * tensor-bound encoder.  0 = default (environment WDR_LANES, else 1); results do not depend on the lane count. */
 int wdr_state_set_lanes(wdr_state* state, int n_lanes);
 /* Encoder self-attention alone: qk bf16 [B*T][2d] (query | key), vt bf16 [d][ldt] = V transposed, window b's tokens at
  * columns b*round_up(T,8) + t (pad columns zero) -> out bf16 [B*T][d].  DEVICE pointers. */

@@ -32,20 +32,24 @@ def pyannet_weights(seed=1234):
             t(f"conv{i}.bias", (co,), 0.0, s)  # the sinc filterbank (conv0) has no bias
         t(f"norm{i}.weight", (co,), 1.0, 0.1)
         t(f"norm{i}.bias", (co,), 0.0, 0.1)
+    # Recurrent / head matrices 2.5x / 2x / 6x wider than PyTorch's default init and +1.5 bias on the "no speaker" class: with
+    # default-init scales a random PyanNet is constant in time and the state machine never emits a segment (csrc/segmentation.cu
+    # uses the same constants).
     s = 1.0 / np.sqrt(128)
     for l in range(4):
         n_in = 60 if l == 0 else 256
         for d in ("", "_reverse"):
-            t(f"lstm.weight_ih_l{l}{d}", (512, n_in), 0.0, s)
-            t(f"lstm.weight_hh_l{l}{d}", (512, 128), 0.0, s)
+            t(f"lstm.weight_ih_l{l}{d}", (512, n_in), 0.0, 2.5 / np.sqrt(128))
+            t(f"lstm.weight_hh_l{l}{d}", (512, 128), 0.0, 2.5 / np.sqrt(128))
             t(f"lstm.bias_ih_l{l}{d}", (512,), 0.0, s)
             t(f"lstm.bias_hh_l{l}{d}", (512,), 0.0, s)
-    t("linear0.weight", (128, 256), 0.0, 1.0 / 16)
+    t("linear0.weight", (128, 256), 0.0, 2.0 / 16)
     t("linear0.bias", (128,), 0.0, 1.0 / 16)
-    t("linear1.weight", (128, 128), 0.0, s)
+    t("linear1.weight", (128, 128), 0.0, 2.0 / np.sqrt(128))
     t("linear1.bias", (128,), 0.0, s)
-    t("classifier.weight", (7, 128), 0.0, s * 4)
+    t("classifier.weight", (7, 128), 0.0, 24.0 / np.sqrt(128))
     t("classifier.bias", (7,), 0.0, 0.5)
+    w["classifier.bias"][0] += np.float32(1.5)
     return w
 
 

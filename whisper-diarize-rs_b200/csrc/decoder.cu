@@ -85,8 +85,15 @@ __device__ __forceinline__ void store_split(__nv_bfloat16* __restrict__ dst, int
 
 // sum of the split-K partials of element (row, col), in split order
 __device__ __forceinline__ float part_sum(const float* __restrict__ part, int n_splits, int64_t split_stride, int64_t idx) {
-    float a = part[idx];
-    for (int s = 1; s < n_splits; s++) a += part[(int64_t)s * split_stride + idx];
+    const float* pp = part + idx;
+    float a = pp[0];
+    int s = 1;
+    for (; s + 4 <= n_splits; s += 4) {  // four loads in flight, summed in split order
+        const float t0 = pp[(int64_t)s * split_stride], t1 = pp[(int64_t)(s + 1) * split_stride];
+        const float t2 = pp[(int64_t)(s + 2) * split_stride], t3 = pp[(int64_t)(s + 3) * split_stride];
+        a += t0; a += t1; a += t2; a += t3;
+    }
+    for (; s < n_splits; s++) a += pp[(int64_t)s * split_stride];
     return a;
 }
 
@@ -121,7 +128,15 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
     if (part) {
         const float* pp = part + (int64_t)row * ldp + i;
         float4 acc = *reinterpret_cast<const float4*>(pp);
-        for (int s = 1; s < n_splits; s++) {
+        int s = 1;
+        for (; s + 4 <= n_splits; s += 4) {  // four loads in flight, summed in split order
+            float4 t[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) t[k] = *reinterpret_cast<const float4*>(pp + (int64_t)(s + k) * split_stride);
+#pragma unroll
+            for (int k = 0; k < 4; k++) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+        }
+        for (; s < n_splits; s++) {
             const float4 t = *reinterpret_cast<const float4*>(pp + (int64_t)s * split_stride);
             acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         }
@@ -141,62 +156,87 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
     store_split(h, lo_off, o + 3, c3 * rstd * gg.w + bb.w);
 }
 
-// self-attention of one (head, window) at position pos.  part: [S][B][3d] partials of the fused QKV GEMM.
-__global__ void __launch_bounds__(128)
+// self-attention at position pos: one WARP per (head, window), blockDim.x / 32 heads per CTA — no block-wide barrier anywhere.
+// part: [S][B][3d] partials of the fused QKV GEMM.  Scores: lane = key position (its 256 B K row against q broadcast from shared
+// memory); softmax by warp shuffles; P V: lane = two columns, V rows stream coalesced, 8 positions in flight per warp.
+constexpr int kSelfMaxHeadsPerCta = 5;
+__global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */) {
-    __shared__ float q[64];
-    __shared__ float p[kDecSeqCap];
-    __shared__ float red[32];
-    __shared__ float acc2[2][64];
-    const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    __shared__ __align__(16) float qs[kSelfMaxHeadsPerCta][64];
+    __shared__ float ps[kSelfMaxHeadsPerCta][kDecSeqCap];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hh = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
     pos = load_pos(pos_ptr, pos);
     if (win && (win[b].completed | win[b].failed)) return;
     if (t_limit && pos >= t_limit[b]) return;
     float* K = sk + (int64_t)b * kDecSeqCap * d + hh * 64;
     float* V = sv + (int64_t)b * kDecSeqCap * d + hh * 64;
-    if (tid < 64) {
-        const int64_t base = (int64_t)b * 3 * d + hh * 64 + tid;
-        q[tid] = part_sum(part, n_splits, split_stride, base) + b_qkv[hh * 64 + tid];
-        const float kv = part_sum(part, n_splits, split_stride, base + d) + b_qkv[d + hh * 64 + tid];
-        const float vv = part_sum(part, n_splits, split_stride, base + 2 * d) + b_qkv[2 * d + hh * 64 + tid];
-        K[(int64_t)pos * d + tid] = kv;
-        V[(int64_t)pos * d + tid] = vv;
+    float* q = qs[warp];
+    float* p = ps[warp];
+#pragma unroll
+    for (int e = lane; e < 64; e += 32) {
+        const int64_t base = (int64_t)b * 3 * d + hh * 64 + e;
+        q[e] = part_sum(part, n_splits, split_stride, base) + b_qkv[hh * 64 + e];
+        K[(int64_t)pos * d + e] = part_sum(part, n_splits, split_stride, base + d) + b_qkv[d + hh * 64 + e];
+        V[(int64_t)pos * d + e] = part_sum(part, n_splits, split_stride, base + 2 * d) + b_qkv[2 * d + hh * 64 + e];
     }
-    __syncthreads();
+    __syncwarp();
     float mx = -INFINITY;
-    for (int t = tid; t <= pos; t += 128) {
+    for (int t = lane; t <= pos; t += 32) {
         const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)t * d);
+        const float4* qv = reinterpret_cast<const float4*>(q);
+        float4 f[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 16; c4++) f[c4] = kr[c4];
         float a = 0.0f;
 #pragma unroll
         for (int c4 = 0; c4 < 16; c4++) {
-            const float4 f = kr[c4];
-            a = fmaf(q[c4 * 4], f.x, a);
-            a = fmaf(q[c4 * 4 + 1], f.y, a);
-            a = fmaf(q[c4 * 4 + 2], f.z, a);
-            a = fmaf(q[c4 * 4 + 3], f.w, a);
+            const float4 qq = qv[c4];
+            a = fmaf(qq.x, f[c4].x, a);
+            a = fmaf(qq.y, f[c4].y, a);
+            a = fmaf(qq.z, f[c4].z, a);
+            a = fmaf(qq.w, f[c4].w, a);
         }
         a *= 0.125f;
         p[t] = a;
         mx = fmaxf(mx, a);
     }
-    mx = block_max(mx, red);
+    mx = warp_max(mx);
     float sum = 0.0f;
-    for (int t = tid; t <= pos; t += 128) {
+    for (int t = lane; t <= pos; t += 32) {
         const float e = expf(p[t] - mx);
         p[t] = e;
         sum += e;
     }
-    sum = block_sum(sum, red);
+    sum = warp_sum(sum);
     const float inv = 1.0f / sum;
-    __syncthreads();
-    const int c = tid & 63, half = tid >> 6;
-    float a = 0.0f;
-    for (int t = half; t <= pos; t += 2) a = fmaf(p[t] * inv, V[(int64_t)t * d + c], a);
-    acc2[half][c] = a;
-    __syncthreads();
-    if (tid < 64) store_split(att, lo_off, (int64_t)b * d + hh * 64 + tid, acc2[0][tid] + acc2[1][tid]);
+    __syncwarp();
+    float a0 = 0.0f, a1 = 0.0f;
+    const float* vc = V + lane;
+    int t = 0;
+    for (; t + 8 <= pos + 1; t += 8) {
+        float v0[8], v1[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            v0[k] = vc[(int64_t)(t + k) * d];
+            v1[k] = vc[(int64_t)(t + k) * d + 32];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const float pt = p[t + k] * inv;
+            a0 = fmaf(pt, v0[k], a0);
+            a1 = fmaf(pt, v1[k], a1);
+        }
+    }
+    for (; t <= pos; t++) {
+        const float pt = p[t] * inv;
+        a0 = fmaf(pt, vc[(int64_t)t * d], a0);
+        a1 = fmaf(pt, vc[(int64_t)t * d + 32], a1);
+    }
+    store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane, a0);
+    store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane + 32, a1);
 }
 
 // cross-attention of one (head, window): q from the cross-query GEMM partials; K_c/V_c rows are 64 bf16 (128 B) at row
@@ -739,17 +779,28 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
     return WDR_OK;
 }
 
-// splits so that tiles * splits covers the SMs, every split owning the same number (>= 1) of 64-wide k-blocks
-static int pick_split(int K, int N) {
-    const int num_kb = (K + 63) / 64, tiles = (N + 63) / 64;
-    int want = (148 + tiles - 1) / tiles;
-    if (want > 16) want = 16;
-    if (want > num_kb) want = num_kb;
-    for (int s = want; s >= 1; s--) {
-        const int per = (num_kb + s - 1) / s;
-        if ((num_kb + per - 1) / per == s) return s;
+// Tile width and split-K factor of a weight-streaming GEMM (M = one 128-row tile).  Every work item loads its K-slice of the
+// (hi, lo) activations (512 B per k), its weight tile (2*bn B per k) and writes a 128 x bn fp32 partial; measured on B200
+// (ncu, in-graph): item time ~ fixed + bytes / ~100 GB/s per SM, and a second wave costs a whole item time again.  So: one wave
+// (items <= SMs), the smallest per-item byte count, a small penalty per split for the consumer's partial-sum reads.
+static void pick_tile(int K, int N, int* bn_out, int* splits_out) {
+    const int num_kb = (K + 63) / 64, sms = 148;
+    double best = 1e30;
+    int best_bn = 64, best_s = 1;
+    for (int bn : {64, 128}) {
+        const int tiles = (N + bn - 1) / bn;
+        for (int s = 1; s <= 16 && s <= num_kb; s++) {
+            const int per = (num_kb + s - 1) / s;
+            if ((num_kb + per - 1) / per != s) continue;  // every split must own >= 1 k-block
+            const int items = tiles * s, waves = (items + sms - 1) / sms;
+            const double ks = per * 64.0;
+            const double kb = (512.0 * ks + 2.0 * bn * ks + 512.0 * bn) / 1024.0;
+            const double cost = waves * (300.0 + kb) + 12.0 * s;
+            if (cost < best) { best = cost; best_bn = bn; best_s = s; }
+        }
     }
-    return 1;
+    *bn_out = best_bn;
+    *splits_out = best_s;
 }
 
 struct SkinnyGemm {
@@ -763,9 +814,9 @@ static int skinny_gemm(const __nv_bfloat16* A, int B, const __nv_bfloat16* W, in
     GemmDesc g;
     g.A = A; g.a_row_stride = K; g.rows_per_batch = B; g.n_batch = 1;
     g.W = W; g.ldw = K; g.N = N; g.K = K;
-    g.epilogue = EPI_F32; g.out = ws.part; g.ldc = N; g.bn = 64;
+    g.epilogue = EPI_F32; g.out = ws.part; g.ldc = N;
     g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * K;
-    g.split_k = pick_split(K, N);
+    pick_tile(K, N, &g.bn, &g.split_k);
     g.split_stride = (int64_t)B * N;
     if ((size_t)g.split_k * B * N > ws.part_elems) { set_error("decoder: split-K workspace too small"); return WDR_ERR_INVALID; }
     out->splits = g.split_k;
@@ -812,7 +863,9 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         if ((rc = skinny_gemm(ws.h, B, e.w_qkv, 3 * d, d, ws, &sg, st, prof)) != WDR_OK) return rc;
         {
             ProfScope ps(prof, KC_DECODER, st);
-            dec_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_qkv,
+            int hpc = kSelfMaxHeadsPerCta;
+            while (H % hpc) hpc--;
+            dec_self_attn_kernel<<<dim3(H / hpc, B), hpc * 32, 0, st>>>(ws.part, sg.splits, sg.split_stride, e.b_qkv,
                                                                ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att,
                                                                (int64_t)ws.cap_B * d, win, t_limit);
             WDR_LAUNCH_CHECK();
@@ -885,7 +938,7 @@ static int packed_gemm(const __nv_bfloat16* A, int64_t M, int64_t M_cap, const _
     GemmDesc g;
     g.A = A; g.a_row_stride = K; g.rows_per_batch = (int)M; g.n_batch = 1;
     g.W = W; g.ldw = K; g.N = N; g.K = K;
-    g.epilogue = EPI_F32; g.out = out; g.ldc = N; g.bn = 64;
+    g.epilogue = EPI_F32; g.out = out; g.ldc = N; g.bn = 128;
     g.dual_a = true; g.a_dual_stride = M_cap * K;
     ProfScope ps(prof, KC_DEC_GEMM, st);
     return gemm_bf16(g, st);

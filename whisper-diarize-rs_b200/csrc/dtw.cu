@@ -276,7 +276,7 @@ static int g_dtw_smem_max = -1;
 // A window keeps its packed trace in shared memory when diagonals + trace words fit (tr_off = -1),
 // otherwise in a global scratch at tr_off.
 int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int32_t* time_idx, int32_t* path_len,
-            int max_path, float* cost_out, int32_t* trace_out, cudaStream_t st) {
+            int max_path, float* cost_out, int32_t* trace_out, cudaStream_t st, void* wins_scratch_dev) {
     const int n = (int)wins.size();
     if (n == 0) return WDR_OK;
     if (g_dtw_smem_max < 0) {
@@ -315,7 +315,8 @@ int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int
     }
     DtwWindow* d_wins = nullptr;
     uint32_t* d_tr = nullptr;
-    WDR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_wins), sizeof(DtwWindow) * n, st));
+    if (wins_scratch_dev) d_wins = reinterpret_cast<DtwWindow*>(wins_scratch_dev);  // caller-owned, >= n entries
+    else WDR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_wins), sizeof(DtwWindow) * n, st));
     WDR_CUDA_TRY(cudaMemcpyAsync(d_wins, wins.data(), sizeof(DtwWindow) * n, cudaMemcpyHostToDevice, st));
     if (global_words) WDR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_tr), sizeof(uint32_t) * global_words, st));
     int threads = ((maxN + 31) / 32) * 32;
@@ -325,7 +326,7 @@ int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int
                                                           trace_out);
     WDR_LAUNCH_CHECK();
     // wins.data() was read by an async copy from pageable memory: the runtime stages it before returning.
-    WDR_CUDA_TRY(cudaFreeAsync(d_wins, st));
+    if (!wins_scratch_dev) WDR_CUDA_TRY(cudaFreeAsync(d_wins, st));
     if (d_tr) WDR_CUDA_TRY(cudaFreeAsync(d_tr, st));
     return WDR_OK;
 }
@@ -417,7 +418,7 @@ extern "C" int wdr_dtw(const float* x, int N, int M, int32_t* text_idx, int32_t*
     WDR_CUDA_TRY(cudaMemcpy(d_x.p, x, sizeof(float) * (size_t)N * M, cudaMemcpyHostToDevice));
     std::vector<DtwWindow> wins(1);
     wins[0].x_off = 0; wins[0].N = N; wins[0].M = M; wins[0].tr_off = 0;
-    rc = dtw_run(d_x.p, wins, d_ti.p, d_tj.p, d_len.p, max_path, cost_out ? d_cost.p : nullptr, cost_out ? d_trace.p : nullptr, 0);
+    rc = dtw_run(d_x.p, wins, d_ti.p, d_tj.p, d_len.p, max_path, cost_out ? d_cost.p : nullptr, cost_out ? d_trace.p : nullptr, 0, nullptr);
     if (rc != WDR_OK) return rc;
     int32_t L = 0;
     WDR_CUDA_TRY(cudaMemcpy(&L, d_len.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
@@ -445,5 +446,5 @@ extern "C" int wdr_dtw_batch_dev(const float* x, const int64_t* x_offset, const 
         WDR_REQUIRE(N[b] >= 0 && M[b] >= 0 && N[b] + M[b] <= max_path, "window does not fit max_path");
         wins[b].x_off = x_offset[b]; wins[b].N = N[b]; wins[b].M = M[b]; wins[b].tr_off = 0;
     }
-    return dtw_run(x, wins, text_idx, time_idx, path_len, max_path, nullptr, nullptr, (cudaStream_t)stream);
+    return dtw_run(x, wins, text_idx, time_idx, path_len, max_path, nullptr, nullptr, (cudaStream_t)stream, nullptr);
 }

@@ -9,10 +9,13 @@
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+#include <cuda_profiler_api.h>
 #include "common.cuh"
 #include "decoder.cuh"
 #include "encoder.cuh"
@@ -24,7 +27,7 @@ namespace wdr {
 int dtw_cost_dev(const float* w, int H, int T, int A, int sot_len, int width, float* mean, float* scale, float* out, cudaStream_t st);
 struct DtwWindow { int64_t x_off; int32_t N, M; int64_t tr_off; };
 int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int32_t* time_idx, int32_t* path_len, int max_path,
-            float* cost_out, int32_t* trace_out, cudaStream_t st);
+            float* cost_out, int32_t* trace_out, cudaStream_t st, void* wins_scratch_dev);
 
 constexpr int kDeltaMin = 10;  // whisper.cpp v1.7.x: "if only 100 ms left, then stop" (delta_min = 10 mel frames)
 
@@ -60,6 +63,20 @@ static int timestamp_to_sample(int64_t t, int n_samples) {
     return (int)s;
 }
 static int64_t sample_to_timestamp(int i) { return (100ll * i) / WDR_SAMPLE_RATE; }
+
+// f(i) for i in [0, n) on up to 16 host threads (dynamic claim); f must not touch shared state
+template <typename F>
+static void parallel_for(int n, F f) {
+    int nt = (int)std::thread::hardware_concurrency();
+    nt = std::max(1, std::min(std::min(nt, 16), n));
+    if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    auto work = [&]() { for (int i; (i = next.fetch_add(1)) < n;) f(i); };
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
 
 // whisper_exp_compute_token_level_timestamps for one segment; st3 = {t_beg, t_last, tid_last}
 static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t t0, int64_t t1, const Vocab& v, const float* energy,
@@ -314,14 +331,37 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     fs.decode_steps += steps_run;
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[3], s));
     // ---- results to the host ----
+    static const bool dbg_time = getenv("WDR_DEBUG_TIMING") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_h0 = now_ms();
     std::vector<wdr_token_data> toks((size_t)B * kDecMaxTokens);
     WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
     WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
     WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    const double t_h1 = now_ms();
     if (p.token_timestamps) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
+    const double t_h2 = now_ms();
 
     struct Pending { int seg; int b; int n_frames; std::vector<int32_t> dtw_seq; int sot_len; };
     std::vector<Pending> pend;
+    struct PostJob { int seg; int b; };
+    std::vector<PostJob> post;
+    // The heuristic token timestamps scan ~1e6 energy samples per window on the host, as whisper.cpp does: ~2 ms per
+    // window.  Windows are independent, so the jobs run on a few host threads, and they run AFTER the DTW pass / DTW kernels have
+    // been queued so that the GPU works underneath them.
+    auto run_post = [&]() {
+        parallel_for((int)post.size(), [&](int i) {
+            ResultSegment& seg = st->results[post[i].seg];
+            const int b = post[i].b;
+            if (p.token_timestamps) {
+                int64_t st3[3] = {0, 0, 0};
+                token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, nv[b], p.thold_pt, p.thold_ptsum, st3);
+            }
+            seg.token_text.reserve(seg.tokens.size());
+            for (auto& t : seg.tokens) seg.token_text.push_back(token_text(v, t.id));
+        });
+        post.clear();
+    };
     for (int b = 0; b < B; b++) {
         const DecWinState& w = win[b];
         ChunkInfo ci;
@@ -350,12 +390,8 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                 seg.text = text;
                 seg.no_speech_prob = w.no_speech_prob;
                 seg.tokens = cur;
-                if (p.token_timestamps) {
-                    int64_t st3[3] = {0, 0, 0};
-                    token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, nv[b], p.thold_pt, p.thold_ptsum, st3);
-                }
-                for (auto& t : seg.tokens) seg.token_text.push_back(token_text(v, t.id));
                 st->results.push_back(std::move(seg));
+                post.push_back({(int)st->results.size() - 1, b});  // token timestamps + token strings: after the DTW launches
                 ci.n_segments = 1;
                 if (ctx->dtw_enabled) {
                     Pending pd;
@@ -375,6 +411,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         }
         st->chunk_info.push_back(ci);
     }
+    if (dbg_time) fprintf(stderr, "[wdr] results D2H+sync %.1f ms, energy wait %.1f ms, host assembly %.1f ms\n", t_h1 - t_h0, t_h2 - t_h1, now_ms() - t_h2);
     // ---- DTW token timestamps: teacher-forced pass capturing the alignment heads, then cost + wavefront + backtrace ----
     if (!pend.empty()) {
         const int Ha = (int)ctx->aheads.size();
@@ -404,6 +441,8 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         if ((rc = grow_dev(&fs.dtw_x, &fs.dtw_x_cap, std::max<size_t>(x_total, 1))) != WDR_OK) return rc;
         if ((rc = grow_dev(&fs.dtw_stat, &fs.dtw_stat_cap, 2 * std::max<size_t>(stat_max, 1))) != WDR_OK) return rc;
         if ((rc = grow_dev(&fs.dtw_path, &fs.dtw_path_cap, (size_t)(2 * max_path + 1) * B)) != WDR_OK) return rc;
+        if ((rc = grow_dev(&fs.dtw_wins, &fs.dtw_wins_cap, (size_t)B * sizeof(DtwWindow))) != WDR_OK) return rc;
+        if ((rc = grow_pinned(&fs.dtw_path_host, &fs.dtw_path_host_cap, (size_t)(2 * max_path + 1) * B)) != WDR_OK) return rc;
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_off, aw_off.data(), sizeof(int64_t) * B, cudaMemcpyHostToDevice, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.aw_T, aw_T.data(), sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
@@ -412,7 +451,13 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         if (stepwise) {
             for (int i = 0; i < max_T; i++)
                 if ((rc = decoder_step(ctx, ws, B, i, false, DEC_MODE_DTW, s, &st->prof)) != WDR_OK) return rc;
-        } else if ((rc = decoder_dtw_pass(ctx, ws, st->dtwp, B, aw_T.data(), s, &st->prof)) != WDR_OK) return rc;
+        } else {
+            static const bool prof_range = getenv("WDR_PROFILE_DTW_PASS") != nullptr;  // ncu --profile-from-start off: capture this pass only
+            if (prof_range) { cudaStreamSynchronize(s); cudaProfilerStart(); }
+            rc = decoder_dtw_pass(ctx, ws, st->dtwp, B, aw_T.data(), s, &st->prof);
+            if (prof_range) { cudaStreamSynchronize(s); cudaProfilerStop(); }
+            if (rc != WDR_OK) return rc;
+        }
         WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[4], s));
         std::vector<DtwWindow> wins;
         std::vector<int> win_b;
@@ -434,20 +479,23 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             int32_t* pl = tj + (size_t)max_path * B;
             {
                 ProfScope ps(&st->prof, KC_DTW, s);
-                if ((rc = dtw_run(fs.dtw_x, wins, ti, tj, pl, max_path, nullptr, nullptr, s)) != WDR_OK) return rc;
+                if ((rc = dtw_run(fs.dtw_x, wins, ti, tj, pl, max_path, nullptr, nullptr, s, fs.dtw_wins)) != WDR_OK) return rc;
             }
             const size_t nw = wins.size();
-            std::vector<int32_t> h_ti(nw * max_path), h_tj(nw * max_path), h_pl(nw);
-            WDR_CUDA_TRY(cudaMemcpyAsync(h_ti.data(), ti, sizeof(int32_t) * h_ti.size(), cudaMemcpyDeviceToHost, s));
-            WDR_CUDA_TRY(cudaMemcpyAsync(h_tj.data(), tj, sizeof(int32_t) * h_tj.size(), cudaMemcpyDeviceToHost, s));
-            WDR_CUDA_TRY(cudaMemcpyAsync(h_pl.data(), pl, sizeof(int32_t) * nw, cudaMemcpyDeviceToHost, s));
+            int32_t* h_ti = fs.dtw_path_host;  // pinned: the three reads below are true async copies
+            int32_t* h_tj = h_ti + nw * max_path;
+            int32_t* h_pl = h_tj + nw * max_path;
+            WDR_CUDA_TRY(cudaMemcpyAsync(h_ti, ti, sizeof(int32_t) * nw * max_path, cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaMemcpyAsync(h_tj, tj, sizeof(int32_t) * nw * max_path, cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaMemcpyAsync(h_pl, pl, sizeof(int32_t) * nw, cudaMemcpyDeviceToHost, s));
+            run_post();  // host work under the queued GPU work
             WDR_CUDA_TRY(cudaStreamSynchronize(s));
             for (size_t k = 0; k < nw; k++) {
                 const Pending& pd = pend[win_b[k]];
                 ResultSegment& seg = st->results[pd.seg];
                 const int seek = 0;
-                const int32_t* a_ti = h_ti.data() + k * max_path;
-                const int32_t* a_tj = h_tj.data() + k * max_path;
+                const int32_t* a_ti = h_ti + k * max_path;
+                const int32_t* a_tj = h_tj + k * max_path;
                 if (h_pl[k] < 0) { set_error("dtw backtrace did not terminate"); return WDR_ERR_CUDA; }
                 int last_v = 0;
                 size_t tix = 0;
@@ -464,9 +512,11 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                 }
             }
         } else {
+            run_post();
             WDR_CUDA_TRY(cudaStreamSynchronize(s));
         }
     }
+    run_post();  // no DTW: nothing was queued above
     {   // phase times of this group (the stream is idle here: every branch above ended with a synchronize)
         const bool dtw = !pend.empty();
         if (!dtw) WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[4], s));
@@ -541,16 +591,16 @@ static int full_range(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     return WDR_OK;
 }
 
-// Lanes: the windows of one call are cut into contiguous ranges, each driven by its own host thread on its own streams and
-// workspaces.  A decode step is a chain of ~400 dependent, latency-bound kernels around one HBM-bound cross-attention per
-// layer; with several lanes in flight the SMs and HBM that one lane leaves idle between its dependent launches serve the
-// others (and one lane's tensor-bound encoder overlaps another's decode).  Windows are independent (sharded mode),
-// every kernel's result for a window is independent of which other windows share its launch, so the output is identical
-// for any lane count.
+// Lanes: the windows of one call can be cut into contiguous ranges, each driven by its own host thread on its own streams and
+// workspaces (one lane's tensor-bound encoder / latency-bound decode chain under another's HBM-bound cross-attention).
+// Windows are independent (sharded mode) and every kernel's result for a window is independent of which other
+// windows share its launch, so the output is identical for any lane count.  Measured on B200 (large-v3, 120 windows): 2 lanes
+// are no faster than 1 — each lane's weight-streaming GEMMs still occupy every SM's shared memory and a half-full 128-row tile
+// costs what a full one does — so the default is ONE lane; the knob stays for many-small-window calls.
 static int default_lanes() {
     static const int n = [] {
         const char* e = getenv("WDR_LANES");
-        const int v = e ? atoi(e) : 3;
+        const int v = e ? atoi(e) : 1;
         return v < 1 ? 1 : (v > 8 ? 8 : v);
     }();
     return n;

@@ -379,13 +379,13 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     const int BN = d.bn == 64 ? 64 : 128;
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
     if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
-    else if (d.split_k > 1 || d.bn == 64) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 are plain fp32-partial GEMMs (EPI_F32, no bias)");
+    else if (d.split_k > 1 || d.bn == 64 || d.dual_a) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 / dual-A are plain fp32-partial GEMMs (EPI_F32, no bias)");
     CUtensorMap ta, tb;
     {
         // in tap mode the last tap reads rows up to rows_per_batch - 1 + (taps - 1): the caller's buffer holds them
         const int num_kb = (d.K + kBK - 1) / kBK;
         const int taps = d.kb_per_tap > 0 ? (num_kb + d.kb_per_tap - 1) / d.kb_per_tap : 1;
-        if (d.dual_a) WDR_REQUIRE(d.n_batch == 1 && d.bn == 64 && d.a_dual_stride > 0 && d.a_dual_stride % 8 == 0, "dual-A GEMMs are single-batch BN=64 GEMMs");
+        if (d.dual_a) WDR_REQUIRE(d.n_batch == 1 && (d.bn == 64 || d.bn == 128) && d.a_dual_stride > 0 && d.a_dual_stride % 8 == 0, "dual-A GEMMs are single-batch BN=64/128 GEMMs");
         const uint64_t dims[3] = {(uint64_t)(d.a_cols > 0 ? d.a_cols : d.K), (uint64_t)(d.rows_per_batch + taps - 1), (uint64_t)(d.dual_a ? 2 : d.n_batch)};
         const uint64_t str[2] = {(uint64_t)d.a_row_stride * 2,
                                  (uint64_t)(d.dual_a ? d.a_dual_stride : d.n_batch > 1 ? d.a_batch_stride : d.a_row_stride * d.rows_per_batch) * 2};
@@ -429,7 +429,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         case EPI_BIAS_RELU_BF16: return launch_gemm<128, 5, EPI_BIAS_RELU_BF16>(ta, tb, p, st);
         case EPI_BIAS_ADD_RELU_BF16: WDR_REQUIRE(d.resid_bf16, "resid_bf16 missing"); return launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16>(ta, tb, p, st);
         case EPI_F32:
-            if (d.dual_a) return launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st);
+            if (d.dual_a) return BN == 64 ? launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st) : launch_gemm<128, 3, EPI_F32, true>(ta, tb, p, st);
             return BN == 64 ? launch_gemm<64, 7, EPI_F32>(ta, tb, p, st) : launch_gemm<128, 5, EPI_F32>(ta, tb, p, st);
     }
     set_error("unknown epilogue %d", d.epilogue);

@@ -234,17 +234,20 @@ extern "C" wdr_seg* wdr_seg_init(const char* path, uint64_t seed, int device) {
     w.conv2b = m->mem.upload(S("conv2.bias", 60, 0.0f, s2));
     w.n2g = m->mem.upload(S("norm2.weight", 60, 1.0f, 0.1f));
     w.n2b = m->mem.upload(S("norm2.bias", 60, 0.0f, 0.1f));
-    const float sl = (float)(1.0 / sqrt(128.0));
+    // Recurrent / head matrices are drawn 2.5x / 2x / 6x wider than PyTorch's default init and the "no speaker" class gets a
+    // +1.5 bias: with default-init scales a random PyanNet's output is constant in time (no segment is ever emitted); with these
+    // the speech state machine flips a few times per window, so get_segments has real work (oracle/pyannet.py: same constants).
+    const float sl = (float)(1.0 / sqrt(128.0)), slw = (float)(2.5 / sqrt(128.0));
     for (int l = 0; l < 4; l++) {
         const int n_in = l == 0 ? 60 : 256;
         std::vector<float> wih, bg, whh;
         for (const char* d : {"", "_reverse"}) {
             char nm[64];
             snprintf(nm, sizeof(nm), "lstm.weight_ih_l%d%s", l, d);
-            auto a = S(nm, (size_t)512 * n_in, 0.0f, sl);
+            auto a = S(nm, (size_t)512 * n_in, 0.0f, slw);
             wih.insert(wih.end(), a.begin(), a.end());
             snprintf(nm, sizeof(nm), "lstm.weight_hh_l%d%s", l, d);
-            auto h = S(nm, 512 * 128, 0.0f, sl);
+            auto h = S(nm, 512 * 128, 0.0f, slw);
             whh.insert(whh.end(), h.begin(), h.end());
             snprintf(nm, sizeof(nm), "lstm.bias_ih_l%d%s", l, d);
             auto b1 = S(nm, 512, 0.0f, sl);
@@ -256,12 +259,16 @@ extern "C" wdr_seg* wdr_seg_init(const char* path, uint64_t seed, int device) {
         w.bg[l] = m->mem.upload(bg);
         w.whh[l] = m->mem.upload(whh);
     }
-    w.l0w = m->mem.upload(S("linear0.weight", 128 * 256, 0.0f, 1.0f / 16));
+    w.l0w = m->mem.upload(S("linear0.weight", 128 * 256, 0.0f, 2.0f / 16));
     w.l0b = m->mem.upload(S("linear0.bias", 128, 0.0f, 1.0f / 16));
-    w.l1w = m->mem.upload(S("linear1.weight", 128 * 128, 0.0f, sl));
+    w.l1w = m->mem.upload(S("linear1.weight", 128 * 128, 0.0f, (float)(2.0 / sqrt(128.0))));
     w.l1b = m->mem.upload(S("linear1.bias", 128, 0.0f, sl));
-    w.cw = m->mem.upload(S("classifier.weight", 7 * 128, 0.0f, sl * 4));
-    w.cb = m->mem.upload(S("classifier.bias", 7, 0.0f, 0.5f));
+    w.cw = m->mem.upload(S("classifier.weight", 7 * 128, 0.0f, (float)(24.0 / sqrt(128.0))));
+    {
+        auto cb = S("classifier.bias", 7, 0.0f, 0.5f);
+        cb[0] += 1.5f;
+        w.cb = m->mem.upload(cb);
+    }
     if (!m->mem.ok || cudaFuncSetAttribute(sinc_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSincSmem) != cudaSuccess) {
         set_error("wdr_seg_init: device allocation failed");
         wdr_seg_free(m);

@@ -39,14 +39,19 @@ struct FullScratch {
     size_t dtw_stat_cap = 0;
     int32_t* dtw_path = nullptr;
     size_t dtw_path_cap = 0;
+    char* dtw_wins = nullptr;  // device DtwWindow table of dtw_run
+    size_t dtw_wins_cap = 0;
+    int32_t* dtw_path_host = nullptr;  // pinned
+    size_t dtw_path_host_cap = 0;
     int last_decode_steps = 0;
     // phase boundaries of the last group on the compute stream: start | encoder | cross-KV | greedy decode | DTW pass | DTW
     cudaEvent_t ev_phase[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[5] = {0, 0, 0, 0, 0};  // accumulated over the groups of the last full call
     int decode_steps = 0;                  // greedy iterations of the last full call (summed over groups)
     void release() {
-        cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path);
+        cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path); cudaFree(dtw_wins);
         if (energy_host) cudaFreeHost(energy_host);
+        if (dtw_path_host) cudaFreeHost(dtw_path_host);
         if (done_host) cudaFreeHost(done_host);
         if (ev_energy) cudaEventDestroy(ev_energy);
         if (ev_energy_done) cudaEventDestroy(ev_energy_done);
@@ -71,7 +76,7 @@ struct wdr_state {
     wdr::Profiler prof;
     // extra lanes of the full pipeline (full.cu): child states with their own streams / workspaces; lane 0 is this state
     std::vector<wdr_state*> lanes;
-    int n_lanes = 0;  // 0 = library default (WDR_LANES, else 3)
+    int n_lanes = 0;  // 0 = library default (WDR_LANES, else 1)
     // device-resident staging / results of the last encode call
     int16_t* pcm_dev = nullptr;
     size_t pcm_cap = 0;

@@ -46,3 +46,32 @@ def vad_mask_and_merge(segs_cs, int_samples):
         if e > s and len(seg):
             out.append(dict(start=s, end=e, samples=seg))
     return mask, out
+
+
+def diarize(segmenter, extractor, int_samples, threshold=0.5, max_speakers=capi.SIZE_MAX, mode="leader"):
+    """The crate's diarize flow around the boundary, batched: pyannote_rs::get_segments (reference src/engine.rs:117-122) ->
+    EmbeddingExtractor::compute per segment (src/transcribe.rs:466-467) -> speaker id per segment.
+
+    mode "leader" = the reference's policy (src/transcribe.rs:480-496): EmbeddingManager in segment order — strict `> threshold`
+    joins the best stored speaker, else a new speaker while fewer than max_speakers exist, else (cap reached) the best match;
+    a segment too short for one fbank frame gets "?".  Computed here as the ordered scan of the pairwise cosine matrix
+    (wdr_cosine_matrix + wdr_cluster_leader), which is the same function of the similarities (tests/test_oracle_cluster.py).
+    mode "agglomerative" = the north-star's average-linkage clustering of the same matrix.
+    Returns [dict(start, end, speaker)] with speaker a str as the crate renders it ("1", "2", ... or "?")."""
+    int_samples = np.asarray(int_samples, np.int16)
+    segs = segmenter.get_segments(int_samples)
+    if not segs:
+        return []
+    off = np.zeros(len(segs) + 1, np.int64)
+    for i, s in enumerate(segs):
+        off[i + 1] = off[i] + len(s["samples"])
+    pcm = np.concatenate([s["samples"] for s in segs]).astype(np.int16) if off[-1] else np.zeros(0, np.int16)
+    emb, status = extractor.compute_batch(pcm, off)
+    ok = np.flatnonzero(status == 0)
+    speakers = ["?"] * len(segs)
+    if len(ok):
+        S = capi.cosine_matrix(emb[ok])
+        labels = capi.cluster_leader(S, threshold, max_speakers) if mode == "leader" else capi.cluster_agglomerative(S, threshold)
+        for i, l in zip(ok, labels):
+            speakers[i] = str(int(l)) if l > 0 else "?"
+    return [dict(start=s["start"], end=s["end"], speaker=sp) for s, sp in zip(segs, speakers)]
