@@ -521,6 +521,13 @@ def main():
             k = kern[dom]
             roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)" if dom == "gemm" else "encoder_attention_kernel (tcgen05)",
                         "achieved": k["achieved_tflops"], "peak": tf_peak, "unit": "TFLOP/s", "frac": k["frac"], "traffic": None}
+        try:  # per-launch DRAM traffic of that kernel from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(roofline["kernel"], {})
+            if full or roofline["kernel"] != "dec_cross_attn_kernel":
+                roofline["traffic"] = tr.get("bytes_per_launch") if args.arch == "large-v3" and B == 120 else None
+                roofline["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
         roofline["peak_source"] = peak_src
         roofline["share_of_step"] = cand[dom] / total_ms
         line = {"metric": metric_name(args.workload), "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,

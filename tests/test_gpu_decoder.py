@@ -170,3 +170,49 @@ def test_lanes_do_not_change_results(wdr):
     assert len(out[0]) - 1 >= 12
     st.close()
     ctx.close()
+
+
+def test_full_sequential_60s_matches_oracle(wdr, oracle):
+    """BASELINE configs[0] shape: base.en, 60 s of 16 kHz audio in ONE state.full call (VAD off), greedy, token timestamps, DTW.
+    whisper_full's own seek loop: data-dependent window starts, prompt carry between windows, buffer-global mel max.  Window
+    starts, token ids, segment times, heuristic t0/t1 and DTW times must equal the oracle's; each window's encoder output comes
+    from the library (the encoder's own parity is tests/test_gpu_encoder.py), so the decode sees identical inputs."""
+    from oracle import weights as W, full, filters
+    arch = "base.en"
+    w = W.whisper_weights(arch, seed=1234)
+    pcm = synth_audio(1001, 60.0)
+    x = pcm.astype(np.float32) / np.float32(32768.0)
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    segs = st.full(pcm)
+    n_win = 0
+    while True:
+        try:
+            st.chunk_info(n_win)
+            n_win += 1
+        except wdr.WdrError:
+            break
+    assert n_win >= 2 and len(segs) >= 2
+    enc_st = ctx.create_state()
+    lib_mel = wdr.MelFrontend(filters.whisper_mel_filters(80)).log_mel(pcm)  # buffer-global max, the kernel the call itself runs
+
+    def encode(mel_window, seek):
+        assert np.abs(mel_window[:, :100] - lib_mel[:, seek:seek + 100]).max() < 1e-4
+        return enc_st.encode(lib_mel, mel_offset=seek)
+
+    dec = oracle.Decoder(arch, W.pack_decoder(arch, w), bf16=True)
+    ref = full.full_sequential(dec, encode, filters.whisper_mel_filters(80), x)
+    dec.close()
+    assert [st.chunk_info(i)["seek_delta"] for i in range(n_win)] == [wi["seek_delta"] for wi in ref["windows"]]
+    assert len(segs) == len(ref["segments"])
+    for g, r in zip(segs, ref["segments"]):
+        assert [t.id for t in g["tokens"]] == [t.id for t in r["tokens"]]
+        assert (g["t0"], g["t1"], g["text"]) == (r["t0"], r["t1"], r["text"])
+        for tg, tr in zip(g["tokens"], r["tokens"]):
+            assert (tg.t0, tg.t1, tg.t_dtw, tg.tid) == (tr.t0, tr.t1, tr.t_dtw, tr.tid), (g["t0"], tg.id)
+    # the f32 entry point takes the same path
+    segs2 = st.full(x)
+    assert [[t.id for t in s["tokens"]] for s in segs2] == [[t.id for t in s["tokens"]] for s in segs]
+    enc_st.close()
+    st.close()
+    ctx.close()

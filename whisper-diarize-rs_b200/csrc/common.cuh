@@ -1,5 +1,6 @@
 // common.cuh — error plumbing, launch accounting and small device helpers shared by every kernel file.
 #pragma once
+#include <utility>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -80,6 +81,26 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor still runs:
+// pdl_launch_dependents() (first statement) lets the successor's CTAs be scheduled once every CTA of this grid has started;
+// pdl_wait() blocks until the predecessor grid has completed and its memory is visible.  Everything before pdl_wait() must
+// neither read the predecessor's output nor write anything it may still read.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
 }
 
 }  // namespace wdr

@@ -87,7 +87,7 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 //                         length ws.aw_T[b], and without logits only the layers up to the last alignment head run.
 enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2 };
 int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof,
-                 bool pos_on_device = false);
+                 bool pos_on_device = false, bool pdl = false);
 // The DTW pass in one shot: the teacher-forced sequences ws.seq[b][0 .. T_b) (T_b = ws.aw_T[b], host copy in T_host; 0 = window
 // not in the pass) of all B windows run through the decoder layers up to the last alignment head as ONE batch of sum(T_b) packed
 // rows — every linear layer is a full-size tcgen05 GEMM (weights read once, not once per token position) and the cross-attention
@@ -96,7 +96,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
 int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorkspace& pw, int B, const int32_t* T_host, cudaStream_t st, Profiler* prof);
 // whisper_process_logits + greedy whisper_sample_token + decoder bookkeeping on ws.logits; appends to ws.tokens / ws.seq[pos+1]
 int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, const SampleParams& sp, cudaStream_t st, Profiler* prof,
-                   bool pos_on_device = false);
+                   bool pos_on_device = false, bool pdl = false);
 int decoder_decode_graph(const wdr_context* ctx, DecoderWorkspace& ws, int B, const SampleParams& sp, cudaStream_t st, cudaGraphExec_t* out);
 
 }  // namespace wdr

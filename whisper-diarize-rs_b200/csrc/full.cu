@@ -24,6 +24,9 @@
 
 namespace wdr {
 
+template <typename In>
+int mel_launch(wdr_mel* m, const In* pcm, int64_t chunk_stride, const int32_t* n_valid_dev, int n_fixed, int n_chunks, int n_frames, int normalize,
+               float* out, float* out_max, cudaStream_t st);
 int dtw_cost_dev(const float* w, int H, int T, int A, int sot_len, int width, float* mean, float* scale, float* out, cudaStream_t st);
 struct DtwWindow { int64_t x_off; int32_t N, M; int64_t tr_off; };
 int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int32_t* time_idx, int32_t* path_len, int max_path,
@@ -217,10 +220,23 @@ static int grow_pinned(T** p, size_t* cap, size_t need) {
     return WDR_OK;
 }
 
-// One group of B <= 128 windows whose PCM is already on the device (In = int16_t or float).
+// Sequential mode (whisper_full's own seek loop over a buffer longer than 30 s): one window of the long buffer.
+struct SeqWindow {
+    const float* mel_dev;         // raw log-mel of the WHOLE buffer [n_mel][n_len] (device)
+    int n_len;
+    const float* max_dev;         // its global maximum (whisper.cpp normalises with the buffer-global max)
+    int seek, seek_end;           // window start / end of audio, mel frames (= centiseconds)
+    const float* energy_host;     // get_signal_energy of the whole buffer (host)
+    int n_samples;
+    int64_t* st3;                 // t_beg, t_last, tid_last carried across the call's segments
+    const std::vector<int32_t>* prompt_past;
+};
+
+// One group of B <= 128 windows whose PCM is already on the device (In = int16_t or float).  sw != nullptr: B == 1 and the
+// window comes from a long buffer's mel at frame sw->seek instead of from pcm_dev.
 template <typename In>
 static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, int lang_id, const In* pcm_dev, int64_t chunk_stride,
-                      const int32_t* n_valid_host, int chunk0, int B) {
+                      const int32_t* n_valid_host, int chunk0, int B, const SeqWindow* sw = nullptr) {
     FullScratch& fs = st->full;
     DecoderWorkspace& ws = st->dec;
     const WhisperArch& a = ctx->arch;
@@ -237,9 +253,13 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         if (!e) WDR_CUDA_TRY(cudaEventCreate(&e));
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[0], s));
     // ---- mel + encoder -> bf16 hidden states ----
-    if ((rc = encode_chunks<In>(ctx, st->enc, pcm_dev, chunk_stride, fs.nvalid_dev, B, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
+    if (sw) {
+        WDR_REQUIRE(B == 1, "sequential mode decodes one window at a time");
+        if ((rc = st->enc.reserve(ctx->arch, 1)) != WDR_OK) return rc;
+        if ((rc = encoder_forward(ctx, st->enc, sw->mel_dev, sw->n_len, sw->seek, sw->max_dev, 0, 1, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
+    } else if ((rc = encode_chunks<In>(ctx, st->enc, pcm_dev, chunk_stride, fs.nvalid_dev, B, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
     // ---- energy for the token-timestamp heuristic (D2H overlaps the decode) ----
-    if (p.token_timestamps) {
+    if (p.token_timestamps && !sw) {
         if ((rc = grow_dev(&fs.energy_dev, &fs.energy_cap, (size_t)B * WDR_CHUNK_SAMPLES)) != WDR_OK) return rc;
         if ((rc = grow_pinned(&fs.energy_host, &fs.energy_host_cap, (size_t)B * WDR_CHUNK_SAMPLES)) != WDR_OK) return rc;
         ProfScope ps(&st->prof, KC_OTHER, s);
@@ -258,10 +278,12 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[2], s));
     // ---- prompt + decoder state ----
     std::vector<int32_t> prompt;
-    if (p.prompt_tokens && p.prompt_n_tokens > 0 && p.n_max_text_ctx > 0) {
-        const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), p.prompt_n_tokens);
+    const int32_t* past = sw ? sw->prompt_past->data() : p.prompt_tokens;
+    const int n_past = sw ? (int)sw->prompt_past->size() : p.prompt_n_tokens;
+    if (past && n_past > 0 && p.n_max_text_ctx > 0) {
+        const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), n_past);
         prompt.push_back(v.prev);
-        for (int i = p.prompt_n_tokens - n_take; i < p.prompt_n_tokens; i++) prompt.push_back(p.prompt_tokens[i]);
+        for (int i = n_past - n_take; i < n_past; i++) prompt.push_back(past[i]);
     }
     prompt.push_back(v.sot);
     if (v.multilingual) {
@@ -279,9 +301,9 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         DecWinState w;
         memset(&w, 0, sizeof(w));
         w.seek_delta = 100 * 30;
-        w.seek = 0;
-        w.seek_end = 1 + (nv[b] + 200 - WDR_N_FFT) / WDR_HOP;  // mel.n_len_org
-        if (nv[b] <= 0 || w.seek_end < w.seek + kDeltaMin || w.seek + kDeltaMin >= w.seek_end) { w.completed = 1; w.seek_delta = 0; n_skip++; }  // too short: no decode
+        w.seek = sw ? sw->seek : 0;
+        w.seek_end = sw ? sw->seek_end : 1 + (nv[b] + 200 - WDR_N_FFT) / WDR_HOP;  // mel.n_len_org
+        if ((!sw && nv[b] <= 0) || w.seek_end < w.seek + kDeltaMin || w.seek + kDeltaMin >= w.seek_end) { w.completed = 1; w.seek_delta = 0; n_skip++; }  // too short: no decode
         win[b] = w;
     }
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
@@ -339,7 +361,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
     WDR_CUDA_TRY(cudaStreamSynchronize(s));
     const double t_h1 = now_ms();
-    if (p.token_timestamps) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
+    if (p.token_timestamps && !sw) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
     const double t_h2 = now_ms();
 
     struct Pending { int seg; int b; int n_frames; std::vector<int32_t> dtw_seq; int sot_len; };
@@ -355,7 +377,8 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             const int b = post[i].b;
             if (p.token_timestamps) {
                 int64_t st3[3] = {0, 0, 0};
-                token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, nv[b], p.thold_pt, p.thold_ptsum, st3);
+                if (sw) token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, sw->energy_host, sw->n_samples, p.thold_pt, p.thold_ptsum, sw->st3);
+                else token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, nv[b], p.thold_pt, p.thold_ptsum, st3);
             }
             seg.token_text.reserve(seg.tokens.size());
             for (auto& t : seg.tokens) seg.token_text.push_back(token_text(v, t.id));
@@ -493,7 +516,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             for (size_t k = 0; k < nw; k++) {
                 const Pending& pd = pend[win_b[k]];
                 ResultSegment& seg = st->results[pd.seg];
-                const int seek = 0;
+                const int seek = sw ? sw->seek : 0;
                 const int32_t* a_ti = h_ti + k * max_path;
                 const int32_t* a_tj = h_tj + k * max_path;
                 if (h_pl[k] < 0) { set_error("dtw backtrace did not terminate"); return WDR_ERR_CUDA; }
@@ -527,6 +550,83 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             if (cudaEventElapsedTime(&t, fs.ev_phase[i], fs.ev_phase[i + 1]) == cudaSuccess) fs.phase_ms[i] += t;
         }
     }
+    return WDR_OK;
+}
+
+// whisper_full_with_state on a buffer longer than 30 s: the seek loop of SURVEY A.4 (what the crate runs when VAD and
+// diarization are off: one SpeechSegment holding the whole file, reference src/engine.rs:124-134, src/transcribe.rs:389).
+// The mel of the whole buffer is computed once and normalised with its global maximum; windows are decoded one at a time
+// (window k+1 starts where window k's last timestamp token says, and is conditioned on window k's tokens), so this mode
+// is sequential by construction: replicas only, no sharding.
+template <typename In>
+static int full_sequential(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, int lang_id, const In* pcm_host, int n) {
+    int rc = ensure_device(ctx->device);
+    if (rc != WDR_OK) return rc;
+    st->results.clear();
+    st->chunk_info.clear();
+    st->lang_id = lang_id;
+    FullScratch& fs = st->full;
+    for (auto& v : fs.phase_ms) v = 0.0;
+    fs.decode_steps = 0;
+    if (!fs.ev_energy) {
+        WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy, cudaEventDisableTiming));
+        WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy_done, cudaEventDisableTiming));
+        WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_h2d, cudaEventDisableTiming));
+        WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.done_host), sizeof(int32_t)));
+    }
+    cudaStream_t s = st->stream;
+    const int n_len = (n + WDR_CHUNK_SAMPLES) / WDR_HOP;
+    const int n_mel = ctx->arch.n_mel;
+    DevBuf<In> d_pcm;
+    DevBuf<float> d_mel, d_max, d_energy;
+    WDR_CUDA_TRY(d_pcm.alloc((size_t)n));
+    WDR_CUDA_TRY(d_mel.alloc((size_t)n_mel * n_len));
+    WDR_CUDA_TRY(d_max.alloc(1));
+    WDR_CUDA_TRY(cudaMemcpyAsync(d_pcm.p, pcm_host, sizeof(In) * (size_t)n, cudaMemcpyHostToDevice, s));
+    if ((rc = mel_launch<In>(ctx->mel, d_pcm.p, 0, nullptr, n, 1, n_len, 0, d_mel.p, d_max.p, s)) != WDR_OK) return rc;
+    std::vector<float> energy;
+    if (p.token_timestamps) {
+        WDR_CUDA_TRY(d_energy.alloc((size_t)n));
+        energy.resize((size_t)n);
+        energy_kernel<In><<<dim3(148 * 8, 1), 256, 0, s>>>(d_pcm.p, 0, nullptr, n, 32, d_energy.p, 0);
+        WDR_LAUNCH_CHECK();
+        WDR_CUDA_TRY(cudaMemcpyAsync(energy.data(), d_energy.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    }
+    WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    const int seek_end = 1 + (n + 200 - WDR_N_FFT) / WDR_HOP;  // mel.n_len_org
+    int seek = 0;
+    int64_t st3[3] = {0, 0, 0};
+    std::vector<int32_t> prompt_past;  // no_context = true (the crate never clears it): starts empty for every call
+    if (p.prompt_tokens && p.prompt_n_tokens > 0) prompt_past.assign(p.prompt_tokens, p.prompt_tokens + p.prompt_n_tokens);
+    const Vocab v = make_vocab(ctx->arch.n_vocab);
+    if (seek_end < seek + kDeltaMin) return WDR_OK;
+    while (seek + kDeltaMin < seek_end) {
+        SeqWindow sw;
+        sw.mel_dev = d_mel.p; sw.n_len = n_len; sw.max_dev = d_max.p; sw.seek = seek; sw.seek_end = seek_end;
+        sw.energy_host = energy.empty() ? nullptr : energy.data(); sw.n_samples = n; sw.st3 = st3; sw.prompt_past = &prompt_past;
+        const size_t n_res0 = st->results.size();
+        rc = full_group<In>(ctx, st, p, lang_id, nullptr, 0, nullptr, 0, 1, &sw);
+        if (rc != WDR_OK) return rc;
+        const ChunkInfo& ci = st->chunk_info.back();
+        // prompt_past <- the part of it that went into this window's prompt + the window's result tokens (whisper_full)
+        {
+            std::vector<int32_t> next;
+            if (!prompt_past.empty() && p.n_max_text_ctx > 0) {
+                const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), (int)prompt_past.size());
+                next.assign(prompt_past.end() - n_take, prompt_past.end());
+            }
+            if (st->results.size() > n_res0) {
+                const ResultSegment& seg = st->results.back();
+                const int n_keep = std::min((int)seg.tokens.size(), ci.result_len);
+                for (int i = 0; i < n_keep; i++) next.push_back(seg.tokens[i].id);
+            }
+            prompt_past.swap(next);
+        }
+        if (p.progress_callback) p.progress_callback(ctx, st, (int)std::min<int64_t>(100, 100ll * (seek + ci.seek_delta) / std::max(1, seek_end)), p.progress_callback_user_data);
+        if (ci.seek_delta <= 0) break;  // no progress: stop rather than spin (whisper.cpp cannot get here with a positive delta_min)
+        seek += ci.seek_delta;
+    }
+    (void)v;
     return WDR_OK;
 }
 
@@ -664,6 +764,15 @@ static int full_batch_impl(wdr_context* ctx, wdr_state* st, const wdr_full_param
     return WDR_OK;
 }
 
+template <typename In>
+static int full_long(wdr_context* ctx, wdr_state* st, const wdr_full_params& p, const In* pcm, int n) {
+    WDR_REQUIRE(ctx && st && st->ctx == ctx && pcm, "bad arguments");
+    int lang_id = 0;
+    int rc = validate_params(ctx, p, &lang_id);
+    if (rc != WDR_OK) return rc;
+    return full_sequential<In>(ctx, st, p, lang_id, pcm, n);
+}
+
 }  // namespace wdr
 
 using namespace wdr;
@@ -696,13 +805,15 @@ extern "C" wdr_full_params wdr_full_default_params(int strategy) {
 
 extern "C" int wdr_full_with_state(wdr_context* ctx, wdr_state* st, wdr_full_params p, const float* pcm, int n) {
     clear_error();
-    WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "wdr_full_with_state takes one buffer of <= 30 s; longer audio goes through wdr_full_batch_i16 in 30 s chunks");
+    WDR_REQUIRE(n >= 0, "negative sample count");
+    if (n > WDR_CHUNK_SAMPLES) return full_long<float>(ctx, st, p, pcm, n);
     const int32_t nv = n;
     return full_batch_impl<float>(ctx, st, p, pcm, WDR_CHUNK_SAMPLES, &nv, 1);
 }
 extern "C" int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm, int n) {
     clear_error();
-    WDR_REQUIRE(n >= 0 && n <= WDR_CHUNK_SAMPLES, "wdr_full_with_state_i16 takes one buffer of <= 30 s");
+    WDR_REQUIRE(n >= 0, "negative sample count");
+    if (n > WDR_CHUNK_SAMPLES) return full_long<int16_t>(ctx, st, p, pcm, n);
     const int32_t nv = n;
     return full_batch_impl<int16_t>(ctx, st, p, pcm, WDR_CHUNK_SAMPLES, &nv, 1);
 }

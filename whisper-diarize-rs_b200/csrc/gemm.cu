@@ -88,6 +88,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + kBK - 1) / kBK;
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
@@ -118,18 +119,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            // The weight operand does not depend on the predecessor kernel: the first item's first STAGES weight tiles are
+            // requested before pdl_wait(), so their HBM latency overlaps the predecessor's tail.
+            int prefetched = 0;
+            if (blockIdx.x < p.total_tiles) {
+                const int w = blockIdx.x;
+                const int t = w / p.splits, sp = w - t * p.splits;
+                const int n_tile = t % p.n_tiles;
+                const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                prefetched = min(STAGES, kb1 - kb0);
+                for (int i = 0; i < prefetched; i++) {
+                    mbar_arrive_expect_tx(&bar_full[i], kAStage + kBBytes);
+                    tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], (kb0 + i) * kBK, n_tile * BN);
+                }
+            }
+            pdl_wait();
             for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w - t * p.splits;
                 const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
                 const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
-                    mbar_wait(&bar_empty[s], ph ^ 1);
-                    mbar_arrive_expect_tx(&bar_full[s], kAStage + kBBytes);
+                    const bool have_b = prefetched > 0;  // this stage's barrier is armed and its weight tile is in flight
+                    if (have_b) prefetched--;
+                    else {
+                        mbar_wait(&bar_empty[s], ph ^ 1);
+                        mbar_arrive_expect_tx(&bar_full[s], kAStage + kBBytes);
+                    }
                     const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
                     tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
                     if (DUAL) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
-                    tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
+                    if (!have_b) tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -173,6 +193,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         }
     } else if (warp >= 4) {
         // ===================== epilogue: 8 warps = 4 TMEM lane quarters x 2 column halves =====================
+        pdl_wait();  // the epilogue reads residuals and overwrites buffers the predecessor may still be reading
         const int q = warp & 3;           // TMEM lane group this warp may access
         const int half = (warp - 4) >> 2;  // which half of the tile's columns
         float4* stage = s_stage[warp - 4];
@@ -356,7 +377,7 @@ int num_sms() {
 }
 
 template <int BN, int STAGES, int EPI, bool DUAL = false>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st, bool pdl = false) {
     constexpr size_t smem = (size_t)STAGES * ((DUAL ? 2 : 1) * kBM * kBK * 2 + BN * kBK * 2) + 1024;
     static bool attr_done = false;
     if (!attr_done) {
@@ -364,7 +385,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
         attr_done = true;
     }
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    gemm_bf16_kernel<BN, STAGES, EPI, DUAL><<<grid, kGemmThreads, smem, st>>>(ta, tb, p);
+    WDR_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, dim3(grid), dim3(kGemmThreads), smem, st, pdl, ta, tb, p));
     WDR_LAUNCH_CHECK();
     return WDR_OK;
 }
@@ -425,11 +446,11 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<128, 5, EPI_BIAS_RESID_F32>(ta, tb, p, st);
         case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<128, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
         case EPI_QKV_BF16: return launch_gemm<128, 5, EPI_QKV_BF16>(ta, tb, p, st);
-        case EPI_BIAS_GELU_SPLIT: return launch_gemm<64, 4, EPI_BIAS_GELU_SPLIT, true>(ta, tb, p, st);
+        case EPI_BIAS_GELU_SPLIT: return launch_gemm<64, 4, EPI_BIAS_GELU_SPLIT, true>(ta, tb, p, st, d.pdl);
         case EPI_BIAS_RELU_BF16: return launch_gemm<128, 5, EPI_BIAS_RELU_BF16>(ta, tb, p, st);
         case EPI_BIAS_ADD_RELU_BF16: WDR_REQUIRE(d.resid_bf16, "resid_bf16 missing"); return launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16>(ta, tb, p, st);
         case EPI_F32:
-            if (d.dual_a) return BN == 64 ? launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st) : launch_gemm<128, 3, EPI_F32, true>(ta, tb, p, st);
+            if (d.dual_a) return BN == 64 ? launch_gemm<64, 4, EPI_F32, true>(ta, tb, p, st, d.pdl) : launch_gemm<128, 3, EPI_F32, true>(ta, tb, p, st, d.pdl);
             return BN == 64 ? launch_gemm<64, 7, EPI_F32>(ta, tb, p, st) : launch_gemm<128, 5, EPI_F32>(ta, tb, p, st);
     }
     set_error("unknown epilogue %d", d.epilogue);

@@ -55,6 +55,9 @@ struct GemmDesc {
     // dual_a: A is a (hi, lo) bf16 pair, lo stored a_dual_stride elements after hi; D = (hi + lo) * W^T with W read once
     bool dual_a = false;
     int64_t a_dual_stride = 0;
+    // programmatic dependent launch: the kernel may start while its predecessor on the stream still runs; it prefetches its first
+    // weight tiles, then waits for the predecessor before touching A / the output (decode graph only)
+    bool pdl = false;
 };
 
 int gemm_bf16(const GemmDesc& d, cudaStream_t st);

@@ -75,3 +75,115 @@ def diarize(segmenter, extractor, int_samples, threshold=0.5, max_speakers=capi.
         for i, l in zip(ok, labels):
             speakers[i] = str(int(l)) if l > 0 else "?"
     return [dict(start=s["start"], end=s["end"], speaker=sp) for s, sp in zip(segs, speakers)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference src/utils.rs and src/transcribe.rs logic that consumes the boundary's results (pure integer / f64 arithmetic)
+# ---------------------------------------------------------------------------------------------------------------------
+def calculate_dtw_mem_size(num_samples):
+    """reference src/utils.rs:3-49: DTW working-set estimate handed to DtwParameters (accepted by wdr_context_params)."""
+    num_frames = (num_samples + 159) // 160
+    band = 96 if num_frames <= 15000 else 128 if num_frames <= 45000 else 160
+    total = 24 * 1024 * 1024 + num_frames * band * 4 * 4 + num_frames * 4
+    clamped = min(max(total, 24 * 1024 * 1024), 768 * 1024 * 1024)
+    align = 8 * 1024 * 1024
+    return (clamped + align - 1) & ~(align - 1)
+
+
+def cs_to_s(cs):
+    """reference src/utils.rs:57-59."""
+    return float(cs) * 0.01
+
+
+def is_whole_control_token(s):
+    """reference src/transcribe.rs:206-212: "[_BEG_]", "[_TT_320]", ... (how whisper.cpp / libwdr_b200 print special tokens)."""
+    t = s.strip("\0").strip()
+    if not (t.startswith("[_") and t.endswith("]")):
+        return False
+    inner = t[2:-1]
+    return bool(inner) and all(("A" <= c <= "Z") or ("0" <= c <= "9") or c == "_" for c in inner)
+
+
+def strip_embedded_control_markers(s):
+    """reference src/transcribe.rs:215-240."""
+    out, i = [], 0
+    while i < len(s):
+        if i + 1 < len(s) and s[i] == "[" and s[i + 1] == "_":
+            j = i + 2
+            while j < len(s) and s[j] != "]":
+                j += 1
+            if j < len(s) and is_whole_control_token(s[i:j + 1]):
+                i = j + 1
+                continue
+        out.append(s[i])
+        i += 1
+    return "".join(out)
+
+
+def get_token_timestamps(token_texts, token_data):
+    """reference src/transcribe.rs:242-320 on one segment: token_texts[i] = to_str_lossy(), token_data[i] has .p .t0 .t1 .t_dtw
+    (centiseconds; t_dtw < 0 = no DTW anchor).  Returns [dict(text, start, end, probability)] in seconds relative to the buffer."""
+    toks = []
+    for raw, td in zip(token_texts, token_data):
+        if is_whole_control_token(raw):
+            continue
+        clean = strip_embedded_control_markers(raw)
+        if not clean.strip("\0").strip():
+            continue
+        toks.append(dict(text=clean, p=float(td.p), t0=cs_to_s(td.t0), t1=cs_to_s(td.t1), anchor=cs_to_s(td.t_dtw) if td.t_dtw >= 0 else None))
+    spans = []
+    for i, t in enumerate(toks):
+        a_prev = toks[i - 1]["anchor"] if i > 0 else None
+        a_here = t["anchor"]
+        a_next = toks[i + 1]["anchor"] if i + 1 < len(toks) else None
+        start = 0.5 * (a_prev + a_here) if (a_prev is not None and a_here is not None) else t["t0"]
+        end = 0.5 * (a_here + a_next) if (a_here is not None and a_next is not None) else t["t1"]
+        spans.append(dict(text=t["text"], start=start, end=end, probability=t["p"]))
+    return spans
+
+
+def interpolate_word_timestamps(line, start, end):
+    """reference src/transcribe.rs:171-203 (translate task: token timings no longer align with the words)."""
+    dur = max(end - start, 0.0)
+    if dur <= 0.0:
+        return []
+    tokens = [t for t in line.split() if t.strip("\0").strip()]
+    if not tokens:
+        return []
+    weights = [max(sum(1 for c in t if c.isalnum()), 1) for t in tokens]
+    total = sum(weights)
+    out, acc = [], 0
+    for i, tok in enumerate(tokens):
+        t0 = start + (acc / total) * dur
+        t1 = end if i + 1 == len(tokens) else start + ((acc + weights[i]) / total) * dur
+        acc += weights[i]
+        out.append(dict(text=tok, start=t0, end=t1, probability=None))
+    return out
+
+
+def assemble_segments(state_segments, base_offset, segments_out, translated=False):
+    """reference src/transcribe.rs:397-459 for the segments of one state.full call (State.segments() dicts): trimmed text, absolute
+    word timestamps (base_offset = SpeechSegment.start + user offset), bounds from the first / last word, and the clipping of the
+    previous segment's end (and its last word) to the new segment's start.  Appends to segments_out and returns it."""
+    for seg in state_segments:
+        text = seg["text"].lstrip()
+        approx_start = base_offset + cs_to_s(seg["t0"])
+        approx_end = base_offset + cs_to_s(seg["t1"])
+        if translated:
+            words = interpolate_word_timestamps(text, approx_start, approx_end)
+        else:
+            words = get_token_timestamps(seg["token_text"], seg["tokens"])
+            for w in words:
+                w["start"] += base_offset
+                w["end"] += base_offset
+        seg_start = words[0]["start"] if words else approx_start
+        seg_end = words[-1]["end"] if words else approx_end
+        if segments_out:
+            last = segments_out[-1]
+            if last["end"] > seg_start:
+                last["end"] = seg_start
+            if last["words"]:
+                if last["words"][-1]["end"] > last["end"]:
+                    last["words"][-1]["end"] = last["end"]
+        segments_out.append(dict(start=seg_start, end=seg_end, text=text, words=words or None, speaker_id=None))
+    return segments_out
