@@ -216,3 +216,30 @@ def test_full_sequential_60s_matches_oracle(wdr, oracle):
     enc_st.close()
     st.close()
     ctx.close()
+
+
+def test_full_batch_more_than_one_decode_group(wdr):
+    """130 windows = two decode groups (128 + 2): chunk order, per-chunk info and results equal the same windows decoded in
+    smaller calls; empty (n_valid = 0) and very short windows yield no segment."""
+    B = 130
+    base = [synth_audio(2000 + b, 30.0) for b in range(2)]
+    pcm = np.zeros((B, 480000), np.int16)
+    for b in range(B):
+        pcm[b] = np.roll(base[b % 2], 104729 * (b // 2))
+    nv = np.full(B, 480000, np.int32)
+    nv[0] = 0
+    nv[64] = 1200   # 75 ms: below whisper_full's 100 ms minimum
+    nv[129] = 160000
+    ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    segs = st.full_batch(pcm, nv)
+    chunks = [s["chunk"] for s in segs]
+    assert chunks == sorted(chunks) and 0 not in chunks and 64 not in chunks and 129 in chunks and 128 in chunks
+    info = [st.chunk_info(b) for b in range(B)]
+    assert info[0]["n_segments"] == 0 and info[64]["n_segments"] == 0
+    key = lambda s: (s["t0"], s["t1"], s["text"], [(t.id, t.t0, t.t1, t.t_dtw) for t in s["tokens"]])
+    tail = st.full_batch(pcm[126:], nv[126:])
+    want = [key(s) for s in segs if s["chunk"] >= 126]
+    assert [key(s) for s in tail] == want and [s["chunk"] for s in tail] == [c - 126 for c in chunks if c >= 126]
+    st.close()
+    ctx.close()

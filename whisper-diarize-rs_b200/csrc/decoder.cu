@@ -251,7 +251,8 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
 
 // cross-attention of one (head, window): q from the cross-query GEMM partials; K_c/V_c rows are 64 bf16 (128 B) at row
 // stride 2d.  8 lanes x 16 B cover one row; a warp covers 4 rows per load, the CTA (8 warps) 32 rows.
-__global__ void __launch_bounds__(256)
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)
 dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
                       const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                       const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
@@ -892,7 +893,11 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         if ((rc = skinny_gemm(ws.h, B, e.w_cq, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
         {
             ProfScope ps(prof, KC_DEC_CROSS, st);
-            WDR_CUDA_TRY(launch_kernel(dec_cross_attn_kernel, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
+            // register budget capped for 6 resident CTAs per SM (40 registers): measured 1900 ms of decode vs 1930 ms at 5 (48
+            // registers); 8 (32 registers) spills and is much slower.  A single-pass online-softmax variant that streams K_c and
+            // V_c rows together was tried and is slower (2070 ms): its per-iteration max -> exp -> FMA chain keeps fewer loads in
+            // flight than the two independent passes do.
+            WDR_CUDA_TRY(launch_kernel(dec_cross_attn_kernel<6>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
                                        (int64_t)ws.cap_B * d, capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T, ws.aw_A, pos_ptr, pos,
                                        win, t_limit));
             WDR_LAUNCH_CHECK();
