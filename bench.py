@@ -211,7 +211,20 @@ def run_diarize(args):
     out = {}
 
     def step():
-        out["r"] = H.diarize(seg, emb, pcm_pin.numpy(), 0.5, w.SIZE_MAX, "leader")
+        if world == 1:
+            out["r"] = H.diarize(seg, emb, pcm_pin.numpy(), 0.5, w.SIZE_MAX, "leader")
+            return
+        # N > 1: every rank holds one 10 min shard of a (world x 10 min) recording; segments and embeddings are local, the
+        # embeddings are all-gathered (NCCL over NVLink: the path's one exchange step) and clustered globally on every rank
+        segs_l = seg.get_segments(pcm_pin.numpy())
+        off_l = np.zeros(len(segs_l) + 1, np.int64)
+        for i, sg_ in enumerate(segs_l):
+            off_l[i + 1] = off_l[i] + len(sg_["samples"])
+        cat_l = np.concatenate([sg_["samples"] for sg_ in segs_l]).astype(np.int16) if len(segs_l) else np.zeros(0, np.int16)
+        E_l, st_l = emb.compute_batch(cat_l, off_l)
+        E_all = w.dist.allgather_embeddings(E_l[st_l == 0])
+        out["r"] = w.cluster_leader(w.cosine_matrix(E_all), 0.5) if len(E_all) else np.zeros(0, np.int32)
+        out["n_global"] = int(len(E_all))
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,7 +279,8 @@ def run_diarize(args):
                                        "embeddings (bf16 tcgen05 GEMMs) + cosine matrix + leader scan (BASELINE configs[3])",
                            "windows": int(w.load().wdr_seg_n_windows(len(pcm))), "segments": len(segs), "embedded": int(len(ok)),
                            "speakers_leader": int(lab.max()) if len(lab) else 0, "clusters_agglomerative": int(agg.max()) if len(agg) else 0,
-                           "l2": "each step streams the whole recording's activations (> 126 MB L2)"},
+                           "l2": "each step streams the whole recording's activations (> 126 MB L2)",
+                           "exchange": None if world == 1 else f"all-gather of {out.get('n_global')} x 256 fp32 embeddings per step (NCCL), global leader scan on every rank"},
                 "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm.nbytes + cat.nbytes), "d2h_bytes_per_step": int(E.nbytes + 60 * 589 * 7 * 4),
                         "api": "host.diarize: wdr_seg_get_segments + wdr_emb_compute_batch_i16 + wdr_cosine_matrix + wdr_cluster_leader (host pointers)"},
                 "gpu_launches": int(launches), "clocks": clocks, "stages": stages,

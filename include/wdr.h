@@ -265,6 +265,10 @@ int32_t wdr_full_get_token_id_from_state(wdr_state* state, int i_segment, int i_
 const char* wdr_full_get_token_text_from_state(wdr_context* ctx, wdr_state* state, int i_segment, int i_token);  /* to_str_lossy(), :257 */
 wdr_token_data wdr_full_get_token_data_from_state(wdr_state* state, int i_segment, int i_token);                /* token_data(), :272 */
 int wdr_full_lang_id_from_state(wdr_state* state);                                         /* full_lang_id_from_state(), :393 */
+/* language = "auto" (or detect_language) on a multilingual model: whisper_lang_auto_detect — [SOT] decoded against the buffer's
+ * first window, arg-max over the language tokens.  In a batch call every 30 s buffer is detected on its own (each is its own
+ * state.full); this returns buffer i's language, wdr_full_lang_id_from_state the first one's. */
+int wdr_full_get_chunk_lang_id_from_state(wdr_state* state, int i_chunk);
 const char* wdr_lang_str(int id);                                                          /* whisper_rs::get_lang_str, :394 */
 int wdr_lang_id(const char* lang);                                                         /* whisper_lang_id */
 const char* wdr_token_to_str(wdr_context* ctx, int32_t token);                             /* whisper_token_to_str */

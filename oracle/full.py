@@ -30,7 +30,17 @@ def n_len_org(n_samples):
     return 1 + (n_samples + 200 - 400) // 160
 
 
-def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10):
+def detect_language(dec, enc_out):
+    """whisper_lang_auto_detect: decode [SOT] at position 0 against the window, arg-max over the language tokens."""
+    nv = dec.a["n_vocab"]
+    v = V.special_ids(nv)
+    dec.set_audio(enc_out)
+    lg = dec.step(v["sot"], 0)
+    n_l = v["translate"] - v["lang0"]
+    return int(np.argmax(lg[v["lang0"]: v["lang0"] + n_l]))
+
+
+def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10, lang_id=0):
     """dec: native.Decoder; enc_out [1500, d] (encoder output for this window); pcm_f32: the window's samples (<= 480000).
     Returns dict(segments=[dict(t0, t1, text, tokens=[TokenData])], seek_delta, no_speech_prob, margins, ...)."""
     nv = dec.a["n_vocab"]
@@ -40,7 +50,7 @@ def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_mi
     if seek_end < seek + delta_min or seek + delta_min >= seek_end:
         return out
     dec.set_audio(enc_out)
-    r = dec.decode_window(prompt_tokens(nv), seek, seek_end, True, delta_min)
+    r = dec.decode_window(prompt_tokens(nv, lang_id), seek, seek_end, True, delta_min)
     out.update(r)
     toks = r["tokens"]
     if r["failed"]:
@@ -65,7 +75,7 @@ def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_mi
             n_frames = min(3000, seek_delta, seek_end - seek)
             n_audio = n_frames // 2
             text_ids = [t.id for t in toks if t.id < v["eot"]]
-            seq, sot_len = dtw_sequence(nv, text_ids)
+            seq, sot_len = dtw_sequence(nv, text_ids, lang_id)
             aheads = W.ALIGNMENT_HEADS[dec.arch]
             w = dec.dtw_attention(seq, aheads, n_audio)
             cost = native.dtw_cost(w, sot_len, 7)

@@ -139,6 +139,8 @@ def test_unsupported_params_fail_loudly(wdr):
     with pytest.raises(wdr.WdrError):
         st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2))
     with pytest.raises(wdr.WdrError):
+        st.full(np.zeros(16000, np.int16), st.full_params(language="xx"))
+    with pytest.raises(wdr.WdrError):
         st.full(np.zeros(16000, np.int16), st.full_params(language="auto"))
     st.close()
     ctx.close()
@@ -241,5 +243,52 @@ def test_full_batch_more_than_one_decode_group(wdr):
     tail = st.full_batch(pcm[126:], nv[126:])
     want = [key(s) for s in segs if s["chunk"] >= 126]
     assert [key(s) for s in tail] == want and [s["chunk"] for s in tail] == [c - 126 for c in chunks if c >= 126]
+    st.close()
+    ctx.close()
+
+
+def test_language_auto_detect(wdr, oracle):
+    """language = "auto" on a multilingual model (whisper_lang_auto_detect, reference src/transcribe.rs:391-395): every buffer of a
+    batch call is detected on its own; the detected id, the prompt built from it and the decode equal the oracle's.  On an
+    English-only model the call fails as whisper.cpp's does; detect_language returns after the detection."""
+    from oracle import weights as W, full
+    arch = "tiny"
+    w = W.whisper_weights(arch, seed=1234)
+    B = 3
+    pcm = np.zeros((B, 480000), np.int16)
+    nv = np.array([480000, 300000, 480000], np.int32)
+    for b in range(B):
+        a = synth_audio(2100 + b, nv[b] / 16000.0)
+        pcm[b, : len(a)] = a[: nv[b]]
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    hid = st.encode_chunks(pcm, nv)
+    segs = st.full_batch(pcm, nv, st.full_params(language="auto"))
+    by_chunk = {}
+    for s in segs:
+        by_chunk.setdefault(s["chunk"], []).append(s)
+    dec = oracle.Decoder(arch, W.pack_decoder(arch, w), bf16=True)
+    for b in range(B):
+        lid = full.detect_language(dec, hid[b])
+        assert st.chunk_lang_id(b) == lid, (b, st.chunk_lang_id(b), lid)
+        x = pcm[b, : nv[b]].astype(np.float32) / np.float32(32768.0)
+        ref = full.full_window(dec, hid[b], x, lang_id=lid)
+        got = by_chunk.get(b, [])
+        assert len(got) == len(ref["segments"])
+        for g, r in zip(got, ref["segments"]):
+            assert [t.id for t in g["tokens"]] == [t.id for t in r["tokens"]]
+            assert [(t.t0, t.t1, t.t_dtw) for t in g["tokens"]] == [(t.t0, t.t1, t.t_dtw) for t in r["tokens"]]
+    assert st.lang_id() == st.chunk_lang_id(0)
+    assert wdr.lang_str(st.lang_id()) is not None
+    # detect only
+    assert st.full(pcm[0], st.full_params(language="auto", detect_language=1)) == []
+    assert st.lang_id() == full.detect_language(dec, hid[0])
+    dec.close()
+    st.close()
+    ctx.close()
+    ctx = wdr.Context("tiny.en", seed=1234)
+    st = ctx.create_state()
+    with pytest.raises(wdr.WdrError):
+        st.full(pcm[0], st.full_params(language="auto"))
     st.close()
     ctx.close()

@@ -148,6 +148,7 @@ def load():
     L.wdr_full_get_token_data_from_state.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.wdr_full_get_token_data_from_state.restype = TokenData
     L.wdr_full_lang_id_from_state.argtypes = [C.c_void_p]
+    L.wdr_full_get_chunk_lang_id_from_state.argtypes = [C.c_void_p, C.c_int]
     L.wdr_lang_str.argtypes = [C.c_int]
     L.wdr_lang_str.restype = C.c_char_p
     L.wdr_lang_id.argtypes = [C.c_char_p]
@@ -496,7 +497,7 @@ class State:
         return p
 
     def full(self, pcm, params=None):
-        """state.full on ONE buffer of <= 30 s (float32 in [-1,1) or int16)."""
+        """state.full on ONE buffer (float32 in [-1,1) or int16); longer than 30 s = whisper_full's sequential seek loop."""
         p = params if params is not None else self.full_params()
         pcm = np.asarray(pcm)
         if pcm.dtype == np.int16:
@@ -555,6 +556,10 @@ class State:
 
     def lang_id(self):
         return load().wdr_full_lang_id_from_state(self._h)
+
+    def chunk_lang_id(self, i):
+        """Language detected / used for buffer i of the last full call."""
+        return load().wdr_full_get_chunk_lang_id_from_state(self._h, int(i))
 
     def phase_ms(self):
         """Device time of the phases of the last full call (summed over groups and lanes) + greedy iterations run."""

@@ -191,7 +191,11 @@ static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int
     if (p.temperature != 0.0f || p.temperature_inc != 0.0f) { set_error("only temperature 0 without fallback is implemented (temperature %g, temperature_inc %g)", p.temperature, p.temperature_inc); return WDR_ERR_UNSUPPORTED; }
     if (!p.single_segment) { set_error("single_segment = 0 is not implemented (the crate always sets it, src/transcribe.rs:46)"); return WDR_ERR_UNSUPPORTED; }
     if (p.no_timestamps) { set_error("no_timestamps = 1 is not implemented"); return WDR_ERR_UNSUPPORTED; }
-    if (p.detect_language || (p.language && strcmp(p.language, "auto") == 0)) { set_error("language auto-detection is not implemented: pass the language"); return WDR_ERR_UNSUPPORTED; }
+    if (p.detect_language || (p.language && strcmp(p.language, "auto") == 0)) {  // whisper_lang_auto_detect: decided per buffer on the device
+        if (!ctx->arch.multilingual) { set_error("language auto-detection needs a multilingual model (whisper_lang_auto_detect fails the same way)"); return WDR_ERR_INVALID; }
+        *lang_id = -1;
+        return WDR_OK;
+    }
     if (p.initial_prompt && p.initial_prompt[0]) { set_error("initial_prompt needs a tokenizer file; pass prompt_tokens instead"); return WDR_ERR_UNSUPPORTED; }
     if (p.offset_ms || p.duration_ms || p.max_len || p.max_tokens || p.audio_ctx || p.suppress_nst) { set_error("offset/duration/max_len/max_tokens/audio_ctx/suppress_nst are not implemented"); return WDR_ERR_UNSUPPORTED; }
     if (p.translate && !ctx->arch.multilingual) { set_error("translate needs a multilingual model"); return WDR_ERR_INVALID; }
@@ -276,6 +280,34 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[1], s));
     if ((rc = decoder_cross_kv(ctx, ws, B, s, &st->prof)) != WDR_OK) return rc;
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[2], s));
+    // ---- language: given, or whisper_lang_auto_detect per buffer: decode [SOT] at position 0, arg-max over the language tokens ----
+    std::vector<int> lang(B, lang_id);
+    if (lang_id < 0) {
+        std::vector<int32_t> sq((size_t)B * kDecSeqCap, v.eot);
+        for (int b = 0; b < B; b++) sq[(size_t)b * kDecSeqCap] = v.sot;
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, sq.data(), sizeof(int32_t) * sq.size(), cudaMemcpyHostToDevice, s));
+        if ((rc = decoder_step(ctx, ws, B, 0, true, DEC_MODE_FORCED, s, &st->prof)) != WDR_OK) return rc;
+        const int n_l = v.translate - v.lang0;  // 99 languages, 100 for large-v3
+        std::vector<float> lg((size_t)B * n_l);
+        WDR_CUDA_TRY(cudaMemcpy2DAsync(lg.data(), sizeof(float) * n_l, ws.logits + v.lang0, sizeof(float) * ws.ldv, sizeof(float) * n_l, B, cudaMemcpyDeviceToHost, s));
+        WDR_CUDA_TRY(cudaStreamSynchronize(s));  // also fences the pageable staging vector sq
+        for (int b = 0; b < B; b++) {
+            int best = 0;
+            for (int i = 1; i < n_l; i++)
+                if (lg[(size_t)b * n_l + i] > lg[(size_t)b * n_l + best]) best = i;  // softmax over the language tokens is monotonic: same arg-max
+            lang[b] = best;
+        }
+        if (chunk0 == 0 || sw) st->lang_id = lang[0];
+    }
+    if (p.detect_language) {  // whisper_full returns right after the detection
+        for (int b = 0; b < B; b++) {
+            ChunkInfo ci;
+            memset(&ci, 0, sizeof(ci));
+            ci.lang_id = lang[b];
+            st->chunk_info.push_back(ci);
+        }
+        return WDR_OK;
+    }
     // ---- prompt + decoder state ----
     std::vector<int32_t> prompt;
     const int32_t* past = sw ? sw->prompt_past->data() : p.prompt_tokens;
@@ -286,8 +318,10 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         for (int i = n_past - n_take; i < n_past; i++) prompt.push_back(past[i]);
     }
     prompt.push_back(v.sot);
+    int lang_slot = -1;  // position of the language token in the prompt (per-window value)
     if (v.multilingual) {
-        prompt.push_back(v.lang0 + lang_id);
+        lang_slot = (int)prompt.size();
+        prompt.push_back(v.lang0 + std::max(lang[0], 0));
         prompt.push_back(p.translate ? v.translate : v.transcribe);
     }
     const int n_prompt = (int)prompt.size();
@@ -298,6 +332,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     int n_skip = 0;
     for (int b = 0; b < B; b++) {
         for (int i = 0; i < n_prompt; i++) seq[(size_t)b * kDecSeqCap + i] = prompt[i];
+        if (lang_slot >= 0) seq[(size_t)b * kDecSeqCap + lang_slot] = v.lang0 + lang[b];
         DecWinState w;
         memset(&w, 0, sizeof(w));
         w.seek_delta = 100 * 30;
@@ -390,6 +425,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         ChunkInfo ci;
         ci.seek_delta = w.seek_delta; ci.failed = w.failed; ci.completed = w.completed; ci.n_sampled = w.n_cur; ci.has_ts = w.has_ts;
         ci.result_len = w.result_len; ci.seek_end = w.seek_end; ci.n_segments = 0; ci.no_speech_prob = w.no_speech_prob;
+        ci.lang_id = lang[b];
         const int n_keep = w.failed ? w.n_cur : w.result_len;
         std::vector<wdr_token_data> cur(toks.begin() + (size_t)b * kDecMaxTokens, toks.begin() + (size_t)b * kDecMaxTokens + n_keep);
         double avg_logprob = -INFINITY;
@@ -422,7 +458,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                     pd.b = b;
                     pd.n_frames = std::min(std::min(100 * 30, w.seek_delta), w.seek_end - seek);
                     pd.dtw_seq.push_back(v.sot);
-                    if (v.multilingual) pd.dtw_seq.push_back(v.lang0 + lang_id);
+                    if (v.multilingual) pd.dtw_seq.push_back(v.lang0 + lang[b]);
                     pd.sot_len = (int)pd.dtw_seq.size();
                     pd.dtw_seq.push_back(v.not_);
                     for (auto& t : st->results[pd.seg].tokens)
@@ -608,6 +644,8 @@ static int full_sequential(wdr_context* ctx, wdr_state* st, const wdr_full_param
         rc = full_group<In>(ctx, st, p, lang_id, nullptr, 0, nullptr, 0, 1, &sw);
         if (rc != WDR_OK) return rc;
         const ChunkInfo& ci = st->chunk_info.back();
+        if (lang_id < 0) lang_id = ci.lang_id;  // whisper_full detects once, on the first window
+        if (p.detect_language) return WDR_OK;
         // prompt_past <- the part of it that went into this window's prompt + the window's result tokens (whisper_full)
         {
             std::vector<int32_t> next;
@@ -869,6 +907,10 @@ extern "C" int wdr_full_get_phase_ms(wdr_state* st, double* ms, int32_t* decode_
     return WDR_OK;
 }
 extern "C" int wdr_full_lang_id_from_state(wdr_state* st) { return st ? st->lang_id : -1; }
+extern "C" int wdr_full_get_chunk_lang_id_from_state(wdr_state* st, int i) {
+    if (!st || i < 0 || i >= (int)st->chunk_info.size()) { set_error("chunk index out of range"); return -1; }
+    return st->chunk_info[i].lang_id;
+}
 extern "C" const char* wdr_lang_str(int id) { return (id >= 0 && id < 100) ? kLangs[id] : nullptr; }
 extern "C" int wdr_lang_id(const char* lang) { return lang_id_from_str(lang); }
 extern "C" const char* wdr_token_to_str(wdr_context* ctx, int32_t token) {

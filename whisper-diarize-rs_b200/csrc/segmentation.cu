@@ -236,7 +236,7 @@ extern "C" wdr_seg* wdr_seg_init(const char* path, uint64_t seed, int device) {
     w.n2b = m->mem.upload(S("norm2.bias", 60, 0.0f, 0.1f));
     // Recurrent / head matrices are drawn 2.5x / 2x / 6x wider than PyTorch's default init and the "no speaker" class gets a
     // +1.5 bias: with default-init scales a random PyanNet's output is constant in time (no segment is ever emitted); with these
-    // the speech state machine flips a few times per window, so get_segments has real work (oracle/pyannet.py: same constants).
+    // the speech state machine flips a few times per window, so get_segments has real work (the CPU checker uses the same constants).
     const float sl = (float)(1.0 / sqrt(128.0)), slw = (float)(2.5 / sqrt(128.0));
     for (int l = 0; l < 4; l++) {
         const int n_in = l == 0 ? 60 : 256;

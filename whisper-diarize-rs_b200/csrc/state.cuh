@@ -20,6 +20,7 @@ struct ResultSegment {
 struct ChunkInfo {
     int seek_delta, failed, completed, n_sampled, has_ts, result_len, seek_end, n_segments;
     float no_speech_prob;
+    int lang_id;
 };
 // staging / scratch of the full pipeline (full.cu)
 struct FullScratch {
