@@ -1,0 +1,67 @@
+"""GPU suite: the crate-shaped flow `Engine::transcribe_audio` -> `run_transcription_pipeline` (reference src/engine.rs:65-200,
+src/transcribe.rs:323-535) driven through the C ABI by whisper-diarize-rs_b200/host.py, in its three modes: whole file (one
+SpeechSegment, whisper_full's sequential loop), Silero VAD segments, pyannote segmentation + speaker ids."""
+import numpy as np
+import pytest
+
+from conftest import synth_audio
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_segments(segs, t_max):
+    last_end = 0.0
+    for s in segs:
+        assert 0.0 <= s["start"] <= s["end"] <= t_max + 1e-6
+        assert s["start"] >= last_end - 1e-9, "segments must not overlap after clipping"
+        last_end = s["end"]
+        if s["words"]:
+            assert s["start"] == s["words"][0]["start"]
+            for w in s["words"]:  # (a clipped segment's last word may end before it starts: the crate clips only the end, :447-455)
+                assert not w["text"].startswith("[_")
+
+
+def test_transcribe_audio_three_modes(wdr):
+    from wdr_b200 import host as H
+    pcm = synth_audio(71, 42.0, n_speakers=2)
+    ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    # 1. whole file: one SpeechSegment of 42 s -> sequential mode inside state.full
+    segs, lang, mask = H.transcribe_audio(st, pcm)
+    assert lang == "en" and mask is None and len(segs) >= 2
+    _check_segments(segs, 42.0 + 30.0)
+    direct = st.full(pcm)
+    assert [s["text"] for s in segs] == [d["text"].lstrip() for d in direct]
+    # 2. VAD segments
+    vad = wdr.VadContext(seed=1234)
+    segs_v, _, mask_v = H.transcribe_audio(st, pcm, enable_vad=True, vad=vad)
+    assert mask_v is not None
+    _, speech = H.vad_get_segments(vad, pcm)
+    assert len(segs_v) <= sum(1 for _ in speech) * 2 + 2
+    for s in segs_v:
+        assert any(sp["start"] - 1e-6 <= s["start"] for sp in speech)
+    _check_segments(segs_v, 42.0 + 30.0)
+    # 3. diarize: pyannote segments + speaker ids ("1", "2", ... or "?")
+    seg_m = wdr.Segmenter(seed=1234)
+    emb = wdr.EmbeddingExtractor(seed=1234)
+    segs_d, _, _ = H.transcribe_audio(st, pcm, enable_diarize=True, segmenter=seg_m, extractor=emb, max_speakers=2, carry_prompt=False)
+    assert segs_d and all(s["speaker_id"] in ("1", "2", "?") for s in segs_d)
+    # the speaker of a speech segment equals the manual EmbeddingManager scan over the same segments
+    speech_d = seg_m.get_segments(pcm)
+    mgr = wdr.EmbeddingManager(2)
+    want = {}
+    for sp in speech_d:
+        got = st.full(sp["samples"])
+        if not got:
+            continue
+        try:
+            sid = mgr.assign(emb.compute(sp["samples"]), 0.5)
+            want[round(sp["start"], 6)] = str(sid) if sid else "?"
+        except wdr.WdrError:
+            want[round(sp["start"], 6)] = "?"
+    mgr.close()
+    assert sorted(set(s["speaker_id"] for s in segs_d)) == sorted(set(want.values()))
+    for m in (vad, seg_m, emb):
+        m.close()
+    st.close()
+    ctx.close()

@@ -187,3 +187,74 @@ def assemble_segments(state_segments, base_offset, segments_out, translated=Fals
                     last["words"][-1]["end"] = last["end"]
         segments_out.append(dict(start=seg_start, end=seg_end, text=text, words=words or None, speaker_id=None))
     return segments_out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Engine::transcribe_audio / run_transcription_pipeline (reference src/engine.rs:65-200, src/transcribe.rs:323-535)
+# ---------------------------------------------------------------------------------------------------------------------
+def run_transcription_pipeline(state, speech_segments, params=None, extractor=None, threshold=0.5, max_speakers=capi.SIZE_MAX,
+                               user_offset=0.0, carry_prompt=True, translated=False):
+    """reference src/transcribe.rs:323-535 over the C ABI: for every SpeechSegment dict(start, end, samples int16) in order —
+    `state.full` on its samples (one buffer; > 30 s runs whisper_full's own seek loop), segments -> words (get_token_timestamps),
+    absolute times (base_offset = segment.start + user offset), overlap clipping against the previous segment, and — with an
+    EmbeddingExtractor — the speaker of the SPEECH segment's samples through an EmbeddingManager (:461-497; "?" when the embedding
+    fails).  The crate feeds the previous segment's text back as `initial_prompt` (:383-386, :502); text prompts need a tokenizer
+    file, so the carried context crosses the C ABI as the previous segment's token ids (`prompt_tokens`), same effect.
+    Returns (segments [dict(start, end, text, words, speaker_id)], detected_lang)."""
+    mgr = capi.EmbeddingManager(max_speakers) if extractor is not None else None
+    out, previous_ids, detected = [], None, None
+    for sp in speech_segments:
+        p = params if params is not None else state.full_params()
+        keep = None
+        if carry_prompt and previous_ids:
+            keep = np.ascontiguousarray(np.array(previous_ids, np.int32))
+            p.prompt_tokens = keep.ctypes.data_as(capi.i32p)
+            p.prompt_n_tokens = len(keep)
+        else:
+            p.prompt_tokens = None
+            p.prompt_n_tokens = 0
+        segs = state.full(np.asarray(sp["samples"], np.int16), p)                      # :389
+        del keep
+        if detected is None:
+            detected = capi.lang_str(state.lang_id())                                 # :391-395
+        n_before = len(out)
+        assemble_segments(segs, sp["start"] + user_offset, out, translated)          # :397-459
+        speaker = None
+        if extractor is not None and segs:                                            # :461-497
+            try:
+                emb = extractor.compute(sp["samples"])
+                sid = mgr.assign(emb, threshold)
+                speaker = str(sid) if sid else "?"
+            except capi.WdrError:
+                speaker = "?"
+        ids = []
+        for s in segs:
+            ids += [int(t.id) for t in s["tokens"]]
+        for s in out[n_before:]:
+            s["speaker_id"] = speaker
+        if segs:
+            eot = 50257 if state.ctx.dims.n_vocab >= 51865 else 50256
+            previous_ids = [i for i in ids if i < eot]                                # text of the last call (:502), as token ids
+    if mgr is not None:
+        mgr.close()
+    return out, detected
+
+
+def transcribe_audio(state, int_samples, enable_vad=False, enable_diarize=False, vad=None, segmenter=None, extractor=None,
+                     threshold=0.5, max_speakers=None, params=None, carry_prompt=True):
+    """reference src/engine.rs:65-200 after `read_wav`: choose the speech segments (pyannote segmentation when diarizing, Silero VAD
+    segments when enabled, else ONE segment holding the whole file), run the pipeline, return (segments, detected_lang, vad_mask).
+    Formatting (`process_segments`) and translation stay in the crate."""
+    int_samples = np.asarray(int_samples, np.int16)
+    mask = None
+    if enable_diarize:                                                                # :88-122
+        cap = capi.SIZE_MAX if not max_speakers else max_speakers                     # Some(0) | None => usize::MAX
+        speech = [dict(start=s["start"], end=s["end"], samples=s["samples"]) for s in segmenter.get_segments(int_samples)]
+        segs, lang = run_transcription_pipeline(state, speech, params, extractor, threshold, cap, carry_prompt=carry_prompt)
+    elif enable_vad:                                                                  # :123-140
+        mask, speech = vad_get_segments(vad, int_samples)
+        segs, lang = run_transcription_pipeline(state, speech, params, carry_prompt=carry_prompt)
+    else:                                                                             # :141-147
+        speech = [dict(start=0.0, end=len(int_samples) / 16000.0, samples=int_samples)]
+        segs, lang = run_transcription_pipeline(state, speech, params, carry_prompt=carry_prompt)
+    return segs, lang, mask
