@@ -397,7 +397,15 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     WDR_REQUIRE((reinterpret_cast<uintptr_t>(d.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.W) & 15) == 0, "operands must be 16-byte aligned");
     WDR_REQUIRE(d.ldc % 8 == 0, "ldc must be a multiple of 8");
     if (d.epilogue == EPI_QKV_BF16) WDR_REQUIRE(d.out_t && d.n_split % 32 == 0, "QKV epilogue needs out_t and n_split % 32 == 0");
-    const int BN = d.bn == 64 ? 64 : 128;
+    int BN = d.bn == 64 ? 64 : 128;
+    // Wide tiles for the big encoder-side GEMMs: a 128 x 128 tile needs 32 KB of operands per 256 tensor-clocks (128 B/clk per SM,
+    // at the L2 -> SM limit, measured 64-71 % of the sustained bf16 peak); 128 x 256 needs 48 KB per 512 clocks (96 B/clk).
+    static const bool wide_ok = getenv("WDR_GEMM_NO_BN256") == nullptr;
+    if (wide_ok && BN == 128 && !d.dual_a && d.split_k == 1 && d.N % 256 == 0 &&
+        (int64_t)((d.rows_per_batch + kBM - 1) / kBM) * d.n_batch * (d.N / 256) >= 2 * num_sms() &&
+        (d.epilogue == EPI_BIAS_BF16 || d.epilogue == EPI_BIAS_GELU_BF16 || d.epilogue == EPI_BIAS_RESID_F32 || d.epilogue == EPI_QKV_BF16 ||
+         d.epilogue == EPI_BIAS_GELU_POS_F32))
+        BN = 256;
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
     if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
     else if (d.split_k > 1 || d.bn == 64 || d.dual_a) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 / dual-A are plain fp32-partial GEMMs (EPI_F32, no bias)");
@@ -440,6 +448,16 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.resid_bf16 = d.resid_bf16;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
+    if (BN == 256) {
+        switch (d.epilogue) {
+            case EPI_BIAS_BF16: return launch_gemm<256, 4, EPI_BIAS_BF16>(ta, tb, p, st);
+            case EPI_BIAS_GELU_BF16: return launch_gemm<256, 4, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
+            case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<256, 4, EPI_BIAS_RESID_F32>(ta, tb, p, st);
+            case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<256, 4, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
+            case EPI_QKV_BF16: return launch_gemm<256, 4, EPI_QKV_BF16>(ta, tb, p, st);
+            default: break;
+        }
+    }
     switch (d.epilogue) {
         case EPI_BIAS_BF16: return launch_gemm<128, 5, EPI_BIAS_BF16>(ta, tb, p, st);
         case EPI_BIAS_GELU_BF16: return launch_gemm<128, 5, EPI_BIAS_GELU_BF16>(ta, tb, p, st);
