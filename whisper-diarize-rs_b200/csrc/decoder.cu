@@ -275,9 +275,10 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
     float q8[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) q8[j] = q[g * 8 + j];
-    const __nv_bfloat16* Kb = ckv + (int64_t)b * kT * 2 * d + hh * 64 + g * 8;
-    const __nv_bfloat16* Vb = Kb + d;
-    const int64_t rs = 2 * (int64_t)d;
+    // head-major cross cache: [(window, head)][K | V][1500][64] — both blocks of a CTA are contiguous 192 KB streams
+    const __nv_bfloat16* Kb = ckv + ((int64_t)b * gridDim.x + hh) * 2 * kT * 64 + g * 8;
+    const __nv_bfloat16* Vb = Kb + kT * 64;
+    const int64_t rs = 64;
     // ---- scores ----
     float mx = -INFINITY;
     for (int t0 = warp * 4 + r; t0 < kT; t0 += 128) {
@@ -479,9 +480,9 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
     }
     for (int e = tid; e < kDtwpQB * 4; e += 256) p[(e >> 2) * kDtwpPStride + kT + (e & 3)] = 0.0f;
     __syncthreads();
-    const __nv_bfloat16* Kb = ckv + (int64_t)b * kT * 2 * d + hh * 64;
-    const __nv_bfloat16* Vb = Kb + d;
-    const int64_t rs = 2 * (int64_t)d;
+    const __nv_bfloat16* Kb = ckv + ((int64_t)b * gridDim.y + hh) * 2 * kT * 64;
+    const __nv_bfloat16* Vb = Kb + kT * 64;
+    const int64_t rs = 64;
     // ---- scores ----
     for (int t = tid; t < kT; t += 256) {
         float k[64];
@@ -786,7 +787,7 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
         GemmDesc g;
         g.A = ws.enc_bf16; g.a_row_stride = d; g.rows_per_batch = B * kT; g.n_batch = 1;
         g.W = e.w_ckv; g.ldw = d; g.N = 2 * d; g.K = d;
-        g.epilogue = EPI_BIAS_BF16; g.out = ws.ckv[l]; g.ldc = 2 * d; g.bias = e.b_ckv;
+        g.epilogue = EPI_HEADS_BF16; g.out = ws.ckv[l]; g.ldc = 2 * d; g.bias = e.b_ckv; g.group_rows = kT;
         ProfScope ps(prof, KC_GEMM, st);
         int rc = gemm_bf16(g, st);
         if (rc != WDR_OK) return rc;

@@ -32,7 +32,7 @@ struct DecoderWorkspace {
     int d = 0, n_layer = 0, n_head = 0;
     int64_t ldv = 0;                   // logits row stride (n_vocab rounded up to 8)
     __nv_bfloat16* enc_bf16 = nullptr; // [B][1500][d]   ln_post output, the cross-KV GEMM's A operand
-    std::vector<__nv_bfloat16*> ckv;   // per layer [B*1500][2d]  (key | value), bf16
+    std::vector<__nv_bfloat16*> ckv;   // per layer [B][H][K | V][1500][64] bf16: head-major, each (window, head) block contiguous
     float* sk = nullptr;               // [L][B][448][d]  self-attention keys / values, fp32
     float* sv = nullptr;
     float* x = nullptr;                // [B][d]  residual stream

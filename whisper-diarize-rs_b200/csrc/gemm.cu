@@ -44,6 +44,7 @@ struct GemmParams {
     int64_t ldt;
     int64_t t_batch_stride;
     int n_split;
+    int group_rows;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -279,6 +280,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32 + row) * p.ldc + n;
                             *reinterpret_cast<uint2*>(o) = whi;
                             *reinterpret_cast<uint2*>(o + p.split_stride) = wlo;
+                        } else if (EPI == EPI_HEADS_BF16) {
+                            const int gi = rib / p.group_rows, t = rib - gi * p.group_rows;
+                            const int half_n = p.N >> 1, sel = n >= half_n, nn = n - sel * half_n;
+                            const int64_t o = ((((int64_t)gi * (half_n >> 6) + (nn >> 6)) * 2 + sel) * p.group_rows + t) * 64 + (nn & 63);
+                            uint2 w;
+                            w.x = pack_bf16(v.x, v.y);
+                            w.y = pack_bf16(v.z, v.w);
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o) = w;
                         } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16 || EPI == EPI_BIAS_RELU_BF16 ||
                                    EPI == EPI_BIAS_ADD_RELU_BF16) {
                             if (EPI == EPI_BIAS_ADD_RELU_BF16) {
@@ -404,7 +413,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     if (wide_ok && BN == 128 && !d.dual_a && d.split_k == 1 && d.N % 256 == 0 &&
         (int64_t)((d.rows_per_batch + kBM - 1) / kBM) * d.n_batch * (d.N / 256) >= 2 * num_sms() &&
         (d.epilogue == EPI_BIAS_BF16 || d.epilogue == EPI_BIAS_GELU_BF16 || d.epilogue == EPI_BIAS_RESID_F32 || d.epilogue == EPI_QKV_BF16 ||
-         d.epilogue == EPI_BIAS_GELU_POS_F32))
+         d.epilogue == EPI_BIAS_GELU_POS_F32 || d.epilogue == EPI_HEADS_BF16))
         BN = 256;
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
     if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
@@ -447,6 +456,8 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.c_batch_stride = d.c_batch_stride > 0 ? d.c_batch_stride : (int64_t)d.rows_per_batch * d.ldc; p.resid = d.resid; p.pos = d.pos;
     p.resid_bf16 = d.resid_bf16;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
+    p.group_rows = d.group_rows;
+    if (d.epilogue == EPI_HEADS_BF16) WDR_REQUIRE(d.group_rows > 0 && d.n_batch == 1 && d.N % 128 == 0, "EPI_HEADS_BF16 needs group_rows, one batch and N = 2 * heads * 64");
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     if (BN == 256) {
         switch (d.epilogue) {
@@ -455,6 +466,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
             case EPI_BIAS_RESID_F32: WDR_REQUIRE(d.resid, "resid missing"); return launch_gemm<256, 4, EPI_BIAS_RESID_F32>(ta, tb, p, st);
             case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<256, 4, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
             case EPI_QKV_BF16: return launch_gemm<256, 4, EPI_QKV_BF16>(ta, tb, p, st);
+            case EPI_HEADS_BF16: return launch_gemm<256, 4, EPI_HEADS_BF16>(ta, tb, p, st);
             default: break;
         }
     }
@@ -465,6 +477,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         case EPI_BIAS_GELU_POS_F32: WDR_REQUIRE(d.pos, "pos missing"); return launch_gemm<128, 5, EPI_BIAS_GELU_POS_F32>(ta, tb, p, st);
         case EPI_QKV_BF16: return launch_gemm<128, 5, EPI_QKV_BF16>(ta, tb, p, st);
         case EPI_BIAS_GELU_SPLIT: return launch_gemm<64, 4, EPI_BIAS_GELU_SPLIT, true>(ta, tb, p, st, d.pdl);
+        case EPI_HEADS_BF16: return launch_gemm<128, 5, EPI_HEADS_BF16>(ta, tb, p, st);
         case EPI_BIAS_RELU_BF16: return launch_gemm<128, 5, EPI_BIAS_RELU_BF16>(ta, tb, p, st);
         case EPI_BIAS_ADD_RELU_BF16: WDR_REQUIRE(d.resid_bf16, "resid_bf16 missing"); return launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16>(ta, tb, p, st);
         case EPI_F32:

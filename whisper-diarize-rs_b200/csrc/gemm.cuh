@@ -16,6 +16,8 @@ enum GemmEpilogue {
     EPI_BIAS_GELU_SPLIT = 6,    // v = gelu_exact(acc + bias) stored as a (hi, lo) bf16 pair: out[.] = hi, out[. + split_stride] = lo (decoder fc1)
     EPI_BIAS_RELU_BF16 = 7,     // out_bf16 = relu(acc + bias)                                  (ResNet34 conv + folded BN + ReLU)
     EPI_BIAS_ADD_RELU_BF16 = 8, // out_bf16 = relu(acc + bias + resid_bf16[row][n])             (BasicBlock tail; resid_bf16 has the output's layout)
+    EPI_HEADS_BF16 = 9,         // out_bf16 = acc + bias, stored head-major: row = g*group_rows + t, n = s*(N/2) + h*64 + c  ->
+                                // out[((g*H + h)*2 + s)*group_rows + t][c]  (decoder cross K|V: each (window, head) K and V block contiguous)
 };
 
 // D[M x N] = A[M x K] * W[N x K]^T.  A rows are organised as n_batch groups of rows_per_batch rows (row r of
@@ -47,6 +49,7 @@ struct GemmDesc {
     int64_t ldt = 0;
     int64_t t_batch_stride = 0;  // column distance between batches in out_t; 0 = rows_per_batch
     int n_split = 0;
+    int group_rows = 0;  // EPI_HEADS_BF16: rows per group (1500 positions per window)
     // weight-streaming (decode) GEMMs: bn = 64 halves the tile width and split_k > 1 cuts K so that >= 148 CTAs stream W;
     // both require EPI_F32 without bias — split s writes its fp32 partial to out + s*split_stride (consumer sums, in order)
     int bn = 128;
