@@ -181,21 +181,23 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     pos = load_pos(pos_ptr, pos);
     if (win && (win[b].completed | win[b].failed)) return;
     if (t_limit && pos >= t_limit[b]) return;
-    float* K = sk + (int64_t)b * kDecSeqCap * d + hh * 64;
-    float* V = sv + (int64_t)b * kDecSeqCap * d + hh * 64;
+    // head-major self cache: [window][head][448][64] fp32 — the positions of one (window, head) are one contiguous stream
+    const int n_heads = d >> 6;
+    float* K = sk + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
+    float* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
     float* q = qs[warp];
     float* p = ps[warp];
 #pragma unroll
     for (int e = lane; e < 64; e += 32) {
         const int64_t base = (int64_t)b * 3 * d + hh * 64 + e;
         q[e] = part_sum(part, n_splits, split_stride, base) + b_qkv[hh * 64 + e];
-        K[(int64_t)pos * d + e] = part_sum(part, n_splits, split_stride, base + d) + b_qkv[d + hh * 64 + e];
-        V[(int64_t)pos * d + e] = part_sum(part, n_splits, split_stride, base + 2 * d) + b_qkv[2 * d + hh * 64 + e];
+        K[(int64_t)pos * 64 + e] = part_sum(part, n_splits, split_stride, base + d) + b_qkv[d + hh * 64 + e];
+        V[(int64_t)pos * 64 + e] = part_sum(part, n_splits, split_stride, base + 2 * d) + b_qkv[2 * d + hh * 64 + e];
     }
     __syncwarp();
     float mx = -INFINITY;
     for (int t = lane; t <= pos; t += 32) {
-        const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)t * d);
+        const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)t * 64);
         const float4* qv = reinterpret_cast<const float4*>(q);
         float4 f[16];
 #pragma unroll
@@ -230,8 +232,8 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
         float v0[8], v1[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            v0[k] = vc[(int64_t)(t + k) * d];
-            v1[k] = vc[(int64_t)(t + k) * d + 32];
+            v0[k] = vc[(int64_t)(t + k) * 64];
+            v1[k] = vc[(int64_t)(t + k) * 64 + 32];
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -242,8 +244,8 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     }
     for (; t <= pos; t++) {
         const float pt = p[t] * inv;
-        a0 = fmaf(pt, vc[(int64_t)t * d], a0);
-        a1 = fmaf(pt, vc[(int64_t)t * d + 32], a1);
+        a0 = fmaf(pt, vc[(int64_t)t * 64], a0);
+        a1 = fmaf(pt, vc[(int64_t)t * 64 + 32], a1);
     }
     store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane, a0);
     store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane + 32, a1);
