@@ -48,6 +48,12 @@ int ensure_device(int device);
         }                                        \
     } while (0)
 
+// Block cache behind DevBuf (core.cu): cudaMalloc / cudaFree of the host-pointer entry points' temporaries showed erratic
+// 10-400 ms stalls per call on the B200 boxes, so released blocks are kept (per device, bucketed by size) and handed out again.
+void* devbuf_acquire(size_t bytes);   // nullptr on allocation failure (last error set by cudaMalloc)
+void devbuf_release(void* p);         // synchronises the device first (what cudaFree did implicitly), then caches the block
+void devbuf_trim();                   // frees every cached block (called when a context / model is destroyed)
+
 // RAII device buffer for the host-pointer entry points.
 template <typename T>
 struct DevBuf {
@@ -56,10 +62,12 @@ struct DevBuf {
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { if (p) cudaFree(p); }
+    ~DevBuf() { if (p) devbuf_release(p); }
     cudaError_t alloc(size_t count) {
         n = count;
-        return cudaMalloc(reinterpret_cast<void**>(&p), (count ? count : 1) * sizeof(T));
+        if (p) { devbuf_release(p); p = nullptr; }
+        p = reinterpret_cast<T*>(devbuf_acquire((count ? count : 1) * sizeof(T)));
+        return p ? cudaSuccess : cudaErrorMemoryAllocation;
     }
 };
 

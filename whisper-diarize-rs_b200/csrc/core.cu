@@ -2,6 +2,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <mutex>
+#include <vector>
 #include "common.cuh"
 
 namespace wdr {
@@ -32,6 +33,75 @@ void log_msg(int level, const char* fmt, ...) {
     g_log_cb(level, buf, g_log_ud);
 }
 
+// ---- DevBuf block cache ----
+namespace {
+struct CachedBlock { void* p; size_t bytes; int dev; };
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache_free;                 // released blocks
+std::vector<CachedBlock> g_cache_live;                 // blocks handed out (to recover their size on release)
+size_t g_cache_free_bytes = 0;
+constexpr size_t kCacheMaxBytes = (size_t)16 << 30;    // beyond this, released blocks really go back to the driver
+}  // namespace
+
+void* devbuf_acquire(size_t bytes) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t want = (bytes + 255) & ~(size_t)255;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        int best = -1;
+        for (int i = 0; i < (int)g_cache_free.size(); i++) {
+            const CachedBlock& b = g_cache_free[i];
+            if (b.dev == dev && b.bytes >= want && b.bytes <= 2 * want + 4096 && (best < 0 || b.bytes < g_cache_free[best].bytes)) best = i;
+        }
+        if (best >= 0) {
+            CachedBlock b = g_cache_free[best];
+            g_cache_free.erase(g_cache_free.begin() + best);
+            g_cache_free_bytes -= b.bytes;
+            g_cache_live.push_back(b);
+            return b.p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        devbuf_trim();  // give the cached blocks back and retry once
+        cudaGetLastError();
+        if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_cache_live.push_back({p, want, dev});
+    return p;
+}
+
+void devbuf_release(void* p) {
+    if (!p) return;
+    cudaDeviceSynchronize();  // cudaFree's implicit guarantee: nothing in flight still touches the block
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (int i = 0; i < (int)g_cache_live.size(); i++)
+        if (g_cache_live[i].p == p) {
+            CachedBlock b = g_cache_live[i];
+            g_cache_live.erase(g_cache_live.begin() + i);
+            if (g_cache_free_bytes + b.bytes > kCacheMaxBytes) { cudaFree(b.p); return; }
+            g_cache_free.push_back(b);
+            g_cache_free_bytes += b.bytes;
+            return;
+        }
+    cudaFree(p);  // not ours (cannot happen through DevBuf)
+}
+
+void devbuf_trim() {
+    std::vector<CachedBlock> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        blocks.swap(g_cache_free);
+        g_cache_free_bytes = 0;
+    }
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& b : blocks) { cudaSetDevice(b.dev); cudaFree(b.p); }
+    cudaSetDevice(cur);
+}
+
 int ensure_device(int device) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -49,6 +119,26 @@ int ensure_device(int device) {
         if (e != cudaSuccess) {
             set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
             return WDR_ERR_CUDA;
+        }
+    }
+    // Stream-ordered allocations (cudaMallocAsync in fbank / DTW helpers) come from the device's default pool, whose release
+    // threshold is 0: every synchronisation hands the freed memory back to the OS and the next call maps it again — measured as
+    // erratic 0.2-3 s stalls per call.  Keep freed blocks cached in the pool instead (once per device).
+    {
+        static std::mutex mu;
+        static bool done[64] = {false};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!done[dev]) {
+                cudaMemPool_t pool;
+                if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                    uint64_t keep = UINT64_MAX;
+                    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                }
+                cudaGetLastError();
+                done[dev] = true;
+            }
         }
     }
     return WDR_OK;

@@ -119,6 +119,8 @@ struct wdr_emb {
     // workspaces (grown on demand)
     __nv_bfloat16 *act[4] = {nullptr, nullptr, nullptr, nullptr}, *col = nullptr;
     size_t act_cap = 0, col_cap = 0;
+    wdr::DevArena io;       // host-pointer API: staged PCM + result embeddings
+    wdr::DevArena scratch;  // per-group features, level tables, pooled statistics, embeddings (grow-only)
     double conv_flops = 0.0;  // of the last call (algorithmic, 2*M*N*K)
 };
 
@@ -193,7 +195,8 @@ static int emb_grow(T** p, size_t* cap, size_t need) {
 }
 
 // One forward batch: feats (device, [frames][80], segment s at frame feat_off[s]) -> out_dev[n][256]
-static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t>& feat_off, float* out_dev, cudaStream_t st) {
+static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t>& feat_off, float* out_dev, int32_t* tab_T, int64_t* tab_off,
+                       float* stats_buf, cudaStream_t st) {
     const int n = (int)feat_off.size() - 1;
     EmbLevel lv[4];
     for (int r = 0; r < 4; r++) {
@@ -210,17 +213,13 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     }
     WDR_REQUIRE(lv[0].rows() < (int64_t)1 << 31, "embedding batch too large");
     // level tables + feat offsets on the device
-    DevBuf<int32_t> d_T;
-    DevBuf<int64_t> d_off;
-    WDR_CUDA_TRY(d_T.alloc((size_t)4 * n));
-    WDR_CUDA_TRY(d_off.alloc((size_t)5 * (n + 1)));
     for (int r = 0; r < 4; r++) {
-        lv[r].d_T = d_T.p + (size_t)r * n;
-        lv[r].d_off = d_off.p + (size_t)r * (n + 1);
+        lv[r].d_T = tab_T + (size_t)r * n;
+        lv[r].d_off = tab_off + (size_t)r * (n + 1);
         WDR_CUDA_TRY(cudaMemcpyAsync(lv[r].d_T, lv[r].T.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, st));
         WDR_CUDA_TRY(cudaMemcpyAsync(lv[r].d_off, lv[r].off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
     }
-    int64_t* d_feat_off = d_off.p + (size_t)4 * (n + 1);
+    int64_t* d_feat_off = tab_off + (size_t)4 * (n + 1);
     WDR_CUDA_TRY(cudaMemcpyAsync(d_feat_off, feat_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
     // workspaces
     const size_t rows0 = (size_t)lv[0].rows();
@@ -276,12 +275,10 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
         std::swap(x, x2);
         level = lout;
     }
-    DevBuf<float> stats;
-    WDR_CUDA_TRY(stats.alloc((size_t)n * kEmbPooled));
-    emb_tstp_kernel<<<dim3(10, n), 256, 0, st>>>(x, lv[3].d_T, lv[3].d_off, stats.p);
+    emb_tstp_kernel<<<dim3(10, n), 256, 0, st>>>(x, lv[3].d_T, lv[3].d_off, stats_buf);
     WDR_LAUNCH_CHECK();
-    if ((rc = sgemm_nt(stats.p, kEmbPooled, m->lin_w, kEmbPooled, m->lin_b, out_dev, kEmbDim, n, kEmbDim, kEmbPooled, NN_ACT_NONE, st)) != WDR_OK) return rc;
-    WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the level tables and stats die with this frame
+    if ((rc = sgemm_nt(stats_buf, kEmbPooled, m->lin_w, kEmbPooled, m->lin_b, out_dev, kEmbDim, n, kEmbDim, kEmbPooled, NN_ACT_NONE, st)) != WDR_OK) return rc;
+    WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the host-side level tables (async H2D sources) die with this frame
     m->conv_flops += flops;
     return WDR_OK;
 }
@@ -341,6 +338,8 @@ extern "C" void wdr_emb_free(wdr_emb* m) {
     cudaFree(m->lin_b);
     for (int i = 0; i < 4; i++) cudaFree(m->act[i]);
     cudaFree(m->col);
+    m->scratch.release();
+    m->io.release();
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -381,25 +380,31 @@ static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector
             if (k > 0 && seg_off[s] != seg_off[live[i0 + k - 1] + 1]) contiguous = false;
             fo[k + 1] = fo[k] + wdr_fbank_frames((int)(seg_off[s + 1] - seg_off[s]));
         }
-        DevBuf<float> feats, emb;
-        DevBuf<int64_t> d_so, d_fo;
-        WDR_CUDA_TRY(feats.alloc((size_t)frames * kEmbBins));
-        WDR_CUDA_TRY(emb.alloc((size_t)g * kEmbDim));
-        WDR_CUDA_TRY(d_fo.alloc((size_t)g + 1));
-        WDR_CUDA_TRY(cudaMemcpyAsync(d_fo.p, fo.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
+        struct { float* p; } feats, emb;
+        struct { int64_t* p; } d_so, d_fo;
         int rc;
+        {
+            DevArena& A = m->scratch;
+            const size_t need = DevArena::padded(sizeof(float) * frames * kEmbBins) + DevArena::padded(sizeof(float) * g * kEmbDim) +
+                                2 * DevArena::padded(sizeof(int64_t) * (g + 2)) + DevArena::padded(sizeof(int32_t) * 4 * g) +
+                                DevArena::padded(sizeof(int64_t) * 5 * (g + 1)) + DevArena::padded(sizeof(float) * g * kEmbPooled);
+            if ((rc = A.reserve(need)) != WDR_OK) return rc;
+            feats.p = A.take<float>((size_t)frames * kEmbBins);
+            emb.p = A.take<float>((size_t)g * kEmbDim);
+            d_fo.p = A.take<int64_t>((size_t)g + 2);
+            d_so.p = A.take<int64_t>((size_t)g + 2);
+        }
+        WDR_CUDA_TRY(cudaMemcpyAsync(d_fo.p, fo.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
         if (contiguous) {
             std::vector<int64_t> s2((size_t)g + 1);
             for (int k = 0; k < g; k++) s2[k] = seg_off[live[i0 + k]];
             s2[g] = seg_off[live[i0 + g - 1] + 1];
-            WDR_CUDA_TRY(d_so.alloc((size_t)g + 1));
             WDR_CUDA_TRY(cudaMemcpyAsync(d_so.p, s2.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
             WDR_CUDA_TRY(cudaStreamSynchronize(st));
             rc = fbank_run(pcm_dev, d_so.p, d_fo.p, s2, kEmbBins, 1, feats.p, st);
             if (rc != WDR_OK) return rc;
         } else {
             // one fbank launch per contiguous run
-            WDR_CUDA_TRY(d_so.alloc((size_t)g + 2));
             int k0 = 0;
             while (k0 < g) {
                 int k1 = k0 + 1;
@@ -415,7 +420,13 @@ static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector
                 k0 = k1;
             }
         }
-        rc = emb_forward(m, feats.p, fo, emb.p, st);
+        {
+            int32_t* tab_T = m->scratch.take<int32_t>((size_t)4 * g);
+            int64_t* tab_off = m->scratch.take<int64_t>((size_t)5 * (g + 1));
+            float* stats_buf = m->scratch.take<float>((size_t)g * kEmbPooled);
+            WDR_REQUIRE(tab_T && tab_off && stats_buf, "embedding scratch under-reserved");
+            rc = emb_forward(m, feats.p, fo, emb.p, tab_T, tab_off, stats_buf, st);
+        }
         if (rc != WDR_OK) return rc;
         for (int k = 0; k < g; k++)
             WDR_CUDA_TRY(cudaMemcpyAsync(out_dev + (size_t)live[i0 + k] * kEmbDim, emb.p + (size_t)k * kEmbDim, sizeof(float) * kEmbDim, cudaMemcpyDeviceToDevice, st));
@@ -436,10 +447,11 @@ extern "C" int wdr_emb_compute_batch_i16(wdr_emb* m, const int16_t* pcm, const i
     for (int s = 0; s < n_segments; s++) WDR_REQUIRE(so[s + 1] >= so[s], "segment offsets must ascend");
     const int64_t base = so[0], total = so[n_segments] - base;
     for (auto& v : so) v -= base;
-    DevBuf<int16_t> d_pcm;
-    DevBuf<float> d_out;
-    WDR_CUDA_TRY(d_pcm.alloc((size_t)std::max<int64_t>(total, 1)));
-    WDR_CUDA_TRY(d_out.alloc((size_t)n_segments * kEmbDim));
+    struct { int16_t* p; } d_pcm;
+    struct { float* p; } d_out;
+    if ((rc = m->io.reserve(DevArena::padded(sizeof(int16_t) * (size_t)std::max<int64_t>(total, 1)) + DevArena::padded(sizeof(float) * (size_t)n_segments * kEmbDim))) != WDR_OK) return rc;
+    d_pcm.p = m->io.take<int16_t>((size_t)std::max<int64_t>(total, 1));
+    d_out.p = m->io.take<float>((size_t)n_segments * kEmbDim);
     WDR_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, sizeof(float) * (size_t)n_segments * kEmbDim, m->stream));
     WDR_CUDA_TRY(cudaMemcpyAsync(d_pcm.p, pcm + base, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, m->stream));
     rc = emb_compute_dev(m, d_pcm.p, so, d_out.p, status, m->stream);

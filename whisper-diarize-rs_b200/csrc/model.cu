@@ -340,6 +340,7 @@ extern "C" void wdr_free(wdr_context* ctx) {
     if (ctx->mel) wdr_mel_free(ctx->mel);
     for (void* p : ctx->allocations) cudaFree(p);
     delete ctx;
+    wdr::devbuf_trim();  // temporaries cached behind the host-pointer entry points go back to the driver with the model
 }
 
 extern "C" int wdr_model_info(const wdr_context* ctx, wdr_model_dims* out) {

@@ -56,6 +56,29 @@ struct NnAllocs {
     }
 };
 
+// Grow-only device scratch: reserve() the total once per call, then take() typed sub-buffers (256-byte aligned).
+struct DevArena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0;
+    int reserve(size_t bytes) {
+        off = 0;
+        if (bytes <= cap) return WDR_OK;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        WDR_CUDA_TRY(cudaMalloc(reinterpret_cast<void**>(&base), bytes));
+        cap = bytes;
+        return WDR_OK;
+    }
+    static size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+    template <typename T>
+    T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += padded(count * sizeof(T));
+        return off <= cap ? p : nullptr;
+    }
+    void release() { if (base) cudaFree(base); base = nullptr; cap = off = 0; }
+};
+
 enum { NN_ACT_NONE = 0, NN_ACT_LEAKY = 1, NN_ACT_RELU = 2 };
 
 // C[M][N] = act(A[M][K] * B[N][K]^T + bias[N]);  64 x 64 tile, 256 threads, 4 x 4 outputs per thread, K step 16.

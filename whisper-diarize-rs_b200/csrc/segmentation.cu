@@ -200,6 +200,12 @@ struct wdr_seg {
     cudaStream_t stream = nullptr;
     SegWeights w;
     NnAllocs mem;
+    float* arena = nullptr;   // grow-only activation workspace of seg_forward (cudaMalloc / cudaFree of ~100 MB per call cost more
+    size_t arena_cap = 0;     // than the network itself)
+    int16_t* pcm_dev = nullptr;
+    size_t pcm_cap = 0;
+    float* scores_dev = nullptr;
+    size_t scores_cap = 0;
 };
 struct wdr_seg_result {
     std::vector<double> start, end;
@@ -280,7 +286,11 @@ extern "C" wdr_seg* wdr_seg_init(const char* path, uint64_t seed, int device) {
 extern "C" void wdr_seg_free(wdr_seg* m) {
     if (!m) return;
     cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
     m->mem.release();
+    cudaFree(m->arena);
+    cudaFree(m->pcm_dev);
+    cudaFree(m->scores_dev);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -291,19 +301,22 @@ extern "C" int wdr_seg_n_windows(int64_t n_samples) { return (int)((n_samples + 
 static int seg_forward(wdr_seg* m, const int16_t* pcm_dev, int64_t n_total, int W, float* scores_dev, cudaStream_t st) {
     const SegWeights& w = m->w;
     const int64_t R = (int64_t)W * kSegFrames;
-    DevBuf<float> wst, x0, st0, x1, st1, x2, st2, seqA, seqB, gates, y0, y1;
-    WDR_CUDA_TRY(wst.alloc(2 * W));
-    WDR_CUDA_TRY(x0.alloc((size_t)W * 80 * kP0));
-    WDR_CUDA_TRY(st0.alloc((size_t)W * 80 * 2));
-    WDR_CUDA_TRY(x1.alloc((size_t)W * 60 * kP1));
-    WDR_CUDA_TRY(st1.alloc((size_t)W * 60 * 2));
-    WDR_CUDA_TRY(x2.alloc((size_t)W * 60 * kP2));
-    WDR_CUDA_TRY(st2.alloc((size_t)W * 60 * 2));
-    WDR_CUDA_TRY(seqA.alloc((size_t)R * 256));
-    WDR_CUDA_TRY(seqB.alloc((size_t)R * 256));
-    WDR_CUDA_TRY(gates.alloc((size_t)R * 1024));
-    WDR_CUDA_TRY(y0.alloc((size_t)R * 128));
-    WDR_CUDA_TRY(y1.alloc((size_t)R * 128));
+    struct Sub { float* p; };
+    const size_t sizes[12] = {(size_t)2 * W, (size_t)W * 80 * kP0, (size_t)W * 80 * 2, (size_t)W * 60 * kP1, (size_t)W * 60 * 2, (size_t)W * 60 * kP2,
+                              (size_t)W * 60 * 2, (size_t)R * 256, (size_t)R * 256, (size_t)R * 1024, (size_t)R * 128, (size_t)R * 128};
+    size_t total = 0;
+    for (size_t n : sizes) total += (n + 63) & ~(size_t)63;
+    if (total > m->arena_cap) {
+        if (m->arena) cudaFree(m->arena);
+        m->arena = nullptr; m->arena_cap = 0;
+        WDR_CUDA_TRY(cudaMalloc(&m->arena, sizeof(float) * total));
+        m->arena_cap = total;
+    }
+    size_t off = 0;
+    int si = 0;
+    auto carve = [&]() { Sub b{m->arena + off}; off += (sizes[si++] + 63) & ~(size_t)63; return b; };
+    Sub wst = carve(), x0 = carve(), st0 = carve(), x1 = carve(), st1 = carve(), x2 = carve(), st2 = carve(), seqA = carve(), seqB = carve(),
+        gates = carve(), y0 = carve(), y1 = carve();
     wav_stats_kernel<<<W, 1024, 0, st>>>(pcm_dev, n_total, wst.p);
     WDR_LAUNCH_CHECK();
     sinc_conv_pool_kernel<<<dim3((kP0 + kSincTile - 1) / kSincTile, W), 256, kSincSmem, st>>>(pcm_dev, n_total, wst.p, w, x0.p);
@@ -334,8 +347,7 @@ static int seg_forward(wdr_seg* m, const int16_t* pcm_dev, int64_t n_total, int 
     if ((rc = sgemm_nt(y0.p, 128, w.l1w, 128, w.l1b, y1.p, 128, (int)R, 128, 128, NN_ACT_LEAKY, st)) != WDR_OK) return rc;
     classifier_kernel<<<(unsigned)((R + 7) / 8), 256, 0, st>>>(y1.p, w.cw, w.cb, R, scores_dev);
     WDR_LAUNCH_CHECK();
-    WDR_CUDA_TRY(cudaStreamSynchronize(st));  // DevBufs go out of scope
-    return WDR_OK;
+    return WDR_OK;  // asynchronous: the arena belongs to the model and the next call runs on the same stream
 }
 
 extern "C" int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, float* scores) {
@@ -345,10 +357,23 @@ extern "C" int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, flo
     if (rc != WDR_OK) return rc;
     const int W = wdr_seg_n_windows(n);
     if (W == 0) return 0;
-    DevBuf<int16_t> d_x;
-    DevBuf<float> d_s;
-    WDR_CUDA_TRY(d_x.alloc((size_t)n));
-    WDR_CUDA_TRY(d_s.alloc((size_t)W * kSegFrames * kSegClasses));
+    struct { int16_t* p; } d_x;
+    struct { float* p; } d_s;
+    if ((size_t)n > m->pcm_cap) {
+        if (m->pcm_dev) cudaFree(m->pcm_dev);
+        m->pcm_dev = nullptr; m->pcm_cap = 0;
+        WDR_CUDA_TRY(cudaMalloc(&m->pcm_dev, sizeof(int16_t) * (size_t)n));
+        m->pcm_cap = (size_t)n;
+    }
+    const size_t n_scores = (size_t)W * kSegFrames * kSegClasses;
+    if (n_scores > m->scores_cap) {
+        if (m->scores_dev) cudaFree(m->scores_dev);
+        m->scores_dev = nullptr; m->scores_cap = 0;
+        WDR_CUDA_TRY(cudaMalloc(&m->scores_dev, sizeof(float) * n_scores));
+        m->scores_cap = n_scores;
+    }
+    d_x.p = m->pcm_dev;
+    d_s.p = m->scores_dev;
     WDR_CUDA_TRY(cudaMemcpyAsync(d_x.p, pcm, sizeof(int16_t) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
     // windows are independent: process them in groups to bound the workspace (x0 alone is 1.7 MB per window)
     const int group = 64;
@@ -357,7 +382,8 @@ extern "C" int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, flo
         rc = seg_forward(m, d_x.p + (int64_t)w0 * kSegWindow, n - (int64_t)w0 * kSegWindow, nw, d_s.p + (size_t)w0 * kSegFrames * kSegClasses, m->stream);
         if (rc != WDR_OK) return rc;
     }
-    WDR_CUDA_TRY(cudaMemcpy(scores, d_s.p, sizeof(float) * (size_t)W * kSegFrames * kSegClasses, cudaMemcpyDeviceToHost));
+    WDR_CUDA_TRY(cudaMemcpyAsync(scores, d_s.p, sizeof(float) * n_scores, cudaMemcpyDeviceToHost, m->stream));
+    WDR_CUDA_TRY(cudaStreamSynchronize(m->stream));
     return W;
 }
 
