@@ -119,7 +119,18 @@ def clustering():
     np.savez_compressed(os.path.join(HERE, "clustering.npz"), emb=emb, S=S, agglomerative_thr05=np.array(labels, np.int32))
 
 
+def formatter():
+    """The reference's OWN fixture: /root/reference/segments.json is the output of `process_segments` that examples/test.rs wrote
+    (FormattingOverrides max_chars_per_line 20, max_lines 2; examples/test.rs:36-50).  Copied verbatim as data (cues with their
+    word timestamps) — the only artefact in the reference that pins anything near the hot path."""
+    import json
+    src = "/root/reference/segments.json"
+    cues = json.load(open(src))
+    json.dump(dict(source="tmoroney/whisper-diarize-rs segments.json (written by examples/test.rs)", overrides=dict(max_chars_per_line=20, max_lines=2),
+                   language="en", cues=cues), open(os.path.join(HERE, "formatter_segments.json"), "w"), indent=0)
+
+
 if __name__ == "__main__":
-    for fn in (mel, median_dtw, fbank, encoder, clustering):
+    for fn in (mel, median_dtw, fbank, encoder, clustering, formatter):
         fn()
         print("wrote", fn.__name__)

@@ -1,0 +1,99 @@
+"""CPU suite for SURVEY §8f row 1: the formatter that CONSUMES the library's output (reference src/formatting.rs), restated in
+whisper-diarize-rs_b200/formatting.py.
+
+* The reference's own unit test (src/formatting.rs:650-670, `basic_split`) restated.
+* The reference's own fixture `segments.json` (written by examples/test.rs through process_segments; committed verbatim as data under
+  tests/golden/formatter_segments.json): its cues are a fixed point of the formatter — flattening the cues' words (leading-space flags
+  recovered from each cue's own text) and formatting them again with the same overrides reproduces the cue boundaries, line breaks
+  and word lists.  5 of the 51 cues are not fixed points for reasons visible in the data: two contain a `<|endoftext|>` token whose
+  start lies AFTER its end, one holds a tiny word that was merged ("going to") and one an apostrophe continuation piece ("hasn" +
+  "'t") whose gap had already been closed by the first pass.
+* Known-answer tests for the byte-wise punctuation splitter, continuation merging, tiny-word clamping and the VAD silence oracle."""
+import importlib
+import json
+import os
+
+F = importlib.import_module("whisper-diarize-rs_b200.formatting")
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _w(text, start, end, p=None):
+    return dict(text=text, start=start, end=end, probability=p)
+
+
+def test_reference_basic_split():
+    cfg = F.default_config()
+    words = [("I", 0.00, 0.10), ("think", 0.10, 0.38), ("I", 0.50, 0.60), ("would", 0.60, 0.80), ("like", 0.80, 0.95), ("to.", 0.95, 1.10)]
+    seg = dict(start=0.0, end=1.1, text="", speaker_id=None, words=[_w(" " + t, a, b) for t, a, b in words])
+    cues = F.process_segments([seg], cfg)
+    assert cues and cues[0]["text"].startswith("I think")
+    cfg2 = dict(cfg, max_lines=2, max_chars_per_line=12)
+    cues2 = F.process_segments([seg], cfg2)
+    assert "\n" in cues2[0]["text"] and cues2[0]["text"].replace("\n", " ") == "I think I would like to."
+
+
+def test_segments_json_is_a_fixed_point():
+    g = json.load(open(os.path.join(G, "formatter_segments.json")))
+    ref = g["cues"]
+    words = []
+    for c in ref:
+        pos, txt = 0, c["text"]
+        for k, w in enumerate(c["words"]):
+            idx = txt.find(w["text"], pos)
+            assert idx >= 0
+            lead = idx > pos or k == 0  # a space / newline sat between the previous word and this one
+            pos = idx + len(w["text"])
+            words.append(_w((" " if lead else "") + w["text"], w["start"], w["end"], w["probability"]))
+    cfg = F.config_for_language(g["language"], g["overrides"])
+    out = F.process_segments([dict(start=0.0, end=0.0, text="", speaker_id=None, words=words)], cfg)
+    assert len(out) == len(ref) == 51
+    bad = []
+    for i, (a, b) in enumerate(zip(out, ref)):
+        same = (a["text"] == b["text"] and abs(a["start"] - b["start"]) < 2.5e-3 and abs(a["end"] - b["end"]) < 2.5e-3 and
+                [w["text"] for w in a["words"]] == [w["text"] for w in b["words"]])
+        if not same:
+            bad.append(i)
+    assert set(bad) <= {10, 23, 24, 38, 40}, bad
+    # every cue respects the 2-line cap, and the probabilities ride through untouched
+    assert all(c["text"].count("\n") <= 1 for c in out)
+    assert [w["probability"] for c in out for w in c["words"]][:20] == [w["probability"] for c in ref for w in c["words"]][:20]
+
+
+def test_split_trailing_punct_is_bytewise_ascii():
+    assert F.split_trailing_punct("word.") == ("word", ".")
+    assert F.split_trailing_punct(' end?!"') == (" end", '?!"')
+    assert F.split_trailing_punct("don't") == ("don't", "")
+    assert F.split_trailing_punct("...") == ("", "...")
+    assert F.split_trailing_punct("好。") == ("好。", "")  # the multi-byte members of the Rust list can never match a single byte
+    assert F.is_terminal_punct("。") and F.is_comma_like("、") and not F.is_terminal_punct(",")
+
+
+def test_merge_and_clamp():
+    cfg = F.default_config()
+    toks = [_w(" trans", 0.0, 0.3), _w("human", 0.3, 0.6), _w("ism", 0.61, 0.9), _w(",", 0.9, 0.9), _w(" a", 1.0, 1.02), _w(" b", 1.02, 1.5)]
+    cues = F.process_segments([dict(start=0, end=1.5, text="", speaker_id="1", words=toks)], cfg)
+    assert [w["text"] for w in cues[0]["words"]] == ["transhumanism,", "a b"]  # continuation pieces joined; the 20 ms word merged into the next
+    assert cues[0]["text"] == "transhumanism, a b" and cues[0]["speaker_id"] == "1"
+    assert F.round3(0.0005) == 0.001 and F.round3(2.3454999) == 2.345
+    # control-token-only / replacement-character tokens vanish
+    cues = F.process_segments([dict(start=0, end=1, text="", speaker_id=None, words=[_w("�", 0, 0.5), _w(" ok.", 0.5, 1.0)])], cfg)
+    assert cues[0]["text"] == "ok."
+
+
+def test_groups_split_on_terminal_punct_and_gaps():
+    cfg = F.default_config()
+    ws = [_w(" One.", 0, 0.5), _w(" Two", 0.5, 1.0), _w(" three", 1.6, 2.0), _w(" four", 2.0, 2.4)]
+    cues = F.process_segments([dict(start=0, end=2.4, text="", speaker_id=None, words=ws)], cfg)
+    assert [c["text"] for c in cues] == ["One.", "Two", "three four"]
+    # a segment without words falls back to its text
+    cues = F.process_segments([dict(start=1.0, end=2.0, text=" hello there", speaker_id=None, words=None)], cfg)
+    assert cues[0]["text"] == "hello there" and (cues[0]["start"], cues[0]["end"]) == (1.0, 2.0)
+
+
+def test_vad_mask_oracle_and_profiles():
+    o = F.VadMaskOracle([(2.0, 3.0), (0.5, 1.0), (4.0, 4.0)])
+    assert o.mask == [(0.5, 1.0), (2.0, 3.0)]
+    assert o.is_silence(1.0, 2.0) and not o.is_silence(0.9, 1.1) and o.is_silence(3.0, 2.0)
+    assert F.profile_for_lang("ja") == "CJK" and F.profile_for_lang("ar") == "RTL" and F.profile_for_lang("xx") == "Latin"
+    cfg = F.config_for_language("ja", dict(max_lines=2))
+    assert cfg["max_chars_per_line"] == 20 and cfg["insert_interword_space"] is False and cfg["max_lines"] == 2

@@ -32,10 +32,17 @@ def test_transcribe_audio_three_modes(wdr):
     _check_segments(segs, 42.0 + 30.0)
     direct = st.full(pcm)
     assert [s["text"] for s in segs] == [d["text"].lstrip() for d in direct]
+    # the consumer (reference src/formatting.rs via formatting.py): cues from the library's token spans
+    cues = H.format_cues(segs, lang, None, dict(max_lines=2))
+    assert cues and all(c["text"].count("\n") <= 1 and "[_" not in c["text"] and c["words"] for c in cues)
+    assert [c["start"] for c in cues] == sorted(c["start"] for c in cues)
+    n_chars = sum(len(w["text"]) for c in cues for w in c["words"])
+    assert n_chars == sum(len(w["text"].strip()) for s in segs for w in (s["words"] or []))  # nothing printable is lost or invented
     # 2. VAD segments
     vad = wdr.VadContext(seed=1234)
     segs_v, _, mask_v = H.transcribe_audio(st, pcm, enable_vad=True, vad=vad)
     assert mask_v is not None
+    assert H.format_cues(segs_v, "en", mask_v) is not None
     _, speech = H.vad_get_segments(vad, pcm)
     assert len(segs_v) <= sum(1 for _ in speech) * 2 + 2
     for s in segs_v:

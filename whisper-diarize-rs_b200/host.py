@@ -240,11 +240,19 @@ def run_transcription_pipeline(state, speech_segments, params=None, extractor=No
     return out, detected
 
 
+def format_cues(segments, lang, vad_mask=None, formatting_overrides=None):
+    """The tail of Engine::transcribe_audio (reference src/engine.rs:189-198): PostProcessConfig::for_language(effective_lang) +
+    overrides, process_segments with the VAD mask as the silence oracle (formatting.py restates src/formatting.rs)."""
+    from . import formatting as F
+    cfg = F.config_for_language(lang or "en", formatting_overrides)
+    return F.process_segments(segments, cfg, F.VadMaskOracle(vad_mask) if vad_mask is not None else None)
+
+
 def transcribe_audio(state, int_samples, enable_vad=False, enable_diarize=False, vad=None, segmenter=None, extractor=None,
                      threshold=0.5, max_speakers=None, params=None, carry_prompt=True):
     """reference src/engine.rs:65-200 after `read_wav`: choose the speech segments (pyannote segmentation when diarizing, Silero VAD
-    segments when enabled, else ONE segment holding the whole file), run the pipeline, return (segments, detected_lang, vad_mask).
-    Formatting (`process_segments`) and translation stay in the crate."""
+    segments when enabled, else ONE segment holding the whole file), run the pipeline, return (segments, detected_lang, vad_mask);
+    `format_cues` is the formatting tail (translation over HTTP stays in the crate)."""
     int_samples = np.asarray(int_samples, np.int16)
     mask = None
     if enable_diarize:                                                                # :88-122
