@@ -836,6 +836,7 @@ static int skinny_gemm(const __nv_bfloat16* A, int B, const __nv_bfloat16* W, in
     g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * K;
     pick_tile(K, N, &g.bn, &g.split_k);
     g.pdl = pdl;
+    g.w_kb_major = true;
     g.split_stride = (int64_t)B * N;
     if ((size_t)g.split_k * B * N > ws.part_elems) { set_error("decoder: split-K workspace too small"); return WDR_ERR_INVALID; }
     out->splits = g.split_k;
@@ -916,6 +917,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * d;
             g.split_stride = (int64_t)ws.cap_B * 4 * d;
             g.pdl = pdl;
+            g.w_kb_major = true;
             ProfScope ps(prof, KC_DEC_GEMM, st);
             if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
@@ -966,6 +968,7 @@ static int packed_gemm(const __nv_bfloat16* A, int64_t M, int64_t M_cap, const _
     g.W = W; g.ldw = K; g.N = N; g.K = K;
     g.epilogue = EPI_F32; g.out = out; g.ldc = N; g.bn = 128;
     g.dual_a = true; g.a_dual_stride = M_cap * K;
+    g.w_kb_major = true;
     ProfScope ps(prof, KC_DEC_GEMM, st);
     return gemm_bf16(g, st);
 }
@@ -1047,6 +1050,7 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
             g.epilogue = EPI_BIAS_GELU_SPLIT; g.out = pw.ff; g.ldc = 4 * d; g.bias = e.b_fc1; g.bn = 64;
             g.dual_a = true; g.a_dual_stride = Mc * d;
             g.split_stride = Mc * 4 * d;
+            g.w_kb_major = true;
             ProfScope ps(prof, KC_DEC_GEMM, st);
             if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }

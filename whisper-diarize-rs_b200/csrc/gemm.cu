@@ -45,6 +45,7 @@ struct GemmParams {
     int64_t t_batch_stride;
     int n_split;
     int group_rows;
+    int w_kb_major;  // B operand coordinates: (0, kb*N + n) instead of (kb*64, n)
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -131,7 +132,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 prefetched = min(STAGES, kb1 - kb0);
                 for (int i = 0; i < prefetched; i++) {
                     mbar_arrive_expect_tx(&bar_full[i], kAStage + kBBytes);
-                    tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], (kb0 + i) * kBK, n_tile * BN);
+                    if (p.w_kb_major) tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], 0, (kb0 + i) * p.N + n_tile * BN);
+                    else tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], (kb0 + i) * kBK, n_tile * BN);
                 }
             }
             pdl_wait();
@@ -150,7 +152,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
                     tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
                     if (DUAL) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
-                    if (!have_b) tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
+                    if (!have_b) {
+                        if (p.w_kb_major) tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], 0, kb * p.N + n_tile * BN);
+                        else tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
+                    }
                     if (++s == STAGES) { s = 0; ph ^= 1; }
                 }
             }
@@ -431,7 +436,14 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         int rc = make_tmap_bf16(&ta, d.A, 3, dims, str, box);
         if (rc != WDR_OK) return rc;
     }
-    {
+    if (d.w_kb_major) {
+        WDR_REQUIRE(d.K % kBK == 0 && d.ldw == d.K && d.kb_per_tap == 0, "kb-major weights need K %% 64 == 0 and a dense [N][K] source");
+        const uint64_t dims[2] = {(uint64_t)kBK, (uint64_t)(d.K / kBK) * (uint64_t)d.N};
+        const uint64_t str[1] = {(uint64_t)kBK * 2};
+        const uint32_t box[2] = {kBK, (uint32_t)BN};
+        int rc = make_tmap_bf16(&tb, d.W, 2, dims, str, box);
+        if (rc != WDR_OK) return rc;
+    } else {
         const uint64_t dims[2] = {(uint64_t)d.K, (uint64_t)d.N};
         const uint64_t str[1] = {(uint64_t)d.ldw * 2};
         const uint32_t box[2] = {kBK, (uint32_t)BN};
@@ -457,6 +469,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.resid_bf16 = d.resid_bf16;
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.group_rows = d.group_rows;
+    p.w_kb_major = d.w_kb_major ? 1 : 0;
     if (d.epilogue == EPI_HEADS_BF16) WDR_REQUIRE(d.group_rows > 0 && d.n_batch == 1 && d.N % 128 == 0, "EPI_HEADS_BF16 needs group_rows, one batch and N = 2 * heads * 64");
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     if (BN == 256) {

@@ -61,6 +61,8 @@ struct GemmDesc {
     // programmatic dependent launch: the kernel may start while its predecessor on the stream still runs; it prefetches its first
     // weight tiles, then waits for the predecessor before touching A / the output (decode graph only)
     bool pdl = false;
+    // W is k-block-major [K/64][N][64] (decoder weights, model.cu: to_kb_major): a tile's rows are contiguous for each k-block
+    bool w_kb_major = false;
 };
 
 int gemm_bf16(const GemmDesc& d, cudaStream_t st);

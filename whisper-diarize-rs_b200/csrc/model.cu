@@ -91,6 +91,20 @@ __global__ void synth_kernel(T* __restrict__ dst, int rows, int cols, int64_t ld
     }
 }
 
+// [N][K] row-major -> k-block-major [K/64][N][64]: for a fixed 64-wide k-block the rows of a weight tile are contiguous, so the
+// TMA box of a weight-streaming GEMM (BN rows x 128 B) is ONE contiguous BN*128-byte read instead of BN pieces at a K*2-byte stride.
+__global__ void kb_major_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K) {
+    const int64_t total = (int64_t)N * K / 8;  // 16-byte vectors
+    const int vec_per_kb = 8, num_kb = K / 64;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < total; v += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t o = v / vec_per_kb;            // (kb, n) pair index in the destination
+        const int c8 = (int)(v - o * vec_per_kb);
+        const int kb = (int)(o / N), n = (int)(o - (int64_t)kb * N);
+        reinterpret_cast<uint4*>(dst)[v] = reinterpret_cast<const uint4*>(src)[((int64_t)n * K + kb * 64) / 8 + c8];
+    }
+    (void)num_kb;
+}
+
 struct Builder {
     wdr_context* ctx;
     int rc = WDR_OK;
@@ -117,6 +131,18 @@ struct Builder {
         synth_kernel<T><<<blocks, 256>>>(dst, rows, cols, ld, tensor_key(ctx->seed, name), offset, scale, mode, cin, cpad);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) { set_error("synth kernel launch failed"); rc = WDR_ERR_CUDA; }
+    }
+    // in-place re-layout of a finished [N][K] matrix to k-block-major (decoder weights: every consumer is a weight-streaming GEMM)
+    void to_kb_major(__nv_bfloat16* w, int N, int K) {
+        if (rc != WDR_OK) return;
+        if (K % 64 != 0 || N % 8 != 0) { set_error("kb-major layout needs K %% 64 == 0"); rc = WDR_ERR_INVALID; return; }
+        __nv_bfloat16* tmp = nullptr;
+        if (cudaMalloc(&tmp, sizeof(__nv_bfloat16) * (size_t)N * K) != cudaSuccess) { set_error("weights: temporary for the kb-major layout"); rc = WDR_ERR_OOM; return; }
+        kb_major_kernel<<<148 * 8, 256>>>(w, tmp, N, K);
+        count_launch();
+        cudaMemcpy(w, tmp, sizeof(__nv_bfloat16) * (size_t)N * K, cudaMemcpyDeviceToDevice);
+        cudaFree(tmp);
+        if (cudaGetLastError() != cudaSuccess) { set_error("kb-major re-layout failed"); rc = WDR_ERR_CUDA; }
     }
     __nv_bfloat16* matrix(int rows, int cols, const std::string& name, float scale) {
         auto* p = alloc<__nv_bfloat16>((size_t)rows * cols);
@@ -230,6 +256,13 @@ static int build_weights(wdr_context* ctx) {
         e.b_fc1 = b.vec(4 * d, p + "mlp.0.bias", 0.0f, kBScale);
         e.w_fc2 = b.matrix(d, 4 * d, p + "mlp.2.weight", dec_out_scale);
         e.b_fc2 = b.vec(d, p + "mlp.2.bias", 0.0f, kBScale);
+        // the decode-time consumers of these six matrices are weight-streaming GEMMs (GemmDesc::w_kb_major)
+        b.to_kb_major(e.w_qkv, 3 * d, d);
+        b.to_kb_major(e.w_o, d, d);
+        b.to_kb_major(e.w_cq, d, d);
+        b.to_kb_major(e.w_co, d, d);
+        b.to_kb_major(e.w_fc1, 4 * d, d);
+        b.to_kb_major(e.w_fc2, d, 4 * d);
     }
     w.dec_ln_g = b.vec(d, "decoder.ln.weight", 1.0f, 0.1f);
     w.dec_ln_b = b.vec(d, "decoder.ln.bias", 0.0f, 0.1f);
