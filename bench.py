@@ -260,6 +260,38 @@ def run_diarize(args):
         raise SystemExit("diarize workload: the segmenter emitted no embeddable segment")
     t = time.perf_counter(); S = w.cosine_matrix(E[ok]); lab = w.cluster_leader(S, 0.5); agg = w.cluster_agglomerative(S, 0.5)
     stages["cosine_cluster_ms"] = (time.perf_counter() - t) * 1e3
+    # Kaldi fbank kernel alone on the recording's segments, device pointers, CUDA events on the launching stream (north-star: the
+    # mel / fbank kernels are quoted in HBM GB/s).  Algorithmic bytes: int16 samples in + 80 fp32 bins per frame out.
+    fb = {}
+    try:
+        live = [i for i in ok]
+        so = np.zeros(len(live) + 1, np.int64)
+        fo = np.zeros(len(live) + 1, np.int64)
+        for k, i in enumerate(live):
+            n_i = int(off[i + 1] - off[i])
+            so[k + 1] = so[k] + n_i
+            fo[k + 1] = fo[k] + (1 + (n_i - 400) // 160)
+        cat_live = np.concatenate([segs[i]["samples"] for i in live]).astype(np.int16)
+        d_pcm = torch.from_numpy(cat_live).cuda()
+        d_so, d_fo = torch.from_numpy(so).cuda(), torch.from_numpy(fo).cuda()
+        d_out = torch.empty(int(fo[-1]) * 80, device="cuda", dtype=torch.float32)
+        stream = torch.cuda.current_stream().cuda_stream
+        L = w.load()
+        call = lambda: L.wdr_kaldi_fbank_batch_i16_dev(d_pcm.data_ptr(), d_so.data_ptr(), d_fo.data_ptr(), len(live), int(fo[-1]), 80, 1, d_out.data_ptr(), stream)
+        for _ in range(3):
+            assert call() == 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_fb = e0.elapsed_time(e1) / 10
+        nbytes = cat_live.nbytes + int(fo[-1]) * 80 * 4
+        fb = {"ms": ms_fb, "frames": int(fo[-1]), "algorithmic_bytes": int(nbytes), "achieved_gbs": nbytes / (ms_fb / 1e3) / 1e9,
+              "note": "fbank + per-segment mean subtraction incl. the call's offset read-back; fp32 512-point FFT per frame: ALU-bound like the log-mel kernel"}
+    except Exception as ex:  # the bench line must not die on the auxiliary measurement
+        fb = {"error": str(ex)}
     if world > 1:
         tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -283,7 +315,7 @@ def run_diarize(args):
                            "exchange": None if world == 1 else f"all-gather of {out.get('n_global')} x 256 fp32 embeddings per step (NCCL), global leader scan on every rank"},
                 "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm.nbytes + cat.nbytes), "d2h_bytes_per_step": int(E.nbytes + 60 * 589 * 7 * 4),
                         "api": "host.diarize: wdr_seg_get_segments + wdr_emb_compute_batch_i16 + wdr_cosine_matrix + wdr_cluster_leader (host pointers)"},
-                "gpu_launches": int(launches), "clocks": clocks, "stages": stages,
+                "gpu_launches": int(launches), "clocks": clocks, "stages": stages, "fbank_kernel": fb,
                 "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05) in the ResNet34 embedding stage (whole stage incl. fbank, im2col, H2D/D2H)",
                              "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
                              "algorithmic_gflop_per_step": flops / 1e9}}
