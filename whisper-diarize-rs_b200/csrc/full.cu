@@ -734,7 +734,9 @@ static int full_range(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
 // Windows are independent (sharded mode) and every kernel's result for a window is independent of which other
 // windows share its launch, so the output is identical for any lane count.  Measured on B200 (large-v3, 120 windows): 2 lanes
 // are no faster than 1 — each lane's weight-streaming GEMMs still occupy every SM's shared memory and a half-full 128-row tile
-// costs what a full one does — so the default is ONE lane; the knob stays for many-small-window calls.
+// costs what a full one does — so the default is ONE lane; the knob stays for many-small-window calls.  A low-footprint
+// cross-attention for multi-lane calls (2 persistent CTAs per SM at 48 registers, so that the other lane's GEMM CTA fits next to
+// them) was measured as well: 2 lanes 2568 ms vs 2190 ms for one lane (each lane's decode 2085 vs 1700 ms), so it was dropped.
 static int default_lanes() {
     static const int n = [] {
         const char* e = getenv("WDR_LANES");
