@@ -292,3 +292,40 @@ def test_language_auto_detect(wdr, oracle):
         st.full(pcm[0], st.full_params(language="auto"))
     st.close()
     ctx.close()
+
+
+def test_progress_and_abort_callbacks(wdr):
+    """set_progress_callback_safe / set_abort_callback_safe (reference src/transcribe.rs:349-357): progress is reported per decode
+    group on the calling side and ends at 100; an abort callback that returns true ends the call with WDR_ERR_ABORTED and leaves
+    no partial result in the state (whisper-rs maps the non-zero return to an error, the crate drops the segment)."""
+    from wdr_b200 import capi
+    ctx = wdr.Context("tiny.en", seed=1234)
+    st = ctx.create_state()
+    pcm = np.zeros((3, 480000), np.int16)
+    for b in range(3):
+        pcm[b] = synth_audio(2000 + b, 30.0)
+    seen = []
+    p = st.full_params()
+    cb = capi.PROGRESS_CB(lambda c, s, pr, ud: seen.append(pr))
+    p.progress_callback = cb
+    segs = st.full_batch(pcm, None, p)
+    assert segs and seen and seen[-1] == 100 and seen == sorted(seen)
+    calls = []
+
+    def abort(ud):
+        calls.append(1)
+        return len(calls) >= 2
+
+    p2 = st.full_params()
+    ab = capi.ABORT_CB(abort)
+    p2.abort_callback = ab
+    with pytest.raises(wdr.WdrError) as e:
+        st.full_batch(pcm, None, p2)
+    assert e.value.code == -5 and len(calls) >= 2
+    # sequential mode reports progress per window
+    seen.clear()
+    long = np.concatenate([pcm[0], pcm[1][:160000]])
+    st.full(long, p)
+    assert len(seen) >= 2 and seen[-1] == 100
+    st.close()
+    ctx.close()
