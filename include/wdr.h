@@ -162,10 +162,16 @@ typedef struct wdr_model_dims {
     int64_t weight_bytes;
 } wdr_model_dims;
 wdr_context_params wdr_context_default_params(void);                                         /* whisper_context_default_params */
-/* whisper_init_from_file_with_params (WhisperContext::new_with_params, src/transcribe.rs:154).  path == NULL:
- * seeded weights of params.arch_name.  Returns NULL on failure, never aborts. */
+/* whisper_init_from_file_with_params (WhisperContext::new_with_params, src/transcribe.rs:154).  path: a whisper.cpp
+ * ggml-<model>.bin checkpoint (f32 / f16 tensors; names at src/model_manager.rs:162) — geometry, mel filterbank, token strings and
+ * weights come from the file, params.dtw_aheads_preset selects the alignment heads as the crate does by model name.  path == NULL:
+ * seeded synthetic weights of params.arch_name (no checkpoint exists offline).  Returns NULL on failure, never aborts. */
 wdr_context* wdr_init_from_file_with_params(const char* path, wdr_context_params params);
 void wdr_free(wdr_context* ctx);                                                             /* whisper_free */
+/* Header of a ggml-<model>.bin checkpoint without touching the GPU: hparams[11] = n_vocab, n_audio_ctx, n_audio_state,
+ * n_audio_head, n_audio_layer, n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels, ftype; tensor and token counts.
+ * (`path` in wdr_init_from_file_with_params: f32 / f16 checkpoints of the OpenAI geometries; quantised files are refused.) */
+int wdr_ggml_probe(const char* path, int32_t* hparams, int32_t* n_tensors, int32_t* n_tokens);
 int wdr_model_info(const wdr_context* ctx, wdr_model_dims* out);                             /* whisper_model_n_* getters */
 wdr_state* wdr_init_state(wdr_context* ctx);                 /* whisper_init_state (ctx.create_state(), src/transcribe.rs:335) */
 void wdr_free_state(wdr_state* state);                       /* whisper_free_state */

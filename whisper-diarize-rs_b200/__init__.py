@@ -14,7 +14,7 @@ from .capi import (  # noqa: F401
     MelFrontend, log_mel, median_filter, dtw_cost, dtw, dtw_batch_dev, kaldi_fbank, fbank_frames,
     signal_energy, convert_integer_to_float_audio, mel_n_len, gemm_bf16_dev,
     Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
-    FullParams, TokenData, lang_str, lang_id,
+    FullParams, TokenData, lang_str, lang_id, ggml_probe,
     VadContext, VadParams, vad_default_params, vad_segments_from_probs,
     Segmenter, seg_segments_from_scores, EmbeddingExtractor,
     EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,

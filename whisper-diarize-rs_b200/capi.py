@@ -117,6 +117,7 @@ def load():
     L.wdr_free.argtypes = [C.c_void_p]
     L.wdr_model_info.argtypes = [C.c_void_p, C.POINTER(ModelDims)]
     L.wdr_init_state.restype = C.c_void_p
+    L.wdr_ggml_probe.argtypes = [C.c_char_p, i32p, i32p, i32p]
     L.wdr_init_state.argtypes = [C.c_void_p]
     L.wdr_free_state.argtypes = [C.c_void_p]
     L.wdr_mel_filters.argtypes = [C.c_int, f32p]
@@ -393,7 +394,9 @@ DTW_PRESETS = {"tiny.en": 0, "tiny": 1, "base.en": 2, "base": 3, "small.en": 4, 
 class Context:
     """wdr_context: WhisperContext::new_with_params (reference src/transcribe.rs:89-166)."""
 
-    def __init__(self, arch_name, seed=1234, gpu_device=0, enable_dtw=False, flash_attn=False, dtw_mem_size=0):
+    def __init__(self, arch_name, seed=1234, gpu_device=0, enable_dtw=False, flash_attn=False, dtw_mem_size=0, model_path=None):
+        """arch_name: the model name the crate maps to a DTW preset (src/transcribe.rs:117-129).  model_path: a ggml-<model>.bin
+        checkpoint (None = seeded synthetic weights of `arch_name`)."""
         L = load()
         p = L.wdr_context_default_params()
         p.gpu_device = gpu_device
@@ -406,7 +409,7 @@ class Context:
             p.dtw_mem_size = dtw_mem_size
         else:
             p.flash_attn = int(flash_attn)
-        self._h = L.wdr_init_from_file_with_params(None, p)
+        self._h = L.wdr_init_from_file_with_params(model_path.encode() if model_path else None, p)
         if not self._h:
             raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, L.wdr_last_error().decode())
         self.arch_name = arch_name
@@ -588,6 +591,18 @@ class State:
 
 def encoder_attention_dev(qk_ptr, vt_ptr, ldt, n_chunks, T, n_head, d_model, out_ptr, stream=0):
     _check(load().wdr_encoder_attention_dev(qk_ptr, vt_ptr, ldt, n_chunks, T, n_head, d_model, out_ptr, stream))
+
+
+def ggml_probe(path):
+    """Header of a ggml checkpoint (no GPU needed): dict of the 11 hyper-parameters + n_tensors + n_tokens."""
+    hp = np.zeros(11, np.int32)
+    nt, nk = C.c_int32(0), C.c_int32(0)
+    _check(load().wdr_ggml_probe(path.encode(), _p(hp, i32p), C.byref(nt), C.byref(nk)))
+    keys = ["n_vocab", "n_audio_ctx", "n_audio_state", "n_audio_head", "n_audio_layer", "n_text_ctx", "n_text_state", "n_text_head",
+            "n_text_layer", "n_mels", "ftype"]
+    d = {k: int(v) for k, v in zip(keys, hp)}
+    d.update(n_tensors=int(nt.value), n_tokens=int(nk.value))
+    return d
 
 
 def lang_str(i):

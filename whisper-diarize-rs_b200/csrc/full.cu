@@ -175,6 +175,18 @@ static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t 
     }
 }
 
+// the context's vocabulary: special-token ids from n_vocab; text-token strings (and the " " token suppress_blank masks) from the
+// checkpoint when the context was loaded from a ggml file
+static Vocab ctx_vocab(const wdr_context* ctx) {
+    Vocab v = make_vocab(ctx->arch.n_vocab);
+    if (!ctx->file_tokens.empty()) {
+        v.file_tokens = &ctx->file_tokens;
+        for (int i = 0; i < (int)ctx->file_tokens.size() && i < v.eot; i++)
+            if (ctx->file_tokens[i] == " ") { v.space = i; break; }
+    }
+    return v;
+}
+
 static SampleParams make_sample_params(const Vocab& v, const wdr_full_params& p) {
     SampleParams sp;
     sp.n_vocab = v.n_vocab; sp.eot = v.eot; sp.sot = v.sot; sp.translate = v.translate; sp.transcribe = v.transcribe; sp.solm = v.solm;
@@ -244,7 +256,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     FullScratch& fs = st->full;
     DecoderWorkspace& ws = st->dec;
     const WhisperArch& a = ctx->arch;
-    const Vocab v = make_vocab(a.n_vocab);
+    const Vocab v = ctx_vocab(ctx);
     cudaStream_t s = st->stream;
     int rc;
     if ((rc = ws.reserve(ctx, B)) != WDR_OK) return rc;
@@ -634,7 +646,7 @@ static int full_sequential(wdr_context* ctx, wdr_state* st, const wdr_full_param
     int64_t st3[3] = {0, 0, 0};
     std::vector<int32_t> prompt_past;  // no_context = true (the crate never clears it): starts empty for every call
     if (p.prompt_tokens && p.prompt_n_tokens > 0) prompt_past.assign(p.prompt_tokens, p.prompt_tokens + p.prompt_n_tokens);
-    const Vocab v = make_vocab(ctx->arch.n_vocab);
+    const Vocab v = ctx_vocab(ctx);
     if (seek_end < seek + kDeltaMin) return WDR_OK;
     while (seek + kDeltaMin < seek_end) {
         SeqWindow sw;
@@ -918,7 +930,7 @@ extern "C" int wdr_lang_id(const char* lang) { return lang_id_from_str(lang); }
 extern "C" const char* wdr_token_to_str(wdr_context* ctx, int32_t token) {
     static thread_local std::string buf;
     if (!ctx || token < 0 || token >= ctx->arch.n_vocab) return nullptr;
-    buf = token_text(make_vocab(ctx->arch.n_vocab), token);
+    buf = token_text(ctx_vocab(ctx), token);
     return buf.c_str();
 }
 extern "C" int wdr_full_get_chunk_info_from_state(wdr_state* st, int i, int32_t* info, float* nsp) {

@@ -11,6 +11,7 @@
 #include <string>
 #include "common.cuh"
 #include "model.cuh"
+#include "ggml_file.cuh"
 
 namespace wdr {
 
@@ -105,9 +106,27 @@ __global__ void kb_major_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
     (void)num_kb;
 }
 
+// file-backed twin of synth_kernel: same destination mapping, values read from the tensor's canonical (OpenAI) layout
+template <typename T>
+__global__ void load_kernel(T* __restrict__ dst, int rows, int cols, int64_t ld, const float* __restrict__ src, int mode, int cin, int cpad) {
+    const int64_t total = (int64_t)rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(e / cols), c = (int)(e % cols);
+        float v;
+        if (mode == 0) v = src[e];
+        else {
+            const int t = c / cpad, ci = c % cpad;
+            v = (ci < cin) ? src[((int64_t)r * cin + ci) * 3 + t] : 0.0f;
+        }
+        if (sizeof(T) == 2) reinterpret_cast<__nv_bfloat16*>(dst)[(int64_t)r * ld + c] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(dst)[(int64_t)r * ld + c] = v;
+    }
+}
+
 struct Builder {
     wdr_context* ctx;
     int rc = WDR_OK;
+    const GgmlFile* file = nullptr;  // non-null: tensors come from a ggml checkpoint instead of the seeded generator
     template <typename T>
     T* alloc(size_t n) {
         if (rc != WDR_OK) return nullptr;
@@ -128,6 +147,21 @@ struct Builder {
         const int64_t total = (int64_t)rows * cols;
         int blocks = (int)((total + 255) / 256);
         if (blocks > 148 * 8) blocks = 148 * 8;
+        if (file) {
+            std::vector<float> host;
+            std::string err;
+            const int64_t expect = mode == 0 ? total : (int64_t)rows * cin * 3;
+            if (!file->read_f32(name, expect, &host, &err)) { set_error("%s", err.c_str()); rc = WDR_ERR_INVALID; return; }
+            float* tmp = nullptr;
+            if (cudaMalloc(&tmp, sizeof(float) * host.size()) != cudaSuccess) { set_error("weights: staging buffer for '%s'", name.c_str()); rc = WDR_ERR_OOM; return; }
+            cudaMemcpy(tmp, host.data(), sizeof(float) * host.size(), cudaMemcpyHostToDevice);
+            load_kernel<T><<<blocks, 256>>>(dst, rows, cols, ld, tmp, mode, cin, cpad);
+            count_launch();
+            cudaDeviceSynchronize();
+            cudaFree(tmp);
+            if (cudaGetLastError() != cudaSuccess) { set_error("weight load kernel failed for '%s'", name.c_str()); rc = WDR_ERR_CUDA; }
+            return;
+        }
         synth_kernel<T><<<blocks, 256>>>(dst, rows, cols, ld, tensor_key(ctx->seed, name), offset, scale, mode, cin, cpad);
         count_launch();
         if (cudaGetLastError() != cudaSuccess) { set_error("synth kernel launch failed"); rc = WDR_ERR_CUDA; }
@@ -164,10 +198,11 @@ struct Builder {
 static const float kWScale = 0.034641016151377546f;  // uniform half-width with std 0.02
 static const float kBScale = 0.02f;
 
-static int build_weights(wdr_context* ctx) {
+static int build_weights(wdr_context* ctx, const GgmlFile* file = nullptr) {
     const WhisperArch& a = ctx->arch;
     WhisperWeights& w = ctx->w;
     Builder b{ctx};
+    b.file = file;
     const int d = a.d;
     // ---- encoder ----
     w.conv1_w = b.alloc<__nv_bfloat16>((size_t)d * 3 * kConv1CPad);
@@ -176,7 +211,9 @@ static int build_weights(wdr_context* ctx) {
     w.conv2_w = b.alloc<__nv_bfloat16>((size_t)d * 3 * d);
     b.fill(w.conv2_w, d, 3 * d, 3 * d, "encoder.conv2.weight", 0.0f, kWScale, 1, d, d);
     w.conv2_b = b.vec(d, "encoder.conv2.bias", 0.0f, kBScale);
-    {
+    if (file) {
+        w.enc_pos = b.vec(WDR_AUDIO_CTX * d, "encoder.positional_embedding", 0.0f, 0.0f);
+    } else {
         // sinusoids(1500, d) of OpenAI Whisper, evaluated in fp32
         std::vector<float> pos((size_t)WDR_AUDIO_CTX * d);
         const int half = d / 2;
@@ -325,21 +362,54 @@ extern "C" wdr_context_params wdr_context_default_params(void) {
     return p;
 }
 
+// WhisperArch of a checkpoint: the named architecture with the same dimensions when there is one (it carries the DTW preset), else
+// an anonymous one.  Refuses geometries the kernels do not cover (head width != 64, contexts other than 1500 / 448).
+static bool arch_from_file(const GgmlFile& f, WhisperArch* out, std::string* name, std::string* err) {
+    if (f.n_audio_ctx != WDR_AUDIO_CTX || f.n_text_ctx != WDR_TEXT_CTX) { *err = "unsupported context sizes (need n_audio_ctx 1500, n_text_ctx 448)"; return false; }
+    if (f.n_text_state != f.n_audio_state || f.n_text_head != f.n_audio_head || f.n_audio_state != 64 * f.n_audio_head) {
+        *err = "unsupported geometry (need n_text_state == n_audio_state == 64 * n_head)";
+        return false;
+    }
+    if (f.n_vocab < 51864 || f.n_vocab > 51866 || (f.n_mels != 80 && f.n_mels != 128)) { *err = "unsupported vocabulary / mel size"; return false; }
+    if (f.filt_n_mel != f.n_mels || f.filt_n_fft != 201) { *err = "mel filterbank block does not match n_mels x 201"; return false; }
+    for (const auto& a : kArchs)
+        if (a.d == f.n_audio_state && a.n_head == f.n_audio_head && a.n_enc_layer == f.n_audio_layer && a.n_dec_layer == f.n_text_layer &&
+            a.n_mel == f.n_mels && a.n_vocab == f.n_vocab) {
+            *out = a;
+            *name = a.name;
+            return true;
+        }
+    WhisperArch a{};
+    a.d = f.n_audio_state; a.n_head = f.n_audio_head; a.n_enc_layer = f.n_audio_layer; a.n_dec_layer = f.n_text_layer;
+    a.n_mel = f.n_mels; a.n_vocab = f.n_vocab; a.multilingual = f.n_vocab >= 51865; a.dtw_preset = -1;
+    *out = a;
+    *name = "ggml-file";
+    return true;
+}
+
 extern "C" wdr_context* wdr_init_from_file_with_params(const char* path, wdr_context_params params) {
     clear_error();
-    if (path && path[0]) {
-        // ggml .bin reader is a SURVEY §8f "next" row; refuse instead of guessing
-        set_error("wdr_init_from_file_with_params: model files are not supported yet (pass NULL + arch_name for seeded weights)");
-        return nullptr;
-    }
     if (!params.use_gpu) { set_error("use_gpu = false: libwdr_b200 has no CPU path"); return nullptr; }
-    const WhisperArch* a = find_arch(params.arch_name);
-    if (!a) { set_error("unknown architecture '%s'", params.arch_name ? params.arch_name : "(null)"); return nullptr; }
+    GgmlFile file;
+    const bool from_file = path && path[0];
+    WhisperArch arch_buf{};
+    std::string arch_name;
+    const WhisperArch* a = nullptr;
+    if (from_file) {  // ggml-<model>.bin, as WhisperContext::new_with_params(model_path, ..) takes it (src/transcribe.rs:154)
+        std::string err;
+        if (!file.open(path, &err)) { set_error("%s", err.c_str()); return nullptr; }
+        if (!arch_from_file(file, &arch_buf, &arch_name, &err)) { set_error("%s: %s", path, err.c_str()); return nullptr; }
+        a = &arch_buf;
+    } else {
+        a = find_arch(params.arch_name);
+        if (!a) { set_error("unknown architecture '%s'", params.arch_name ? params.arch_name : "(null)"); return nullptr; }
+        arch_name = a->name;
+    }
     if (ensure_device(params.gpu_device) != WDR_OK) return nullptr;
     wdr_context* ctx = new wdr_context();
     ctx->device = params.gpu_device;
     ctx->arch = *a;
-    ctx->arch_name = a->name;
+    ctx->arch_name = arch_name;
     ctx->arch.name = ctx->arch_name.c_str();
     ctx->seed = params.seed;
     ctx->dtw_enabled = params.dtw_token_timestamps;
@@ -352,19 +422,38 @@ extern "C" wdr_context* wdr_init_from_file_with_params(const char* path, wdr_con
         const auto* ah = aheads_for_preset(preset);
         if (!ah) { set_error("unknown alignment-head preset %d", preset); delete ctx; return nullptr; }
         for (auto& lh : *ah) {
-            if (lh.first >= a->n_dec_layer || lh.second >= a->n_head) { set_error("alignment-head preset %d does not fit %s", preset, a->name); delete ctx; return nullptr; }
+            if (lh.first >= a->n_dec_layer || lh.second >= a->n_head) { set_error("alignment-head preset %d does not fit %s", preset, ctx->arch.name); delete ctx; return nullptr; }
             ctx->aheads.push_back(lh);
         }
         ctx->dtw_preset = preset;
     }
-    if (build_weights(ctx) != WDR_OK) { wdr_free(ctx); return nullptr; }
-    ctx->mel_filters.resize((size_t)a->n_mel * 201);
-    whisper_mel_filters(a->n_mel, ctx->mel_filters.data());
+    if (build_weights(ctx, from_file ? &file : nullptr) != WDR_OK) { wdr_free(ctx); return nullptr; }
+    if (from_file) {
+        ctx->mel_filters = file.filters;      // whisper.cpp takes the filterbank from the checkpoint
+        ctx->file_tokens = file.tokens;       // and the token strings
+    } else {
+        ctx->mel_filters.resize((size_t)a->n_mel * 201);
+        whisper_mel_filters(a->n_mel, ctx->mel_filters.data());
+    }
     ctx->mel = wdr_mel_init(ctx->mel_filters.data(), a->n_mel, ctx->device);
     if (!ctx->mel) { wdr_free(ctx); return nullptr; }
-    log_msg(1, "wdr: %s d=%d heads=%d enc=%d dec=%d mel=%d vocab=%d weights=%.1f MB (seed %llu)", a->name, a->d, a->n_head,
+    log_msg(1, "wdr: %s d=%d heads=%d enc=%d dec=%d mel=%d vocab=%d weights=%.1f MB (seed %llu)", ctx->arch.name, a->d, a->n_head,
             a->n_enc_layer, a->n_dec_layer, a->n_mel, a->n_vocab, ctx->weight_bytes / 1048576.0, (unsigned long long)ctx->seed);
     return ctx;
+}
+
+extern "C" int wdr_ggml_probe(const char* path, int32_t* hparams, int32_t* n_tensors, int32_t* n_tokens) {
+    clear_error();
+    WDR_REQUIRE(path && hparams, "bad arguments");
+    GgmlFile f;
+    std::string err;
+    if (!f.open(path, &err)) { set_error("%s", err.c_str()); return WDR_ERR_INVALID; }
+    const int32_t hp[11] = {f.n_vocab, f.n_audio_ctx, f.n_audio_state, f.n_audio_head, f.n_audio_layer, f.n_text_ctx, f.n_text_state, f.n_text_head,
+                            f.n_text_layer, f.n_mels, f.ftype};
+    memcpy(hparams, hp, sizeof(hp));
+    if (n_tensors) *n_tensors = (int32_t)f.tensors.size();
+    if (n_tokens) *n_tokens = (int32_t)f.tokens.size();
+    return WDR_OK;
 }
 
 extern "C" void wdr_free(wdr_context* ctx) {

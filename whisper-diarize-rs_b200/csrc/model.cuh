@@ -79,6 +79,7 @@ struct wdr_context {
     std::vector<void*> allocations;  // everything cudaMalloc'ed for the weights
     wdr_mel* mel = nullptr;
     std::vector<float> mel_filters;  // host copy [n_mel][201]
+    std::vector<std::string> file_tokens;  // token strings of a ggml checkpoint (empty: synthetic vocabulary)
     std::vector<std::pair<int, int>> aheads;  // (layer, head) alignment heads of the DTW preset
     int dtw_enabled = 0;
     int dtw_preset = -1;

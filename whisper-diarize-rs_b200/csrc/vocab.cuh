@@ -3,6 +3,8 @@
 // Special tokens use whisper.cpp's bracket names, which the reference's control-token filter relies on
 // (reference src/transcribe.rs:206-212).
 #pragma once
+#include <string>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -12,6 +14,7 @@ namespace wdr {
 struct Vocab {
     int n_vocab, eot, sot, translate, transcribe, solm, prev, nosp, not_, beg, lang0, n_langs, space;
     bool multilingual;
+    const std::vector<std::string>* file_tokens = nullptr;  // token strings of a ggml checkpoint (ids below its size)
 };
 
 inline Vocab make_vocab(int n_vocab) {
@@ -44,6 +47,7 @@ inline int lang_id_from_str(const char* s) {
 
 inline std::string token_text(const Vocab& v, int i) {
     char buf[48];
+    if (v.file_tokens && i >= 0 && i < (int)v.file_tokens->size() && i < v.eot) return (*v.file_tokens)[i];
     if (i < v.eot) {
         if (i == v.space) return " ";
         std::string s;
