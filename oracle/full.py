@@ -40,7 +40,129 @@ def detect_language(dec, enc_out):
     return int(np.argmax(lg[v["lang0"]: v["lang0"] + n_l]))
 
 
-def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10, lang_id=0):
+def beam_decode_window(dec, prompt, seek, seek_end, beam_size=5, delta_min=10, suppress_blank=True, max_initial_ts=1.0):
+    """whisper_full's beam search at temperature 0 for one window (the crate's default strategy, reference src/transcribe.rs:22,
+    29-32), restated from whisper.cpp: every live beam proposes its `beam_size` best tokens (by log-probability, ties to the lower
+    id); candidates are stably sorted by cumulative log-probability; each live beam, in index order, takes the next candidate and —
+    after the first iteration — skips the candidates that repeat its token sequence; the per-beam bookkeeping is the greedy loop's
+    (timestamp pairing, seek_delta, completion, failure); the winner is the non-failed beam with the best average log-probability
+    over its kept tokens (first maximum).  Not restated: the entropy test that only feeds the temperature fallback.
+    dec.set_audio(...) must have been called.  Returns the dict decode_window returns (tokens = the winner's)."""
+    nv = dec.a["n_vocab"]
+    v = V.special_ids(nv)
+    n_prompt = len(prompt)
+    n_max = 448 // 2 - 4
+    for i, t in enumerate(prompt):
+        lg0 = dec.step(int(t), i, want_logits=(i == n_prompt - 1))
+    kv0 = dec.get_kv()
+    lp0 = lg0 - (np.log(np.exp((lg0 - lg0.max()).astype(np.float32)).sum(dtype=np.float32)) + lg0.max())
+    no_speech_prob = float(np.exp(np.float32(lp0[v["nosp"]])))
+
+    class Beam:
+        pass
+
+    beams = []
+    for k in range(beam_size):
+        b = Beam()
+        b.tokens, b.sum_all, b.has_ts, b.seek_delta, b.result_len, b.failed, b.completed = [], 0.0, 0, 3000, 0, False, False
+        b.logits, b.kv = lg0, kv0
+        beams.append(b)
+    for i in range(n_max):
+        cl = []
+        props = {}
+        for k, b in enumerate(beams):
+            if b.completed or b.failed:
+                continue
+            _, _, lpb, pb = native.process_logits(b.logits, nv, [t.id for t in b.tokens], b.has_ts, b.seek_delta, suppress_blank, max_initial_ts)
+            fin = np.flatnonzero(lpb > -np.inf)
+            order = fin[np.lexsort((fin, -lpb[fin].astype(np.float64)))][:beam_size]
+            g = native.sample_stats(pb, lpb, nv)  # tid / pt / ptsum of the distribution
+            props[k] = (order, lpb, pb, g)
+            for r, tid_ in enumerate(order):
+                cl.append((k, r, b.sum_all + float(lpb[tid_])))
+        if not cl:
+            break
+        cl.sort(key=lambda c: -c[2])  # Python's sort is stable: generation order (beam, rank) breaks ties, as std::stable_sort does
+
+        def tok_of(c):
+            return int(props[c[0]][0][c[1]])
+
+        def same_seq(a, b_):
+            if tok_of(a) != tok_of(b_):
+                return False
+            ta, tb = beams[a[0]].tokens, beams[b_[0]].tokens
+            return len(ta) == len(tb) and all(x.id == y.id for x, y in zip(ta, tb))
+
+        new = list(beams)
+        cur_c = 0
+        any_live = False
+        for k, b in enumerate(beams):
+            if b.completed or b.failed:
+                continue
+            if cur_c >= len(cl):
+                cur_c = 0
+            cur = cl[cur_c]
+            cur_c += 1
+            while len(cl) > cur_c and i > 0 and same_seq(cl[cur_c], cur):
+                cur_c += 1
+            src = beams[cur[0]]
+            order, lpb, pb, g = props[cur[0]]
+            tid_ = int(order[cur[1]])
+            td = native.TokenData()
+            td.id, td.tid, td.p, td.plog, td.pt, td.ptsum, td.t0, td.t1, td.t_dtw, td.vlen = tid_, g.tid, float(pb[tid_]), float(lpb[tid_]), g.pt, g.ptsum, -1, -1, -1, 0.0
+            if tid_ >= v["beg"]:
+                td.tid, td.pt = tid_, td.p
+            h = Beam()
+            h.tokens, h.sum_all, h.has_ts, h.seek_delta, h.result_len = src.tokens + [td], cur[2], src.has_ts, src.seek_delta, src.result_len
+            h.failed, h.completed, h.logits, h.kv = False, False, None, src.kv
+            done = False
+            if td.id > v["beg"]:
+                sd_new = 2 * (td.id - v["beg"])
+                if h.has_ts and h.seek_delta > sd_new and h.result_len < i:
+                    h.failed, done = True, True
+                else:
+                    h.seek_delta, h.result_len, h.has_ts = sd_new, i + 1, 1
+            if not done and (td.id == v["eot"] or (h.has_ts and seek + h.seek_delta + delta_min >= seek_end)):
+                fail = False
+                if h.result_len == 0:
+                    if seek + h.seek_delta + delta_min >= seek_end:
+                        h.result_len = i + 1
+                    else:
+                        fail = True
+                if fail:
+                    h.failed = True
+                else:
+                    h.result_len, h.seek_delta, h.completed = i + 1, 3000, True  # single_segment
+                done = True
+            if not done and i == n_max - 1 and (h.result_len == 0 or h.seek_delta < 3000 // 2):
+                h.failed, done = True, True
+            new[k] = h
+            any_live = any_live or not done
+        beams = new
+        if not any_live or i == n_max - 1:
+            break
+        for b in beams:
+            if b.completed or b.failed:
+                continue
+            dec.set_kv(b.kv)
+            b.logits = dec.step(b.tokens[-1].id, n_prompt + i)
+            b.kv = dec.get_kv()
+    best, best_score = -1, -np.inf
+    for k, b in enumerate(beams):
+        if b.failed or b.result_len <= 0:
+            continue
+        score = sum(float(t.plog) for t in b.tokens[: b.result_len]) / b.result_len
+        if best < 0 or score > best_score:
+            best, best_score = k, score
+    if best < 0:
+        best = 0
+    w = beams[best]
+    n_keep = len(w.tokens) if w.failed else w.result_len
+    return dict(tokens=w.tokens[:n_keep], seek_delta=w.seek_delta, failed=w.failed, completed=w.completed, n_sampled=len(w.tokens),
+                result_len=w.result_len, no_speech_prob=no_speech_prob, margins=np.zeros(0, np.float32), beam=best)
+
+
+def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10, lang_id=0, beam_size=1):
     """dec: native.Decoder; enc_out [1500, d] (encoder output for this window); pcm_f32: the window's samples (<= 480000).
     Returns dict(segments=[dict(t0, t1, text, tokens=[TokenData])], seek_delta, no_speech_prob, margins, ...)."""
     nv = dec.a["n_vocab"]
@@ -50,7 +172,10 @@ def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_mi
     if seek_end < seek + delta_min or seek + delta_min >= seek_end:
         return out
     dec.set_audio(enc_out)
-    r = dec.decode_window(prompt_tokens(nv, lang_id), seek, seek_end, True, delta_min)
+    if beam_size > 1:
+        r = beam_decode_window(dec, prompt_tokens(nv, lang_id), seek, seek_end, beam_size, delta_min)
+    else:
+        r = dec.decode_window(prompt_tokens(nv, lang_id), seek, seek_end, True, delta_min)
     out.update(r)
     toks = r["tokens"]
     if r["failed"]:

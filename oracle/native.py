@@ -169,6 +169,10 @@ def _full():
         L.oracle_dec_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_int]
         L.oracle_dec_free.argtypes = [C.c_void_p]
         L.oracle_dec_set_audio.argtypes = [C.c_void_p, f32p]
+        L.oracle_dec_get_self_kv.argtypes = [C.c_void_p, f32p, f32p]
+        L.oracle_dec_get_self_kv.restype = None
+        L.oracle_dec_set_self_kv.argtypes = [C.c_void_p, f32p, f32p]
+        L.oracle_dec_set_self_kv.restype = None
         L.oracle_dec_step.argtypes = [C.c_void_p, C.c_int, C.c_int, f32p, i32p, C.c_int, f32p]
         L.oracle_process_logits.argtypes = [f32p, C.POINTER(Vocab), C.POINTER(LogitParams), C.POINTER(TokenData), C.c_int, C.c_int, C.c_int,
                                             f32p, f32p]
@@ -208,6 +212,16 @@ class Decoder:
 
     def __del__(self):
         self.close()
+
+    def get_kv(self):
+        n = self.a["n_dec"] * 448 * self.a["d"]
+        k, v = np.empty(n, np.float32), np.empty(n, np.float32)
+        _full().oracle_dec_get_self_kv(self.h, k.ctypes.data_as(C.POINTER(C.c_float)), v.ctypes.data_as(C.POINTER(C.c_float)))
+        return k, v
+
+    def set_kv(self, kv):
+        k, v = kv
+        _full().oracle_dec_set_self_kv(self.h, k.ctypes.data_as(C.POINTER(C.c_float)), v.ctypes.data_as(C.POINTER(C.c_float)))
 
     def set_audio(self, enc):
         e, ep = _f32(enc)
@@ -268,6 +282,15 @@ def process_logits(logits, n_vocab, tokens_cur, has_ts, seek_delta, suppress_bla
                                   lpb.ctypes.data_as(f32p), pb.ctypes.data_as(f32p))
     tok = _full().oracle_sample_greedy(pb.ctypes.data_as(f32p), lpb.ctypes.data_as(f32p), C.byref(v))
     return tok, lg, lpb, pb
+
+
+def sample_stats(probs, logprobs, n_vocab):
+    """tid / pt / ptsum (and the greedy pick) of a processed distribution: oracle_sample_greedy."""
+    v = make_vocab(n_vocab)
+    f32p = C.POINTER(C.c_float)
+    pb = np.ascontiguousarray(probs, np.float32)
+    lpb = np.ascontiguousarray(logprobs, np.float32)
+    return _full().oracle_sample_greedy(pb.ctypes.data_as(f32p), lpb.ctypes.data_as(f32p), C.byref(v))
 
 
 def token_timestamps(tokens, t0, t1, vlen, energy, token_beg, token_eot, state3, thold_pt=0.01, thold_ptsum=0.01):

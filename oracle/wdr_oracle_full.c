@@ -119,6 +119,18 @@ void oracle_dec_free(oracle_dec *m) {
     free((void *)m->lw); free(m->ck); free(m->cv); free(m->sk); free(m->sv); free(m->scratch); free(m);
 }
 
+/* self-attention cache snapshots (beam search: a beam that switches parents continues from the parent's cache) */
+void oracle_dec_get_self_kv(const oracle_dec *m, float *k, float *v) {
+    const size_t n = (size_t)m->n_layer * 448 * m->d;
+    memcpy(k, m->sk, sizeof(float) * n);
+    memcpy(v, m->sv, sizeof(float) * n);
+}
+void oracle_dec_set_self_kv(oracle_dec *m, const float *k, const float *v) {
+    const size_t n = (size_t)m->n_layer * 448 * m->d;
+    memcpy(m->sk, k, sizeof(float) * n);
+    memcpy(m->sv, v, sizeof(float) * n);
+}
+
 /* A.2 cross-KV: K_c = Wk enc (no bias), V_c = Wv enc + b, per decoder layer. enc: [1500][d] */
 void oracle_dec_set_audio(oracle_dec *m, const float *enc) {
     const int d = m->d, T = 1500;

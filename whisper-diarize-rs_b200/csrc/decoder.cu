@@ -171,7 +171,9 @@ constexpr int kSelfMaxHeadsPerCta = 5;
 __global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
-                     const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */) {
+                     const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */,
+                     const int32_t* __restrict__ anc /* beam search: [448][anc_ld] row that holds position t of this row's history; null = own row */,
+                     int anc_ld) {
     __shared__ __align__(16) float qs[kSelfMaxHeadsPerCta][64];
     __shared__ float ps[kSelfMaxHeadsPerCta][kDecSeqCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,6 +187,9 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     const int n_heads = d >> 6;
     float* K = sk + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
     float* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
+    // beam search: position t < pos of this row's history lives in the cache of row anc[t][b] (the beam it descended from)
+    const int64_t row_step = (int64_t)n_heads * kDecSeqCap * 64;
+#define WDR_ANC_ROW(t) (anc ? (int64_t)(anc[(int64_t)(t) * anc_ld + b] - b) * row_step : (int64_t)0)
     float* q = qs[warp];
     float* p = ps[warp];
 #pragma unroll
@@ -197,7 +202,7 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     __syncwarp();
     float mx = -INFINITY;
     for (int t = lane; t <= pos; t += 32) {
-        const float4* kr = reinterpret_cast<const float4*>(K + (int64_t)t * 64);
+        const float4* kr = reinterpret_cast<const float4*>(K + (t < pos ? WDR_ANC_ROW(t) : 0) + (int64_t)t * 64);
         const float4* qv = reinterpret_cast<const float4*>(q);
         float4 f[16];
 #pragma unroll
@@ -232,8 +237,9 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
         float v0[8], v1[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
-            v0[k] = vc[(int64_t)(t + k) * 64];
-            v1[k] = vc[(int64_t)(t + k) * 64 + 32];
+            const int64_t ro = (t + k) < pos ? WDR_ANC_ROW(t + k) : 0;
+            v0[k] = vc[ro + (int64_t)(t + k) * 64];
+            v1[k] = vc[ro + (int64_t)(t + k) * 64 + 32];
         }
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -244,11 +250,13 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     }
     for (; t <= pos; t++) {
         const float pt = p[t] * inv;
-        a0 = fmaf(pt, vc[(int64_t)t * 64], a0);
-        a1 = fmaf(pt, vc[(int64_t)t * 64 + 32], a1);
+        const int64_t ro = t < pos ? WDR_ANC_ROW(t) : 0;
+        a0 = fmaf(pt, vc[ro + (int64_t)t * 64], a0);
+        a1 = fmaf(pt, vc[ro + (int64_t)t * 64 + 32], a1);
     }
     store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane, a0);
     store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane + 32, a1);
+#undef WDR_ANC_ROW
 }
 
 // cross-attention of one (head, window): q from the cross-query GEMM partials; K_c/V_c rows are 64 bf16 (128 B) at row
@@ -260,7 +268,7 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
                       const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
                       float* __restrict__ aw, const int64_t* __restrict__ aw_off, const int32_t* __restrict__ aw_T,
                       const int32_t* __restrict__ aw_A, const int32_t* __restrict__ pos_ptr, int pos, const DecWinState* __restrict__ win,
-                      const int32_t* __restrict__ t_limit) {
+                      const int32_t* __restrict__ t_limit, int rows_per_window /* beam search: rows b share the cross cache of window b / rows_per_window */) {
     __shared__ float q[64];
     __shared__ float p[kT + 4];
     __shared__ float red[32];
@@ -278,7 +286,7 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
 #pragma unroll
     for (int j = 0; j < 8; j++) q8[j] = q[g * 8 + j];
     // head-major cross cache: [(window, head)][K | V][1500][64] — both blocks of a CTA are contiguous 192 KB streams
-    const __nv_bfloat16* Kb = ckv + ((int64_t)b * gridDim.x + hh) * 2 * kT * 64 + g * 8;
+    const __nv_bfloat16* Kb = ckv + ((int64_t)(b / rows_per_window) * gridDim.x + hh) * 2 * kT * 64 + g * 8;
     const __nv_bfloat16* Vb = Kb + kT * 64;
     const int64_t rs = 64;
     // ---- scores ----
@@ -728,12 +736,151 @@ dec_sample_kernel(const float* __restrict__ logits, int64_t ldv, DecWinState* __
     if (done) atomicAdd(done_count, 1);
 }
 
+// Beam search: whisper_process_logits for one row from its own history summary (BeamRow), then the k best tokens by log-probability
+// (ties: lower id) with the statistics whisper_sample_token_topk attaches to each (p, plog; tid, pt, ptsum of the distribution).
+__global__ void __launch_bounds__(kSampThreads, 1)
+dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __restrict__ rows, const SampleParams sp, int k_top,
+                BeamCand* __restrict__ cands /* [rows][kBeamMax] */, float* __restrict__ no_speech /* [rows], written when n_cur == 0 */) {
+    __shared__ float red[32];
+    __shared__ unsigned long long red64[32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const BeamRow st = rows[b];
+    if (!st.active) return;
+    const int n = sp.n_vocab;
+    const bool is_initial = st.n_cur == 0;
+    const bool last_was_ts = st.n_cur > 0 && st.last_id >= sp.beg;
+    const bool penult_was_ts = st.n_cur < 2 || st.penult_id >= sp.beg;
+    const float* lg = logits + (int64_t)b * ldv;
+    float v[kSampPer];
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        v[k] = (i < n) ? lg[i] : -INFINITY;
+    }
+    if (is_initial) {
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < kSampPer; k++) m = fmaxf(m, v[k]);
+        m = block_max(m, red);
+        float s = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) s += expf(v[k] - m);
+        s = block_sum(s, red);
+        if (tid == 0) no_speech[b] = expf(lg[sp.nosp] - (logf(s) + m));
+    }
+    const int ts_floor = st.has_ts ? sp.beg + st.seek_delta / 2 : sp.beg;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        bool mask = false;
+        if (sp.suppress_blank && is_initial && (i == sp.eot || i == sp.space)) mask = true;
+        if (i == sp.not_ || i == sp.sot || i == sp.nosp || i == sp.solm || i == sp.translate || i == sp.transcribe || i == sp.prev) mask = true;
+        if (sp.no_timestamps && i >= sp.beg) mask = true;
+        if (i >= sp.lang0 && i < sp.lang0 + sp.n_langs) mask = true;
+        if (last_was_ts) {
+            if (penult_was_ts) { if (i >= sp.beg) mask = true; }
+            else { if (i < sp.eot) mask = true; }
+        }
+        if (is_initial && sp.initial_tid0 >= 0 && i >= sp.beg + sp.initial_tid0 + 1) mask = true;
+        if (i >= sp.beg && i < ts_floor) mask = true;
+        if (mask) v[k] = -INFINITY;
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) m = fmaxf(m, v[k]);
+    m = block_max(m, red);
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) s += expf(v[k] - m);
+    s = block_sum(s, red);
+    const float lse = logf(s) + m;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) v[k] -= lse;  // v = logprobs
+    float tmax = -INFINITY, xmax = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        if (i >= sp.beg) tmax = fmaxf(tmax, v[k]); else xmax = fmaxf(xmax, v[k]);
+    }
+    tmax = block_max(tmax, red);
+    xmax = block_max(xmax, red);
+    float tsum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        if (i >= sp.beg && v[k] > -INFINITY) tsum += expf(v[k] - tmax);
+    }
+    tsum = block_sum(tsum, red);
+    const float ts_logprob = tsum > 0.0f ? logf(tsum) + tmax : -INFINITY;
+    const bool mask_text = ts_logprob > xmax;
+    float sum_ts = 0.0f;
+    unsigned long long best_ts = 0ull;
+#pragma unroll
+    for (int k = 0; k < kSampPer; k++) {
+        const int i = tid + k * kSampThreads;
+        if (mask_text && i < sp.beg) v[k] = -INFINITY;
+        const float pr = v[k] > -INFINITY ? expf(v[k]) : 0.0f;
+        if (pr > 0.0f && i >= sp.beg) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(pr) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+            sum_ts += pr;
+            best_ts = key > best_ts ? key : best_ts;
+        }
+    }
+    sum_ts = block_sum(sum_ts, red);
+    best_ts = block_max_u64(best_ts, red64);
+    int tid_tok = 0;
+    float pt = 0.0f;
+    {
+        double max_ts = 0.0;
+        if (best_ts) { tid_tok = (int)(0xFFFFFFFFu - (unsigned)(best_ts & 0xFFFFFFFFull)); max_ts = (double)__uint_as_float((unsigned)(best_ts >> 32)); }
+        pt = (float)(max_ts / ((double)sum_ts + 1e-10));
+    }
+    // ---- k rounds of block arg-max over the log-probabilities (key = order-preserving float bits | inverted id) ----
+    for (int r = 0; r < k_top; r++) {
+        unsigned long long best = 0ull;
+#pragma unroll
+        for (int k = 0; k < kSampPer; k++) {
+            const int i = tid + k * kSampThreads;
+            if (v[k] > -INFINITY) {
+                const unsigned long long key = ((unsigned long long)float_to_key(v[k]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+                best = key > best ? key : best;
+            }
+        }
+        best = block_max_u64(best, red64);
+        BeamCand c;
+        c.id = -1; c.tid = tid_tok; c.p = 0.0f; c.plog = -INFINITY; c.pt = pt; c.ptsum = sum_ts;
+        if (best) {
+            const int id = (int)(0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFull));
+            const float lp = key_to_float((unsigned)(best >> 32));
+            c.id = id; c.plog = lp; c.p = expf(lp);
+            if (id >= sp.beg) { c.tid = id; c.pt = c.p; }
+#pragma unroll
+            for (int k = 0; k < kSampPer; k++)
+                if (tid + k * kSampThreads == id) v[k] = -INFINITY;  // taken
+        }
+        if (tid == 0) cands[(int64_t)b * kBeamMax + r] = c;
+        __syncthreads();
+    }
+}
+
+// ancestry update after a beam reassignment at sampling position i (0-based): new row b continues old row parent[b];
+// the history position that old row just wrote (pos_last) now belongs to parent[b], earlier ones follow the parent's ancestry.
+__global__ void beam_anc_kernel(const int32_t* __restrict__ anc_old, int32_t* __restrict__ anc_new, const int32_t* __restrict__ parent, int n_rows, int ld,
+                                int pos_last) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_rows) return;
+    const int pb = parent[b];
+    for (int t = 0; t < pos_last; t++) anc_new[(int64_t)t * ld + b] = anc_old[(int64_t)t * ld + pb];
+    anc_new[(int64_t)pos_last * ld + b] = pb;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
 void DecoderWorkspace::release() {
     for (void* p : {(void*)enc_bf16, (void*)sk, (void*)sv, (void*)x, (void*)h, (void*)att, (void*)ff, (void*)part, (void*)logits, (void*)seq,
-                    (void*)tokens, (void*)win, (void*)done_count, (void*)pos_dev, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
+                    (void*)tokens, (void*)win, (void*)done_count, (void*)pos_dev, (void*)beam_anc[0], (void*)beam_anc[1], (void*)beam_limit, (void*)beam_rows,
+                    (void*)beam_cands, (void*)beam_parent, (void*)beam_nosp, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
         if (p) cudaFree(p);
     for (auto p : ckv) if (p) cudaFree(p);
     if (step_graph) cudaGraphExecDestroy(step_graph);
@@ -765,6 +912,12 @@ int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
     WDR_CUDA_TRY(cudaMalloc(&win, sizeof(DecWinState) * B));
     WDR_CUDA_TRY(cudaMalloc(&done_count, sizeof(int32_t)));
     WDR_CUDA_TRY(cudaMalloc(&pos_dev, sizeof(int32_t)));
+    for (int i = 0; i < 2; i++) WDR_CUDA_TRY(cudaMalloc(&beam_anc[i], sizeof(int32_t) * kDecSeqCap * kDecMaxBatch));
+    WDR_CUDA_TRY(cudaMalloc(&beam_limit, sizeof(int32_t) * kDecMaxBatch));
+    WDR_CUDA_TRY(cudaMalloc(&beam_rows, sizeof(BeamRow) * kDecMaxBatch));
+    WDR_CUDA_TRY(cudaMalloc(&beam_cands, sizeof(BeamCand) * kDecMaxBatch * kBeamMax));
+    WDR_CUDA_TRY(cudaMalloc(&beam_parent, sizeof(int32_t) * kDecMaxBatch));
+    WDR_CUDA_TRY(cudaMalloc(&beam_nosp, sizeof(float) * kDecMaxBatch));
     WDR_CUDA_TRY(cudaMalloc(&ahead_map, sizeof(int32_t) * n_layer * n_head));
     WDR_CUDA_TRY(cudaMalloc(&aw_off, sizeof(int64_t) * B));
     WDR_CUDA_TRY(cudaMalloc(&aw_T, sizeof(int32_t) * B));
@@ -871,8 +1024,9 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
     };
     static const int dbg_layers = getenv("WDR_DEBUG_DEC_LAYERS") ? atoi(getenv("WDR_DEBUG_DEC_LAYERS")) : 1 << 30;  // bring-up aid: truncate the stack
     const bool capture = mode == DEC_MODE_DTW;
+    const bool beam = mode == DEC_MODE_BEAM;  // rows = windows x beams: shared cross cache per window, ancestry-indexed self cache
     const DecWinState* win = mode == DEC_MODE_DECODE ? ws.win : nullptr;
-    const int32_t* t_limit = mode == DEC_MODE_DTW ? ws.aw_T : nullptr;
+    const int32_t* t_limit = mode == DEC_MODE_DTW ? ws.aw_T : beam ? ws.beam_limit : nullptr;
     int L_run = L;
     if (capture && !want_logits) {  // the DTW pass only needs the layers up to the last alignment head
         L_run = 0;
@@ -888,7 +1042,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             while (H % hpc) hpc--;
             WDR_CUDA_TRY(launch_kernel(dec_self_attn_kernel, dim3(H / hpc, B), dim3(hpc * 32), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_qkv,
                                        ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att,
-                                       (int64_t)ws.cap_B * d, win, t_limit));
+                                       (int64_t)ws.cap_B * d, win, t_limit, beam ? ws.beam_anc_cur : nullptr, kDecMaxBatch));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
@@ -903,7 +1057,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             // flight than the two independent passes do.
             WDR_CUDA_TRY(launch_kernel(dec_cross_attn_kernel<6>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
                                        (int64_t)ws.cap_B * d, capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T, ws.aw_A, pos_ptr, pos,
-                                       win, t_limit));
+                                       win, t_limit, beam ? ws.beam_width : 1));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
@@ -1067,6 +1221,23 @@ int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos,
     WDR_CUDA_TRY(launch_kernel(dec_sample_kernel, dim3(B), dim3(kSampThreads), 0, st, pdl, ws.logits, ws.ldv, ws.win, ws.tokens, ws.seq,
                                pos_on_device ? ws.pos_dev : nullptr, pos, sp, ws.done_count));
     WDR_LAUNCH_CHECK();
+    return WDR_OK;
+}
+
+int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, cudaStream_t st, Profiler* prof) {
+    WDR_REQUIRE(sp.n_vocab <= kSampThreads * kSampPer && k_top >= 1 && k_top <= kBeamMax && R <= kDecMaxBatch, "decoder_topk: bad arguments");
+    ProfScope ps(prof, KC_DECODER, st);
+    dec_topk_kernel<<<R, kSampThreads, 0, st>>>(ws.logits, ws.ldv, ws.beam_rows, sp, k_top, ws.beam_cands, ws.beam_nosp);
+    WDR_LAUNCH_CHECK();
+    return WDR_OK;
+}
+
+int decoder_beam_reorder(DecoderWorkspace& ws, int R, int pos_last, cudaStream_t st) {
+    int32_t* old_t = ws.beam_anc_cur;
+    int32_t* new_t = old_t == ws.beam_anc[0] ? ws.beam_anc[1] : ws.beam_anc[0];
+    beam_anc_kernel<<<(R + 127) / 128, 128, 0, st>>>(old_t, new_t, ws.beam_parent, R, kDecMaxBatch, pos_last);
+    WDR_LAUNCH_CHECK();
+    ws.beam_anc_cur = new_t;
     return WDR_OK;
 }
 

@@ -27,6 +27,16 @@ struct SampleParams {
     int initial_tid0;  // round(max_initial_ts / 0.02), or -1 when max_initial_ts <= 0
 };
 
+// ---- beam search (rows = windows x beams) ----
+constexpr int kBeamMax = 8;
+struct BeamRow {   // what whisper_process_logits needs to know about a beam's history
+    int32_t active, n_cur, last_id, penult_id, has_ts, seek_delta;
+};
+struct BeamCand {  // one entry of whisper_sample_token_topk
+    int32_t id, tid;
+    float p, plog, pt, ptsum;
+};
+
 struct DecoderWorkspace {
     int cap_B = 0;
     int d = 0, n_layer = 0, n_head = 0;
@@ -47,6 +57,15 @@ struct DecoderWorkspace {
     DecWinState* win = nullptr;        // [B]
     int32_t* done_count = nullptr;
     int32_t* pos_dev = nullptr;        // device-resident step counter read by the graph-replayed decode step
+    // beam search: ancestry tables [448][128] (double-buffered), per-row limits / history summaries / candidates / parents
+    int32_t* beam_anc[2] = {nullptr, nullptr};
+    int32_t* beam_anc_cur = nullptr;
+    int32_t* beam_limit = nullptr;
+    BeamRow* beam_rows = nullptr;
+    BeamCand* beam_cands = nullptr;
+    int32_t* beam_parent = nullptr;
+    float* beam_nosp = nullptr;
+    int beam_width = 1;
     cudaGraphExec_t step_graph = nullptr;  // one greedy iteration (sample, advance, step), see decoder_decode_graph
     int graph_B = 0, graph_nodes = 0;
     SampleParams graph_sp{};
@@ -85,7 +104,11 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 //       DEC_MODE_FORCED = teacher-forced, every window runs;
 //       DEC_MODE_DTW    = teacher-forced DTW pass: alignment-head cross-attention rows go to ws.aw, windows stop at their own
 //                         length ws.aw_T[b], and without logits only the layers up to the last alignment head run.
-enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2 };
+//       DEC_MODE_BEAM   = beam search: rows = windows x ws.beam_width; a window's rows share its cross cache, the self cache of a
+//                         row is read through the ancestry table ws.beam_anc_cur, rows with ws.beam_limit[b] <= pos are skipped.
+enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2, DEC_MODE_BEAM = 3 };
+int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, cudaStream_t st, Profiler* prof);
+int decoder_beam_reorder(DecoderWorkspace& ws, int R, int pos_last, cudaStream_t st);
 int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof,
                  bool pos_on_device = false, bool pdl = false);
 // The DTW pass in one shot: the teacher-forced sequences ws.seq[b][0 .. T_b) (T_b = ws.aw_T[b], host copy in T_host; 0 = window

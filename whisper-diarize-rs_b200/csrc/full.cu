@@ -199,7 +199,7 @@ static SampleParams make_sample_params(const Vocab& v, const wdr_full_params& p)
 }
 
 static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int* lang_id) {
-    if (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) { set_error("beam search (beam_size %d) is not implemented yet: use WDR_SAMPLING_GREEDY", p.beam_size); return WDR_ERR_UNSUPPORTED; }
+    if (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > kBeamMax) { set_error("beam_size %d exceeds the supported maximum of %d", p.beam_size, kBeamMax); return WDR_ERR_UNSUPPORTED; }
     if (p.temperature != 0.0f || p.temperature_inc != 0.0f) { set_error("only temperature 0 without fallback is implemented (temperature %g, temperature_inc %g)", p.temperature, p.temperature_inc); return WDR_ERR_UNSUPPORTED; }
     if (!p.single_segment) { set_error("single_segment = 0 is not implemented (the crate always sets it, src/transcribe.rs:46)"); return WDR_ERR_UNSUPPORTED; }
     if (p.no_timestamps) { set_error("no_timestamps = 1 is not implemented"); return WDR_ERR_UNSUPPORTED; }
@@ -236,6 +236,176 @@ static int grow_pinned(T** p, size_t* cap, size_t need) {
     return WDR_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Beam search (whisper_full with WHISPER_SAMPLING_BEAM_SEARCH at temperature 0 — the crate's default strategy,
+// reference src/transcribe.rs:22, 29-32).  Rows of the decode batch = windows x beams.  Per iteration the device scores every
+// live row (whisper_process_logits + the K best tokens, dec_topk_kernel); the host runs whisper.cpp's candidate logic per
+// window — K candidates per live beam, stable sort by cumulative log-probability, each live beam takes the next candidate that
+// is not a duplicate of the previous one (after the first iteration), then the per-beam bookkeeping of the greedy loop
+// (timestamp pairing, seek_delta, completion, failure) — and sends back parents + tokens; the self cache is never copied:
+// beam_anc_kernel re-threads an ancestry table that the self-attention kernel reads through.  Ranking: average log-probability
+// over the kept tokens, first maximum.  Not restated: the entropy check that feeds the temperature fallback (no fallback here).
+// ---------------------------------------------------------------------------------------------------
+struct HostBeam {
+    std::vector<wdr_token_data> tokens;
+    double sum_all = 0.0;
+    int has_ts = 0, seek_delta = 100 * 30, result_len = 0;
+    bool failed = false, completed = false;
+};
+
+static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, const wdr_full_params& p, const SampleParams& sp, const Vocab& v,
+                       int B, int K, int n_prompt, const std::vector<int32_t>& seq_win /* [B][448] */, std::vector<DecWinState>& win,
+                       std::vector<wdr_token_data>& toks_out /* [B][224] */, int* steps_out) {
+    cudaStream_t s = st->stream;
+    const int R = B * K, n_max = sp.n_max;
+    int rc;
+    std::vector<int32_t> seq((size_t)R * kDecSeqCap);
+    for (int r = 0; r < R; r++) memcpy(&seq[(size_t)r * kDecSeqCap], &seq_win[(size_t)(r / K) * kDecSeqCap], sizeof(int32_t) * kDecSeqCap);
+    std::vector<int32_t> anc((size_t)kDecSeqCap * kDecMaxBatch);
+    for (int t = 0; t < kDecSeqCap; t++)
+        for (int b = 0; b < kDecMaxBatch; b++) anc[(size_t)t * kDecMaxBatch + b] = b;
+    std::vector<int32_t> limit(kDecMaxBatch, 0);
+    for (int r = 0; r < R; r++) limit[r] = win[r / K].completed ? 0 : 1 << 30;
+    ws.beam_width = K;
+    ws.beam_anc_cur = ws.beam_anc[0];
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_anc[0], anc.data(), sizeof(int32_t) * anc.size(), cudaMemcpyHostToDevice, s));
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_limit, limit.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < n_prompt; i++)
+        if ((rc = decoder_step(ctx, ws, R, i, i == n_prompt - 1, DEC_MODE_BEAM, s, &st->prof)) != WDR_OK) return rc;
+    std::vector<std::vector<HostBeam>> beams(B, std::vector<HostBeam>(K));
+    std::vector<BeamRow> rows(R);
+    std::vector<BeamCand> cands((size_t)R * kBeamMax);
+    std::vector<float> nosp(R, 0.0f);
+    std::vector<int32_t> parent(R), next_tok(R);
+    int steps = 0;
+    struct Cand { int k, r; double sum; };
+    for (int i = 0; i < n_max; i++) {
+        for (int r = 0; r < R; r++) {
+            const HostBeam& hb = beams[r / K][r % K];
+            BeamRow br;
+            br.active = !win[r / K].completed && !hb.completed && !hb.failed;
+            br.n_cur = (int)hb.tokens.size();
+            br.last_id = br.n_cur > 0 ? hb.tokens[br.n_cur - 1].id : 0;
+            br.penult_id = br.n_cur > 1 ? hb.tokens[br.n_cur - 2].id : 0;
+            br.has_ts = hb.has_ts;
+            br.seek_delta = hb.seek_delta;
+            rows[r] = br;
+        }
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_rows, rows.data(), sizeof(BeamRow) * R, cudaMemcpyHostToDevice, s));
+        if ((rc = decoder_topk(ctx, ws, R, sp, K, s, &st->prof)) != WDR_OK) return rc;
+        WDR_CUDA_TRY(cudaMemcpyAsync(cands.data(), ws.beam_cands, sizeof(BeamCand) * (size_t)R * kBeamMax, cudaMemcpyDeviceToHost, s));
+        if (i == 0) WDR_CUDA_TRY(cudaMemcpyAsync(nosp.data(), ws.beam_nosp, sizeof(float) * R, cudaMemcpyDeviceToHost, s));
+        WDR_CUDA_TRY(cudaStreamSynchronize(s));
+        steps = i + 1;
+        if (i == 0)
+            for (int w = 0; w < B; w++) win[w].no_speech_prob = nosp[(size_t)w * K];
+        bool any_live = false;
+        for (int r = 0; r < R; r++) { parent[r] = r; next_tok[r] = v.eot; }
+        for (int w = 0; w < B; w++) {
+            if (win[w].completed) continue;
+            std::vector<HostBeam>& bw = beams[w];
+            std::vector<Cand> cl;
+            for (int k = 0; k < K; k++) {
+                if (bw[k].completed || bw[k].failed) continue;
+                for (int r = 0; r < K; r++) {
+                    const BeamCand& c = cands[((size_t)w * K + k) * kBeamMax + r];
+                    if (c.id >= 0) cl.push_back({k, r, bw[k].sum_all + (double)c.plog});
+                }
+            }
+            if (cl.empty()) continue;
+            std::stable_sort(cl.begin(), cl.end(), [](const Cand& a, const Cand& b) { return a.sum > b.sum; });
+            auto cand_tok = [&](const Cand& c) -> const BeamCand& { return cands[((size_t)w * K + c.k) * kBeamMax + c.r]; };
+            auto same_seq = [&](const Cand& a, const Cand& b) {
+                if (cand_tok(a).id != cand_tok(b).id) return false;
+                const auto &ta = bw[a.k].tokens, &tb = bw[b.k].tokens;
+                if (ta.size() != tb.size()) return false;
+                for (size_t j = 0; j < ta.size(); j++)
+                    if (ta[j].id != tb[j].id) return false;
+                return true;
+            };
+            std::vector<HostBeam> nb = bw;
+            size_t cur_c = 0;
+            for (int k = 0; k < K; k++) {
+                if (bw[k].completed || bw[k].failed) continue;
+                if (cur_c >= cl.size()) cur_c = 0;
+                const Cand cur = cl[cur_c++];
+                while (cl.size() > cur_c && i > 0 && same_seq(cl[cur_c], cur)) ++cur_c;
+                const BeamCand& c = cand_tok(cur);
+                HostBeam h = bw[cur.k];
+                wdr_token_data td;
+                memset(&td, 0, sizeof(td));
+                td.id = c.id; td.tid = c.tid; td.p = c.p; td.plog = c.plog; td.pt = c.pt; td.ptsum = c.ptsum; td.t0 = -1; td.t1 = -1; td.t_dtw = -1;
+                h.tokens.push_back(td);
+                h.sum_all = cur.sum;
+                // ---- per-beam bookkeeping (the greedy loop's rules) ----
+                const int seek = win[w].seek, seek_end = win[w].seek_end;
+                bool done = false;
+                if (td.id > v.beg) {
+                    const int sd_new = 2 * (td.id - v.beg);
+                    if (h.has_ts && h.seek_delta > sd_new && h.result_len < i) { h.failed = true; done = true; }
+                    else { h.seek_delta = sd_new; h.result_len = i + 1; h.has_ts = 1; }
+                }
+                if (!done && (td.id == v.eot || (h.has_ts && seek + h.seek_delta + sp.delta_min >= seek_end))) {
+                    bool fail = false;
+                    if (h.result_len == 0 && !sp.no_timestamps) {
+                        if (seek + h.seek_delta + sp.delta_min >= seek_end) h.result_len = i + 1;
+                        else fail = true;
+                    }
+                    if (fail) h.failed = true;
+                    else {
+                        if (sp.single_segment || sp.no_timestamps) { h.result_len = i + 1; h.seek_delta = 100 * 30; }
+                        h.completed = true;
+                    }
+                    done = true;
+                }
+                if (!done && i == n_max - 1 && (h.result_len == 0 || h.seek_delta < 100 * 30 / 2)) { h.failed = true; done = true; }
+                nb[k] = h;
+                parent[(size_t)w * K + k] = w * K + cur.k;
+                next_tok[(size_t)w * K + k] = td.id;
+                if (!done) any_live = true;
+            }
+            bw.swap(nb);
+        }
+        if (!any_live || i == n_max - 1) break;
+        if (p.abort_callback && (i & 7) == 7 && p.abort_callback(p.abort_callback_user_data)) { set_error("aborted by callback"); return WDR_ERR_ABORTED; }
+        // ---- next step: re-thread the ancestry, feed the chosen tokens, skip dead rows ----
+        const int pos_last = n_prompt - 1 + i;
+        for (int r = 0; r < R; r++) {
+            const HostBeam& hb = beams[r / K][r % K];
+            limit[r] = (win[r / K].completed || hb.completed || hb.failed) ? 0 : 1 << 30;
+        }
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_parent, parent.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_limit, limit.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpy2DAsync(ws.seq + pos_last + 1, sizeof(int32_t) * kDecSeqCap, next_tok.data(), sizeof(int32_t), sizeof(int32_t), R, cudaMemcpyHostToDevice, s));
+        if ((rc = decoder_beam_reorder(ws, R, pos_last, s)) != WDR_OK) return rc;
+        if ((rc = decoder_step(ctx, ws, R, pos_last + 1, true, DEC_MODE_BEAM, s, &st->prof)) != WDR_OK) return rc;
+        WDR_CUDA_TRY(cudaStreamSynchronize(s));  // parent / limit / next_tok are reused by the next iteration
+    }
+    // ---- rank the beams of every window: average log-probability over the kept tokens, first maximum ----
+    for (int w = 0; w < B; w++) {
+        if (win[w].completed) continue;  // was never decoded (too short)
+        int best = -1;
+        double best_score = -INFINITY;
+        for (int k = 0; k < K; k++) {
+            const HostBeam& h = beams[w][k];
+            if (h.failed || h.result_len <= 0) continue;
+            double sum = 0.0;
+            for (int j = 0; j < h.result_len; j++) sum += h.tokens[j].plog;
+            const double score = sum / h.result_len;
+            if (best < 0 || score > best_score) { best = k; best_score = score; }
+        }
+        if (best < 0) best = 0;  // every beam failed: keep beam 0's tokens as a failed decode (there is no temperature to fall back to)
+        const HostBeam& h = beams[w][best];
+        DecWinState& ww = win[w];
+        ww.n_cur = (int)h.tokens.size(); ww.has_ts = h.has_ts; ww.seek_delta = h.seek_delta; ww.result_len = h.result_len;
+        ww.failed = h.failed ? 1 : 0; ww.completed = h.completed ? 1 : 0;
+        for (size_t j = 0; j < h.tokens.size() && j < (size_t)kDecMaxTokens; j++) toks_out[(size_t)w * kDecMaxTokens + j] = h.tokens[j];
+    }
+    *steps_out = steps;
+    return WDR_OK;
+}
+
 // Sequential mode (whisper_full's own seek loop over a buffer longer than 30 s): one window of the long buffer.
 struct SeqWindow {
     const float* mel_dev;         // raw log-mel of the WHOLE buffer [n_mel][n_len] (device)
@@ -259,7 +429,9 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     const Vocab v = ctx_vocab(ctx);
     cudaStream_t s = st->stream;
     int rc;
-    if ((rc = ws.reserve(ctx, B)) != WDR_OK) return rc;
+    const int beam_K = (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1;  // rows per window of the decode batch
+    WDR_REQUIRE(B * beam_K <= kDecMaxBatch, "windows x beams exceeds the 128-row decode batch");
+    if ((rc = ws.reserve(ctx, B * beam_K)) != WDR_OK) return rc;
     // ---- n_valid on the device ----
     if ((rc = grow_dev(&fs.nvalid_dev, &fs.nvalid_cap, (size_t)B)) != WDR_OK) return rc;
     std::vector<int32_t> nv(B);
@@ -358,9 +530,13 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     WDR_CUDA_TRY(cudaMemsetAsync(ws.done_count, 0, sizeof(int32_t), s));
     WDR_CUDA_TRY(cudaMemsetAsync(ws.tokens, 0, sizeof(wdr_token_data) * (size_t)B * kDecMaxTokens, s));
     const SampleParams sp = make_sample_params(v, p);
-    // ---- greedy decode ----
+    // ---- decode: beam search (rows = windows x beams) or greedy ----
     int steps_run = 0;
-    if (n_skip < B) {
+    std::vector<wdr_token_data> toks((size_t)B * kDecMaxTokens);
+    memset(toks.data(), 0, sizeof(wdr_token_data) * toks.size());
+    if (beam_K > 1 && n_skip < B) {
+        if ((rc = beam_decode(ctx, st, ws, p, sp, v, B, beam_K, n_prompt, seq, win, toks, &steps_run)) != WDR_OK) return rc;
+    } else if (n_skip < B) {
         for (int i = 0; i < n_prompt; i++)
             if ((rc = decoder_step(ctx, ws, B, i, i == n_prompt - 1, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
         int32_t* done_host = fs.done_host;
@@ -403,9 +579,10 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     static const bool dbg_time = getenv("WDR_DEBUG_TIMING") != nullptr;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_h0 = now_ms();
-    std::vector<wdr_token_data> toks((size_t)B * kDecMaxTokens);
-    WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
-    WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
+    if (beam_K == 1) {
+        WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
+    }
     WDR_CUDA_TRY(cudaStreamSynchronize(s));
     const double t_h1 = now_ms();
     if (p.token_timestamps && !sw) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
@@ -711,8 +888,9 @@ static int full_range(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_h2d, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.done_host), sizeof(int32_t)));
     }
-    for (int c0 = c_begin; c0 < c_end; c0 += kDecMaxBatch) {
-        const int B = std::min(kDecMaxBatch, c_end - c0);
+    const int group_max = kDecMaxBatch / ((p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1);
+    for (int c0 = c_begin; c0 < c_end; c0 += group_max) {
+        const int B = std::min(group_max, c_end - c0);
         if (pcm_on_device) {
             rc = full_group<In>(ctx, st, p, lang_id, pcm + (size_t)c0 * chunk_stride, chunk_stride, n_valid, c0, B);
             if (rc != WDR_OK) return rc;
