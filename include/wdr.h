@@ -57,6 +57,15 @@ uint64_t wdr_launch_count(void);
 /* ---- audio (reference src/audio.rs:4-24, src/transcribe.rs:380-381, src/vad.rs:11-12) ---------- */
 /* whisper_rs::convert_integer_to_float_audio: out[i] = in[i] / 32768.0f, exact. Device kernel. */
 int wdr_convert_integer_to_float_audio(const int16_t* pcm, int n, float* out);
+/* Resample interleaved int16 PCM at any common rate to 16 kHz mono (north-star piece 1; the reference's audio::read_wav,
+ * src/audio.rs:9-20, only accepts 16 kHz mono and leaves the conversion to the caller).  Rational polyphase FIR on the
+ * device: up/down = 16000/rate reduced, 20*max(up,down)+1 Kaiser(beta 5) windowed-sinc taps with unit DC gain — the
+ * definition scipy.signal.resample_poly uses.  Channels are averaged.  out_i16 (round to nearest even, saturated) and/or
+ * out_f32 (unrounded / 32768) receive *n_out = wdr_resample_n_out(n_frames, rate) samples; WDR_ERR_UNSUPPORTED for rates
+ * whose reduced ratio needs more than 40001 taps, WDR_ERR_INVALID if out_cap is too small (*n_out is still set). */
+int64_t wdr_resample_n_out(int64_t n_frames, int sample_rate);
+int wdr_resample_i16(const int16_t* pcm, int64_t n_frames, int channels, int sample_rate, int16_t* out_i16, float* out_f32,
+                     int64_t out_cap, int64_t* n_out);
 
 /* ---- log-mel (whisper.cpp log_mel_spectrogram inside state.full, src/transcribe.rs:389) --------- */
 /* Mel front end: holds the [n_mel][201] filterbank (read from the ggml model file upstream), the

@@ -189,3 +189,35 @@ def test_kaldi_fbank_batch_dev(wdr, oracle):
 def test_signal_energy_bit_exact(wdr, oracle):
     x = synth_audio(77, 1.0).astype(np.float32) / 32768.0
     assert np.array_equal(wdr.signal_energy(x, 32), oracle.signal_energy(x, 32))
+
+
+@pytest.mark.parametrize("rate,channels,seconds", [(48000, 1, 1.3), (44100, 2, 0.9), (8000, 1, 2.0), (22050, 1, 0.7), (16000, 1, 0.5),
+                                                   (96000, 1, 0.4), (11025, 1, 0.6), (48000, 1, 0.0)])
+def test_resample_to_16k(wdr, rate, channels, seconds):
+    """wdr_resample_i16 (north-star piece 1) against oracle/resample.py (itself pinned to scipy.signal.resample_poly): the
+    float output within 2e-6 of full scale (fp32 vs float64 accumulation over <= 81 taps), the int16 output within 1 LSB and
+    identical wherever the exact value is not within 0.01 of a rounding boundary; 16 kHz input passes through unchanged."""
+    from oracle import resample as R
+    rng = np.random.default_rng(rate + channels)
+    n = int(seconds * rate)
+    t = np.arange(n) / rate
+    mono = 12000 * np.sin(2 * np.pi * 523.25 * t) + 6000 * np.sin(2 * np.pi * 2750 * t) + rng.normal(0, 500, n)
+    x = np.clip(np.rint(np.stack([mono * (1 - 0.2 * c) for c in range(channels)], axis=1)), -32768, 32767).astype(np.int16).reshape(-1)
+    got16, got32 = wdr.resample_to_16k(x, rate, channels, want_f32=True)
+    ref16, ref = R.resample_to_16k(x, rate, channels)
+    assert len(got16) == len(ref16) == R.n_out(n, rate)
+    if n == 0:
+        return
+    assert np.abs(got32.astype(np.float64) - ref).max() < 2e-6
+    d = np.abs(got16.astype(np.int32) - ref16.astype(np.int32))
+    assert d.max() <= 1
+    frac = np.abs((ref * 32768.0) - np.floor(ref * 32768.0) - 0.5)
+    assert not (d[frac > 0.01] != 0).any()
+    if rate == 16000:
+        assert np.array_equal(got16, x)
+
+
+def test_resample_rejects_unsupported_rate(wdr):
+    with pytest.raises(wdr.WdrError) as e:
+        wdr.resample_to_16k(np.zeros(1000, np.int16), 16001)
+    assert e.value.code == -7

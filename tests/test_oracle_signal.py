@@ -128,3 +128,23 @@ def test_oracle_signal_energy(oracle):
     x = np.array([1, -2, 3, -4, 5], np.float32)
     e = oracle.signal_energy(x, hw=1)
     assert np.allclose(e, np.array([3, 6, 9, 12, 9], np.float32) / 3)
+
+
+@pytest.mark.parametrize("rate,channels", [(48000, 1), (44100, 1), (8000, 1), (22050, 2), (16000, 1), (32000, 1)])
+def test_oracle_resampler_matches_scipy(rate, channels):
+    """The polyphase restatement (oracle/resample.py) against scipy.signal.resample_poly with the same Kaiser(5) design."""
+    from scipy.signal import resample_poly
+    from oracle import resample as R
+    rng = np.random.default_rng(rate)
+    n = 2 * rate // 5 + 7
+    t = np.arange(n) / rate
+    mono = 9000 * np.sin(2 * np.pi * 440 * t) + 4000 * np.sin(2 * np.pi * 3100 * t) + rng.normal(0, 300, n)
+    x = np.clip(np.rint(np.stack([mono + 50 * c for c in range(channels)], axis=1)), -32768, 32767).astype(np.int16)
+    got16, got = R.resample_to_16k(x.reshape(-1), rate, channels)
+    up, down = R.ratio(rate)
+    xm = x.astype(np.float32).sum(axis=1, dtype=np.float32) * np.float32(1.0 / channels) if channels > 1 else x[:, 0].astype(np.float32)
+    ref = resample_poly(xm.astype(np.float64), up, down, window=("kaiser", 5.0))
+    assert len(got) == len(ref) == R.n_out(n, rate)
+    assert np.abs(got * 32768.0 - ref).max() < 2e-3 * np.abs(ref).max() + 1e-6  # fp32-rounded taps vs scipy's float64 taps
+    if rate == 16000:
+        assert np.array_equal(got16, x[:, 0])  # identity: one tap of weight 1

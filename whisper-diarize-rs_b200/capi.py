@@ -100,6 +100,9 @@ def load():
     L.wdr_log_mel_batch_i16_dev.argtypes = L.wdr_log_mel_batch_f32_dev.argtypes
     L.wdr_log_mel_batch_i16.argtypes = [C.c_void_p, i16p, C.c_int64, i32p, C.c_int, C.c_int, f32p]
     L.wdr_convert_integer_to_float_audio.argtypes = [i16p, C.c_int, f32p]
+    L.wdr_resample_n_out.argtypes = [C.c_int64, C.c_int]
+    L.wdr_resample_n_out.restype = C.c_int64
+    L.wdr_resample_i16.argtypes = [i16p, C.c_int64, C.c_int, C.c_int, i16p, f32p, C.c_int64, C.POINTER(C.c_int64)]
     L.wdr_median_filter.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
     L.wdr_dtw_cost.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
     L.wdr_dtw.argtypes = [f32p, C.c_int, C.c_int, i32p, i32p, C.POINTER(C.c_int), f32p, i32p]
@@ -312,6 +315,22 @@ def convert_integer_to_float_audio(pcm_i16):
     out = np.empty(len(x), np.float32)
     _check(load().wdr_convert_integer_to_float_audio(_p(x, i16p), len(x), _p(out, f32p)))
     return out
+
+
+def resample_to_16k(pcm_i16, sample_rate, channels=1, want_f32=False):
+    """interleaved int16 at `sample_rate` -> 16 kHz mono int16 (and the unrounded f32 / 32768 if want_f32): wdr_resample_i16."""
+    x = _np(pcm_i16, np.int16).reshape(-1)
+    n_frames = len(x) // channels
+    n = int(load().wdr_resample_n_out(n_frames, int(sample_rate)))
+    if n < 0:
+        raise ValueError("bad sample rate")
+    o16 = np.empty(n, np.int16)
+    o32 = np.empty(n, np.float32) if want_f32 else None
+    n_out = C.c_int64(0)
+    _check(load().wdr_resample_i16(_p(x, i16p), n_frames, channels, int(sample_rate), _p(o16, i16p),
+                                   _p(o32, f32p) if want_f32 else None, n, C.byref(n_out)))
+    assert n_out.value == n
+    return (o16, o32) if want_f32 else o16
 
 
 def median_filter(w, width=7):
