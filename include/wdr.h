@@ -226,9 +226,11 @@ typedef struct wdr_token_data {
 } wdr_token_data;
 enum wdr_sampling_strategy { WDR_SAMPLING_GREEDY = 0, WDR_SAMPLING_BEAM_SEARCH = 1 };
 /* == whisper_full_params, the fields the crate sets (setup_params, src/transcribe.rs:20-87) plus whisper.cpp's defaults
- * for the rest.  Supported decoding: greedy at temperature 0 without temperature fallback (temperature_inc defaults to 0
- * here; beam search and the fallback ladder are SURVEY §8f-4 rows and are refused with WDR_ERR_UNSUPPORTED), language given
- * (no auto-detect), single_segment = 1 as the crate always sets (src/transcribe.rs:46).  Strings are borrowed for the call. */
+ * for the rest.  Supported decoding: greedy at temperature 0; beam search (beam_size <= 8) with whisper_full's temperature
+ * ladder (temperature_inc > 0: failing windows are decoded again at +temperature_inc ... <= 1).  temperature_inc defaults to 0
+ * here (whisper.cpp: 0.2) — set it to 0.2 for upstream's default behaviour.  Multinomial sampling (greedy strategy or
+ * best_of > 1 above temperature 0: whisper.cpp's per-decoder std::mt19937 stream) is refused with WDR_ERR_UNSUPPORTED.
+ * language given or "auto"; single_segment = 1 as the crate always sets (src/transcribe.rs:46).  Strings are borrowed for the call. */
 typedef struct wdr_full_params {
     int strategy;            /* enum wdr_sampling_strategy */
     int n_threads;           /* accepted, unused */
@@ -294,6 +296,9 @@ const char* wdr_token_to_str(wdr_context* ctx, int32_t token);                  
  * decode_steps = greedy iterations run. */
 int wdr_full_get_phase_ms(wdr_state* state, double* ms, int32_t* decode_steps);
 int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* info, float* no_speech_prob);
+/* Temperature of the ladder (temperature, +temperature_inc, ... <= 1) whose result stands for chunk i of the last full call;
+ * -1 if i is out of range. */
+float wdr_full_get_chunk_temperature_from_state(wdr_state* state, int i_chunk);
 /* Stage-level decoder access for parity tests: teacher-forced pass of `n_seq` tokens over window 0.. of the last encode/full call.
  * enc: optional HOST encoder output [n_chunks][1500][d] to install first (NULL = keep the state's).  seq: HOST [n_chunks][n_seq].
  * logits_out: HOST [n_chunks][n_seq][n_vocab] or NULL.  aheads_out: HOST [n_chunks][n_aheads][n_seq][1500] or NULL (needs a DTW

@@ -1,6 +1,8 @@
 """whisper_full_with_state as the reference drives it, composed from the oracle's C pieces, for ONE
 buffer of <= 30 s (the sharded mode of SURVEY §0.4: single_segment, no prompt carry, per-chunk mel max).  Test
 infrastructure only."""
+import math
+
 import numpy as np
 
 from . import native, vocab as V, weights as W, filters
@@ -40,29 +42,50 @@ def detect_language(dec, enc_out):
     return int(np.argmax(lg[v["lang0"]: v["lang0"] + n_l]))
 
 
-def beam_decode_window(dec, prompt, seek, seek_end, beam_size=5, delta_min=10, suppress_blank=True, max_initial_ts=1.0):
-    """whisper_full's beam search at temperature 0 for one window (the crate's default strategy, reference src/transcribe.rs:22,
-    29-32), restated from whisper.cpp: every live beam proposes its `beam_size` best tokens (by log-probability, ties to the lower
-    id); candidates are stably sorted by cumulative log-probability; each live beam, in index order, takes the next candidate and —
-    after the first iteration — skips the candidates that repeat its token sequence; the per-beam bookkeeping is the greedy loop's
-    (timestamp pairing, seek_delta, completion, failure); the winner is the non-failed beam with the best average log-probability
-    over its kept tokens (first maximum).  Not restated: the entropy test that only feeds the temperature fallback.
-    dec.set_audio(...) must have been called.  Returns the dict decode_window returns (tokens = the winner's)."""
+def sequence_entropy(tokens, result_len):
+    """whisper_sequence_score: entropy of the ids of the last 32 kept tokens (std::map order = ascending id)."""
+    ids = [t.id for t in tokens[max(0, result_len - 32): result_len]]
+    e = 0.0
+    for i in sorted(set(ids)):
+        p = ids.count(i) / len(ids)
+        e -= p * math.log(p)
+    return e
+
+
+def beam_decode_window(dec, prompt, seek, seek_end, beam_size=5, delta_min=10, suppress_blank=True, max_initial_ts=1.0,
+                       n_decoders=None, temperature=0.0, entropy_thold=2.4):
+    """whisper_full's beam search for one window at one temperature (the crate's default strategy, reference src/transcribe.rs:22,
+    29-32), restated from whisper.cpp: logits are divided by the temperature when it is > 0 (whisper_process_logits); every live
+    decoder proposes its `beam_size` best tokens (by log-probability, ties to the lower id); candidates are stably sorted by
+    cumulative log-probability; each live decoder, in index order, takes the next candidate and — after the first iteration — skips
+    the candidates that repeat its token sequence; the per-decoder bookkeeping is the greedy loop's (timestamp pairing, seek_delta,
+    completion, failure); ranking (whisper_sequence_score): failed decoders are skipped, a decoder whose last 32 kept tokens have
+    entropy < entropy_thold (result_len > 32) fails, the best average log-probability wins (first maximum, decoder 0 if none).
+    n_decoders: beam_size at temperature 0, max(1, greedy.best_of) = 1 above (whisper_full_default_params leaves best_of at -1 for
+    the beam strategy).  dec.set_audio(...) must have been called.  Returns the dict decode_window returns (tokens = the winner's)
+    plus dec_failed (the winner counts as failed for the fallback test) and avg_logprob."""
     nv = dec.a["n_vocab"]
     v = V.special_ids(nv)
     n_prompt = len(prompt)
     n_max = 448 // 2 - 4
+    n_dec = beam_size if n_decoders is None else n_decoders
+    T = np.float32(temperature)
+
+    def scaled(lg):
+        return (lg / T).astype(np.float32) if temperature > 0 else lg
+
     for i, t in enumerate(prompt):
         lg0 = dec.step(int(t), i, want_logits=(i == n_prompt - 1))
     kv0 = dec.get_kv()
-    lp0 = lg0 - (np.log(np.exp((lg0 - lg0.max()).astype(np.float32)).sum(dtype=np.float32)) + lg0.max())
+    ls0 = scaled(lg0)
+    lp0 = ls0 - (np.log(np.exp((ls0 - ls0.max()).astype(np.float32)).sum(dtype=np.float32)) + ls0.max())
     no_speech_prob = float(np.exp(np.float32(lp0[v["nosp"]])))
 
     class Beam:
         pass
 
     beams = []
-    for k in range(beam_size):
+    for k in range(n_dec):
         b = Beam()
         b.tokens, b.sum_all, b.has_ts, b.seek_delta, b.result_len, b.failed, b.completed = [], 0.0, 0, 3000, 0, False, False
         b.logits, b.kv = lg0, kv0
@@ -73,7 +96,7 @@ def beam_decode_window(dec, prompt, seek, seek_end, beam_size=5, delta_min=10, s
         for k, b in enumerate(beams):
             if b.completed or b.failed:
                 continue
-            _, _, lpb, pb = native.process_logits(b.logits, nv, [t.id for t in b.tokens], b.has_ts, b.seek_delta, suppress_blank, max_initial_ts)
+            _, _, lpb, pb = native.process_logits(scaled(b.logits), nv, [t.id for t in b.tokens], b.has_ts, b.seek_delta, suppress_blank, max_initial_ts)
             fin = np.flatnonzero(lpb > -np.inf)
             order = fin[np.lexsort((fin, -lpb[fin].astype(np.float64)))][:beam_size]
             g = native.sample_stats(pb, lpb, nv)  # tid / pt / ptsum of the distribution
@@ -147,22 +170,40 @@ def beam_decode_window(dec, prompt, seek, seek_end, beam_size=5, delta_min=10, s
             dec.set_kv(b.kv)
             b.logits = dec.step(b.tokens[-1].id, n_prompt + i)
             b.kv = dec.get_kv()
-    best, best_score = -1, -np.inf
+    best, best_score, failed_k = 0, -np.inf, [b.failed for b in beams]
     for k, b in enumerate(beams):
-        if b.failed or b.result_len <= 0:
+        if b.failed:
+            continue
+        if b.result_len <= 0:
+            failed_k[k] = True
             continue
         score = sum(float(t.plog) for t in b.tokens[: b.result_len]) / b.result_len
-        if best < 0 or score > best_score:
+        if b.result_len > 32 and sequence_entropy(b.tokens, b.result_len) < entropy_thold:
+            failed_k[k] = True
+            continue
+        if best_score < score:
             best, best_score = k, score
-    if best < 0:
-        best = 0
     w = beams[best]
     n_keep = len(w.tokens) if w.failed else w.result_len
+    avg = sum(float(t.plog) for t in w.tokens[: w.result_len]) / w.result_len if w.result_len > 0 else -np.inf
     return dict(tokens=w.tokens[:n_keep], seek_delta=w.seek_delta, failed=w.failed, completed=w.completed, n_sampled=len(w.tokens),
-                result_len=w.result_len, no_speech_prob=no_speech_prob, margins=np.zeros(0, np.float32), beam=best)
+                result_len=w.result_len, no_speech_prob=no_speech_prob, margins=np.zeros(0, np.float32), beam=best,
+                dec_failed=bool(failed_k[best]), avg_logprob=avg)
 
 
-def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10, lang_id=0, beam_size=1):
+def temperature_ladder(temperature_inc, temperature=0.0):
+    """whisper_full: for (float t = temperature; t < 1.0f + 1e-6f; t += temperature_inc) — float32 arithmetic."""
+    if temperature_inc <= 0:
+        return [float(temperature)]
+    out, t, inc = [], np.float32(temperature), np.float32(temperature_inc)
+    while t < np.float32(1.0) + np.float32(1e-6):
+        out.append(float(t))
+        t = np.float32(t + inc)
+    return out
+
+
+def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10, lang_id=0, beam_size=1,
+                temperature_inc=0.0, logprob_thold=-1.0, no_speech_thold=0.6, entropy_thold=2.4):
     """dec: native.Decoder; enc_out [1500, d] (encoder output for this window); pcm_f32: the window's samples (<= 480000).
     Returns dict(segments=[dict(t0, t1, text, tokens=[TokenData])], seek_delta, no_speech_prob, margins, ...)."""
     nv = dec.a["n_vocab"]
@@ -172,17 +213,27 @@ def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_mi
     if seek_end < seek + delta_min or seek + delta_min >= seek_end:
         return out
     dec.set_audio(enc_out)
-    if beam_size > 1:
-        r = beam_decode_window(dec, prompt_tokens(nv, lang_id), seek, seek_end, beam_size, delta_min)
-    else:
-        r = dec.decode_window(prompt_tokens(nv, lang_id), seek, seek_end, True, delta_min)
+    temps = temperature_ladder(temperature_inc)
+    assert len(temps) == 1 or beam_size > 1, "the ladder is restated for the beam strategy (deterministic: one decoder above T = 0)"
+    for it, t_cur in enumerate(temps):
+        if beam_size > 1:
+            r = beam_decode_window(dec, prompt_tokens(nv, lang_id), seek, seek_end, beam_size, delta_min,
+                                   n_decoders=beam_size if t_cur <= 0 else 1, temperature=t_cur, entropy_thold=entropy_thold)
+        else:
+            r = dec.decode_window(prompt_tokens(nv, lang_id), seek, seek_end, True, delta_min)
+        r["temperature"] = t_cur
+        # "was the decoding successful for the current temperature?" — the last temperature's result stands whatever it is
+        if it != len(temps) - 1 and (r["dec_failed"] or r["result_len"] <= 0 or
+                                     (r["avg_logprob"] < logprob_thold and r["no_speech_prob"] < no_speech_thold)):
+            continue
+        break
     out.update(r)
     toks = r["tokens"]
     if r["failed"]:
         avg_logprob = -np.inf
     else:
         avg_logprob = sum(float(t.plog) for t in toks) / max(1, r["result_len"]) if r["result_len"] else -np.inf
-    is_no_speech = r["no_speech_prob"] > 0.6 and avg_logprob < -1.0
+    is_no_speech = r["no_speech_prob"] > no_speech_thold and avg_logprob < logprob_thold
     out["is_no_speech"] = bool(is_no_speech)
     if not toks or is_no_speech:
         return out

@@ -137,7 +137,9 @@ def test_unsupported_params_fail_loudly(wdr):
         st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=9))  # beams beyond the 8 the row budget is cut for
     assert e.value.code == -7
     with pytest.raises(wdr.WdrError):
-        st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2))
+        st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2))  # greedy strategy above T = 0 = multinomial sampling: not restated
+    with pytest.raises(wdr.WdrError):
+        st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=5, temperature=0.2))  # the ladder starts at 0
     with pytest.raises(wdr.WdrError):
         st.full(np.zeros(16000, np.int16), st.full_params(language="xx"))
     with pytest.raises(wdr.WdrError):
@@ -374,5 +376,65 @@ def test_beam_search_matches_oracle(wdr, oracle, tiny_w):
     long = np.concatenate([pcm[0], pcm[2][:200000]])
     s_long = st.full(long, st.full_params(strategy=1, beam_size=5))
     assert len(s_long) >= 2 and s_long[0]["t0"] <= s_long[1]["t0"]
+    st.close()
+    ctx.close()
+
+
+def test_temperature_fallback_matches_oracle(wdr, oracle, tiny_w):
+    """The temperature ladder of whisper_full for the crate's default strategy (beam search; whisper.cpp's temperature_inc > 0):
+    a window whose best decoder failed or whose average log-probability is below logprob_thold is decoded again at the next
+    temperature (logits / T, one decoder, beam_size candidates), the last temperature's result stands.  logprob_thold is put
+    between the two windows' T = 0 scores, so one window stops at T = 0 and the other goes up the ladder; a second call with a
+    threshold nothing can meet walks it to the end.  Everything (final temperature, tokens, statistics, segment / token / DTW
+    times) equals the oracle's restatement."""
+    from oracle import weights as W, full
+    arch = "tiny.en"
+    B = 2
+    pcm = np.zeros((B, 480000), np.int16)
+    nv = np.array([480000, 200000], np.int32)
+    for b in range(B):
+        a = synth_audio(2100 + b, nv[b] / 16000.0)
+        pcm[b, : len(a)] = a[: nv[b]]
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    hid = st.encode_chunks(pcm, nv)
+    xs = [pcm[b, : nv[b]].astype(np.float32) / np.float32(32768.0) for b in range(B)]
+    dec = oracle.Decoder(arch, W.pack_decoder(arch, tiny_w), bf16=True)
+    avg0 = [full.full_window(dec, hid[b], xs[b], beam_size=5, dtw=False, token_timestamps=False)["avg_logprob"] for b in range(B)]
+    assert abs(avg0[0] - avg0[1]) > 1e-3
+    thold = 0.5 * (avg0[0] + avg0[1])
+    segs = st.full_batch(pcm, nv, st.full_params(strategy=1, beam_size=5, temperature_inc=0.4, logprob_thold=thold))
+    by_chunk = {s["chunk"]: s for s in segs}
+    temps = []
+    for b in range(B):
+        ref = full.full_window(dec, hid[b], xs[b], beam_size=5, temperature_inc=0.4, logprob_thold=thold)
+        info = st.chunk_info(b)
+        temps.append(info["temperature"])
+        assert abs(info["temperature"] - ref["temperature"]) < 1e-6, (b, info["temperature"], ref["temperature"])
+        got = by_chunk.get(b)
+        assert (got is not None) == bool(ref["segments"]), b
+        assert info["seek_delta"] == ref["seek_delta"] and info["n_sampled"] == ref["n_sampled"] and info["failed"] == int(ref["failed"])
+        assert abs(info["no_speech_prob"] - ref["no_speech_prob"]) <= 1e-3 * ref["no_speech_prob"] + 1e-9
+        if got is None:
+            continue
+        r = ref["segments"][0]
+        assert [t.id for t in got["tokens"]] == [t.id for t in r["tokens"]], (b, ref["temperature"])
+        assert (got["t0"], got["t1"], got["text"]) == (r["t0"], r["t1"], r["text"])
+        for tg, tr in zip(got["tokens"], r["tokens"]):
+            assert tg.tid == tr.tid and abs(tg.p - tr.p) <= 1e-3 * tr.p + 1e-9 and abs(tg.plog - tr.plog) <= 2e-3
+            assert (tg.t0, tg.t1, tg.t_dtw) == (tr.t0, tr.t1, tr.t_dtw), (b, tg.id)
+    assert min(temps) == 0.0 and max(temps) > 0.0, temps  # one window stopped at T = 0, the other went up the ladder
+    # a threshold nothing can meet: every window walks the ladder to its last temperature, whose result stands
+    segs = st.full_batch(pcm, nv, st.full_params(strategy=1, beam_size=5, temperature_inc=0.4, logprob_thold=0.0))
+    assert [round(st.chunk_info(b)["temperature"], 3) for b in range(B)] == [0.8, 0.8]
+    ref = full.full_window(dec, hid[1], xs[1], beam_size=5, temperature_inc=0.4, logprob_thold=0.0)
+    assert abs(ref["temperature"] - 0.8) < 1e-6
+    got = {s["chunk"]: s for s in segs}.get(1)
+    assert (got is not None) == bool(ref["segments"])
+    if got is not None:
+        r = ref["segments"][0]
+        assert [t.id for t in got["tokens"]] == [t.id for t in r["tokens"]]
+        assert [(t.t0, t.t1, t.t_dtw) for t in got["tokens"]] == [(t.t0, t.t1, t.t_dtw) for t in r["tokens"]]
+    dec.close()
     st.close()
     ctx.close()

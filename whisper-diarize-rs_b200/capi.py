@@ -159,6 +159,8 @@ def load():
     L.wdr_token_to_str.argtypes = [C.c_void_p, C.c_int32]
     L.wdr_token_to_str.restype = C.c_char_p
     L.wdr_full_get_chunk_info_from_state.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
+    L.wdr_full_get_chunk_temperature_from_state.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_full_get_chunk_temperature_from_state.restype = C.c_float
     L.wdr_decode_teacher_forced.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, i32p, C.c_int, f32p, f32p]
     L.wdr_vad_default_context_params.restype = VadContextParams
     L.wdr_vad_default_params.restype = VadParams
@@ -574,6 +576,7 @@ class State:
         keys = ["seek_delta", "failed", "completed", "n_sampled", "has_ts", "result_len", "seek_end", "n_segments"]
         d = {k: int(v) for k, v in zip(keys, info)}
         d["no_speech_prob"] = float(nsp.value)
+        d["temperature"] = float(load().wdr_full_get_chunk_temperature_from_state(self._h, i))
         return d
 
     def lang_id(self):

@@ -268,7 +268,7 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
                       const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
                       float* __restrict__ aw, const int64_t* __restrict__ aw_off, const int32_t* __restrict__ aw_T,
                       const int32_t* __restrict__ aw_A, const int32_t* __restrict__ pos_ptr, int pos, const DecWinState* __restrict__ win,
-                      const int32_t* __restrict__ t_limit, int rows_per_window /* beam search: rows b share the cross cache of window b / rows_per_window */) {
+                      const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window /* beam search / fallback: row b reads the cross cache of window row_window[b]; null = b */) {
     __shared__ float q[64];
     __shared__ float p[kT + 4];
     __shared__ float red[32];
@@ -286,7 +286,7 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
 #pragma unroll
     for (int j = 0; j < 8; j++) q8[j] = q[g * 8 + j];
     // head-major cross cache: [(window, head)][K | V][1500][64] — both blocks of a CTA are contiguous 192 KB streams
-    const __nv_bfloat16* Kb = ckv + ((int64_t)(b / rows_per_window) * gridDim.x + hh) * 2 * kT * 64 + g * 8;
+    const __nv_bfloat16* Kb = ckv + ((int64_t)(row_window ? row_window[b] : b) * gridDim.x + hh) * 2 * kT * 64 + g * 8;
     const __nv_bfloat16* Vb = Kb + kT * 64;
     const int64_t rs = 64;
     // ---- scores ----
@@ -739,8 +739,9 @@ dec_sample_kernel(const float* __restrict__ logits, int64_t ldv, DecWinState* __
 // Beam search: whisper_process_logits for one row from its own history summary (BeamRow), then the k best tokens by log-probability
 // (ties: lower id) with the statistics whisper_sample_token_topk attaches to each (p, plog; tid, pt, ptsum of the distribution).
 __global__ void __launch_bounds__(kSampThreads, 1)
-dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __restrict__ rows, const SampleParams sp, int k_top,
-                BeamCand* __restrict__ cands /* [rows][kBeamMax] */, float* __restrict__ no_speech /* [rows], written when n_cur == 0 */) {
+dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __restrict__ rows, const SampleParams sp, int k_top, float temperature,
+                BeamCand* __restrict__ cands /* [rows][kBeamMax] */, float* __restrict__ no_speech /* [rows], written when n_cur == 0 */,
+                float* __restrict__ probs_out /* optional [rows][ldv]: the processed distribution (temperature sampling on the host) */) {
     __shared__ float red[32];
     __shared__ unsigned long long red64[32];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -756,6 +757,7 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
     for (int k = 0; k < kSampPer; k++) {
         const int i = tid + k * kSampThreads;
         v[k] = (i < n) ? lg[i] : -INFINITY;
+        if (temperature > 0.0f) v[k] = __fdiv_rn(v[k], temperature);  // whisper_process_logits: logits[i] /= temperature, first of all
     }
     if (is_initial) {
         float m = -INFINITY;
@@ -766,7 +768,7 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
 #pragma unroll
         for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) s += expf(v[k] - m);
         s = block_sum(s, red);
-        if (tid == 0) no_speech[b] = expf(lg[sp.nosp] - (logf(s) + m));
+        if (tid == 0) no_speech[b] = expf((temperature > 0.0f ? __fdiv_rn(lg[sp.nosp], temperature) : lg[sp.nosp]) - (logf(s) + m));
     }
     const int ts_floor = st.has_ts ? sp.beg + st.seek_delta / 2 : sp.beg;
 #pragma unroll
@@ -820,6 +822,7 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
         const int i = tid + k * kSampThreads;
         if (mask_text && i < sp.beg) v[k] = -INFINITY;
         const float pr = v[k] > -INFINITY ? expf(v[k]) : 0.0f;
+        if (probs_out && i < n) probs_out[(int64_t)b * ldv + i] = pr;
         if (pr > 0.0f && i >= sp.beg) {
             const unsigned long long key = ((unsigned long long)__float_as_uint(pr) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
             sum_ts += pr;
@@ -880,7 +883,7 @@ __global__ void beam_anc_kernel(const int32_t* __restrict__ anc_old, int32_t* __
 void DecoderWorkspace::release() {
     for (void* p : {(void*)enc_bf16, (void*)sk, (void*)sv, (void*)x, (void*)h, (void*)att, (void*)ff, (void*)part, (void*)logits, (void*)seq,
                     (void*)tokens, (void*)win, (void*)done_count, (void*)pos_dev, (void*)beam_anc[0], (void*)beam_anc[1], (void*)beam_limit, (void*)beam_rows,
-                    (void*)beam_cands, (void*)beam_parent, (void*)beam_nosp, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
+                    (void*)beam_cands, (void*)beam_parent, (void*)beam_nosp, (void*)beam_rowwin, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
         if (p) cudaFree(p);
     for (auto p : ckv) if (p) cudaFree(p);
     if (step_graph) cudaGraphExecDestroy(step_graph);
@@ -918,6 +921,7 @@ int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
     WDR_CUDA_TRY(cudaMalloc(&beam_cands, sizeof(BeamCand) * kDecMaxBatch * kBeamMax));
     WDR_CUDA_TRY(cudaMalloc(&beam_parent, sizeof(int32_t) * kDecMaxBatch));
     WDR_CUDA_TRY(cudaMalloc(&beam_nosp, sizeof(float) * kDecMaxBatch));
+    WDR_CUDA_TRY(cudaMalloc(&beam_rowwin, sizeof(int32_t) * kDecMaxBatch));
     WDR_CUDA_TRY(cudaMalloc(&ahead_map, sizeof(int32_t) * n_layer * n_head));
     WDR_CUDA_TRY(cudaMalloc(&aw_off, sizeof(int64_t) * B));
     WDR_CUDA_TRY(cudaMalloc(&aw_T, sizeof(int32_t) * B));
@@ -1057,7 +1061,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             // flight than the two independent passes do.
             WDR_CUDA_TRY(launch_kernel(dec_cross_attn_kernel<6>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
                                        (int64_t)ws.cap_B * d, capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T, ws.aw_A, pos_ptr, pos,
-                                       win, t_limit, beam ? ws.beam_width : 1));
+                                       win, t_limit, beam ? ws.beam_rowwin : nullptr));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
@@ -1224,10 +1228,11 @@ int decoder_sample(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos,
     return WDR_OK;
 }
 
-int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, cudaStream_t st, Profiler* prof) {
+int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, float temperature, float* probs_out,
+                 cudaStream_t st, Profiler* prof) {
     WDR_REQUIRE(sp.n_vocab <= kSampThreads * kSampPer && k_top >= 1 && k_top <= kBeamMax && R <= kDecMaxBatch, "decoder_topk: bad arguments");
     ProfScope ps(prof, KC_DECODER, st);
-    dec_topk_kernel<<<R, kSampThreads, 0, st>>>(ws.logits, ws.ldv, ws.beam_rows, sp, k_top, ws.beam_cands, ws.beam_nosp);
+    dec_topk_kernel<<<R, kSampThreads, 0, st>>>(ws.logits, ws.ldv, ws.beam_rows, sp, k_top, temperature, ws.beam_cands, ws.beam_nosp, probs_out);
     WDR_LAUNCH_CHECK();
     return WDR_OK;
 }

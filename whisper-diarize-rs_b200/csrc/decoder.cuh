@@ -65,7 +65,7 @@ struct DecoderWorkspace {
     BeamCand* beam_cands = nullptr;
     int32_t* beam_parent = nullptr;
     float* beam_nosp = nullptr;
-    int beam_width = 1;
+    int32_t* beam_rowwin = nullptr;    // [128] row -> window whose cross cache it reads
     cudaGraphExec_t step_graph = nullptr;  // one greedy iteration (sample, advance, step), see decoder_decode_graph
     int graph_B = 0, graph_nodes = 0;
     SampleParams graph_sp{};
@@ -104,10 +104,13 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 //       DEC_MODE_FORCED = teacher-forced, every window runs;
 //       DEC_MODE_DTW    = teacher-forced DTW pass: alignment-head cross-attention rows go to ws.aw, windows stop at their own
 //                         length ws.aw_T[b], and without logits only the layers up to the last alignment head run.
-//       DEC_MODE_BEAM   = beam search: rows = windows x ws.beam_width; a window's rows share its cross cache, the self cache of a
+//       DEC_MODE_BEAM   = beam search / temperature fallback: row b decodes window ws.beam_rowwin[b] (shared cross cache), the self cache of a
 //                         row is read through the ancestry table ws.beam_anc_cur, rows with ws.beam_limit[b] <= pos are skipped.
 enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2, DEC_MODE_BEAM = 3 };
-int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, cudaStream_t st, Profiler* prof);
+// temperature > 0: logits are divided by it first (whisper_process_logits); probs_out (optional, [R][ws.ldv]) receives the processed
+// distribution of every active row (what whisper_sample_token draws from at temperature > 0)
+int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, float temperature, float* probs_out,
+                 cudaStream_t st, Profiler* prof);
 int decoder_beam_reorder(DecoderWorkspace& ws, int R, int pos_last, cudaStream_t st);
 int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, bool want_logits, int mode, cudaStream_t st, Profiler* prof,
                  bool pos_on_device = false, bool pdl = false);

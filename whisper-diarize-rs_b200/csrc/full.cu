@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <map>
 #include <vector>
 #include <cuda_profiler_api.h>
 #include "common.cuh"
@@ -200,7 +201,14 @@ static SampleParams make_sample_params(const Vocab& v, const wdr_full_params& p)
 
 static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int* lang_id) {
     if (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > kBeamMax) { set_error("beam_size %d exceeds the supported maximum of %d", p.beam_size, kBeamMax); return WDR_ERR_UNSUPPORTED; }
-    if (p.temperature != 0.0f || p.temperature_inc != 0.0f) { set_error("only temperature 0 without fallback is implemented (temperature %g, temperature_inc %g)", p.temperature, p.temperature_inc); return WDR_ERR_UNSUPPORTED; }
+    if (p.temperature != 0.0f) { set_error("the temperature ladder must start at 0 (temperature %g)", p.temperature); return WDR_ERR_UNSUPPORTED; }
+    if (p.temperature_inc < 0.0f) { set_error("temperature_inc must be >= 0"); return WDR_ERR_INVALID; }
+    if (p.temperature_inc > 0.0f && (p.strategy != WDR_SAMPLING_BEAM_SEARCH || p.greedy_best_of > 1)) {
+        // greedy strategy at T > 0 (and best_of > 1 decoders) draws from whisper.cpp's per-decoder std::mt19937 stream: not restated
+        set_error("temperature fallback is implemented for the beam-search strategy with best_of <= 1 (deterministic); "
+                  "multinomial sampling at temperature > 0 is not");
+        return WDR_ERR_UNSUPPORTED;
+    }
     if (!p.single_segment) { set_error("single_segment = 0 is not implemented (the crate always sets it, src/transcribe.rs:46)"); return WDR_ERR_UNSUPPORTED; }
     if (p.no_timestamps) { set_error("no_timestamps = 1 is not implemented"); return WDR_ERR_UNSUPPORTED; }
     if (p.detect_language || (p.language && strcmp(p.language, "auto") == 0)) {  // whisper_lang_auto_detect: decided per buffer on the device
@@ -237,14 +245,17 @@ static int grow_pinned(T** p, size_t* cap, size_t need) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Beam search (whisper_full with WHISPER_SAMPLING_BEAM_SEARCH at temperature 0 — the crate's default strategy,
-// reference src/transcribe.rs:22, 29-32).  Rows of the decode batch = windows x beams.  Per iteration the device scores every
-// live row (whisper_process_logits + the K best tokens, dec_topk_kernel); the host runs whisper.cpp's candidate logic per
-// window — K candidates per live beam, stable sort by cumulative log-probability, each live beam takes the next candidate that
-// is not a duplicate of the previous one (after the first iteration), then the per-beam bookkeeping of the greedy loop
-// (timestamp pairing, seek_delta, completion, failure) — and sends back parents + tokens; the self cache is never copied:
-// beam_anc_kernel re-threads an ancestry table that the self-attention kernel reads through.  Ranking: average log-probability
-// over the kept tokens, first maximum.  Not restated: the entropy check that feeds the temperature fallback (no fallback here).
+// Beam search and the temperature ladder (whisper_full with WHISPER_SAMPLING_BEAM_SEARCH — the crate's default strategy,
+// reference src/transcribe.rs:22, 29-32 — at one temperature of `for t = temperature; t < 1 + 1e-6; t += temperature_inc`).
+// Rows of the decode batch = the windows of this pass x Kd decoders (T = 0: Kd = beam_size; T > 0: Kd = max(1, greedy.best_of),
+// which whisper_full_default_params leaves at -1 for the beam strategy, so one decoder).  Per iteration the device scores every live
+// row (whisper_process_logits on logits / T + the Kc = beam_size best tokens, dec_topk_kernel); the host runs whisper.cpp's candidate
+// logic per window — Kc candidates per live decoder, stable sort by cumulative log-probability, each live decoder takes the next
+// candidate that is not a duplicate of the previous one (after the first iteration), then the per-decoder bookkeeping of the greedy
+// loop (timestamp pairing, seek_delta, completion, failure) — and sends back parents + tokens; the self cache is never copied:
+// beam_anc_kernel re-threads an ancestry table that the self-attention kernel reads through.  Ranking (whisper_sequence_score):
+// decoders that failed are skipped, a decoder whose last 32 kept tokens have entropy < entropy_thold (result_len > 32) fails,
+// the best score (sum of log-probabilities / length, or the length_penalty form) wins, first maximum, decoder 0 if none.
 // ---------------------------------------------------------------------------------------------------
 struct HostBeam {
     std::vector<wdr_token_data> tokens;
@@ -253,27 +264,54 @@ struct HostBeam {
     bool failed = false, completed = false;
 };
 
+// entropy of the ids of the last 32 kept tokens (whisper_sequence_score: std::map order = ascending id)
+static double sequence_entropy(const wdr_token_data* t, int result_len) {
+    std::map<int32_t, int> counts;
+    int cnt = 0;
+    for (int i = std::max(0, result_len - 32); i < result_len; i++) { counts[t[i].id]++; cnt++; }
+    double e = 0.0;
+    for (auto& kv : counts) { const double pr = (double)kv.second / cnt; e -= pr * log(pr); }
+    return e;
+}
+
+static double sequence_score(const wdr_token_data* t, int result_len, float length_penalty, double* avg) {
+    double sum = 0.0;
+    for (int j = 0; j < result_len; j++) sum += t[j].plog;
+    *avg = sum / result_len;
+    double penalty = result_len;
+    if (length_penalty > 0.0f) penalty = pow((5.0 + penalty) / 6.0, (double)length_penalty);
+    return sum / penalty;
+}
+
+// wins: the windows of this pass (indices into win / toks_out / seq_win).  On return win[w] / toks_out[w] hold the best decoder of
+// every window w of the pass and dec_failed[w] says whether that decoder counts as failed for the fallback test.
 static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, const wdr_full_params& p, const SampleParams& sp, const Vocab& v,
-                       int B, int K, int n_prompt, const std::vector<int32_t>& seq_win /* [B][448] */, std::vector<DecWinState>& win,
-                       std::vector<wdr_token_data>& toks_out /* [B][224] */, int* steps_out) {
+                       const std::vector<int>& wins, int Kd, int Kc, float temperature, int n_prompt, const std::vector<int32_t>& seq_win /* [B][448] */,
+                       std::vector<DecWinState>& win, std::vector<wdr_token_data>& toks_out /* [B][224] */, std::vector<char>& dec_failed, int* steps_out) {
     cudaStream_t s = st->stream;
-    const int R = B * K, n_max = sp.n_max;
+    const int nW = (int)wins.size(), K = Kd;
+    const int R = nW * K, n_max = sp.n_max;
+    WDR_REQUIRE(R >= 1 && R <= kDecMaxBatch && R <= ws.cap_B && Kc >= 1 && Kc <= kBeamMax, "beam_decode: bad batch");
     int rc;
     std::vector<int32_t> seq((size_t)R * kDecSeqCap);
-    for (int r = 0; r < R; r++) memcpy(&seq[(size_t)r * kDecSeqCap], &seq_win[(size_t)(r / K) * kDecSeqCap], sizeof(int32_t) * kDecSeqCap);
+    std::vector<int32_t> rowwin(kDecMaxBatch, 0);
+    for (int r = 0; r < R; r++) {
+        memcpy(&seq[(size_t)r * kDecSeqCap], &seq_win[(size_t)wins[r / K] * kDecSeqCap], sizeof(int32_t) * kDecSeqCap);
+        rowwin[r] = wins[r / K];
+    }
     std::vector<int32_t> anc((size_t)kDecSeqCap * kDecMaxBatch);
     for (int t = 0; t < kDecSeqCap; t++)
         for (int b = 0; b < kDecMaxBatch; b++) anc[(size_t)t * kDecMaxBatch + b] = b;
     std::vector<int32_t> limit(kDecMaxBatch, 0);
-    for (int r = 0; r < R; r++) limit[r] = win[r / K].completed ? 0 : 1 << 30;
-    ws.beam_width = K;
+    for (int r = 0; r < R; r++) limit[r] = win[wins[r / K]].completed ? 0 : 1 << 30;
     ws.beam_anc_cur = ws.beam_anc[0];
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_anc[0], anc.data(), sizeof(int32_t) * anc.size(), cudaMemcpyHostToDevice, s));
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_limit, limit.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, s));
+    WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_rowwin, rowwin.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, s));
     for (int i = 0; i < n_prompt; i++)
         if ((rc = decoder_step(ctx, ws, R, i, i == n_prompt - 1, DEC_MODE_BEAM, s, &st->prof)) != WDR_OK) return rc;
-    std::vector<std::vector<HostBeam>> beams(B, std::vector<HostBeam>(K));
+    std::vector<std::vector<HostBeam>> beams(nW, std::vector<HostBeam>(K));
     std::vector<BeamRow> rows(R);
     std::vector<BeamCand> cands((size_t)R * kBeamMax);
     std::vector<float> nosp(R, 0.0f);
@@ -284,7 +322,7 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
         for (int r = 0; r < R; r++) {
             const HostBeam& hb = beams[r / K][r % K];
             BeamRow br;
-            br.active = !win[r / K].completed && !hb.completed && !hb.failed;
+            br.active = !win[wins[r / K]].completed && !hb.completed && !hb.failed;
             br.n_cur = (int)hb.tokens.size();
             br.last_id = br.n_cur > 0 ? hb.tokens[br.n_cur - 1].id : 0;
             br.penult_id = br.n_cur > 1 ? hb.tokens[br.n_cur - 2].id : 0;
@@ -293,22 +331,22 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
             rows[r] = br;
         }
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_rows, rows.data(), sizeof(BeamRow) * R, cudaMemcpyHostToDevice, s));
-        if ((rc = decoder_topk(ctx, ws, R, sp, K, s, &st->prof)) != WDR_OK) return rc;
+        if ((rc = decoder_topk(ctx, ws, R, sp, Kc, temperature, nullptr, s, &st->prof)) != WDR_OK) return rc;
         WDR_CUDA_TRY(cudaMemcpyAsync(cands.data(), ws.beam_cands, sizeof(BeamCand) * (size_t)R * kBeamMax, cudaMemcpyDeviceToHost, s));
         if (i == 0) WDR_CUDA_TRY(cudaMemcpyAsync(nosp.data(), ws.beam_nosp, sizeof(float) * R, cudaMemcpyDeviceToHost, s));
         WDR_CUDA_TRY(cudaStreamSynchronize(s));
         steps = i + 1;
         if (i == 0)
-            for (int w = 0; w < B; w++) win[w].no_speech_prob = nosp[(size_t)w * K];
+            for (int w = 0; w < nW; w++) win[wins[w]].no_speech_prob = nosp[(size_t)w * K];
         bool any_live = false;
         for (int r = 0; r < R; r++) { parent[r] = r; next_tok[r] = v.eot; }
-        for (int w = 0; w < B; w++) {
-            if (win[w].completed) continue;
+        for (int w = 0; w < nW; w++) {
+            if (win[wins[w]].completed) continue;
             std::vector<HostBeam>& bw = beams[w];
             std::vector<Cand> cl;
             for (int k = 0; k < K; k++) {
                 if (bw[k].completed || bw[k].failed) continue;
-                for (int r = 0; r < K; r++) {
+                for (int r = 0; r < Kc; r++) {
                     const BeamCand& c = cands[((size_t)w * K + k) * kBeamMax + r];
                     if (c.id >= 0) cl.push_back({k, r, bw[k].sum_all + (double)c.plog});
                 }
@@ -338,8 +376,8 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
                 td.id = c.id; td.tid = c.tid; td.p = c.p; td.plog = c.plog; td.pt = c.pt; td.ptsum = c.ptsum; td.t0 = -1; td.t1 = -1; td.t_dtw = -1;
                 h.tokens.push_back(td);
                 h.sum_all = cur.sum;
-                // ---- per-beam bookkeeping (the greedy loop's rules) ----
-                const int seek = win[w].seek, seek_end = win[w].seek_end;
+                // ---- per-decoder bookkeeping (the greedy loop's rules) ----
+                const int seek = win[wins[w]].seek, seek_end = win[wins[w]].seek_end;
                 bool done = false;
                 if (td.id > v.beg) {
                     const int sd_new = 2 * (td.id - v.beg);
@@ -373,7 +411,7 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
         const int pos_last = n_prompt - 1 + i;
         for (int r = 0; r < R; r++) {
             const HostBeam& hb = beams[r / K][r % K];
-            limit[r] = (win[r / K].completed || hb.completed || hb.failed) ? 0 : 1 << 30;
+            limit[r] = (win[wins[r / K]].completed || hb.completed || hb.failed) ? 0 : 1 << 30;
         }
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_parent, parent.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_limit, limit.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, s));
@@ -382,25 +420,28 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
         if ((rc = decoder_step(ctx, ws, R, pos_last + 1, true, DEC_MODE_BEAM, s, &st->prof)) != WDR_OK) return rc;
         WDR_CUDA_TRY(cudaStreamSynchronize(s));  // parent / limit / next_tok are reused by the next iteration
     }
-    // ---- rank the beams of every window: average log-probability over the kept tokens, first maximum ----
-    for (int w = 0; w < B; w++) {
-        if (win[w].completed) continue;  // was never decoded (too short)
-        int best = -1;
+    // ---- rank the decoders of every window (whisper_sequence_score + the entropy test) ----
+    for (int w = 0; w < nW; w++) {
+        DecWinState& ww = win[wins[w]];
+        if (ww.completed) continue;  // was never decoded (too short)
+        int best = 0;
         double best_score = -INFINITY;
+        std::vector<char> failed_k(K, 0);
         for (int k = 0; k < K; k++) {
             const HostBeam& h = beams[w][k];
-            if (h.failed || h.result_len <= 0) continue;
-            double sum = 0.0;
-            for (int j = 0; j < h.result_len; j++) sum += h.tokens[j].plog;
-            const double score = sum / h.result_len;
-            if (best < 0 || score > best_score) { best = k; best_score = score; }
+            failed_k[k] = h.failed;
+            if (h.failed) continue;
+            if (h.result_len <= 0) { failed_k[k] = 1; continue; }  // nothing kept: whisper_sequence_score returns early and the stale score never wins
+            double avg;
+            const double score = sequence_score(h.tokens.data(), h.result_len, p.length_penalty, &avg);
+            if (h.result_len > 32 && sequence_entropy(h.tokens.data(), h.result_len) < (double)p.entropy_thold) { failed_k[k] = 1; continue; }
+            if (best_score < score) { best = k; best_score = score; }
         }
-        if (best < 0) best = 0;  // every beam failed: keep beam 0's tokens as a failed decode (there is no temperature to fall back to)
         const HostBeam& h = beams[w][best];
-        DecWinState& ww = win[w];
         ww.n_cur = (int)h.tokens.size(); ww.has_ts = h.has_ts; ww.seek_delta = h.seek_delta; ww.result_len = h.result_len;
         ww.failed = h.failed ? 1 : 0; ww.completed = h.completed ? 1 : 0;
-        for (size_t j = 0; j < h.tokens.size() && j < (size_t)kDecMaxTokens; j++) toks_out[(size_t)w * kDecMaxTokens + j] = h.tokens[j];
+        dec_failed[wins[w]] = failed_k[best];
+        for (size_t j = 0; j < h.tokens.size() && j < (size_t)kDecMaxTokens; j++) toks_out[(size_t)wins[w] * kDecMaxTokens + j] = h.tokens[j];
     }
     *steps_out = steps;
     return WDR_OK;
@@ -431,7 +472,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     int rc;
     const int beam_K = (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1;  // rows per window of the decode batch
     WDR_REQUIRE(B * beam_K <= kDecMaxBatch, "windows x beams exceeds the 128-row decode batch");
-    if ((rc = ws.reserve(ctx, B * beam_K)) != WDR_OK) return rc;
+    if ((rc = ws.reserve(ctx, std::max(B * beam_K, B))) != WDR_OK) return rc;  // fallback passes: <= B rows (one decoder per failing window)
     // ---- n_valid on the device ----
     if ((rc = grow_dev(&fs.nvalid_dev, &fs.nvalid_cap, (size_t)B)) != WDR_OK) return rc;
     std::vector<int32_t> nv(B);
@@ -493,30 +534,45 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         return WDR_OK;
     }
     // ---- prompt + decoder state ----
-    std::vector<int32_t> prompt;
+    // whisper_full: [PREV] + the tail of prompt_past only while the temperature is below 0.5, then [SOT, (LANG, TASK)]
     const int32_t* past = sw ? sw->prompt_past->data() : p.prompt_tokens;
     const int n_past = sw ? (int)sw->prompt_past->size() : p.prompt_n_tokens;
-    if (past && n_past > 0 && p.n_max_text_ctx > 0) {
-        const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), n_past);
-        prompt.push_back(v.prev);
-        for (int i = n_past - n_take; i < n_past; i++) prompt.push_back(past[i]);
-    }
-    prompt.push_back(v.sot);
     int lang_slot = -1;  // position of the language token in the prompt (per-window value)
-    if (v.multilingual) {
-        lang_slot = (int)prompt.size();
-        prompt.push_back(v.lang0 + std::max(lang[0], 0));
-        prompt.push_back(p.translate ? v.translate : v.transcribe);
-    }
-    const int n_prompt = (int)prompt.size();
+    auto build_prompt = [&](bool with_past) {
+        std::vector<int32_t> prompt;
+        if (with_past && past && n_past > 0 && p.n_max_text_ctx > 0) {
+            const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), n_past);
+            prompt.push_back(v.prev);
+            for (int i = n_past - n_take; i < n_past; i++) prompt.push_back(past[i]);
+        }
+        prompt.push_back(v.sot);
+        lang_slot = -1;
+        if (v.multilingual) {
+            lang_slot = (int)prompt.size();
+            prompt.push_back(v.lang0 + std::max(lang[0], 0));
+            prompt.push_back(p.translate ? v.translate : v.transcribe);
+        }
+        return prompt;
+    };
+    std::vector<float> temps;  // the temperature ladder
+    if (p.temperature_inc > 0.0f) for (float t = p.temperature; t < 1.0f + 1e-6f; t += p.temperature_inc) temps.push_back(t);
+    else temps.push_back(p.temperature);
+    std::vector<int32_t> prompt = build_prompt(temps[0] < 0.5f);
+    int n_prompt = (int)prompt.size();
     const int n_max = WDR_TEXT_CTX / 2 - 4;
     WDR_REQUIRE(n_prompt + n_max <= kDecSeqCap, "prompt too long");
     std::vector<int32_t> seq((size_t)B * kDecSeqCap, v.eot);
     std::vector<DecWinState> win(B);
     int n_skip = 0;
+    auto fill_seq = [&]() {
+        std::fill(seq.begin(), seq.end(), v.eot);
+        for (int b = 0; b < B; b++) {
+            for (int i = 0; i < n_prompt; i++) seq[(size_t)b * kDecSeqCap + i] = prompt[i];
+            if (lang_slot >= 0) seq[(size_t)b * kDecSeqCap + lang_slot] = v.lang0 + lang[b];
+        }
+    };
+    fill_seq();
     for (int b = 0; b < B; b++) {
-        for (int i = 0; i < n_prompt; i++) seq[(size_t)b * kDecSeqCap + i] = prompt[i];
-        if (lang_slot >= 0) seq[(size_t)b * kDecSeqCap + lang_slot] = v.lang0 + lang[b];
         DecWinState w;
         memset(&w, 0, sizeof(w));
         w.seek_delta = 100 * 30;
@@ -525,17 +581,24 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         if ((!sw && nv[b] <= 0) || w.seek_end < w.seek + kDeltaMin || w.seek + kDeltaMin >= w.seek_end) { w.completed = 1; w.seek_delta = 0; n_skip++; }  // too short: no decode
         win[b] = w;
     }
+    const std::vector<DecWinState> win0 = win;  // the state every temperature starts from
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.win, win.data(), sizeof(DecWinState) * B, cudaMemcpyHostToDevice, s));
     WDR_CUDA_TRY(cudaMemsetAsync(ws.done_count, 0, sizeof(int32_t), s));
     WDR_CUDA_TRY(cudaMemsetAsync(ws.tokens, 0, sizeof(wdr_token_data) * (size_t)B * kDecMaxTokens, s));
     const SampleParams sp = make_sample_params(v, p);
-    // ---- decode: beam search (rows = windows x beams) or greedy ----
+    // ---- decode at the first temperature: beam search (rows = windows x beams) or greedy ----
     int steps_run = 0;
     std::vector<wdr_token_data> toks((size_t)B * kDecMaxTokens);
     memset(toks.data(), 0, sizeof(wdr_token_data) * toks.size());
+    std::vector<char> dec_failed(B, 0);       // the best decoder counts as failed (bookkeeping failure or the entropy test)
+    std::vector<float> final_temp(B, temps[0]);
+    bool results_on_host = false;
     if (beam_K > 1 && n_skip < B) {
-        if ((rc = beam_decode(ctx, st, ws, p, sp, v, B, beam_K, n_prompt, seq, win, toks, &steps_run)) != WDR_OK) return rc;
+        std::vector<int> all;
+        for (int b = 0; b < B; b++) all.push_back(b);
+        if ((rc = beam_decode(ctx, st, ws, p, sp, v, all, beam_K, beam_K, temps[0], n_prompt, seq, win, toks, dec_failed, &steps_run)) != WDR_OK) return rc;
+        results_on_host = true;
     } else if (n_skip < B) {
         for (int i = 0; i < n_prompt; i++)
             if ((rc = decoder_step(ctx, ws, B, i, i == n_prompt - 1, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
@@ -572,6 +635,57 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             if (!use_graph && (rc = decoder_step(ctx, ws, B, n_prompt + i, true, DEC_MODE_DECODE, s, &st->prof)) != WDR_OK) return rc;
         }
     }
+    // ---- temperature fallback (whisper_full: "was the decoding successful for the current temperature?") ----
+    // A window whose best decoder failed, or whose average log-probability is below logprob_thold while it is not a no-speech
+    // window, is decoded again at the next temperature; the last temperature's result stands whatever it is.  Windows are
+    // independent, so only the failing ones go on, as rows of a fresh decode batch that read their cross caches in place.
+    if (temps.size() > 1 && n_skip < B) {
+        if (!results_on_host) {
+            WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
+            WDR_CUDA_TRY(cudaStreamSynchronize(s));
+            results_on_host = true;
+            for (int b = 0; b < B; b++) {  // single greedy decoder: the entropy test of the ranking step
+                const DecWinState& w = win[b];
+                dec_failed[b] = w.failed || (!w.failed && w.result_len > 32 &&
+                                             sequence_entropy(&toks[(size_t)b * kDecMaxTokens], w.result_len) < (double)p.entropy_thold);
+            }
+        }
+        auto unsuccessful = [&](int b) {
+            const DecWinState& w = win[b];
+            if (dec_failed[b]) return true;
+            if (w.result_len <= 0) return true;  // nothing kept: avg_logprobs is undefined upstream; treated as a failed decode
+            double avg;
+            sequence_score(&toks[(size_t)b * kDecMaxTokens], w.result_len, p.length_penalty, &avg);
+            return avg < (double)p.logprob_thold && w.no_speech_prob < p.no_speech_thold;
+        };
+        std::vector<int> fb;
+        for (int b = 0; b < B; b++)
+            if (!win0[b].completed && unsuccessful(b)) fb.push_back(b);
+        const int Kd = std::max(1, p.greedy_best_of);
+        for (size_t it = 1; it < temps.size() && !fb.empty(); it++) {
+            prompt = build_prompt(temps[it] < 0.5f);
+            n_prompt = (int)prompt.size();
+            fill_seq();
+            const int per_pass = kDecMaxBatch / Kd;
+            for (size_t o = 0; o < fb.size(); o += per_pass) {
+                std::vector<int> sub(fb.begin() + o, fb.begin() + std::min(fb.size(), o + per_pass));
+                for (int b : sub) {
+                    win[b] = win0[b];
+                    final_temp[b] = temps[it];
+                    memset(&toks[(size_t)b * kDecMaxTokens], 0, sizeof(wdr_token_data) * kDecMaxTokens);
+                }
+                int steps_pass = 0;
+                if ((rc = beam_decode(ctx, st, ws, p, sp, v, sub, Kd, p.beam_size, temps[it], n_prompt, seq, win, toks, dec_failed, &steps_pass)) != WDR_OK) return rc;
+                steps_run += steps_pass;
+            }
+            if (it + 1 == temps.size()) break;
+            std::vector<int> still;
+            for (int b : fb)
+                if (unsuccessful(b)) still.push_back(b);
+            fb.swap(still);
+        }
+    }
     fs.last_decode_steps = steps_run;
     fs.decode_steps += steps_run;
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[3], s));
@@ -579,7 +693,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     static const bool dbg_time = getenv("WDR_DEBUG_TIMING") != nullptr;
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_h0 = now_ms();
-    if (beam_K == 1) {
+    if (!results_on_host) {
         WDR_CUDA_TRY(cudaMemcpyAsync(toks.data(), ws.tokens, sizeof(wdr_token_data) * toks.size(), cudaMemcpyDeviceToHost, s));
         WDR_CUDA_TRY(cudaMemcpyAsync(win.data(), ws.win, sizeof(DecWinState) * B, cudaMemcpyDeviceToHost, s));
     }
@@ -615,6 +729,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         ci.seek_delta = w.seek_delta; ci.failed = w.failed; ci.completed = w.completed; ci.n_sampled = w.n_cur; ci.has_ts = w.has_ts;
         ci.result_len = w.result_len; ci.seek_end = w.seek_end; ci.n_segments = 0; ci.no_speech_prob = w.no_speech_prob;
         ci.lang_id = lang[b];
+        ci.temperature = final_temp[b];
         const int n_keep = w.failed ? w.n_cur : w.result_len;
         std::vector<wdr_token_data> cur(toks.begin() + (size_t)b * kDecMaxTokens, toks.begin() + (size_t)b * kDecMaxTokens + n_keep);
         double avg_logprob = -INFINITY;
@@ -1119,6 +1234,12 @@ extern "C" int wdr_full_get_chunk_info_from_state(wdr_state* st, int i, int32_t*
     info[6] = c.seek_end; info[7] = c.n_segments;
     if (nsp) *nsp = c.no_speech_prob;
     return WDR_OK;
+}
+
+extern "C" float wdr_full_get_chunk_temperature_from_state(wdr_state* st, int i) {
+    clear_error();
+    if (!st || i < 0 || i >= (int)st->chunk_info.size()) { set_error("chunk index out of range"); return -1.0f; }
+    return st->chunk_info[i].temperature;
 }
 
 extern "C" int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* st, const float* enc, int n_chunks, const int32_t* seq_in, int n_seq,

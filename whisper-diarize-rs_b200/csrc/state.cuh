@@ -21,6 +21,7 @@ struct ChunkInfo {
     int seek_delta, failed, completed, n_sampled, has_ts, result_len, seek_end, n_segments;
     float no_speech_prob;
     int lang_id;
+    float temperature;  // the temperature whose result stands (0 unless the fallback ladder ran)
 };
 // staging / scratch of the full pipeline (full.cu)
 struct FullScratch {
