@@ -228,8 +228,10 @@ enum wdr_sampling_strategy { WDR_SAMPLING_GREEDY = 0, WDR_SAMPLING_BEAM_SEARCH =
 /* == whisper_full_params, the fields the crate sets (setup_params, src/transcribe.rs:20-87) plus whisper.cpp's defaults
  * for the rest.  Supported decoding: greedy at temperature 0; beam search (beam_size <= 8) with whisper_full's temperature
  * ladder (temperature_inc > 0: failing windows are decoded again at +temperature_inc ... <= 1).  temperature_inc defaults to 0
- * here (whisper.cpp: 0.2) — set it to 0.2 for upstream's default behaviour.  Multinomial sampling (greedy strategy or
- * best_of > 1 above temperature 0: whisper.cpp's per-decoder std::mt19937 stream) is refused with WDR_ERR_UNSUPPORTED.
+ * here (whisper.cpp: 0.2) — set it to 0.2 for upstream's default behaviour.  Above temperature 0 the greedy strategy draws
+ * every token from std::discrete_distribution with best_of (<= 8) decoders per window, decoder j of a window seeded
+ * std::mt19937(j) (upstream's stream runs on across the windows of a call; here every window restarts it, so windows stay
+ * independent and shardable).
  * language given or "auto"; single_segment = 1 as the crate always sets (src/transcribe.rs:46).  Strings are borrowed for the call. */
 typedef struct wdr_full_params {
     int strategy;            /* enum wdr_sampling_strategy */
@@ -299,6 +301,10 @@ int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* i
 /* Temperature of the ladder (temperature, +temperature_inc, ... <= 1) whose result stands for chunk i of the last full call;
  * -1 if i is out of range. */
 float wdr_full_get_chunk_temperature_from_state(wdr_state* state, int i_chunk);
+/* The host-side sampler of the temperature ladder for the greedy strategy (whisper_sample_token, best = false): n_draws
+ * consecutive draws from std::discrete_distribution over expf(logprobs) (-inf = probability 0) with one std::mt19937(seed).
+ * Pure host code (no device needed); exposed so that the draw can be checked bit for bit against the oracle's restatement. */
+int wdr_sample_discrete(const float* logprobs, int n, uint32_t seed, int n_draws, int32_t* ids);
 /* Stage-level decoder access for parity tests: teacher-forced pass of `n_seq` tokens over window 0.. of the last encode/full call.
  * enc: optional HOST encoder output [n_chunks][1500][d] to install first (NULL = keep the state's).  seq: HOST [n_chunks][n_seq].
  * logits_out: HOST [n_chunks][n_seq][n_vocab] or NULL.  aheads_out: HOST [n_chunks][n_aheads][n_seq][1500] or NULL (needs a DTW

@@ -137,7 +137,7 @@ def test_unsupported_params_fail_loudly(wdr):
         st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=9))  # beams beyond the 8 the row budget is cut for
     assert e.value.code == -7
     with pytest.raises(wdr.WdrError):
-        st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2))  # greedy strategy above T = 0 = multinomial sampling: not restated
+        st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2, greedy_best_of=9))  # more decoders per window than the row budget
     with pytest.raises(wdr.WdrError):
         st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=5, temperature=0.2))  # the ladder starts at 0
     with pytest.raises(wdr.WdrError):
@@ -436,5 +436,57 @@ def test_temperature_fallback_matches_oracle(wdr, oracle, tiny_w):
         assert [t.id for t in got["tokens"]] == [t.id for t in r["tokens"]]
         assert [(t.t0, t.t1, t.t_dtw) for t in got["tokens"]] == [(t.t0, t.t1, t.t_dtw) for t in r["tokens"]]
     dec.close()
+    st.close()
+    ctx.close()
+
+
+def test_greedy_strategy_temperature_sampling(wdr, oracle, tiny_w):
+    """Greedy strategy with the temperature ladder: above T = 0 every one of best_of decoders draws its tokens
+    (whisper_sample_token, best = false; the draw itself is pinned bit for bit by tests/test_capi_cpu.py).  A device distribution
+    cannot be reproduced bit for bit by an fp32 oracle, so the end-to-end checks are the properties that do not depend on the last
+    ulp: windows that pass the success test at T = 0 keep their greedy result, the others end at a higher temperature, the call is
+    deterministic (per-window generators restart), independent of which other windows share the batch, and every kept token obeys
+    the logit rules (p = exp(plog), probabilities of the drawn ids are positive, timestamps non-decreasing)."""
+    from oracle import weights as W, full
+    arch = "tiny.en"
+    B = 3
+    pcm = np.zeros((B, 480000), np.int16)
+    nv = np.array([480000, 200000, 320000], np.int32)
+    for b in range(B):
+        a = synth_audio(2200 + b, nv[b] / 16000.0)
+        pcm[b, : len(a)] = a[: nv[b]]
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    greedy = {s["chunk"]: s for s in st.full_batch(pcm, nv)}
+    info0 = [st.chunk_info(b) for b in range(B)]
+    # a failed decode falls back whatever its score, and so does one whose last 32 kept ids repeat themselves (entropy < 2.4)
+    ok0 = [b for b in range(B) if not info0[b]["failed"] and info0[b]["result_len"] > 0 and
+           not (info0[b]["result_len"] > 32 and full.sequence_entropy(greedy[b]["tokens"], info0[b]["result_len"]) < 2.4)]
+    assert len(ok0) >= 2 and all(b in greedy for b in ok0)
+    avg0 = {b: float(np.mean([t.plog for t in greedy[b]["tokens"]])) for b in ok0}
+    order = sorted(avg0, key=avg0.get)
+    thold = 0.5 * (avg0[order[0]] + avg0[order[1]])  # the worst-scoring window falls back, the better ones pass at T = 0
+    prm = dict(strategy=0, greedy_best_of=3, temperature_inc=0.5, logprob_thold=thold)
+    segs = {s["chunk"]: s for s in st.full_batch(pcm, nv, st.full_params(**prm))}
+    temps = [st.chunk_info(b)["temperature"] for b in range(B)]
+    for b in range(B):
+        assert (temps[b] == 0.0) == (b in order[1:]), (b, temps, order)
+    for b in order[1:]:
+        assert [t.id for t in segs[b]["tokens"]] == [t.id for t in greedy[b]["tokens"]]
+    fb = order[0]
+    ids1 = [t.id for t in segs[fb]["tokens"]]
+    assert ids1 != [t.id for t in greedy[fb]["tokens"]]
+    last_ts = -1
+    for t in segs[fb]["tokens"]:
+        assert t.p > 0.0 and abs(np.log(t.p) - t.plog) < 1e-4
+        if t.id >= 50363:  # tiny.en token_beg + 0
+            assert t.id >= last_ts
+            last_ts = t.id
+    # deterministic, and independent of the batch the window is decoded in
+    again = {s["chunk"]: s for s in st.full_batch(pcm, nv, st.full_params(**prm))}
+    assert [t.id for t in again[fb]["tokens"]] == ids1
+    alone = st.full_batch(pcm[fb : fb + 1], nv[fb : fb + 1], st.full_params(**prm))
+    assert [t.id for t in alone[0]["tokens"]] == ids1
+    assert [(t.t0, t.t1, t.t_dtw) for t in alone[0]["tokens"]] == [(t.t0, t.t1, t.t_dtw) for t in segs[fb]["tokens"]]
     st.close()
     ctx.close()

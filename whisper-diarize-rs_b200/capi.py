@@ -159,6 +159,7 @@ def load():
     L.wdr_token_to_str.argtypes = [C.c_void_p, C.c_int32]
     L.wdr_token_to_str.restype = C.c_char_p
     L.wdr_full_get_chunk_info_from_state.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
+    L.wdr_sample_discrete.argtypes = [f32p, C.c_int, C.c_uint32, C.c_int, i32p]
     L.wdr_full_get_chunk_temperature_from_state.argtypes = [C.c_void_p, C.c_int]
     L.wdr_full_get_chunk_temperature_from_state.restype = C.c_float
     L.wdr_decode_teacher_forced.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, i32p, C.c_int, f32p, f32p]
@@ -333,6 +334,14 @@ def resample_to_16k(pcm_i16, sample_rate, channels=1, want_f32=False):
                                    _p(o32, f32p) if want_f32 else None, n, C.byref(n_out)))
     assert n_out.value == n
     return (o16, o32) if want_f32 else o16
+
+
+def sample_discrete(logprobs, seed, n_draws):
+    """n_draws consecutive whisper_sample_token(best=false) draws (host-side sampler of the temperature ladder)."""
+    lp = _np(logprobs, np.float32)
+    ids = np.empty(n_draws, np.int32)
+    _check(load().wdr_sample_discrete(_p(lp, f32p), len(lp), int(seed), int(n_draws), _p(ids, i32p)))
+    return ids
 
 
 def median_filter(w, width=7):

@@ -741,7 +741,7 @@ dec_sample_kernel(const float* __restrict__ logits, int64_t ldv, DecWinState* __
 __global__ void __launch_bounds__(kSampThreads, 1)
 dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __restrict__ rows, const SampleParams sp, int k_top, float temperature,
                 BeamCand* __restrict__ cands /* [rows][kBeamMax] */, float* __restrict__ no_speech /* [rows], written when n_cur == 0 */,
-                float* __restrict__ probs_out /* optional [rows][ldv]: the processed distribution (temperature sampling on the host) */) {
+                float* __restrict__ probs_out /* optional [rows][ldv]: the processed LOG-probabilities (temperature sampling on the host); slot 1 of cands then carries the distribution's raw tid / pt / ptsum */) {
     __shared__ float red[32];
     __shared__ unsigned long long red64[32];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -822,7 +822,7 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
         const int i = tid + k * kSampThreads;
         if (mask_text && i < sp.beg) v[k] = -INFINITY;
         const float pr = v[k] > -INFINITY ? expf(v[k]) : 0.0f;
-        if (probs_out && i < n) probs_out[(int64_t)b * ldv + i] = pr;
+        if (probs_out && i < n) probs_out[(int64_t)b * ldv + i] = v[k];  // processed log-probability (-inf = masked)
         if (pr > 0.0f && i >= sp.beg) {
             const unsigned long long key = ((unsigned long long)__float_as_uint(pr) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
             sum_ts += pr;
@@ -863,6 +863,11 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
         }
         if (tid == 0) cands[(int64_t)b * kBeamMax + r] = c;
         __syncthreads();
+    }
+    if (probs_out && tid == 0 && k_top < kBeamMax) {  // what whisper_sample_token attaches to a drawn token before its own override
+        BeamCand c;
+        c.id = -1; c.tid = tid_tok; c.p = 0.0f; c.plog = -INFINITY; c.pt = pt; c.ptsum = sum_ts;
+        cands[(int64_t)b * kBeamMax + k_top] = c;
     }
 }
 

@@ -108,7 +108,8 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 //                         row is read through the ancestry table ws.beam_anc_cur, rows with ws.beam_limit[b] <= pos are skipped.
 enum { DEC_MODE_DECODE = 0, DEC_MODE_FORCED = 1, DEC_MODE_DTW = 2, DEC_MODE_BEAM = 3 };
 // temperature > 0: logits are divided by it first (whisper_process_logits); probs_out (optional, [R][ws.ldv]) receives the processed
-// distribution of every active row (what whisper_sample_token draws from at temperature > 0)
+// log-probabilities of every active row (what whisper_sample_token draws from at temperature > 0) and candidate slot k_top the raw
+// tid / pt / ptsum of the distribution
 int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const SampleParams& sp, int k_top, float temperature, float* probs_out,
                  cudaStream_t st, Profiler* prof);
 int decoder_beam_reorder(DecoderWorkspace& ws, int R, int pos_last, cudaStream_t st);

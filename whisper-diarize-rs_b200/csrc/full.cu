@@ -15,6 +15,7 @@
 #include <string>
 #include <thread>
 #include <map>
+#include <random>
 #include <vector>
 #include <cuda_profiler_api.h>
 #include "common.cuh"
@@ -203,12 +204,7 @@ static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int
     if (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > kBeamMax) { set_error("beam_size %d exceeds the supported maximum of %d", p.beam_size, kBeamMax); return WDR_ERR_UNSUPPORTED; }
     if (p.temperature != 0.0f) { set_error("the temperature ladder must start at 0 (temperature %g)", p.temperature); return WDR_ERR_UNSUPPORTED; }
     if (p.temperature_inc < 0.0f) { set_error("temperature_inc must be >= 0"); return WDR_ERR_INVALID; }
-    if (p.temperature_inc > 0.0f && (p.strategy != WDR_SAMPLING_BEAM_SEARCH || p.greedy_best_of > 1)) {
-        // greedy strategy at T > 0 (and best_of > 1 decoders) draws from whisper.cpp's per-decoder std::mt19937 stream: not restated
-        set_error("temperature fallback is implemented for the beam-search strategy with best_of <= 1 (deterministic); "
-                  "multinomial sampling at temperature > 0 is not");
-        return WDR_ERR_UNSUPPORTED;
-    }
+    if (p.temperature_inc > 0.0f && p.greedy_best_of > kBeamMax) { set_error("best_of %d exceeds the supported maximum of %d", p.greedy_best_of, kBeamMax); return WDR_ERR_UNSUPPORTED; }
     if (!p.single_segment) { set_error("single_segment = 0 is not implemented (the crate always sets it, src/transcribe.rs:46)"); return WDR_ERR_UNSUPPORTED; }
     if (p.no_timestamps) { set_error("no_timestamps = 1 is not implemented"); return WDR_ERR_UNSUPPORTED; }
     if (p.detect_language || (p.language && strcmp(p.language, "auto") == 0)) {  // whisper_lang_auto_detect: decided per buffer on the device
@@ -257,6 +253,15 @@ static int grow_pinned(T** p, size_t* cap, size_t need) {
 // decoders that failed are skipped, a decoder whose last 32 kept tokens have entropy < entropy_thold (result_len > 32) fails,
 // the best score (sum of log-probabilities / length, or the length_penalty form) wins, first maximum, decoder 0 if none.
 // ---------------------------------------------------------------------------------------------------
+// whisper_sample_token(best = false): std::discrete_distribution over probs = expf(logprobs) drawn with the decoder's std::mt19937 —
+// the very libstdc++ objects whisper.cpp uses, so a draw is bit-identical given identical log-probabilities.
+static int sample_discrete(const float* logprobs, int n, std::mt19937& rng, std::vector<float>& probs) {
+    probs.resize(n);
+    for (int i = 0; i < n; i++) probs[i] = logprobs[i] == -INFINITY ? 0.0f : expf(logprobs[i]);
+    std::discrete_distribution<> dist(probs.begin(), probs.end());
+    return dist(rng);
+}
+
 struct HostBeam {
     std::vector<wdr_token_data> tokens;
     double sum_all = 0.0;
@@ -291,8 +296,19 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
     cudaStream_t s = st->stream;
     const int nW = (int)wins.size(), K = Kd;
     const int R = nW * K, n_max = sp.n_max;
-    WDR_REQUIRE(R >= 1 && R <= kDecMaxBatch && R <= ws.cap_B && Kc >= 1 && Kc <= kBeamMax, "beam_decode: bad batch");
+    WDR_REQUIRE(R >= 1 && R <= kDecMaxBatch && R <= ws.cap_B && Kc >= 0 && Kc <= kBeamMax, "beam_decode: bad batch");
     int rc;
+    // Kc == 0: the greedy strategy above temperature 0 — every decoder draws its next token from its own distribution
+    // (whisper_sample_token, best = false) with its own generator; decoder j of a window starts from std::mt19937(j).
+    const bool sampling = Kc == 0;
+    FullScratch& fs = st->full;
+    std::vector<std::mt19937> rngs;
+    if (sampling) {
+        WDR_REQUIRE(temperature > 0.0f, "sampling needs a temperature above 0");
+        if ((rc = grow_dev(&fs.lp_dev, &fs.lp_dev_cap, (size_t)R * ws.ldv)) != WDR_OK) return rc;
+        if ((rc = grow_pinned(&fs.lp_host, &fs.lp_host_cap, (size_t)R * ws.ldv)) != WDR_OK) return rc;
+        for (int r = 0; r < R; r++) rngs.emplace_back((uint32_t)(r % K));
+    }
     std::vector<int32_t> seq((size_t)R * kDecSeqCap);
     std::vector<int32_t> rowwin(kDecMaxBatch, 0);
     for (int r = 0; r < R; r++) {
@@ -331,8 +347,12 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
             rows[r] = br;
         }
         WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_rows, rows.data(), sizeof(BeamRow) * R, cudaMemcpyHostToDevice, s));
-        if ((rc = decoder_topk(ctx, ws, R, sp, Kc, temperature, nullptr, s, &st->prof)) != WDR_OK) return rc;
+        if ((rc = decoder_topk(ctx, ws, R, sp, sampling ? 1 : Kc, temperature, sampling ? fs.lp_dev : nullptr, s, &st->prof)) != WDR_OK) return rc;
         WDR_CUDA_TRY(cudaMemcpyAsync(cands.data(), ws.beam_cands, sizeof(BeamCand) * (size_t)R * kBeamMax, cudaMemcpyDeviceToHost, s));
+        if (sampling)
+            for (int r = 0; r < R; r++)
+                if (rows[r].active)
+                    WDR_CUDA_TRY(cudaMemcpyAsync(fs.lp_host + (size_t)r * ws.ldv, fs.lp_dev + (size_t)r * ws.ldv, sizeof(float) * sp.n_vocab, cudaMemcpyDeviceToHost, s));
         if (i == 0) WDR_CUDA_TRY(cudaMemcpyAsync(nosp.data(), ws.beam_nosp, sizeof(float) * R, cudaMemcpyDeviceToHost, s));
         WDR_CUDA_TRY(cudaStreamSynchronize(s));
         steps = i + 1;
@@ -340,19 +360,32 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
             for (int w = 0; w < nW; w++) win[wins[w]].no_speech_prob = nosp[(size_t)w * K];
         bool any_live = false;
         for (int r = 0; r < R; r++) { parent[r] = r; next_tok[r] = v.eot; }
+        if (sampling) {  // draw on the host; slot 0 of the row's candidates becomes the drawn token
+            parallel_for(R, [&](int r) {
+                if (!rows[r].active) return;
+                std::vector<float> probs;
+                const float* lp = fs.lp_host + (size_t)r * ws.ldv;
+                const int id = sample_discrete(lp, sp.n_vocab, rngs[r], probs);
+                const BeamCand raw = cands[(size_t)r * kBeamMax + 1];
+                BeamCand c;
+                c.id = id; c.tid = raw.tid; c.p = probs[id]; c.plog = lp[id]; c.pt = raw.pt; c.ptsum = raw.ptsum;
+                if (id >= v.beg) { c.tid = id; c.pt = c.p; }
+                cands[(size_t)r * kBeamMax] = c;
+            });
+        }
         for (int w = 0; w < nW; w++) {
             if (win[wins[w]].completed) continue;
             std::vector<HostBeam>& bw = beams[w];
             std::vector<Cand> cl;
             for (int k = 0; k < K; k++) {
                 if (bw[k].completed || bw[k].failed) continue;
-                for (int r = 0; r < Kc; r++) {
+                for (int r = 0; r < (sampling ? 1 : Kc); r++) {
                     const BeamCand& c = cands[((size_t)w * K + k) * kBeamMax + r];
                     if (c.id >= 0) cl.push_back({k, r, bw[k].sum_all + (double)c.plog});
                 }
             }
             if (cl.empty()) continue;
-            std::stable_sort(cl.begin(), cl.end(), [](const Cand& a, const Cand& b) { return a.sum > b.sum; });
+            if (!sampling) std::stable_sort(cl.begin(), cl.end(), [](const Cand& a, const Cand& b) { return a.sum > b.sum; });
             auto cand_tok = [&](const Cand& c) -> const BeamCand& { return cands[((size_t)w * K + c.k) * kBeamMax + c.r]; };
             auto same_seq = [&](const Cand& a, const Cand& b) {
                 if (cand_tok(a).id != cand_tok(b).id) return false;
@@ -368,7 +401,7 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
                 if (bw[k].completed || bw[k].failed) continue;
                 if (cur_c >= cl.size()) cur_c = 0;
                 const Cand cur = cl[cur_c++];
-                while (cl.size() > cur_c && i > 0 && same_seq(cl[cur_c], cur)) ++cur_c;
+                while (!sampling && cl.size() > cur_c && i > 0 && same_seq(cl[cur_c], cur)) ++cur_c;
                 const BeamCand& c = cand_tok(cur);
                 HostBeam h = bw[cur.k];
                 wdr_token_data td;
@@ -472,7 +505,9 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     int rc;
     const int beam_K = (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1;  // rows per window of the decode batch
     WDR_REQUIRE(B * beam_K <= kDecMaxBatch, "windows x beams exceeds the 128-row decode batch");
-    if ((rc = ws.reserve(ctx, std::max(B * beam_K, B))) != WDR_OK) return rc;  // fallback passes: <= B rows (one decoder per failing window)
+    const int fb_Kd = std::max(1, p.greedy_best_of);  // decoders per window of a fallback pass (temperature > 0)
+    const int fb_rows = p.temperature_inc > 0.0f ? std::min(B, kDecMaxBatch / fb_Kd) * fb_Kd : 0;
+    if ((rc = ws.reserve(ctx, std::max(std::max(B * beam_K, B), fb_rows))) != WDR_OK) return rc;
     // ---- n_valid on the device ----
     if ((rc = grow_dev(&fs.nvalid_dev, &fs.nvalid_cap, (size_t)B)) != WDR_OK) return rc;
     std::vector<int32_t> nv(B);
@@ -676,7 +711,8 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                     memset(&toks[(size_t)b * kDecMaxTokens], 0, sizeof(wdr_token_data) * kDecMaxTokens);
                 }
                 int steps_pass = 0;
-                if ((rc = beam_decode(ctx, st, ws, p, sp, v, sub, Kd, p.beam_size, temps[it], n_prompt, seq, win, toks, dec_failed, &steps_pass)) != WDR_OK) return rc;
+                const int Kc = p.strategy == WDR_SAMPLING_BEAM_SEARCH ? std::max(1, p.beam_size) : 0;  // greedy strategy: every decoder draws (sampling)
+                if ((rc = beam_decode(ctx, st, ws, p, sp, v, sub, Kd, Kc, temps[it], n_prompt, seq, win, toks, dec_failed, &steps_pass)) != WDR_OK) return rc;
                 steps_run += steps_pass;
             }
             if (it + 1 == temps.size()) break;
@@ -1233,6 +1269,15 @@ extern "C" int wdr_full_get_chunk_info_from_state(wdr_state* st, int i, int32_t*
     info[0] = c.seek_delta; info[1] = c.failed; info[2] = c.completed; info[3] = c.n_sampled; info[4] = c.has_ts; info[5] = c.result_len;
     info[6] = c.seek_end; info[7] = c.n_segments;
     if (nsp) *nsp = c.no_speech_prob;
+    return WDR_OK;
+}
+
+extern "C" int wdr_sample_discrete(const float* logprobs, int n, uint32_t seed, int n_draws, int32_t* ids) {
+    clear_error();
+    WDR_REQUIRE(logprobs && n > 0 && n_draws >= 0 && (n_draws == 0 || ids), "bad arguments");
+    std::mt19937 rng(seed);
+    std::vector<float> probs;
+    for (int i = 0; i < n_draws; i++) ids[i] = sample_discrete(logprobs, n, rng, probs);
     return WDR_OK;
 }
 

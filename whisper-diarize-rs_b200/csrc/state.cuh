@@ -45,13 +45,18 @@ struct FullScratch {
     size_t dtw_wins_cap = 0;
     int32_t* dtw_path_host = nullptr;  // pinned
     size_t dtw_path_host_cap = 0;
+    float* lp_dev = nullptr;       // [rows][ldv] processed log-probabilities of a sampling pass (temperature > 0, greedy strategy)
+    size_t lp_dev_cap = 0;
+    float* lp_host = nullptr;      // pinned
+    size_t lp_host_cap = 0;
     int last_decode_steps = 0;
     // phase boundaries of the last group on the compute stream: start | encoder | cross-KV | greedy decode | DTW pass | DTW
     cudaEvent_t ev_phase[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[5] = {0, 0, 0, 0, 0};  // accumulated over the groups of the last full call
     int decode_steps = 0;                  // greedy iterations of the last full call (summed over groups)
     void release() {
-        cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path); cudaFree(dtw_wins);
+        cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path); cudaFree(dtw_wins); cudaFree(lp_dev);
+        if (lp_host) cudaFreeHost(lp_host);
         if (energy_host) cudaFreeHost(energy_host);
         if (dtw_path_host) cudaFreeHost(dtw_path_host);
         if (done_host) cudaFreeHost(done_host);
