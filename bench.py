@@ -384,6 +384,8 @@ def main():
     ap.add_argument("--arch", default=None)
     ap.add_argument("--chunks", type=int, default=None, help="30 s windows per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--beam", type=int, default=0, help="transcribe workload: beam search with this beam size (the crate's default strategy, beam 5) instead of greedy")
+    ap.add_argument("--temperature-inc", type=float, default=0.0, help="transcribe workload: whisper_full's temperature ladder increment (whisper.cpp default 0.2; 0 = no fallback)")
     args = ap.parse_args()
     if args.arch is None:
         args.arch = "large-v3" if args.workload == "transcribe" else "tiny.en"
@@ -427,7 +429,10 @@ def main():
     pcm_pin = torch.from_numpy(pcm_host).pin_memory()
     pcm_dev = pcm_pin.cuda(non_blocking=False)
     stream = torch.cuda.current_stream().cuda_stream
-    params = st.full_params() if full else None
+    params = None
+    if full:
+        kw = dict(temperature_inc=args.temperature_inc)
+        params = st.full_params(strategy=1, beam_size=args.beam, **kw) if args.beam > 1 else st.full_params(**kw)
     hidden = None if full else torch.empty(B, 1500, d, device="cuda", dtype=torch.float32)
     stats = {"segments": 0, "tokens": 0}
 
@@ -580,7 +585,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": workload_name(args), "windows_per_gpu": B, "weights": "seeded random-init, bf16 matrices",
-                           "pcm": "int16 16 kHz", "decode": "greedy T=0, single_segment, token_timestamps, DTW (alignment-head preset)" if full else None,
+                           "pcm": "int16 16 kHz", "decode": ((f"beam search (beam {args.beam})" if args.beam > 1 else "greedy") + (f", temperature ladder +{args.temperature_inc}" if args.temperature_inc > 0 else " T=0") + ", single_segment, token_timestamps, DTW (alignment-head preset)") if full else None,
                            "l2": "no explicit flush: each step streams several GB of activations / KV cache, far above the 126 MB L2"},
                 "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm_host.nbytes), "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_s / args.steps * 1e3,
