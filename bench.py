@@ -335,6 +335,101 @@ def run_diarize(args):
         dist.destroy_process_group()
 
 
+def run_pipeline(args):
+    """BASELINE configs[4] in miniature: the whole crate-shaped flow on one recording per GPU — Silero VAD mask, pyannote
+    segmentation -> SpeechSegments, every segment through state.full (large-v3-turbo, token + DTW timestamps) and the WeSpeaker
+    embedding, EmbeddingManager speaker ids, subtitle cues — through whisper-diarize-rs_b200.host with HOST buffers (there is no
+    device-resident arm: the step IS the public API call, so value == e2e).  The full config is 8 h over 8 GPUs (1 h per GPU);
+    the default here is a 10 min recording per GPU so that the run finishes in minutes (--minutes)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import synth_audio
+    import torch
+    import torch.distributed as dist
+    import wdr_b200 as w
+    from wdr_b200 import host as H
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if w.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: libwdr_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    seconds = 60.0 * args.minutes
+    pcm = synth_audio(5001 + rank, seconds, n_speakers=4)
+    arch = args.arch
+    ctx = w.Context(arch, seed=1234, gpu_device=local, enable_dtw=True)
+    st = ctx.create_state()
+    vad = w.VadContext(seed=1234, gpu_device=local)
+    seg = w.Segmenter(seed=1234, device=local)
+    emb = w.EmbeddingExtractor(seed=1234, device=local)
+    out = {}
+
+    def step():
+        t = time.perf_counter()
+        mask, _ = H.vad_get_segments(vad, pcm)
+        t1 = time.perf_counter()
+        speech = [dict(start=s_["start"], end=s_["end"], samples=s_["samples"]) for s_ in seg.get_segments(pcm)]
+        t2 = time.perf_counter()
+        segs, lang = H.run_transcription_pipeline_sharded(st, speech, None, emb, 0.5, w.SIZE_MAX)
+        t3 = time.perf_counter()
+        cues = H.format_cues(segs, lang, mask)
+        t4 = time.perf_counter()
+        out.update(mask=len(mask), speech=len(speech), segments=len(segs), cues=len(cues), speakers=len(set(s_["speaker_id"] for s_ in segs)),
+                   stages={"vad_ms": (t1 - t) * 1e3, "segmentation_ms": (t2 - t1) * 1e3, "transcribe_embed_ms": (t3 - t2) * 1e3, "format_ms": (t4 - t3) * 1e3},
+                   pcm_bytes=int(pcm.nbytes + sum(len(s_["samples"]) for s_ in speech) * 2 * 2))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = w.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    barrier()
+    dt = time.perf_counter() - t0
+    launches = w.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    value = world * seconds * args.steps / dt
+    if rank == 0:
+        line = {"metric": "RTFx VAD + diarization + transcribe", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16/f32", "data": "synthetic",
+                "config": {"workload": f"{arch} transcribe + diarization + Silero VAD of a {args.minutes} min 4-speaker synthetic recording per GPU through the "
+                                       "crate-shaped host flow, speech segments batched 128 per wdr_full_batch_i16 call (BASELINE configs[4], bounded)",
+                           "speech_segments": out["speech"], "vad_ranges": out["mask"], "segments": out["segments"], "cues": out["cues"], "speakers": out["speakers"],
+                           "note": "every speech segment is its own 30 s whisper window, as in the reference; the random-init segmentation net emits "
+                                   "many short segments, so windows per audio-hour are far above a real recording's",
+                           "l2": "each step streams the whole recording's activations (> 126 MB L2)"},
+                "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": out["pcm_bytes"], "d2h_bytes_per_step": None,
+                        "api": "host.vad_get_segments + Segmenter.get_segments + host.run_transcription_pipeline_sharded + host.format_cues"},
+                "gpu_launches": int(launches), "clocks": clocks, "stages_last_step": out["stages"], "roofline": None, "cpu_baseline": None}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+    for m in (vad, seg, emb, st, ctx):
+        m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def metric_name(workload):
     return "RTFx full transcribe+DTW" if workload == "transcribe" else "RTFx mel+encoder"
 
@@ -380,7 +475,8 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="transcribe", choices=["transcribe", "encoder", "diarize"])
+    ap.add_argument("--workload", default="transcribe", choices=["transcribe", "encoder", "diarize", "pipeline"])
+    ap.add_argument("--minutes", type=int, default=10, help="pipeline workload: recording length per GPU")
     ap.add_argument("--arch", default=None)
     ap.add_argument("--chunks", type=int, default=None, help="30 s windows per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -388,7 +484,7 @@ def main():
     ap.add_argument("--temperature-inc", type=float, default=0.0, help="transcribe workload: whisper_full's temperature ladder increment (whisper.cpp default 0.2; 0 = no fallback)")
     args = ap.parse_args()
     if args.arch is None:
-        args.arch = "large-v3" if args.workload == "transcribe" else "tiny.en"
+        args.arch = "large-v3" if args.workload == "transcribe" else "large-v3-turbo" if args.workload == "pipeline" else "tiny.en"
     if args.chunks is None:
         args.chunks = 120 if args.workload == "transcribe" else 64
     if args.steps is None:
@@ -398,6 +494,13 @@ def main():
         if args.steps is None or args.steps > 40:
             args.steps = 10
         return run_diarize(args)
+    if args.workload == "pipeline":
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the pipeline workload has no CPU arm; see the transcribe and diarize workloads"}))
+            return
+        if args.steps is None or args.steps > 10:
+            args.steps = 3
+        return run_pipeline(args)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -72,3 +72,36 @@ def test_transcribe_audio_three_modes(wdr):
         m.close()
     st.close()
     ctx.close()
+
+
+def test_sharded_pipeline_equals_sequential(wdr):
+    """run_transcription_pipeline_sharded (all speech segments through ONE wdr_full_batch_i16 / ONE wdr_emb_compute_batch_i16 call)
+    returns exactly what the crate-shaped loop returns without prompt carry (one state.full + one EmbeddingExtractor::compute per
+    segment): same segments, texts, word spans to the last bit, same speaker ids — for pyannote segments (diarize) and for Silero VAD
+    segments, including a speech segment longer than 30 s (which keeps whisper_full's sequential seek loop)."""
+    from wdr_b200 import host as H
+    pcm = synth_audio(73, 48.0, n_speakers=3)
+    ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    seg_m = wdr.Segmenter(seed=1234)
+    emb = wdr.EmbeddingExtractor(seed=1234)
+    speech = [dict(start=s["start"], end=s["end"], samples=s["samples"]) for s in seg_m.get_segments(pcm)]
+    assert len(speech) >= 3
+    speech.append(dict(start=50.0, end=50.0 + 36.0, samples=synth_audio(74, 36.0)))  # > 30 s: sequential mode inside the sharded call
+    a, lang_a = H.run_transcription_pipeline(st, speech, None, emb, 0.5, 2, carry_prompt=False)
+    b, lang_b = H.run_transcription_pipeline_sharded(st, speech, None, emb, 0.5, 2, batch=5)  # several batches
+    assert lang_a == lang_b == "en" and len(a) == len(b) and len(a) >= 3
+    for x, y in zip(a, b):
+        assert (x["start"], x["end"], x["text"], x["speaker_id"]) == (y["start"], y["end"], y["text"], y["speaker_id"])
+        assert x["words"] == y["words"]
+    vad = wdr.VadContext(seed=1234)
+    _, speech_v = H.vad_get_segments(vad, pcm)
+    a, _ = H.run_transcription_pipeline(st, speech_v, carry_prompt=False)
+    b, _ = H.run_transcription_pipeline_sharded(st, speech_v)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert (x["start"], x["end"], x["text"]) == (y["start"], y["end"], y["text"]) and x["words"] == y["words"]
+    for m in (vad, seg_m, emb):
+        m.close()
+    st.close()
+    ctx.close()

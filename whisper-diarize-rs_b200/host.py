@@ -240,6 +240,68 @@ def run_transcription_pipeline(state, speech_segments, params=None, extractor=No
     return out, detected
 
 
+def run_transcription_pipeline_sharded(state, speech_segments, params=None, extractor=None, threshold=0.5, max_speakers=capi.SIZE_MAX,
+                                       user_offset=0.0, translated=False, batch=128):
+    """The same pipeline at throughput (SURVEY §0.4's independent-chunk mode, §8e): every SpeechSegment is its own `state.full`
+    buffer, so — once the previous segment's text is no longer fed back as a prompt — the segments are independent and go through
+    the library `batch` at a time: ONE wdr_full_batch_i16 call per `batch` segments of <= 30 s (mel, encoder, decode and DTW of all
+    of them as one batch), ONE wdr_emb_compute_batch_i16 call for all speaker embeddings, then the crate's host logic in segment
+    order (assemble_segments, overlap clipping, EmbeddingManager).  Segments longer than 30 s keep whisper_full's sequential seek loop
+    (one `state.full` each).  Output == run_transcription_pipeline(..., carry_prompt=False) on the same input."""
+    speech_segments = list(speech_segments)
+    per_seg = [None] * len(speech_segments)
+    short = [i for i, sp in enumerate(speech_segments) if len(sp["samples"]) <= 480000]
+    p = params if params is not None else state.full_params()
+    p.prompt_tokens = None
+    p.prompt_n_tokens = 0
+    detected = None
+    for o in range(0, len(short), batch):
+        ids = short[o: o + batch]
+        pcm = np.zeros((len(ids), 480000), np.int16)
+        nv = np.zeros(len(ids), np.int32)
+        for r, i in enumerate(ids):
+            x = np.asarray(speech_segments[i]["samples"], np.int16)
+            pcm[r, : len(x)] = x
+            nv[r] = len(x)
+        segs = state.full_batch(pcm, nv, p)
+        if detected is None and ids and ids[0] == 0:
+            detected = capi.lang_str(state.chunk_lang_id(0))
+        for r, i in enumerate(ids):
+            per_seg[i] = [sg for sg in segs if sg["chunk"] == r]
+    for i, sp in enumerate(speech_segments):
+        if per_seg[i] is None:
+            per_seg[i] = state.full(np.asarray(sp["samples"], np.int16), p)
+            if detected is None and i == 0:
+                detected = capi.lang_str(state.lang_id())
+    emb = status = None
+    if extractor is not None and speech_segments:
+        off = np.zeros(len(speech_segments) + 1, np.int64)
+        for i, sp in enumerate(speech_segments):
+            off[i + 1] = off[i] + len(sp["samples"])
+        cat = np.concatenate([np.asarray(sp["samples"], np.int16) for sp in speech_segments]) if off[-1] else np.zeros(0, np.int16)
+        emb, status = extractor.compute_batch(cat, off)
+    mgr = capi.EmbeddingManager(max_speakers) if extractor is not None else None
+    out = []
+    for i, sp in enumerate(speech_segments):
+        segs = per_seg[i]
+        n_before = len(out)
+        assemble_segments(segs, sp["start"] + user_offset, out, translated)
+        speaker = None
+        if extractor is not None and segs:
+            if status[i] == 0:
+                sid = mgr.assign(emb[i], threshold)
+                speaker = str(sid) if sid else "?"
+            else:
+                speaker = "?"
+        for sgm in out[n_before:]:
+            sgm["speaker_id"] = speaker
+    if mgr is not None:
+        mgr.close()
+    if detected is None:
+        detected = capi.lang_str(state.lang_id())
+    return out, detected
+
+
 def format_cues(segments, lang, vad_mask=None, formatting_overrides=None):
     """The tail of Engine::transcribe_audio (reference src/engine.rs:189-198): PostProcessConfig::for_language(effective_lang) +
     overrides, process_segments with the VAD mask as the silence oracle (formatting.py restates src/formatting.rs)."""
