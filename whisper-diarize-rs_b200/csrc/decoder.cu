@@ -168,6 +168,9 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
 // part: [S][B][3d] partials of the fused QKV GEMM.  Scores: lane = key position (its 256 B K row against q broadcast from shared
 // memory); softmax by warp shuffles; P V: lane = two columns, V rows stream coalesced, 8 positions in flight per warp.
 constexpr int kSelfMaxHeadsPerCta = 5;
+// ANC = beam search / fallback rows (history read through the ancestry table); the greedy instantiation carries none of that code:
+// with a run-time `anc ? ... : 0` in the loops the greedy decode lost 160 ms per 120-window step (loads no longer batched).
+template <bool ANC>
 __global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
@@ -189,7 +192,7 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     float* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
     // beam search: position t < pos of this row's history lives in the cache of row anc[t][b] (the beam it descended from)
     const int64_t row_step = (int64_t)n_heads * kDecSeqCap * 64;
-#define WDR_ANC_ROW(t) (anc ? (int64_t)(anc[(int64_t)(t) * anc_ld + b] - b) * row_step : (int64_t)0)
+#define WDR_ANC_ROW(t) (ANC ? (int64_t)(anc[(int64_t)(t) * anc_ld + b] - b) * row_step : (int64_t)0)
     float* q = qs[warp];
     float* p = ps[warp];
 #pragma unroll
@@ -261,7 +264,7 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
 
 // cross-attention of one (head, window): q from the cross-query GEMM partials; K_c/V_c rows are 64 bf16 (128 B) at row
 // stride 2d.  8 lanes x 16 B cover one row; a warp covers 4 rows per load, the CTA (8 warps) 32 rows.
-template <int MINB>
+template <int MINB, bool ROWMAP>
 __global__ void __launch_bounds__(256, MINB)
 dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
                       const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
@@ -286,7 +289,7 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
 #pragma unroll
     for (int j = 0; j < 8; j++) q8[j] = q[g * 8 + j];
     // head-major cross cache: [(window, head)][K | V][1500][64] — both blocks of a CTA are contiguous 192 KB streams
-    const __nv_bfloat16* Kb = ckv + ((int64_t)(row_window ? row_window[b] : b) * gridDim.x + hh) * 2 * kT * 64 + g * 8;
+    const __nv_bfloat16* Kb = ckv + ((int64_t)(ROWMAP ? row_window[b] : b) * gridDim.x + hh) * 2 * kT * 64 + g * 8;
     const __nv_bfloat16* Vb = Kb + kT * 64;
     const int64_t rs = 64;
     // ---- scores ----
@@ -1049,9 +1052,10 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             ProfScope ps(prof, KC_DECODER, st);
             int hpc = kSelfMaxHeadsPerCta;
             while (H % hpc) hpc--;
-            WDR_CUDA_TRY(launch_kernel(dec_self_attn_kernel, dim3(H / hpc, B), dim3(hpc * 32), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_qkv,
-                                       ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d, ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att,
-                                       (int64_t)ws.cap_B * d, win, t_limit, beam ? ws.beam_anc_cur : nullptr, kDecMaxBatch));
+            WDR_CUDA_TRY(launch_kernel(beam ? dec_self_attn_kernel<true> : dec_self_attn_kernel<false>, dim3(H / hpc, B), dim3(hpc * 32), 0, st, pdl, ws.part,
+                                       sg.splits, sg.split_stride, e.b_qkv, ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d,
+                                       ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att, (int64_t)ws.cap_B * d, win, t_limit,
+                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecMaxBatch));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
@@ -1064,9 +1068,9 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             // registers); 8 (32 registers) spills and is much slower.  A single-pass online-softmax variant that streams K_c and
             // V_c rows together was tried and is slower (2070 ms): its per-iteration max -> exp -> FMA chain keeps fewer loads in
             // flight than the two independent passes do.
-            WDR_CUDA_TRY(launch_kernel(dec_cross_attn_kernel<6>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
+            WDR_CUDA_TRY(launch_kernel(beam ? dec_cross_attn_kernel<6, true> : dec_cross_attn_kernel<6, false>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
                                        (int64_t)ws.cap_B * d, capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T, ws.aw_A, pos_ptr, pos,
-                                       win, t_limit, beam ? ws.beam_rowwin : nullptr));
+                                       win, t_limit, beam ? (const int32_t*)ws.beam_rowwin : (const int32_t*)nullptr));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
