@@ -487,9 +487,11 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
     const int64_t r0 = row_off[b] + q0;
     float* qs = sm;                         // [16][64]
     float* p = qs + kDtwpQB * 64;           // [16][1504]; reused as the P V reduction buffer [8][16][64]
+    // queries interleaved in pairs, qs[(qi / 2) * 128 + 2 c + (qi & 1)]: one 64-bit operand holds column c of two queries, so the
+    // scores below are packed FFMA2s (fma.rn.f32x2, the key value broadcast) — per query the same fmaf chain in the same order
     for (int e = tid; e < kDtwpQB * 64; e += 256) {
         const int qi = e >> 6, c = e & 63;
-        qs[e] = qi < nq ? (qpart[(r0 + qi) * (int64_t)d + hh * 64 + c] + b_q[hh * 64 + c]) * 0.125f : 0.0f;
+        qs[(qi >> 1) * 128 + 2 * c + (qi & 1)] = qi < nq ? (qpart[(r0 + qi) * (int64_t)d + hh * 64 + c] + b_q[hh * 64 + c]) * 0.125f : 0.0f;
     }
     for (int e = tid; e < kDtwpQB * 4; e += 256) p[(e >> 2) * kDtwpPStride + kT + (e & 3)] = 0.0f;
     __syncthreads();
@@ -512,18 +514,17 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
             }
         }
 #pragma unroll 4
-        for (int qi = 0; qi < kDtwpQB; qi++) {
-            const float4* qv = reinterpret_cast<const float4*>(qs + qi * 64);
-            float a = 0.0f;
+        for (int qp = 0; qp < kDtwpQB / 2; qp++) {
+            const float4* qv = reinterpret_cast<const float4*>(qs + qp * 128);
+            float2 a = make_float2(0.0f, 0.0f);  // (query 2 qp, query 2 qp + 1)
 #pragma unroll
-            for (int c4 = 0; c4 < 16; c4++) {
-                const float4 f = qv[c4];
-                a = fmaf(f.x, k[c4 * 4], a);
-                a = fmaf(f.y, k[c4 * 4 + 1], a);
-                a = fmaf(f.z, k[c4 * 4 + 2], a);
-                a = fmaf(f.w, k[c4 * 4 + 3], a);
+            for (int c2 = 0; c2 < 32; c2++) {
+                const float4 f = qv[c2];  // columns 2 c2 and 2 c2 + 1 of both queries
+                a = __ffma2_rn(make_float2(f.x, f.y), make_float2(k[2 * c2], k[2 * c2]), a);
+                a = __ffma2_rn(make_float2(f.z, f.w), make_float2(k[2 * c2 + 1], k[2 * c2 + 1]), a);
             }
-            p[qi * kDtwpPStride + t] = a;
+            p[(2 * qp) * kDtwpPStride + t] = a.x;
+            p[(2 * qp + 1) * kDtwpPStride + t] = a.y;
         }
     }
     __syncthreads();
@@ -552,9 +553,9 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
     }
     __syncthreads();
     // ---- P V: warp = key slice (groups of 4 keys), lane = column pair ----
-    float acc[kDtwpQB][2];
+    float2 acc[kDtwpQB];  // packed FFMA2 with the probability broadcast: per column the same fmaf chain as a scalar loop
 #pragma unroll
-    for (int qi = 0; qi < kDtwpQB; qi++) { acc[qi][0] = 0.0f; acc[qi][1] = 0.0f; }
+    for (int qi = 0; qi < kDtwpQB; qi++) acc[qi] = make_float2(0.0f, 0.0f);
     for (int t4 = warp * 4; t4 < kT; t4 += 32) {
         float2 v[4];
 #pragma unroll
@@ -563,18 +564,18 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
 #pragma unroll
         for (int qi = 0; qi < kDtwpQB; qi++) {
             const float4 pv = *reinterpret_cast<const float4*>(p + qi * kDtwpPStride + t4);
-            acc[qi][0] = fmaf(pv.x, v[0].x, acc[qi][0]); acc[qi][1] = fmaf(pv.x, v[0].y, acc[qi][1]);
-            acc[qi][0] = fmaf(pv.y, v[1].x, acc[qi][0]); acc[qi][1] = fmaf(pv.y, v[1].y, acc[qi][1]);
-            acc[qi][0] = fmaf(pv.z, v[2].x, acc[qi][0]); acc[qi][1] = fmaf(pv.z, v[2].y, acc[qi][1]);
-            acc[qi][0] = fmaf(pv.w, v[3].x, acc[qi][0]); acc[qi][1] = fmaf(pv.w, v[3].y, acc[qi][1]);
+            acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[0], acc[qi]);
+            acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[1], acc[qi]);
+            acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[2], acc[qi]);
+            acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[3], acc[qi]);
         }
     }
     __syncthreads();  // all warps are done reading p
     float* red = p;   // [8][16][64]
 #pragma unroll
     for (int qi = 0; qi < kDtwpQB; qi++) {
-        red[(warp * kDtwpQB + qi) * 64 + 2 * lane] = acc[qi][0];
-        red[(warp * kDtwpQB + qi) * 64 + 2 * lane + 1] = acc[qi][1];
+        red[(warp * kDtwpQB + qi) * 64 + 2 * lane] = acc[qi].x;
+        red[(warp * kDtwpQB + qi) * 64 + 2 * lane + 1] = acc[qi].y;
     }
     __syncthreads();
     for (int e = tid; e < nq * 64; e += 256) {
