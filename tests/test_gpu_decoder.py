@@ -436,6 +436,10 @@ def test_temperature_fallback_matches_oracle(wdr, oracle, tiny_w):
         assert [t.id for t in got["tokens"]] == [t.id for t in r["tokens"]]
         assert [(t.t0, t.t1, t.t_dtw) for t in got["tokens"]] == [(t.t0, t.t1, t.t_dtw) for t in r["tokens"]]
     dec.close()
+    # the ladder inside the sequential seek loop (one long buffer): every window is decoded, windows that fail walk the ladder
+    long = np.concatenate([pcm[0], pcm[1][:200000]])
+    s_long = st.full(long, st.full_params(strategy=1, beam_size=5, temperature_inc=0.4, logprob_thold=thold))
+    assert len(s_long) >= 2 and s_long[0]["t0"] <= s_long[1]["t0"]
     st.close()
     ctx.close()
 
