@@ -498,33 +498,46 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
     const __nv_bfloat16* Kb = ckv + ((int64_t)b * gridDim.y + hh) * 2 * kT * 64;
     const __nv_bfloat16* Vb = Kb + kT * 64;
     const int64_t rs = 64;
-    // ---- scores ----
-    for (int t = tid; t < kT; t += 256) {
-        float k[64];
-        const uint4* kr = reinterpret_cast<const uint4*>(Kb + (int64_t)t * rs);
+    // ---- scores: two key rows per thread (kept as packed bf16, 64 registers), columns outer, query pairs inner — every
+    // broadcast LDS.128 of the queries (the shared-memory pipe bounds this loop) feeds four FFMA2s instead of two ----
+    for (int t = tid; t < kT; t += 512) {
+        const int t1 = t + 256;
+        const bool has1 = t1 < kT;
+        uint4 ka[8], kb[8];
+        {
+            const uint4* kra = reinterpret_cast<const uint4*>(Kb + (int64_t)t * rs);
+            const uint4* krb = reinterpret_cast<const uint4*>(Kb + (int64_t)(has1 ? t1 : t) * rs);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++) { ka[c8] = __ldg(kra + c8); kb[c8] = __ldg(krb + c8); }
+        }
+        float2 a0[kDtwpQB / 2], a1[kDtwpQB / 2];  // (query 2 qp, query 2 qp + 1) of row t / row t1
+#pragma unroll
+        for (int qp = 0; qp < kDtwpQB / 2; qp++) { a0[qp] = make_float2(0.0f, 0.0f); a1[qp] = make_float2(0.0f, 0.0f); }
 #pragma unroll
         for (int c8 = 0; c8 < 8; c8++) {
-            const uint4 u = __ldg(kr + c8);
-            const __nv_bfloat162* e = reinterpret_cast<const __nv_bfloat162*>(&u);
+            const __nv_bfloat162* ea = reinterpret_cast<const __nv_bfloat162*>(&ka[c8]);
+            const __nv_bfloat162* eb = reinterpret_cast<const __nv_bfloat162*>(&kb[c8]);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const float2 f = __bfloat1622float2(e[j]);
-                k[c8 * 8 + 2 * j] = f.x;
-                k[c8 * 8 + 2 * j + 1] = f.y;
+                const float2 fa = __bfloat1622float2(ea[j]), fb = __bfloat1622float2(eb[j]);  // columns 2 c2, 2 c2 + 1 (c2 = 4 c8 + j)
+#pragma unroll
+                for (int qp = 0; qp < kDtwpQB / 2; qp++) {
+                    const float4 f = *reinterpret_cast<const float4*>(qs + qp * 128 + (c8 * 4 + j) * 4);  // those columns of both queries
+                    a0[qp] = __ffma2_rn(make_float2(f.x, f.y), make_float2(fa.x, fa.x), a0[qp]);
+                    a0[qp] = __ffma2_rn(make_float2(f.z, f.w), make_float2(fa.y, fa.y), a0[qp]);
+                    a1[qp] = __ffma2_rn(make_float2(f.x, f.y), make_float2(fb.x, fb.x), a1[qp]);
+                    a1[qp] = __ffma2_rn(make_float2(f.z, f.w), make_float2(fb.y, fb.y), a1[qp]);
+                }
             }
         }
-#pragma unroll 4
-        for (int qp = 0; qp < kDtwpQB / 2; qp++) {
-            const float4* qv = reinterpret_cast<const float4*>(qs + qp * 128);
-            float2 a = make_float2(0.0f, 0.0f);  // (query 2 qp, query 2 qp + 1)
 #pragma unroll
-            for (int c2 = 0; c2 < 32; c2++) {
-                const float4 f = qv[c2];  // columns 2 c2 and 2 c2 + 1 of both queries
-                a = __ffma2_rn(make_float2(f.x, f.y), make_float2(k[2 * c2], k[2 * c2]), a);
-                a = __ffma2_rn(make_float2(f.z, f.w), make_float2(k[2 * c2 + 1], k[2 * c2 + 1]), a);
+        for (int qp = 0; qp < kDtwpQB / 2; qp++) {
+            p[(2 * qp) * kDtwpPStride + t] = a0[qp].x;
+            p[(2 * qp + 1) * kDtwpPStride + t] = a0[qp].y;
+            if (has1) {
+                p[(2 * qp) * kDtwpPStride + t1] = a1[qp].x;
+                p[(2 * qp + 1) * kDtwpPStride + t1] = a1[qp].y;
             }
-            p[(2 * qp) * kDtwpPStride + t] = a.x;
-            p[(2 * qp + 1) * kDtwpPStride + t] = a.y;
         }
     }
     __syncthreads();
