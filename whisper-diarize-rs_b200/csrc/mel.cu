@@ -44,7 +44,11 @@ constexpr size_t kMelSmemBytes = MEL_TILE_SAMPLES * sizeof(float) + MEL_NFFT * s
                                  MEL_PAIRS_PER_CTA * MEL_ZPITCH * sizeof(cpx) + MEL_NBINS * MEL_PPITCH * sizeof(float);
 
 __device__ __forceinline__ float decode_sample(float v) { return v; }
-__device__ __forceinline__ float decode_sample(int16_t v) { return (float)v * (1.0f / 32768.0f); }
+// int16 -> fp32 without I2F (which runs on the 4-lane XU pipe and held 10 % of this kernel's stall samples): 1.5 * 2^23 + v is
+// exact in fp32 for |v| < 2^22, so the integer add into its bit pattern followed by the subtraction gives (float)v exactly
+__device__ __forceinline__ float decode_sample(int16_t v) {
+    return (__int_as_float(0x4B400000 + (int)v) - 12582912.0f) * (1.0f / 32768.0f);
+}
 
 // sample at signed position s of the reflect-padded / zero-extended signal
 template <typename In>
