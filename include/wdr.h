@@ -244,7 +244,7 @@ typedef struct wdr_full_params {
     float thold_pt, thold_ptsum;
     int max_len, split_on_word, max_tokens;
     int audio_ctx;
-    const char* initial_prompt;      /* needs a tokenizer file: refused when non-empty */
+    const char* initial_prompt;      /* tokenised with the context's vocabulary (wdr_tokenize); then replaces prompt_tokens, as upstream */
     const int32_t* prompt_tokens;    /* ids appended to the text context ([PREV] + tokens + sot sequence) */
     int prompt_n_tokens;
     const char* language;            /* "en", "de", ...; NULL = "en" */
@@ -291,6 +291,12 @@ int wdr_full_get_chunk_lang_id_from_state(wdr_state* state, int i_chunk);
 const char* wdr_lang_str(int id);                                                          /* whisper_rs::get_lang_str, :394 */
 int wdr_lang_id(const char* lang);                                                         /* whisper_lang_id */
 const char* wdr_token_to_str(wdr_context* ctx, int32_t token);                             /* whisper_token_to_str */
+/* whisper_tokenize (what whisper_full applies to `initial_prompt`; the crate feeds the previous segment's text back through it,
+ * src/transcribe.rs:383-386): GPT-2 style word split + longest vocabulary entry at every position.  Returns the number of tokens
+ * written, or the negated count if it exceeds n_max_tokens.  Host code (no device work).  wdr_tokenize_with_vocab runs the same
+ * tokenizer over an explicit vocabulary (token_strings[i] = text of id i; NULL entries are skipped). */
+int wdr_tokenize(wdr_context* ctx, const char* text, int32_t* tokens, int n_max_tokens);
+int wdr_tokenize_with_vocab(const char* const* token_strings, int n_tokens, const char* text, int32_t* tokens, int n_max_tokens);
 /* Per-chunk decoder summary of the last full call: info[8] = {seek_delta, failed, completed, n_sampled, has_ts, result_len,
  * seek_end, n_segments}; *no_speech_prob optional.  For parity tests. */
 /* Device time (CUDA events on the compute stream) of the phases of the last full call, summed over its groups (and lanes):

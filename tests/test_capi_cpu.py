@@ -87,3 +87,33 @@ def test_sampler_matches_oracle_restatement(wdr):
     lp = np.full(100, -np.inf, np.float32)
     lp[37] = 0.0
     assert (wdr.sample_discrete(lp, 9, 20) == 37).all()
+
+
+def test_tokenizer_matches_oracle_restatement(wdr):
+    """wdr_tokenize_with_vocab (whisper_tokenize: the step that turns `initial_prompt` into prompt tokens; host code) against
+    oracle/tokenizer.py on a GPT-2 flavoured mini vocabulary and on the synthetic vocabulary of the seeded contexts: word split
+    (contractions, letter / digit / punctuation runs with an optional leading space, trailing whitespace), longest match from the
+    left, unknown bytes skipped, duplicate strings resolved to the highest id, UTF-8 bytes, and the buffer-too-small convention."""
+    from oracle import tokenizer as T, vocab as V
+    vocab = [" hello", " world", "hello", "he", "llo", " wor", "ld", ",", " ,", "!", " ", "  ", "\n", "'s", "'", "s", " it", " 20", "2", "0",
+             " 2024", "é".encode(), b"\xc3", " the", " th", "e", "e", None, " x"]
+    texts = [" hello world", "hello, world!", " it's 2024 20 2", "  hello   world  ", "\n hello\n\n", "héllo thé", " unknownzzz x", "", "''s's",
+             " the the  the", "x y z"]
+    for text in texts:
+        ref = T.tokenize(vocab, text)
+        got = wdr.tokenize_with_vocab(vocab, text)
+        assert list(got) == ref, (text, list(got), ref)
+    assert list(wdr.tokenize_with_vocab(vocab, "e")) == [26]  # the later duplicate wins
+    nv = 51864
+    synth = [V.token_text(i, nv) for i in range(nv)]
+    rng = np.random.default_rng(5)
+    ids = [int(i) for i in rng.integers(0, 50256, 40)]
+    text = "".join(synth[i] for i in ids)  # text assembled from tokens, as the crate's carried prompt is
+    ref = T.tokenize(synth, text)
+    got = wdr.tokenize_with_vocab(synth, text)
+    assert list(got) == ref and len(ref) > 0
+    assert "".join(synth[i] for i in ref).replace(" ", "") == text.replace(" ", "") or len(ref) > 0
+    L = wdr.load()
+    arr = (ctypes.c_char_p * 2)(b" a", b"b")
+    out = np.zeros(1, np.int32)
+    assert L.wdr_tokenize_with_vocab(arr, 2, b" a b b", out.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 1) == -3

@@ -494,3 +494,33 @@ def test_greedy_strategy_temperature_sampling(wdr, oracle, tiny_w):
     assert [(t.t0, t.t1, t.t_dtw) for t in alone[0]["tokens"]] == [(t.t0, t.t1, t.t_dtw) for t in segs[fb]["tokens"]]
     st.close()
     ctx.close()
+
+
+def test_initial_prompt_is_tokenized_like_whisper(wdr, oracle):
+    """`initial_prompt` (the crate feeds the previous segment's text back through it, reference src/transcribe.rs:383-386, and the
+    user's own prompt, :74-76): whisper_full tokenises the string with the context's vocabulary and uses the ids as the prompt tokens.
+    The context's tokenizer equals the oracle restatement on the same vocabulary, the decode with the string equals the decode with
+    those ids passed as prompt_tokens, and the prompt does change the result."""
+    import ctypes as C
+    from oracle import tokenizer as T, vocab as V
+    arch, nv = "tiny.en", 51864
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    pcm = synth_audio(2300, 14.0)
+    plain = st.full(pcm)
+    assert plain
+    text = plain[0]["text"] + " and,"  # the text of a segment, as the crate carries it, plus something typed by a user
+    ids = ctx.tokenize(text)
+    synth = [V.token_text(i, nv) for i in range(nv)]
+    assert list(ids) == T.tokenize(synth, text) and len(ids) >= 3
+    with_text = st.full(pcm, st.full_params(initial_prompt=text))
+    keep = np.ascontiguousarray(ids, np.int32)
+    p = st.full_params()
+    p.prompt_tokens = keep.ctypes.data_as(C.POINTER(C.c_int32))
+    p.prompt_n_tokens = len(keep)
+    with_ids = st.full(pcm, p)
+    sig = lambda segs: [[(t.id, t.t0, t.t1, t.t_dtw) for t in s["tokens"]] for s in segs]
+    assert sig(with_text) == sig(with_ids)
+    assert sig(with_text) != sig(plain), "the prompt never reached the decoder"
+    st.close()
+    ctx.close()

@@ -12,7 +12,7 @@ or through the `wdr_b200` alias module at the repo root.
 from .capi import (  # noqa: F401
     WdrError, load, lib_path, build, version, device_count, launch_count,
     MelFrontend, log_mel, median_filter, dtw_cost, dtw, dtw_batch_dev, kaldi_fbank, fbank_frames,
-    signal_energy, convert_integer_to_float_audio, resample_to_16k, sample_discrete, mel_n_len, gemm_bf16_dev,
+    signal_energy, convert_integer_to_float_audio, resample_to_16k, sample_discrete, tokenize_with_vocab, mel_n_len, gemm_bf16_dev,
     Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
     FullParams, TokenData, lang_str, lang_id, ggml_probe,
     VadContext, VadParams, vad_default_params, vad_segments_from_probs,

@@ -160,6 +160,8 @@ def load():
     L.wdr_token_to_str.restype = C.c_char_p
     L.wdr_full_get_chunk_info_from_state.argtypes = [C.c_void_p, C.c_int, i32p, f32p]
     L.wdr_sample_discrete.argtypes = [f32p, C.c_int, C.c_uint32, C.c_int, i32p]
+    L.wdr_tokenize.argtypes = [C.c_void_p, C.c_char_p, i32p, C.c_int]
+    L.wdr_tokenize_with_vocab.argtypes = [C.POINTER(C.c_char_p), C.c_int, C.c_char_p, i32p, C.c_int]
     L.wdr_full_get_chunk_temperature_from_state.argtypes = [C.c_void_p, C.c_int]
     L.wdr_full_get_chunk_temperature_from_state.restype = C.c_float
     L.wdr_decode_teacher_forced.argtypes = [C.c_void_p, C.c_void_p, f32p, C.c_int, i32p, C.c_int, f32p, f32p]
@@ -336,6 +338,16 @@ def resample_to_16k(pcm_i16, sample_rate, channels=1, want_f32=False):
     return (o16, o32) if want_f32 else o16
 
 
+def tokenize_with_vocab(token_strings, text, n_max=4096):
+    """whisper_tokenize over an explicit vocabulary (list of str / bytes / None by id): wdr_tokenize_with_vocab."""
+    arr = (C.c_char_p * len(token_strings))(*[None if t is None else (t if isinstance(t, bytes) else t.encode()) for t in token_strings])
+    out = np.empty(n_max, np.int32)
+    n = load().wdr_tokenize_with_vocab(arr, len(token_strings), text.encode() if isinstance(text, str) else text, _p(out, i32p), n_max)
+    if n < 0:
+        raise ValueError(f"{-n} tokens do not fit {n_max}")
+    return out[:n].copy()
+
+
 def sample_discrete(logprobs, seed, n_draws):
     """n_draws consecutive whisper_sample_token(best=false) draws (host-side sampler of the temperature ladder)."""
     lp = _np(logprobs, np.float32)
@@ -456,6 +468,14 @@ class Context:
 
     def create_state(self):
         return State(self)
+
+    def tokenize(self, text, n_max=4096):
+        """whisper_tokenize with this context's vocabulary (what whisper_full applies to `initial_prompt`)."""
+        out = np.empty(n_max, np.int32)
+        n = load().wdr_tokenize(self._h, text.encode() if isinstance(text, str) else text, _p(out, i32p), n_max)
+        if n < 0:
+            raise ValueError(f"{-n} tokens do not fit {n_max}")
+        return out[:n].copy()
 
 
 class State:

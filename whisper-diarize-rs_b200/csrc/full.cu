@@ -212,13 +212,23 @@ static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int
         *lang_id = -1;
         return WDR_OK;
     }
-    if (p.initial_prompt && p.initial_prompt[0]) { set_error("initial_prompt needs a tokenizer file; pass prompt_tokens instead"); return WDR_ERR_UNSUPPORTED; }
     if (p.offset_ms || p.duration_ms || p.max_len || p.max_tokens || p.audio_ctx || p.suppress_nst) { set_error("offset/duration/max_len/max_tokens/audio_ctx/suppress_nst are not implemented"); return WDR_ERR_UNSUPPORTED; }
     if (p.translate && !ctx->arch.multilingual) { set_error("translate needs a multilingual model"); return WDR_ERR_INVALID; }
     int id = lang_id_from_str(p.language ? p.language : "en");
     if (id < 0) { set_error("unknown language '%s'", p.language); return WDR_ERR_INVALID; }
     *lang_id = id;
     return WDR_OK;
+}
+
+int tokenize_for_context(const wdr_context* ctx, const char* text, std::vector<int32_t>& out);  // tokenizer.cu
+
+// whisper_full: `initial_prompt` is tokenised first and then IS the prompt-token list (it replaces params.prompt_tokens)
+static void resolve_initial_prompt(const wdr_context* ctx, wdr_full_params& p, std::vector<int32_t>& store) {
+    if (!ctx || !p.initial_prompt || !p.initial_prompt[0]) return;
+    tokenize_for_context(ctx, p.initial_prompt, store);
+    p.prompt_tokens = store.data();
+    p.prompt_n_tokens = (int)store.size();
+    p.initial_prompt = nullptr;
 }
 
 template <typename T>
@@ -1174,7 +1184,7 @@ extern "C" wdr_full_params wdr_full_default_params(int strategy) {
     p.temperature = 0.0f;
     p.max_initial_ts = 1.0f;
     p.length_penalty = -1.0f;
-    p.temperature_inc = 0.0f;  // whisper.cpp: 0.2 — the fallback ladder is not implemented
+    p.temperature_inc = 0.0f;  // whisper.cpp: 0.2; the ladder is implemented, callers opt in (include/wdr.h)
     p.entropy_thold = 2.4f;
     p.logprob_thold = -1.0f;
     p.no_speech_thold = 0.6f;
@@ -1186,6 +1196,8 @@ extern "C" wdr_full_params wdr_full_default_params(int strategy) {
 
 extern "C" int wdr_full_with_state(wdr_context* ctx, wdr_state* st, wdr_full_params p, const float* pcm, int n) {
     clear_error();
+    std::vector<int32_t> prompt_store;
+    resolve_initial_prompt(ctx, p, prompt_store);
     WDR_REQUIRE(n >= 0, "negative sample count");
     if (n > WDR_CHUNK_SAMPLES) return full_long<float>(ctx, st, p, pcm, n);
     const int32_t nv = n;
@@ -1193,6 +1205,8 @@ extern "C" int wdr_full_with_state(wdr_context* ctx, wdr_state* st, wdr_full_par
 }
 extern "C" int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm, int n) {
     clear_error();
+    std::vector<int32_t> prompt_store;
+    resolve_initial_prompt(ctx, p, prompt_store);
     WDR_REQUIRE(n >= 0, "negative sample count");
     if (n > WDR_CHUNK_SAMPLES) return full_long<int16_t>(ctx, st, p, pcm, n);
     const int32_t nv = n;
@@ -1200,11 +1214,15 @@ extern "C" int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* st, wdr_full
 }
 extern "C" int wdr_full_batch_i16(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm, int64_t chunk_stride,
                                   const int32_t* n_valid, int n_chunks) {
+    std::vector<int32_t> prompt_store;
+    resolve_initial_prompt(ctx, p, prompt_store);
     return full_batch_impl<int16_t>(ctx, st, p, pcm, chunk_stride, n_valid, n_chunks);
 }
 
 extern "C" int wdr_full_batch_i16_dev(wdr_context* ctx, wdr_state* st, wdr_full_params p, const int16_t* pcm_dev, int64_t chunk_stride,
                                       const int32_t* n_valid, int n_chunks) {
+    std::vector<int32_t> prompt_store;
+    resolve_initial_prompt(ctx, p, prompt_store);
     return full_batch_impl<int16_t>(ctx, st, p, pcm_dev, chunk_stride, n_valid, n_chunks, true);
 }
 

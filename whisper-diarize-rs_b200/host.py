@@ -198,21 +198,20 @@ def run_transcription_pipeline(state, speech_segments, params=None, extractor=No
     `state.full` on its samples (one buffer; > 30 s runs whisper_full's own seek loop), segments -> words (get_token_timestamps),
     absolute times (base_offset = segment.start + user offset), overlap clipping against the previous segment, and — with an
     EmbeddingExtractor — the speaker of the SPEECH segment's samples through an EmbeddingManager (:461-497; "?" when the embedding
-    fails).  The crate feeds the previous segment's text back as `initial_prompt` (:383-386, :502); text prompts need a tokenizer
-    file, so the carried context crosses the C ABI as the previous segment's token ids (`prompt_tokens`), same effect.
+    fails).  The crate feeds the previous segment's (left-trimmed) text back as `initial_prompt` (:383-386, :502): the library
+    tokenises it with the context's vocabulary as whisper_full does (wdr_tokenize).
     Returns (segments [dict(start, end, text, words, speaker_id)], detected_lang)."""
     mgr = capi.EmbeddingManager(max_speakers) if extractor is not None else None
-    out, previous_ids, detected = [], None, None
+    out, previous_text, detected = [], None, None
+    sticky = None  # `params.set_initial_prompt` mutates the params the loop clones: once set, a prompt stays until replaced
     for sp in speech_segments:
         p = params if params is not None else state.full_params()
-        keep = None
-        if carry_prompt and previous_ids:
-            keep = np.ascontiguousarray(np.array(previous_ids, np.int32))
-            p.prompt_tokens = keep.ctypes.data_as(capi.i32p)
-            p.prompt_n_tokens = len(keep)
-        else:
-            p.prompt_tokens = None
-            p.prompt_n_tokens = 0
+        p.prompt_tokens = None
+        p.prompt_n_tokens = 0
+        if carry_prompt and previous_text is not None:                                   # :383-386
+            sticky = previous_text.encode()
+        keep = sticky                                                                    # kept alive for the call (borrowed string)
+        p.initial_prompt = keep
         segs = state.full(np.asarray(sp["samples"], np.int16), p)                      # :389
         del keep
         if detected is None:
@@ -227,14 +226,9 @@ def run_transcription_pipeline(state, speech_segments, params=None, extractor=No
                 speaker = str(sid) if sid else "?"
             except capi.WdrError:
                 speaker = "?"
-        ids = []
-        for s in segs:
-            ids += [int(t.id) for t in s["tokens"]]
         for s in out[n_before:]:
             s["speaker_id"] = speaker
-        if segs:
-            eot = 50257 if state.ctx.dims.n_vocab >= 51865 else 50256
-            previous_ids = [i for i in ids if i < eot]                                # text of the last call (:502), as token ids
+            previous_text = s["text"] if s["text"].strip() else None                    # :502 (updated per whisper segment)
     if mgr is not None:
         mgr.close()
     return out, detected
