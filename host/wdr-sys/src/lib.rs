@@ -88,6 +88,14 @@ extern "C" {
     pub fn wdr_full_lang_id_from_state(st: *mut wdr_state) -> c_int;                              // :393
     pub fn wdr_lang_str(id: c_int) -> *const c_char;                                              // whisper_rs::get_lang_str, :394
     pub fn wdr_convert_integer_to_float_audio(pcm: *const i16, n: c_int, out: *mut c_float) -> c_int; // src/vad.rs:12
+    // src/audio.rs:17-19: instead of bailing on a non-16 kHz / multi-channel WAV, resample on the device
+    pub fn wdr_resample_n_out(n_frames: i64, sample_rate: c_int) -> i64;
+    pub fn wdr_resample_i16(pcm: *const i16, n_frames: i64, channels: c_int, sample_rate: c_int, out_i16: *mut i16, out_f32: *mut c_float,
+                            out_cap: i64, n_out: *mut i64) -> c_int;
+    // whisper_tokenize (WhisperContext::tokenize): what whisper_full applies to `initial_prompt` (src/transcribe.rs:74-76, 383-386)
+    pub fn wdr_tokenize(ctx: *mut wdr_context, text: *const c_char, tokens: *mut i32, n_max_tokens: c_int) -> c_int;
+    // temperature ladder: the temperature whose result stands for chunk i of the last call (-1.0 if out of range)
+    pub fn wdr_full_get_chunk_temperature_from_state(st: *mut wdr_state, i_chunk: c_int) -> c_float;
     // ---- Silero VAD (src/vad.rs:15-43) ----------------------------------------------------------------------------
     pub fn wdr_vad_default_context_params() -> wdr_vad_context_params;
     pub fn wdr_vad_default_params() -> wdr_vad_params;
