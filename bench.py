@@ -511,6 +511,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:  # one process per GPU shares the box's cores: split them instead of 16 host threads per rank
+        os.environ.setdefault("WDR_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // world)))
     if w.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: libwdr_b200 has no CPU path")
     torch.cuda.set_device(local)

@@ -69,11 +69,13 @@ static int timestamp_to_sample(int64_t t, int n_samples) {
 }
 static int64_t sample_to_timestamp(int i) { return (100ll * i) / WDR_SAMPLE_RATE; }
 
-// f(i) for i in [0, n) on up to 16 host threads (dynamic claim); f must not touch shared state
+// f(i) for i in [0, n) on up to 16 host threads (dynamic claim); f must not touch shared state.  WDR_HOST_THREADS caps the count:
+// with one process per GPU on a box with few cores, eight ranks x 16 threads would oversubscribe the host under the DTW pass.
 template <typename F>
 static void parallel_for(int n, F f) {
+    static const int cap = getenv("WDR_HOST_THREADS") ? std::max(1, atoi(getenv("WDR_HOST_THREADS"))) : 16;
     int nt = (int)std::thread::hardware_concurrency();
-    nt = std::max(1, std::min(std::min(nt, 16), n));
+    nt = std::max(1, std::min(std::min(nt, cap), n));
     if (nt <= 1) { for (int i = 0; i < n; i++) f(i); return; }
     std::atomic<int> next{0};
     std::vector<std::thread> th;
