@@ -383,6 +383,144 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
     }
 }
 
+// Beam search / best_of decoding: the K rows (decoders) of a window share its K_c / V_c.  One CTA per (head, window) reads the two
+// 192 KB blocks ONCE for all its rows (the single-query kernel re-reads them per row and is L2-bound at beam 5: 113 us per launch
+// against 30 us of HBM time).  Same arithmetic as the batched DTW-pass kernel: thread = key row, the queries (pre-scaled by 1/8,
+// interleaved in pairs) broadcast from shared memory into packed FFMA2s, one fmaf chain per (row, query) in column order; softmax
+// by one warp per row; P V with warp = key slice, lane = column pair.  NQP = query pairs (rows padded to 2 NQP with zero queries).
+// Rows b = w * K + i; rows with t_limit[b] <= pos are dead: nothing is stored for them; a window with no live row returns at once.
+template <int NQP>
+__global__ void __launch_bounds__(256)
+dec_cross_attn_rows_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
+                           const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off, int pos,
+                           const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window, int K) {
+    extern __shared__ __align__(16) float rows_smem[];
+    constexpr int NQ = 2 * NQP;
+    constexpr int kPS = kT + 4;
+    float* qs = rows_smem;        // [NQP][64 columns][2 queries]
+    float* p = qs + NQP * 128;    // [NQ][kT + 4]; reused as the P V reduction buffer [8][NQ][64]
+    const int hh = blockIdx.x, w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = w * K;
+    bool any = false;
+    for (int i = 0; i < K; i++) any |= pos < t_limit[b0 + i];
+    if (!any) return;
+    for (int e = tid; e < NQP * 128; e += 256) {
+        const int qp = e >> 7, c = (e & 127) >> 1, qi = 2 * qp + (e & 1);
+        qs[e] = qi < K ? (part_sum(part, n_splits, split_stride, (int64_t)(b0 + qi) * d + hh * 64 + c) + b_q[hh * 64 + c]) * 0.125f : 0.0f;
+    }
+    for (int e = tid; e < NQ * 4; e += 256) p[(e >> 2) * kPS + kT + (e & 3)] = 0.0f;
+    __syncthreads();
+    const __nv_bfloat16* Kb = ckv + ((int64_t)row_window[b0] * gridDim.x + hh) * 2 * kT * 64;
+    const __nv_bfloat16* Vb = Kb + kT * 64;
+    // ---- scores: two key rows per thread, columns outer, query pairs inner ----
+    for (int t = tid; t < kT; t += 512) {
+        const int t1 = t + 256;
+        const bool has1 = t1 < kT;
+        uint4 ka[8], kb[8];
+        {
+            const uint4* kra = reinterpret_cast<const uint4*>(Kb + (int64_t)t * 64);
+            const uint4* krb = reinterpret_cast<const uint4*>(Kb + (int64_t)(has1 ? t1 : t) * 64);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; c8++) { ka[c8] = __ldg(kra + c8); kb[c8] = __ldg(krb + c8); }
+        }
+        float2 a0[NQP], a1[NQP];
+#pragma unroll
+        for (int qp = 0; qp < NQP; qp++) { a0[qp] = make_float2(0.0f, 0.0f); a1[qp] = make_float2(0.0f, 0.0f); }
+#pragma unroll
+        for (int c8 = 0; c8 < 8; c8++) {
+            const __nv_bfloat162* ea = reinterpret_cast<const __nv_bfloat162*>(&ka[c8]);
+            const __nv_bfloat162* eb = reinterpret_cast<const __nv_bfloat162*>(&kb[c8]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 fa = __bfloat1622float2(ea[j]), fb = __bfloat1622float2(eb[j]);
+#pragma unroll
+                for (int qp = 0; qp < NQP; qp++) {
+                    const float4 f = *reinterpret_cast<const float4*>(qs + qp * 128 + (c8 * 4 + j) * 4);
+                    a0[qp] = __ffma2_rn(make_float2(f.x, f.y), make_float2(fa.x, fa.x), a0[qp]);
+                    a0[qp] = __ffma2_rn(make_float2(f.z, f.w), make_float2(fa.y, fa.y), a0[qp]);
+                    a1[qp] = __ffma2_rn(make_float2(f.x, f.y), make_float2(fb.x, fb.x), a1[qp]);
+                    a1[qp] = __ffma2_rn(make_float2(f.z, f.w), make_float2(fb.y, fb.y), a1[qp]);
+                }
+            }
+        }
+#pragma unroll
+        for (int qp = 0; qp < NQP; qp++) {
+            p[(2 * qp) * kPS + t] = a0[qp].x;
+            p[(2 * qp + 1) * kPS + t] = a0[qp].y;
+            if (has1) {
+                p[(2 * qp) * kPS + t1] = a1[qp].x;
+                p[(2 * qp + 1) * kPS + t1] = a1[qp].y;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- softmax: warp i = row i ----
+    if (warp < K) {
+        float* pr = p + warp * kPS;
+        float mx = -INFINITY;
+        for (int t = lane; t < kT; t += 32) mx = fmaxf(mx, pr[t]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int t = lane; t < kT; t += 32) {
+            const float e = expf(pr[t] - mx);
+            pr[t] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int t = lane; t < kT; t += 32) pr[t] *= inv;
+    }
+    __syncthreads();
+    // ---- P V: warp = key slice (groups of 4 keys), lane = column pair ----
+    float2 acc[NQ];
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) acc[qi] = make_float2(0.0f, 0.0f);
+    for (int t4 = warp * 4; t4 < kT; t4 += 32) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vb + (int64_t)(t4 + j) * 64 + 2 * lane));
+#pragma unroll
+        for (int qi = 0; qi < NQ; qi++) {
+            const float4 pv = *reinterpret_cast<const float4*>(p + qi * kPS + t4);
+            acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[0], acc[qi]);
+            acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[1], acc[qi]);
+            acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[2], acc[qi]);
+            acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[3], acc[qi]);
+        }
+    }
+    __syncthreads();  // all warps are done reading p
+    float* red = p;   // [8][NQ][64]
+#pragma unroll
+    for (int qi = 0; qi < NQ; qi++) {
+        red[(warp * NQ + qi) * 64 + 2 * lane] = acc[qi].x;
+        red[(warp * NQ + qi) * 64 + 2 * lane + 1] = acc[qi].y;
+    }
+    __syncthreads();
+    for (int e = tid; e < K * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        if (pos >= t_limit[b0 + qi]) continue;
+        float a = 0.0f;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) a += red[(wv * NQ + qi) * 64 + c];
+        store_split(att, lo_off, (int64_t)(b0 + qi) * d + hh * 64 + c, a);
+    }
+}
+
+template <int NQP>
+static cudaError_t launch_cross_rows(int H, int nW, int K, cudaStream_t st, const float* part, int n_splits, int64_t split_stride, const float* b_q,
+                                     const __nv_bfloat16* ckv, int d, __nv_bfloat16* att, int64_t lo_off, int pos, const int32_t* t_limit,
+                                     const int32_t* row_window) {
+    const size_t smem = sizeof(float) * ((size_t)NQP * 128 + (size_t)2 * NQP * (kT + 4));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dec_cross_attn_rows_kernel<NQP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dec_cross_attn_rows_kernel<NQP><<<dim3(H, nW), 256, smem, st>>>(part, n_splits, split_stride, b_q, ckv, d, att, lo_off, pos, t_limit, row_window, K);
+    return cudaGetLastError();
+}
+
 __global__ void dec_bias_gelu_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ bias,
                                      int n, int64_t total, __nv_bfloat16* __restrict__ out, int64_t lo_off) {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -1082,6 +1220,15 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             // registers); 8 (32 registers) spills and is much slower.  A single-pass online-softmax variant that streams K_c and
             // V_c rows together was tried and is slower (2070 ms): its per-iteration max -> exp -> FMA chain keeps fewer loads in
             // flight than the two independent passes do.
+            static const bool no_rows = getenv("WDR_NO_ROWS_KERNEL") != nullptr;  // bring-up aid: one CTA per row even when rows share a window
+            if (beam && ws.beam_K > 1 && B % ws.beam_K == 0 && !pos_on_device && !no_rows) {
+                const int nW = B / ws.beam_K, nqp = (ws.beam_K + 1) / 2;
+                cudaError_t ce;
+#define WDR_ROWS(N) launch_cross_rows<N>(H, nW, ws.beam_K, st, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d, pos, t_limit, ws.beam_rowwin)
+                ce = nqp == 1 ? WDR_ROWS(1) : nqp == 2 ? WDR_ROWS(2) : nqp == 3 ? WDR_ROWS(3) : WDR_ROWS(4);
+#undef WDR_ROWS
+                WDR_CUDA_TRY(ce);
+            } else
             WDR_CUDA_TRY(launch_kernel(beam ? dec_cross_attn_kernel<6, true> : dec_cross_attn_kernel<6, false>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
                                        (int64_t)ws.cap_B * d, capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T, ws.aw_A, pos_ptr, pos,
                                        win, t_limit, beam ? (const int32_t*)ws.beam_rowwin : (const int32_t*)nullptr));

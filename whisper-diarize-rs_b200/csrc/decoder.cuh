@@ -66,6 +66,7 @@ struct DecoderWorkspace {
     int32_t* beam_parent = nullptr;
     float* beam_nosp = nullptr;
     int32_t* beam_rowwin = nullptr;    // [128] row -> window whose cross cache it reads
+    int beam_K = 1;                    // rows per window of the current beam / fallback pass (rows w*K .. w*K+K-1 decode window w of the pass)
     cudaGraphExec_t step_graph = nullptr;  // one greedy iteration (sample, advance, step), see decoder_decode_graph
     int graph_B = 0, graph_nodes = 0;
     SampleParams graph_sp{};

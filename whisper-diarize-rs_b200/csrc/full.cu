@@ -333,6 +333,7 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
     std::vector<int32_t> limit(kDecMaxBatch, 0);
     for (int r = 0; r < R; r++) limit[r] = win[wins[r / K]].completed ? 0 : 1 << 30;
     ws.beam_anc_cur = ws.beam_anc[0];
+    ws.beam_K = K;
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.seq, seq.data(), sizeof(int32_t) * seq.size(), cudaMemcpyHostToDevice, s));
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_anc[0], anc.data(), sizeof(int32_t) * anc.size(), cudaMemcpyHostToDevice, s));
     WDR_CUDA_TRY(cudaMemcpyAsync(ws.beam_limit, limit.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, s));
