@@ -390,7 +390,7 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
 // by one warp per row; P V with warp = key slice, lane = column pair.  NQP = query pairs (rows padded to 2 NQP with zero queries).
 // Rows b = w * K + i; rows with t_limit[b] <= pos are dead: nothing is stored for them; a window with no live row returns at once.
 template <int NQP>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)  // four CTAs per SM: the 500 CTAs of a 25-window beam-5 batch are one wave
 dec_cross_attn_rows_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
                            const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off, int pos,
                            const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window, int K) {
@@ -475,17 +475,24 @@ dec_cross_attn_rows_kernel(const float* __restrict__ part, int n_splits, int64_t
     float2 acc[NQ];
 #pragma unroll
     for (int qi = 0; qi < NQ; qi++) acc[qi] = make_float2(0.0f, 0.0f);
-    for (int t4 = warp * 4; t4 < kT; t4 += 32) {
-        float2 v[4];
+    // eight keys per trip (eight independent 128 B row loads per warp in flight); kT = 1500 = 8 * 187 + 4: the last trip is half
+    for (int t8 = warp * 8; t8 < kT; t8 += 64) {
+        const bool second = t8 + 4 < kT;  // warp-uniform
+        float2 v[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vb + (int64_t)(t4 + j) * 64 + 2 * lane));
+        for (int j = 0; j < 8; j++)
+            v[j] = (j < 4 || second) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vb + (int64_t)(t8 + j) * 64 + 2 * lane)) : make_float2(0.0f, 0.0f);
 #pragma unroll
-        for (int qi = 0; qi < NQ; qi++) {
-            const float4 pv = *reinterpret_cast<const float4*>(p + qi * kPS + t4);
-            acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[0], acc[qi]);
-            acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[1], acc[qi]);
-            acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[2], acc[qi]);
-            acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[3], acc[qi]);
+        for (int g4 = 0; g4 < 2; g4++) {
+            if (g4 == 1 && !second) break;
+#pragma unroll
+            for (int qi = 0; qi < NQ; qi++) {
+                const float4 pv = *reinterpret_cast<const float4*>(p + qi * kPS + t8 + 4 * g4);
+                acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[4 * g4], acc[qi]);
+                acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[4 * g4 + 1], acc[qi]);
+                acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[4 * g4 + 2], acc[qi]);
+                acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[4 * g4 + 3], acc[qi]);
+            }
         }
     }
     __syncthreads();  // all warps are done reading p
