@@ -714,18 +714,27 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
     float2 acc[kDtwpQB];  // packed FFMA2 with the probability broadcast: per column the same fmaf chain as a scalar loop
 #pragma unroll
     for (int qi = 0; qi < kDtwpQB; qi++) acc[qi] = make_float2(0.0f, 0.0f);
-    for (int t4 = warp * 4; t4 < kT; t4 += 32) {
-        float2 v[4];
+    // two of the warp's key groups (t4 and t4 + 32) are loaded per trip and consumed in the same order as before: half as many
+    // dependent load -> FFMA2 round trips, identical arithmetic
+    for (int t4 = warp * 4; t4 < kT; t4 += 64) {
+        const bool second = t4 + 32 < kT;  // warp-uniform
+        float2 v[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++)
-            v[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vb + (int64_t)(t4 + j) * rs + 2 * lane));
+        for (int j = 0; j < 8; j++) {
+            const int t = t4 + (j < 4 ? j : 28 + j);
+            v[j] = (j < 4 || second) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(Vb + (int64_t)t * rs + 2 * lane)) : make_float2(0.0f, 0.0f);
+        }
 #pragma unroll
-        for (int qi = 0; qi < kDtwpQB; qi++) {
-            const float4 pv = *reinterpret_cast<const float4*>(p + qi * kDtwpPStride + t4);
-            acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[0], acc[qi]);
-            acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[1], acc[qi]);
-            acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[2], acc[qi]);
-            acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[3], acc[qi]);
+        for (int g2 = 0; g2 < 2; g2++) {
+            if (g2 == 1 && !second) break;
+#pragma unroll
+            for (int qi = 0; qi < kDtwpQB; qi++) {
+                const float4 pv = *reinterpret_cast<const float4*>(p + qi * kDtwpPStride + t4 + 32 * g2);
+                acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[4 * g2], acc[qi]);
+                acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[4 * g2 + 1], acc[qi]);
+                acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[4 * g2 + 2], acc[qi]);
+                acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[4 * g2 + 3], acc[qi]);
+            }
         }
     }
     __syncthreads();  // all warps are done reading p
