@@ -88,12 +88,20 @@ __device__ __forceinline__ float part_sum(const float* __restrict__ part, int n_
     const float* pp = part + idx;
     float a = pp[0];
     int s = 1;
-    for (; s + 4 <= n_splits; s += 4) {  // four loads in flight, summed in split order
-        const float t0 = pp[(int64_t)s * split_stride], t1 = pp[(int64_t)(s + 1) * split_stride];
-        const float t2 = pp[(int64_t)(s + 2) * split_stride], t3 = pp[(int64_t)(s + 3) * split_stride];
-        a += t0; a += t1; a += t2; a += t3;
+    for (; s + 8 <= n_splits; s += 8) {  // eight loads in flight (one L2 round trip for the usual 7-9 splits), summed in split order
+        float t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = pp[(int64_t)(s + k) * split_stride];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a += t[k];
     }
-    for (; s < n_splits; s++) a += pp[(int64_t)s * split_stride];
+    if (s < n_splits) {  // the tail: still all loads first, then the adds in split order
+        float t[7];
+#pragma unroll
+        for (int k = 0; k < 7; k++) t[k] = (s + k < n_splits) ? pp[(int64_t)(s + k) * split_stride] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 7; k++) if (s + k < n_splits) a += t[k];
+    }
     return a;
 }
 
@@ -138,16 +146,21 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
         const float* pp = part + (int64_t)row * ldp + i;
         float4 acc = *reinterpret_cast<const float4*>(pp);
         int s = 1;
-        for (; s + 4 <= n_splits; s += 4) {  // four loads in flight, summed in split order
-            float4 t[4];
+        for (; s + 8 <= n_splits; s += 8) {  // eight loads in flight, summed in split order
+            float4 t[8];
 #pragma unroll
-            for (int k = 0; k < 4; k++) t[k] = *reinterpret_cast<const float4*>(pp + (int64_t)(s + k) * split_stride);
+            for (int k = 0; k < 8; k++) t[k] = *reinterpret_cast<const float4*>(pp + (int64_t)(s + k) * split_stride);
 #pragma unroll
-            for (int k = 0; k < 4; k++) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
+            for (int k = 0; k < 8; k++) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
         }
-        for (; s < n_splits; s++) {
-            const float4 t = *reinterpret_cast<const float4*>(pp + (int64_t)s * split_stride);
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        if (s < n_splits) {  // the tail (<= 7 splits): all loads first — one L2 round trip —, then the adds in split order
+            float4 t[7];
+#pragma unroll
+            for (int k = 0; k < 7; k++)
+                t[k] = (s + k < n_splits) ? *reinterpret_cast<const float4*>(pp + (int64_t)(s + k) * split_stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 7; k++)
+                if (s + k < n_splits) { acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w; }
         }
         const float4 bs = *reinterpret_cast<const float4*>(bias + i);
         a.x += acc.x + bs.x; a.y += acc.y + bs.y; a.z += acc.z + bs.z; a.w += acc.w + bs.w;
