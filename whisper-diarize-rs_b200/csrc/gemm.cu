@@ -92,15 +92,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int num_kb = (p.K + kBK - 1) / kBK;
     pdl_launch_dependents();
 
+    // The producer thread initialises the operand barriers itself and requests the first item's first STAGES k-blocks at once —
+    // before the TMEM allocation and the block-wide barrier of the prologue, so their latency (tensor-map fetch + HBM / L2) runs
+    // under it; the decode GEMMs are a few microseconds long and one such round trip is a visible share of them.
+    int prefetched = 0;
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
-    }
-    if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(&bar_full[s], 1);
             mbar_init(&bar_empty[s], 1);
         }
+        mbar_fence_init();
+        if (blockIdx.x < p.total_tiles) {
+            const int w = blockIdx.x;
+            const int t = w / p.splits, sp = w - t * p.splits;
+            const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
+            const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
+            const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+            prefetched = min(STAGES, kb1 - kb0);
+            pdl_wait();  // (a no-op unless launched as a programmatic dependent: then A must wait for the predecessor)
+            for (int i = 0; i < prefetched; i++) {
+                const int kb = kb0 + i;
+                mbar_arrive_expect_tx(&bar_full[i], kAStage + kBBytes);
+                const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                tma_load_3d(sA + i * kAStage, &tma_a, &bar_full[i], kcol * kBK, mt * kBM + tap, batch);
+                if (DUAL) tma_load_3d(sA + i * kAStage + kABytes, &tma_a, &bar_full[i], kcol * kBK, mt * kBM + tap, 1);
+                if (p.w_kb_major) tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], 0, kb * p.N + n_tile * BN);
+                else tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], kb * kBK, n_tile * BN);
+            }
+        }
+    }
+    if (warp == 1 && lane == 0) {
         for (int s = 0; s < 2; s++) {
             mbar_init(&bar_tfull[s], 1);
             mbar_init(&bar_tempty[s], 8);
@@ -121,38 +144,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            // The weight operand does not depend on the predecessor kernel: the first item's first STAGES weight tiles are
-            // requested before pdl_wait(), so their HBM latency overlaps the predecessor's tail.
-            int prefetched = 0;
-            if (blockIdx.x < p.total_tiles) {
-                const int w = blockIdx.x;
-                const int t = w / p.splits, sp = w - t * p.splits;
-                const int n_tile = t % p.n_tiles;
-                const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-                prefetched = min(STAGES, kb1 - kb0);
-                for (int i = 0; i < prefetched; i++) {
-                    mbar_arrive_expect_tx(&bar_full[i], kAStage + kBBytes);
-                    if (p.w_kb_major) tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], 0, (kb0 + i) * p.N + n_tile * BN);
-                    else tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], (kb0 + i) * kBK, n_tile * BN);
-                }
-            }
-            pdl_wait();
             for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w - t * p.splits;
                 const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
                 const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; kb++) {
-                    const bool have_b = prefetched > 0;  // this stage's barrier is armed and its weight tile is in flight
-                    if (have_b) prefetched--;
+                    if (prefetched > 0) prefetched--;  // requested in the prologue: this stage is armed and both tiles are in flight
                     else {
                         mbar_wait(&bar_empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&bar_full[s], kAStage + kBBytes);
-                    }
-                    const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
-                    tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
-                    if (DUAL) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
-                    if (!have_b) {
+                        const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                        tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
+                        if (DUAL) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
                         if (p.w_kb_major) tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], 0, kb * p.N + n_tile * BN);
                         else tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
                     }
