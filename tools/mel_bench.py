@@ -28,3 +28,4 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
 alg = B * (480000 * 2 + n_mel * 3000 * 4)
 print(f"log-mel {n_mel} bins, {B} windows: {ms * 1e3:.1f} us  {alg / ms / 1e6:.0f} GB/s (incl. the normalise pass)")
+fe.close()
