@@ -194,7 +194,7 @@ def run_diarize(args):
     import torch
     import torch.distributed as dist
     import wdr_b200 as w
-    from wdr_b200 import host as H
+    from hostmirror import host as H
     if w.device_count() == 0:
         raise SystemExit("bench.py needs a CUDA device: libwdr_b200 has no CPU path")
     torch.cuda.set_device(local)
@@ -346,7 +346,7 @@ def run_pipeline(args):
     import torch
     import torch.distributed as dist
     import wdr_b200 as w
-    from wdr_b200 import host as H
+    from hostmirror import host as H
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

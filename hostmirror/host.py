@@ -4,7 +4,7 @@ build image; in production this logic stays in the crate (reference src/vad.rs, 
 changes (INTEGRATION.md)."""
 import numpy as np
 
-from . import capi
+import wdr_b200 as capi  # the ctypes binding over include/wdr.h (the product boundary)
 
 F = np.float32
 
@@ -39,9 +39,13 @@ def vad_mask_and_merge(segs_cs, int_samples):
         else:
             merged.append([s, e])
     out = []
-    for s, e in merged:                                                              # :66-81 (f32 arithmetic, round half away from zero)
-        si = int(np.clip(np.floor(F(F(s) * SR) + F(0.5)), F(0.0), n_f32))
-        ei = int(np.clip(np.floor(F(F(e) * SR) + F(0.5)), F(0.0), n_f32))
+    def idx(t):  # ((t as f32 * SR).round()).clamp(0.0, n_f32) as usize — f32::round is half away from zero; done in f64, where
+        x = float(F(F(t) * SR))  # x + 0.5 is exact for every f32 x (floor(x + 0.5) in f32 is off by one for odd x above 2^23)
+        r = np.floor(x + 0.5) if x >= 0.0 else -np.floor(-x + 0.5)
+        return int(min(max(r, 0.0), float(n_f32)))
+
+    for s, e in merged:                                                              # :66-81
+        si, ei = idx(s), idx(e)
         seg = int_samples[si:ei] if ei > si else int_samples[:0]
         if e > s and len(seg):
             out.append(dict(start=s, end=e, samples=seg))
@@ -203,7 +207,9 @@ def run_transcription_pipeline(state, speech_segments, params=None, extractor=No
     Returns (segments [dict(start, end, text, words, speaker_id)], detected_lang)."""
     mgr = capi.EmbeddingManager(max_speakers) if extractor is not None else None
     out, previous_text, detected = [], None, None
-    sticky = None  # `params.set_initial_prompt` mutates the params the loop clones: once set, a prompt stays until replaced
+    # `params.set_initial_prompt` mutates the params the loop clones: once set, a prompt stays until replaced — and a prompt the
+    # caller set (advanced.init_prompt, :74-76) stays until the first non-empty segment text replaces it
+    sticky = params.initial_prompt if params is not None and params.initial_prompt else None
     for sp in speech_segments:
         p = params if params is not None else state.full_params()
         p.prompt_tokens = None

@@ -226,13 +226,17 @@ typedef struct wdr_token_data {
 } wdr_token_data;
 enum wdr_sampling_strategy { WDR_SAMPLING_GREEDY = 0, WDR_SAMPLING_BEAM_SEARCH = 1 };
 /* == whisper_full_params, the fields the crate sets (setup_params, src/transcribe.rs:20-87) plus whisper.cpp's defaults
- * for the rest.  Supported decoding: greedy at temperature 0; beam search (beam_size <= 8) with whisper_full's temperature
- * ladder (temperature_inc > 0: failing windows are decoded again at +temperature_inc ... <= 1).  temperature_inc defaults to 0
- * here (whisper.cpp: 0.2) — set it to 0.2 for upstream's default behaviour.  Above temperature 0 the greedy strategy draws
- * every token from std::discrete_distribution with best_of (<= 8) decoders per window, decoder j of a window seeded
- * std::mt19937(j) (upstream's stream runs on across the windows of a call; here every window restarts it, so windows stay
- * independent and shardable).
- * language given or "auto"; single_segment = 1 as the crate always sets (src/transcribe.rs:46).  Strings are borrowed for the call. */
+ * for the rest (wdr_full_default_params == whisper_full_default_params, temperature_inc = 0.2 included).  Supported decoding:
+ * greedy and beam search (beam_size <= 8) with whisper_full's temperature ladder `for (t = temperature; t < 1 + 1e-6;
+ * t += temperature_inc)`: windows whose decode fails whisper_full's success test are decoded again at the next temperature;
+ * `temperature` may start above 0 (the crate forwards advanced.temperature, src/transcribe.rs:58-68).  Above temperature 0
+ * both strategies run max(1, greedy.best_of) (<= 8) decoders per window; the greedy strategy draws every token from
+ * std::discrete_distribution, decoder j of a window seeded std::mt19937(j) (upstream's stream runs on across the windows of a
+ * call; here every window restarts it, so windows stay independent and shardable).  no_speech_prob is always taken from the
+ * raw logits of the prompt decode (before the temperature division), as upstream does.
+ * language given or "auto"; single_segment = 1 as the crate always sets (src/transcribe.rs:46).  Parameters that are not
+ * implemented (offset_ms, duration_ms, max_len, max_tokens, audio_ctx, suppress_nst, no_timestamps, single_segment = 0) are
+ * refused with WDR_ERR_UNSUPPORTED, never silently ignored.  Strings are borrowed for the call. */
 typedef struct wdr_full_params {
     int strategy;            /* enum wdr_sampling_strategy */
     int n_threads;           /* accepted, unused */
@@ -260,7 +264,9 @@ typedef struct wdr_full_params {
     void* abort_callback_user_data;
 } wdr_full_params;
 wdr_full_params wdr_full_default_params(int strategy);                                     /* whisper_full_default_params */
-/* state.full(params, &samples): one buffer of <= 30 s (what the crate submits per SpeechSegment, src/transcribe.rs:376-389).
+/* state.full(params, &samples) on one buffer of any length (what the crate submits per SpeechSegment, src/transcribe.rs:376-389).
+ * n <= 480000: one window.  Longer: whisper_full's sequential seek loop (global mel max, window k+1 starts where window k's last
+ * timestamp says and is prompted with [PREV] + prompt_past; timestamp state carried) — replicas only, it does not shard.
  * 0 = ok; results stay in the state until the next call.  Host pointers. */
 int wdr_full_with_state(wdr_context* ctx, wdr_state* state, wdr_full_params params, const float* pcm, int n);
 int wdr_full_with_state_i16(wdr_context* ctx, wdr_state* state, wdr_full_params params, const int16_t* pcm, int n);
@@ -351,18 +357,20 @@ typedef struct wdr_seg wdr_seg;
 typedef struct wdr_seg_result wdr_seg_result;
 wdr_seg* wdr_seg_init(const char* path /* NULL: seeded weights */, uint64_t seed, int device);
 void wdr_seg_free(wdr_seg* m);
-int wdr_seg_n_windows(int64_t n_samples);                              /* ceil(n / 160000) */
+int wdr_seg_n_windows(int64_t n_samples);                              /* n / 160000 + 1: pyannote-rs pads `window - len % window` zeros, so an exact
+                                                                          multiple of 10 s gets one more (silent) window */
 /* PyanNet over every 10 s window (raw int16 values as f32, zero padded): scores[n_windows][589][7] log-probabilities. Host ptrs.
  * Returns n_windows. */
 int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, float* scores);
 /* get_segments: windows -> scores -> per-frame argmax != 0 state machine (frame 270 samples, first frame at sample 721). */
 wdr_seg_result* wdr_seg_get_segments(wdr_seg* m, const int16_t* pcm, int64_t n);
-/* The state machine alone on caller-supplied scores (host logic; bit-exact given the scores). */
-wdr_seg_result* wdr_seg_segments_from_scores(const float* scores, int n_windows, int64_t n_samples_padded);
+/* The state machine alone on caller-supplied scores (host logic; bit-exact given the scores).  n_samples = the ORIGINAL sample
+ * count: sample ranges are clamped to it (start to n - 1, end to n) as pyannote-rs does, so no segment carries padding zeros. */
+wdr_seg_result* wdr_seg_segments_from_scores(const float* scores, int n_windows, int64_t n_samples);
 int wdr_seg_result_n(wdr_seg_result* r);
 double wdr_seg_result_start(wdr_seg_result* r, int i);                 /* Segment.start, seconds (f64) */
 double wdr_seg_result_end(wdr_seg_result* r, int i);
-int64_t wdr_seg_result_sample_range(wdr_seg_result* r, int i, int64_t* i1);   /* [i0, i1) into the zero-padded input */
+int64_t wdr_seg_result_sample_range(wdr_seg_result* r, int i, int64_t* i1);   /* [i0, i1) into the input (clamped to its length) */
 const int16_t* wdr_seg_result_samples(wdr_seg_result* r, int i, int64_t* count);  /* Segment.samples (owned by the result) */
 void wdr_seg_result_free(wdr_seg_result* r);
 
@@ -397,11 +405,16 @@ int wdr_debug_decoder_read(wdr_state* state, int which, float* out, int64_t coun
  * epilogue: 0 bias->bf16, 1 bias+GELU->bf16, 2 resid+bias->f32 (resid_or_pos = resid[M][ldc]),
  * 3 GELU(bias)+pos->f32 (resid_or_pos = pos[rows_per_batch][N]), 4 QKV (columns >= n_split stored transposed
  * into out_t[n - n_split][batch * t_batch_stride + row_in_batch], row stride ldt; t_batch_stride 0 = rows_per_batch),
- * 5 bias->f32.  DEVICE pointers, asynchronous on stream. */
+ * 5 bias->f32, 9 bias->bf16 stored head-major (the decoder's cross K|V cache: n_split = rows per group g, row = g*n_split + t,
+ * n = s*(N/2) + h*64 + c -> out[((g*H + h)*2 + s)*n_split + t][c]).  DEVICE pointers, asynchronous on stream. */
 int wdr_gemm_bf16_dev(const uint16_t* A, int64_t lda, int rows_per_batch, int n_batch, int64_t a_batch_stride,
                       const uint16_t* W, int64_t ldw, int N, int K, int kb_per_tap, int a_cols, const float* bias,
                       int epilogue, void* out, int64_t ldc, const float* resid_or_pos, uint16_t* out_t, int64_t ldt,
                       int n_split, int64_t t_batch_stride, void* stream);
+
+/* N-tile width (64 / 128 / 256) the last wdr_gemm_bf16_dev call on this thread ran with: parity tests assert that the shapes of the
+ * benchmark configuration really select the 128 x 256 tile. */
+int wdr_gemm_last_tile_n(void);
 
 #ifdef __cplusplus
 }

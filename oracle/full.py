@@ -77,7 +77,7 @@ def beam_decode_window(dec, prompt, seek, seek_end, beam_size=5, delta_min=10, s
     for i, t in enumerate(prompt):
         lg0 = dec.step(int(t), i, want_logits=(i == n_prompt - 1))
     kv0 = dec.get_kv()
-    ls0 = scaled(lg0)
+    ls0 = lg0  # whisper_full reads no_speech_prob from the RAW logits of the prompt decode, before the temperature division
     lp0 = ls0 - (np.log(np.exp((ls0 - ls0.max()).astype(np.float32)).sum(dtype=np.float32)) + ls0.max())
     no_speech_prob = float(np.exp(np.float32(lp0[v["nosp"]])))
 
@@ -203,7 +203,7 @@ def temperature_ladder(temperature_inc, temperature=0.0):
 
 
 def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_min=10, lang_id=0, beam_size=1,
-                temperature_inc=0.0, logprob_thold=-1.0, no_speech_thold=0.6, entropy_thold=2.4):
+                temperature_inc=0.0, logprob_thold=-1.0, no_speech_thold=0.6, entropy_thold=2.4, temperature=0.0, translate=False):
     """dec: native.Decoder; enc_out [1500, d] (encoder output for this window); pcm_f32: the window's samples (<= 480000).
     Returns dict(segments=[dict(t0, t1, text, tokens=[TokenData])], seek_delta, no_speech_prob, margins, ...)."""
     nv = dec.a["n_vocab"]
@@ -213,14 +213,14 @@ def full_window(dec, enc_out, pcm_f32, dtw=True, token_timestamps=True, delta_mi
     if seek_end < seek + delta_min or seek + delta_min >= seek_end:
         return out
     dec.set_audio(enc_out)
-    temps = temperature_ladder(temperature_inc)
-    assert len(temps) == 1 or beam_size > 1, "the ladder is restated for the beam strategy (deterministic: one decoder above T = 0)"
+    temps = temperature_ladder(temperature_inc, temperature)
+    assert (len(temps) == 1 and temps[0] <= 0) or beam_size > 1, "above T = 0 only the beam strategy is restated (deterministic: one decoder)"
     for it, t_cur in enumerate(temps):
         if beam_size > 1:
-            r = beam_decode_window(dec, prompt_tokens(nv, lang_id), seek, seek_end, beam_size, delta_min,
+            r = beam_decode_window(dec, prompt_tokens(nv, lang_id, translate), seek, seek_end, beam_size, delta_min,
                                    n_decoders=beam_size if t_cur <= 0 else 1, temperature=t_cur, entropy_thold=entropy_thold)
         else:
-            r = dec.decode_window(prompt_tokens(nv, lang_id), seek, seek_end, True, delta_min)
+            r = dec.decode_window(prompt_tokens(nv, lang_id, translate), seek, seek_end, True, delta_min)
         r["temperature"] = t_cur
         # "was the decoding successful for the current temperature?" — the last temperature's result stands whatever it is
         if it != len(temps) - 1 and (r["dec_failed"] or r["result_len"] <= 0 or
@@ -300,7 +300,9 @@ def full_sequential(dec, encode, filt, pcm_f32, dtw=True, token_timestamps=True,
         else:
             avg_logprob = sum(float(t.plog) for t in toks) / max(1, r["result_len"]) if r["result_len"] else -np.inf
         is_no_speech = r["no_speech_prob"] > 0.6 and avg_logprob < -1.0
-        new_ids = []
+        # whisper_full appends tokens_cur[0 .. result_len) to prompt_past unless the window is a no-speech window, whether or not a
+        # segment comes out of them
+        new_ids = [] if is_no_speech else [int(t.id) for t in toks[: r["result_len"]]]
         if toks and not is_no_speech:
             seek_delta = r["seek_delta"]
             t0 = seek + 2 * (toks[0].tid - v["beg"])
@@ -318,7 +320,6 @@ def full_sequential(dec, encode, filt, pcm_f32, dtw=True, token_timestamps=True,
                     ti, tj = native.dtw(native.dtw_cost(w, sot_len, 7))
                     toks = native.dtw_stamp(toks, v["eot"], ti, tj, seek)
                 out["segments"].append(dict(t0=t0, t1=t1, text=text, tokens=toks))
-                new_ids = [int(t.id) for t in toks[: r["result_len"]]]
         past = (past[len(past) - n_take:] if n_take else []) + new_ids
         if r["seek_delta"] <= 0:
             break

@@ -124,8 +124,10 @@ def pyannet_forward(window_f32, w):
     return (z - m - np.log(np.exp(z - m).sum(1, keepdims=True))).astype(F)
 
 
-def segments_from_scores(scores, n_samples_padded, sample_rate=16000):
-    """pyannote-rs state machine over consecutive windows' scores [n_windows, 589, 7] -> [(start_s, end_s, start_idx, end_idx)]."""
+def segments_from_scores(scores, n_samples, sample_rate=16000):
+    """pyannote-rs state machine over consecutive windows' scores [n_windows, 589, 7] -> [(start_s, end_s, start_idx, end_idx)].
+    n_samples = the ORIGINAL sample count: upstream computes `start = start_offset / sr`, `start_f64 = start * sr`,
+    `start_idx = start_f64.min((len - 1) as f64) as usize`, `end_idx = end_f64.min(len as f64) as usize` (f64 round trip, truncation)."""
     segs = []
     offset = FRAME_START
     speaking = False
@@ -138,8 +140,10 @@ def segments_from_scores(scores, n_samples_padded, sample_rate=16000):
                     start = offset
                     speaking = True
             elif speaking:
-                s_idx, e_idx = min(start, n_samples_padded), min(offset, n_samples_padded)
-                segs.append((start / sample_rate, offset / sample_rate, s_idx, e_idx))
+                t0, t1 = float(start) / float(sample_rate), float(offset) / float(sample_rate)
+                s_idx = int(min(t0 * float(sample_rate), float(max(n_samples - 1, 0))))
+                e_idx = max(s_idx, int(min(t1 * float(sample_rate), float(n_samples))))
+                segs.append((t0, t1, s_idx, e_idx))
                 speaking = False
             offset += FRAME_SIZE
     return segs
@@ -148,9 +152,9 @@ def segments_from_scores(scores, n_samples_padded, sample_rate=16000):
 def get_segments(int_samples, w):
     """pyannote_rs::get_segments(&samples, 16000, model) (reference src/engine.rs:117-122)."""
     x = np.asarray(int_samples, np.int16)
-    n_win = (len(x) + WINDOW - 1) // WINDOW
+    n_win = len(x) // WINDOW + 1  # padded.extend(vec![0; window_size - (len % window_size)]): a whole extra window on exact multiples
     padded = np.zeros(n_win * WINDOW, np.int16)
     padded[: len(x)] = x
-    scores = np.stack([pyannet_forward(padded[i * WINDOW:(i + 1) * WINDOW].astype(F), w) for i in range(n_win)]) if n_win else np.zeros((0, N_FRAMES, 7), F)
-    segs = segments_from_scores(scores, len(padded))
+    scores = np.stack([pyannet_forward(padded[i * WINDOW:(i + 1) * WINDOW].astype(F), w) for i in range(n_win)])
+    segs = segments_from_scores(scores, len(x))
     return [dict(start=s, end=e, samples=padded[a:b]) for s, e, a, b in segs], scores

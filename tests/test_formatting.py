@@ -1,5 +1,5 @@
 """CPU suite for SURVEY §8f row 1: the formatter that CONSUMES the library's output (reference src/formatting.rs), restated in
-whisper-diarize-rs_b200/formatting.py.
+hostmirror/formatting.py.
 
 * The reference's own unit test (src/formatting.rs:650-670, `basic_split`) restated.
 * The reference's own fixture `segments.json` (written by examples/test.rs through process_segments; committed verbatim as data under
@@ -13,7 +13,7 @@ import importlib
 import json
 import os
 
-F = importlib.import_module("whisper-diarize-rs_b200.formatting")
+F = importlib.import_module("hostmirror.formatting")
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

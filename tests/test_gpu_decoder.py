@@ -139,7 +139,13 @@ def test_unsupported_params_fail_loudly(wdr):
     with pytest.raises(wdr.WdrError):
         st.full(np.zeros(16000, np.int16), st.full_params(temperature_inc=0.2, greedy_best_of=9))  # more decoders per window than the row budget
     with pytest.raises(wdr.WdrError):
-        st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=5, temperature=0.2))  # the ladder starts at 0
+        st.full(np.zeros(16000, np.int16), st.full_params(strategy=1, beam_size=5, temperature=1.5))  # outside [0, 1]
+    for bad in (dict(offset_ms=10), dict(max_len=5), dict(audio_ctx=700), dict(suppress_nst=1)):  # refused, never silently ignored
+        with pytest.raises(wdr.WdrError) as e:
+            st.full(np.zeros(16000, np.int16), st.full_params(**bad))
+        assert e.value.code == -7, bad
+    with pytest.raises(wdr.WdrError):
+        st.full(np.zeros(16000, np.int16), st.full_params(translate=1))  # tiny.en is not multilingual
     with pytest.raises(wdr.WdrError):
         st.full(np.zeros(16000, np.int16), st.full_params(language="xx"))
     with pytest.raises(wdr.WdrError):
@@ -522,5 +528,78 @@ def test_initial_prompt_is_tokenized_like_whisper(wdr, oracle):
     sig = lambda segs: [[(t.id, t.t0, t.t1, t.t_dtw) for t in s["tokens"]] for s in segs]
     assert sig(with_text) == sig(with_ids)
     assert sig(with_text) != sig(plain), "the prompt never reached the decoder"
+    st.close()
+    ctx.close()
+
+
+def test_unsupported_params_are_refused_in_auto_language_mode(wdr):
+    """validate_params: the unsupported-parameter checks run before the language = "auto" early return."""
+    ctx = wdr.Context("tiny", seed=1234)
+    st = ctx.create_state()
+    for bad in (dict(offset_ms=10), dict(duration_ms=10), dict(max_tokens=3), dict(audio_ctx=700), dict(suppress_nst=1)):
+        with pytest.raises(wdr.WdrError) as e:
+            st.full(np.zeros(16000, np.int16), st.full_params(language="auto", **bad))
+        assert e.value.code == -7, bad
+    st.close()
+    ctx.close()
+
+
+def test_default_params_equal_whisper_cpp(wdr):
+    """wdr_full_default_params == whisper_full_default_params: a drop-in host that takes the defaults gets the 0.2 ladder."""
+    L = wdr.load()
+    g, b = L.wdr_full_default_params(0), L.wdr_full_default_params(1)
+    for p in (g, b):
+        assert abs(p.temperature_inc - 0.2) < 1e-7 and p.temperature == 0.0 and abs(p.entropy_thold - 2.4) < 1e-6
+        assert p.logprob_thold == -1.0 and abs(p.no_speech_thold - 0.6) < 1e-6 and p.max_initial_ts == 1.0 and p.length_penalty == -1.0
+        assert p.n_max_text_ctx == 16384 and p.no_context == 1 and p.suppress_blank == 1 and p.single_segment == 0 and p.token_timestamps == 0
+    assert (g.greedy_best_of, g.beam_size) == (5, -1) and (b.greedy_best_of, b.beam_size) == (-1, 5)
+
+
+def test_start_temperature_and_translate_match_oracle(wdr, oracle):
+    """advanced.temperature (reference src/transcribe.rs:58-68: forwarded to set_temperature) starts the ladder above 0: the beam
+    strategy then runs max(1, best_of) = 1 decoder over beam_size candidates on logits / T — deterministic, so tokens, statistics and
+    times must equal the oracle's; no_speech_prob comes from the RAW logits (not divided by T).  whisper_to_english
+    (src/transcribe.rs:54-56): the TRANSLATE task token replaces TRANSCRIBE in the prompt of a multilingual model."""
+    from oracle import weights as W, full
+    arch = "tiny"
+    w = W.whisper_weights(arch, seed=1234)
+    B = 2
+    pcm = np.zeros((B, 480000), np.int16)
+    nv = np.array([480000, 200000], np.int32)
+    for b in range(B):
+        a = synth_audio(2400 + b, nv[b] / 16000.0)
+        pcm[b, : len(a)] = a[: nv[b]]
+    ctx = wdr.Context(arch, seed=1234, enable_dtw=True)
+    st = ctx.create_state()
+    hid = st.encode_chunks(pcm, nv)
+    dec = oracle.Decoder(arch, W.pack_decoder(arch, w), bf16=True)
+    cases = [dict(lib=dict(strategy=1, beam_size=5, temperature=0.4, language="de"), ora=dict(beam_size=5, temperature=0.4, lang_id=wdr.lang_id("de"))),
+             dict(lib=dict(translate=1, language="de"), ora=dict(translate=True, lang_id=wdr.lang_id("de"))),
+             dict(lib=dict(strategy=1, beam_size=5, translate=1, language="fr"), ora=dict(beam_size=5, translate=True, lang_id=wdr.lang_id("fr")))]
+    plain = {s["chunk"]: [t.id for t in s["tokens"]] for s in st.full_batch(pcm, nv, st.full_params(language="de"))}
+    n_seg = 0
+    for case in cases:
+        segs = {s["chunk"]: s for s in st.full_batch(pcm, nv, st.full_params(**case["lib"]))}
+        for b in range(B):
+            x = pcm[b, : nv[b]].astype(np.float32) / np.float32(32768.0)
+            ref = full.full_window(dec, hid[b], x, **case["ora"])
+            info = st.chunk_info(b)
+            got = segs.get(b)
+            assert (got is not None) == bool(ref["segments"]), (case, b)
+            assert abs(info["no_speech_prob"] - ref["no_speech_prob"]) <= 1e-3 * ref["no_speech_prob"] + 1e-9, (case, b)
+            assert abs(info["temperature"] - case["ora"].get("temperature", 0.0)) < 1e-6
+            if got is None:
+                continue
+            n_seg += 1
+            r = ref["segments"][0]
+            assert [t.id for t in got["tokens"]] == [t.id for t in r["tokens"]], (case, b)
+            assert (got["t0"], got["t1"], got["text"]) == (r["t0"], r["t1"], r["text"])
+            for tg, tr in zip(got["tokens"], r["tokens"]):
+                assert tg.tid == tr.tid and abs(tg.p - tr.p) <= 1e-3 * tr.p + 1e-9 and abs(tg.plog - tr.plog) <= 2e-3
+                assert (tg.t0, tg.t1, tg.t_dtw) == (tr.t0, tr.t1, tr.t_dtw), (case, b, tg.id)
+        if "translate" in case["lib"] and case["lib"].get("strategy", 0) == 0:
+            assert any(segs[b]["tokens"] and [t.id for t in segs[b]["tokens"]] != plain.get(b) for b in segs), "the TRANSLATE token never reached the decoder"
+    assert n_seg >= 4
+    dec.close()
     st.close()
     ctx.close()

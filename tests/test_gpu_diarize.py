@@ -1,5 +1,5 @@
 """GPU suite for the diarize flow around the boundary (reference src/engine.rs:117-122, src/transcribe.rs:461-497) as mirrored by
-whisper-diarize-rs_b200.host.diarize: get_segments -> embeddings -> speaker ids.
+hostmirror.host.diarize: get_segments -> embeddings -> speaker ids.
 
 Bit-exact checks: the labels are the oracle's leader scan (strict >, cap -> best match) / agglomerative clustering applied to the
 library's own similarity matrix; short segments (< one fbank frame) get "?".  Floating point: the similarity matrix agrees with the
@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 def test_diarize_flow(wdr, oracle):
     from oracle import cluster as K, resnet
-    from wdr_b200 import host as H
+    from hostmirror import host as H
     pcm = synth_audio(61, 35.0, n_speakers=3)
     seg = wdr.Segmenter(seed=1234)
     ex = wdr.EmbeddingExtractor(seed=1234)

@@ -91,3 +91,85 @@ def test_gemm_conv_tap_mode(wdr):
     ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), b, stride=2, padding=1).transpose(1, 2)
     ref = gelu_tanh(ref).reshape(B * rows, N)
     assert (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+
+
+# ---- the 128 x 256 tile (gemm.cu: picked when N % 256 == 0 and the grid has >= 2 waves): it carries essentially all of the encoder /
+# cross-KV time of the benchmark configuration (large-v3: d = 1280, 4d = 5120, 3d = 3840, 2d = 2560), so every one of its six
+# epilogues is checked at those widths against fp32 torch, and the test asserts that the wide tile really ran.
+BIG_M = 9600  # 75 row tiles: x (N / 256) >= 296 tiles for every N below
+
+
+def _operands(M, N, K, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).bfloat16()
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.03).bfloat16()
+    b = torch.randn(N, device="cuda", generator=g) * 0.1
+    return g, A, W, b
+
+
+@pytest.mark.parametrize("N,K", [(1280, 1280), (5120, 1280), (1280, 5120)])
+def test_gemm_wide_tile_bias_gelu_resid(wdr, N, K):
+    g, A, W, b = _operands(BIG_M, N, K, N + K)
+    L = wdr.load()
+    ref = A.float() @ W.float().T + b
+    out, _ = run(wdr, A, W, 0, b)
+    assert L.wdr_gemm_last_tile_n() == 256
+    assert torch.isfinite(out.float()).all() and (out.float() - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    out, _ = run(wdr, A, W, 1, b)
+    assert L.wdr_gemm_last_tile_n() == 256
+    rg = gelu_tanh(ref)
+    assert (out.float() - rg).abs().max().item() <= 1e-2 * rg.abs().max().item() + 1e-3
+    resid = torch.randn(BIG_M, N, device="cuda", generator=g)
+    out32, _ = run(wdr, A, W, 2, b, extra=resid, out_dtype=torch.float32)
+    assert L.wdr_gemm_last_tile_n() == 256
+    r2 = resid + ref
+    assert (out32 - r2).abs().max().item() <= 1e-4 * r2.abs().max().item() + 1e-5
+
+
+def test_gemm_wide_tile_qkv_and_heads_and_conv_pos(wdr):
+    L = wdr.load()
+    d = 1280
+    # fused QKV with transposed V (encoder blocks): 8 windows x 1500 rows, V columns at batch stride 1504
+    B, R = 8, 1500
+    g, A, W, b = _operands(B * R, 3 * d, d, 5)
+    ldt = B * 1504
+    N = 3 * d
+    out = torch.full((B * R, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    out_t = torch.zeros(d, ldt, dtype=torch.bfloat16, device="cuda")
+    wdr.gemm_bf16_dev(A.data_ptr(), d, R, B, R * d, W.data_ptr(), d, N, d, out.data_ptr(), N, 4, b.data_ptr(), None, out_t.data_ptr(), ldt, 2 * d, 0, 0, 1504,
+                      torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert L.wdr_gemm_last_tile_n() == 256
+    ref = A.float() @ W.float().T + b
+    tol = 1e-2 * ref.abs().max().item() + 1e-3
+    assert (out[:, : 2 * d].float() - ref[:, : 2 * d]).abs().max().item() <= tol
+    vt = out_t.view(d, B, 1504)[:, :, :R].float()                     # [c][batch][t]
+    assert (vt - ref[:, 2 * d:].view(B, R, d).permute(2, 0, 1)).abs().max().item() <= tol
+    # head-major cross K|V store (decoder_cross_kv): [(window, head)][K|V][1500][64]
+    g, A, W, b = _operands(B * R, 2 * d, d, 6)
+    H = d // 64
+    out = torch.full((B * H * 2 * R, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    wdr.gemm_bf16_dev(A.data_ptr(), d, B * R, 1, 0, W.data_ptr(), d, 2 * d, d, out.data_ptr(), 2 * d, 9, b.data_ptr(), None, None, 0, R, 0, 0, 0,
+                      torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert L.wdr_gemm_last_tile_n() == 256
+    ref = (A.float() @ W.float().T + b).view(B, R, 2, H, 64).permute(0, 3, 2, 1, 4)   # [window][head][K|V][t][c]
+    got = out.view(B, H, 2, R, 64).float()
+    assert torch.isfinite(got).all() and (got - ref).abs().max().item() <= 1e-2 * ref.abs().max().item() + 1e-3
+    # conv2 of the stem (implicit GEMM over row pairs, 3 taps) + GELU + sinusoids, fp32 out
+    Bc, C, T = 8, d, 3000
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = (torch.randn(Bc, T, C, device="cuda", generator=g) * 0.5).bfloat16()
+    w = (torch.randn(d, C, 3, device="cuda", generator=g) * 0.02).bfloat16()
+    b = torch.randn(d, device="cuda", generator=g) * 0.1
+    P = torch.zeros(Bc, T + 2, C, device="cuda", dtype=torch.bfloat16)
+    P[:, 1: T + 1] = x
+    Wk = w.permute(0, 2, 1).contiguous().view(d, 3 * C)
+    rows = T // 2
+    pos = torch.randn(rows, d, device="cuda", generator=g)
+    out3, _ = run(wdr, P.view(Bc * (T + 2) // 2, 2 * C), Wk, 3, b, extra=pos, rows_per_batch=rows, n_batch=Bc, a_batch_stride=(T + 2) * C,
+                  K=3 * C, lda=2 * C, kb_per_tap=2 * C // 64, a_cols=2 * C, M_out=Bc * rows, out_dtype=torch.float32)
+    assert L.wdr_gemm_last_tile_n() == 256
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), b, stride=2, padding=1).transpose(1, 2)
+    ref = gelu_tanh(ref) + pos
+    assert (out3.view(Bc, rows, d) - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-4

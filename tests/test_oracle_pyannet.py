@@ -43,11 +43,23 @@ def test_state_machine_kat_and_library(wdr):
     cls[580:600] = 1      # runs across the window boundary: offsets are absolute
     cls[1170:] = 2        # still speaking at the end: never closed, never emitted
     scores = _scores_from_classes(cls).reshape(2, 589, 7)
-    ref = P.segments_from_scores(scores, 2 * P.WINDOW)
-    assert [(a, b) for _, _, a, b in ref] == [(721 + 2700, 721 + 8100), (721 + 580 * 270, 721 + 600 * 270)]
+    n = 2 * P.WINDOW - 7
+    ref = P.segments_from_scores(scores, n)
+    # upstream's f64 seconds round trip (offset / sr * sr, truncated) may land one sample below the integer offset
+    for (_, _, a, b), (ea, eb) in zip(ref, [(721 + 2700, 721 + 8100), (721 + 580 * 270, 721 + 600 * 270)]):
+        assert ea - 1 <= a <= ea and eb - 1 <= b <= eb
+        assert a == int(ea / 16000.0 * 16000.0) and b == int(eb / 16000.0 * 16000.0)
     assert ref[0][0] == (721 + 2700) / 16000 and ref[0][1] == (721 + 8100) / 16000
-    got = wdr.seg_segments_from_scores(scores, 2 * P.WINDOW)
+    got = wdr.seg_segments_from_scores(scores, n)
     assert [(g["start"], g["end"], g["i0"], g["i1"]) for g in got] == ref
+    # sample ranges are clamped to the ORIGINAL length (start to n - 1, end to n): a short input cuts the second segment
+    n_short = 721 + 590 * 270
+    ref = P.segments_from_scores(scores, n_short)
+    got = wdr.seg_segments_from_scores(scores, n_short)
+    assert [(g["start"], g["end"], g["i0"], g["i1"]) for g in got] == ref and ref[1][3] == n_short and ref[1][1] * 16000 > n_short
+    ref = P.segments_from_scores(scores, 1000)   # everything beyond the input: start clamps to n - 1, end to n
+    got = wdr.seg_segments_from_scores(scores, 1000)
+    assert [(g["start"], g["end"], g["i0"], g["i1"]) for g in got] == ref and [(a, b) for _, _, a, b in ref] == [(999, 1000), (999, 1000)]
     # ties: argmax takes the FIRST maximum (class 0 wins a 0-vs-k tie => silence)
     tie = np.zeros((1, 589, 7), np.float32)
     assert wdr.seg_segments_from_scores(tie, P.WINDOW) == [] == P.segments_from_scores(tie, P.WINDOW)

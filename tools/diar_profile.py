@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 import wdr_b200 as w
-from wdr_b200 import host as H
+from hostmirror import host as H
 from conftest import synth_audio
 pcm = synth_audio(4001, 600.0, n_speakers=4)
 seg = w.Segmenter(seed=1234); emb = w.EmbeddingExtractor(seed=1234)

@@ -20,4 +20,3 @@ from .capi import (  # noqa: F401
     EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
 )
 from . import dist  # noqa: F401,E402
-from . import host  # noqa: F401,E402  (host-side mirror of the reference's own Rust logic around the boundary)

@@ -190,6 +190,8 @@ def load():
     L.wdr_seg_init.restype = C.c_void_p
     L.wdr_seg_init.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
     L.wdr_seg_free.argtypes = [C.c_void_p]
+    L.wdr_gemm_last_tile_n.restype = C.c_int
+    L.wdr_gemm_last_tile_n.argtypes = []
     L.wdr_seg_n_windows.argtypes = [C.c_int64]
     L.wdr_seg_scores_i16.argtypes = [C.c_void_p, i16p, C.c_int64, f32p]
     L.wdr_seg_get_segments.restype = C.c_void_p
@@ -535,9 +537,13 @@ class State:
         return {n: {"ms": ms[i], "records": ln[i]} for i, n in enumerate(names)}
 
     # ---- full transcription (state.full, reference src/transcribe.rs:389; accessors :393-412, :252-282) ----
-    def full_params(self, strategy=0, **kw):
-        """FullParams as setup_params builds them (src/transcribe.rs:20-87): suppress_blank, token_timestamps, single_segment."""
+    def full_params(self, strategy=0, temperature_inc=0.0, **kw):
+        """FullParams as setup_params builds them (src/transcribe.rs:20-87): suppress_blank, token_timestamps, single_segment.
+        wdr_full_default_params returns whisper.cpp's temperature_inc = 0.2 (what the crate runs with); THIS helper defaults to 0 (no
+        fallback ladder) because a random-init model fails the log-probability test on every window — pass temperature_inc=0.2 for
+        the crate's default behaviour."""
         p = load().wdr_full_default_params(strategy)
+        p.temperature_inc = temperature_inc
         p.print_special = 0
         p.print_progress = 1
         p.print_realtime = 0

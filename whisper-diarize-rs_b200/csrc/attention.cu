@@ -327,11 +327,8 @@ int encoder_attention(const __nv_bfloat16* qk, const __nv_bfloat16* vt, int64_t 
         int rc = make_tmap_bf16(&tvt, vt, 2, dims, str, box);
         if (rc != WDR_OK) return rc;
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        WDR_CUDA_TRY(cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem));
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    WDR_CUDA_TRY(per_device_once(attr_once, [] { return cudaFuncSetAttribute(encoder_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem); }));
     AttParams p;
     p.T = T;
     p.T_pad = T_pad;

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
+#include <mutex>
 #include "../../include/wdr.h"
 
 namespace wdr {
@@ -109,6 +110,24 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
     cfg.attrs = at;
     cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
+// Function attributes (cudaFuncSetAttribute) and device properties belong to ONE device: a process that opens contexts on several
+// devices (wdr_context_params.gpu_device) must set them on each.  f() runs once per (call site, current device).
+struct DeviceOnce {
+    std::mutex mu;
+    uint64_t done = 0;
+};
+template <typename F>
+inline cudaError_t per_device_once(DeviceOnce& o, F f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    std::lock_guard<std::mutex> lk(o.mu);
+    if (o.done & bit) return cudaSuccess;
+    const cudaError_t e = f();
+    if (e == cudaSuccess) o.done |= bit;
+    return e;
 }
 
 }  // namespace wdr

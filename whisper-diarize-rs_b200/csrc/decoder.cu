@@ -531,11 +531,10 @@ static cudaError_t launch_cross_rows(int H, int nW, int K, cudaStream_t st, cons
                                      const __nv_bfloat16* ckv, int d, __nv_bfloat16* att, int64_t lo_off, int pos, const int32_t* t_limit,
                                      const int32_t* row_window) {
     const size_t smem = sizeof(float) * ((size_t)NQP * 128 + (size_t)2 * NQP * (kT + 4));
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(dec_cross_attn_rows_kernel<NQP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    static DeviceOnce attr_once;
+    {
+        const cudaError_t e = per_device_once(attr_once, [&] { return cudaFuncSetAttribute(dec_cross_attn_rows_kernel<NQP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     dec_cross_attn_rows_kernel<NQP><<<dim3(H, nW), 256, smem, st>>>(part, n_splits, split_stride, b_q, ckv, d, att, lo_off, pos, t_limit, row_window, K);
     return cudaGetLastError();
@@ -941,8 +940,9 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
     for (int k = 0; k < kSampPer; k++) {
         const int i = tid + k * kSampThreads;
         v[k] = (i < n) ? lg[i] : -INFINITY;
-        if (temperature > 0.0f) v[k] = __fdiv_rn(v[k], temperature);  // whisper_process_logits: logits[i] /= temperature, first of all
     }
+    // no_speech_prob: whisper_full takes it once, from the RAW logits after the prompt decode ("this has to be done before any logit
+    // filtering") — before whisper_process_logits divides by the temperature
     if (is_initial) {
         float m = -INFINITY;
 #pragma unroll
@@ -952,7 +952,11 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
 #pragma unroll
         for (int k = 0; k < kSampPer; k++) if (v[k] > -INFINITY) s += expf(v[k] - m);
         s = block_sum(s, red);
-        if (tid == 0) no_speech[b] = expf((temperature > 0.0f ? __fdiv_rn(lg[sp.nosp], temperature) : lg[sp.nosp]) - (logf(s) + m));
+        if (tid == 0) no_speech[b] = expf(lg[sp.nosp] - (logf(s) + m));
+    }
+    if (temperature > 0.0f) {  // whisper_process_logits: logits[i] /= temperature, first of all
+#pragma unroll
+        for (int k = 0; k < kSampPer; k++) v[k] = __fdiv_rn(v[k], temperature);
     }
     const int ts_floor = st.has_ts ? sp.beg + st.seek_delta / 2 : sp.beg;
 #pragma unroll
@@ -1352,14 +1356,13 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
     WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_pos, row_pos.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
     WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_off, row_off.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, st));
     WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors die with this frame
-    static bool attr_done = false;
+    static DeviceOnce attr_once;
     const int smem_self = (int)sizeof(float) * (2 * kDtwpMaxT * 65 + 8 * 64 + 8 * kDtwpMaxT);
     const int smem_cross = (int)sizeof(float) * (kDtwpQB * 64 + kDtwpQB * kDtwpPStride);
-    if (!attr_done) {
-        WDR_CUDA_TRY(cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self));
-        WDR_CUDA_TRY(cudaFuncSetAttribute(dtwp_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross));
-        attr_done = true;
-    }
+    WDR_CUDA_TRY(per_device_once(attr_once, [&] {
+        const cudaError_t e = cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self);
+        return e != cudaSuccess ? e : cudaFuncSetAttribute(dtwp_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross);
+    }));
     int L_run = 0;
     for (auto& lh : ctx->aheads) L_run = std::max(L_run, lh.first + 1);
     L_run = std::min(L_run, a.n_dec_layer);

@@ -270,7 +270,7 @@ dtw_wavefront_kernel(const float* __restrict__ xbase, const DtwWindow* __restric
     if (threadIdx.x == 0) path_len[blockIdx.x] = L;
 }
 
-static int g_dtw_smem_max = -1;
+static int g_dtw_smem_by_dev[64];  // 0 = not yet queried on that device (the opt-in limit and the attribute are per device)
 
 // Runs DTW over the windows.  x / outputs are device pointers; `wins` (host) describes the layout.
 // A window keeps its packed trace in shared memory when diagonals + trace words fit (tr_off = -1),
@@ -279,9 +279,11 @@ int dtw_run(const float* x, std::vector<DtwWindow>& wins, int32_t* text_idx, int
             int max_path, float* cost_out, int32_t* trace_out, cudaStream_t st, void* wins_scratch_dev) {
     const int n = (int)wins.size();
     if (n == 0) return WDR_OK;
-    if (g_dtw_smem_max < 0) {
-        int dev = 0, v = 0;
-        WDR_CUDA_TRY(cudaGetDevice(&dev));
+    int dev_cur = 0;
+    WDR_CUDA_TRY(cudaGetDevice(&dev_cur));
+    int& g_dtw_smem_max = g_dtw_smem_by_dev[dev_cur & 63];
+    if (g_dtw_smem_max <= 0) {
+        int dev = dev_cur, v = 0;
         WDR_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         cudaFuncAttributes fa;
         WDR_CUDA_TRY(cudaFuncGetAttributes(&fa, dtw_wavefront_kernel));

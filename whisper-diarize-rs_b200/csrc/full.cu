@@ -204,18 +204,20 @@ static SampleParams make_sample_params(const Vocab& v, const wdr_full_params& p)
 
 static int validate_params(const wdr_context* ctx, const wdr_full_params& p, int* lang_id) {
     if (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > kBeamMax) { set_error("beam_size %d exceeds the supported maximum of %d", p.beam_size, kBeamMax); return WDR_ERR_UNSUPPORTED; }
-    if (p.temperature != 0.0f) { set_error("the temperature ladder must start at 0 (temperature %g)", p.temperature); return WDR_ERR_UNSUPPORTED; }
+    // the crate forwards advanced.temperature (src/transcribe.rs:58-68): the ladder may start anywhere in [0, 1]
+    if (!(p.temperature >= 0.0f) || p.temperature > 1.0f) { set_error("temperature %g outside [0, 1]", p.temperature); return WDR_ERR_INVALID; }
     if (p.temperature_inc < 0.0f) { set_error("temperature_inc must be >= 0"); return WDR_ERR_INVALID; }
-    if (p.temperature_inc > 0.0f && p.greedy_best_of > kBeamMax) { set_error("best_of %d exceeds the supported maximum of %d", p.greedy_best_of, kBeamMax); return WDR_ERR_UNSUPPORTED; }
+    if ((p.temperature_inc > 0.0f || p.temperature > 0.0f) && p.greedy_best_of > kBeamMax) { set_error("best_of %d exceeds the supported maximum of %d", p.greedy_best_of, kBeamMax); return WDR_ERR_UNSUPPORTED; }
     if (!p.single_segment) { set_error("single_segment = 0 is not implemented (the crate always sets it, src/transcribe.rs:46)"); return WDR_ERR_UNSUPPORTED; }
     if (p.no_timestamps) { set_error("no_timestamps = 1 is not implemented"); return WDR_ERR_UNSUPPORTED; }
+    // parameters that are not implemented are refused, never silently ignored — whatever the language mode
+    if (p.offset_ms || p.duration_ms || p.max_len || p.max_tokens || p.audio_ctx || p.suppress_nst) { set_error("offset/duration/max_len/max_tokens/audio_ctx/suppress_nst are not implemented"); return WDR_ERR_UNSUPPORTED; }
+    if (p.translate && !ctx->arch.multilingual) { set_error("translate needs a multilingual model"); return WDR_ERR_INVALID; }
     if (p.detect_language || (p.language && strcmp(p.language, "auto") == 0)) {  // whisper_lang_auto_detect: decided per buffer on the device
         if (!ctx->arch.multilingual) { set_error("language auto-detection needs a multilingual model (whisper_lang_auto_detect fails the same way)"); return WDR_ERR_INVALID; }
         *lang_id = -1;
         return WDR_OK;
     }
-    if (p.offset_ms || p.duration_ms || p.max_len || p.max_tokens || p.audio_ctx || p.suppress_nst) { set_error("offset/duration/max_len/max_tokens/audio_ctx/suppress_nst are not implemented"); return WDR_ERR_UNSUPPORTED; }
-    if (p.translate && !ctx->arch.multilingual) { set_error("translate needs a multilingual model"); return WDR_ERR_INVALID; }
     int id = lang_id_from_str(p.language ? p.language : "en");
     if (id < 0) { set_error("unknown language '%s'", p.language); return WDR_ERR_INVALID; }
     *lang_id = id;
@@ -503,6 +505,7 @@ struct SeqWindow {
     int n_samples;
     int64_t* st3;                 // t_beg, t_last, tid_last carried across the call's segments
     const std::vector<int32_t>* prompt_past;
+    std::vector<int32_t>* result_ids;  // out: tokens_cur[0 .. result_len) of the window unless it is a no-speech window (what whisper_full appends to prompt_past)
 };
 
 // One group of B <= 128 windows whose PCM is already on the device (In = int16_t or float).  sw != nullptr: B == 1 and the
@@ -519,7 +522,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     const int beam_K = (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1;  // rows per window of the decode batch
     WDR_REQUIRE(B * beam_K <= kDecMaxBatch, "windows x beams exceeds the 128-row decode batch");
     const int fb_Kd = std::max(1, p.greedy_best_of);  // decoders per window of a fallback pass (temperature > 0)
-    const int fb_rows = p.temperature_inc > 0.0f ? std::min(B, kDecMaxBatch / fb_Kd) * fb_Kd : 0;
+    const int fb_rows = (p.temperature_inc > 0.0f || p.temperature > 0.0f) ? std::min(B, kDecMaxBatch / fb_Kd) * fb_Kd : 0;
     if ((rc = ws.reserve(ctx, std::max(std::max(B * beam_K, B), fb_rows))) != WDR_OK) return rc;
     // ---- n_valid on the device ----
     if ((rc = grow_dev(&fs.nvalid_dev, &fs.nvalid_cap, (size_t)B)) != WDR_OK) return rc;
@@ -642,7 +645,36 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     std::vector<char> dec_failed(B, 0);       // the best decoder counts as failed (bookkeeping failure or the entropy test)
     std::vector<float> final_temp(B, temps[0]);
     bool results_on_host = false;
-    if (beam_K > 1 && n_skip < B) {
+    // One pass of the ladder above temperature 0 over the windows `list`: max(1, greedy.best_of) decoders per window (both strategies),
+    // the beam strategy ranks beam_size candidates per decoder, the greedy strategy draws (whisper_sample_token, best = false).
+    const int ladder_Kd = std::max(1, p.greedy_best_of);
+    auto ladder_pass = [&](const std::vector<int>& list, size_t it) -> int {
+        prompt = build_prompt(temps[it] < 0.5f);
+        n_prompt = (int)prompt.size();
+        fill_seq();
+        const int per_pass = kDecMaxBatch / ladder_Kd;
+        for (size_t o = 0; o < list.size(); o += per_pass) {
+            std::vector<int> sub(list.begin() + o, list.begin() + std::min(list.size(), o + per_pass));
+            for (int b : sub) {
+                win[b] = win0[b];
+                final_temp[b] = temps[it];
+                memset(&toks[(size_t)b * kDecMaxTokens], 0, sizeof(wdr_token_data) * kDecMaxTokens);
+            }
+            int steps_pass = 0;
+            const int Kc = p.strategy == WDR_SAMPLING_BEAM_SEARCH ? std::max(1, p.beam_size) : 0;  // greedy strategy: every decoder draws (sampling)
+            int rc2 = beam_decode(ctx, st, ws, p, sp, v, sub, ladder_Kd, Kc, temps[it], n_prompt, seq, win, toks, dec_failed, &steps_pass);
+            if (rc2 != WDR_OK) return rc2;
+            steps_run += steps_pass;
+        }
+        return WDR_OK;
+    };
+    if (temps[0] > 0.0f && n_skip < B) {  // the crate's advanced.temperature: the ladder starts above 0, every window is decoded the way a fallback pass is
+        std::vector<int> all;
+        for (int b = 0; b < B; b++)
+            if (!win0[b].completed) all.push_back(b);
+        if ((rc = ladder_pass(all, 0)) != WDR_OK) return rc;
+        results_on_host = true;
+    } else if (beam_K > 1 && n_skip < B) {
         std::vector<int> all;
         for (int b = 0; b < B; b++) all.push_back(b);
         if ((rc = beam_decode(ctx, st, ws, p, sp, v, all, beam_K, beam_K, temps[0], n_prompt, seq, win, toks, dec_failed, &steps_run)) != WDR_OK) return rc;
@@ -710,24 +742,8 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         std::vector<int> fb;
         for (int b = 0; b < B; b++)
             if (!win0[b].completed && unsuccessful(b)) fb.push_back(b);
-        const int Kd = std::max(1, p.greedy_best_of);
         for (size_t it = 1; it < temps.size() && !fb.empty(); it++) {
-            prompt = build_prompt(temps[it] < 0.5f);
-            n_prompt = (int)prompt.size();
-            fill_seq();
-            const int per_pass = kDecMaxBatch / Kd;
-            for (size_t o = 0; o < fb.size(); o += per_pass) {
-                std::vector<int> sub(fb.begin() + o, fb.begin() + std::min(fb.size(), o + per_pass));
-                for (int b : sub) {
-                    win[b] = win0[b];
-                    final_temp[b] = temps[it];
-                    memset(&toks[(size_t)b * kDecMaxTokens], 0, sizeof(wdr_token_data) * kDecMaxTokens);
-                }
-                int steps_pass = 0;
-                const int Kc = p.strategy == WDR_SAMPLING_BEAM_SEARCH ? std::max(1, p.beam_size) : 0;  // greedy strategy: every decoder draws (sampling)
-                if ((rc = beam_decode(ctx, st, ws, p, sp, v, sub, Kd, Kc, temps[it], n_prompt, seq, win, toks, dec_failed, &steps_pass)) != WDR_OK) return rc;
-                steps_run += steps_pass;
-            }
+            if ((rc = ladder_pass(fb, it)) != WDR_OK) return rc;
             if (it + 1 == temps.size()) break;
             std::vector<int> still;
             for (int b : fb)
@@ -788,6 +804,11 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
             avg_logprob = sum / w.result_len;
         }
         const bool is_no_speech = w.no_speech_prob > p.no_speech_thold && avg_logprob < p.logprob_thold;
+        if (sw && sw->result_ids) {
+            sw->result_ids->clear();
+            if (!is_no_speech)
+                for (int i = 0; i < w.result_len && i < (int)cur.size(); i++) sw->result_ids->push_back(cur[i].id);
+        }
         if (!cur.empty() && !is_no_speech) {
             const int seek = w.seek;
             const int64_t t0 = seek + 2 * (cur.front().tid - v.beg);
@@ -993,24 +1014,23 @@ static int full_sequential(wdr_context* ctx, wdr_state* st, const wdr_full_param
         SeqWindow sw;
         sw.mel_dev = d_mel.p; sw.n_len = n_len; sw.max_dev = d_max.p; sw.seek = seek; sw.seek_end = seek_end;
         sw.energy_host = energy.empty() ? nullptr : energy.data(); sw.n_samples = n; sw.st3 = st3; sw.prompt_past = &prompt_past;
-        const size_t n_res0 = st->results.size();
+        std::vector<int32_t> result_ids;
+        sw.result_ids = &result_ids;
         rc = full_group<In>(ctx, st, p, lang_id, nullptr, 0, nullptr, 0, 1, &sw);
         if (rc != WDR_OK) return rc;
         const ChunkInfo& ci = st->chunk_info.back();
         if (lang_id < 0) lang_id = ci.lang_id;  // whisper_full detects once, on the first window
         if (p.detect_language) return WDR_OK;
-        // prompt_past <- the part of it that went into this window's prompt + the window's result tokens (whisper_full)
+        // whisper_full: prompt_past.clear(); if the winning prompt began with [PREV] (it does only below temperature 0.5) the part
+        // of the old past that went into it is kept; then tokens_cur[0 .. result_len) are appended unless the window is a
+        // no-speech window — whether or not a segment came out of them
         {
             std::vector<int32_t> next;
-            if (!prompt_past.empty() && p.n_max_text_ctx > 0) {
+            if (!prompt_past.empty() && p.n_max_text_ctx > 0 && ci.temperature < 0.5f) {
                 const int n_take = std::min(std::min(p.n_max_text_ctx, WDR_TEXT_CTX / 2), (int)prompt_past.size());
                 next.assign(prompt_past.end() - n_take, prompt_past.end());
             }
-            if (st->results.size() > n_res0) {
-                const ResultSegment& seg = st->results.back();
-                const int n_keep = std::min((int)seg.tokens.size(), ci.result_len);
-                for (int i = 0; i < n_keep; i++) next.push_back(seg.tokens[i].id);
-            }
+            next.insert(next.end(), result_ids.begin(), result_ids.end());
             prompt_past.swap(next);
         }
         if (p.progress_callback) p.progress_callback(ctx, st, (int)std::min<int64_t>(100, 100ll * (seek + ci.seek_delta) / std::max(1, seek_end)), p.progress_callback_user_data);
@@ -1187,7 +1207,7 @@ extern "C" wdr_full_params wdr_full_default_params(int strategy) {
     p.temperature = 0.0f;
     p.max_initial_ts = 1.0f;
     p.length_penalty = -1.0f;
-    p.temperature_inc = 0.0f;  // whisper.cpp: 0.2; the ladder is implemented, callers opt in (include/wdr.h)
+    p.temperature_inc = 0.2f;  // == whisper_full_default_params: a host that takes the defaults gets the fallback ladder
     p.entropy_thold = 2.4f;
     p.logprob_thold = -1.0f;
     p.no_speech_thold = 0.6f;

@@ -383,25 +383,28 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t*
     return WDR_OK;
 }
 
-static int g_num_sms = 0;
+static thread_local int g_last_bn = 0;  // tile width the last gemm_bf16 call on this thread picked (tests assert that the 256-wide path ran)
+int gemm_last_bn() { return g_last_bn; }
+
+// SM count of the CURRENT device (a process may hold contexts on several devices)
 int num_sms() {
-    if (!g_num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_num_sms <= 0) g_num_sms = 148;
+    static std::atomic<int> sms[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = sms[dev & 63].load(std::memory_order_relaxed);
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        if (v <= 0) v = 148;
+        sms[dev & 63].store(v, std::memory_order_relaxed);
     }
-    return g_num_sms;
+    return v;
 }
 
 template <int BN, int STAGES, int EPI, bool DUAL = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st, bool pdl = false) {
     constexpr size_t smem = (size_t)STAGES * ((DUAL ? 2 : 1) * kBM * kBK * 2 + BN * kBK * 2) + 1024;
-    static bool attr_done = false;
-    if (!attr_done) {
-        WDR_CUDA_TRY(cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    static DeviceOnce attr_once;
+    WDR_CUDA_TRY(per_device_once(attr_once, [] { return cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     WDR_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, dim3(grid), dim3(kGemmThreads), smem, st, pdl, ta, tb, p));
     WDR_LAUNCH_CHECK();
@@ -424,6 +427,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
         (d.epilogue == EPI_BIAS_BF16 || d.epilogue == EPI_BIAS_GELU_BF16 || d.epilogue == EPI_BIAS_RESID_F32 || d.epilogue == EPI_QKV_BF16 ||
          d.epilogue == EPI_BIAS_GELU_POS_F32 || d.epilogue == EPI_HEADS_BF16))
         BN = 256;
+    g_last_bn = BN;
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
     if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
     else if (d.split_k > 1 || d.bn == 64 || d.dual_a) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 / dual-A are plain fp32-partial GEMMs (EPI_F32, no bias)");

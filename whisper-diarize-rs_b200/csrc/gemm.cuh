@@ -66,5 +66,6 @@ struct GemmDesc {
 };
 
 int gemm_bf16(const GemmDesc& d, cudaStream_t st);
+int gemm_last_bn();  // N-tile width (64 / 128 / 256) of the last gemm_bf16 call on this thread
 
 }  // namespace wdr

@@ -50,6 +50,13 @@ bool GgmlFile::open(const char* p, std::string* err) {
         tokens[i].resize(len);
         if (len && !rd(f, &tokens[i][0], len)) return fail("truncated vocabulary");
     }
+    int64_t file_size = 0;
+    {   // every tensor is bounded by the file's real size before anything is multiplied or sought
+        const int64_t here = ftello(f);
+        if (here < 0 || fseeko(f, 0, SEEK_END) != 0) return fail("cannot seek");
+        file_size = ftello(f);
+        if (fseeko(f, here, SEEK_SET) != 0) return fail("cannot seek");
+    }
     while (true) {
         int32_t n_dims = 0, name_len = 0, type = 0;
         if (!rd(f, &n_dims, 4)) break;  // EOF
@@ -62,21 +69,17 @@ bool GgmlFile::open(const char* p, std::string* err) {
             int32_t ne = 0;
             if (!rd(f, &ne, 4) || ne <= 0) return fail("bad tensor shape");
             t.ne.push_back(ne);
+            if (t.n_elem > file_size / ne) return fail("tensor shape larger than the file");  // also keeps the running product from overflowing
             t.n_elem *= ne;
         }
         std::string name(name_len, 0);
         if (!rd(f, &name[0], name_len)) return fail("truncated tensor name");
         if (type != 0 && type != 1) return fail("tensor '" + name + "' is quantised (type " + std::to_string(type) + "): only f32 / f16 checkpoints are supported");
-        t.file_offset = ftell(f);
+        t.file_offset = ftello(f);
         const int64_t bytes = t.n_elem * (type == 0 ? 4 : 2);
-        if (fseek(f, (long)bytes, SEEK_CUR) != 0) return fail("truncated tensor data");
+        if (t.file_offset < 0 || bytes <= 0 || bytes > file_size - t.file_offset) return fail("tensor '" + name + "' runs past the end of the file");
+        if (fseeko(f, (off_t)bytes, SEEK_CUR) != 0) return fail("truncated tensor data");
         tensors[name] = t;
-    }
-    {   // the last seek may run past EOF without failing: check the real size
-        fseek(f, 0, SEEK_END);
-        const int64_t size = ftell(f);
-        for (auto& kv : tensors)
-            if (kv.second.file_offset + kv.second.n_elem * (kv.second.type == 0 ? 4 : 2) > size) return fail("tensor '" + kv.first + "' runs past the end of the file");
     }
     fclose(f);
     if (tensors.empty()) { *err = path + ": no tensors"; return false; }
@@ -90,7 +93,7 @@ bool GgmlFile::read_f32(const std::string& name, int64_t expect_elems, std::vect
     if (t.n_elem != expect_elems) { *err = path + ": tensor '" + name + "' has " + std::to_string(t.n_elem) + " elements, expected " + std::to_string(expect_elems); return false; }
     FILE* f = fopen(path.c_str(), "rb");
     if (!f) { *err = "cannot reopen " + path; return false; }
-    bool ok = fseek(f, (long)t.file_offset, SEEK_SET) == 0;
+    bool ok = fseeko(f, (off_t)t.file_offset, SEEK_SET) == 0;
     out->resize((size_t)t.n_elem);
     if (ok && t.type == 0) ok = rd(f, out->data(), (size_t)t.n_elem * 4);
     else if (ok) {

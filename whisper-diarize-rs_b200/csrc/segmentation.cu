@@ -295,7 +295,9 @@ extern "C" void wdr_seg_free(wdr_seg* m) {
     delete m;
 }
 
-extern "C" int wdr_seg_n_windows(int64_t n_samples) { return (int)((n_samples + kSegWindow - 1) / kSegWindow); }
+// pyannote-rs pads `window_size - (len % window_size)` zeros: floor(n / window) + 1 windows — an exact multiple of 10 s gets a whole
+// extra silent window (which closes a speaker still active at the end of the audio), n = 0 gets one
+extern "C" int wdr_seg_n_windows(int64_t n_samples) { return n_samples < 0 ? 0 : (int)(n_samples / kSegWindow + 1); }
 
 // scores[W][589][7] (device) for W windows of pcm (device int16, n_total valid samples; the tail of the last window reads as 0)
 static int seg_forward(wdr_seg* m, const int16_t* pcm_dev, int64_t n_total, int W, float* scores_dev, cudaStream_t st) {
@@ -356,7 +358,6 @@ extern "C" int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, flo
     int rc = ensure_device(m->device);
     if (rc != WDR_OK) return rc;
     const int W = wdr_seg_n_windows(n);
-    if (W == 0) return 0;
     struct { int16_t* p; } d_x;
     struct { float* p; } d_s;
     if ((size_t)n > m->pcm_cap) {
@@ -374,7 +375,7 @@ extern "C" int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, flo
     }
     d_x.p = m->pcm_dev;
     d_s.p = m->scores_dev;
-    WDR_CUDA_TRY(cudaMemcpyAsync(d_x.p, pcm, sizeof(int16_t) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
+    if (n) WDR_CUDA_TRY(cudaMemcpyAsync(d_x.p, pcm, sizeof(int16_t) * (size_t)n, cudaMemcpyHostToDevice, m->stream));
     // windows are independent: process them in groups to bound the workspace (x0 alone is 1.7 MB per window)
     const int group = 64;
     for (int w0 = 0; w0 < W; w0 += group) {
@@ -387,8 +388,10 @@ extern "C" int wdr_seg_scores_i16(wdr_seg* m, const int16_t* pcm, int64_t n, flo
     return W;
 }
 
-// pyannote-rs' state machine on [n_windows][589][7] scores (host logic, bit-exact given the scores)
-static void seg_state_machine(const float* scores, int W, int64_t n_padded, wdr_seg_result* out) {
+// pyannote-rs' state machine on [n_windows][589][7] scores (host logic, bit-exact given the scores).  n = the ORIGINAL sample count:
+// upstream clamps the sample range to it (start to n - 1, end to n), not to the padded length, after a seconds round trip in f64
+// (start = offset / sr; idx = (start * sr) as usize), which is restated literally because the truncation can land one below offset.
+static void seg_state_machine(const float* scores, int W, int64_t n, wdr_seg_result* out) {
     int64_t offset = kSegFrameStart, start = 0;
     bool speaking = false;
     for (int64_t f = 0; f < (int64_t)W * kSegFrames; f++) {
@@ -399,21 +402,27 @@ static void seg_state_machine(const float* scores, int W, int64_t n_padded, wdr_
         if (cls != 0) {
             if (!speaking) { start = offset; speaking = true; }
         } else if (speaking) {
-            out->start.push_back((double)start / WDR_SAMPLE_RATE);
-            out->end.push_back((double)offset / WDR_SAMPLE_RATE);
-            out->i0.push_back(start < n_padded ? start : n_padded);
-            out->i1.push_back(offset < n_padded ? offset : n_padded);
+            const double sr = (double)WDR_SAMPLE_RATE;
+            const double t0 = (double)start / sr, t1 = (double)offset / sr;
+            out->start.push_back(t0);
+            out->end.push_back(t1);
+            const double lim0 = (double)(n > 0 ? n - 1 : 0), lim1 = (double)n;
+            const double s_f = t0 * sr, e_f = t1 * sr;
+            int64_t a = (int64_t)(s_f < lim0 ? s_f : lim0), b = (int64_t)(e_f < lim1 ? e_f : lim1);
+            if (b < a) b = a;  // upstream would panic on start > end; cannot happen for n >= 1
+            out->i0.push_back(a);
+            out->i1.push_back(b);
             speaking = false;
         }
         offset += kSegFrameSize;
     }
 }
 
-extern "C" wdr_seg_result* wdr_seg_segments_from_scores(const float* scores, int n_windows, int64_t n_samples_padded) {
+extern "C" wdr_seg_result* wdr_seg_segments_from_scores(const float* scores, int n_windows, int64_t n_samples) {
     clear_error();
-    if (n_windows < 0 || (!scores && n_windows)) { set_error("bad arguments"); return nullptr; }
+    if (n_windows < 0 || n_samples < 0 || (!scores && n_windows)) { set_error("bad arguments"); return nullptr; }
     wdr_seg_result* r = new wdr_seg_result();
-    seg_state_machine(scores, n_windows, n_samples_padded, r);
+    seg_state_machine(scores, n_windows, n_samples, r);
     return r;
 }
 
@@ -426,7 +435,7 @@ extern "C" wdr_seg_result* wdr_seg_get_segments(wdr_seg* m, const int16_t* pcm, 
     wdr_seg_result* r = new wdr_seg_result();
     r->padded.assign((size_t)W * kSegWindow, 0);
     if (n) memcpy(r->padded.data(), pcm, sizeof(int16_t) * (size_t)n);
-    seg_state_machine(scores.data(), W, (int64_t)W * kSegWindow, r);
+    seg_state_machine(scores.data(), W, n, r);
     return r;
 }
 extern "C" int wdr_seg_result_n(wdr_seg_result* r) { return r ? (int)r->start.size() : 0; }

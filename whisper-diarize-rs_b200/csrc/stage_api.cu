@@ -34,5 +34,8 @@ extern "C" int wdr_gemm_bf16_dev(const uint16_t* A, int64_t lda, int rows_per_ba
     d.ldt = ldt;
     d.n_split = n_split;
     d.t_batch_stride = t_batch_stride;
+    if (epilogue == EPI_HEADS_BF16) { d.group_rows = n_split; d.n_split = 0; }  // head-major K|V store: n_split carries the rows per group
     return gemm_bf16(d, (cudaStream_t)stream);
 }
+
+extern "C" int wdr_gemm_last_tile_n(void) { return gemm_last_bn(); }
