@@ -107,10 +107,39 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU port (the oracle) — the reported baseline and the --impl reference arm
 # ---------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """Cores this process may run on (the affinity mask, not the machine's count)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def claim_cpu_threads(n=None):
+    """The CPU arm sets its thread count ITSELF: a launcher may export OMP_NUM_THREADS=1 (torch.distributed.run does for
+    multi-rank launches), which would run the port on one thread while the line claims all cores.  Returns the team size an OpenMP
+    parallel region of the port really gets — the number reported as `cores`."""
+    from oracle import native
+    n = n or host_cores()
+    got = native.set_threads(n)
+    try:  # the numpy / torch parts of the diarization port (oracle/pyannet.py, oracle/resnet.py)
+        import torch
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=n)
+    except Exception:
+        pass
+    return got
+
+
 class CpuPort:
     def __init__(self, arch, workload):
         from oracle import native, weights as W, filters
         native.build()
+        self.threads = claim_cpu_threads()
         self.native, self.W = native, W
         self.arch, self.workload = arch, workload
         self.a = W.ARCHS[arch]
@@ -120,7 +149,7 @@ class CpuPort:
         self.dec = native.Decoder(arch, W.pack_decoder(arch, w), bf16=True) if workload == "transcribe" else None
 
     def run(self, pcm, n_chunks):
-        """Processes n_chunks windows; returns (RTFx, seconds, tokens)."""
+        """Processes n_chunks windows; returns (RTFx, seconds, tokens).  The result of window 0 is kept in self.last0."""
         from oracle import full
         t0 = time.perf_counter()
         n_tok = 0
@@ -131,8 +160,17 @@ class CpuPort:
             if self.dec is not None:
                 r = full.full_window(self.dec, enc, x)
                 n_tok += r.get("n_sampled", 0)
+                if i == 0:
+                    self.last0 = r
         dt = time.perf_counter() - t0
         return n_chunks * 30.0 / dt, dt, n_tok
+
+    def window_on_encoder_output(self, pcm_row, enc_out):
+        """The decode half (greedy decode, token timestamps, DTW) of one window on a GIVEN encoder output: the strict checker of
+        what the GPU arm produced for that window (identical inputs to the decoder => ids / t0 / t1 / t_dtw must be identical)."""
+        from oracle import full
+        x = pcm_row.astype(np.float32) / np.float32(32768.0)
+        return full.full_window(self.dec, enc_out, x)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -173,7 +211,7 @@ def run_diarize(args):
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count()
+        cores = claim_cpu_threads()
         n_w, n_s = 2, 4
         t0 = time.perf_counter()
         steps = max(1, min(args.steps, 3))
@@ -319,11 +357,12 @@ def run_diarize(args):
                 "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05) in the ResNet34 embedding stage (whole stage incl. fbank, im2col, H2D/D2H)",
                              "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
                              "algorithmic_gflop_per_step": flops / 1e9}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
+            cpu_threads = claim_cpu_threads()
             t_seg, t_emb = diar_cpu(pcm, 2, 4)
             frames = sum(1 + (int(off[i + 1] - off[i]) - 400) // 160 for i in ok)
             est = 60 * t_seg + frames * t_emb
-            line["cpu_baseline"] = {"value": seconds / est, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port",
+            line["cpu_baseline"] = {"value": seconds / est, "unit": "audio-s/s", "cores": cpu_threads, "kind": "port",
                                     "sample": f"2 of 60 segmentation windows ({t_seg:.2f} s each) + 4 x 3 s embeddings ({t_emb * 1e3:.2f} ms per fbank frame), "
                                               f"extrapolated to the recording's 60 windows and {frames} frames; oracle/pyannet.py (numpy) + oracle/resnet.py (torch CPU)"}
         sys.stdout.flush()
@@ -430,6 +469,44 @@ def run_pipeline(args):
         dist.destroy_process_group()
 
 
+def parity_check(w, st, ctx, port, pcm_host, params):
+    """bench.py checks what it times: window 0 of the timed batch against the CPU port.
+    strict: the port's decode half (greedy decode, A.5 token timestamps, DTW) on the LIBRARY's encoder output for that window —
+            identical decoder inputs, so token ids, segment times, t0 / t1 and t_dtw must be identical;
+    from_pcm: the port end to end in fp32 from the PCM (its own mel and fp32 encoder, already computed by the cpu_baseline sample) —
+            a divergence there is legitimate only where the fp32 model's own top-1 margin is below the bf16 noise floor."""
+    L = w.load()
+    hid0 = st.encode_chunks(pcm_host[0:1])[0]
+    st.full_batch(pcm_host[0:1], None, params)  # window 0 alone: results are independent of the batch composition (tests/test_gpu_full_size.py)
+    got = [s_ for s_ in st.segments() if s_["chunk"] == 0]
+    ids_g = [t.id for s_ in got for t in s_["tokens"]]
+    out = {"window": 0, "n_tokens": len(ids_g)}
+    ref = port.window_on_encoder_output(pcm_host[0], hid0)
+    toks_r = [t for s_ in ref["segments"] for t in s_["tokens"]]
+    ids_r = [t.id for t in toks_r]
+    same = ids_g == ids_r
+    out["tokens_identical"] = bool(same)
+    if same:
+        toks_g = [t for s_ in got for t in s_["tokens"]]
+        out["first_divergence"] = None
+        out["segment_times_identical"] = [(s_["t0"], s_["t1"]) for s_ in got] == [(s_["t0"], s_["t1"]) for s_ in ref["segments"]]
+        out["t0_t1_identical"] = [(t.t0, t.t1) for t in toks_g] == [(t.t0, t.t1) for t in toks_r]
+        out["t_dtw_identical"] = [t.t_dtw for t in toks_g] == [t.t_dtw for t in toks_r]
+    else:
+        k = next((i for i, (a_, b_) in enumerate(zip(ids_g, ids_r)) if a_ != b_), min(len(ids_g), len(ids_r)))
+        out["first_divergence"] = int(k)
+        out["margin"] = float(ref["margins"][k]) if k < len(ref["margins"]) else None
+    fp = getattr(port, "last0", None)
+    if fp is not None:
+        ids_f = [t.id for s_ in fp["segments"] for t in s_["tokens"]]
+        out["from_pcm_fp32_encoder"] = {"tokens_identical": ids_f == ids_g}
+        if ids_f != ids_g:
+            k = next((i for i, (a_, b_) in enumerate(zip(ids_g, ids_f)) if a_ != b_), min(len(ids_g), len(ids_f)))
+            out["from_pcm_fp32_encoder"].update(first_divergence=int(k), oracle_top1_margin=float(fp["margins"][k]) if k < len(fp["margins"]) else None)
+    out["checker"] = "oracle/full.py:full_window on oracle/wdr_oracle_full.c (bf16 cross-KV storage mode), window 0 of the timed batch"
+    return out
+
+
 def metric_name(workload):
     return "RTFx full transcribe+DTW" if workload == "transcribe" else "RTFx mel+encoder"
 
@@ -438,9 +515,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
     pcm = synth_pcm(4)
     port = CpuPort(args.arch, args.workload)
+    cores = port.threads  # the OpenMP team size the port really runs with (set explicitly; OMP_NUM_THREADS of a launcher is overridden)
     _, t1, _ = port.run(pcm, 1)  # warm (page-in) and calibrate the per-step sample
     per_step = max(1, min(4, int(8.0 / max(t1, 1e-3))))
     for _ in range(max(args.warmup - 1, 0)):
@@ -457,7 +534,8 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "chunks_per_step": per_step},
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                             "sample": f"{per_step} x 30 s window(s) per step x {steps} steps on {cores} host threads (OpenMP), oracle/wdr_oracle*.c"},
+                             "sample": f"{per_step} x 30 s window(s) per step x {steps} steps on {cores} OpenMP threads (omp_get_num_threads() inside a parallel region; "
+                                       f"{host_cores()} cores in the affinity mask), oracle/wdr_oracle*.c"},
             "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -587,11 +665,33 @@ def main():
     ms_profiled = p0.elapsed_time(p1)
     prof = st.profile_collect()
     st.profile_enable(False)
+    cross_launches, cross_live = st.cross_attn_stats() if full else (0, 0)  # of the last step, counted on the device
     if world > 1:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     value = world * B * 30.0 * args.steps / (ms / 1e3)
+
+    # ---- strong scaling (N > 1): BASELINE configs[2] read literally — args.chunks windows in TOTAL, chunks / N per GPU ----
+    strong = None
+    if full and world > 1:
+        Bs = max(1, B // world)
+        for _ in range(2):
+            st.full_batch_dev(pcm_dev.data_ptr(), Bs, 480000, params)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            st.full_batch_dev(pcm_dev.data_ptr(), Bs, 480000, params)
+        s1.record()
+        barrier()
+        ms_s = s0.elapsed_time(s1)
+        t = torch.tensor([ms_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_s = float(t.item())
+        strong = {"scaling": "strong", "windows_total": Bs * world, "windows_per_gpu": Bs, "value": world * Bs * 30.0 * args.steps / (ms_s / 1e3),
+                  "unit": "audio-s/s", "ms_per_step": ms_s / args.steps, "phases_ms_last_step": st.phase_ms(),
+                  "note": "same K steps, device-resident PCM, CUDA events, max over ranks; divide by the N=1 weak value for the strong-scaling efficiency"}
 
     # ---- end-to-end arm: host PCM through the C ABI, H2D inside the timed region, results read back ----
     def step_e2e():
@@ -659,11 +759,15 @@ def main():
             kern["mel"] = {"ms_per_step": prof["mel"]["ms"] / args.steps, "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak,
                            "algorithmic_bytes_per_window": 480000 * 2 + n_mel * 3000 * 4}
         if prof["dec_cross"]["ms"] > 0:
-            # algorithmic bytes of one cross-attention launch: K_c and V_c of every (window, head): 2 x 1500 x d bf16 per window
-            per_launch = B * 2 * 1500 * dm * 2
+            # algorithmic bytes of one cross-attention launch: K_c and V_c of every LIVE (window, head): 2 x 1500 x d bf16 per window.
+            # Live windows per launch are counted on the device (wdr_full_get_cross_attn_stats): finished windows exit at once and
+            # stream nothing, so with weights that emit EOT a launch serves fewer than B windows.
+            live_per_launch = cross_live / cross_launches if cross_launches else float(B)
+            per_launch = live_per_launch * 2 * 1500 * dm * 2
             gbs = per_launch * prof["dec_cross"]["records"] / (prof["dec_cross"]["ms"] / 1e3) / 1e9
             kern["dec_cross_attention"] = {"ms_per_step": prof["dec_cross"]["ms"] / args.steps, "launches_per_step": prof["dec_cross"]["records"] / args.steps,
-                                           "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak, "algorithmic_bytes_per_launch": per_launch}
+                                           "achieved_gbs": gbs, "frac_hbm": gbs / hbm_peak, "algorithmic_bytes_per_launch": per_launch,
+                                           "live_windows_per_launch": live_per_launch, "launches_counted_on_device_last_step": cross_launches}
         for name in ("mel_aux", "layernorm", "decoder", "dec_gemm", "dec_cross_batched", "dtw", "other"):
             if prof[name]["ms"] > 0:
                 kern[name] = {"ms_per_step": prof[name]["ms"] / args.steps, "launches_per_step": prof[name]["records"] / args.steps}
@@ -700,9 +804,11 @@ def main():
                 "kernel_ms_sum_per_step": total_ms / args.steps, "profiled_pass_ms_per_step": ms_profiled / args.steps,
                 "lanes": int(os.environ.get("WDR_LANES", "1")) if full else 1, "phases_ms_last_step": phases,
                 "encoder_tflops_overall": None if full else fl["total_enc"] * B * args.steps / (ms / 1e3) / 1e12}
-        if not args.no_cpu_baseline:
-            cores = os.cpu_count()
+        if strong is not None:
+            line["strong"] = strong
+        if not args.no_cpu_baseline and world == 1:  # the CPU arm is reported on rank 0 at N = 1 only
             port = CpuPort(args.arch, args.workload)
+            cores = port.threads
             _, t1, _ = port.run(pcm_host, 1)
             n = max(1, min(8, int(15.0 / max(t1, 1e-3)))) if t1 < 15.0 else 0
             if n:
@@ -710,7 +816,10 @@ def main():
             else:
                 n, v, dt = 1, 30.0 / t1, t1
             line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                                    "sample": f"{n} of the {B} windows ({dt:.1f} s of CPU work) on {cores} host threads, oracle/wdr_oracle*.c"}
+                                    "sample": f"{n} of the {B} windows ({dt:.1f} s of CPU work) on {cores} OpenMP threads "
+                                              f"({host_cores()} cores in the affinity mask), oracle/wdr_oracle*.c"}
+            if full:
+                line["parity"] = parity_check(w, st, ctx, port, pcm_host, params)
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -310,6 +310,10 @@ int wdr_tokenize_with_vocab(const char* const* token_strings, int n_tokens, cons
  * decode_steps = greedy iterations run. */
 int wdr_full_get_phase_ms(wdr_state* state, double* ms, int32_t* decode_steps);
 int wdr_full_get_chunk_info_from_state(wdr_state* state, int i_chunk, int32_t* info, float* no_speech_prob);
+/* dec_cross_attn_kernel of the last full call, counted on the device: launches, and (launch, window) pairs in which the window was
+ * still decoding and really streamed its K_c / V_c (finished windows exit at once).  bench.py's roofline uses live_windows, so the
+ * algorithmic bytes follow the windows that were live (with checkpoints that emit EOT a launch serves fewer than B windows). */
+int wdr_full_get_cross_attn_stats(wdr_state* state, int64_t* launches, int64_t* live_windows);
 /* Temperature of the ladder (temperature, +temperature_inc, ... <= 1) whose result stands for chunk i of the last full call;
  * -1 if i is out of range. */
 float wdr_full_get_chunk_temperature_from_state(wdr_state* state, int i_chunk);

@@ -36,6 +36,17 @@ def lib():
     return _lib
 
 
+def set_threads(n):
+    """OpenMP threads of the C port (overrides OMP_NUM_THREADS); returns the team size a parallel region really gets."""
+    L = lib()
+    L.oracle_set_threads(int(n))
+    return int(L.oracle_threads_in_parallel())
+
+
+def threads():
+    return int(lib().oracle_threads_in_parallel())
+
+
 def _f32(a):
     a = np.ascontiguousarray(a, dtype=np.float32)
     return a, a.ctypes.data_as(C.POINTER(C.c_float))

@@ -577,3 +577,29 @@ void oracle_synth_fill(float *dst, int64_t n, uint64_t key, float offset, float 
         dst[i] = v;
     }
 }
+
+
+/* ------------------------------------------------------------------------------------------------
+ * OpenMP thread control for the timed CPU arm (bench.py): a launcher may export OMP_NUM_THREADS=1
+ * (torch.distributed.run does for multi-rank launches), which would silently run the port on one
+ * thread while the bench line claims all cores.  The bench sets the count explicitly and reports
+ * what the runtime really uses.
+ * ------------------------------------------------------------------------------------------------ */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_max_threads(void) { return omp_get_max_threads(); }
+int oracle_threads_in_parallel(void) {
+    int n = 1;
+#pragma omp parallel
+    {
+#pragma omp single
+        n = omp_get_num_threads();
+    }
+    return n;
+}
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_max_threads(void) { return 1; }
+int oracle_threads_in_parallel(void) { return 1; }
+#endif

@@ -190,6 +190,7 @@ def load():
     L.wdr_seg_init.restype = C.c_void_p
     L.wdr_seg_init.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
     L.wdr_seg_free.argtypes = [C.c_void_p]
+    L.wdr_full_get_cross_attn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.wdr_gemm_last_tile_n.restype = C.c_int
     L.wdr_gemm_last_tile_n.argtypes = []
     L.wdr_seg_n_windows.argtypes = [C.c_int64]
@@ -620,6 +621,12 @@ class State:
     def chunk_lang_id(self, i):
         """Language detected / used for buffer i of the last full call."""
         return load().wdr_full_get_chunk_lang_id_from_state(self._h, int(i))
+
+    def cross_attn_stats(self):
+        """(launches, live (launch, window) pairs) of dec_cross_attn_kernel in the last full call, counted on the device."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        _check(load().wdr_full_get_cross_attn_stats(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def phase_ms(self):
         """Device time of the phases of the last full call (summed over groups and lanes) + greedy iterations run."""

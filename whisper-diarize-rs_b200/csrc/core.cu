@@ -121,6 +121,9 @@ int ensure_device(int device) {
             return WDR_ERR_CUDA;
         }
     }
+    // A non-sticky error left behind by an unrelated earlier runtime call (another library, a failed probe, an object destroyed out
+    // of order) must not be reported by this call's first launch check: every compute entry point starts here, so start clean.
+    cudaGetLastError();
     // Stream-ordered allocations (cudaMallocAsync in fbank / DTW helpers) come from the device's default pool, whose release
     // threshold is 0: every synchronisation hands the freed memory back to the OS and the next call maps it again — measured as
     // erratic 0.2-3 s stalls per call.  Keep freed blocks cached in the pool instead (once per device).

@@ -284,7 +284,8 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
                       const int32_t* __restrict__ ahead_map /* this layer's [H] -> alignment-head index or -1; null = no capture */,
                       float* __restrict__ aw, const int64_t* __restrict__ aw_off, const int32_t* __restrict__ aw_T,
                       const int32_t* __restrict__ aw_A, const int32_t* __restrict__ pos_ptr, int pos, const DecWinState* __restrict__ win,
-                      const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window /* beam search / fallback: row b reads the cross cache of window row_window[b]; null = b */) {
+                      const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window /* beam search / fallback: row b reads the cross cache of window row_window[b]; null = b */,
+                      unsigned long long* __restrict__ stats /* optional [2]: launches, (launch, window) pairs that really streamed their K_c / V_c */) {
     __shared__ float q[64];
     __shared__ float p[kT + 4];
     __shared__ float red[32];
@@ -294,8 +295,10 @@ dec_cross_attn_kernel(const float* __restrict__ part, int n_splits, int64_t spli
     pdl_launch_dependents();
     pdl_wait();
     pos = load_pos(pos_ptr, pos);
+    if (stats && tid == 0 && hh == 0 && b == 0) atomicAdd(&stats[0], 1ull);
     if (win && (win[b].completed | win[b].failed)) return;  // finished windows stop streaming their K/V
     if (t_limit && pos >= t_limit[b]) return;
+    if (stats && tid == 0 && hh == 0) atomicAdd(&stats[1], 1ull);  // bench.py: algorithmic bytes follow the LIVE windows of a launch
     if (tid < 64) q[tid] = part_sum(part, n_splits, split_stride, (int64_t)b * d + hh * 64 + tid) + b_q[hh * 64 + tid];
     __syncthreads();
     float q8[8];
@@ -1076,7 +1079,7 @@ __global__ void beam_anc_kernel(const int32_t* __restrict__ anc_old, int32_t* __
 void DecoderWorkspace::release() {
     for (void* p : {(void*)enc_bf16, (void*)sk, (void*)sv, (void*)x, (void*)h, (void*)att, (void*)ff, (void*)part, (void*)logits, (void*)seq,
                     (void*)tokens, (void*)win, (void*)done_count, (void*)pos_dev, (void*)beam_anc[0], (void*)beam_anc[1], (void*)beam_limit, (void*)beam_rows,
-                    (void*)beam_cands, (void*)beam_parent, (void*)beam_nosp, (void*)beam_rowwin, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A})
+                    (void*)beam_cands, (void*)beam_parent, (void*)beam_nosp, (void*)beam_rowwin, (void*)ahead_map, (void*)aw, (void*)aw_off, (void*)aw_T, (void*)aw_A, (void*)cross_stats})
         if (p) cudaFree(p);
     for (auto p : ckv) if (p) cudaFree(p);
     if (step_graph) cudaGraphExecDestroy(step_graph);
@@ -1119,6 +1122,8 @@ int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
     WDR_CUDA_TRY(cudaMalloc(&aw_off, sizeof(int64_t) * B));
     WDR_CUDA_TRY(cudaMalloc(&aw_T, sizeof(int32_t) * B));
     WDR_CUDA_TRY(cudaMalloc(&aw_A, sizeof(int32_t) * B));
+    WDR_CUDA_TRY(cudaMalloc(&cross_stats, sizeof(unsigned long long) * 2));
+    WDR_CUDA_TRY(cudaMemset(cross_stats, 0, sizeof(unsigned long long) * 2));
     {
         std::vector<int32_t> map((size_t)n_layer * n_head, -1);
         n_aheads = (int)ctx->aheads.size();
@@ -1264,7 +1269,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             } else
             WDR_CUDA_TRY(launch_kernel(beam ? dec_cross_attn_kernel<6, true> : dec_cross_attn_kernel<6, false>, dim3(H, B), dim3(256), 0, st, pdl, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att,
                                        (int64_t)ws.cap_B * d, capture ? ws.ahead_map + (size_t)l * H : nullptr, ws.aw, ws.aw_off, ws.aw_T, ws.aw_A, pos_ptr, pos,
-                                       win, t_limit, beam ? (const int32_t*)ws.beam_rowwin : (const int32_t*)nullptr));
+                                       win, t_limit, beam ? (const int32_t*)ws.beam_rowwin : (const int32_t*)nullptr, ws.cross_stats));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;

@@ -78,6 +78,7 @@ struct DecoderWorkspace {
     int64_t* aw_off = nullptr;
     int32_t* aw_T = nullptr;
     int32_t* aw_A = nullptr;
+    unsigned long long* cross_stats = nullptr;  // [2] dec_cross_attn_kernel: launches, live (launch, window) pairs since the last reset
     int reserve(const wdr_context* ctx, int B);
     void release();
 };

@@ -554,6 +554,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy_done, st->copy_stream));
     }
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[1], s));
+    WDR_CUDA_TRY(cudaMemsetAsync(ws.cross_stats, 0, sizeof(unsigned long long) * 2, s));
     if ((rc = decoder_cross_kv(ctx, ws, B, s, &st->prof)) != WDR_OK) return rc;
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[2], s));
     // ---- language: given, or whisper_lang_auto_detect per buffer: decode [SOT] at position 0, arg-max over the language tokens ----
@@ -950,6 +951,13 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         }
     }
     run_post();  // no DTW: nothing was queued above
+    {   // cross-attention launch / live-window counters of this group (stepwise DTW passes included)
+        if (!fs.cross_stats_host) WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.cross_stats_host), sizeof(unsigned long long) * 2));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.cross_stats_host, ws.cross_stats, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
+        WDR_CUDA_TRY(cudaStreamSynchronize(s));
+        fs.cross_launches += (int64_t)fs.cross_stats_host[0];
+        fs.cross_live += (int64_t)fs.cross_stats_host[1];
+    }
     {   // phase times of this group (the stream is idle here: every branch above ended with a synchronize)
         const bool dtw = !pend.empty();
         if (!dtw) WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[4], s));
@@ -978,6 +986,7 @@ static int full_sequential(wdr_context* ctx, wdr_state* st, const wdr_full_param
     FullScratch& fs = st->full;
     for (auto& v : fs.phase_ms) v = 0.0;
     fs.decode_steps = 0;
+    fs.cross_launches = fs.cross_live = 0;
     if (!fs.ev_energy) {
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy_done, cudaEventDisableTiming));
@@ -1066,6 +1075,7 @@ static int full_range(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     FullScratch& fs = st->full;
     for (auto& v : fs.phase_ms) v = 0.0;
     fs.decode_steps = 0;
+    fs.cross_launches = fs.cross_live = 0;
     if (!fs.ev_energy) {
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_energy_done, cudaEventDisableTiming));
@@ -1288,6 +1298,14 @@ extern "C" int wdr_full_get_phase_ms(wdr_state* st, double* ms, int32_t* decode_
         steps += ln->full.decode_steps;
     }
     if (decode_steps) *decode_steps = steps;
+    return WDR_OK;
+}
+extern "C" int wdr_full_get_cross_attn_stats(wdr_state* st, int64_t* launches, int64_t* live_windows) {
+    clear_error();
+    WDR_REQUIRE(st && launches && live_windows, "bad arguments");
+    *launches = st->full.cross_launches;
+    *live_windows = st->full.cross_live;
+    for (auto ln : st->lanes) { *launches += ln->full.cross_launches; *live_windows += ln->full.cross_live; }
     return WDR_OK;
 }
 extern "C" int wdr_full_lang_id_from_state(wdr_state* st) { return st ? st->lang_id : -1; }

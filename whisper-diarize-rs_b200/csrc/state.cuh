@@ -54,12 +54,15 @@ struct FullScratch {
     cudaEvent_t ev_phase[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double phase_ms[5] = {0, 0, 0, 0, 0};  // accumulated over the groups of the last full call
     int decode_steps = 0;                  // greedy iterations of the last full call (summed over groups)
+    unsigned long long* cross_stats_host = nullptr;  // pinned [2]
+    int64_t cross_launches = 0, cross_live = 0;      // dec_cross_attn_kernel launches / live (launch, window) pairs of the last full call
     void release() {
         cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path); cudaFree(dtw_wins); cudaFree(lp_dev);
         if (lp_host) cudaFreeHost(lp_host);
         if (energy_host) cudaFreeHost(energy_host);
         if (dtw_path_host) cudaFreeHost(dtw_path_host);
         if (done_host) cudaFreeHost(done_host);
+        if (cross_stats_host) cudaFreeHost(cross_stats_host);
         if (ev_energy) cudaEventDestroy(ev_energy);
         if (ev_energy_done) cudaEventDestroy(ev_energy_done);
         if (ev_h2d) cudaEventDestroy(ev_h2d);
