@@ -50,6 +50,15 @@ bool GgmlFile::open(const char* p, std::string* err) {
         tokens[i].resize(len);
         if (len && !rd(f, &tokens[i][0], len)) return fail("truncated vocabulary");
     }
+    if (!read_tensor_index(f, err)) { fclose(f); return false; }
+    fclose(f);
+    if (tensors.empty()) { *err = path + ": no tensors"; return false; }
+    return true;
+}
+
+// The tensor index shared by every legacy-ggml container (whisper models and the Silero VAD file): from the current position to EOF.
+bool GgmlFile::read_tensor_index(FILE* f, std::string* err) {
+    auto fail = [&](const std::string& m) { *err = path + ": " + m; return false; };
     int64_t file_size = 0;
     {   // every tensor is bounded by the file's real size before anything is multiplied or sought
         const int64_t here = ftello(f);
@@ -81,6 +90,31 @@ bool GgmlFile::open(const char* p, std::string* err) {
         if (fseeko(f, (off_t)bytes, SEEK_CUR) != 0) return fail("truncated tensor data");
         tensors[name] = t;
     }
+    return true;
+}
+
+// ggml-silero-v5.1.2.bin (whisper.cpp whisper_vad_init_from_file_with_params; written by models/convert-silero-vad-to-ggml.py):
+//   u32 magic | i32 len, model type string ("silero-16k") | i32 version major, minor, patch | i32 n_encoder_layers,
+//   {i32 in_channels, out_channels, kernel_size} per layer | i32 lstm_input_size, lstm_hidden_size, final_conv_in, final_conv_out |
+//   tensors until EOF (same records as the whisper container).
+bool GgmlFile::open_silero(const char* p, SileroHeader* h, std::string* err) {
+    path = p ? p : "";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { *err = "cannot open " + path; return false; }
+    auto fail = [&](const std::string& m) { *err = path + ": " + m; fclose(f); return false; };
+    uint32_t magic = 0;
+    if (!rd(f, &magic, 4) || magic != 0x67676d6cu) return fail("not a ggml file (bad magic)");
+    int32_t len = 0;
+    if (!rd(f, &len, 4) || len <= 0 || len > 256) return fail("bad model-type string");
+    h->model_type.assign((size_t)len, 0);
+    if (!rd(f, &h->model_type[0], (size_t)len)) return fail("truncated model-type string");
+    if (!rd(f, h->version, 12)) return fail("truncated version");
+    if (!rd(f, &h->n_encoder_layers, 4) || h->n_encoder_layers <= 0 || h->n_encoder_layers > 16) return fail("bad encoder layer count");
+    h->enc_in.resize(h->n_encoder_layers); h->enc_out.resize(h->n_encoder_layers); h->enc_kernel.resize(h->n_encoder_layers);
+    for (int i = 0; i < h->n_encoder_layers; i++)
+        if (!rd(f, &h->enc_in[i], 4) || !rd(f, &h->enc_out[i], 4) || !rd(f, &h->enc_kernel[i], 4)) return fail("truncated encoder hyper-parameters");
+    if (!rd(f, &h->lstm_input, 4) || !rd(f, &h->lstm_hidden, 4) || !rd(f, &h->final_in, 4) || !rd(f, &h->final_out, 4)) return fail("truncated hyper-parameters");
+    if (!read_tensor_index(f, err)) { fclose(f); return false; }
     fclose(f);
     if (tensors.empty()) { *err = path + ": no tensors"; return false; }
     return true;

@@ -22,6 +22,14 @@ struct GgmlTensorInfo {
     int64_t file_offset = 0;
 };
 
+struct SileroHeader {  // header of ggml-silero-v5.1.2.bin (src/model_manager.rs:305-315 downloads it; src/vad.rs:15-17 opens it)
+    std::string model_type;
+    int32_t version[3] = {0, 0, 0};
+    int32_t n_encoder_layers = 0;
+    std::vector<int32_t> enc_in, enc_out, enc_kernel;
+    int32_t lstm_input = 0, lstm_hidden = 0, final_in = 0, final_out = 0;
+};
+
 struct GgmlFile {
     int32_t n_vocab = 0, n_audio_ctx = 0, n_audio_state = 0, n_audio_head = 0, n_audio_layer = 0;
     int32_t n_text_ctx = 0, n_text_state = 0, n_text_head = 0, n_text_layer = 0, n_mels = 0, ftype = 0;
@@ -32,6 +40,9 @@ struct GgmlFile {
     std::string path;
     // Parses the header, vocabulary and tensor index (tensor data stays on disk).  false + err on failure.
     bool open(const char* path, std::string* err);
+    // The Silero VAD container: its own header, then the same tensor records.
+    bool open_silero(const char* path, SileroHeader* h, std::string* err);
+    bool read_tensor_index(FILE* f, std::string* err);
     // Reads one tensor as fp32 (f16 is widened).  false + err on failure (missing tensor, wrong element count, short read).
     bool read_f32(const std::string& name, int64_t expect_elems, std::vector<float>* out, std::string* err) const;
 };
