@@ -247,6 +247,9 @@ def run_diarize(args):
     emb = w.EmbeddingExtractor(seed=1234, device=local)
     pcm_pin = torch.from_numpy(pcm).pin_memory()
     out = {}
+    wd = w.dist.connect(w, local) if world > 1 else None  # the exchange itself is the library's (csrc/dist.cu, NCCL); torch only carries the id
+    gathered = torch.empty(world * 4096, emb.dim, device="cuda", dtype=torch.float32) if world > 1 else None
+    mgr_box = {}
 
     def step():
         if world == 1:
@@ -259,10 +262,21 @@ def run_diarize(args):
         for i, sg_ in enumerate(segs_l):
             off_l[i + 1] = off_l[i] + len(sg_["samples"])
         cat_l = np.concatenate([sg_["samples"] for sg_ in segs_l]).astype(np.int16) if len(segs_l) else np.zeros(0, np.int16)
-        E_l, st_l = emb.compute_batch(cat_l, off_l)
-        E_all = w.dist.allgather_embeddings(E_l[st_l == 0])
-        out["r"] = w.cluster_leader(w.cosine_matrix(E_all), 0.5) if len(E_all) else np.zeros(0, np.int32)
-        out["n_global"] = int(len(E_all))
+        # embeddings stay on the device: segment PCM H2D -> fbank + ResNet34 -> rows of E_dev; the rows of embeddable segments are
+        # L2-normalised into the send buffer and all-gathered by the library (wdr_allgather_embeddings_dev); one D2H of the global
+        # table; the crate's speaker policy (wdr_spk_assign_batch) runs on it on every rank: O(n x speakers x D), no n x n matrix
+        pcm_d = torch.from_numpy(cat_l).pin_memory().cuda(non_blocking=True)
+        E_dev = torch.empty(max(len(segs_l), 1), emb.dim, device="cuda", dtype=torch.float32)
+        st_l = emb.compute_batch_dev(pcm_d.data_ptr(), off_l, E_dev.data_ptr(), torch.cuda.current_stream().cuda_stream) if len(segs_l) else np.zeros(0, np.int32)
+        ok_l = np.flatnonzero(st_l == 0)
+        E_ok = E_dev[torch.from_numpy(ok_l).cuda()].contiguous() if len(ok_l) else E_dev[:0]
+        n_all, counts = wd.allgather_embeddings_dev(E_ok.data_ptr(), int(len(ok_l)), emb.dim, gathered.data_ptr(), gathered.shape[0], normalize=True,
+                                                    stream=torch.cuda.current_stream().cuda_stream)
+        E_all = gathered[:n_all].cpu().numpy()
+        mgr = w.EmbeddingManager(w.SIZE_MAX)
+        out["r"] = mgr.assign_batch(E_all, 0.5)
+        mgr.close()
+        out["n_global"] = int(n_all)
 
     def barrier():
         torch.cuda.synchronize()
@@ -350,7 +364,8 @@ def run_diarize(args):
                            "windows": int(w.load().wdr_seg_n_windows(len(pcm))), "segments": len(segs), "embedded": int(len(ok)),
                            "speakers_leader": int(lab.max()) if len(lab) else 0, "clusters_agglomerative": int(agg.max()) if len(agg) else 0,
                            "l2": "each step streams the whole recording's activations (> 126 MB L2)",
-                           "exchange": None if world == 1 else f"all-gather of {out.get('n_global')} x 256 fp32 embeddings per step (NCCL), global leader scan on every rank"},
+                           "exchange": None if world == 1 else f"all-gather of {out.get('n_global')} x {emb.dim} fp32 L2-normalised embeddings per step inside the library "
+                                                                f"(wdr_allgather_embeddings_dev, NCCL {w.load().wdr_dist_nccl_version()}), the crate's speaker policy on the global table on every rank"},
                 "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm.nbytes + cat.nbytes), "d2h_bytes_per_step": int(E.nbytes + 60 * 589 * 7 * 4),
                         "api": "host.diarize: wdr_seg_get_segments + wdr_emb_compute_batch_i16 + wdr_cosine_matrix + wdr_cluster_leader (host pointers)"},
                 "gpu_launches": int(launches), "clocks": clocks, "stages": stages, "fbank_kernel": fb,
@@ -370,6 +385,8 @@ def run_diarize(args):
         print(json.dumps(line), flush=True)
     seg.close()
     emb.close()
+    if wd is not None:
+        wd.close()
     if world > 1:
         dist.destroy_process_group()
 

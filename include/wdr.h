@@ -130,13 +130,13 @@ int wdr_kaldi_fbank_batch_i16_dev(const int16_t* pcm, const int64_t* seg_offset,
 /* WeSpeaker ResNet34 (the north-star's model; the crate downloads the CAM++ export, same "feats" -> "embs" contract): int16
  * samples cast to f32 without scaling -> Kaldi fbank (80 bins) -> per-column mean subtraction -> ResNet34 -> TSTP -> 256-d. */
 typedef struct wdr_emb wdr_emb;
-wdr_emb* wdr_emb_init(const char* path /* NULL: seeded weights */, uint64_t seed, int device);   /* EmbeddingExtractor::new(path) */
+wdr_emb* wdr_emb_init(const char* path /* a WeSpeaker ResNet34 .onnx export; NULL: seeded weights */, uint64_t seed, int device);   /* EmbeddingExtractor::new(path) */
 void wdr_emb_free(wdr_emb* m);
-int wdr_emb_dim(wdr_emb* m);                                                                       /* 256 */
+int wdr_emb_dim(wdr_emb* m);   /* embedding width D: a property of the loaded model (rows of its last Linear): 256 for WeSpeaker ResNet34 */
 /* compute(&samples): HOST pointers.  WDR_ERR_TOO_SHORT when the segment yields no fbank frame (< 400 samples): the crate maps
  * that error to speaker "?" (src/transcribe.rs:468-476). */
-int wdr_emb_compute_i16(wdr_emb* m, const int16_t* pcm, int64_t n, float* out /* [256] */);
-/* All segments of a recording in one call: segment s = pcm[seg_offset[s] .. seg_offset[s+1]) (HOST arrays); out [n][256];
+int wdr_emb_compute_i16(wdr_emb* m, const int16_t* pcm, int64_t n, float* out /* [D] */);
+/* All segments of a recording in one call: segment s = pcm[seg_offset[s] .. seg_offset[s+1]) (HOST arrays); out [n][D];
  * status[s] = 0 or WDR_ERR_TOO_SHORT (that row of out is zero).  _dev: pcm / out are DEVICE pointers, offsets / status HOST. */
 int wdr_emb_compute_batch_i16(wdr_emb* m, const int16_t* pcm, const int64_t* seg_offset, int n_segments, float* out, int32_t* status);
 int wdr_emb_compute_batch_i16_dev(wdr_emb* m, const int16_t* pcm_dev, const int64_t* seg_offset_host, int n_segments, float* out_dev,
@@ -181,6 +181,17 @@ void wdr_free(wdr_context* ctx);                                                
  * n_audio_head, n_audio_layer, n_text_ctx, n_text_state, n_text_head, n_text_layer, n_mels, ftype; tensor and token counts.
  * (`path` in wdr_init_from_file_with_params: f32 / f16 checkpoints of the OpenAI geometries; quantised files are refused.) */
 int wdr_ggml_probe(const char* path, int32_t* hparams, int32_t* n_tensors, int32_t* n_tokens);
+/* The other model files the crate opens, read without touching the GPU (dependency-free readers, csrc/onnx_file.cu, csrc/ggml_file.cu):
+ * wdr_onnx_probe: segmentation-3.0.onnx (kind 0, src/engine.rs:90) or the WeSpeaker ResNet34 export (kind 1, src/engine.rs:91) —
+ *   info[6] = nodes, constant tensors, graph inputs, graph outputs, parameters the loader takes, embedding width (kind 1).
+ *   Fails with the reason when the operator sequence is not that architecture (e.g. the CAM++ export).
+ * wdr_onnx_read_param: one extracted parameter under its PyTorch-style name and layout ("lstm.weight_ih_l0_reverse", "layer2.0.conv1.weight",
+ *   ...; LSTM gates re-ordered from ONNX i,o,f,c to i,f,g,o; BatchNorm folded); returns the element count (out may be NULL).
+ * wdr_silero_probe: ggml-silero-v5.1.2.bin (src/model_manager.rs:305-315) — hparams[20] = version[3], n_encoder_layers,
+ *   {in, out, kernel} x 4, lstm_input, lstm_hidden, final_conv_in, final_conv_out. */
+int wdr_onnx_probe(const char* path, int kind, int32_t* info);
+int64_t wdr_onnx_read_param(const char* path, int kind, const char* name, float* out, int64_t cap);
+int wdr_silero_probe(const char* path, int32_t* hparams, int32_t* n_tensors);
 int wdr_model_info(const wdr_context* ctx, wdr_model_dims* out);                             /* whisper_model_n_* getters */
 wdr_state* wdr_init_state(wdr_context* ctx);                 /* whisper_init_state (ctx.create_state(), src/transcribe.rs:335) */
 void wdr_free_state(wdr_state* state);                       /* whisper_free_state */
@@ -338,7 +349,7 @@ typedef struct wdr_vad_params {
 } wdr_vad_params;
 wdr_vad_context_params wdr_vad_default_context_params(void);                     /* whisper_vad_default_context_params */
 wdr_vad_params wdr_vad_default_params(void);                                      /* whisper_vad_default_params */
-wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad_context_params params);  /* path NULL: seeded weights */
+wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad_context_params params);  /* path: ggml-silero-v5.1.2.bin; NULL: seeded weights */
 void wdr_vad_free(wdr_vad* v);
 /* whisper_vad_detect_speech: one probability per 512-sample frame (last frame zero padded); LSTM state reset per call. Host ptr. */
 int wdr_vad_detect_speech(wdr_vad* v, const float* pcm, int n);
@@ -359,7 +370,7 @@ void wdr_vad_free_segments(wdr_vad_segments* s);
 /* ---- pyannote segmentation (pyannote_rs::get_segments, reference src/engine.rs:117-122) ------------------------- */
 typedef struct wdr_seg wdr_seg;
 typedef struct wdr_seg_result wdr_seg_result;
-wdr_seg* wdr_seg_init(const char* path /* NULL: seeded weights */, uint64_t seed, int device);
+wdr_seg* wdr_seg_init(const char* path /* segmentation-3.0.onnx; NULL: seeded weights */, uint64_t seed, int device);
 void wdr_seg_free(wdr_seg* m);
 int wdr_seg_n_windows(int64_t n_samples);                              /* n / 160000 + 1: pyannote-rs pads `window - len % window` zeros, so an exact
                                                                           multiple of 10 s gets one more (silent) window */
@@ -388,6 +399,10 @@ int wdr_spk_count(wdr_spk* m);                         /* get_all_speakers().len
 int wdr_spk_search(wdr_spk* m, const float* emb, int dim, float threshold);
 /* get_best_speaker_match(embedding): best cosine match regardless of threshold; WDR_ERR_INVALID when no speaker is stored. */
 int wdr_spk_best_match(wdr_spk* m, const float* emb, int dim);
+/* The crate's per-segment policy (cap reached -> get_best_speaker_match, else search_speaker; src/transcribe.rs:480-492) applied to n
+ * embeddings in order; labels[i] = id >= 1 or 0 for "?".  Returns the number of speakers.  Host logic (what a multi-GPU host runs on the
+ * all-gathered table). */
+int wdr_spk_assign_batch(wdr_spk* m, const float* emb, int n, int dim, float threshold, int32_t* labels);
 /* Pairwise cosine similarity S[N][N] of embeddings emb[N][D] on the device (host pointers). */
 int wdr_cosine_matrix(const float* emb, int N, int D, float* S);
 /* The crate's per-segment policy (cap reached -> best match, else search/create) as a pure function of S, segments in time
@@ -396,6 +411,33 @@ int wdr_cluster_leader(const float* S, int N, float threshold, size_t max_speake
 /* Average-linkage agglomerative clustering of S on the device: merges the first maximal pair while its similarity > threshold.
  * labels[i] = 1.. in order of each cluster's smallest member.  Returns the number of clusters.  Bit-exact given S. */
 int wdr_cluster_agglomerative(const float* S, int N, float threshold, int32_t* labels);
+
+/* ---- multi-GPU exchange ----------------------------------------------------------------------------------------------
+ * The path shards by independent unit (30 s window, 10 s diarization window, speech segment): one context per GPU, static contiguous
+ * blocks of units per rank, weights replicated, NO data-path collective.  Its one exchange is the all-gather of per-rank speaker
+ * embeddings ahead of global clustering: NCCL (opened at run time: libnccl.so.2 or $WDR_NCCL_LIB) over NVLink / NVSwitch on device
+ * buffers.  The reference itself is single-GPU (`gpu_device`, src/engine.rs:14, src/transcribe.rs:110-112); a host that drives N GPUs
+ * creates one wdr_dist per rank: N processes (rank 0 calls wdr_dist_get_unique_id, the id travels over the host's own channel, every rank
+ * calls wdr_dist_init) or N threads of one process (the same, or wdr_dist_init_all).  n_ranks = 1 needs no NCCL. */
+#define WDR_DIST_ID_BYTES 128
+typedef struct wdr_dist wdr_dist;
+int wdr_dist_available(void);                                   /* 1 if NCCL could be opened */
+int wdr_dist_nccl_version(void);                                /* ncclGetVersion, 0 if unavailable */
+int wdr_dist_get_unique_id(uint8_t* id /* [WDR_DIST_ID_BYTES] */);
+wdr_dist* wdr_dist_init(const uint8_t* id, int n_ranks, int rank, int device);     /* collective: every rank calls it; NULL on failure */
+int wdr_dist_init_all(int n_gpus, const int* devices /* NULL: 0 .. n_gpus-1 */, wdr_dist** out /* [n_gpus] */);
+void wdr_dist_free(wdr_dist* d);
+int wdr_dist_size(wdr_dist* d);
+int wdr_dist_rank(wdr_dist* d);
+/* emb [n_local][D] of this rank -> out [sum_r n_r][D] in rank order on EVERY rank (segments stay in time order when shards are
+ * contiguous); counts_out[r] = n_r (HOST, may be NULL).  Ranks may hold different, also zero, row counts.  normalize != 0: rows are
+ * scaled to unit L2 norm on the way into the send buffer (the cosine matrix of the gathered table is then a plain E E^T).  Returns the
+ * number of rows gathered.  _dev: emb / out are DEVICE pointers (out_cap_rows rows available), blocking on `stream` (NULL: the
+ * communicator's own); without suffix: HOST pointers. */
+int wdr_allgather_embeddings_dev(wdr_dist* d, const float* emb_dev, int n_local, int D, int normalize, float* out_dev, int64_t out_cap_rows,
+                                 int32_t* counts_out, void* stream);
+int wdr_allgather_embeddings(wdr_dist* d, const float* emb, int n_local, int D, int normalize, float* out, int64_t out_cap_rows,
+                             int32_t* counts_out);
 
 /* Bring-up aid: copies a decoder workspace buffer of the last step to the host as fp32 (0 x, 1 h, 2 att, 3 ff, 4 layer-0 cross K|V,
  * 5 split-K partials). */

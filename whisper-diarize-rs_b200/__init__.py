@@ -14,9 +14,9 @@ from .capi import (  # noqa: F401
     MelFrontend, log_mel, median_filter, dtw_cost, dtw, dtw_batch_dev, kaldi_fbank, fbank_frames,
     signal_energy, convert_integer_to_float_audio, resample_to_16k, sample_discrete, tokenize_with_vocab, mel_n_len, gemm_bf16_dev,
     Context, State, ContextParams, ModelDims, mel_filters, encoder_attention_dev, DTW_PRESETS,
-    FullParams, TokenData, lang_str, lang_id, ggml_probe,
+    FullParams, TokenData, lang_str, lang_id, ggml_probe, onnx_probe, onnx_read_param, silero_probe, ONNX_PYANNET, ONNX_RESNET34,
     VadContext, VadParams, vad_default_params, vad_segments_from_probs,
     Segmenter, seg_segments_from_scores, EmbeddingExtractor,
-    EmbeddingManager, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
+    EmbeddingManager, Dist, dist_available, dist_unique_id, cosine_matrix, cluster_leader, cluster_agglomerative, SIZE_MAX,
 )
 from . import dist  # noqa: F401,E402

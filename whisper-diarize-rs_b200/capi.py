@@ -121,6 +121,10 @@ def load():
     L.wdr_model_info.argtypes = [C.c_void_p, C.POINTER(ModelDims)]
     L.wdr_init_state.restype = C.c_void_p
     L.wdr_ggml_probe.argtypes = [C.c_char_p, i32p, i32p, i32p]
+    L.wdr_onnx_probe.argtypes = [C.c_char_p, C.c_int, i32p]
+    L.wdr_onnx_read_param.argtypes = [C.c_char_p, C.c_int, C.c_char_p, f32p, C.c_int64]
+    L.wdr_onnx_read_param.restype = C.c_int64
+    L.wdr_silero_probe.argtypes = [C.c_char_p, i32p, i32p]
     L.wdr_init_state.argtypes = [C.c_void_p]
     L.wdr_free_state.argtypes = [C.c_void_p]
     L.wdr_mel_filters.argtypes = [C.c_int, f32p]
@@ -191,6 +195,16 @@ def load():
     L.wdr_seg_init.argtypes = [C.c_char_p, C.c_uint64, C.c_int]
     L.wdr_seg_free.argtypes = [C.c_void_p]
     L.wdr_full_get_cross_attn_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    u8p = C.POINTER(C.c_uint8)
+    L.wdr_dist_get_unique_id.argtypes = [u8p]
+    L.wdr_dist_init.restype = C.c_void_p
+    L.wdr_dist_init.argtypes = [u8p, C.c_int, C.c_int, C.c_int]
+    L.wdr_dist_free.argtypes = [C.c_void_p]
+    L.wdr_dist_size.argtypes = [C.c_void_p]
+    L.wdr_dist_rank.argtypes = [C.c_void_p]
+    L.wdr_allgather_embeddings.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_int, f32p, C.c_int64, i32p]
+    L.wdr_allgather_embeddings_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, i32p, C.c_void_p]
+    L.wdr_spk_assign_batch.argtypes = [C.c_void_p, f32p, C.c_int, C.c_int, C.c_float, i32p]
     L.wdr_gemm_last_tile_n.restype = C.c_int
     L.wdr_gemm_last_tile_n.argtypes = []
     L.wdr_seg_n_windows.argtypes = [C.c_int64]
@@ -669,6 +683,35 @@ def ggml_probe(path):
     return d
 
 
+ONNX_PYANNET, ONNX_RESNET34 = 0, 1
+
+
+def onnx_probe(path, kind):
+    """What the dependency-free ONNX reader finds in `path` and takes from it for network `kind` (no GPU needed)."""
+    info = np.zeros(6, np.int32)
+    _check(load().wdr_onnx_probe(path.encode(), kind, _p(info, i32p)))
+    return dict(zip(["nodes", "tensors", "inputs", "outputs", "params", "emb_dim"], (int(v) for v in info)))
+
+
+def onnx_read_param(path, kind, name):
+    """One parameter as the loader extracts it (PyTorch name / layout; LSTM gates re-ordered; BatchNorm folded), flat fp32."""
+    L = load()
+    n = L.wdr_onnx_read_param(path.encode(), kind, name.encode(), None, 0)
+    if n < 0:
+        _check(int(n))
+    out = np.empty(int(n), np.float32)
+    L.wdr_onnx_read_param(path.encode(), kind, name.encode(), _p(out, f32p), int(n))
+    return out
+
+
+def silero_probe(path):
+    hp = np.zeros(20, np.int32)
+    nt = C.c_int32(0)
+    _check(load().wdr_silero_probe(path.encode(), _p(hp, i32p), C.byref(nt)))
+    return dict(version=tuple(int(v) for v in hp[:3]), n_encoder_layers=int(hp[3]), encoder=[tuple(int(v) for v in hp[4 + 3 * i: 7 + 3 * i]) for i in range(4)],
+                lstm_input=int(hp[16]), lstm_hidden=int(hp[17]), final_in=int(hp[18]), final_out=int(hp[19]), n_tensors=int(nt.value))
+
+
 def lang_str(i):
     r = load().wdr_lang_str(int(i))
     return r.decode() if r else None
@@ -706,6 +749,14 @@ class EmbeddingManager:
     def get_best_speaker_match(self, emb):
         e = _np(emb, np.float32)
         return _check(load().wdr_spk_best_match(self._h, _p(e, f32p), len(e)))
+
+    def assign_batch(self, emb, threshold):
+        """The crate's policy over n embeddings in order (wdr_spk_assign_batch): labels [n] (0 = "?")."""
+        e = _np(emb, np.float32)
+        lab = np.zeros(e.shape[0], np.int32)
+        if e.shape[0]:
+            _check(load().wdr_spk_assign_batch(self._h, _p(e, f32p), e.shape[0], e.shape[1], threshold, _p(lab, i32p)))
+        return lab
 
     def assign(self, emb, threshold):
         """The crate's policy (src/transcribe.rs:482-492): id, or None for "?"."""
@@ -761,12 +812,12 @@ def vad_segments_from_probs(probs, params=None):
 class VadContext:
     """wdr_vad: WhisperVadContext (reference src/vad.rs:15-18)."""
 
-    def __init__(self, seed=1234, gpu_device=0):
+    def __init__(self, seed=1234, gpu_device=0, path=None):
         L = load()
         p = L.wdr_vad_default_context_params()
         p.seed = seed
         p.gpu_device = gpu_device
-        self._h = L.wdr_vad_init_from_file_with_params(None, p)
+        self._h = L.wdr_vad_init_from_file_with_params(path.encode() if path else None, p)  # path: ggml-silero-v5.1.2.bin
         if not self._h:
             raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, L.wdr_last_error().decode())
 
@@ -827,8 +878,8 @@ def seg_segments_from_scores(scores, n_samples_padded):
 class Segmenter:
     """wdr_seg: the segmentation-3.0 session pyannote_rs::get_segments opens (reference src/engine.rs:117)."""
 
-    def __init__(self, seed=1234, device=0):
-        self._h = load().wdr_seg_init(None, seed, device)
+    def __init__(self, seed=1234, device=0, path=None):
+        self._h = load().wdr_seg_init(path.encode() if path else None, seed, device)  # path: segmentation-3.0.onnx
         if not self._h:
             raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, load().wdr_last_error().decode())
 
@@ -856,8 +907,8 @@ class Segmenter:
 class EmbeddingExtractor:
     """wdr_emb: pyannote_rs::EmbeddingExtractor (reference src/transcribe.rs:343, 466-467) — WeSpeaker ResNet34, 256-d."""
 
-    def __init__(self, seed=1234, device=0):
-        self._h = load().wdr_emb_init(None, seed, device)
+    def __init__(self, seed=1234, device=0, path=None):
+        self._h = load().wdr_emb_init(path.encode() if path else None, seed, device)  # path: a WeSpeaker ResNet34 .onnx export
         if not self._h:
             raise WdrError(WDR_ERR_NO_DEVICE if device_count() == 0 else -3, load().wdr_last_error().decode())
         self.dim = load().wdr_emb_dim(self._h)
@@ -895,3 +946,49 @@ class EmbeddingExtractor:
 
     def last_flops(self):
         return float(load().wdr_emb_last_flops(self._h))
+
+
+DIST_ID_BYTES = 128
+
+
+def dist_available():
+    return bool(load().wdr_dist_available())
+
+
+def dist_unique_id():
+    """ncclGetUniqueId through the C ABI (rank 0): 128 bytes to hand to every rank over the host's own channel."""
+    buf = (C.c_uint8 * DIST_ID_BYTES)()
+    _check(load().wdr_dist_get_unique_id(buf))
+    return bytes(buf)
+
+
+class Dist:
+    """wdr_dist: this rank's handle on the path's one exchange (the all-gather of speaker embeddings), NCCL inside the library."""
+
+    def __init__(self, unique_id, n_ranks, rank, device):
+        buf = (C.c_uint8 * DIST_ID_BYTES).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._h = load().wdr_dist_init(buf, n_ranks, rank, device)
+        if not self._h:
+            raise WdrError(-3, load().wdr_last_error().decode())
+        self.n_ranks, self.rank = n_ranks, rank
+
+    def close(self):
+        if self._h:
+            load().wdr_dist_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def allgather_embeddings(self, emb_local, max_rows, normalize=False):
+        """emb_local [n, D] host -> ([sum n_r, D] in rank order, counts [n_ranks])."""
+        e = _np(emb_local, np.float32).reshape(len(emb_local), -1)
+        D = e.shape[1]
+        out = np.empty((max_rows, D), np.float32)
+        counts = np.zeros(self.n_ranks, np.int32)
+        n = _check(load().wdr_allgather_embeddings(self._h, _p(e, f32p), e.shape[0], D, int(normalize), _p(out, f32p), max_rows, _p(counts, i32p)))
+        return out[:n], counts
+
+    def allgather_embeddings_dev(self, emb_dev_ptr, n_local, D, out_dev_ptr, out_cap_rows, normalize=False, stream=None):
+        counts = np.zeros(self.n_ranks, np.int32)
+        n = _check(load().wdr_allgather_embeddings_dev(self._h, emb_dev_ptr, n_local, D, int(normalize), out_dev_ptr, out_cap_rows, _p(counts, i32p), stream))
+        return n, counts

@@ -167,6 +167,23 @@ extern "C" int wdr_spk_best_match(wdr_spk* m, const float* emb, int dim) {
     return best_id;
 }
 
+// The crate's per-segment policy (src/transcribe.rs:480-492) over n embeddings in order: the speaker cap reached -> best match,
+// else search / create.  labels[i] = id >= 1, or 0 for None ("?").  What a multi-GPU host runs on the all-gathered table
+// (wdr_allgather_embeddings): O(n * speakers * D) on the host, no n x n similarity matrix.
+extern "C" int wdr_spk_assign_batch(wdr_spk* m, const float* emb, int n, int dim, float threshold, int32_t* labels) {
+    clear_error();
+    WDR_REQUIRE(m && (emb || n == 0) && n >= 0 && dim > 0 && labels, "bad arguments");
+    for (int i = 0; i < n; i++) {
+        const float* e = emb + (size_t)i * dim;
+        int id;
+        if (m->speakers.size() == m->max_speakers && !m->speakers.empty()) id = wdr_spk_best_match(m, e, dim);
+        else id = wdr_spk_search(m, e, dim, threshold);
+        if (id < 0) return id;
+        labels[i] = id;
+    }
+    return (int)m->speakers.size();
+}
+
 // ---- batch forms over a similarity matrix ----------------------------------------------------------------------------
 extern "C" int wdr_cosine_matrix(const float* emb, int N, int D, float* S) {
     clear_error();

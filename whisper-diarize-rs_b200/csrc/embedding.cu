@@ -18,6 +18,7 @@
 #include <vector>
 #include "common.cuh"
 #include "gemm.cuh"
+#include "onnx_file.cuh"
 #include "nn_common.cuh"
 
 namespace wdr {
@@ -25,7 +26,7 @@ namespace wdr {
 int fbank_run(const int16_t* pcm, const int64_t* seg_offset_dev, const int64_t* feat_offset_dev, const std::vector<int64_t>& seg_offset_host,
               int n_bins, int subtract_mean, float* out, cudaStream_t st);
 
-constexpr int kEmbDim = 256, kEmbBins = 80, kEmbPooled = 5120;
+constexpr int kEmbDimDefault = 256, kEmbBins = 80, kEmbPooled = 5120;  // the width is a property of the loaded model (seg_1 rows): 256 for WeSpeaker ResNet34
 constexpr int kEmbMaxFramesPerGroup = 8192;  // fbank frames per forward batch (bounds the im2col workspace: 80 * frames * 288 bf16)
 
 struct ConvW {
@@ -122,13 +123,35 @@ struct wdr_emb {
     wdr::DevArena io;       // host-pointer API: staged PCM + result embeddings
     wdr::DevArena scratch;  // per-group features, level tables, pooled statistics, embeddings (grow-only)
     double conv_flops = 0.0;  // of the last call (algorithmic, 2*M*N*K)
+    int emb_dim = wdr::kEmbDimDefault;  // rows of the embedding layer (runtime: read from the ONNX file when one is loaded)
 };
 
 namespace wdr {
 
-static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, int ci, int co, int k, int stride, ConvW* out) {
+// file != nullptr: the convolution comes from an ONNX export with its BatchNorm already folded (onnx_extract_resnet34): weight
+// [co][ci][k][k] and bias are used as they are; otherwise seeded tensors are drawn and folded here.
+static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, int ci, int co, int k, int stride, ConvW* out, const NamedTensors* file = nullptr) {
     const int fan = ci * k * k;
     const std::string base = "resnet34." + name;
+    if (file) {
+        auto iw = file->find(name + ".weight"), ib = file->find(name + ".bias");
+        if (iw == file->end() || ib == file->end() || iw->second.size() != (size_t)co * fan || ib->second.size() != (size_t)co) { set_error("wdr_emb_init: %s missing from the model file", name.c_str()); return WDR_ERR_INVALID; }
+        const int K = ci == 1 ? 16 : fan;
+        std::vector<uint16_t> wb((size_t)co * K, 0);
+        for (int o = 0; o < co; o++)
+            for (int c = 0; c < ci; c++)
+                for (int t = 0; t < k * k; t++) wb[(size_t)o * K + (size_t)t * ci + c] = f32_to_bf16_bits(iw->second[((size_t)o * ci + c) * k * k + t]);
+        __nv_bfloat16* dw = nullptr;
+        float* db = nullptr;
+        WDR_CUDA_TRY(cudaMalloc(&dw, sizeof(uint16_t) * wb.size()));
+        m->allocs.push_back(dw);
+        WDR_CUDA_TRY(cudaMalloc(&db, sizeof(float) * co));
+        m->allocs.push_back(db);
+        WDR_CUDA_TRY(cudaMemcpy(dw, wb.data(), sizeof(uint16_t) * wb.size(), cudaMemcpyHostToDevice));
+        WDR_CUDA_TRY(cudaMemcpy(db, ib->second.data(), sizeof(float) * co, cudaMemcpyHostToDevice));
+        *out = ConvW{ci, co, k, stride, K, dw, db};
+        return WDR_OK;
+    }
     std::vector<float> w = nn_synth(seed, base + ".weight", (size_t)co * fan, 0.0f, (float)sqrt(6.0 / fan));
     const bool tail = name.size() >= 5 && (name.compare(name.size() - 5, 5, "conv2") == 0 || name.compare(name.size() - 8 > name.size() ? 0 : name.size() - 8, 8, "shortcut") == 0);
     std::vector<float> g = nn_synth(seed, base + ".bn.weight", co, tail ? 0.7f : 1.0f, 0.1f);
@@ -277,7 +300,7 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     }
     emb_tstp_kernel<<<dim3(10, n), 256, 0, st>>>(x, lv[3].d_T, lv[3].d_off, stats_buf);
     WDR_LAUNCH_CHECK();
-    if ((rc = sgemm_nt(stats_buf, kEmbPooled, m->lin_w, kEmbPooled, m->lin_b, out_dev, kEmbDim, n, kEmbDim, kEmbPooled, NN_ACT_NONE, st)) != WDR_OK) return rc;
+    if ((rc = sgemm_nt(stats_buf, kEmbPooled, m->lin_w, kEmbPooled, m->lin_b, out_dev, m->emb_dim, n, m->emb_dim, kEmbPooled, NN_ACT_NONE, st)) != WDR_OK) return rc;
     WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the host-side level tables (async H2D sources) die with this frame
     m->conv_flops += flops;
     return WDR_OK;
@@ -287,12 +310,23 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
 
 extern "C" wdr_emb* wdr_emb_init(const char* path, uint64_t seed, int device) {
     clear_error();
-    if (path && path[0]) { set_error("wdr_emb_init: ONNX files are not supported yet (pass NULL for seeded weights)"); return nullptr; }
+    // EmbeddingExtractor::new(path) (src/transcribe.rs:343): a WeSpeaker ResNet34 ONNX export; NULL / "" = seeded weights
+    NamedTensors file_w;
+    const NamedTensors* fw = nullptr;
+    int dim = kEmbDimDefault;
+    if (path && path[0]) {
+        OnnxFile of;
+        std::string err;
+        if (!of.load(path, &err) || !onnx_extract_resnet34(of, &file_w, &dim, &err)) { set_error("wdr_emb_init: %s", err.c_str()); return nullptr; }
+        if (dim <= 0 || dim > 4096) { set_error("wdr_emb_init: implausible embedding width %d", dim); return nullptr; }
+        fw = &file_w;
+    }
     if (ensure_device(device) != WDR_OK) return nullptr;
     wdr_emb* m = new wdr_emb();
     m->device = device;
+    m->emb_dim = dim;
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("wdr_emb_init: stream"); delete m; return nullptr; }
-    int rc = emb_upload_conv(m, seed, "conv1", 1, 32, 3, 1, &m->conv1);
+    int rc = emb_upload_conv(m, seed, "conv1", 1, 32, 3, 1, &m->conv1, fw);
     static const int planes[4] = {32, 64, 128, 256}, nblocks[4] = {3, 4, 6, 3}, strides[4] = {1, 2, 2, 2};
     int c_in = 32;
     for (int li = 0; li < 4 && rc == WDR_OK; li++)
@@ -301,21 +335,22 @@ extern "C" wdr_emb* wdr_emb_init(const char* path, uint64_t seed, int device) {
             char nm[64];
             BlockW b{};
             snprintf(nm, sizeof(nm), "layer%d.%d.conv1", li + 1, bi);
-            rc = emb_upload_conv(m, seed, nm, c_in, planes[li], 3, s, &b.c1);
+            rc = emb_upload_conv(m, seed, nm, c_in, planes[li], 3, s, &b.c1, fw);
             snprintf(nm, sizeof(nm), "layer%d.%d.conv2", li + 1, bi);
-            if (rc == WDR_OK) rc = emb_upload_conv(m, seed, nm, planes[li], planes[li], 3, 1, &b.c2);
+            if (rc == WDR_OK) rc = emb_upload_conv(m, seed, nm, planes[li], planes[li], 3, 1, &b.c2, fw);
             b.has_sc = s != 1 || c_in != planes[li];
             if (b.has_sc && rc == WDR_OK) {
                 snprintf(nm, sizeof(nm), "layer%d.%d.shortcut", li + 1, bi);
-                rc = emb_upload_conv(m, seed, nm, c_in, planes[li], 1, s, &b.sc);
+                rc = emb_upload_conv(m, seed, nm, c_in, planes[li], 1, s, &b.sc, fw);
             }
             m->blocks.push_back(b);
             c_in = planes[li];
         }
     if (rc == WDR_OK) {
-        std::vector<float> lw = nn_synth(seed, "resnet34.seg_1.weight", (size_t)kEmbDim * kEmbPooled, 0.0f, (float)(1.0 / sqrt(5120.0)));
-        std::vector<float> lb = nn_synth(seed, "resnet34.seg_1.bias", kEmbDim, 0.0f, 0.05f);
-        if (cudaMalloc(&m->lin_w, sizeof(float) * lw.size()) != cudaSuccess || cudaMalloc(&m->lin_b, sizeof(float) * lb.size()) != cudaSuccess) rc = WDR_ERR_CUDA;
+        std::vector<float> lw = fw ? file_w["seg_1.weight"] : nn_synth(seed, "resnet34.seg_1.weight", (size_t)dim * kEmbPooled, 0.0f, (float)(1.0 / sqrt(5120.0)));
+        std::vector<float> lb = fw ? file_w["seg_1.bias"] : nn_synth(seed, "resnet34.seg_1.bias", dim, 0.0f, 0.05f);
+        if (lw.size() != (size_t)dim * kEmbPooled || lb.size() != (size_t)dim) { set_error("wdr_emb_init: embedding layer shape"); rc = WDR_ERR_INVALID; }
+        else if (cudaMalloc(&m->lin_w, sizeof(float) * lw.size()) != cudaSuccess || cudaMalloc(&m->lin_b, sizeof(float) * lb.size()) != cudaSuccess) rc = WDR_ERR_CUDA;
         else {
             cudaMemcpy(m->lin_w, lw.data(), sizeof(float) * lw.size(), cudaMemcpyHostToDevice);
             cudaMemcpy(m->lin_b, lb.data(), sizeof(float) * lb.size(), cudaMemcpyHostToDevice);
@@ -344,7 +379,7 @@ extern "C" void wdr_emb_free(wdr_emb* m) {
     delete m;
 }
 
-extern "C" int wdr_emb_dim(wdr_emb* m) { return m ? kEmbDim : 0; }
+extern "C" int wdr_emb_dim(wdr_emb* m) { return m ? m->emb_dim : 0; }
 
 extern "C" double wdr_emb_last_flops(wdr_emb* m) { return m ? m->conv_flops : 0.0; }
 
@@ -385,12 +420,12 @@ static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector
         int rc;
         {
             DevArena& A = m->scratch;
-            const size_t need = DevArena::padded(sizeof(float) * frames * kEmbBins) + DevArena::padded(sizeof(float) * g * kEmbDim) +
+            const size_t need = DevArena::padded(sizeof(float) * frames * kEmbBins) + DevArena::padded(sizeof(float) * g * m->emb_dim) +
                                 2 * DevArena::padded(sizeof(int64_t) * (g + 2)) + DevArena::padded(sizeof(int32_t) * 4 * g) +
                                 DevArena::padded(sizeof(int64_t) * 5 * (g + 1)) + DevArena::padded(sizeof(float) * g * kEmbPooled);
             if ((rc = A.reserve(need)) != WDR_OK) return rc;
             feats.p = A.take<float>((size_t)frames * kEmbBins);
-            emb.p = A.take<float>((size_t)g * kEmbDim);
+            emb.p = A.take<float>((size_t)g * m->emb_dim);
             d_fo.p = A.take<int64_t>((size_t)g + 2);
             d_so.p = A.take<int64_t>((size_t)g + 2);
         }
@@ -429,7 +464,7 @@ static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector
         }
         if (rc != WDR_OK) return rc;
         for (int k = 0; k < g; k++)
-            WDR_CUDA_TRY(cudaMemcpyAsync(out_dev + (size_t)live[i0 + k] * kEmbDim, emb.p + (size_t)k * kEmbDim, sizeof(float) * kEmbDim, cudaMemcpyDeviceToDevice, st));
+            WDR_CUDA_TRY(cudaMemcpyAsync(out_dev + (size_t)live[i0 + k] * m->emb_dim, emb.p + (size_t)k * m->emb_dim, sizeof(float) * m->emb_dim, cudaMemcpyDeviceToDevice, st));
         WDR_CUDA_TRY(cudaStreamSynchronize(st));
         i0 = i1;
     }
@@ -449,14 +484,14 @@ extern "C" int wdr_emb_compute_batch_i16(wdr_emb* m, const int16_t* pcm, const i
     for (auto& v : so) v -= base;
     struct { int16_t* p; } d_pcm;
     struct { float* p; } d_out;
-    if ((rc = m->io.reserve(DevArena::padded(sizeof(int16_t) * (size_t)std::max<int64_t>(total, 1)) + DevArena::padded(sizeof(float) * (size_t)n_segments * kEmbDim))) != WDR_OK) return rc;
+    if ((rc = m->io.reserve(DevArena::padded(sizeof(int16_t) * (size_t)std::max<int64_t>(total, 1)) + DevArena::padded(sizeof(float) * (size_t)n_segments * m->emb_dim))) != WDR_OK) return rc;
     d_pcm.p = m->io.take<int16_t>((size_t)std::max<int64_t>(total, 1));
-    d_out.p = m->io.take<float>((size_t)n_segments * kEmbDim);
-    WDR_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, sizeof(float) * (size_t)n_segments * kEmbDim, m->stream));
+    d_out.p = m->io.take<float>((size_t)n_segments * m->emb_dim);
+    WDR_CUDA_TRY(cudaMemsetAsync(d_out.p, 0, sizeof(float) * (size_t)n_segments * m->emb_dim, m->stream));
     WDR_CUDA_TRY(cudaMemcpyAsync(d_pcm.p, pcm + base, sizeof(int16_t) * (size_t)total, cudaMemcpyHostToDevice, m->stream));
     rc = emb_compute_dev(m, d_pcm.p, so, d_out.p, status, m->stream);
     if (rc != WDR_OK) return rc;
-    WDR_CUDA_TRY(cudaMemcpyAsync(out, d_out.p, sizeof(float) * (size_t)n_segments * kEmbDim, cudaMemcpyDeviceToHost, m->stream));
+    WDR_CUDA_TRY(cudaMemcpyAsync(out, d_out.p, sizeof(float) * (size_t)n_segments * m->emb_dim, cudaMemcpyDeviceToHost, m->stream));
     WDR_CUDA_TRY(cudaStreamSynchronize(m->stream));
     return WDR_OK;
 }

@@ -16,6 +16,7 @@
 #include <vector>
 #include "common.cuh"
 #include "nn_common.cuh"
+#include "onnx_file.cuh"
 
 namespace wdr {
 
@@ -215,13 +216,26 @@ struct wdr_seg_result {
 
 extern "C" wdr_seg* wdr_seg_init(const char* path, uint64_t seed, int device) {
     clear_error();
-    if (path && path[0]) { set_error("wdr_seg_init: ONNX files are not supported yet (pass NULL for seeded weights)"); return nullptr; }
+    // pyannote_rs::get_segments(.., model_path) (src/engine.rs:117-122): segmentation-3.0.onnx; NULL / "" = seeded weights
+    NamedTensors file_w;
+    const bool from_file = path && path[0];
+    if (from_file) {
+        OnnxFile of;
+        std::string err;
+        if (!of.load(path, &err) || !onnx_extract_pyannet(of, &file_w, &err)) { set_error("wdr_seg_init: %s", err.c_str()); return nullptr; }
+    }
     if (ensure_device(device) != WDR_OK) return nullptr;
     wdr_seg* m = new wdr_seg();
     m->device = device;
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream"); delete m; return nullptr; }
     SegWeights& w = m->w;
-    auto S = [&](const char* n, size_t cnt, float off, float sc) { return nn_synth(seed, std::string("pyannet.") + n, cnt, off, sc); };
+    bool file_ok = true;
+    auto S = [&](const char* n, size_t cnt, float off, float sc) {
+        if (!from_file) return nn_synth(seed, std::string("pyannet.") + n, cnt, off, sc);
+        auto it = file_w.find(n);  // same PyTorch-style names and layouts (onnx_extract_pyannet)
+        if (it == file_w.end() || it->second.size() != cnt) { file_ok = false; return std::vector<float>(cnt, 0.0f); }
+        return it->second;
+    };
     w.wav_g = S("wav_norm.weight", 1, 1.0f, 0.1f)[0];
     w.wav_b = S("wav_norm.bias", 1, 0.0f, 0.1f)[0];
     {
@@ -272,9 +286,10 @@ extern "C" wdr_seg* wdr_seg_init(const char* path, uint64_t seed, int device) {
     w.cw = m->mem.upload(S("classifier.weight", 7 * 128, 0.0f, (float)(24.0 / sqrt(128.0))));
     {
         auto cb = S("classifier.bias", 7, 0.0f, 0.5f);
-        cb[0] += 1.5f;
+        if (!from_file) cb[0] += 1.5f;  // seeded weights only (see above)
         w.cb = m->mem.upload(cb);
     }
+    if (!file_ok) { set_error("wdr_seg_init: the model file lacks a PyanNet parameter"); wdr_seg_free(m); return nullptr; }
     if (!m->mem.ok || cudaFuncSetAttribute(sinc_conv_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSincSmem) != cudaSuccess) {
         set_error("wdr_seg_init: device allocation failed");
         wdr_seg_free(m);

@@ -18,6 +18,7 @@
 #include <string.h>
 #include <vector>
 #include "common.cuh"
+#include "ggml_file.cuh"
 
 namespace wdr {
 
@@ -309,13 +310,36 @@ extern "C" wdr_vad_params wdr_vad_default_params(void) {
 
 extern "C" wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad_context_params params) {
     clear_error();
-    if (path && path[0]) { set_error("wdr_vad_init: model files are not supported yet (pass NULL for seeded weights)"); return nullptr; }
+    // WhisperVadContext::new(path, params) (src/vad.rs:15-17): ggml-silero-v5.1.2.bin (src/model_manager.rs:305-315); NULL / "" = seeded weights
+    GgmlFile gf;
+    SileroHeader sh;
+    const bool from_file = path && path[0];
+    if (from_file) {
+        std::string err;
+        if (!gf.open_silero(path, &sh, &err)) { set_error("wdr_vad_init: %s", err.c_str()); return nullptr; }
+        static const int want[4][3] = {{129, 128, 3}, {128, 64, 3}, {64, 64, 3}, {64, 128, 3}};
+        bool ok = sh.n_encoder_layers == 4 && sh.lstm_input == 128 && sh.lstm_hidden == 128 && sh.final_in == 128 && sh.final_out == 1;
+        for (int i = 0; ok && i < 4; i++) ok = sh.enc_in[i] == want[i][0] && sh.enc_out[i] == want[i][1] && sh.enc_kernel[i] == want[i][2];
+        if (!ok) { set_error("wdr_vad_init: %s is not a Silero v5 16 kHz model (encoder 129-128-64-64-128, LSTM 128)", path); return nullptr; }
+    }
     if (ensure_device(params.gpu_device) != WDR_OK) return nullptr;
     wdr_vad* v = new wdr_vad();
     v->device = params.gpu_device;
     if (cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking) != cudaSuccess) { set_error("stream"); delete v; return nullptr; }
     std::vector<float> t, tt;
-    {   // true windowed DFT basis, transposed to [k][c]
+    std::string ferr;
+    // a tensor of the model file under whisper.cpp's names (models/convert-silero-vad-to-ggml.py), or the seeded one
+    auto T = [&](std::vector<float>& dst, size_t cnt, const char* file_name, const char* synth_name, float off, float sc) {
+        if (from_file) { if (ferr.empty() && !gf.read_f32(file_name, (int64_t)cnt, &dst, &ferr)) dst.assign(cnt, 0.0f); }
+        else vad_synth(dst, cnt, params.seed, synth_name, off, sc);
+    };
+    if (from_file) {  // the STFT basis travels in the file: [258][1][256] (cos rows, then -sin rows, Hann-windowed), transposed to [k][c]
+        T(t, 258 * 256, "_model.stft.forward_basis_buffer", "", 0.0f, 0.0f);
+        tt.resize(256 * 258);
+        for (int c = 0; c < 258; c++)
+            for (int k = 0; k < 256; k++) tt[k * 258 + c] = t[(size_t)c * 256 + k];
+        v->w.basis_t = vad_upload(v, tt);
+    } else {   // true windowed DFT basis, transposed to [k][c]
         tt.resize(256 * 258);
         for (int c = 0; c < 129; c++)
             for (int k = 0; k < 256; k++) {
@@ -330,34 +354,38 @@ extern "C" wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad
         const int ci = chans[i][0], co = chans[i][1];
         const float s = (float)(1.0 / sqrt((double)ci * 3));
         char name[64];
+        char fname[96];
         snprintf(name, sizeof(name), "vad.encoder.%d.weight", i);
-        vad_synth(t, (size_t)co * ci * 3, params.seed, name, 0.0f, s);
+        snprintf(fname, sizeof(fname), "_model.encoder.%d.reparam_conv.weight", i);
+        T(t, (size_t)co * ci * 3, fname, name, 0.0f, s);
         tt.resize(t.size());
         for (int o = 0; o < co; o++)
             for (int c = 0; c < ci; c++)
                 for (int k = 0; k < 3; k++) tt[((size_t)c * 3 + k) * co + o] = t[((size_t)o * ci + c) * 3 + k];
         v->w.w_t[i] = vad_upload(v, tt);
         snprintf(name, sizeof(name), "vad.encoder.%d.bias", i);
-        vad_synth(t, co, params.seed, name, 0.0f, s);
+        snprintf(fname, sizeof(fname), "_model.encoder.%d.reparam_conv.bias", i);
+        T(t, co, fname, name, 0.0f, s);
         v->w.b[i] = vad_upload(v, t);
     }
     const float s = (float)(1.0 / sqrt(128.0));
-    vad_synth(t, 512 * 128, params.seed, "vad.lstm.weight_ih", 0.0f, s);
+    T(t, 512 * 128, "_model.decoder.rnn.weight_ih", "vad.lstm.weight_ih", 0.0f, s);
     tt.resize(t.size());
     for (int r = 0; r < 512; r++)
         for (int j = 0; j < 128; j++) tt[(size_t)j * 512 + r] = t[(size_t)r * 128 + j];
     v->w.wih_t = vad_upload(v, tt);
-    vad_synth(t, 512 * 128, params.seed, "vad.lstm.weight_hh", 0.0f, s);
+    T(t, 512 * 128, "_model.decoder.rnn.weight_hh", "vad.lstm.weight_hh", 0.0f, s);
     v->w.whh = vad_upload(v, t);
     std::vector<float> b1, b2;
-    vad_synth(b1, 512, params.seed, "vad.lstm.bias_ih", 0.0f, s);
-    vad_synth(b2, 512, params.seed, "vad.lstm.bias_hh", 0.0f, s);
+    T(b1, 512, "_model.decoder.rnn.bias_ih", "vad.lstm.bias_ih", 0.0f, s);
+    T(b2, 512, "_model.decoder.rnn.bias_hh", "vad.lstm.bias_hh", 0.0f, s);
     for (int i = 0; i < 512; i++) b1[i] = b1[i] + b2[i];
     v->w.b_gates = vad_upload(v, b1);
-    vad_synth(t, 128, params.seed, "vad.final_conv.weight", 0.0f, 0.5f);
+    T(t, 128, "_model.decoder.decoder.2.weight", "vad.final_conv.weight", 0.0f, 0.5f);
     v->w.w_out = vad_upload(v, t);
-    vad_synth(t, 1, params.seed, "vad.final_conv.bias", 0.0f, 0.1f);
+    T(t, 1, "_model.decoder.decoder.2.bias", "vad.final_conv.bias", 0.0f, 0.1f);
     v->w.b_out = t[0];
+    if (!ferr.empty()) { set_error("wdr_vad_init: %s", ferr.c_str()); wdr_vad_free(v); return nullptr; }
     for (void* p : v->allocs)
         if (!p) { set_error("wdr_vad_init: out of device memory"); wdr_vad_free(v); return nullptr; }
     return v;

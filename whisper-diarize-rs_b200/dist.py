@@ -1,7 +1,20 @@
 """Multi-GPU plumbing: the path shards by independent unit (30 s window, 10 s diarization window, speech segment),
 so ranks never exchange data on the hot path.  The one real exchange is the all-gather of per-rank speaker embeddings ahead of
-global clustering — NCCL over NVLink on the GPU box, gloo in the CPU tests.  torch.distributed is plumbing only."""
+global clustering.  On the GPU box that exchange runs INSIDE the library (csrc/dist.cu: wdr_dist_init / wdr_allgather_embeddings,
+NCCL over NVLink on device buffers); `connect()` only carries the 128-byte NCCL id from rank 0 to the others over the launcher's
+torch.distributed group, which is what a Rust host would do over its own channel.  `allgather_embeddings` below is the same
+exchange over torch.distributed for the CPU-only (gloo) test of the host logic."""
 import numpy as np
+
+
+def connect(capi, device):
+    """One wdr_dist per rank from an initialised torch.distributed group (any backend): rank 0 draws the NCCL id through the C ABI,
+    the group broadcasts the bytes, every rank calls wdr_dist_init."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [capi.dist_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return capi.Dist(box[0], world, rank, device)
 
 
 def shard_range(n_units, rank, world):
