@@ -438,7 +438,7 @@ bool onnx_extract_pyannet(const OnnxFile& f, NamedTensors* out, std::string* err
 
 bool onnx_extract_resnet34(const OnnxFile& f, NamedTensors* out, int* emb_dim, std::string* err) {
     out->clear();
-    // conv_specs() of oracle/resnet.py: execution order, a block's shortcut conv after its conv2
+    // the 36 convolutions of wespeaker/models/resnet.py in execution order, a block's shortcut conv after its conv2
     struct Spec { std::string name; int64_t ci, co, k, stride; };
     std::vector<Spec> specs;
     specs.push_back({"conv1", 1, 32, 3, 1});
@@ -473,7 +473,7 @@ bool onnx_extract_resnet34(const OnnxFile& f, NamedTensors* out, int* emb_dim, s
         std::vector<float> w = W->f32, b((size_t)sp.co, 0.0f);
         const OnnxTensor* B = n->inputs.size() >= 3 ? f.tensor(n->inputs[2]) : nullptr;
         if (B) { if ((int64_t)B->f32.size() != sp.co) { *err = "Conv " + sp.name + ": bias length"; return false; } b = B->f32; }
-        // an un-folded export keeps BatchNormalization(conv_out, scale, B, mean, var): fold it (fp32, the order of oracle/resnet.py:fold)
+        // an un-folded export keeps BatchNormalization(conv_out, scale, B, mean, var): fold it (fp32: s = g / sqrt(var + eps), w *= s, b = beta - mean * s)
         for (auto& bn : f.nodes) {
             if (bn.op_type != "BatchNormalization" || bn.inputs.size() < 5 || n->outputs.empty() || bn.inputs[0] != n->outputs[0]) continue;
             const OnnxTensor *g = f.tensor(bn.inputs[1]), *beta = f.tensor(bn.inputs[2]), *mean = f.tensor(bn.inputs[3]), *var = f.tensor(bn.inputs[4]);

@@ -65,7 +65,7 @@ typedef std::map<std::string, std::vector<float>> NamedTensors;
 // classifier.{weight,bias}.
 bool onnx_extract_pyannet(const OnnxFile& f, NamedTensors* out, std::string* err);
 // WeSpeaker ResNet34: <conv>.weight [co][ci][k][k] + <conv>.bias with the BatchNorm already folded (either by the exporter or here
-// from a following BatchNormalization node), conv names in execution order as oracle/resnet.py:conv_specs(); seg_1.{weight,bias}.
+// from a following BatchNormalization node), conv names conv1, layer<l>.<b>.conv1 / conv2 / shortcut in execution order (a block's shortcut after its conv2); seg_1.{weight,bias}.
 // *emb_dim receives the embedding width (rows of the final Gemm).
 bool onnx_extract_resnet34(const OnnxFile& f, NamedTensors* out, int* emb_dim, std::string* err);
 
