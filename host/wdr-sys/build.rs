@@ -20,6 +20,7 @@ fn main() {
     println!("cargo:rustc-link-search=native={cuda}/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=dl");  // NCCL is opened at run time (csrc/dist.cu): no link-time dependency on libnccl
     println!("cargo:rerun-if-changed={}", csrc.display());
     println!("cargo:rerun-if-changed={}", manifest.join("../../include/wdr.h").display());
 }

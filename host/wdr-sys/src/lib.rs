@@ -18,6 +18,8 @@ pub const WDR_SAMPLING_BEAM_SEARCH: c_int = 1;
 #[repr(C)] pub struct wdr_seg_result { _p: [u8; 0] }
 #[repr(C)] pub struct wdr_emb { _p: [u8; 0] }
 #[repr(C)] pub struct wdr_spk { _p: [u8; 0] }
+#[repr(C)] pub struct wdr_dist { _p: [u8; 0] }
+pub const WDR_DIST_ID_BYTES: usize = 128;
 
 /// == whisper_context_params (WhisperContextParameters, src/transcribe.rs:102-136) + the synthetic-weights extension.
 #[repr(C)] #[derive(Clone, Copy)]
@@ -129,6 +131,22 @@ extern "C" {
     pub fn wdr_cosine_matrix(emb: *const c_float, n: c_int, d: c_int, s: *mut c_float) -> c_int;
     pub fn wdr_cluster_leader(s: *const c_float, n: c_int, threshold: c_float, max_speakers: size_t, labels: *mut i32) -> c_int;
     pub fn wdr_cluster_agglomerative(s: *const c_float, n: c_int, threshold: c_float, labels: *mut i32) -> c_int;
+    // the crate's per-segment speaker policy (src/transcribe.rs:480-492) over n embeddings in order; labels 0 = None -> "?"
+    pub fn wdr_spk_assign_batch(m: *mut wdr_spk, emb: *const c_float, n: c_int, dim: c_int, threshold: c_float, labels: *mut i32) -> c_int;
+    // ---- multi-GPU: the path's one exchange (the reference is single-GPU: `gpu_device`, src/engine.rs:14) ------------------------
+    // one wdr_dist per GPU; n processes: rank 0 draws the id, every rank calls wdr_dist_init; one process: wdr_dist_init_all
+    pub fn wdr_dist_available() -> c_int;
+    pub fn wdr_dist_get_unique_id(id: *mut u8) -> c_int;
+    pub fn wdr_dist_init(id: *const u8, n_ranks: c_int, rank: c_int, device: c_int) -> *mut wdr_dist;
+    pub fn wdr_dist_init_all(n_gpus: c_int, devices: *const c_int, out: *mut *mut wdr_dist) -> c_int;
+    pub fn wdr_dist_free(d: *mut wdr_dist);
+    pub fn wdr_dist_size(d: *mut wdr_dist) -> c_int;
+    pub fn wdr_dist_rank(d: *mut wdr_dist) -> c_int;
+    pub fn wdr_allgather_embeddings(d: *mut wdr_dist, emb: *const c_float, n_local: c_int, dim: c_int, normalize: c_int, out: *mut c_float,
+                                    out_cap_rows: i64, counts_out: *mut i32) -> c_int;
+    // ---- model files read without a device (src/engine.rs:90-91, src/model_manager.rs:305-315) -----------------------------------
+    pub fn wdr_onnx_probe(path: *const c_char, kind: c_int, info: *mut i32) -> c_int;
+    pub fn wdr_silero_probe(path: *const c_char, hparams: *mut i32, n_tensors: *mut i32) -> c_int;
 }
 
 const _: () = assert!(std::mem::size_of::<wdr_token_data>() == 56);

@@ -432,8 +432,9 @@ int wdr_dist_rank(wdr_dist* d);
 /* emb [n_local][D] of this rank -> out [sum_r n_r][D] in rank order on EVERY rank (segments stay in time order when shards are
  * contiguous); counts_out[r] = n_r (HOST, may be NULL).  Ranks may hold different, also zero, row counts.  normalize != 0: rows are
  * scaled to unit L2 norm on the way into the send buffer (the cosine matrix of the gathered table is then a plain E E^T).  Returns the
- * number of rows gathered.  _dev: emb / out are DEVICE pointers (out_cap_rows rows available), blocking on `stream` (NULL: the
- * communicator's own); without suffix: HOST pointers. */
+ * number of rows gathered.  _dev: emb / out are DEVICE pointers (out_cap_rows rows available); the collective runs on `stream`
+ * (NULL = the default stream) after whatever the caller queued there, and the call returns once it has completed; without suffix:
+ * HOST pointers. */
 int wdr_allgather_embeddings_dev(wdr_dist* d, const float* emb_dev, int n_local, int D, int normalize, float* out_dev, int64_t out_cap_rows,
                                  int32_t* counts_out, void* stream);
 int wdr_allgather_embeddings(wdr_dist* d, const float* emb, int n_local, int D, int normalize, float* out, int64_t out_cap_rows,

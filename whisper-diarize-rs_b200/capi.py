@@ -979,10 +979,11 @@ class Dist:
 
     __del__ = close
 
-    def allgather_embeddings(self, emb_local, max_rows, normalize=False):
-        """emb_local [n, D] host -> ([sum n_r, D] in rank order, counts [n_ranks])."""
-        e = _np(emb_local, np.float32).reshape(len(emb_local), -1)
-        D = e.shape[1]
+    def allgather_embeddings(self, emb_local, max_rows, normalize=False, dim=None):
+        """emb_local [n, D] host -> ([sum n_r, D] in rank order, counts [n_ranks]).  A rank without rows passes dim = D."""
+        e = _np(emb_local, np.float32)
+        D = int(dim) if dim is not None else int(e.shape[1])
+        e = e.reshape(-1, D)
         out = np.empty((max_rows, D), np.float32)
         counts = np.zeros(self.n_ranks, np.int32)
         n = _check(load().wdr_allgather_embeddings(self._h, _p(e, f32p), e.shape[0], D, int(normalize), _p(out, f32p), max_rows, _p(counts, i32p)))

@@ -1086,16 +1086,20 @@ void DecoderWorkspace::release() {
     *this = DecoderWorkspace();
 }
 
-int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
-    if (B <= cap_B) return WDR_OK;
-    WDR_REQUIRE(B <= kDecMaxBatch, "decode batch exceeds 128 windows");
+int DecoderWorkspace::reserve(const wdr_context* ctx, int windows, int rows) {
+    if (rows < windows) rows = windows;
+    if (windows <= cap_W && rows <= cap_B) return WDR_OK;
+    WDR_REQUIRE(windows <= kDecMaxWindows && rows <= kDecMaxRows, "decode batch exceeds 128 windows / 640 rows");
+    windows = std::max(windows, cap_W);
+    rows = std::max(rows, cap_B);
     release();
+    const int W = windows, B = rows;
     const WhisperArch& a = ctx->arch;
     d = a.d; n_layer = a.n_dec_layer; n_head = a.n_head;
     ldv = (a.n_vocab + 7) / 8 * 8;
-    WDR_CUDA_TRY(cudaMalloc(&enc_bf16, sizeof(__nv_bfloat16) * (size_t)B * kT * d));
+    WDR_CUDA_TRY(cudaMalloc(&enc_bf16, sizeof(__nv_bfloat16) * (size_t)W * kT * d));
     ckv.assign(n_layer, nullptr);
-    for (int l = 0; l < n_layer; l++) WDR_CUDA_TRY(cudaMalloc(&ckv[l], sizeof(__nv_bfloat16) * (size_t)B * kT * 2 * d));
+    for (int l = 0; l < n_layer; l++) WDR_CUDA_TRY(cudaMalloc(&ckv[l], sizeof(__nv_bfloat16) * (size_t)W * kT * 2 * d));
     const size_t skv = (size_t)n_layer * B * kDecSeqCap * d;
     WDR_CUDA_TRY(cudaMalloc(&sk, sizeof(float) * skv));
     WDR_CUDA_TRY(cudaMalloc(&sv, sizeof(float) * skv));
@@ -1134,6 +1138,7 @@ int DecoderWorkspace::reserve(const wdr_context* ctx, int B) {
         WDR_CUDA_TRY(cudaMemcpy(ahead_map, map.data(), sizeof(int32_t) * map.size(), cudaMemcpyHostToDevice));
     }
     cap_B = B;
+    cap_W = W;
     return WDR_OK;
 }
 
@@ -1156,8 +1161,8 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 // (hi, lo) activations (512 B per k), its weight tile (2*bn B per k) and writes a 128 x bn fp32 partial; measured on B200
 // (ncu, in-graph): item time ~ fixed + bytes / ~100 GB/s per SM, and a second wave costs a whole item time again.  So: one wave
 // (items <= SMs), the smallest per-item byte count, a small penalty per split for the consumer's partial-sum reads.
-static void pick_tile(int K, int N, int* bn_out, int* splits_out) {
-    const int num_kb = (K + 63) / 64, sms = 148;
+static void pick_tile(int K, int N, int rows, int* bn_out, int* splits_out) {
+    const int num_kb = (K + 63) / 64, sms = 148, m_tiles = (rows + 127) / 128;  // beam batches: several 128-row M tiles
     double best = 1e30;
     int best_bn = 64, best_s = 1;
     for (int bn : {64, 128}) {
@@ -1165,7 +1170,7 @@ static void pick_tile(int K, int N, int* bn_out, int* splits_out) {
         for (int s = 1; s <= 16 && s <= num_kb; s++) {
             const int per = (num_kb + s - 1) / s;
             if ((num_kb + per - 1) / per != s) continue;  // every split must own >= 1 k-block
-            const int items = tiles * s, waves = (items + sms - 1) / sms;
+            const int items = tiles * s * m_tiles, waves = (items + sms - 1) / sms;
             const double ks = per * 64.0;
             const double kb = (512.0 * ks + 2.0 * bn * ks + 512.0 * bn) / 1024.0;
             const double cost = waves * (300.0 + kb) + 12.0 * s;
@@ -1189,7 +1194,7 @@ static int skinny_gemm(const __nv_bfloat16* A, int B, const __nv_bfloat16* W, in
     g.W = W; g.ldw = K; g.N = N; g.K = K;
     g.epilogue = EPI_F32; g.out = ws.part; g.ldc = N;
     g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * K;
-    pick_tile(K, N, &g.bn, &g.split_k);
+    pick_tile(K, N, B, &g.bn, &g.split_k);
     g.pdl = pdl;
     g.w_kb_major = true;
     g.split_stride = (int64_t)B * N;
@@ -1322,7 +1327,7 @@ int DtwPassWorkspace::reserve(int64_t rows, int d_model) {
     WDR_CUDA_TRY(cudaMalloc(&part, sizeof(float) * M * 4 * d));
     WDR_CUDA_TRY(cudaMalloc(&row_b, sizeof(int32_t) * M));
     WDR_CUDA_TRY(cudaMalloc(&row_pos, sizeof(int32_t) * M));
-    WDR_CUDA_TRY(cudaMalloc(&row_off, sizeof(int32_t) * kDecMaxBatch));
+    WDR_CUDA_TRY(cudaMalloc(&row_off, sizeof(int32_t) * kDecMaxWindows));
     cap_rows = (int64_t)M;
     return WDR_OK;
 }
@@ -1343,8 +1348,8 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
     const WhisperArch& a = ctx->arch;
     const WhisperWeights& w = ctx->w;
     const int d = a.d, H = a.n_head;
-    WDR_REQUIRE(B > 0 && B <= ws.cap_B && B <= kDecMaxBatch, "decoder_dtw_pass: bad batch");
-    std::vector<int32_t> row_b, row_pos, row_off(kDecMaxBatch, 0);
+    WDR_REQUIRE(B > 0 && B <= ws.cap_W && B <= kDecMaxWindows, "decoder_dtw_pass: bad batch");
+    std::vector<int32_t> row_b, row_pos, row_off(kDecMaxWindows, 0);
     int max_T = 0;
     for (int b = 0; b < B; b++) {
         WDR_REQUIRE(T_host[b] >= 0 && T_host[b] <= kDtwpMaxT && T_host[b] <= kDecSeqCap, "decoder_dtw_pass: sequence too long");
@@ -1359,7 +1364,7 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
     const int64_t Mc = pw.cap_rows;
     WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_b, row_b.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
     WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_pos, row_pos.data(), sizeof(int32_t) * M, cudaMemcpyHostToDevice, st));
-    WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_off, row_off.data(), sizeof(int32_t) * kDecMaxBatch, cudaMemcpyHostToDevice, st));
+    WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_off, row_off.data(), sizeof(int32_t) * kDecMaxWindows, cudaMemcpyHostToDevice, st));
     WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors die with this frame
     static DeviceOnce attr_once;
     const int smem_self = (int)sizeof(float) * (2 * kDtwpMaxT * 65 + 8 * 64 + 8 * kDtwpMaxT);

@@ -10,7 +10,13 @@
 
 namespace wdr {
 
-constexpr int kDecMaxBatch = 128;   // windows per decode batch = one 128-row M tile of the tcgen05 GEMM
+// A decode batch has WINDOWS (each owns a cross-KV cache: 245.8 MB for large-v3, so their number is bounded by memory) and ROWS
+// (decoders: greedy = one per window; beam search / best_of = several per window, sharing its cross cache).  Greedy batches are one
+// 128-row M tile of the tcgen05 GEMM; beam batches run up to kDecMaxRows rows (five M tiles) so that the weight-streaming chain is
+// paid once per iteration for all beams of up to 128 windows instead of once per 25 windows.
+constexpr int kDecMaxWindows = 128;
+constexpr int kDecMaxRows = 640;
+constexpr int kDecMaxBatch = kDecMaxRows;  // row capacity of the per-row beam tables
 constexpr int kDecMaxTokens = 224;  // sampled tokens kept per window (n_text_ctx/2)
 constexpr int kDecSeqCap = WDR_TEXT_CTX;
 
@@ -79,7 +85,8 @@ struct DecoderWorkspace {
     int32_t* aw_T = nullptr;
     int32_t* aw_A = nullptr;
     unsigned long long* cross_stats = nullptr;  // [2] dec_cross_attn_kernel: launches, live (launch, window) pairs since the last reset
-    int reserve(const wdr_context* ctx, int B);
+    int cap_W = 0;                     // windows the cross-side buffers (enc_bf16, ckv) hold; cap_B counts ROWS
+    int reserve(const wdr_context* ctx, int windows, int rows = 0);  // rows = 0: one row per window
     void release();
 };
 
@@ -94,7 +101,7 @@ struct DtwPassWorkspace {
     float* part = nullptr;         // [M][4d] GEMM output (fp32)
     int32_t* row_b = nullptr;      // [M] window of each packed row
     int32_t* row_pos = nullptr;    // [M] token position of each packed row
-    int32_t* row_off = nullptr;    // [kDecMaxBatch] first packed row of each window
+    int32_t* row_off = nullptr;    // [kDecMaxWindows] first packed row of each window
     int reserve(int64_t rows, int d_model);
     void release();
 };

@@ -230,7 +230,7 @@ extern "C" int wdr_allgather_embeddings_dev(wdr_dist* d, const float* emb_dev, i
     WDR_REQUIRE(d && n_local >= 0 && D > 0 && (emb_dev || n_local == 0) && out_dev && out_cap_rows >= 0, "bad arguments");
     int rc = ensure_device(d->device);
     if (rc != WDR_OK) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : d->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA: the caller's producer kernels are ordered before the gather
     const int R = d->n_ranks;
     if (R == 1) {
         WDR_REQUIRE(out_cap_rows >= n_local, "output too small");

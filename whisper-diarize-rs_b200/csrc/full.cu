@@ -85,12 +85,14 @@ static void parallel_for(int n, F f) {
     for (auto& t : th) t.join();
 }
 
-// whisper_exp_compute_token_level_timestamps for one segment; st3 = {t_beg, t_last, tid_last}
-static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t t0, int64_t t1, const Vocab& v, const float* energy,
-                                   int n_samples, float thold_pt, float thold_ptsum, int64_t* st3) {
+// whisper_exp_compute_token_level_timestamps for one segment; st3 = {t_beg, t_last, tid_last}.
+// Part 1: everything up to the energy pass (timestamp-token anchors, voice-length split, monotonic fix-up) — scalar logic on the
+// token list alone.  Returns true when the energy pass applies (n >= 2).
+static bool token_level_timestamps_part1(std::vector<wdr_token_data>& tokens, int64_t t0, int64_t t1, const Vocab& v,
+                                         int n_samples, float thold_pt, float thold_ptsum, int64_t* st3) {
     const int n = (int)tokens.size();
-    if (n_samples == 0 || n == 0) return;
-    if (n == 1) { tokens[0].t0 = t0; tokens[0].t1 = t1; return; }
+    if (n_samples == 0 || n == 0) return false;
+    if (n == 1) { tokens[0].t0 = t0; tokens[0].t1 = t1; return false; }
     int64_t &t_beg = st3[0], &t_last = st3[1], &tid_last = st3[2];
     for (int j = 0; j < n; j++) {
         wdr_token_data& tk = tokens[j];
@@ -139,6 +141,13 @@ static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t 
             tokens[j].t1 = std::max(tokens[j].t0, tokens[j].t1);
         }
     }
+    return true;
+}
+
+// Part 2, host form (sequential mode: one long buffer whose energy envelope lives on the host): the energy "VAD" pass.  The
+// batched mode runs the same arithmetic on the device (a5_thold_kernel / a5_adjust_kernel below).
+static void token_level_timestamps_energy(std::vector<wdr_token_data>& tokens, const Vocab& v, const float* energy, int n_samples) {
+    const int n = (int)tokens.size();
     const int hw = WDR_SAMPLE_RATE / 8;
     for (int j = 0; j < n; j++) {
         if (tokens[j].id >= v.eot) continue;
@@ -176,6 +185,118 @@ static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t 
                 tokens[j].t1 = sample_to_timestamp(k);
             }
         }
+    }
+}
+
+static void token_level_timestamps(std::vector<wdr_token_data>& tokens, int64_t t0, int64_t t1, const Vocab& v, const float* energy,
+                                   int n_samples, float thold_pt, float thold_ptsum, int64_t* st3) {
+    if (token_level_timestamps_part1(tokens, t0, t1, v, n_samples, thold_pt, thold_ptsum, st3)) token_level_timestamps_energy(tokens, v, energy, n_samples);
+}
+
+// ---- the energy pass of A.5 on the device (batched mode): the envelope never leaves HBM ----
+// One entry per token of a window's segment: t0 / t1 after part 1 (centiseconds), text != 0 for ids below EOT.
+struct A5Token { int64_t t0, t1; };
+__device__ __forceinline__ int a5_ts_to_sample(int64_t t, int n_samples) {
+    int64_t s = (t * WDR_SAMPLE_RATE) / 100;
+    if (s > n_samples - 1) s = n_samples - 1;
+    if (s < 0) s = 0;
+    return (int)s;
+}
+// thold[j] = 0.5f * (energy[ss0] + ... + energy[ss1 - 1]) / ns, the sum taken sequentially in fp32 exactly as the scalar loop does.
+// One WARP per token: 32 consecutive samples per coalesced load, added in index order through shuffles (same chain of fp32 adds).
+__global__ void __launch_bounds__(256)
+a5_thold_kernel(const A5Token* __restrict__ tok, const uint8_t* __restrict__ is_text, const int32_t* __restrict__ n_tok, const int32_t* __restrict__ n_valid,
+                const float* __restrict__ energy, int64_t energy_stride, float* __restrict__ thold) {
+    const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = n_tok[b], n_samples = n_valid[b];
+    const float* e = energy + (int64_t)b * energy_stride;
+    for (int j = blockIdx.x * (blockDim.x >> 5) + warp; j < n; j += gridDim.x * (blockDim.x >> 5)) {
+        const int64_t o = (int64_t)b * kDecMaxTokens + j;
+        if (!is_text[o]) continue;
+        const int hw = WDR_SAMPLE_RATE / 8;
+        const int s0 = a5_ts_to_sample(tok[o].t0, n_samples), s1 = a5_ts_to_sample(tok[o].t1, n_samples);
+        const int ss0 = max(s0 - hw, 0), ss1 = min(s1 + hw, n_samples), ns = ss1 - ss0;
+        float sum = 0.0f;
+        for (int k0 = ss0; k0 < ss1; k0 += 32) {
+            const int k = k0 + lane;
+            const float x = k < ss1 ? e[k] : 0.0f;
+            const int cnt = min(32, ss1 - k0);
+            for (int l = 0; l < cnt; l++) sum += __shfl_sync(0xffffffffu, x, l);  // every lane carries the same running sum
+        }
+        if (lane == 0) thold[o] = __fdiv_rn(0.5f * sum, (float)ns);
+    }
+}
+// The expand / contract scans of every text token, tokens in order (token j reads token j-1's new t1): one WARP per window,
+// 32 samples per step (ballot finds the first sample that ends the scalar loop), lane 0 holds the state.
+__device__ __forceinline__ int a5_scan_down(const float* e, int k, int stop_at, float thold, bool while_above) {
+    // scalar loop: while (k > stop_at && cond(e[k])) k--   with cond = (e > thold) if while_above else (e < thold)
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        const int i = k - lane;
+        bool ends = true;
+        if (i > stop_at) { const float x = e[i]; ends = while_above ? !(x > thold) : !(x < thold); }
+        const unsigned m = __ballot_sync(0xffffffffu, ends);
+        if (m) return k - (__ffs(m) - 1);
+        k -= 32;
+    }
+}
+__device__ __forceinline__ int a5_scan_up(const float* e, int k, int stop_at, float thold, bool while_above) {
+    // scalar loop: while (k < stop_at && cond(e[k])) k++
+    const int lane = threadIdx.x & 31;
+    while (true) {
+        const int i = k + lane;
+        bool ends = true;
+        if (i < stop_at) { const float x = e[i]; ends = while_above ? !(x > thold) : !(x < thold); }
+        const unsigned m = __ballot_sync(0xffffffffu, ends);
+        if (m) return k + (__ffs(m) - 1);
+        k += 32;
+    }
+}
+__global__ void __launch_bounds__(32)
+a5_adjust_kernel(A5Token* __restrict__ tok, const uint8_t* __restrict__ is_text, const int32_t* __restrict__ n_tok, const int32_t* __restrict__ n_valid,
+                 const float* __restrict__ energy, int64_t energy_stride, const float* __restrict__ thold_all) {
+    const int b = blockIdx.x;
+    const int n = n_tok[b], n_samples = n_valid[b];
+    if (n < 2 || n_samples <= 0) return;
+    const float* e = energy + (int64_t)b * energy_stride;
+    A5Token* t = tok + (int64_t)b * kDecMaxTokens;
+    const int hw = WDR_SAMPLE_RATE / 8;
+    for (int j = 0; j < n; j++) {
+        if (!is_text[(int64_t)b * kDecMaxTokens + j]) continue;  // warp-uniform
+        int64_t tj0 = t[j].t0, tj1 = t[j].t1;
+        int s0 = a5_ts_to_sample(tj0, n_samples), s1 = a5_ts_to_sample(tj1, n_samples);
+        const int ns = min(s1 + hw, n_samples) - max(s0 - hw, 0);
+        const float thold = thold_all[(int64_t)b * kDecMaxTokens + j];
+        {
+            int k = s0;
+            if (e[k] > thold && j > 0) {
+                k = a5_scan_down(e, k, 0, thold, true);            // while (k > 0 && e[k] > thold) k--
+                tj0 = (100ll * k) / WDR_SAMPLE_RATE;
+                const int64_t prev_t1 = t[j - 1].t1;
+                if (tj0 < prev_t1) tj0 = prev_t1;
+                else s0 = k;
+            } else {
+                k = a5_scan_up(e, k, s1, thold, false);            // while (e[k] < thold && k < s1) k++
+                s0 = k;
+                tj0 = (100ll * k) / WDR_SAMPLE_RATE;
+            }
+        }
+        {
+            int k = s1;
+            if (e[k] > thold) {
+                k = a5_scan_up(e, k, n_samples - 1, thold, true);  // while (k < n_samples - 1 && e[k] > thold) k++
+                tj1 = (100ll * k) / WDR_SAMPLE_RATE;
+                if (j < ns - 1 && j + 1 < n && tj1 > t[j + 1].t0) tj1 = t[j + 1].t0;
+                else s1 = k;
+            } else {
+                k = a5_scan_down(e, k, s0, thold, false);          // while (e[k] < thold && k > s0) k--
+                s1 = k;
+                tj1 = (100ll * k) / WDR_SAMPLE_RATE;
+            }
+        }
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) { t[j].t0 = tj0; t[j].t1 = tj1; }
+        __syncwarp();
     }
 }
 
@@ -520,10 +641,10 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     cudaStream_t s = st->stream;
     int rc;
     const int beam_K = (p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1;  // rows per window of the decode batch
-    WDR_REQUIRE(B * beam_K <= kDecMaxBatch, "windows x beams exceeds the 128-row decode batch");
+    WDR_REQUIRE(B <= kDecMaxWindows && B * beam_K <= kDecMaxRows, "windows x beams exceeds the decode batch (128 windows, 640 rows)");
     const int fb_Kd = std::max(1, p.greedy_best_of);  // decoders per window of a fallback pass (temperature > 0)
-    const int fb_rows = (p.temperature_inc > 0.0f || p.temperature > 0.0f) ? std::min(B, kDecMaxBatch / fb_Kd) * fb_Kd : 0;
-    if ((rc = ws.reserve(ctx, std::max(std::max(B * beam_K, B), fb_rows))) != WDR_OK) return rc;
+    const int fb_rows = (p.temperature_inc > 0.0f || p.temperature > 0.0f) ? std::min(B, kDecMaxRows / fb_Kd) * fb_Kd : 0;
+    if ((rc = ws.reserve(ctx, B, std::max(std::max(B * beam_K, B), fb_rows))) != WDR_OK) return rc;
     // ---- n_valid on the device ----
     if ((rc = grow_dev(&fs.nvalid_dev, &fs.nvalid_cap, (size_t)B)) != WDR_OK) return rc;
     std::vector<int32_t> nv(B);
@@ -539,19 +660,12 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         if ((rc = encoder_forward(ctx, st->enc, sw->mel_dev, sw->n_len, sw->seek, sw->max_dev, 0, 1, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
     } else if ((rc = encode_chunks<In>(ctx, st->enc, pcm_dev, chunk_stride, fs.nvalid_dev, B, nullptr, ws.enc_bf16, s, &st->prof)) != WDR_OK) return rc;
     // ---- energy for the token-timestamp heuristic (D2H overlaps the decode) ----
+    // The envelope stays in HBM: the energy pass of A.5 runs on the device (a5_thold_kernel / a5_adjust_kernel) after the decode.
     if (p.token_timestamps && !sw) {
         if ((rc = grow_dev(&fs.energy_dev, &fs.energy_cap, (size_t)B * WDR_CHUNK_SAMPLES)) != WDR_OK) return rc;
-        if ((rc = grow_pinned(&fs.energy_host, &fs.energy_host_cap, (size_t)B * WDR_CHUNK_SAMPLES)) != WDR_OK) return rc;
         ProfScope ps(&st->prof, KC_OTHER, s);
         energy_kernel<In><<<dim3(256, B), 256, 0, s>>>(pcm_dev, chunk_stride, fs.nvalid_dev, WDR_CHUNK_SAMPLES, 32, fs.energy_dev, WDR_CHUNK_SAMPLES);
         WDR_LAUNCH_CHECK();
-        WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy, s));
-        WDR_CUDA_TRY(cudaStreamWaitEvent(st->copy_stream, fs.ev_energy, 0));
-        for (int b = 0; b < B; b++)
-            if (nv[b] > 0)
-                WDR_CUDA_TRY(cudaMemcpyAsync(fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, fs.energy_dev + (size_t)b * WDR_CHUNK_SAMPLES,
-                                             sizeof(float) * nv[b], cudaMemcpyDeviceToHost, st->copy_stream));
-        WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy_done, st->copy_stream));
     }
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[1], s));
     WDR_CUDA_TRY(cudaMemsetAsync(ws.cross_stats, 0, sizeof(unsigned long long) * 2, s));
@@ -653,7 +767,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         prompt = build_prompt(temps[it] < 0.5f);
         n_prompt = (int)prompt.size();
         fill_seq();
-        const int per_pass = kDecMaxBatch / ladder_Kd;
+        const int per_pass = kDecMaxRows / ladder_Kd;
         for (size_t o = 0; o < list.size(); o += per_pass) {
             std::vector<int> sub(list.begin() + o, list.begin() + std::min(list.size(), o + per_pass));
             for (int b : sub) {
@@ -765,7 +879,6 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     }
     WDR_CUDA_TRY(cudaStreamSynchronize(s));
     const double t_h1 = now_ms();
-    if (p.token_timestamps && !sw) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
     const double t_h2 = now_ms();
 
     struct Pending { int seg; int b; int n_frames; std::vector<int32_t> dtw_seq; int sot_len; };
@@ -775,15 +888,15 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
     // The heuristic token timestamps scan ~1e6 energy samples per window on the host, as whisper.cpp does: ~2 ms per
     // window.  Windows are independent, so the jobs run on a few host threads, and they run AFTER the DTW pass / DTW kernels have
     // been queued so that the GPU works underneath them.
+    // Batched mode: part 1 of A.5 (scalar logic on the token list) runs on the host right where the segment is assembled; its energy
+    // pass is queued on the device (the envelope never leaves HBM) and the adjusted t0 / t1 come back with the DTW paths.
+    // Sequential mode (one long buffer, envelope on the host, timestamp state carried across windows): host code.
+    std::vector<int> a5_seg(B, -1);   // window -> result segment whose tokens went to the device
+    std::vector<int32_t> a5_n(B, 0);
     auto run_post = [&]() {
         parallel_for((int)post.size(), [&](int i) {
             ResultSegment& seg = st->results[post[i].seg];
-            const int b = post[i].b;
-            if (p.token_timestamps) {
-                int64_t st3[3] = {0, 0, 0};
-                if (sw) token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, sw->energy_host, sw->n_samples, p.thold_pt, p.thold_ptsum, sw->st3);
-                else token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, fs.energy_host + (size_t)b * WDR_CHUNK_SAMPLES, nv[b], p.thold_pt, p.thold_ptsum, st3);
-            }
+            if (p.token_timestamps && sw) token_level_timestamps(seg.tokens, seg.t0, seg.t1, v, sw->energy_host, sw->n_samples, p.thold_pt, p.thold_ptsum, sw->st3);
             seg.token_text.reserve(seg.tokens.size());
             for (auto& t : seg.tokens) seg.token_text.push_back(token_text(v, t.id));
         });
@@ -825,8 +938,16 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                 seg.no_speech_prob = w.no_speech_prob;
                 seg.tokens = cur;
                 st->results.push_back(std::move(seg));
-                post.push_back({(int)st->results.size() - 1, b});  // token timestamps + token strings: after the DTW launches
+                post.push_back({(int)st->results.size() - 1, b});  // token strings (and, in sequential mode, token timestamps): after the DTW launches
                 ci.n_segments = 1;
+                if (p.token_timestamps && !sw) {
+                    ResultSegment& rs = st->results.back();
+                    int64_t st3[3] = {0, 0, 0};
+                    if (token_level_timestamps_part1(rs.tokens, rs.t0, rs.t1, v, nv[b], p.thold_pt, p.thold_ptsum, st3)) {
+                        a5_seg[b] = (int)st->results.size() - 1;
+                        a5_n[b] = (int32_t)std::min<size_t>(rs.tokens.size(), kDecMaxTokens);
+                    }
+                }
                 if (ctx->dtw_enabled) {
                     Pending pd;
                     pd.seg = (int)st->results.size() - 1;
@@ -845,7 +966,58 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         }
         st->chunk_info.push_back(ci);
     }
-    if (dbg_time) fprintf(stderr, "[wdr] results D2H+sync %.1f ms, energy wait %.1f ms, host assembly %.1f ms\n", t_h1 - t_h0, t_h2 - t_h1, now_ms() - t_h2);
+    if (dbg_time) fprintf(stderr, "[wdr] results D2H+sync %.1f ms, host assembly %.1f ms\n", t_h1 - t_h0, now_ms() - t_h2);
+    // ---- energy pass of A.5 on the device ----
+    bool a5_any = false;
+    for (int b = 0; b < B; b++) a5_any |= a5_n[b] > 0;
+    if (a5_any) {
+        const size_t n_tok = (size_t)B * kDecMaxTokens;
+        if ((rc = grow_dev(&fs.a5_tok_dev, &fs.a5_tok_cap, n_tok * 2)) != WDR_OK) return rc;
+        if ((rc = grow_pinned(&fs.a5_tok_host, &fs.a5_tok_host_cap, n_tok * 2)) != WDR_OK) return rc;
+        if ((rc = grow_dev(&fs.a5_text_dev, &fs.a5_text_cap, n_tok)) != WDR_OK) return rc;
+        if ((rc = grow_pinned(&fs.a5_text_host, &fs.a5_text_host_cap, n_tok)) != WDR_OK) return rc;
+        if ((rc = grow_dev(&fs.a5_n_dev, &fs.a5_n_cap, (size_t)B)) != WDR_OK) return rc;
+        if ((rc = grow_pinned(&fs.a5_n_host, &fs.a5_n_host_cap, (size_t)B)) != WDR_OK) return rc;
+        if ((rc = grow_dev(&fs.a5_thold_dev, &fs.a5_thold_cap, n_tok)) != WDR_OK) return rc;
+        A5Token* th = reinterpret_cast<A5Token*>(fs.a5_tok_host);
+        for (int b = 0; b < B; b++) {
+            fs.a5_n_host[b] = a5_n[b];
+            if (a5_n[b] <= 0) continue;
+            const ResultSegment& rs = st->results[a5_seg[b]];
+            for (int j = 0; j < a5_n[b]; j++) {
+                th[(size_t)b * kDecMaxTokens + j] = A5Token{rs.tokens[j].t0, rs.tokens[j].t1};
+                fs.a5_text_host[(size_t)b * kDecMaxTokens + j] = rs.tokens[j].id < v.eot ? 1 : 0;
+            }
+        }
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_tok_dev, fs.a5_tok_host, sizeof(int64_t) * n_tok * 2, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_text_dev, fs.a5_text_host, n_tok, cudaMemcpyHostToDevice, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_n_dev, fs.a5_n_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+        {
+            ProfScope ps(&st->prof, KC_OTHER, s);
+            a5_thold_kernel<<<dim3(8, B), 256, 0, s>>>(reinterpret_cast<const A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev,
+                                                       WDR_CHUNK_SAMPLES, fs.a5_thold_dev);
+            WDR_LAUNCH_CHECK();
+        }
+        {
+            ProfScope ps(&st->prof, KC_OTHER, s);
+            a5_adjust_kernel<<<B, 32, 0, s>>>(reinterpret_cast<A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev, WDR_CHUNK_SAMPLES,
+                                              fs.a5_thold_dev);
+            WDR_LAUNCH_CHECK();
+        }
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_tok_host, fs.a5_tok_dev, sizeof(int64_t) * n_tok * 2, cudaMemcpyDeviceToHost, s));
+    }
+    auto apply_a5 = [&]() {  // after the stream has drained: the adjusted times go into the result tokens
+        if (!a5_any) return;
+        const A5Token* th = reinterpret_cast<const A5Token*>(fs.a5_tok_host);
+        for (int b = 0; b < B; b++) {
+            if (a5_n[b] <= 0) continue;
+            ResultSegment& rs = st->results[a5_seg[b]];
+            for (int j = 0; j < a5_n[b]; j++) {
+                rs.tokens[j].t0 = th[(size_t)b * kDecMaxTokens + j].t0;
+                rs.tokens[j].t1 = th[(size_t)b * kDecMaxTokens + j].t1;
+            }
+        }
+    };
     // ---- DTW token timestamps: teacher-forced pass capturing the alignment heads, then cost + wavefront + backtrace ----
     if (!pend.empty()) {
         const int Ha = (int)ctx->aheads.size();
@@ -951,6 +1123,8 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         }
     }
     run_post();  // no DTW: nothing was queued above
+    if (a5_any) WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    apply_a5();
     {   // cross-attention launch / live-window counters of this group (stepwise DTW passes included)
         if (!fs.cross_stats_host) WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.cross_stats_host), sizeof(unsigned long long) * 2));
         WDR_CUDA_TRY(cudaMemcpyAsync(fs.cross_stats_host, ws.cross_stats, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, s));
@@ -1082,7 +1256,8 @@ static int full_range(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         WDR_CUDA_TRY(cudaEventCreateWithFlags(&fs.ev_h2d, cudaEventDisableTiming));
         WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.done_host), sizeof(int32_t)));
     }
-    const int group_max = kDecMaxBatch / ((p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1);
+    // windows per decode group: bounded by the cross-KV memory (128 windows) and by the row capacity (windows x beams <= 640)
+    const int group_max = std::min(kDecMaxWindows, kDecMaxRows / ((p.strategy == WDR_SAMPLING_BEAM_SEARCH && p.beam_size > 1) ? p.beam_size : 1));
     for (int c0 = c_begin; c0 < c_end; c0 += group_max) {
         const int B = std::min(group_max, c_end - c0);
         if (pcm_on_device) {
@@ -1349,7 +1524,7 @@ extern "C" float wdr_full_get_chunk_temperature_from_state(wdr_state* st, int i)
 extern "C" int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* st, const float* enc, int n_chunks, const int32_t* seq_in, int n_seq,
                                          float* logits_out, float* aheads_out) {
     clear_error();
-    WDR_REQUIRE(ctx && st && st->ctx == ctx && seq_in && n_chunks > 0 && n_chunks <= kDecMaxBatch && n_seq > 0 && n_seq <= kDecSeqCap, "bad arguments");
+    WDR_REQUIRE(ctx && st && st->ctx == ctx && seq_in && n_chunks > 0 && n_chunks <= kDecMaxWindows && n_seq > 0 && n_seq <= kDecSeqCap, "bad arguments");
     WDR_REQUIRE(!aheads_out || !ctx->aheads.empty(), "alignment heads need a context created with dtw_token_timestamps");
     int rc = ensure_device(ctx->device);
     if (rc != WDR_OK) return rc;
@@ -1367,7 +1542,7 @@ extern "C" int wdr_decode_teacher_forced(wdr_context* ctx, wdr_state* st, const 
         if ((rc = decoder_cross_kv(ctx, ws, B, s, &st->prof)) != WDR_OK) return rc;
         WDR_CUDA_TRY(cudaStreamSynchronize(s));
     }
-    WDR_REQUIRE(ws.cap_B >= B, "no encoder output in the state for that many windows");
+    WDR_REQUIRE(ws.cap_W >= B, "no encoder output in the state for that many windows");
     const Vocab v = make_vocab(nv);
     std::vector<int32_t> seq((size_t)B * kDecSeqCap, v.eot);
     for (int b = 0; b < B; b++)

@@ -45,6 +45,21 @@ struct FullScratch {
     size_t dtw_wins_cap = 0;
     int32_t* dtw_path_host = nullptr;  // pinned
     size_t dtw_path_host_cap = 0;
+    // the energy pass of A.5 on the device: per-token (t0, t1) in / out, text flags, token counts, thresholds
+    int64_t* a5_tok_dev = nullptr;
+    size_t a5_tok_cap = 0;
+    int64_t* a5_tok_host = nullptr;   // pinned
+    size_t a5_tok_host_cap = 0;
+    uint8_t* a5_text_dev = nullptr;
+    size_t a5_text_cap = 0;
+    uint8_t* a5_text_host = nullptr;  // pinned
+    size_t a5_text_host_cap = 0;
+    int32_t* a5_n_dev = nullptr;
+    size_t a5_n_cap = 0;
+    int32_t* a5_n_host = nullptr;     // pinned
+    size_t a5_n_host_cap = 0;
+    float* a5_thold_dev = nullptr;
+    size_t a5_thold_cap = 0;
     float* lp_dev = nullptr;       // [rows][ldv] processed log-probabilities of a sampling pass (temperature > 0, greedy strategy)
     size_t lp_dev_cap = 0;
     float* lp_host = nullptr;      // pinned
@@ -58,6 +73,10 @@ struct FullScratch {
     int64_t cross_launches = 0, cross_live = 0;      // dec_cross_attn_kernel launches / live (launch, window) pairs of the last full call
     void release() {
         cudaFree(pcm_dev); cudaFree(nvalid_dev); cudaFree(energy_dev); cudaFree(dtw_x); cudaFree(dtw_stat); cudaFree(dtw_path); cudaFree(dtw_wins); cudaFree(lp_dev);
+        cudaFree(a5_tok_dev); cudaFree(a5_text_dev); cudaFree(a5_n_dev); cudaFree(a5_thold_dev);
+        if (a5_tok_host) cudaFreeHost(a5_tok_host);
+        if (a5_text_host) cudaFreeHost(a5_text_host);
+        if (a5_n_host) cudaFreeHost(a5_n_host);
         if (lp_host) cudaFreeHost(lp_host);
         if (energy_host) cudaFreeHost(energy_host);
         if (dtw_path_host) cudaFreeHost(dtw_path_host);
