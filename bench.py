@@ -465,7 +465,55 @@ def run_pipeline(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
     value = world * seconds * args.steps / dt
+    # one more step with a CUDA-event pair around every launch of the transcription state (wdr_profile_*): the kernel-class times
+    # behind the roofline block (the encoder dominates large-v3-turbo: 32 encoder layers against 4 decoder layers)
+    st.profile_enable(True)
+    st.profile_collect()
+    step()
+    torch.cuda.synchronize()
+    prof = st.profile_collect()
+    st.profile_enable(False)
     if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        fl = flops_per_window(arch)
+        n_win = out["speech"]  # every speech segment is its own 30 s whisper window
+        roofline, kern = None, {}
+        if prof["gemm"]["ms"] > 0:
+            ach = (fl["gemm_enc"] + fl["cross_kv"]) * n_win / (prof["gemm"]["ms"] / 1e3) / 1e12
+            roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05): encoder + cross-KV GEMMs of the transcription stage", "achieved": ach, "peak": tf_peak,
+                        "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "windows": n_win,
+                        "share_of_profiled_kernel_time": prof["gemm"]["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9),
+                        "peak_source": "measured (MEASURED_PEAKS.json: sustained bf16)" if peaks else "fallback (B200_PROFILING.md)"}
+        for name, v in prof.items():
+            if v["ms"] > 0:
+                kern[name] = {"ms_per_step": v["ms"], "launches_per_step": v["records"]}
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            # the CPU port on a bounded sample of the same recording: VAD on 10 s, 1 segmentation window, 2 speech segments through
+            # mel + encoder + decode + DTW (large-v3-turbo) and the ResNet34 embedding; extrapolated per stage to the recording
+            from oracle import vad as OV
+            threads = claim_cpu_threads()
+            x10 = pcm[:160000].astype(np.float32) / np.float32(32768.0)
+            t = time.perf_counter(); OV.silero_probs(x10, OV.vad_weights(1234)); t_vad = (time.perf_counter() - t) / 10.0
+            t_seg, t_emb = diar_cpu(pcm, 1, 2)
+            port = CpuPort(arch, "transcribe")
+            win = np.zeros((2, 480000), np.int16)
+            take = [s_ for s_ in seg.get_segments(pcm)][:2]
+            for i_, s_ in enumerate(take):
+                win[i_, : min(len(s_["samples"]), 480000)] = s_["samples"][:480000]
+            _, t_asr, _ = port.run(win, max(1, len(take)))
+            t_asr /= max(1, len(take))
+            frames = sum(max(0, 1 + (len(s_["samples"]) - 400) // 160) for s_ in seg.get_segments(pcm))
+            est = seconds * t_vad + (seconds / 10.0) * t_seg + n_win * t_asr + frames * t_emb
+            cpu = {"value": seconds / est, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                   "sample": f"VAD on 10 s ({t_vad * 1e3:.1f} ms per audio-second), 1 segmentation window ({t_seg:.2f} s), {len(take)} speech segments through "
+                             f"mel + encoder + decode + DTW ({t_asr:.1f} s each) and 2 x 3 s embeddings ({t_emb * 1e3:.2f} ms per fbank frame), extrapolated to "
+                             f"{seconds:.0f} s of audio, {n_win} speech segments, {frames} fbank frames; oracle/*.py + oracle/wdr_oracle*.c"}
         line = {"metric": "RTFx VAD + diarization + transcribe", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16/f32", "data": "synthetic",
                 "config": {"workload": f"{arch} transcribe + diarization + Silero VAD of a {args.minutes} min 4-speaker synthetic recording per GPU through the "
@@ -476,7 +524,7 @@ def run_pipeline(args):
                            "l2": "each step streams the whole recording's activations (> 126 MB L2)"},
                 "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": out["pcm_bytes"], "d2h_bytes_per_step": None,
                         "api": "host.vad_get_segments + Segmenter.get_segments + host.run_transcription_pipeline_sharded + host.format_cues"},
-                "gpu_launches": int(launches), "clocks": clocks, "stages_last_step": out["stages"], "roofline": None, "cpu_baseline": None}
+                "gpu_launches": int(launches), "clocks": clocks, "stages_last_step": out["stages"], "roofline": roofline, "kernels": kern, "cpu_baseline": cpu}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

