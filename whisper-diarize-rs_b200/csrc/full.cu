@@ -5,6 +5,7 @@
 // Device work: log-mel -> encoder -> cross-KV -> greedy decode (decoder.cu) -> DTW pass (teacher-forced decoder steps that
 // capture the alignment heads, dtw.cu).  Host work (scalar, data dependent, restated from SURVEY A.4-A.6): segment assembly,
 // whisper_exp_compute_token_level_timestamps, stamping t_dtw from the DTW path.
+#include <limits.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -203,7 +204,8 @@ __device__ __forceinline__ int a5_ts_to_sample(int64_t t, int n_samples) {
     return (int)s;
 }
 // thold[j] = 0.5f * (energy[ss0] + ... + energy[ss1 - 1]) / ns, the sum taken sequentially in fp32 exactly as the scalar loop does.
-// One WARP per token: 32 consecutive samples per coalesced load, added in index order through shuffles (same chain of fp32 adds).
+// One WARP per token: 32 consecutive samples per coalesced load (the next chunk is requested before the current one is added), added
+// in index order through shuffles — the same chain of fp32 adds.
 __global__ void __launch_bounds__(256)
 a5_thold_kernel(const A5Token* __restrict__ tok, const uint8_t* __restrict__ is_text, const int32_t* __restrict__ n_tok, const int32_t* __restrict__ n_valid,
                 const float* __restrict__ energy, int64_t energy_stride, float* __restrict__ thold) {
@@ -217,52 +219,69 @@ a5_thold_kernel(const A5Token* __restrict__ tok, const uint8_t* __restrict__ is_
         const int s0 = a5_ts_to_sample(tok[o].t0, n_samples), s1 = a5_ts_to_sample(tok[o].t1, n_samples);
         const int ss0 = max(s0 - hw, 0), ss1 = min(s1 + hw, n_samples), ns = ss1 - ss0;
         float sum = 0.0f;
+        float x = (ss0 + lane < ss1) ? e[ss0 + lane] : 0.0f;
         for (int k0 = ss0; k0 < ss1; k0 += 32) {
-            const int k = k0 + lane;
-            const float x = k < ss1 ? e[k] : 0.0f;
+            const int kn = k0 + 32 + lane;
+            const float xn = kn < ss1 ? e[kn] : 0.0f;  // in flight under the adds below
             const int cnt = min(32, ss1 - k0);
-            for (int l = 0; l < cnt; l++) sum += __shfl_sync(0xffffffffu, x, l);  // every lane carries the same running sum
+            if (cnt == 32) {
+#pragma unroll
+                for (int l = 0; l < 32; l++) sum += __shfl_sync(0xffffffffu, x, l);  // every lane carries the same running sum
+            } else {
+                for (int l = 0; l < cnt; l++) sum += __shfl_sync(0xffffffffu, x, l);
+            }
+            x = xn;
         }
         if (lane == 0) thold[o] = __fdiv_rn(0.5f * sum, (float)ns);
     }
 }
-// The expand / contract scans of every text token, tokens in order (token j reads token j-1's new t1): one WARP per window,
-// 32 samples per step (ballot finds the first sample that ends the scalar loop), lane 0 holds the state.
-__device__ __forceinline__ int a5_scan_down(const float* e, int k, int stop_at, float thold, bool while_above) {
-    // scalar loop: while (k > stop_at && cond(e[k])) k--   with cond = (e > thold) if while_above else (e < thold)
-    const int lane = threadIdx.x & 31;
+
+// The expand / contract scans of every text token, tokens in order (token j reads token j-1's new t1): one CTA per window.  A scan
+// `while (k > stop && cond(e[k])) k--` (or the upward form) may run over hundreds of thousands of samples when a stretch of speech
+// stays above its local threshold, so the CTA examines kA5Step samples per step — 16 independent loads per thread, one block-wide
+// minimum — and returns the first sample (in scan order) that ends the scalar loop: the same k the scalar code stops at.
+constexpr int kA5Threads = 256, kA5PerThread = 16, kA5Step = kA5Threads * kA5PerThread;
+template <bool DOWN>
+__device__ __forceinline__ int a5_scan(const float* __restrict__ e, int k, int stop_at, float thold, bool while_above, int* s_first) {
+    const int tid = threadIdx.x;
     while (true) {
-        const int i = k - lane;
-        bool ends = true;
-        if (i > stop_at) { const float x = e[i]; ends = while_above ? !(x > thold) : !(x < thold); }
-        const unsigned m = __ballot_sync(0xffffffffu, ends);
-        if (m) return k - (__ffs(m) - 1);
-        k -= 32;
+        if (tid == 0) *s_first = INT_MAX;
+        __syncthreads();
+        float x[kA5PerThread];
+        const int p0 = tid * kA5PerThread;  // position in scan order of this thread's first sample
+#pragma unroll
+        for (int j = 0; j < kA5PerThread; j++) {
+            const int i = DOWN ? k - (p0 + j) : k + (p0 + j);
+            const bool inside = DOWN ? i > stop_at : i < stop_at;
+            x[j] = inside ? e[i] : (while_above ? -INFINITY : INFINITY);  // outside the range the scalar loop has ended: cond is false
+        }
+        int first = INT_MAX;
+#pragma unroll
+        for (int j = kA5PerThread - 1; j >= 0; j--) {
+            const bool ends = while_above ? !(x[j] > thold) : !(x[j] < thold);
+            if (ends) first = p0 + j;
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        if ((tid & 31) == 0 && first != INT_MAX) atomicMin(s_first, first);
+        __syncthreads();
+        const int f = *s_first;
+        __syncthreads();  // everyone has read it before the next step resets it
+        if (f != INT_MAX) return DOWN ? k - f : k + f;
+        k = DOWN ? k - kA5Step : k + kA5Step;
     }
 }
-__device__ __forceinline__ int a5_scan_up(const float* e, int k, int stop_at, float thold, bool while_above) {
-    // scalar loop: while (k < stop_at && cond(e[k])) k++
-    const int lane = threadIdx.x & 31;
-    while (true) {
-        const int i = k + lane;
-        bool ends = true;
-        if (i < stop_at) { const float x = e[i]; ends = while_above ? !(x > thold) : !(x < thold); }
-        const unsigned m = __ballot_sync(0xffffffffu, ends);
-        if (m) return k + (__ffs(m) - 1);
-        k += 32;
-    }
-}
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kA5Threads)
 a5_adjust_kernel(A5Token* __restrict__ tok, const uint8_t* __restrict__ is_text, const int32_t* __restrict__ n_tok, const int32_t* __restrict__ n_valid,
                  const float* __restrict__ energy, int64_t energy_stride, const float* __restrict__ thold_all) {
+    __shared__ int s_first;
     const int b = blockIdx.x;
     const int n = n_tok[b], n_samples = n_valid[b];
     if (n < 2 || n_samples <= 0) return;
     const float* e = energy + (int64_t)b * energy_stride;
     A5Token* t = tok + (int64_t)b * kDecMaxTokens;
     const int hw = WDR_SAMPLE_RATE / 8;
-    for (int j = 0; j < n; j++) {
-        if (!is_text[(int64_t)b * kDecMaxTokens + j]) continue;  // warp-uniform
+    for (int j = 0; j < n; j++) {  // block-uniform control flow throughout
+        if (!is_text[(int64_t)b * kDecMaxTokens + j]) continue;
         int64_t tj0 = t[j].t0, tj1 = t[j].t1;
         int s0 = a5_ts_to_sample(tj0, n_samples), s1 = a5_ts_to_sample(tj1, n_samples);
         const int ns = min(s1 + hw, n_samples) - max(s0 - hw, 0);
@@ -270,13 +289,13 @@ a5_adjust_kernel(A5Token* __restrict__ tok, const uint8_t* __restrict__ is_text,
         {
             int k = s0;
             if (e[k] > thold && j > 0) {
-                k = a5_scan_down(e, k, 0, thold, true);            // while (k > 0 && e[k] > thold) k--
+                k = a5_scan<true>(e, k, 0, thold, true, &s_first);              // while (k > 0 && e[k] > thold) k--
                 tj0 = (100ll * k) / WDR_SAMPLE_RATE;
                 const int64_t prev_t1 = t[j - 1].t1;
                 if (tj0 < prev_t1) tj0 = prev_t1;
                 else s0 = k;
             } else {
-                k = a5_scan_up(e, k, s1, thold, false);            // while (e[k] < thold && k < s1) k++
+                k = a5_scan<false>(e, k, s1, thold, false, &s_first);           // while (e[k] < thold && k < s1) k++
                 s0 = k;
                 tj0 = (100ll * k) / WDR_SAMPLE_RATE;
             }
@@ -284,19 +303,19 @@ a5_adjust_kernel(A5Token* __restrict__ tok, const uint8_t* __restrict__ is_text,
         {
             int k = s1;
             if (e[k] > thold) {
-                k = a5_scan_up(e, k, n_samples - 1, thold, true);  // while (k < n_samples - 1 && e[k] > thold) k++
+                k = a5_scan<false>(e, k, n_samples - 1, thold, true, &s_first);  // while (k < n_samples - 1 && e[k] > thold) k++
                 tj1 = (100ll * k) / WDR_SAMPLE_RATE;
                 if (j < ns - 1 && j + 1 < n && tj1 > t[j + 1].t0) tj1 = t[j + 1].t0;
                 else s1 = k;
             } else {
-                k = a5_scan_down(e, k, s0, thold, false);          // while (e[k] < thold && k > s0) k--
+                k = a5_scan<true>(e, k, s0, thold, false, &s_first);            // while (e[k] < thold && k > s0) k--
                 s1 = k;
                 tj1 = (100ll * k) / WDR_SAMPLE_RATE;
             }
         }
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) { t[j].t0 = tj0; t[j].t1 = tj1; }
-        __syncwarp();
+        __syncthreads();
+        if (threadIdx.x == 0) { t[j].t0 = tj0; t[j].t1 = tj1; }
+        __syncthreads();  // token j + 1 reads t[j].t1
     }
 }
 
@@ -1000,7 +1019,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         }
         {
             ProfScope ps(&st->prof, KC_OTHER, s);
-            a5_adjust_kernel<<<B, 32, 0, s>>>(reinterpret_cast<A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev, WDR_CHUNK_SAMPLES,
+            a5_adjust_kernel<<<B, kA5Threads, 0, s>>>(reinterpret_cast<A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev, WDR_CHUNK_SAMPLES,
                                               fs.a5_thold_dev);
             WDR_LAUNCH_CHECK();
         }
