@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */,
-                     const int32_t* __restrict__ anc /* beam search: [448][anc_ld] row that holds position t of this row's history; null = own row */,
+                     const int32_t* __restrict__ anc /* beam search: [rows][anc_ld = 448] row that holds position t of this row's history; null = own row */,
                      int anc_ld) {
     __shared__ __align__(16) float qs[kSelfMaxHeadsPerCta][64];
     __shared__ float ps[kSelfMaxHeadsPerCta][kDecSeqCap];
@@ -205,7 +205,8 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     float* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
     // beam search: position t < pos of this row's history lives in the cache of row anc[t][b] (the beam it descended from)
     const int64_t row_step = (int64_t)n_heads * kDecSeqCap * 64;
-#define WDR_ANC_ROW(t) (ANC ? (int64_t)(anc[(int64_t)(t) * anc_ld + b] - b) * row_step : (int64_t)0)
+    // the table is row-major [row][448]: a warp's 32 consecutive positions are one coalesced 128-byte read
+#define WDR_ANC_ROW(t) (ANC ? (int64_t)(anc[(int64_t)b * anc_ld + (t)] - b) * row_step : (int64_t)0)
     float* q = qs[warp];
     float* p = ps[warp];
 #pragma unroll
@@ -1064,13 +1065,14 @@ dec_topk_kernel(const float* __restrict__ logits, int64_t ldv, const BeamRow* __
 
 // ancestry update after a beam reassignment at sampling position i (0-based): new row b continues old row parent[b];
 // the history position that old row just wrote (pos_last) now belongs to parent[b], earlier ones follow the parent's ancestry.
+// Tables are row-major [row][ld = 448]: one CTA per new row copies its parent's history (coalesced) and appends the parent itself.
 __global__ void beam_anc_kernel(const int32_t* __restrict__ anc_old, int32_t* __restrict__ anc_new, const int32_t* __restrict__ parent, int n_rows, int ld,
                                 int pos_last) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x;
     if (b >= n_rows) return;
     const int pb = parent[b];
-    for (int t = 0; t < pos_last; t++) anc_new[(int64_t)t * ld + b] = anc_old[(int64_t)t * ld + pb];
-    anc_new[(int64_t)pos_last * ld + b] = pb;
+    for (int t = threadIdx.x; t < pos_last; t += blockDim.x) anc_new[(int64_t)b * ld + t] = anc_old[(int64_t)pb * ld + t];
+    if (threadIdx.x == 0) anc_new[(int64_t)b * ld + pos_last] = pb;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1250,7 +1252,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             WDR_CUDA_TRY(launch_kernel(beam ? dec_self_attn_kernel<true> : dec_self_attn_kernel<false>, dim3(H / hpc, B), dim3(hpc * 32), 0, st, pdl, ws.part,
                                        sg.splits, sg.split_stride, e.b_qkv, ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d,
                                        ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att, (int64_t)ws.cap_B * d, win, t_limit,
-                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecMaxBatch));
+                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecSeqCap));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
@@ -1452,7 +1454,7 @@ int decoder_topk(const wdr_context* ctx, DecoderWorkspace& ws, int R, const Samp
 int decoder_beam_reorder(DecoderWorkspace& ws, int R, int pos_last, cudaStream_t st) {
     int32_t* old_t = ws.beam_anc_cur;
     int32_t* new_t = old_t == ws.beam_anc[0] ? ws.beam_anc[1] : ws.beam_anc[0];
-    beam_anc_kernel<<<(R + 127) / 128, 128, 0, st>>>(old_t, new_t, ws.beam_parent, R, kDecMaxBatch, pos_last);
+    beam_anc_kernel<<<R, 128, 0, st>>>(old_t, new_t, ws.beam_parent, R, kDecSeqCap, pos_last);
     WDR_LAUNCH_CHECK();
     ws.beam_anc_cur = new_t;
     return WDR_OK;

@@ -63,7 +63,7 @@ struct DecoderWorkspace {
     DecWinState* win = nullptr;        // [B]
     int32_t* done_count = nullptr;
     int32_t* pos_dev = nullptr;        // device-resident step counter read by the graph-replayed decode step
-    // beam search: ancestry tables [448][128] (double-buffered), per-row limits / history summaries / candidates / parents
+    // beam search: ancestry tables [rows][448] (row-major, double-buffered), per-row limits / history summaries / candidates / parents
     int32_t* beam_anc[2] = {nullptr, nullptr};
     int32_t* beam_anc_cur = nullptr;
     int32_t* beam_limit = nullptr;

@@ -470,8 +470,8 @@ static int beam_decode(wdr_context* ctx, wdr_state* st, DecoderWorkspace& ws, co
         rowwin[r] = wins[r / K];
     }
     std::vector<int32_t> anc((size_t)kDecSeqCap * kDecMaxBatch);
-    for (int t = 0; t < kDecSeqCap; t++)
-        for (int b = 0; b < kDecMaxBatch; b++) anc[(size_t)t * kDecMaxBatch + b] = b;
+    for (int b = 0; b < kDecMaxBatch; b++)  // row-major [row][448]: every position of a fresh row lives in the row itself
+        for (int t = 0; t < kDecSeqCap; t++) anc[(size_t)b * kDecSeqCap + t] = b;
     std::vector<int32_t> limit(kDecMaxBatch, 0);
     for (int r = 0; r < R; r++) limit[r] = win[wins[r / K]].completed ? 0 : 1 << 30;
     ws.beam_anc_cur = ws.beam_anc[0];
@@ -685,6 +685,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         ProfScope ps(&st->prof, KC_OTHER, s);
         energy_kernel<In><<<dim3(256, B), 256, 0, s>>>(pcm_dev, chunk_stride, fs.nvalid_dev, WDR_CHUNK_SAMPLES, 32, fs.energy_dev, WDR_CHUNK_SAMPLES);
         WDR_LAUNCH_CHECK();
+        WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy, s));  // the A.5 kernels run on the side stream, under the DTW pass
     }
     WDR_CUDA_TRY(cudaEventRecord(fs.ev_phase[1], s));
     WDR_CUDA_TRY(cudaMemsetAsync(ws.cross_stats, 0, sizeof(unsigned long long) * 2, s));
@@ -1008,22 +1009,26 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
                 fs.a5_text_host[(size_t)b * kDecMaxTokens + j] = rs.tokens[j].id < v.eot ? 1 : 0;
             }
         }
-        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_tok_dev, fs.a5_tok_host, sizeof(int64_t) * n_tok * 2, cudaMemcpyHostToDevice, s));
-        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_text_dev, fs.a5_text_host, n_tok, cudaMemcpyHostToDevice, s));
-        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_n_dev, fs.a5_n_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, s));
+        // side stream: these kernels touch a few SMs' worth of threads and no tensor-core resources, so they run under the DTW pass
+        cudaStream_t cs = st->copy_stream;
+        WDR_CUDA_TRY(cudaStreamWaitEvent(cs, fs.ev_energy, 0));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_tok_dev, fs.a5_tok_host, sizeof(int64_t) * n_tok * 2, cudaMemcpyHostToDevice, cs));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_text_dev, fs.a5_text_host, n_tok, cudaMemcpyHostToDevice, cs));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_n_dev, fs.a5_n_host, sizeof(int32_t) * B, cudaMemcpyHostToDevice, cs));
         {
-            ProfScope ps(&st->prof, KC_OTHER, s);
-            a5_thold_kernel<<<dim3(8, B), 256, 0, s>>>(reinterpret_cast<const A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev,
+            ProfScope ps(&st->prof, KC_OTHER, cs);
+            a5_thold_kernel<<<dim3(8, B), 256, 0, cs>>>(reinterpret_cast<const A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev,
                                                        WDR_CHUNK_SAMPLES, fs.a5_thold_dev);
             WDR_LAUNCH_CHECK();
         }
         {
-            ProfScope ps(&st->prof, KC_OTHER, s);
-            a5_adjust_kernel<<<B, kA5Threads, 0, s>>>(reinterpret_cast<A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev, WDR_CHUNK_SAMPLES,
+            ProfScope ps(&st->prof, KC_OTHER, cs);
+            a5_adjust_kernel<<<B, kA5Threads, 0, cs>>>(reinterpret_cast<A5Token*>(fs.a5_tok_dev), fs.a5_text_dev, fs.a5_n_dev, fs.nvalid_dev, fs.energy_dev, WDR_CHUNK_SAMPLES,
                                               fs.a5_thold_dev);
             WDR_LAUNCH_CHECK();
         }
-        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_tok_host, fs.a5_tok_dev, sizeof(int64_t) * n_tok * 2, cudaMemcpyDeviceToHost, s));
+        WDR_CUDA_TRY(cudaMemcpyAsync(fs.a5_tok_host, fs.a5_tok_dev, sizeof(int64_t) * n_tok * 2, cudaMemcpyDeviceToHost, cs));
+        WDR_CUDA_TRY(cudaEventRecord(fs.ev_energy_done, cs));
     }
     auto apply_a5 = [&]() {  // after the stream has drained: the adjusted times go into the result tokens
         if (!a5_any) return;
@@ -1142,7 +1147,7 @@ static int full_group(wdr_context* ctx, wdr_state* st, const wdr_full_params& p,
         }
     }
     run_post();  // no DTW: nothing was queued above
-    if (a5_any) WDR_CUDA_TRY(cudaStreamSynchronize(s));
+    if (a5_any) WDR_CUDA_TRY(cudaEventSynchronize(fs.ev_energy_done));
     apply_a5();
     {   // cross-attention launch / live-window counters of this group (stepwise DTW passes included)
         if (!fs.cross_stats_host) WDR_CUDA_TRY(cudaMallocHost(reinterpret_cast<void**>(&fs.cross_stats_host), sizeof(unsigned long long) * 2));
