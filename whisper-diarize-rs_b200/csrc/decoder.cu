@@ -25,7 +25,6 @@
 #include "common.cuh"
 #include "decoder.cuh"
 #include "gemm.cuh"
-#include "sm100.cuh"
 
 namespace wdr {
 
@@ -185,16 +184,18 @@ constexpr int kSelfMaxHeadsPerCta = 5;
 // ANC = beam search / fallback rows (history read through the ancestry table); the greedy instantiation carries none of that code:
 // with a run-time `anc ? ... : 0` in the loops the greedy decode lost 160 ms per 120-window step (loads no longer batched).
 template <bool ANC>
-__global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
+__global__ void __launch_bounds__(kBeamMax * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */,
                      const int32_t* __restrict__ anc /* beam search: [rows][anc_ld = 448] row that holds position t of this row's history; null = own row */,
-                     int anc_ld) {
-    __shared__ __align__(16) float qs[kSelfMaxHeadsPerCta][64];
-    __shared__ float ps[kSelfMaxHeadsPerCta][kDecSeqCap];
+                     int anc_ld, int rows_per_cta /* beam search: > 0 = the CTA's warps are the K rows of ONE (window, head) — beams share most of their
+                     history, so the K / V rows one warp pulls are L1 hits for its siblings; 0 = the CTA's warps are heads of one row */) {
+    __shared__ __align__(16) float qs[kBeamMax][64];
+    __shared__ float ps[kBeamMax][kDecSeqCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hh = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
+    const int hh = (ANC && rows_per_cta > 0) ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + warp);
+    const int b = (ANC && rows_per_cta > 0) ? (int)blockIdx.y * rows_per_cta + warp : (int)blockIdx.y;
     pdl_launch_dependents();
     pdl_wait();
     pos = load_pos(pos_ptr, pos);
@@ -529,186 +530,6 @@ dec_cross_attn_rows_kernel(const float* __restrict__ part, int n_splits, int64_t
         for (int wv = 0; wv < 8; wv++) a += red[(wv * NQ + qi) * 64 + c];
         store_split(att, lo_off, (int64_t)(b0 + qi) * d + hh * 64 + c, a);
     }
-}
-
-// Version 2 of the rows kernel: the V block (a contiguous 192 KB stream per (window, head)) goes through a 4-stage (3 for seven / eight rows per window) shared-memory
-// ring filled by 1-D bulk copies (cp.async.bulk, one elected thread, mbarrier completion).  The first four 16 KB chunks are
-// requested at kernel entry, so V streams in under the scores and softmax phases, and the P V loop reads shared memory instead of
-// waiting on a chain of dependent global loads (version 1 kept eight 128-byte rows per warp in flight: 52 % of the HBM roofline at
-// 120 windows).  Every warp accumulates exactly the keys it did before, in the same order, and the partial sums are combined in
-// the same order: results are bit-identical to version 1.
-constexpr int kRowsChunk = 128;   // V rows per ring stage (16 KB)
-template <int NQP>
-__global__ void __launch_bounds__(256, 2)
-dec_cross_attn_rows2_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
-                            const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off, int pos,
-                            const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window, int K) {
-    extern __shared__ __align__(128) unsigned char rows2_smem[];
-    constexpr int kRowsStages = NQP == 4 ? 3 : 4;  // two CTAs per SM must fit: 4 stages up to six rows per window, 3 for seven / eight
-    constexpr int NQ = 2 * NQP;
-    constexpr int kPS = kT + 4;
-    __nv_bfloat16* vring = reinterpret_cast<__nv_bfloat16*>(rows2_smem);                       // [stages][128 rows][64]
-    float* qs = reinterpret_cast<float*>(rows2_smem + kRowsStages * kRowsChunk * 128);          // [NQP][64 columns][2 queries]
-    float* p = qs + NQP * 128;                                                                  // [NQ][kT + 4]; reused as the reduction buffer
-    __shared__ __align__(8) uint64_t bar_full[kRowsStages];
-    __shared__ __align__(8) uint64_t bar_empty[kRowsStages];
-    const int hh = blockIdx.x, w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b0 = w * K;
-    bool any = false;
-    for (int i = 0; i < K; i++) any |= pos < t_limit[b0 + i];
-    if (!any) return;
-    const __nv_bfloat16* Kb = ckv + ((int64_t)row_window[b0] * gridDim.x + hh) * 2 * kT * 64;
-    const __nv_bfloat16* Vb = Kb + kT * 64;
-    constexpr int n_chunks = (kT + kRowsChunk - 1) / kRowsChunk;
-    if (tid == 0) {
-        for (int s = 0; s < kRowsStages; s++) { sm100::mbar_init(&bar_full[s], 1); sm100::mbar_init(&bar_empty[s], 8); }
-        sm100::mbar_fence_init();
-        for (int c = 0; c < kRowsStages && c < n_chunks; c++) {  // V starts streaming before the scores are computed
-            const int rows = min(kRowsChunk, kT - c * kRowsChunk);
-            sm100::mbar_arrive_expect_tx(&bar_full[c], rows * 128);
-            sm100::bulk_load_1d(vring + (size_t)c * kRowsChunk * 64, Vb + (size_t)c * kRowsChunk * 64, rows * 128, &bar_full[c]);
-        }
-    }
-    for (int e = tid; e < NQP * 128; e += 256) {
-        const int qp = e >> 7, c = (e & 127) >> 1, qi = 2 * qp + (e & 1);
-        qs[e] = qi < K ? (part_sum(part, n_splits, split_stride, (int64_t)(b0 + qi) * d + hh * 64 + c) + b_q[hh * 64 + c]) * 0.125f : 0.0f;
-    }
-    for (int e = tid; e < NQ * 4; e += 256) p[(e >> 2) * kPS + kT + (e & 3)] = 0.0f;
-    __syncthreads();
-    // ---- scores: two key rows per thread, columns outer, query pairs inner (as version 1) ----
-    for (int t = tid; t < kT; t += 512) {
-        const int t1 = t + 256;
-        const bool has1 = t1 < kT;
-        uint4 ka[8], kb[8];
-        {
-            const uint4* kra = reinterpret_cast<const uint4*>(Kb + (int64_t)t * 64);
-            const uint4* krb = reinterpret_cast<const uint4*>(Kb + (int64_t)(has1 ? t1 : t) * 64);
-#pragma unroll
-            for (int c8 = 0; c8 < 8; c8++) { ka[c8] = __ldg(kra + c8); kb[c8] = __ldg(krb + c8); }
-        }
-        float2 a0[NQP], a1[NQP];
-#pragma unroll
-        for (int qp = 0; qp < NQP; qp++) { a0[qp] = make_float2(0.0f, 0.0f); a1[qp] = make_float2(0.0f, 0.0f); }
-#pragma unroll
-        for (int c8 = 0; c8 < 8; c8++) {
-            const __nv_bfloat162* ea = reinterpret_cast<const __nv_bfloat162*>(&ka[c8]);
-            const __nv_bfloat162* eb = reinterpret_cast<const __nv_bfloat162*>(&kb[c8]);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float2 fa = __bfloat1622float2(ea[j]), fb = __bfloat1622float2(eb[j]);
-#pragma unroll
-                for (int qp = 0; qp < NQP; qp++) {
-                    const float4 f = *reinterpret_cast<const float4*>(qs + qp * 128 + (c8 * 4 + j) * 4);
-                    a0[qp] = __ffma2_rn(make_float2(f.x, f.y), make_float2(fa.x, fa.x), a0[qp]);
-                    a0[qp] = __ffma2_rn(make_float2(f.z, f.w), make_float2(fa.y, fa.y), a0[qp]);
-                    a1[qp] = __ffma2_rn(make_float2(f.x, f.y), make_float2(fb.x, fb.x), a1[qp]);
-                    a1[qp] = __ffma2_rn(make_float2(f.z, f.w), make_float2(fb.y, fb.y), a1[qp]);
-                }
-            }
-        }
-#pragma unroll
-        for (int qp = 0; qp < NQP; qp++) {
-            p[(2 * qp) * kPS + t] = a0[qp].x;
-            p[(2 * qp + 1) * kPS + t] = a0[qp].y;
-            if (has1) {
-                p[(2 * qp) * kPS + t1] = a1[qp].x;
-                p[(2 * qp + 1) * kPS + t1] = a1[qp].y;
-            }
-        }
-    }
-    __syncthreads();
-    // ---- softmax: warp i = row i ----
-    if (warp < K) {
-        float* pr = p + warp * kPS;
-        float mx = -INFINITY;
-        for (int t = lane; t < kT; t += 32) mx = fmaxf(mx, pr[t]);
-        mx = warp_max(mx);
-        float sum = 0.0f;
-        for (int t = lane; t < kT; t += 32) {
-            const float e = expf(pr[t] - mx);
-            pr[t] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        for (int t = lane; t < kT; t += 32) pr[t] *= inv;
-    }
-    __syncthreads();
-    // ---- P V from the ring: chunk c = keys [128 c, 128 c + 128); warp w takes the key groups it took in version 1
-    //      (t8 = 8 w + 64 i: two groups of eight keys per chunk), lane = column pair ----
-    float2 acc[NQ];
-#pragma unroll
-    for (int qi = 0; qi < NQ; qi++) acc[qi] = make_float2(0.0f, 0.0f);
-    for (int c = 0; c < n_chunks; c++) {
-        const int s = c % kRowsStages;
-        const uint32_t ph = (uint32_t)(c / kRowsStages) & 1u;
-        sm100::mbar_wait(&bar_full[s], ph);
-        const __nv_bfloat16* vs = vring + (size_t)s * kRowsChunk * 64;
-#pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int r0 = half * 64 + warp * 8;      // row inside the chunk
-            const int t8 = c * kRowsChunk + r0;        // key index
-            if (t8 < kT) {                             // warp-uniform
-                const bool second = t8 + 4 < kT;
-                float2 v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++)
-                    v[j] = (j < 4 || second) ? __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vs + (size_t)(r0 + j) * 64 + 2 * lane)) : make_float2(0.0f, 0.0f);
-#pragma unroll
-                for (int g4 = 0; g4 < 2; g4++) {
-                    if (g4 == 1 && !second) break;
-#pragma unroll
-                    for (int qi = 0; qi < NQ; qi++) {
-                        const float4 pv = *reinterpret_cast<const float4*>(p + qi * kPS + t8 + 4 * g4);
-                        acc[qi] = __ffma2_rn(make_float2(pv.x, pv.x), v[4 * g4], acc[qi]);
-                        acc[qi] = __ffma2_rn(make_float2(pv.y, pv.y), v[4 * g4 + 1], acc[qi]);
-                        acc[qi] = __ffma2_rn(make_float2(pv.z, pv.z), v[4 * g4 + 2], acc[qi]);
-                        acc[qi] = __ffma2_rn(make_float2(pv.w, pv.w), v[4 * g4 + 3], acc[qi]);
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        if (lane == 0) sm100::mbar_arrive(&bar_empty[s]);  // this warp is done with the stage
-        if (tid == 0 && c + kRowsStages < n_chunks) {      // refill it with chunk c + stages once every warp has released it
-            sm100::mbar_wait(&bar_empty[s], ph);
-            const int cn = c + kRowsStages;
-            const int rows = min(kRowsChunk, kT - cn * kRowsChunk);
-            sm100::mbar_arrive_expect_tx(&bar_full[s], rows * 128);
-            sm100::bulk_load_1d(vring + (size_t)s * kRowsChunk * 64, Vb + (size_t)cn * kRowsChunk * 64, rows * 128, &bar_full[s]);
-        }
-    }
-    __syncthreads();  // all warps are done reading p
-    float* red = p;   // [8][NQ][64]
-#pragma unroll
-    for (int qi = 0; qi < NQ; qi++) {
-        red[(warp * NQ + qi) * 64 + 2 * lane] = acc[qi].x;
-        red[(warp * NQ + qi) * 64 + 2 * lane + 1] = acc[qi].y;
-    }
-    __syncthreads();
-    for (int e = tid; e < K * 64; e += 256) {
-        const int qi = e >> 6, c = e & 63;
-        if (pos >= t_limit[b0 + qi]) continue;
-        float a = 0.0f;
-#pragma unroll
-        for (int wv = 0; wv < 8; wv++) a += red[(wv * NQ + qi) * 64 + c];
-        store_split(att, lo_off, (int64_t)(b0 + qi) * d + hh * 64 + c, a);
-    }
-}
-
-template <int NQP>
-static cudaError_t launch_cross_rows2(int H, int nW, int K, cudaStream_t st, const float* part, int n_splits, int64_t split_stride, const float* b_q,
-                                      const __nv_bfloat16* ckv, int d, __nv_bfloat16* att, int64_t lo_off, int pos, const int32_t* t_limit,
-                                      const int32_t* row_window) {
-    constexpr int kRowsStages = NQP == 4 ? 3 : 4;
-    const size_t smem = (size_t)kRowsStages * kRowsChunk * 128 + sizeof(float) * ((size_t)NQP * 128 + (size_t)2 * NQP * (kT + 4));
-    static DeviceOnce attr_once;
-    {
-        const cudaError_t e = per_device_once(attr_once, [&] { return cudaFuncSetAttribute(dec_cross_attn_rows2_kernel<NQP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
-        if (e != cudaSuccess) return e;
-    }
-    dec_cross_attn_rows2_kernel<NQP><<<dim3(H, nW), 256, smem, st>>>(part, n_splits, split_stride, b_q, ckv, d, att, lo_off, pos, t_limit, row_window, K);
-    return cudaGetLastError();
 }
 
 template <int NQP>
@@ -1430,10 +1251,14 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             ProfScope ps(prof, KC_DECODER, st);
             int hpc = kSelfMaxHeadsPerCta;
             while (H % hpc) hpc--;
-            WDR_CUDA_TRY(launch_kernel(beam ? dec_self_attn_kernel<true> : dec_self_attn_kernel<false>, dim3(H / hpc, B), dim3(hpc * 32), 0, st, pdl, ws.part,
+            // beam search: one CTA = the K rows of a (window, head) (siblings share history -> L1 hits); otherwise hpc heads of one row
+            const int rpc = (beam && ws.beam_K > 1 && ws.beam_K <= kBeamMax && B % ws.beam_K == 0) ? ws.beam_K : 0;
+            const dim3 sgrid = rpc ? dim3(H, B / rpc) : dim3(H / hpc, B);
+            const dim3 sblock = rpc ? dim3(rpc * 32) : dim3(hpc * 32);
+            WDR_CUDA_TRY(launch_kernel(beam ? dec_self_attn_kernel<true> : dec_self_attn_kernel<false>, sgrid, sblock, 0, st, pdl, ws.part,
                                        sg.splits, sg.split_stride, e.b_qkv, ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d,
                                        ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att, (int64_t)ws.cap_B * d, win, t_limit,
-                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecSeqCap));
+                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecSeqCap, rpc));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
@@ -1450,9 +1275,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             if (beam && ws.beam_K > 1 && B % ws.beam_K == 0 && !pos_on_device && !no_rows) {
                 const int nW = B / ws.beam_K, nqp = (ws.beam_K + 1) / 2;
                 cudaError_t ce;
-                static const bool rows_v1 = getenv("WDR_ROWS_V1") != nullptr;  // A/B knob: version 1 (V rows straight from global memory)
-#define WDR_ROWS(N) (rows_v1 ? launch_cross_rows<N>(H, nW, ws.beam_K, st, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d, pos, t_limit, ws.beam_rowwin) \
-                             : launch_cross_rows2<N>(H, nW, ws.beam_K, st, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d, pos, t_limit, ws.beam_rowwin))
+#define WDR_ROWS(N) launch_cross_rows<N>(H, nW, ws.beam_K, st, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d, pos, t_limit, ws.beam_rowwin)
                 ce = nqp == 1 ? WDR_ROWS(1) : nqp == 2 ? WDR_ROWS(2) : nqp == 3 ? WDR_ROWS(3) : WDR_ROWS(4);
 #undef WDR_ROWS
                 WDR_CUDA_TRY(ce);
