@@ -142,6 +142,11 @@ int wdr_emb_compute_batch_i16(wdr_emb* m, const int16_t* pcm, const int64_t* seg
 int wdr_emb_compute_batch_i16_dev(wdr_emb* m, const int16_t* pcm_dev, const int64_t* seg_offset_host, int n_segments, float* out_dev,
                                   int32_t* status_host, void* stream);
 double wdr_emb_last_flops(wdr_emb* m);  /* algorithmic conv FLOPs (2*M*N*K) of the last compute call */
+/* Measurement aid: with profiling on, every tcgen05 GEMM and every im2col gather of a compute call is bracketed by a CUDA-event pair on
+ * the launching stream; wdr_emb_last_kernel_ms returns their summed device times for the last call (bench.py quotes the GEMMs alone
+ * against the tensor roofline). */
+int wdr_emb_profile(wdr_emb* m, int enable);
+int wdr_emb_last_kernel_ms(wdr_emb* m, double* gemm_ms, double* gather_ms);
 
 /* ---- get_signal_energy (whisper.cpp, used by the token-timestamp heuristic) --------- */
 int wdr_signal_energy(const float* pcm, int n, int half_window, float* out);

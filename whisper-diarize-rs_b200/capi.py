@@ -232,6 +232,8 @@ def load():
     L.wdr_emb_compute_batch_i16_dev.argtypes = [C.c_void_p, C.c_void_p, i64p, C.c_int, C.c_void_p, i32p, C.c_void_p]
     L.wdr_emb_last_flops.argtypes = [C.c_void_p]
     L.wdr_emb_last_flops.restype = C.c_double
+    L.wdr_emb_profile.argtypes = [C.c_void_p, C.c_int]
+    L.wdr_emb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.wdr_full_get_phase_ms.argtypes = [C.c_void_p, C.POINTER(C.c_double), i32p]
     L.wdr_spk_init.restype = C.c_void_p
     L.wdr_spk_init.argtypes = [C.c_size_t]
@@ -946,6 +948,15 @@ class EmbeddingExtractor:
 
     def last_flops(self):
         return float(load().wdr_emb_last_flops(self._h))
+
+    def profile(self, on=True):
+        _check(load().wdr_emb_profile(self._h, int(on)))
+
+    def last_kernel_ms(self):
+        """(tcgen05 GEMM ms, im2col gather ms) of the last compute call (profiling on)."""
+        a, b = C.c_double(0), C.c_double(0)
+        _check(load().wdr_emb_last_kernel_ms(self._h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
 
 
 DIST_ID_BYTES = 128

@@ -184,18 +184,16 @@ constexpr int kSelfMaxHeadsPerCta = 5;
 // ANC = beam search / fallback rows (history read through the ancestry table); the greedy instantiation carries none of that code:
 // with a run-time `anc ? ... : 0` in the loops the greedy decode lost 160 ms per 120-window step (loads no longer batched).
 template <bool ANC>
-__global__ void __launch_bounds__(kBeamMax * 32)
+__global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */,
                      const int32_t* __restrict__ anc /* beam search: [rows][anc_ld = 448] row that holds position t of this row's history; null = own row */,
-                     int anc_ld, int rows_per_cta /* beam search: > 0 = the CTA's warps are the K rows of ONE (window, head) — beams share most of their
-                     history, so the K / V rows one warp pulls are L1 hits for its siblings; 0 = the CTA's warps are heads of one row */) {
-    __shared__ __align__(16) float qs[kBeamMax][64];
-    __shared__ float ps[kBeamMax][kDecSeqCap];
+                     int anc_ld) {
+    __shared__ __align__(16) float qs[kSelfMaxHeadsPerCta][64];
+    __shared__ float ps[kSelfMaxHeadsPerCta][kDecSeqCap];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hh = (ANC && rows_per_cta > 0) ? (int)blockIdx.x : (int)(blockIdx.x * (blockDim.x >> 5) + warp);
-    const int b = (ANC && rows_per_cta > 0) ? (int)blockIdx.y * rows_per_cta + warp : (int)blockIdx.y;
+    const int hh = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
     pdl_launch_dependents();
     pdl_wait();
     pos = load_pos(pos_ptr, pos);
@@ -207,8 +205,14 @@ dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split
     float* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
     // beam search: position t < pos of this row's history lives in the cache of row anc[t][b] (the beam it descended from)
     const int64_t row_step = (int64_t)n_heads * kDecSeqCap * 64;
-    // the table is row-major [row][448]: a warp's 32 consecutive positions are one coalesced 128-byte read
-#define WDR_ANC_ROW(t) (ANC ? (int64_t)(anc[(int64_t)b * anc_ld + (t)] - b) * row_step : (int64_t)0)
+    // The table is row-major [row][448].  This row's ancestry is copied into shared memory once (coalesced), so that the scores and
+    // P V loops below pay ONE global round trip per step (the K / V row), not two dependent ones (table entry, then the row).
+    __shared__ int32_t as_[ANC ? kSelfMaxHeadsPerCta : 1][ANC ? kDecSeqCap : 1];
+    if (ANC) {
+        for (int t = lane; t < pos; t += 32) as_[warp][t] = anc[(int64_t)b * anc_ld + t];
+        __syncwarp();
+    }
+#define WDR_ANC_ROW(t) (ANC ? (int64_t)(as_[warp][(t)] - b) * row_step : (int64_t)0)
     float* q = qs[warp];
     float* p = ps[warp];
 #pragma unroll
@@ -1251,14 +1255,12 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             ProfScope ps(prof, KC_DECODER, st);
             int hpc = kSelfMaxHeadsPerCta;
             while (H % hpc) hpc--;
-            // beam search: one CTA = the K rows of a (window, head) (siblings share history -> L1 hits); otherwise hpc heads of one row
-            const int rpc = (beam && ws.beam_K > 1 && ws.beam_K <= kBeamMax && B % ws.beam_K == 0) ? ws.beam_K : 0;
-            const dim3 sgrid = rpc ? dim3(H, B / rpc) : dim3(H / hpc, B);
-            const dim3 sblock = rpc ? dim3(rpc * 32) : dim3(hpc * 32);
-            WDR_CUDA_TRY(launch_kernel(beam ? dec_self_attn_kernel<true> : dec_self_attn_kernel<false>, sgrid, sblock, 0, st, pdl, ws.part,
+            // (measured and dropped: one CTA per (window, head) over its K beam rows, so that siblings' shared history hits L1 — 748 vs 766
+            // audio-s/s at beam 5, and the wider launch bounds / shared arrays cost the greedy instantiation 125 ms per step)
+            WDR_CUDA_TRY(launch_kernel(beam ? dec_self_attn_kernel<true> : dec_self_attn_kernel<false>, dim3(H / hpc, B), dim3(hpc * 32), 0, st, pdl, ws.part,
                                        sg.splits, sg.split_stride, e.b_qkv, ws.sk + (size_t)l * ws.cap_B * kDecSeqCap * d,
                                        ws.sv + (size_t)l * ws.cap_B * kDecSeqCap * d, pos_ptr, pos, d, ws.att, (int64_t)ws.cap_B * d, win, t_limit,
-                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecSeqCap, rpc));
+                                       beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecSeqCap));
             WDR_LAUNCH_CHECK();
         }
         if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;

@@ -108,6 +108,7 @@ __global__ void emb_tstp_kernel(const __nv_bfloat16* __restrict__ x, const int32
 
 }  // namespace wdr
 
+namespace wdr { struct EmbProf; }
 using namespace wdr;
 
 struct wdr_emb {
@@ -123,6 +124,8 @@ struct wdr_emb {
     wdr::DevArena io;       // host-pointer API: staged PCM + result embeddings
     wdr::DevArena scratch;  // per-group features, level tables, pooled statistics, embeddings (grow-only)
     double conv_flops = 0.0;  // of the last call (algorithmic, 2*M*N*K)
+    wdr::EmbProf* prof = nullptr;          // wdr_emb_profile
+    double gemm_ms = 0.0, gather_ms = 0.0; // of the last profiled call
     int emb_dim = wdr::kEmbDimDefault;  // rows of the embedding layer (runtime: read from the ONNX file when one is loaded)
 };
 
@@ -185,11 +188,37 @@ static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, i
     return WDR_OK;
 }
 
+// Measurement aid (wdr_emb_profile): a CUDA-event pair on the launching stream around every GEMM / every im2col gather of a call,
+// so that bench.py can quote the tcgen05 GEMMs of this stage against the tensor roofline without the gathers, fbank and copies.
+struct EmbProf {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm, gather;
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+};
+static EmbProf* g_emb_prof = nullptr;  // set for the duration of one emb_forward (single caller per model, &mut self upstream)
+struct EmbProfScope {
+    cudaEvent_t a = nullptr, b = nullptr;
+    cudaStream_t st;
+    bool gemm;
+    EmbProfScope(bool is_gemm, cudaStream_t s) : st(s), gemm(is_gemm) {
+        if (g_emb_prof && g_emb_prof->on) { a = g_emb_prof->get(); b = g_emb_prof->get(); cudaEventRecord(a, st); }
+    }
+    ~EmbProfScope() {
+        if (a) { cudaEventRecord(b, st); (gemm ? g_emb_prof->gemm : g_emb_prof->gather).push_back({a, b}); }
+    }
+};
+
 static int emb_gemm(const __nv_bfloat16* A, int64_t rows, const ConvW& c, int epi, const __nv_bfloat16* resid, __nv_bfloat16* out, cudaStream_t st) {
     GemmDesc g;
     g.A = A; g.a_row_stride = c.K; g.rows_per_batch = (int)rows; g.n_batch = 1;
     g.W = c.w; g.ldw = c.K; g.N = c.c_out; g.K = c.K;
     g.epilogue = epi; g.out = out; g.ldc = c.c_out; g.bias = c.b; g.resid_bf16 = resid;
+    EmbProfScope ps(true, st);
     return gemm_bf16(g, st);
 }
 
@@ -255,11 +284,15 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     }
     int rc;
     if ((rc = emb_grow(&m->col, &m->col_cap, col_need)) != WDR_OK) return rc;
+    g_emb_prof = m->prof;
     auto blocks_for = [](int64_t work) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, 148 * 8)); };
     double flops = 0.0;
     // conv1
     {
-        emb_im2col_feats_kernel<<<dim3(blocks_for(lv[0].max_rows()), n), 256, 0, st>>>(feats, d_feat_off, lv[0].d_T, lv[0].d_off, m->col);
+        {
+            EmbProfScope ps(false, st);
+            emb_im2col_feats_kernel<<<dim3(blocks_for(lv[0].max_rows()), n), 256, 0, st>>>(feats, d_feat_off, lv[0].d_T, lv[0].d_off, m->col);
+        }
         WDR_LAUNCH_CHECK();
         if ((rc = emb_gemm(m->col, lv[0].rows(), m->conv1, EPI_BIAS_RELU_BF16, nullptr, m->act[0], st)) != WDR_OK) return rc;
         flops += 2.0 * lv[0].rows() * 32 * 9;
@@ -268,6 +301,7 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     int level = 0;
     auto im2col = [&](const __nv_bfloat16* in, const ConvW& c, int lin, int lout) -> int {
         const int64_t work = (int64_t)lv[lout].max_rows() * c.k * c.k * (c.c_in / 8);
+        EmbProfScope ps(false, st);
         if (c.k == 3)
             emb_im2col_kernel<3><<<dim3(blocks_for(work), n), 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lout].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off,
                                                                            lv[lout].d_off, m->col);
@@ -302,6 +336,18 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     WDR_LAUNCH_CHECK();
     if ((rc = sgemm_nt(stats_buf, kEmbPooled, m->lin_w, kEmbPooled, m->lin_b, out_dev, m->emb_dim, n, m->emb_dim, kEmbPooled, NN_ACT_NONE, st)) != WDR_OK) return rc;
     WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the host-side level tables (async H2D sources) die with this frame
+    g_emb_prof = nullptr;
+    if (m->prof && m->prof->on) {
+        auto total = [](std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& v) {
+            double ms = 0.0;
+            for (auto& e : v) { float t = 0.0f; if (cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess) ms += t; }
+            v.clear();
+            return ms;
+        };
+        m->gemm_ms += total(m->prof->gemm);
+        m->gather_ms += total(m->prof->gather);
+        m->prof->used = 0;
+    }
     m->conv_flops += flops;
     return WDR_OK;
 }
@@ -376,17 +422,36 @@ extern "C" void wdr_emb_free(wdr_emb* m) {
     m->scratch.release();
     m->io.release();
     if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->prof) {
+        for (auto e : m->prof->pool) cudaEventDestroy(e);
+        delete m->prof;
+    }
     delete m;
 }
 
 extern "C" int wdr_emb_dim(wdr_emb* m) { return m ? m->emb_dim : 0; }
 
 extern "C" double wdr_emb_last_flops(wdr_emb* m) { return m ? m->conv_flops : 0.0; }
+extern "C" int wdr_emb_profile(wdr_emb* m, int enable) {
+    clear_error();
+    WDR_REQUIRE(m, "bad arguments");
+    if (!m->prof) m->prof = new EmbProf();
+    m->prof->on = enable != 0;
+    return WDR_OK;
+}
+extern "C" int wdr_emb_last_kernel_ms(wdr_emb* m, double* gemm_ms, double* gather_ms) {
+    clear_error();
+    WDR_REQUIRE(m && gemm_ms && gather_ms, "bad arguments");
+    *gemm_ms = m->gemm_ms;
+    *gather_ms = m->gather_ms;
+    return WDR_OK;
+}
 
 // pcm_dev: device int16, segment s = [seg_off[s], seg_off[s+1]) (host offsets).  out_dev [n][256]; status[s] = 0 or WDR_ERR_TOO_SHORT.
 static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector<int64_t>& seg_off, float* out_dev, int32_t* status, cudaStream_t st) {
     const int n = (int)seg_off.size() - 1;
     m->conv_flops = 0.0;
+    m->gemm_ms = m->gather_ms = 0.0;
     // segments that yield at least one frame, in order, cut into forward groups by total frames
     std::vector<int> live;
     for (int s = 0; s < n; s++) {
