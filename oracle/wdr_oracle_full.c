@@ -12,8 +12,8 @@
  *
  * Precision policy switch `bf16`: 0 = fp32 everywhere (the whisper.cpp-fp32 gold the north-star tolerances refer to);
  * 1 = the storage precision of libwdr_b200's decoder: the encoder output and the cross-KV cache are rounded to bf16 once
- * (whisper.cpp keeps its KV caches in f16); every activation, the self-KV cache and all accumulation stay fp32 (the library
- * carries activations as (hi, lo) bf16 pairs = 16 mantissa bits, see csrc/decoder.cu).
+ * and the self-KV cache to f16 when a position is appended (whisper.cpp keeps both KV caches in f16); every activation and all
+ * accumulation stay fp32 (the library carries activations as (hi, lo) bf16 pairs = 16 mantissa bits, see csrc/decoder.cu).
  */
 #include <math.h>
 #include <stdint.h>
@@ -54,6 +54,19 @@ static inline float bf16r(float x) {
     return x;
 }
 static inline float rnd(const oracle_dec *m, float x) { return m->bf16 ? bf16r(x) : x; }
+/* float -> IEEE binary16 (round-to-nearest-even, overflow to inf, gradual underflow) -> float: what storing into an f16 cache does */
+static inline float f16r(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    const uint32_t a = u & 0x7fffffffu;
+    if (a >= 0x7f800000u) return x;                          /* inf / nan */
+    if (a < 0x38800000u) return rintf(x * 16777216.0f) / 16777216.0f; /* |x| < 2^-14: multiples of 2^-24 (rintf: ties to even) */
+    u = (u + 0xfffu + ((u >> 13) & 1u)) & 0xffffe000u;
+    if ((u & 0x7fffffffu) >= 0x47800000u) u = (u & 0x80000000u) | 0x7f800000u; /* >= 65520 rounds to inf */
+    memcpy(&x, &u, 4);
+    return x;
+}
+static inline float rnd16(const oracle_dec *m, float x) { return m->bf16 ? f16r(x) : x; }
 static inline float gelu_tanh_f(float x) {
     return 0.5f * x * (1.0f + tanhf(0.79788456080286535587989211986876f * x * (1.0f + 0.044715f * x * x)));
 }
@@ -173,6 +186,11 @@ int oracle_dec_step(oracle_dec *m, int token, int pos, float *logits, const int3
         gemv(w[W_QW], w[W_QB], h, q, d, d);
         gemv(w[W_KW], NULL, h, sk + (size_t)pos * d, d, d);
         gemv(w[W_VW], w[W_VB], h, sv + (size_t)pos * d, d, d);
+        if (m->bf16) /* storage mode: the library's self-KV cache is f16 (as whisper.cpp's kv_self is) */
+            for (int i = 0; i < d; i++) {
+                sk[(size_t)pos * d + i] = rnd16(m, sk[(size_t)pos * d + i]);
+                sv[(size_t)pos * d + i] = rnd16(m, sv[(size_t)pos * d + i]);
+            }
         for (int hh = 0; hh < H; hh++) {
             float *s = sc + (size_t)hh * T;
             float mx = -INFINITY;

@@ -75,7 +75,8 @@ def test_large_v3_two_windows_match_oracle(wdr, oracle):
         dec.set_audio(hid[b])
         for i, t in enumerate(seqs[b]):
             lg = dec.step(int(t), i)
-            assert np.abs(lg - logits[b, i]).max() <= 1e-4 * np.abs(lg).max(), (b, i, np.abs(lg - logits[b, i]).max(), np.abs(lg).max())
+            # 5e-4: f16 self-cache rounding boundaries (see test_teacher_forced_logits_and_alignment_heads); fp32-cache builds held 1e-4
+            assert np.abs(lg - logits[b, i]).max() <= 5e-4 * np.abs(lg).max(), (b, i, np.abs(lg - logits[b, i]).max(), np.abs(lg).max())
     # ---- the whole call: greedy ids / segment times / token timestamps / DTW times identical ----
     segs = st.full_batch(pcm, nv)
     by_chunk = {s["chunk"]: s for s in segs}

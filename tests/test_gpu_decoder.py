@@ -48,7 +48,11 @@ def test_teacher_forced_logits_and_alignment_heads(wdr, oracle, arch):
     st = ctx.create_state()
     logits, ah = st.decode_teacher_forced(seqs, enc=enc, want_logits=True, want_aheads=True, n_aheads=len(aheads))
     pw = W.pack_decoder(arch, w)
-    for bf16, tol in ((True, 3e-5), (False, 1e-3)):
+    # Storage mode: 3e-4 of max|logit|.  Both sides round the new k / v to f16 when they enter the self cache (as whisper.cpp's
+    # kv_self does); the library's pre-rounding values differ from the oracle's fp32 ones by ~1e-5 relative (16-bit-mantissa
+    # activations), so a few per cent of the entries fall on the other side of an f16 rounding boundary (one f16 ulp = 5e-4 relative):
+    # measured 8.5e-5 of max|logit| (with the fp32 cache of round 1 it was < 3e-5).  Token identity is asserted elsewhere.
+    for bf16, tol in ((True, 3e-4), (False, 1e-3)):
         for b in range(B):
             dec = oracle.Decoder(arch, pw, bf16=bf16)
             dec.set_audio(enc[b])
@@ -56,7 +60,7 @@ def test_teacher_forced_logits_and_alignment_heads(wdr, oracle, arch):
                 lg, pr = dec.step(int(t), i, aheads=aheads)
                 scale = np.abs(lg).max()
                 assert np.abs(lg - logits[b, i]).max() <= tol * scale, (arch, bf16, b, i)
-                assert np.abs(pr - ah[b, :, i, :]).max() <= (1e-6 if bf16 else 1e-5), (arch, bf16, b, i)
+                assert np.abs(pr - ah[b, :, i, :]).max() <= 1e-5, (arch, bf16, b, i)
             dec.close()
     st.close()
     ctx.close()

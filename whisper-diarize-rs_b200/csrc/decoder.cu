@@ -177,108 +177,178 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
     store_split(h, lo_off, o + 3, c3 * rstd * gg.w + bb.w);
 }
 
-// self-attention at position pos: one WARP per (head, window), blockDim.x / 32 heads per CTA — no block-wide barrier anywhere.
-// part: [S][B][3d] partials of the fused QKV GEMM.  Scores: lane = key position (its 256 B K row against q broadcast from shared
-// memory); softmax by warp shuffles; P V: lane = two columns, V rows stream coalesced, 8 positions in flight per warp.
-constexpr int kSelfMaxHeadsPerCta = 5;
-// ANC = beam search / fallback rows (history read through the ancestry table); the greedy instantiation carries none of that code:
-// with a run-time `anc ? ... : 0` in the loops the greedy decode lost 160 ms per 120-window step (loads no longer batched).
+// self-attention at position pos: one WARP per (head, window), one warp per CTA — no block-wide barrier anywhere.
+// part: [S][B][3d] partials of the fused QKV GEMM.
+//
+// Self cache: f16 (whisper.cpp keeps kv_self in GGML_TYPE_F16 as well), head-major, [window][head] blocks of 448 x 64.  V is
+// row-major [t][64] (128 B rows).  K is stored TRANSPOSED IN BLOCKS OF 32 POSITIONS — [t / 32][c / 8][t % 32][c % 8] — so that
+// "lane = key position" reads of a block are conflict-free 16-byte pieces, in global and in shared memory alike.
+//
+// The kernel is bound by its chain of dependent memory round trips, not by bytes (ncu, large-v3, 120 windows, in-graph): with an fp32
+// cache read straight into registers it took 15 us at pos 3 and 34-40 us at pos 110 (one round trip per 32 keys, then one per 8-16
+// value rows; 212 ms of a 1623 ms decode), and an f16 cache alone changed nothing — under a register budget that keeps all 2400
+// (window, head) warps of a 120-window batch resident, ptxas serialises the "batched" loads.  So the history does not go through
+// registers at all: the warp streams it as 4 KB chunks (32 positions of K, then 32 rows of V) with cp.async into a two-buffer ring
+// in shared memory — requested first thing, before the q / k / v partial sums of the new position are even fetched — and computes
+// each chunk from shared memory.  The new position's k / v never make the global round trip: they are patched into the chunk that
+// holds them.  Scores: lane = key position (one fmaf chain in column order); softmax by warp shuffles; P V: lane = two adjacent
+// columns, one fmaf chain in position order.
+constexpr int kSelfMaxHeadsPerCta = 1;
+__device__ __forceinline__ int64_t self_k_off(int t, int c) { return (int64_t)(t >> 5) * 2048 + (c >> 3) * 256 + (t & 31) * 8 + (c & 7); }
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ANC = beam search / fallback rows (history read through the ancestry table); the greedy instantiation carries none of that code.
 template <bool ANC>
-__global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
+__global__ void __launch_bounds__(32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
-                     float* __restrict__ sk, float* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
+                     __half* __restrict__ sk, __half* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */,
                      const int32_t* __restrict__ anc /* beam search: [rows][anc_ld = 448] row that holds position t of this row's history; null = own row */,
                      int anc_ld) {
-    __shared__ __align__(16) float qs[kSelfMaxHeadsPerCta][64];
-    __shared__ float ps[kSelfMaxHeadsPerCta][kDecSeqCap];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hh = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
+    __shared__ __align__(16) unsigned char ring[2][4096];
+    __shared__ __align__(16) float q[64];
+    __shared__ float p[kDecSeqCap];
+    __shared__ int32_t as_[ANC ? kDecSeqCap : 1];
+    const int lane = threadIdx.x;
+    const int hh = blockIdx.x, b = blockIdx.y;
     pdl_launch_dependents();
     pdl_wait();
     pos = load_pos(pos_ptr, pos);
     if (win && (win[b].completed | win[b].failed)) return;
     if (t_limit && pos >= t_limit[b]) return;
-    // head-major self cache: [window][head][448][64] fp32 — the positions of one (window, head) are one contiguous stream
     const int n_heads = d >> 6;
-    float* K = sk + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
-    float* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
-    // beam search: position t < pos of this row's history lives in the cache of row anc[t][b] (the beam it descended from)
+    __half* K = sk + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
+    __half* V = sv + ((int64_t)b * n_heads + hh) * kDecSeqCap * 64;
+    // beam search: position t < pos of this row's history lives in the cache of row anc[t][b] (the beam it descended from); the
+    // table is row-major [row][448], this row's ancestry is copied into shared memory once (coalesced)
     const int64_t row_step = (int64_t)n_heads * kDecSeqCap * 64;
-    // The table is row-major [row][448].  This row's ancestry is copied into shared memory once (coalesced), so that the scores and
-    // P V loops below pay ONE global round trip per step (the K / V row), not two dependent ones (table entry, then the row).
-    __shared__ int32_t as_[ANC ? kSelfMaxHeadsPerCta : 1][ANC ? kDecSeqCap : 1];
     if (ANC) {
-        for (int t = lane; t < pos; t += 32) as_[warp][t] = anc[(int64_t)b * anc_ld + t];
+        for (int t = lane; t < kDecSeqCap; t += 32) as_[t] = t < pos ? anc[(int64_t)b * anc_ld + t] : b;
         __syncwarp();
     }
-#define WDR_ANC_ROW(t) (ANC ? (int64_t)(as_[warp][(t)] - b) * row_step : (int64_t)0)
-    float* q = qs[warp];
-    float* p = ps[warp];
+#define WDR_ANC_ROW(t) (ANC ? (int64_t)(as_[(t)] - b) * row_step : (int64_t)0)
+    // chunk i of the stream: i < nc -> K block i, else V rows 32 (i - nc) .. + 31 (positions beyond pos are copied too: cache memory
+    // of this (window, head), never used)
+    const int nc = (pos >> 5) + 1;
+    auto issue = [&](int i) {
+        if (i < 2 * nc) {
+            unsigned char* dst = ring[i & 1];
+            if (i < nc) {
+                const int t = 32 * i + lane;
+                const __half* src = K + WDR_ANC_ROW(t) + (int64_t)i * 2048 + lane * 8;
 #pragma unroll
-    for (int e = lane; e < 64; e += 32) {
-        const int64_t base = (int64_t)b * 3 * d + hh * 64 + e;
-        q[e] = part_sum(part, n_splits, split_stride, base) + b_qkv[hh * 64 + e];
-        K[(int64_t)pos * 64 + e] = part_sum(part, n_splits, split_stride, base + d) + b_qkv[d + hh * 64 + e];
-        V[(int64_t)pos * 64 + e] = part_sum(part, n_splits, split_stride, base + 2 * d) + b_qkv[2 * d + hh * 64 + e];
+                for (int c8 = 0; c8 < 8; c8++) cp_async_16(dst + c8 * 512 + lane * 16, src + c8 * 256);
+            } else {
+                const int j = i - nc;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int r = k * 4 + (lane >> 3), t = 32 * j + r;
+                    cp_async_16(dst + r * 128 + (lane & 7) * 16, V + WDR_ANC_ROW(t) + (int64_t)t * 64 + (lane & 7) * 8);
+                }
+            }
+        }
+        cp_async_commit();  // (an empty group when the stream has ended: the wait below always allows exactly one pending group)
+    };
+    issue(0);
+    issue(1);
+    // q / k / v of the new position: all partial loads of a split batch are issued together, summed in split order
+    float qkv[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    {
+        const float* pp = part + (int64_t)b * 3 * d + hh * 64 + lane;
+        for (int s0 = 0; s0 < n_splits; s0 += 4) {
+            float t[4][6];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float* ps = pp + (int64_t)min(s0 + k, n_splits - 1) * split_stride;
+#pragma unroll
+                for (int m = 0; m < 6; m++) t[k][m] = ps[(m >> 1) * d + (m & 1) * 32];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (s0 + k < n_splits) {
+#pragma unroll
+                    for (int m = 0; m < 6; m++) qkv[m] += t[k][m];
+                }
+        }
+    }
+    __half kn[2], vn[2];
+#pragma unroll
+    for (int m = 0; m < 2; m++) {
+        const int e = lane + 32 * m;
+        q[e] = qkv[m] + b_qkv[hh * 64 + e];
+        kn[m] = __float2half_rn(qkv[2 + m] + b_qkv[d + hh * 64 + e]);
+        vn[m] = __float2half_rn(qkv[4 + m] + b_qkv[2 * d + hh * 64 + e]);
+        K[self_k_off(pos, e)] = kn[m];
+        V[(int64_t)pos * 64 + e] = vn[m];
     }
     __syncwarp();
-    float mx = -INFINITY;
-    for (int t = lane; t <= pos; t += 32) {
-        const float4* kr = reinterpret_cast<const float4*>(K + (t < pos ? WDR_ANC_ROW(t) : 0) + (int64_t)t * 64);
-        const float4* qv = reinterpret_cast<const float4*>(q);
-        float4 f[16];
+    const float4* qv = reinterpret_cast<const float4*>(q);
+    float mx = -INFINITY, inv = 0.0f, a0 = 0.0f, a1 = 0.0f;
+    for (int i = 0; i < 2 * nc; i++) {
+        cp_async_wait<1>();
+        __syncwarp();
+        unsigned char* buf = ring[i & 1];
+        if (i == nc - 1 || i == 2 * nc - 1) {  // the chunk that holds the new position: patch k / v in (the copy brought stale memory)
 #pragma unroll
-        for (int c4 = 0; c4 < 16; c4++) f[c4] = kr[c4];
-        float a = 0.0f;
-#pragma unroll
-        for (int c4 = 0; c4 < 16; c4++) {
-            const float4 qq = qv[c4];
-            a = fmaf(qq.x, f[c4].x, a);
-            a = fmaf(qq.y, f[c4].y, a);
-            a = fmaf(qq.z, f[c4].z, a);
-            a = fmaf(qq.w, f[c4].w, a);
+            for (int m = 0; m < 2; m++) {
+                const int e = lane + 32 * m;
+                if (i < nc) *reinterpret_cast<__half*>(buf + (e >> 3) * 512 + (pos & 31) * 16 + (e & 7) * 2) = kn[m];
+                else *reinterpret_cast<__half*>(buf + (pos & 31) * 128 + e * 2) = vn[m];
+            }
+            __syncwarp();
         }
-        a *= 0.125f;
-        p[t] = a;
-        mx = fmaxf(mx, a);
-    }
-    mx = warp_max(mx);
-    float sum = 0.0f;
-    for (int t = lane; t <= pos; t += 32) {
-        const float e = expf(p[t] - mx);
-        p[t] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    const float inv = 1.0f / sum;
-    __syncwarp();
-    float a0 = 0.0f, a1 = 0.0f;
-    const float* vc = V + lane;
-    int t = 0;
-    for (; t + 8 <= pos + 1; t += 8) {
-        float v0[8], v1[8];
+        if (i < nc) {
+            // ---- scores of 32 positions: lane = position ----
+            const int t = 32 * i + lane;
+            float a = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int64_t ro = (t + k) < pos ? WDR_ANC_ROW(t + k) : 0;
-            v0[k] = vc[ro + (int64_t)(t + k) * 64];
-            v1[k] = vc[ro + (int64_t)(t + k) * 64 + 32];
+            for (int c8 = 0; c8 < 8; c8++) {
+                const uint4 u = *reinterpret_cast<const uint4*>(buf + c8 * 512 + lane * 16);
+                const float4 qa = qv[2 * c8], qb = qv[2 * c8 + 1];
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u.z)), f3 = __half22float2(*reinterpret_cast<const __half2*>(&u.w));
+                a = fmaf(qa.x, f0.x, a); a = fmaf(qa.y, f0.y, a); a = fmaf(qa.z, f1.x, a); a = fmaf(qa.w, f1.y, a);
+                a = fmaf(qb.x, f2.x, a); a = fmaf(qb.y, f2.y, a); a = fmaf(qb.z, f3.x, a); a = fmaf(qb.w, f3.y, a);
+            }
+            a *= 0.125f;
+            if (t <= pos) { p[t] = a; mx = fmaxf(mx, a); }
+            if (i == nc - 1) {  // all scores are in: softmax
+                mx = warp_max(mx);
+                __syncwarp();
+                float sum = 0.0f;
+                for (int tt = lane; tt <= pos; tt += 32) {
+                    const float e = expf(p[tt] - mx);
+                    p[tt] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                inv = 1.0f / sum;
+            }
+        } else {
+            // ---- P V over 32 rows: lane = columns 2 lane, 2 lane + 1 ----
+            const int t0 = 32 * (i - nc), n = min(32, pos + 1 - t0);
+            for (int r = 0; r < n; r++) {
+                const float pt = p[t0 + r] * inv;
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(buf + r * 128 + lane * 4));
+                a0 = fmaf(pt, f.x, a0);
+                a1 = fmaf(pt, f.y, a1);
+            }
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const float pt = p[t + k] * inv;
-            a0 = fmaf(pt, v0[k], a0);
-            a1 = fmaf(pt, v1[k], a1);
-        }
+        __syncwarp();  // every lane is done with this buffer before the next chunk lands in it
+        issue(i + 2);
     }
-    for (; t <= pos; t++) {
-        const float pt = p[t] * inv;
-        const int64_t ro = t < pos ? WDR_ANC_ROW(t) : 0;
-        a0 = fmaf(pt, vc[ro + (int64_t)t * 64], a0);
-        a1 = fmaf(pt, vc[ro + (int64_t)t * 64 + 32], a1);
+    {   // (hi, lo) of the two adjacent columns as packed stores
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(a0, a1);
+        const float2 hf = __bfloat1622float2(hi);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(a0 - hf.x, a1 - hf.y);
+        __nv_bfloat16* o = att + (int64_t)b * d + hh * 64 + 2 * lane;
+        *reinterpret_cast<__nv_bfloat162*>(o) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(o + lo_off) = lo;
     }
-    store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane, a0);
-    store_split(att, lo_off, (int64_t)b * d + hh * 64 + lane + 32, a1);
 #undef WDR_ANC_ROW
 }
 
@@ -574,7 +644,7 @@ __global__ void dtwp_embed_kernel(const int32_t* __restrict__ seq, const int32_t
 
 constexpr int kDtwpMaxT = 256;  // longest teacher-forced sequence (sot, lang, not, <= 220 text tokens, eot)
 
-// causal self-attention of one (head, window) over all its T_b positions; K and V (+bias) staged in shared memory as fp32
+// causal self-attention of one (head, window) over all its T_b positions; K and V (+bias, f16-rounded) staged in shared memory as fp32
 // (row stride 65: conflict-free for "lane = key" and "lane = column" accesses alike); one warp per query.
 __global__ void __launch_bounds__(256)
 dtwp_self_attn_kernel(const float* __restrict__ qkv /* [M][3d] */, const float* __restrict__ b_qkv, const int32_t* __restrict__ row_off,
@@ -591,8 +661,9 @@ dtwp_self_attn_kernel(const float* __restrict__ qkv /* [M][3d] */, const float* 
     for (int e = tid; e < T_b * 64; e += 256) {
         const int t = e >> 6, c = e & 63;
         const float* src = qkv + (r0 + t) * 3 * (int64_t)d + hh * 64 + c;
-        Ks[t * 65 + c] = src[d] + b_qkv[d + hh * 64 + c];
-        Vs[t * 65 + c] = src[2 * d] + b_qkv[2 * d + hh * 64 + c];
+        // rounded to f16 as the decode's self cache stores them: the forced pass sees the keys / values the decode saw
+        Ks[t * 65 + c] = __half2float(__float2half_rn(src[d] + b_qkv[d + hh * 64 + c]));
+        Vs[t * 65 + c] = __half2float(__float2half_rn(src[2 * d] + b_qkv[2 * d + hh * 64 + c]));
     }
     __syncthreads();
     float* q = qs + warp * 64;
@@ -1109,8 +1180,8 @@ int DecoderWorkspace::reserve(const wdr_context* ctx, int windows, int rows) {
     ckv.assign(n_layer, nullptr);
     for (int l = 0; l < n_layer; l++) WDR_CUDA_TRY(cudaMalloc(&ckv[l], sizeof(__nv_bfloat16) * (size_t)W * kT * 2 * d));
     const size_t skv = (size_t)n_layer * B * kDecSeqCap * d;
-    WDR_CUDA_TRY(cudaMalloc(&sk, sizeof(float) * skv));
-    WDR_CUDA_TRY(cudaMalloc(&sv, sizeof(float) * skv));
+    WDR_CUDA_TRY(cudaMalloc(&sk, sizeof(__half) * skv));
+    WDR_CUDA_TRY(cudaMalloc(&sv, sizeof(__half) * skv));
     WDR_CUDA_TRY(cudaMalloc(&x, sizeof(float) * (size_t)B * d));
     WDR_CUDA_TRY(cudaMalloc(&h, sizeof(__nv_bfloat16) * (size_t)2 * B * d));    // (hi, lo) planes
     WDR_CUDA_TRY(cudaMalloc(&att, sizeof(__nv_bfloat16) * (size_t)2 * B * d));
@@ -1229,7 +1300,11 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         WDR_CUDA_TRY(launch_kernel(dec_embed_kernel, dim3(B), dim3(128), 0, st, pdl, ws.seq, pos_ptr, pos, w.tok_emb, w.dec_pos, d, a.n_vocab, ws.x));
         WDR_LAUNCH_CHECK();
     }
+    // measurement aid (tools/full_phases.py): leave kernels of the chain out to see what each costs INSIDE the replayed graph — results
+    // are garbage.  bit 0 self-attention, 1 LayerNorms, 2 cross-attention, 3 QKV, 4 out-projection, 5 cross-query, 6 cross-out, 7 fc1, 8 fc2
+    static const int dbg_skip = getenv("WDR_DEBUG_SKIP") ? atoi(getenv("WDR_DEBUG_SKIP")) : 0;
     auto ln = [&](const float* g, const float* b) -> int {
+        if (dbg_skip & 2) { pending = false; return WDR_OK; }
         ProfScope ps(prof, KC_DECODER, st);
         WDR_CUDA_TRY(launch_kernel(dec_ln_kernel, dim3(B), dim3(d / 4), 0, st, pdl, ws.x, pending ? ws.part : nullptr, sg.splits, sg.split_stride, d, pend_bias, g, b,
                                    ws.h, (int64_t)ws.cap_B * d, d));
@@ -1250,8 +1325,8 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
     for (int l = 0; l < L_run && l < dbg_layers; l++) {
         const DecLayerW& e = w.dec[l];
         if ((rc = ln(e.ln1_g, e.ln1_b)) != WDR_OK) return rc;
-        if ((rc = skinny_gemm(ws.h, B, e.w_qkv, 3 * d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
-        {
+        if (!(dbg_skip & 8) && (rc = skinny_gemm(ws.h, B, e.w_qkv, 3 * d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
+        if (!(dbg_skip & 1)) {
             ProfScope ps(prof, KC_DECODER, st);
             int hpc = kSelfMaxHeadsPerCta;
             while (H % hpc) hpc--;
@@ -1263,11 +1338,11 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
                                        beam ? (const int32_t*)ws.beam_anc_cur : (const int32_t*)nullptr, kDecSeqCap));
             WDR_LAUNCH_CHECK();
         }
-        if ((rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
+        if (!(dbg_skip & 16) && (rc = skinny_gemm(ws.att, B, e.w_o, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
         pending = true; pend_bias = e.b_o;
         if ((rc = ln(e.ln2_g, e.ln2_b)) != WDR_OK) return rc;
-        if ((rc = skinny_gemm(ws.h, B, e.w_cq, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
-        {
+        if (!(dbg_skip & 32) && (rc = skinny_gemm(ws.h, B, e.w_cq, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
+        if (!(dbg_skip & 4)) {
             ProfScope ps(prof, KC_DEC_CROSS, st);
             // register budget capped for 6 resident CTAs per SM (40 registers): measured 1900 ms of decode vs 1930 ms at 5 (48
             // registers); 8 (32 registers) spills and is much slower.  A single-pass online-softmax variant that streams K_c and
@@ -1287,10 +1362,10 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
                                        win, t_limit, beam ? (const int32_t*)ws.beam_rowwin : (const int32_t*)nullptr, ws.cross_stats));
             WDR_LAUNCH_CHECK();
         }
-        if ((rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
+        if (!(dbg_skip & 64) && (rc = skinny_gemm(ws.att, B, e.w_co, d, d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
         pending = true; pend_bias = e.b_co;
         if ((rc = ln(e.ln3_g, e.ln3_b)) != WDR_OK) return rc;
-        {   // fc1 with the bias + GELU + (hi, lo) split fused into the epilogue (N = 4d gives >= 24 x 64-wide tiles; no split-K)
+        if (!(dbg_skip & 128)) {   // fc1 with the bias + GELU + (hi, lo) split fused into the epilogue (N = 4d gives >= 24 x 64-wide tiles; no split-K)
             GemmDesc g;
             g.A = ws.h; g.a_row_stride = d; g.rows_per_batch = B; g.n_batch = 1;
             g.W = e.w_fc1; g.ldw = d; g.N = 4 * d; g.K = d;
@@ -1302,7 +1377,7 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
             ProfScope ps(prof, KC_DEC_GEMM, st);
             if ((rc = gemm_bf16(g, st)) != WDR_OK) return rc;
         }
-        if ((rc = skinny_gemm(ws.ff, B, e.w_fc2, d, 4 * d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
+        if (!(dbg_skip & 256) && (rc = skinny_gemm(ws.ff, B, e.w_fc2, d, 4 * d, ws, &sg, st, prof, pdl)) != WDR_OK) return rc;
         pending = true; pend_bias = e.b_fc2;
     }
     if (want_logits) {

@@ -49,8 +49,8 @@ struct DecoderWorkspace {
     int64_t ldv = 0;                   // logits row stride (n_vocab rounded up to 8)
     __nv_bfloat16* enc_bf16 = nullptr; // [B][1500][d]   ln_post output, the cross-KV GEMM's A operand
     std::vector<__nv_bfloat16*> ckv;   // per layer [B][H][K | V][1500][64] bf16: head-major, each (window, head) block contiguous
-    float* sk = nullptr;               // [L][B][H][448][64]  self-attention keys / values, fp32, head-major
-    float* sv = nullptr;
+    __half* sk = nullptr;              // [L][B][H] blocks of 448 x 64 f16 (whisper.cpp: kv_self is f16): keys transposed in blocks of 32 positions
+    __half* sv = nullptr;              //            values row-major [448][64]
     float* x = nullptr;                // [B][d]  residual stream
     __nv_bfloat16* h = nullptr;        // [2][B][d]   (hi, lo) planes of the LayerNorm output
     __nv_bfloat16* att = nullptr;      // [2][B][d]

@@ -46,6 +46,8 @@ struct GemmParams {
     int n_split;
     int group_rows;
     int w_kb_major;  // B operand coordinates: (0, kb*N + n) instead of (kb*64, n)
+    int dbg_no_a;    // measurement aid (WDR_DEBUG_GEMM_NO_A, dual-A GEMMs only): the activation tiles are not loaded at all — WRONG results;
+                     // what remains is the weight stream alone, i.e. the most any activation-traffic optimisation could win
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -111,15 +113,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
             const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
             prefetched = min(STAGES, kb1 - kb0);
-            pdl_wait();  // (a no-op unless launched as a programmatic dependent: then A must wait for the predecessor)
+            // The weight tiles never depend on the predecessor kernel: they are requested (from HBM: the long latency) BEFORE the
+            // programmatic-dependency wait, the activation tiles (L2-resident, just written by the predecessor) after it.
             for (int i = 0; i < prefetched; i++) {
                 const int kb = kb0 + i;
-                mbar_arrive_expect_tx(&bar_full[i], kAStage + kBBytes);
+                mbar_arrive_expect_tx(&bar_full[i], (DUAL && p.dbg_no_a) ? kBBytes : kAStage + kBBytes);
+                if (p.w_kb_major) tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], 0, kb * p.N + n_tile * BN);
+                else tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], kb * kBK, n_tile * BN);
+            }
+            pdl_wait();  // (a no-op unless launched as a programmatic dependent: then A must wait for the predecessor)
+            for (int i = 0; i < prefetched && !(DUAL && p.dbg_no_a); i++) {
+                const int kb = kb0 + i;
                 const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
                 tma_load_3d(sA + i * kAStage, &tma_a, &bar_full[i], kcol * kBK, mt * kBM + tap, batch);
                 if (DUAL) tma_load_3d(sA + i * kAStage + kABytes, &tma_a, &bar_full[i], kcol * kBK, mt * kBM + tap, 1);
-                if (p.w_kb_major) tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], 0, kb * p.N + n_tile * BN);
-                else tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], kb * kBK, n_tile * BN);
             }
         }
     }
@@ -153,10 +160,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     if (prefetched > 0) prefetched--;  // requested in the prologue: this stage is armed and both tiles are in flight
                     else {
                         mbar_wait(&bar_empty[s], ph ^ 1);
-                        mbar_arrive_expect_tx(&bar_full[s], kAStage + kBBytes);
+                        mbar_arrive_expect_tx(&bar_full[s], (DUAL && p.dbg_no_a) ? kBBytes : kAStage + kBBytes);
                         const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
-                        tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
-                        if (DUAL) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
+                        if (!(DUAL && p.dbg_no_a)) tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
+                        if (DUAL && !p.dbg_no_a) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
                         if (p.w_kb_major) tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], 0, kb * p.N + n_tile * BN);
                         else tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], kb * kBK, n_tile * BN);
                     }
@@ -478,6 +485,8 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.group_rows = d.group_rows;
     p.w_kb_major = d.w_kb_major ? 1 : 0;
+    static const int dbg_no_a = getenv("WDR_DEBUG_GEMM_NO_A") ? 1 : 0;
+    p.dbg_no_a = dbg_no_a;
     if (d.epilogue == EPI_HEADS_BF16) WDR_REQUIRE(d.group_rows > 0 && d.n_batch == 1 && d.N % 128 == 0, "EPI_HEADS_BF16 needs group_rows, one batch and N = 2 * heads * 64");
     p.t_batch_stride = d.t_batch_stride > 0 ? d.t_batch_stride : d.rows_per_batch;
     if (BN == 256) {
