@@ -1242,6 +1242,9 @@ int decoder_cross_kv(const wdr_context* ctx, DecoderWorkspace& ws, int B, cudaSt
 // (items <= SMs), the smallest per-item byte count, a small penalty per split for the consumer's partial-sum reads.
 static void pick_tile(int K, int N, int rows, int* bn_out, int* splits_out) {
     const int num_kb = (K + 63) / 64, sms = 148, m_tiles = (rows + 127) / 128;  // beam batches: several 128-row M tiles
+    static const double c_fixed = getenv("WDR_PT_FIXED") ? atof(getenv("WDR_PT_FIXED")) : 300.0;   // tuning knobs of the cost model below
+    static const double c_split = getenv("WDR_PT_SPLIT") ? atof(getenv("WDR_PT_SPLIT")) : 12.0;
+    static const double c_bytes = getenv("WDR_PT_BYTES") ? atof(getenv("WDR_PT_BYTES")) : 1.0;
     double best = 1e30;
     int best_bn = 64, best_s = 1;
     for (int bn : {64, 128}) {
@@ -1252,7 +1255,7 @@ static void pick_tile(int K, int N, int rows, int* bn_out, int* splits_out) {
             const int items = tiles * s * m_tiles, waves = (items + sms - 1) / sms;
             const double ks = per * 64.0;
             const double kb = (512.0 * ks + 2.0 * bn * ks + 512.0 * bn) / 1024.0;
-            const double cost = waves * (300.0 + kb) + 12.0 * s;
+            const double cost = waves * (c_fixed + c_bytes * kb) + c_split * s;
             if (cost < best) { best = cost; best_bn = bn; best_s = s; }
         }
     }
