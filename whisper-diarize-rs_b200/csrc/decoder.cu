@@ -847,6 +847,193 @@ dtwp_cross_attn_kernel(const float* __restrict__ qpart /* [M][d] */, const float
     }
 }
 
+// The same operator on the tensor cores (warp-level mma.sync m16n8k16, bf16 x bf16 -> fp32): 16 queries are exactly one M tile.
+// K_c / V_c are bf16 already; the fp32 queries and probabilities enter as THREE bf16 terms each (x = hi + mid + lo, 24 mantissa
+// bits, every product exact, fp32 accumulation), three MMAs per k-step on the same B fragment.  Fragments come straight from
+// global memory with 16-byte loads — no shared-memory staging, no ldmatrix: the contraction index (scores: the 64 columns) and
+// the output column index (P V) are PERMUTED so that the 2-element fragment entries a thread needs are adjacent in its 16 bytes:
+//   scores, n-tile = 8 keys: thread (g = lane / 4, t = lane % 4) loads columns 8t .. 8t+7 and 32+8t .. 32+8t+7 of key g (each
+//     warp instruction = eight 64-byte row halves); k-step s uses word pair (2s, 2s+1) of those 32 bytes, i.e. logical k = 2t+{0,1}
+//     <-> column base(s) + 8t + {0,1}, logical k = 2t+8+{0,1} <-> column base(s) + 8t + 2 + {0,1}, base = {0, 4, 32, 36}; the
+//     query fragments are built once per CTA with the same map;
+//   P V, k-step = 16 keys: the thread loads columns 8g .. 8g+7 of keys 2t, 2t+1, 2t+8, 2t+9 (each warp instruction = four full
+//     128-byte rows); word p of those loads holds physical columns 8g+2p, 8g+2p+1, which two byte permutes turn into the B fragments
+//     of n-tiles 2p and 2p+1 — logical column n of n-tile 2p (2p+1) is physical column 8n + 2p (8n + 2p + 1).
+// S stays fp32 in shared memory with the exact two-pass softmax of the kernel above (so the alignment heads' probabilities are
+// produced by the same code); warp w takes n-tiles / k-steps w, w + 8, ..., partial O tiles are reduced through shared memory.
+constexpr int kMqPitch = kT + 12;  // S row pitch: == 8 (mod 32), so the 64-bit fragment accesses of a warp spread over all banks
+constexpr int kMqQPitch = 68;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// (x0, x1) as three packed bf16 pairs: x = hi + mid + lo to 24 bits (x0 in the low half: the lower fragment index)
+__device__ __forceinline__ void split3_bf16(float x0, float x1, uint32_t& hi, uint32_t& mid, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    const float2 hf = __bfloat1622float2(h);
+    const float r0 = x0 - hf.x, r1 = x1 - hf.y;
+    const __nv_bfloat162 m = __floats2bfloat162_rn(r0, r1);
+    const float2 mf = __bfloat1622float2(m);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0 - mf.x, r1 - mf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    mid = *reinterpret_cast<const uint32_t*>(&m);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(256, 2)
+dtwp_cross_attn_mma_kernel(const float* __restrict__ qpart /* [M][d] */, const float* __restrict__ b_q, const __nv_bfloat16* __restrict__ ckv, int d,
+                           const int32_t* __restrict__ row_off, const int32_t* __restrict__ T, __nv_bfloat16* __restrict__ att, int64_t lo_off,
+                           const int32_t* __restrict__ ahead_map, float* __restrict__ aw, const int64_t* __restrict__ aw_off,
+                           const int32_t* __restrict__ aw_A) {
+    extern __shared__ float sm[];
+    const int hh = blockIdx.y, b = blockIdx.z, q0 = blockIdx.x * kDtwpQB, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T_b = T[b];
+    if (q0 >= T_b) return;
+    const int nq = min(kDtwpQB, T_b - q0);
+    const int64_t r0 = row_off[b] + q0;
+    float* qs = sm;                          // [16][68], pre-scaled by 1/8; rows >= nq are zero
+    float* p = qs + kDtwpQB * kMqQPitch;     // [16][kMqPitch]; reused as the P V reduction buffer [8][16][64]
+    for (int e = tid; e < kDtwpQB * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        qs[qi * kMqQPitch + c] = qi < nq ? (qpart[(r0 + qi) * (int64_t)d + hh * 64 + c] + b_q[hh * 64 + c]) * 0.125f : 0.0f;
+    }
+    for (int e = tid; e < kDtwpQB * (kMqPitch - kT); e += 256) p[(e / (kMqPitch - kT)) * kMqPitch + kT + e % (kMqPitch - kT)] = 0.0f;
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* Kb = ckv + ((int64_t)b * gridDim.y + hh) * 2 * kT * 64;
+    const __nv_bfloat16* Vb = Kb + kT * 64;
+    // ---- scores ----
+    {
+        uint32_t ah[4][4], am[4][4], al[4][4];  // query fragments of the four k-steps, three terms
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int c0 = (s & 1) * 4 + (s >> 1) * 32 + 8 * t;
+            const float2 x0 = *reinterpret_cast<const float2*>(qs + g * kMqQPitch + c0);
+            const float2 x1 = *reinterpret_cast<const float2*>(qs + (g + 8) * kMqQPitch + c0);
+            const float2 x2 = *reinterpret_cast<const float2*>(qs + g * kMqQPitch + c0 + 2);
+            const float2 x3 = *reinterpret_cast<const float2*>(qs + (g + 8) * kMqQPitch + c0 + 2);
+            split3_bf16(x0.x, x0.y, ah[s][0], am[s][0], al[s][0]);
+            split3_bf16(x1.x, x1.y, ah[s][1], am[s][1], al[s][1]);
+            split3_bf16(x2.x, x2.y, ah[s][2], am[s][2], al[s][2]);
+            split3_bf16(x3.x, x3.y, ah[s][3], am[s][3], al[s][3]);
+        }
+        constexpr int kNT = (kT + 7) / 8;  // 188 n-tiles; the last one holds 4 keys (the others are clamped re-reads, not stored)
+        auto load_k = [&](int nt, uint4& u0, uint4& u1) {
+            const uint4* src = reinterpret_cast<const uint4*>(Kb + (int64_t)min(nt * 8 + g, kT - 1) * 64 + 8 * t);
+            u0 = __ldg(src);
+            u1 = __ldg(src + 4);
+        };
+        uint4 u0, u1, v0, v1;
+        load_k(warp, u0, u1);
+        for (int nt = warp; nt < kNT; nt += 8) {
+            const bool more = nt + 8 < kNT;  // warp-uniform
+            if (more) load_k(nt + 8, v0, v1);
+            float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            mma_bf16_16816(dd, al[0], u0.x, u0.y); mma_bf16_16816(dd, am[0], u0.x, u0.y); mma_bf16_16816(dd, ah[0], u0.x, u0.y);
+            mma_bf16_16816(dd, al[1], u0.z, u0.w); mma_bf16_16816(dd, am[1], u0.z, u0.w); mma_bf16_16816(dd, ah[1], u0.z, u0.w);
+            mma_bf16_16816(dd, al[2], u1.x, u1.y); mma_bf16_16816(dd, am[2], u1.x, u1.y); mma_bf16_16816(dd, ah[2], u1.x, u1.y);
+            mma_bf16_16816(dd, al[3], u1.z, u1.w); mma_bf16_16816(dd, am[3], u1.z, u1.w); mma_bf16_16816(dd, ah[3], u1.z, u1.w);
+            const int k = nt * 8 + 2 * t;
+            if (k < kT) {  // kT is even: k + 1 < kT as well
+                *reinterpret_cast<float2*>(p + g * kMqPitch + k) = make_float2(dd[0], dd[1]);
+                *reinterpret_cast<float2*>(p + (g + 8) * kMqPitch + k) = make_float2(dd[2], dd[3]);
+            }
+            if (more) { u0 = v0; u1 = v1; }
+        }
+    }
+    __syncthreads();
+    // ---- softmax (warp w: queries w, w + 8) and alignment-head capture ----
+    const int ahead = ahead_map ? ahead_map[hh] : -1;
+    for (int qi = warp; qi < nq; qi += 8) {
+        float* pr = p + qi * kMqPitch;
+        float mx = -INFINITY;
+        for (int tt = lane; tt < kT; tt += 32) mx = fmaxf(mx, pr[tt]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int tt = lane; tt < kT; tt += 32) {
+            const float e = expf(pr[tt] - mx);
+            pr[tt] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int tt = lane; tt < kT; tt += 32) pr[tt] *= inv;
+        if (ahead >= 0) {
+            __syncwarp();
+            const int A_b = aw_A[b];
+            float* dst = aw + aw_off[b] + ((int64_t)ahead * T_b + (q0 + qi)) * A_b;
+            for (int tt = lane; tt < A_b; tt += 32) dst[tt] = pr[tt];
+        }
+    }
+    __syncthreads();
+    // ---- P V ----
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) { o[nt][0] = 0.0f; o[nt][1] = 0.0f; o[nt][2] = 0.0f; o[nt][3] = 0.0f; }
+    {
+        constexpr int kKS = (kT + 15) / 16;  // 94 k-steps; keys >= kT: clamped V rows against zero probabilities
+        auto load_v = [&](int ks, uint4 (&w)[4]) {
+            const int k0 = ks * 16 + 2 * t;
+            w[0] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0, kT - 1) * 64 + 8 * g));
+            w[1] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0 + 1, kT - 1) * 64 + 8 * g));
+            w[2] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0 + 8, kT - 1) * 64 + 8 * g));
+            w[3] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0 + 9, kT - 1) * 64 + 8 * g));
+        };
+        uint4 w[4], wn[4];
+        load_v(warp, w);
+        for (int ks = warp; ks < kKS; ks += 8) {
+            const bool more = ks + 8 < kKS;  // warp-uniform
+            if (more) load_v(ks + 8, wn);
+            uint32_t ph[4], pm[4], pl[4];
+            {
+                const float* pp = p + ks * 16 + 2 * t;
+                const float2 x0 = *reinterpret_cast<const float2*>(pp + g * kMqPitch);
+                const float2 x1 = *reinterpret_cast<const float2*>(pp + (g + 8) * kMqPitch);
+                const float2 x2 = *reinterpret_cast<const float2*>(pp + g * kMqPitch + 8);
+                const float2 x3 = *reinterpret_cast<const float2*>(pp + (g + 8) * kMqPitch + 8);
+                split3_bf16(x0.x, x0.y, ph[0], pm[0], pl[0]);
+                split3_bf16(x1.x, x1.y, ph[1], pm[1], pl[1]);
+                split3_bf16(x2.x, x2.y, ph[2], pm[2], pl[2]);
+                split3_bf16(x3.x, x3.y, ph[3], pm[3], pl[3]);
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) {
+                const uint32_t w0 = reinterpret_cast<const uint32_t*>(&w[0])[pp], w1 = reinterpret_cast<const uint32_t*>(&w[1])[pp];
+                const uint32_t w2 = reinterpret_cast<const uint32_t*>(&w[2])[pp], w3 = reinterpret_cast<const uint32_t*>(&w[3])[pp];
+                const uint32_t e0 = __byte_perm(w0, w1, 0x5410), e1 = __byte_perm(w2, w3, 0x5410);  // physical column 8g + 2pp
+                const uint32_t f0 = __byte_perm(w0, w1, 0x7632), f1 = __byte_perm(w2, w3, 0x7632);  // physical column 8g + 2pp + 1
+                mma_bf16_16816(o[2 * pp], pl, e0, e1); mma_bf16_16816(o[2 * pp], pm, e0, e1); mma_bf16_16816(o[2 * pp], ph, e0, e1);
+                mma_bf16_16816(o[2 * pp + 1], pl, f0, f1); mma_bf16_16816(o[2 * pp + 1], pm, f0, f1); mma_bf16_16816(o[2 * pp + 1], ph, f0, f1);
+            }
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) w[i] = wn[i];
+            }
+        }
+    }
+    __syncthreads();  // all warps are done reading p
+    float* red = p;   // [8][16][64]
+#pragma unroll
+    for (int pp = 0; pp < 4; pp++) {
+        // n-tiles 2pp / 2pp+1, logical columns n = 2t, 2t+1 -> physical columns 8n + 2pp (+1): pairs of adjacent columns
+        float* r = red + (warp * kDtwpQB) * 64 + 2 * pp;
+        *reinterpret_cast<float2*>(r + g * 64 + 8 * (2 * t)) = make_float2(o[2 * pp][0], o[2 * pp + 1][0]);
+        *reinterpret_cast<float2*>(r + g * 64 + 8 * (2 * t + 1)) = make_float2(o[2 * pp][1], o[2 * pp + 1][1]);
+        *reinterpret_cast<float2*>(r + (g + 8) * 64 + 8 * (2 * t)) = make_float2(o[2 * pp][2], o[2 * pp + 1][2]);
+        *reinterpret_cast<float2*>(r + (g + 8) * 64 + 8 * (2 * t + 1)) = make_float2(o[2 * pp][3], o[2 * pp + 1][3]);
+    }
+    __syncthreads();
+    for (int e = tid; e < nq * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        float a = 0.0f;
+#pragma unroll
+        for (int w = 0; w < 8; w++) a += red[(w * kDtwpQB + qi) * 64 + c];
+        store_split(att, lo_off, (r0 + qi) * (int64_t)d + hh * 64 + c, a);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // whisper_process_logits + whisper_sample_token(best) + the decoder bookkeeping of whisper_full's inner loop
 // ---------------------------------------------------------------------------------------------------
@@ -1457,8 +1644,11 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
     static DeviceOnce attr_once;
     const int smem_self = (int)sizeof(float) * (2 * kDtwpMaxT * 65 + 8 * 64 + 8 * kDtwpMaxT);
     const int smem_cross = (int)sizeof(float) * (kDtwpQB * 64 + kDtwpQB * kDtwpPStride);
+    const int smem_cross_mma = (int)sizeof(float) * (kDtwpQB * kMqQPitch + kDtwpQB * kMqPitch);
+    static const bool cross_ffma = getenv("WDR_DTWP_FFMA") != nullptr;  // A/B knob: the fp32-FMA kernel instead of the tensor-core one
     WDR_CUDA_TRY(per_device_once(attr_once, [&] {
-        const cudaError_t e = cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self);
+        cudaError_t e = cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(dtwp_cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross_mma);
         return e != cudaSuccess ? e : cudaFuncSetAttribute(dtwp_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross);
     }));
     int L_run = 0;
@@ -1493,8 +1683,12 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
         if ((rc = packed_gemm(pw.h, M, Mc, e.w_cq, d, d, pw.part, st, prof)) != WDR_OK) return rc;
         {
             ProfScope ps(prof, KC_DEC_CROSS_BATCHED, st);
-            dtwp_cross_attn_kernel<<<dim3((max_T + kDtwpQB - 1) / kDtwpQB, H, B), 256, smem_cross, st>>>(
-                pw.part, e.b_cq, ws.ckv[l], d, pw.row_off, ws.aw_T, pw.att, Mc * d, ws.ahead_map + (size_t)l * H, ws.aw, ws.aw_off, ws.aw_A);
+            if (cross_ffma)
+                dtwp_cross_attn_kernel<<<dim3((max_T + kDtwpQB - 1) / kDtwpQB, H, B), 256, smem_cross, st>>>(
+                    pw.part, e.b_cq, ws.ckv[l], d, pw.row_off, ws.aw_T, pw.att, Mc * d, ws.ahead_map + (size_t)l * H, ws.aw, ws.aw_off, ws.aw_A);
+            else
+                dtwp_cross_attn_mma_kernel<<<dim3((max_T + kDtwpQB - 1) / kDtwpQB, H, B), 256, smem_cross_mma, st>>>(
+                    pw.part, e.b_cq, ws.ckv[l], d, pw.row_off, ws.aw_T, pw.att, Mc * d, ws.ahead_map + (size_t)l * H, ws.aw, ws.aw_off, ws.aw_A);
             WDR_LAUNCH_CHECK();
         }
         if (l == L_run - 1) break;  // nothing after the last alignment head's probabilities is used
