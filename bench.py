@@ -165,12 +165,12 @@ class CpuPort:
         dt = time.perf_counter() - t0
         return n_chunks * 30.0 / dt, dt, n_tok
 
-    def window_on_encoder_output(self, pcm_row, enc_out):
-        """The decode half (greedy decode, token timestamps, DTW) of one window on a GIVEN encoder output: the strict checker of
-        what the GPU arm produced for that window (identical inputs to the decoder => ids / t0 / t1 / t_dtw must be identical)."""
+    def window_on_encoder_output(self, pcm_row, enc_out, beam_size=1):
+        """The decode half (greedy / beam decode, token timestamps, DTW) of one window on a GIVEN encoder output: the strict checker
+        of what the GPU arm produced for that window (identical inputs to the decoder => ids / t0 / t1 / t_dtw must be identical)."""
         from oracle import full
         x = pcm_row.astype(np.float32) / np.float32(32768.0)
-        return full.full_window(self.dec, enc_out, x)
+        return full.full_window(self.dec, enc_out, x, beam_size=beam_size)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -542,7 +542,7 @@ def run_pipeline(args):
         dist.destroy_process_group()
 
 
-def parity_check(w, st, ctx, port, pcm_host, params):
+def parity_check(w, st, ctx, port, pcm_host, params, beam_size=1):
     """bench.py checks what it times: window 0 of the timed batch against the CPU port.
     strict: the port's decode half (greedy decode, A.5 token timestamps, DTW) on the LIBRARY's encoder output for that window —
             identical decoder inputs, so token ids, segment times, t0 / t1 and t_dtw must be identical;
@@ -554,7 +554,7 @@ def parity_check(w, st, ctx, port, pcm_host, params):
     got = [s_ for s_ in st.segments() if s_["chunk"] == 0]
     ids_g = [t.id for s_ in got for t in s_["tokens"]]
     out = {"window": 0, "n_tokens": len(ids_g)}
-    ref = port.window_on_encoder_output(pcm_host[0], hid0)
+    ref = port.window_on_encoder_output(pcm_host[0], hid0, beam_size=beam_size)
     toks_r = [t for s_ in ref["segments"] for t in s_["tokens"]]
     ids_r = [t.id for t in toks_r]
     same = ids_g == ids_r
@@ -569,14 +569,15 @@ def parity_check(w, st, ctx, port, pcm_host, params):
         k = next((i for i, (a_, b_) in enumerate(zip(ids_g, ids_r)) if a_ != b_), min(len(ids_g), len(ids_r)))
         out["first_divergence"] = int(k)
         out["margin"] = float(ref["margins"][k]) if k < len(ref["margins"]) else None
-    fp = getattr(port, "last0", None)
+    fp = getattr(port, "last0", None) if beam_size <= 1 else None  # the cpu_baseline sample is a greedy run
     if fp is not None:
         ids_f = [t.id for s_ in fp["segments"] for t in s_["tokens"]]
         out["from_pcm_fp32_encoder"] = {"tokens_identical": ids_f == ids_g}
         if ids_f != ids_g:
             k = next((i for i, (a_, b_) in enumerate(zip(ids_g, ids_f)) if a_ != b_), min(len(ids_g), len(ids_f)))
             out["from_pcm_fp32_encoder"].update(first_divergence=int(k), oracle_top1_margin=float(fp["margins"][k]) if k < len(fp["margins"]) else None)
-    out["checker"] = "oracle/full.py:full_window on oracle/wdr_oracle_full.c (bf16 cross-KV storage mode), window 0 of the timed batch"
+    out["checker"] = ("oracle/full.py:full_window on oracle/wdr_oracle_full.c (library storage mode: bf16 cross-KV, f16 self-KV)" +
+                      (f", beam search (beam {beam_size})" if beam_size > 1 else ", greedy") + ", window 0 of the timed batch")
     return out
 
 
@@ -892,7 +893,7 @@ def main():
                                     "sample": f"{n} of the {B} windows ({dt:.1f} s of CPU work) on {cores} OpenMP threads "
                                               f"({host_cores()} cores in the affinity mask), oracle/wdr_oracle*.c"}
             if full:
-                line["parity"] = parity_check(w, st, ctx, port, pcm_host, params)
+                line["parity"] = parity_check(w, st, ctx, port, pcm_host, params, beam_size=max(1, args.beam))
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)

@@ -1034,6 +1034,158 @@ dtwp_cross_attn_mma_kernel(const float* __restrict__ qpart /* [M][d] */, const f
     }
 }
 
+// Beam search / best_of decoding on the same tensor-core scheme: the K <= 8 rows (decoders) of a window against its K_c / V_c, one CTA
+// per (head, window), both 192 KB blocks read ONCE for all rows.  Eight queries fill half an M tile, so the three bf16 terms are
+// laid out as A1 = [hi (rows 0-7); mid (rows 8-15)] and A2 = [lo; 0]: two MMAs per k-step into ONE accumulator, and the value of
+// query g is c(row g) + c(row g + 8) — both live in the same thread.  Replaces dec_cross_attn_rows_kernel (fp32 FFMA2: 273 us per
+// launch for 120 windows x 5 rows = 0.52 of the HBM roofline, the FMA pipe and its load -> FMA round trips in the way).
+__global__ void __launch_bounds__(256, 2)
+dec_cross_attn_rows_mma_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_q,
+                               const __nv_bfloat16* __restrict__ ckv, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off, int pos,
+                               const int32_t* __restrict__ t_limit, const int32_t* __restrict__ row_window, int K) {
+    extern __shared__ float sm[];
+    constexpr int NQ = 8;
+    float* qs = sm;                     // [8][68], pre-scaled by 1/8; rows >= K are zero
+    float* p = qs + NQ * kMqQPitch;     // [8][kMqPitch]; reused as the P V reduction buffer [8 warps][8][64]
+    const int hh = blockIdx.x, w = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = w * K;
+    bool any = false;
+    for (int i = 0; i < K; i++) any |= pos < t_limit[b0 + i];
+    if (!any) return;
+    for (int e = tid; e < NQ * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        qs[qi * kMqQPitch + c] = qi < K ? (part_sum(part, n_splits, split_stride, (int64_t)(b0 + qi) * d + hh * 64 + c) + b_q[hh * 64 + c]) * 0.125f : 0.0f;
+    }
+    for (int e = tid; e < NQ * (kMqPitch - kT); e += 256) p[(e / (kMqPitch - kT)) * kMqPitch + kT + e % (kMqPitch - kT)] = 0.0f;
+    __syncthreads();
+    const int g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* Kb = ckv + ((int64_t)row_window[b0] * gridDim.x + hh) * 2 * kT * 64;
+    const __nv_bfloat16* Vb = Kb + kT * 64;
+    // ---- scores ----
+    {
+        uint32_t a1[4][4], a2[4][4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int c0 = (s & 1) * 4 + (s >> 1) * 32 + 8 * t;
+            const float2 x0 = *reinterpret_cast<const float2*>(qs + g * kMqQPitch + c0);
+            const float2 x2 = *reinterpret_cast<const float2*>(qs + g * kMqQPitch + c0 + 2);
+            split3_bf16(x0.x, x0.y, a1[s][0], a1[s][1], a2[s][0]);
+            split3_bf16(x2.x, x2.y, a1[s][2], a1[s][3], a2[s][2]);
+            a2[s][1] = 0u;
+            a2[s][3] = 0u;
+        }
+        constexpr int kNT = (kT + 7) / 8;
+        auto load_k = [&](int nt, uint4& u0, uint4& u1) {
+            const uint4* src = reinterpret_cast<const uint4*>(Kb + (int64_t)min(nt * 8 + g, kT - 1) * 64 + 8 * t);
+            u0 = __ldg(src);
+            u1 = __ldg(src + 4);
+        };
+        // two n-tiles ahead: 3 x 1 KB per warp in flight (this kernel has to keep HBM busy, unlike the DTW-pass one)
+        uint4 u0, u1, v0, v1, x0, x1;
+        load_k(warp, u0, u1);
+        load_k(min(warp + 8, kNT - 1), v0, v1);
+        for (int nt = warp; nt < kNT; nt += 8) {
+            load_k(min(nt + 16, kNT - 1), x0, x1);
+            float dd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            mma_bf16_16816(dd, a2[0], u0.x, u0.y); mma_bf16_16816(dd, a1[0], u0.x, u0.y);
+            mma_bf16_16816(dd, a2[1], u0.z, u0.w); mma_bf16_16816(dd, a1[1], u0.z, u0.w);
+            mma_bf16_16816(dd, a2[2], u1.x, u1.y); mma_bf16_16816(dd, a1[2], u1.x, u1.y);
+            mma_bf16_16816(dd, a2[3], u1.z, u1.w); mma_bf16_16816(dd, a1[3], u1.z, u1.w);
+            const int k = nt * 8 + 2 * t;
+            if (k < kT) *reinterpret_cast<float2*>(p + g * kMqPitch + k) = make_float2(dd[0] + dd[2], dd[1] + dd[3]);
+            u0 = v0; u1 = v1; v0 = x0; v1 = x1;
+        }
+    }
+    __syncthreads();
+    // ---- softmax: warp i = row i ----
+    if (warp < K) {
+        float* pr = p + warp * kMqPitch;
+        float mx = -INFINITY;
+        for (int tt = lane; tt < kT; tt += 32) mx = fmaxf(mx, pr[tt]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int tt = lane; tt < kT; tt += 32) {
+            const float e = expf(pr[tt] - mx);
+            pr[tt] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int tt = lane; tt < kT; tt += 32) pr[tt] *= inv;
+    }
+    __syncthreads();
+    // ---- P V ----
+    float o[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) { o[nt][0] = 0.0f; o[nt][1] = 0.0f; o[nt][2] = 0.0f; o[nt][3] = 0.0f; }
+    {
+        constexpr int kKS = (kT + 15) / 16;
+        auto load_v = [&](int ks, uint4 (&wv)[4]) {
+            const int k0 = ks * 16 + 2 * t;
+            wv[0] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0, kT - 1) * 64 + 8 * g));
+            wv[1] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0 + 1, kT - 1) * 64 + 8 * g));
+            wv[2] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0 + 8, kT - 1) * 64 + 8 * g));
+            wv[3] = __ldg(reinterpret_cast<const uint4*>(Vb + (int64_t)min(k0 + 9, kT - 1) * 64 + 8 * g));
+        };
+        uint4 wc[4], wn[4];
+        load_v(warp, wc);
+        for (int ks = warp; ks < kKS; ks += 8) {
+            load_v(min(ks + 8, kKS - 1), wn);
+            uint32_t pa1[4], pa2[4];
+            {
+                const float* pp = p + g * kMqPitch + ks * 16 + 2 * t;
+                const float2 x0 = *reinterpret_cast<const float2*>(pp);
+                const float2 x2 = *reinterpret_cast<const float2*>(pp + 8);
+                split3_bf16(x0.x, x0.y, pa1[0], pa1[1], pa2[0]);
+                split3_bf16(x2.x, x2.y, pa1[2], pa1[3], pa2[2]);
+                pa2[1] = 0u;
+                pa2[3] = 0u;
+            }
+#pragma unroll
+            for (int pp = 0; pp < 4; pp++) {
+                const uint32_t w0 = reinterpret_cast<const uint32_t*>(&wc[0])[pp], w1 = reinterpret_cast<const uint32_t*>(&wc[1])[pp];
+                const uint32_t w2 = reinterpret_cast<const uint32_t*>(&wc[2])[pp], w3 = reinterpret_cast<const uint32_t*>(&wc[3])[pp];
+                const uint32_t e0 = __byte_perm(w0, w1, 0x5410), e1 = __byte_perm(w2, w3, 0x5410);
+                const uint32_t f0 = __byte_perm(w0, w1, 0x7632), f1 = __byte_perm(w2, w3, 0x7632);
+                mma_bf16_16816(o[2 * pp], pa2, e0, e1); mma_bf16_16816(o[2 * pp], pa1, e0, e1);
+                mma_bf16_16816(o[2 * pp + 1], pa2, f0, f1); mma_bf16_16816(o[2 * pp + 1], pa1, f0, f1);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) wc[i] = wn[i];
+        }
+    }
+    __syncthreads();  // all warps are done reading p
+    float* red = p;   // [8 warps][8][64]
+#pragma unroll
+    for (int pp = 0; pp < 4; pp++) {
+        float* r = red + (warp * NQ + g) * 64 + 2 * pp;
+        *reinterpret_cast<float2*>(r + 8 * (2 * t)) = make_float2(o[2 * pp][0] + o[2 * pp][2], o[2 * pp + 1][0] + o[2 * pp + 1][2]);
+        *reinterpret_cast<float2*>(r + 8 * (2 * t + 1)) = make_float2(o[2 * pp][1] + o[2 * pp][3], o[2 * pp + 1][1] + o[2 * pp + 1][3]);
+    }
+    __syncthreads();
+    for (int e = tid; e < K * 64; e += 256) {
+        const int qi = e >> 6, c = e & 63;
+        if (pos >= t_limit[b0 + qi]) continue;
+        float a = 0.0f;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) a += red[(wv * NQ + qi) * 64 + c];
+        store_split(att, lo_off, (int64_t)(b0 + qi) * d + hh * 64 + c, a);
+    }
+}
+
+static cudaError_t launch_cross_rows_mma(int H, int nW, int K, cudaStream_t st, const float* part, int n_splits, int64_t split_stride, const float* b_q,
+                                         const __nv_bfloat16* ckv, int d, __nv_bfloat16* att, int64_t lo_off, int pos, const int32_t* t_limit,
+                                         const int32_t* row_window) {
+    const size_t smem = sizeof(float) * ((size_t)8 * kMqQPitch + (size_t)8 * kMqPitch);
+    static DeviceOnce attr_once;
+    {
+        const cudaError_t e = per_device_once(attr_once, [&] { return cudaFuncSetAttribute(dec_cross_attn_rows_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
+        if (e != cudaSuccess) return e;
+    }
+    dec_cross_attn_rows_mma_kernel<<<dim3(H, nW), 256, smem, st>>>(part, n_splits, split_stride, b_q, ckv, d, att, lo_off, pos, t_limit, row_window, K);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // whisper_process_logits + whisper_sample_token(best) + the decoder bookkeeping of whisper_full's inner loop
 // ---------------------------------------------------------------------------------------------------
@@ -1543,6 +1695,10 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
                 const int nW = B / ws.beam_K, nqp = (ws.beam_K + 1) / 2;
                 cudaError_t ce;
 #define WDR_ROWS(N) launch_cross_rows<N>(H, nW, ws.beam_K, st, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d, pos, t_limit, ws.beam_rowwin)
+                static const bool rows_ffma = getenv("WDR_ROWS_FFMA") != nullptr;  // A/B knob: the fp32-FMA rows kernel
+                if (!rows_ffma && ws.beam_K <= 8)
+                    ce = launch_cross_rows_mma(H, nW, ws.beam_K, st, ws.part, sg.splits, sg.split_stride, e.b_cq, ws.ckv[l], d, ws.att, (int64_t)ws.cap_B * d, pos, t_limit, ws.beam_rowwin);
+                else
                 ce = nqp == 1 ? WDR_ROWS(1) : nqp == 2 ? WDR_ROWS(2) : nqp == 3 ? WDR_ROWS(3) : WDR_ROWS(4);
 #undef WDR_ROWS
                 WDR_CUDA_TRY(ce);
