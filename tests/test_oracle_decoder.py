@@ -77,6 +77,34 @@ def test_bf16_policy_is_close_to_fp32(oracle, tiny):
     assert np.abs(la - lb).max() < 2e-2 * np.abs(la).max()
 
 
+def test_storage_mode_self_cache_is_f16(oracle, tiny):
+    """Storage mode rounds the appended self k / v to IEEE binary16 (round-to-nearest-even), as whisper.cpp's f16 kv_self and
+    libwdr_b200's self cache do: the cached rows equal numpy's float16 rounding of the fp32 mode's first-layer rows."""
+    from oracle import weights as W
+    arch = "tiny.en"
+    d = W.ARCHS[arch]["d"]
+    rng = np.random.default_rng(5)
+    enc = rng.standard_normal((1500, d)).astype(np.float32)
+    a = oracle.Decoder(arch, W.pack_decoder(arch, tiny), bf16=False)
+    b = oracle.Decoder(arch, W.pack_decoder(arch, tiny), bf16=True)
+    a.set_audio(enc)
+    b.set_audio(enc)
+    a.step(50257, 0, want_logits=False)
+    b.step(50257, 0, want_logits=False)
+    (ka, va), (kb, vb) = a.get_kv(), b.get_kv()
+    # layer 0, position 0: the layer's input is the same in both modes (embedding + position), so k / v differ by the rounding only
+    for xa, xb in ((ka[:d], kb[:d]), (va[:d], vb[:d])):
+        assert np.array_equal(xb, xa.astype(np.float16).astype(np.float32))
+        assert np.any(xa != xb)
+    # every cached row of every layer is f16-representable
+    L = W.ARCHS[arch]["n_dec"]
+    for l in range(L):
+        row = kb[l * 448 * d: l * 448 * d + d]
+        assert np.array_equal(row, row.astype(np.float16).astype(np.float32))
+    a.close()
+    b.close()
+
+
 def _logits(n_vocab, fill=0.0):
     return np.full(n_vocab, fill, np.float32)
 
