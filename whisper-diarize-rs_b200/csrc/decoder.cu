@@ -1731,7 +1731,11 @@ int decoder_step(const wdr_context* ctx, DecoderWorkspace& ws, int B, int pos, b
         GemmDesc g;
         g.A = ws.h; g.a_row_stride = d; g.rows_per_batch = B; g.n_batch = 1;
         g.W = w.tok_emb; g.ldw = d; g.N = (int)ws.ldv; g.K = d;
-        g.epilogue = EPI_F32; g.out = ws.logits; g.ldc = ws.ldv; g.bn = 64;
+        // Tile width of the logits GEMM (51 866 x d weights = 133 MB, every item re-reads its (hi, lo) activation slice from L2): measured per
+        // launch at 120 windows (ncu, in-graph) 56.1 us with 64-wide tiles (811 items), 41.8 us with 128 (406 items: half the activation traffic),
+        // 40.7 us with 256 (203 items = 1.4 waves; instantiation not kept)
+        static const int logits_bn = getenv("WDR_LOGITS_BN") ? atoi(getenv("WDR_LOGITS_BN")) : 128;
+        g.epilogue = EPI_F32; g.out = ws.logits; g.ldc = ws.ldv; g.bn = logits_bn == 64 ? 64 : 128;
         g.dual_a = true; g.a_dual_stride = (int64_t)ws.cap_B * d;
         g.pdl = pdl;
         ProfScope ps(prof, KC_DEC_GEMM, st);
