@@ -66,25 +66,38 @@ __global__ void emb_im2col_feats_kernel(const float* __restrict__ feats, const i
     }
 }
 
-// in [rows_in][C] bf16 -> A [rows_out][KS*KS*C] bf16, one 16-byte vector (8 channels of one tap) per thread iteration
+// in [rows_in][C] bf16 -> A [rows_out][KS*KS*C] bf16.  One WARP per output row (all segments' rows are one packed index space: a
+// binary search over the segment offsets finds the row's segment), lanes over the row's 16-byte vectors (8 channels of one tap):
+// one division per row instead of several 64-bit ones per vector, contiguous 576 B .. 4.6 KB stores per row, and a grid sized by
+// the work instead of (1184 x segments) CTAs most of which found nothing to do (round 1's kernel: 24.6 of the 50.8 ms of the
+// embedding stage of a 10 min recording).
 template <int KS>
-__global__ void emb_im2col_kernel(const __nv_bfloat16* __restrict__ in, int C, int F_in, int F_out, int stride, const int32_t* __restrict__ T_in,
-                                  const int32_t* __restrict__ T_out, const int64_t* __restrict__ in_off, const int64_t* __restrict__ out_off,
-                                  __nv_bfloat16* __restrict__ A) {
-    const int seg = blockIdx.y, Ti = T_in[seg], To = T_out[seg];
-    const int cv_n = C >> 3, vec_per_row = KS * KS * cv_n;
-    const int64_t total = (int64_t)F_out * To * vec_per_row;
-    const uint4* src = reinterpret_cast<const uint4*>(in) + in_off[seg] * cv_n;
-    uint4* dst = reinterpret_cast<uint4*>(A) + out_off[seg] * vec_per_row;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = idx / vec_per_row;
-        const int v = (int)(idx - row * vec_per_row);
-        const int tap = v / cv_n, cv = v - tap * cv_n;
-        const int f = (int)(row / To), t = (int)(row - (int64_t)f * To);
-        const int fi = f * stride + tap / KS - KS / 2, ti = t * stride + tap % KS - KS / 2;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (fi >= 0 && fi < F_in && ti >= 0 && ti < Ti) val = __ldg(src + ((int64_t)fi * Ti + ti) * cv_n + cv);
-        dst[idx] = val;
+__global__ void __launch_bounds__(256)
+emb_im2col_kernel(const __nv_bfloat16* __restrict__ in, int C, int F_in, int stride, const int32_t* __restrict__ T_in,
+                  const int32_t* __restrict__ T_out, const int64_t* __restrict__ in_off, const int64_t* __restrict__ out_off, int n_seg,
+                  int64_t total_rows, __nv_bfloat16* __restrict__ A) {
+    const int lane = threadIdx.x & 31;
+    const int cv_n = C >> 3, cv_shift = 31 - __clz(cv_n), vec_per_row = KS * KS * cv_n;  // C is a power of two (32 .. 256)
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t R = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); R < total_rows; R += warps) {
+        int lo = 0, hi = n_seg - 1;  // largest seg with out_off[seg] <= R
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ldg(out_off + mid) <= R) lo = mid; else hi = mid - 1;
+        }
+        const int seg = lo, Ti = __ldg(T_in + seg), To = __ldg(T_out + seg);
+        const int row = (int)(R - __ldg(out_off + seg));
+        const int f = row / To, t = row - f * To;
+        const uint4* src = reinterpret_cast<const uint4*>(in) + __ldg(in_off + seg) * cv_n;
+        uint4* dst = reinterpret_cast<uint4*>(A) + R * vec_per_row;
+        for (int v = lane; v < vec_per_row; v += 32) {
+            const int tap = v >> cv_shift, cv = v & (cv_n - 1);
+            const int ky = tap / KS, kx = tap - ky * KS;
+            const int fi = f * stride + ky - KS / 2, ti = t * stride + kx - KS / 2;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (fi >= 0 && fi < F_in && ti >= 0 && ti < Ti) val = __ldg(src + ((int64_t)fi * Ti + ti) * cv_n + cv);
+            dst[v] = val;
+        }
     }
 }
 
@@ -300,14 +313,13 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     __nv_bfloat16 *x = m->act[0], *y1 = m->act[1], *sc = m->act[2], *x2 = m->act[3];
     int level = 0;
     auto im2col = [&](const __nv_bfloat16* in, const ConvW& c, int lin, int lout) -> int {
-        const int64_t work = (int64_t)lv[lout].max_rows() * c.k * c.k * (c.c_in / 8);
+        const int64_t total_rows = lv[lout].rows();
+        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total_rows + 7) / 8, 148 * 16));
         EmbProfScope ps(false, st);
         if (c.k == 3)
-            emb_im2col_kernel<3><<<dim3(blocks_for(work), n), 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lout].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off,
-                                                                           lv[lout].d_off, m->col);
+            emb_im2col_kernel<3><<<grid, 256, 0, st>>>(in, c.c_in, lv[lin].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off, lv[lout].d_off, n, total_rows, m->col);
         else
-            emb_im2col_kernel<1><<<dim3(blocks_for(work), n), 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lout].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off,
-                                                                           lv[lout].d_off, m->col);
+            emb_im2col_kernel<1><<<grid, 256, 0, st>>>(in, c.c_in, lv[lin].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off, lv[lout].d_off, n, total_rows, m->col);
         WDR_LAUNCH_CHECK();
         flops += 2.0 * lv[lout].rows() * c.c_out * c.c_in * c.k * c.k;
         return WDR_OK;
