@@ -4,13 +4,16 @@
 // int16 samples cast to f32 without scaling -> knf fbank (fbank.cu) -> per-column mean subtraction -> ONNX model "feats" [1,T,80]
 // -> "embs" [1,D].  The crate ships the CAM++ export; the north-star names WeSpeaker ResNet34: D = 256.
 //
-// Segments are independent, so a call takes a batch of them.  Activations are bf16, channels innermost: level r holds
-// [segment][f < 80 >> r][t < T_r][C] as packed rows (segment s starts at row off_r[s]); every convolution is one GEMM
-//     out[rows][C_out] = im2col(in)[rows][k*k*C_in] * W[C_out][k*k*C_in]^T
-// on the tcgen05 kernel (gemm.cu) with the folded BatchNorm shift, the residual add and the ReLU in its epilogue.  The im2col
-// matrix is materialised in bf16 by a coalesced 16-byte gather (zero rows at the borders): 9x the activation bytes, HBM-trivial
-// next to the GEMM at these sizes.  TSTP (mean / unbiased std over time per (channel, frequency)) and the 5120 -> 256 linear
-// layer are fp32.
+// Segments are independent, so a call takes a batch of them.  Activations are bf16, channels innermost.  Level r holds, per segment,
+// a ZERO-PADDED map of F = 80 >> r rows and T_r columns stored as packed rows with pitch P = T_r + 1: position (f, t) is row
+// (f + 1) * P + t of the segment's block; row f = -1, row f = F and column t = T_r are zero, and a block is a multiple of 128 rows
+// (one GEMM M tile never straddles two maps).  In that layout a 3 x 3 stride-1 convolution is NINE SHIFTED GEMMs over the activation
+// matrix itself — tap (dy, dx) reads the tile's rows shifted by dy * P + dx — so 29 of the 36 convolutions run as implicit GEMMs on the
+// tcgen05 kernel (gemm.cu, conv2d) with no im2col matrix at all; its epilogue (folded BatchNorm shift, residual add, ReLU) writes zero
+// at every non-interior position, so every output is again a padded map.  Only the stem (1 input channel), the three stride-2 3 x 3
+// convolutions and their 1 x 1 stride-2 shortcuts gather a (small) operand first.  Round 1 materialised the im2col matrix of every
+// convolution (9 x the activation bytes, written and read back: 25 + 15 of the 51 ms of a 10 min recording's embedding stage).
+// TSTP (mean / unbiased std over time per (channel, frequency)) and the 5120 -> 256 linear layer are fp32.
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -31,8 +34,9 @@ constexpr int kEmbMaxFramesPerGroup = 8192;  // fbank frames per forward batch (
 
 struct ConvW {
     int c_in, c_out, k, stride, K;  // K = GEMM inner size (k*k*c_in, conv1: 16)
-    __nv_bfloat16* w;               // [c_out][K]
+    __nv_bfloat16* w;               // [c_out][K], tap-major: column (ky*k + kx)*c_in + c
     float* b;                       // [c_out]
+    __nv_bfloat16* w_pair;          // c_in = 32, 3 x 3, stride 1 only: [c_out][3][4][32] — per dy the taps dx = -1, 0, +1 and a zero phantom tap
 };
 struct BlockW { ConvW c1, c2, sc; bool has_sc; };
 
@@ -43,70 +47,81 @@ static inline uint16_t f32_to_bf16_bits(float f) {
     return (uint16_t)((u + r) >> 16);
 }
 
-// fbank feats [t][80] fp32 -> conv1's im2col matrix [rows = (f, t)][16] bf16 (taps (ky, kx) over (f, t); columns 9..15 zero)
+// (segment, f + 1, t) of padded row R: largest seg with poff[seg] <= R, then the position inside that segment's block
+__device__ __forceinline__ void emb_locate(const int64_t* __restrict__ poff, const int32_t* __restrict__ T, int n_seg, int64_t R, int& seg, int& f1, int& t, int& Ts) {
+    int lo = 0, hi = n_seg - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(poff + mid) <= R) lo = mid; else hi = mid - 1;
+    }
+    seg = lo;
+    Ts = __ldg(T + seg);
+    const int local = (int)(R - __ldg(poff + seg)), P = Ts + 1;
+    f1 = local / P;
+    t = local - f1 * P;
+}
+
+// fbank feats [t][80] fp32 -> the stem's operand [padded rows of level 0][16] bf16 (taps (ky, kx) over (f, t); columns 9..15 and the
+// non-interior rows zero)
 __global__ void emb_im2col_feats_kernel(const float* __restrict__ feats, const int64_t* __restrict__ feat_off, const int32_t* __restrict__ T,
-                                        const int64_t* __restrict__ row_off, __nv_bfloat16* __restrict__ A) {
-    const int seg = blockIdx.y, Ts = T[seg];
-    const int64_t rows = (int64_t)kEmbBins * Ts;
-    const float* x = feats + feat_off[seg] * kEmbBins;
-    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < rows; row += (int64_t)gridDim.x * blockDim.x) {
-        const int f = (int)(row / Ts), t = (int)(row - (int64_t)f * Ts);
+                                        const int64_t* __restrict__ poff, int n_seg, int64_t total_rows, __nv_bfloat16* __restrict__ A) {
+    for (int64_t R = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; R < total_rows; R += (int64_t)gridDim.x * blockDim.x) {
+        int seg, f1, t, Ts;
+        emb_locate(poff, T, n_seg, R, seg, f1, t, Ts);
+        const int f = f1 - 1;
         __align__(16) __nv_bfloat16 v[16];
 #pragma unroll
-        for (int tap = 0; tap < 9; tap++) {
-            const int fi = f + tap / 3 - 1, ti = t + tap % 3 - 1;
-            const float a = (fi >= 0 && fi < kEmbBins && ti >= 0 && ti < Ts) ? x[(int64_t)ti * kEmbBins + fi] : 0.0f;
-            v[tap] = __float2bfloat16_rn(a);
-        }
+        for (int tap = 0; tap < 16; tap++) v[tap] = __float2bfloat16_rn(0.0f);
+        if (f >= 0 && f < kEmbBins && t < Ts) {
+            const float* x = feats + __ldg(feat_off + seg) * kEmbBins;
 #pragma unroll
-        for (int tap = 9; tap < 16; tap++) v[tap] = __float2bfloat16_rn(0.0f);
-        uint4* dst = reinterpret_cast<uint4*>(A + (row_off[seg] + row) * 16);
+            for (int tap = 0; tap < 9; tap++) {
+                const int fi = f + tap / 3 - 1, ti = t + tap % 3 - 1;
+                if (fi >= 0 && fi < kEmbBins && ti >= 0 && ti < Ts) v[tap] = __float2bfloat16_rn(x[(int64_t)ti * kEmbBins + fi]);
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(A + R * 16);
         dst[0] = *reinterpret_cast<const uint4*>(v);
         dst[1] = *reinterpret_cast<const uint4*>(v + 8);
     }
 }
 
-// in [rows_in][C] bf16 -> A [rows_out][KS*KS*C] bf16.  One WARP per output row (all segments' rows are one packed index space: a
-// binary search over the segment offsets finds the row's segment), lanes over the row's 16-byte vectors (8 channels of one tap):
-// one division per row instead of several 64-bit ones per vector, contiguous 576 B .. 4.6 KB stores per row, and a grid sized by
-// the work instead of (1184 x segments) CTAs most of which found nothing to do (round 1's kernel: 24.6 of the 50.8 ms of the
-// embedding stage of a 10 min recording).
+// Stride-2 convolutions (3 x 3 and the 1 x 1 shortcut): padded map of level r -> operand [padded rows of level r + 1][KS*KS*C] bf16.
+// One WARP per output row (a binary search over the block offsets finds its segment), lanes over the row's 16-byte vectors (8
+// channels of one tap); rows that are not interior positions of the output map are zero.
 template <int KS>
 __global__ void __launch_bounds__(256)
-emb_im2col_kernel(const __nv_bfloat16* __restrict__ in, int C, int F_in, int stride, const int32_t* __restrict__ T_in,
-                  const int32_t* __restrict__ T_out, const int64_t* __restrict__ in_off, const int64_t* __restrict__ out_off, int n_seg,
-                  int64_t total_rows, __nv_bfloat16* __restrict__ A) {
+emb_im2col_s2_kernel(const __nv_bfloat16* __restrict__ in, int C, int F_in, const int32_t* __restrict__ T_in, const int32_t* __restrict__ T_out,
+                     const int64_t* __restrict__ in_poff, const int64_t* __restrict__ out_poff, int n_seg, int64_t total_rows, __nv_bfloat16* __restrict__ A) {
     const int lane = threadIdx.x & 31;
-    const int cv_n = C >> 3, cv_shift = 31 - __clz(cv_n), vec_per_row = KS * KS * cv_n;  // C is a power of two (32 .. 256)
+    const int cv_n = C >> 3, cv_shift = 31 - __clz(cv_n), vec_per_row = KS * KS * cv_n;  // C is a power of two (32 .. 128)
+    const int F_out = F_in >> 1;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t R = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); R < total_rows; R += warps) {
-        int lo = 0, hi = n_seg - 1;  // largest seg with out_off[seg] <= R
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (__ldg(out_off + mid) <= R) lo = mid; else hi = mid - 1;
-        }
-        const int seg = lo, Ti = __ldg(T_in + seg), To = __ldg(T_out + seg);
-        const int row = (int)(R - __ldg(out_off + seg));
-        const int f = row / To, t = row - f * To;
-        const uint4* src = reinterpret_cast<const uint4*>(in) + __ldg(in_off + seg) * cv_n;
+        int seg, f1, t, To;
+        emb_locate(out_poff, T_out, n_seg, R, seg, f1, t, To);
+        const int f = f1 - 1;
+        const bool interior = f >= 0 && f < F_out && t < To;
+        const int Ti = __ldg(T_in + seg), Pi = Ti + 1;
+        const uint4* src = reinterpret_cast<const uint4*>(in) + __ldg(in_poff + seg) * cv_n;
         uint4* dst = reinterpret_cast<uint4*>(A) + R * vec_per_row;
         for (int v = lane; v < vec_per_row; v += 32) {
             const int tap = v >> cv_shift, cv = v & (cv_n - 1);
             const int ky = tap / KS, kx = tap - ky * KS;
-            const int fi = f * stride + ky - KS / 2, ti = t * stride + kx - KS / 2;
+            const int fi = f * 2 + ky - KS / 2, ti = t * 2 + kx - KS / 2;
             uint4 val = make_uint4(0, 0, 0, 0);
-            if (fi >= 0 && fi < F_in && ti >= 0 && ti < Ti) val = __ldg(src + ((int64_t)fi * Ti + ti) * cv_n + cv);
+            if (interior && fi >= 0 && fi < F_in && ti >= 0 && ti < Ti) val = __ldg(src + ((int64_t)(fi + 1) * Pi + ti) * cv_n + cv);
             dst[v] = val;
         }
     }
 }
 
-// TSTP: x [rows][256] bf16 at level 3 (F = 10) -> stats[seg][c*10 + f] = mean_t, stats[seg][2560 + c*10 + f] = sqrt(unbiased var_t + 1e-7)
-__global__ void emb_tstp_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ T3, const int64_t* __restrict__ off3,
+// TSTP: x = padded maps of level 3 (F = 10, 256 channels) -> stats[seg][c*10 + f] = mean_t, stats[seg][2560 + c*10 + f] = sqrt(unbiased var_t + 1e-7)
+__global__ void emb_tstp_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ T3, const int64_t* __restrict__ poff3,
                                 float* __restrict__ stats) {
     const int seg = blockIdx.y, f = blockIdx.x, c = threadIdx.x;  // 256 threads = channels
     const int Ts = T3[seg];
-    const __nv_bfloat16* p = x + (off3[seg] + (int64_t)f * Ts) * 256 + c;
+    const __nv_bfloat16* p = x + (poff3[seg] + (int64_t)(f + 1) * (Ts + 1)) * 256 + c;
     double s = 0.0, q = 0.0;
     for (int t = 0; t < Ts; t++) {
         const double v = (double)__bfloat162float(p[(int64_t)t * 256]);
@@ -134,6 +149,8 @@ struct wdr_emb {
     // workspaces (grown on demand)
     __nv_bfloat16 *act[4] = {nullptr, nullptr, nullptr, nullptr}, *col = nullptr;
     size_t act_cap = 0, col_cap = 0;
+    int32_t* tiles = nullptr;  // per level and 128-row tile: pitch of the map that owns it, row where that map's block starts
+    size_t tiles_cap = 0;
     wdr::DevArena io;       // host-pointer API: staged PCM + result embeddings
     wdr::DevArena scratch;  // per-group features, level tables, pooled statistics, embeddings (grow-only)
     double conv_flops = 0.0;  // of the last call (algorithmic, 2*M*N*K)
@@ -146,6 +163,22 @@ namespace wdr {
 
 // file != nullptr: the convolution comes from an ONNX export with its BatchNorm already folded (onnx_extract_resnet34): weight
 // [co][ci][k][k] and bias are used as they are; otherwise seeded tensors are drawn and folded here.
+// c_in = 32, 3 x 3, stride 1: the weights once more as [c_out][dy][4 taps][32] (dx = -1, 0, +1 and a zero phantom tap), the K layout of
+// the implicit GEMM over overlapping 64-element activation rows (gemm.cuh, conv2d = 2)
+static int emb_upload_pair_layout(wdr_emb* m, const std::vector<uint16_t>& wb, int ci, int co, int k, int stride, int K, __nv_bfloat16** out) {
+    *out = nullptr;
+    if (!(ci == 32 && k == 3 && stride == 1)) return WDR_OK;
+    std::vector<uint16_t> wp((size_t)co * 384, 0);
+    for (int o = 0; o < co; o++)
+        for (int ky = 0; ky < 3; ky++)
+            for (int kx = 0; kx < 3; kx++)
+                for (int c = 0; c < 32; c++) wp[(size_t)o * 384 + (size_t)(ky * 4 + kx) * 32 + c] = wb[(size_t)o * K + (size_t)(ky * 3 + kx) * 32 + c];
+    WDR_CUDA_TRY(cudaMalloc(out, sizeof(uint16_t) * wp.size()));
+    m->allocs.push_back(*out);
+    WDR_CUDA_TRY(cudaMemcpy(*out, wp.data(), sizeof(uint16_t) * wp.size(), cudaMemcpyHostToDevice));
+    return WDR_OK;
+}
+
 static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, int ci, int co, int k, int stride, ConvW* out, const NamedTensors* file = nullptr) {
     const int fan = ci * k * k;
     const std::string base = "resnet34." + name;
@@ -165,7 +198,10 @@ static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, i
         m->allocs.push_back(db);
         WDR_CUDA_TRY(cudaMemcpy(dw, wb.data(), sizeof(uint16_t) * wb.size(), cudaMemcpyHostToDevice));
         WDR_CUDA_TRY(cudaMemcpy(db, ib->second.data(), sizeof(float) * co, cudaMemcpyHostToDevice));
-        *out = ConvW{ci, co, k, stride, K, dw, db};
+        __nv_bfloat16* dp = nullptr;
+        const int rcp = emb_upload_pair_layout(m, wb, ci, co, k, stride, K, &dp);
+        if (rcp != WDR_OK) return rcp;
+        *out = ConvW{ci, co, k, stride, K, dw, db, dp};
         return WDR_OK;
     }
     std::vector<float> w = nn_synth(seed, base + ".weight", (size_t)co * fan, 0.0f, (float)sqrt(6.0 / fan));
@@ -197,7 +233,10 @@ static int emb_upload_conv(wdr_emb* m, uint64_t seed, const std::string& name, i
     m->allocs.push_back(db);
     WDR_CUDA_TRY(cudaMemcpy(dw, wb.data(), sizeof(uint16_t) * wb.size(), cudaMemcpyHostToDevice));
     WDR_CUDA_TRY(cudaMemcpy(db, bias.data(), sizeof(float) * co, cudaMemcpyHostToDevice));
-    *out = ConvW{ci, co, k, stride, K, dw, db};
+    __nv_bfloat16* dp = nullptr;
+    const int rcp = emb_upload_pair_layout(m, wb, ci, co, k, stride, K, &dp);
+    if (rcp != WDR_OK) return rcp;
+    *out = ConvW{ci, co, k, stride, K, dw, db, dp};
     return WDR_OK;
 }
 
@@ -226,28 +265,36 @@ struct EmbProfScope {
     }
 };
 
-static int emb_gemm(const __nv_bfloat16* A, int64_t rows, const ConvW& c, int epi, const __nv_bfloat16* resid, __nv_bfloat16* out, cudaStream_t st) {
-    GemmDesc g;
-    g.A = A; g.a_row_stride = c.K; g.rows_per_batch = (int)rows; g.n_batch = 1;
-    g.W = c.w; g.ldw = c.K; g.N = c.c_out; g.K = c.K;
-    g.epilogue = epi; g.out = out; g.ldc = c.c_out; g.bias = c.b; g.resid_bf16 = resid;
-    EmbProfScope ps(true, st);
-    return gemm_bf16(g, st);
-}
-
 struct EmbLevel {
     int F;
     std::vector<int32_t> T;
-    std::vector<int64_t> off;  // n + 1
+    std::vector<int64_t> off;  // n + 1: block offsets of the zero-padded maps (multiples of 128 rows)
+    int64_t interior = 0;      // sum of F * T: the rows a convolution really computes (FLOP accounting)
     int32_t* d_T = nullptr;
     int64_t* d_off = nullptr;
+    int32_t *d_pitch = nullptr, *d_row0 = nullptr;  // per 128-row tile
     int64_t rows() const { return off.back(); }
-    int max_rows() const {
-        int64_t m = 0;
-        for (size_t i = 0; i + 1 < off.size(); i++) m = std::max(m, off[i + 1] - off[i]);
-        return (int)m;
-    }
 };
+
+// One convolution as a GEMM.  A = nullptr: implicit (3 x 3, stride 1: the operand is the padded input map `in` itself); otherwise A is
+// a gathered operand [rows][c.K].  The output is a padded map of level `lv`.
+static int emb_gemm(const __nv_bfloat16* A, const __nv_bfloat16* in, const EmbLevel& lv, const ConvW& c, int epi, const __nv_bfloat16* resid, __nv_bfloat16* out,
+                    cudaStream_t st) {
+    GemmDesc g;
+    g.rows_per_batch = (int)lv.rows(); g.n_batch = 1;
+    g.N = c.c_out;
+    g.epilogue = epi; g.out = out; g.ldc = c.c_out; g.bias = c.b; g.resid_bf16 = resid;
+    g.tile_pitch = lv.d_pitch; g.tile_row0 = lv.d_row0; g.conv_F = lv.F;
+    if (A) {
+        g.A = A; g.a_row_stride = c.K; g.W = c.w; g.ldw = c.K; g.K = c.K; g.conv2d = 3;
+    } else if (c.c_in == 32) {
+        g.A = in; g.a_row_stride = 32; g.W = c.w_pair; g.ldw = 384; g.K = 384; g.conv2d = 2;
+    } else {
+        g.A = in; g.a_row_stride = c.c_in; g.a_cols = c.c_in; g.kb_per_tap = c.c_in / 64; g.W = c.w; g.ldw = c.K; g.K = c.K; g.conv2d = 1;
+    }
+    EmbProfScope ps(true, st);
+    return gemm_bf16(g, st);
+}
 
 template <typename T>
 static int emb_grow(T** p, size_t* cap, size_t need) {
@@ -263,7 +310,9 @@ static int emb_grow(T** p, size_t* cap, size_t need) {
 static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t>& feat_off, float* out_dev, int32_t* tab_T, int64_t* tab_off,
                        float* stats_buf, cudaStream_t st) {
     const int n = (int)feat_off.size() - 1;
+    static const int chan[4] = {32, 64, 128, 256};
     EmbLevel lv[4];
+    size_t n_tiles_all = 0;
     for (int r = 0; r < 4; r++) {
         lv[r].F = kEmbBins >> r;
         lv[r].T.resize(n);
@@ -273,11 +322,32 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
             int T = T0;
             for (int k = 0; k < r; k++) T = (T + 1) / 2;
             lv[r].T[s] = T;
-            lv[r].off[s + 1] = lv[r].off[s] + (int64_t)lv[r].F * T;
+            const int64_t block = ((int64_t)(lv[r].F + 2) * (T + 1) + 127) / 128 * 128;
+            lv[r].off[s + 1] = lv[r].off[s] + block;
+            lv[r].interior += (int64_t)lv[r].F * T;
         }
+        n_tiles_all += (size_t)(lv[r].rows() / 128);
     }
     WDR_REQUIRE(lv[0].rows() < (int64_t)1 << 31, "embedding batch too large");
+    int rc;
+    if ((rc = emb_grow(&m->tiles, &m->tiles_cap, 2 * n_tiles_all)) != WDR_OK) return rc;
     // level tables + feat offsets on the device
+    std::vector<int32_t> tiles_host(2 * n_tiles_all);
+    {
+        size_t at = 0;
+        for (int r = 0; r < 4; r++) {
+            const size_t nt = (size_t)(lv[r].rows() / 128);
+            lv[r].d_pitch = m->tiles + at;
+            lv[r].d_row0 = m->tiles + at + nt;
+            for (int s = 0; s < n; s++)
+                for (int64_t tl = lv[r].off[s] / 128; tl < lv[r].off[s + 1] / 128; tl++) {
+                    tiles_host[at + (size_t)tl] = lv[r].T[s] + 1;
+                    tiles_host[at + nt + (size_t)tl] = (int32_t)lv[r].off[s];
+                }
+            at += 2 * nt;
+        }
+    }
+    WDR_CUDA_TRY(cudaMemcpyAsync(m->tiles, tiles_host.data(), sizeof(int32_t) * tiles_host.size(), cudaMemcpyHostToDevice, st));
     for (int r = 0; r < 4; r++) {
         lv[r].d_T = tab_T + (size_t)r * n;
         lv[r].d_off = tab_off + (size_t)r * (n + 1);
@@ -286,61 +356,66 @@ static int emb_forward(wdr_emb* m, const float* feats, const std::vector<int64_t
     }
     int64_t* d_feat_off = tab_off + (size_t)4 * (n + 1);
     WDR_CUDA_TRY(cudaMemcpyAsync(d_feat_off, feat_off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, st));
-    // workspaces
-    const size_t rows0 = (size_t)lv[0].rows();
-    const size_t act_need = rows0 * 32 + 1024, col_need = rows0 * 288 + 1024;
+    // workspaces: activations of the widest level (+ slack: the C = 32 implicit GEMM views rows 64 elements wide); the gathered operands
+    // of the stem (16 columns) and of the stride-2 convolutions (9 C_in columns at the OUTPUT level's rows)
+    size_t act_need = 0, col_need = (size_t)lv[0].rows() * 16;
+    for (int r = 0; r < 4; r++) act_need = std::max(act_need, (size_t)lv[r].rows() * chan[r]);
+    for (int r = 1; r < 4; r++) col_need = std::max(col_need, (size_t)lv[r].rows() * 9 * chan[r - 1]);
+    act_need += 1024; col_need += 1024;
     if (act_need > m->act_cap) {
         for (int i = 0; i < 4; i++) { if (m->act[i]) cudaFree(m->act[i]); m->act[i] = nullptr; }
         m->act_cap = 0;
-        for (int i = 0; i < 4; i++) WDR_CUDA_TRY(cudaMalloc(&m->act[i], sizeof(__nv_bfloat16) * act_need));
+        for (int i = 0; i < 4; i++) {
+            WDR_CUDA_TRY(cudaMalloc(&m->act[i], sizeof(__nv_bfloat16) * act_need));
+            // every map is written whole before it is read, except the 32 elements behind the last row that the C = 32 implicit GEMM's
+            // 64-wide row view touches (against zero weights): they must hold finite values
+            WDR_CUDA_TRY(cudaMemsetAsync(m->act[i], 0, sizeof(__nv_bfloat16) * act_need, st));
+        }
         m->act_cap = act_need;
     }
-    int rc;
     if ((rc = emb_grow(&m->col, &m->col_cap, col_need)) != WDR_OK) return rc;
     g_emb_prof = m->prof;
-    auto blocks_for = [](int64_t work) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, 148 * 8)); };
     double flops = 0.0;
-    // conv1
+    // stem
     {
         {
             EmbProfScope ps(false, st);
-            emb_im2col_feats_kernel<<<dim3(blocks_for(lv[0].max_rows()), n), 256, 0, st>>>(feats, d_feat_off, lv[0].d_T, lv[0].d_off, m->col);
+            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((lv[0].rows() + 255) / 256, 148 * 16));
+            emb_im2col_feats_kernel<<<grid, 256, 0, st>>>(feats, d_feat_off, lv[0].d_T, lv[0].d_off, n, lv[0].rows(), m->col);
         }
         WDR_LAUNCH_CHECK();
-        if ((rc = emb_gemm(m->col, lv[0].rows(), m->conv1, EPI_BIAS_RELU_BF16, nullptr, m->act[0], st)) != WDR_OK) return rc;
-        flops += 2.0 * lv[0].rows() * 32 * 9;
+        if ((rc = emb_gemm(m->col, nullptr, lv[0], m->conv1, EPI_BIAS_RELU_BF16, nullptr, m->act[0], st)) != WDR_OK) return rc;
+        flops += 2.0 * lv[0].interior * 32 * 9;
     }
     __nv_bfloat16 *x = m->act[0], *y1 = m->act[1], *sc = m->act[2], *x2 = m->act[3];
     int level = 0;
-    auto im2col = [&](const __nv_bfloat16* in, const ConvW& c, int lin, int lout) -> int {
-        const int64_t total_rows = lv[lout].rows();
-        const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total_rows + 7) / 8, 148 * 16));
-        EmbProfScope ps(false, st);
-        if (c.k == 3)
-            emb_im2col_kernel<3><<<grid, 256, 0, st>>>(in, c.c_in, lv[lin].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off, lv[lout].d_off, n, total_rows, m->col);
-        else
-            emb_im2col_kernel<1><<<grid, 256, 0, st>>>(in, c.c_in, lv[lin].F, c.stride, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off, lv[lout].d_off, n, total_rows, m->col);
-        WDR_LAUNCH_CHECK();
-        flops += 2.0 * lv[lout].rows() * c.c_out * c.c_in * c.k * c.k;
-        return WDR_OK;
+    // a convolution of input map `in` (level lin) into a padded map of level lout
+    auto conv = [&](const __nv_bfloat16* in, const ConvW& c, int lin, int lout, int epi, const __nv_bfloat16* resid, __nv_bfloat16* out) -> int {
+        flops += 2.0 * lv[lout].interior * c.c_out * c.c_in * c.k * c.k;
+        if (c.k == 3 && c.stride == 1) return emb_gemm(nullptr, in, lv[lout], c, epi, resid, out, st);   // implicit GEMM
+        if (c.k == 1 && c.stride == 1) return emb_gemm(in, nullptr, lv[lout], c, epi, resid, out, st);   // the map itself is the operand
+        {
+            const int64_t total_rows = lv[lout].rows();
+            const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((total_rows + 7) / 8, 148 * 16));
+            EmbProfScope ps(false, st);
+            if (c.k == 3)
+                emb_im2col_s2_kernel<3><<<grid, 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off, lv[lout].d_off, n, total_rows, m->col);
+            else
+                emb_im2col_s2_kernel<1><<<grid, 256, 0, st>>>(in, c.c_in, lv[lin].F, lv[lin].d_T, lv[lout].d_T, lv[lin].d_off, lv[lout].d_off, n, total_rows, m->col);
+            WDR_LAUNCH_CHECK();
+        }
+        return emb_gemm(m->col, nullptr, lv[lout], c, epi, resid, out, st);
     };
     for (const BlockW& b : m->blocks) {
         const int lout = level + (b.c1.stride == 2 ? 1 : 0);
-        if ((rc = im2col(x, b.c1, level, lout)) != WDR_OK) return rc;
-        if ((rc = emb_gemm(m->col, lv[lout].rows(), b.c1, EPI_BIAS_RELU_BF16, nullptr, y1, st)) != WDR_OK) return rc;
+        WDR_REQUIRE(b.c1.stride == 1 || b.c1.stride == 2, "ResNet34 strides are 1 or 2");
+        if ((rc = conv(x, b.c1, level, lout, EPI_BIAS_RELU_BF16, nullptr, y1)) != WDR_OK) return rc;
         const __nv_bfloat16* resid = x;
         if (b.has_sc) {
-            if (b.sc.stride == 1) {  // 1x1 stride 1: the activation matrix itself is the GEMM operand
-                if ((rc = emb_gemm(x, lv[lout].rows(), b.sc, EPI_BIAS_BF16, nullptr, sc, st)) != WDR_OK) return rc;
-                flops += 2.0 * lv[lout].rows() * b.sc.c_out * b.sc.c_in;
-            } else {
-                if ((rc = im2col(x, b.sc, level, lout)) != WDR_OK) return rc;
-                if ((rc = emb_gemm(m->col, lv[lout].rows(), b.sc, EPI_BIAS_BF16, nullptr, sc, st)) != WDR_OK) return rc;
-            }
+            if ((rc = conv(x, b.sc, level, lout, EPI_BIAS_BF16, nullptr, sc)) != WDR_OK) return rc;
             resid = sc;
         }
-        if ((rc = im2col(y1, b.c2, lout, lout)) != WDR_OK) return rc;
-        if ((rc = emb_gemm(m->col, lv[lout].rows(), b.c2, EPI_BIAS_ADD_RELU_BF16, resid, x2, st)) != WDR_OK) return rc;
+        if ((rc = conv(y1, b.c2, lout, lout, EPI_BIAS_ADD_RELU_BF16, resid, x2)) != WDR_OK) return rc;
         std::swap(x, x2);
         level = lout;
     }
@@ -431,6 +506,7 @@ extern "C" void wdr_emb_free(wdr_emb* m) {
     cudaFree(m->lin_b);
     for (int i = 0; i < 4; i++) cudaFree(m->act[i]);
     cudaFree(m->col);
+    cudaFree(m->tiles);
     m->scratch.release();
     m->io.release();
     if (m->stream) cudaStreamDestroy(m->stream);

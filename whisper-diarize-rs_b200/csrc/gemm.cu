@@ -46,6 +46,9 @@ struct GemmParams {
     int n_split;
     int group_rows;
     int w_kb_major;  // B operand coordinates: (0, kb*N + n) instead of (kb*64, n)
+    const int32_t* tile_pitch;  // CONV: per M tile, pitch of the padded map that owns it / row where that map's block starts
+    const int32_t* tile_row0;
+    int conv_F;
     int dbg_no_a;    // measurement aid (WDR_DEBUG_GEMM_NO_A, dual-A GEMMs only): the activation tiles are not loaded at all — WRONG results;
                      // what remains is the weight stream alone, i.e. the most any activation-traffic optimisation could win
 };
@@ -68,7 +71,23 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN, int STAGES, int EPI, bool DUAL>
+// CONV (gemm.cuh, conv2d): 1 / 2 = the A rows of k-block kb are the tile's rows shifted by (dy * pitch + dx) — the 3 x 3 convolution as an
+// implicit GEMM over a zero-padded map; 1, 2, 3 = the epilogue zeroes the non-interior rows of the output map.
+// A row shift of k-block kb (and its column block) for the implicit convolution
+template <int CONV>
+__device__ __forceinline__ void conv_a_coord(int kb, int kb_per_tap, int pitch, int& kcol, int& shift) {
+    if (CONV == 1) {
+        const int tap = kb / kb_per_tap;
+        kcol = kb - tap * kb_per_tap;
+        const int ky = tap / 3;
+        shift = (ky - 1) * pitch + (tap - ky * 3) - 1;
+    } else {  // CONV == 2: (dy, pair of taps)
+        kcol = 0;
+        shift = ((kb >> 1) - 1) * pitch + ((kb & 1) << 1) - 1;
+    }
+}
+
+template <int BN, int STAGES, int EPI, bool DUAL, int CONV = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
     constexpr int kABytes = kBM * kBK * 2;
@@ -122,9 +141,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 else tma_load_2d(sB + i * kBBytes, &tma_b, &bar_full[i], kb * kBK, n_tile * BN);
             }
             pdl_wait();  // (a no-op unless launched as a programmatic dependent: then A must wait for the predecessor)
+            const int pitch0 = (CONV == 1 || CONV == 2) ? p.tile_pitch[m_tile] : 0;
             for (int i = 0; i < prefetched && !(DUAL && p.dbg_no_a); i++) {
                 const int kb = kb0 + i;
-                const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                if (CONV == 1 || CONV == 2) conv_a_coord<CONV>(kb, p.kb_per_tap, pitch0, kcol, tap);
                 tma_load_3d(sA + i * kAStage, &tma_a, &bar_full[i], kcol * kBK, mt * kBM + tap, batch);
                 if (DUAL) tma_load_3d(sA + i * kAStage + kABytes, &tma_a, &bar_full[i], kcol * kBK, mt * kBM + tap, 1);
             }
@@ -156,12 +177,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
                 const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
+                const int pitch = (CONV == 1 || CONV == 2) ? p.tile_pitch[m_tile] : 0;
                 for (int kb = kb0; kb < kb1; kb++) {
                     if (prefetched > 0) prefetched--;  // requested in the prologue: this stage is armed and both tiles are in flight
                     else {
                         mbar_wait(&bar_empty[s], ph ^ 1);
                         mbar_arrive_expect_tx(&bar_full[s], (DUAL && p.dbg_no_a) ? kBBytes : kAStage + kBBytes);
-                        const int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                        int tap = kb / p.kb_per_tap, kcol = kb - tap * p.kb_per_tap;
+                        if (CONV == 1 || CONV == 2) conv_a_coord<CONV>(kb, p.kb_per_tap, pitch, kcol, tap);
                         if (!(DUAL && p.dbg_no_a)) tma_load_3d(sA + s * kAStage, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, batch);
                         if (DUAL && !p.dbg_no_a) tma_load_3d(sA + s * kAStage + kABytes, &tma_a, &bar_full[s], kcol * kBK, mt * kBM + tap, 1);
                         if (p.w_kb_major) tma_load_2d(sB + s * kBBytes, &tma_b, &bar_full[s], 0, kb * p.N + n_tile * BN);
@@ -224,6 +247,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             const int r_in_batch = mt * kBM + q * 32 + lane;
             const bool row_ok = r_in_batch < p.rows_per_batch;
             const int64_t c_base = (int64_t)sp * p.split_stride + (int64_t)batch * p.c_batch_stride + (int64_t)(mt * kBM + q * 32) * p.ldc;
+            uint32_t interior = 0xffu;  // CONV: bit `it` = row it * 4 + rsub of this warp's 32 is an interior position of its padded map
+            if (CONV != 0) {
+                const int P = p.tile_pitch[m_tile], local0 = mt * kBM + q * 32 - p.tile_row0[m_tile];
+                interior = 0u;
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int local = local0 + it * 4 + rsub, f1 = local / P, tt = local - f1 * P;
+                    if (f1 >= 1 && f1 <= p.conv_F && tt < P - 1) interior |= 1u << it;
+                }
+            }
             bool waited = false;
 #pragma unroll 1
             for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); c++) {
@@ -315,6 +348,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                             if (EPI == EPI_BIAS_RELU_BF16 || EPI == EPI_BIAS_ADD_RELU_BF16) {
                                 v.x = fmaxf(v.x, 0.0f); v.y = fmaxf(v.y, 0.0f); v.z = fmaxf(v.z, 0.0f); v.w = fmaxf(v.w, 0.0f);
                             }
+                            if (CONV != 0 && !((interior >> it) & 1u)) v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                             uint2 w;
                             w.x = pack_bf16(v.x, v.y);
                             w.y = pack_bf16(v.z, v.w);
@@ -407,13 +441,13 @@ int num_sms() {
     return v;
 }
 
-template <int BN, int STAGES, int EPI, bool DUAL = false>
+template <int BN, int STAGES, int EPI, bool DUAL = false, int CONV = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st, bool pdl = false) {
     constexpr size_t smem = (size_t)STAGES * ((DUAL ? 2 : 1) * kBM * kBK * 2 + BN * kBK * 2) + 1024;
     static DeviceOnce attr_once;
-    WDR_CUDA_TRY(per_device_once(attr_once, [] { return cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
+    WDR_CUDA_TRY(per_device_once(attr_once, [] { return cudaFuncSetAttribute(gemm_bf16_kernel<BN, STAGES, EPI, DUAL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); }));
     int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    WDR_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, STAGES, EPI, DUAL>, dim3(grid), dim3(kGemmThreads), smem, st, pdl, ta, tb, p));
+    WDR_CUDA_TRY(launch_kernel(gemm_bf16_kernel<BN, STAGES, EPI, DUAL, CONV>, dim3(grid), dim3(kGemmThreads), smem, st, pdl, ta, tb, p));
     WDR_LAUNCH_CHECK();
     return WDR_OK;
 }
@@ -429,7 +463,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     // Wide tiles for the big encoder-side GEMMs: a 128 x 128 tile needs 32 KB of operands per 256 tensor-clocks (128 B/clk per SM,
     // at the L2 -> SM limit, measured 64-71 % of the sustained bf16 peak); 128 x 256 needs 48 KB per 512 clocks (96 B/clk).
     static const bool wide_ok = getenv("WDR_GEMM_NO_BN256") == nullptr;
-    if (wide_ok && BN == 128 && !d.dual_a && d.split_k == 1 && d.N % 256 == 0 &&
+    if (wide_ok && BN == 128 && !d.dual_a && !d.conv2d && d.split_k == 1 && d.N % 256 == 0 &&
         (int64_t)((d.rows_per_batch + kBM - 1) / kBM) * d.n_batch * (d.N / 256) >= 2 * num_sms() &&
         (d.epilogue == EPI_BIAS_BF16 || d.epilogue == EPI_BIAS_GELU_BF16 || d.epilogue == EPI_BIAS_RESID_F32 || d.epilogue == EPI_QKV_BF16 ||
          d.epilogue == EPI_BIAS_GELU_POS_F32 || d.epilogue == EPI_HEADS_BF16))
@@ -438,8 +472,24 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
     if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
     else if (d.split_k > 1 || d.bn == 64 || d.dual_a) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 / dual-A are plain fp32-partial GEMMs (EPI_F32, no bias)");
+    if (d.conv2d) {
+        WDR_REQUIRE(d.conv2d >= 1 && d.conv2d <= 3 && d.tile_pitch && d.tile_row0 && d.conv_F > 0 && d.n_batch == 1 && !d.dual_a && d.split_k == 1 && d.bn != 64,
+                    "conv2d GEMMs are single-batch plain-tile GEMMs with per-tile map tables");
+        WDR_REQUIRE(d.epilogue == EPI_BIAS_BF16 || d.epilogue == EPI_BIAS_RELU_BF16 || d.epilogue == EPI_BIAS_ADD_RELU_BF16, "conv2d epilogues: bias / bias+ReLU / bias+residual+ReLU");
+        WDR_REQUIRE(d.rows_per_batch % kBM == 0, "padded maps are blocks of whole 128-row tiles");
+        if (d.conv2d == 1) WDR_REQUIRE(d.a_cols > 0 && d.a_cols % kBK == 0 && d.K == 9 * d.a_cols && d.kb_per_tap == d.a_cols / kBK && d.a_row_stride == d.a_cols, "conv2d = 1: K = 9 C, C a multiple of 64");
+        if (d.conv2d == 2) WDR_REQUIRE(d.a_row_stride == 32 && d.K == 6 * kBK, "conv2d = 2: C = 32, K = 3 x 128");
+    }
     CUtensorMap ta, tb;
-    {
+    if (d.conv2d == 1 || d.conv2d == 2) {
+        // the activation matrix itself: [rows][C] (C >= 64), or overlapping 64-element rows at a 32-element stride (C = 32: the caller's
+        // buffer holds 32 elements of slack behind the last row).  Shifted tiles reach before row 0 / behind the last row: zero fill.
+        const uint64_t dims[3] = {(uint64_t)(d.conv2d == 1 ? d.a_cols : 64), (uint64_t)d.rows_per_batch, 1};
+        const uint64_t str[2] = {(uint64_t)d.a_row_stride * 2, (uint64_t)d.a_row_stride * 2 * (uint64_t)d.rows_per_batch};
+        const uint32_t box[3] = {kBK, kBM, 1};
+        int rc = make_tmap_bf16(&ta, d.A, 3, dims, str, box);
+        if (rc != WDR_OK) return rc;
+    } else {
         // in tap mode the last tap reads rows up to rows_per_batch - 1 + (taps - 1): the caller's buffer holds them
         const int num_kb = (d.K + kBK - 1) / kBK;
         const int taps = d.kb_per_tap > 0 ? (num_kb + d.kb_per_tap - 1) / d.kb_per_tap : 1;
@@ -485,6 +535,7 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     p.out_t = d.out_t; p.ldt = d.ldt; p.n_split = d.n_split;
     p.group_rows = d.group_rows;
     p.w_kb_major = d.w_kb_major ? 1 : 0;
+    p.tile_pitch = d.tile_pitch; p.tile_row0 = d.tile_row0; p.conv_F = d.conv_F;
     static const int dbg_no_a = getenv("WDR_DEBUG_GEMM_NO_A") ? 1 : 0;
     p.dbg_no_a = dbg_no_a;
     if (d.epilogue == EPI_HEADS_BF16) WDR_REQUIRE(d.group_rows > 0 && d.n_batch == 1 && d.N % 128 == 0, "EPI_HEADS_BF16 needs group_rows, one batch and N = 2 * heads * 64");
@@ -499,6 +550,20 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
             case EPI_HEADS_BF16: return launch_gemm<256, 4, EPI_HEADS_BF16>(ta, tb, p, st);
             default: break;
         }
+    }
+    if (d.conv2d) {
+#define WDR_CONV_CASE(E) \
+        case E: return d.conv2d == 1 ? launch_gemm<128, 5, E, false, 1>(ta, tb, p, st) : d.conv2d == 2 ? launch_gemm<128, 5, E, false, 2>(ta, tb, p, st) \
+                                                                                       : launch_gemm<128, 5, E, false, 3>(ta, tb, p, st);
+        switch (d.epilogue) {
+            WDR_CONV_CASE(EPI_BIAS_BF16)
+            WDR_CONV_CASE(EPI_BIAS_RELU_BF16)
+            case EPI_BIAS_ADD_RELU_BF16: WDR_REQUIRE(d.resid_bf16, "resid_bf16 missing");
+                return d.conv2d == 1 ? launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16, false, 1>(ta, tb, p, st) : d.conv2d == 2 ? launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16, false, 2>(ta, tb, p, st)
+                                                                                                            : launch_gemm<128, 5, EPI_BIAS_ADD_RELU_BF16, false, 3>(ta, tb, p, st);
+            default: break;
+        }
+#undef WDR_CONV_CASE
     }
     switch (d.epilogue) {
         case EPI_BIAS_BF16: return launch_gemm<128, 5, EPI_BIAS_BF16>(ta, tb, p, st);

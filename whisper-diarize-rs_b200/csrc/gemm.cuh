@@ -63,6 +63,20 @@ struct GemmDesc {
     bool pdl = false;
     // W is k-block-major [K/64][N][64] (decoder weights, model.cu: to_kb_major): a tile's rows are contiguous for each k-block
     bool w_kb_major = false;
+    // Implicit-GEMM 3 x 3 convolution (stride 1) over zero-padded 2-D maps stored as packed rows (embedding.cu: position (f, t) of a map
+    // with pitch P = T + 1 is row (f + 1) * P + t of its block; row f = -1, row f = F and column t = T are zero).  The A operand is the
+    // activation matrix itself — no im2col:
+    //   conv2d = 1: C a multiple of 64, K = 9 C; k-block kb = (tap, 64-channel chunk); tap (dy, dx) reads the tile's rows shifted by dy P + dx;
+    //   conv2d = 2: C = 32; A is viewed as OVERLAPPING 64-element rows (the channels of a position and of the next one), K = 3 x 128:
+    //               k-block (dy, pair): pair 0 = taps dx = -1, 0; pair 1 = taps dx = +1, "+2" (the weights of the phantom tap are zero).
+    //   conv2d = 3: plain GEMM whose output is such a map (stem, stride-2 and 1 x 1 convolutions over a materialised operand).
+    // tile_pitch / tile_row0: per 128-row M tile, the pitch of the map that owns it and the row where that map's block starts (blocks are
+    // multiples of 128 rows, so a tile never straddles two maps); conv_F: rows of a map.  The epilogue writes ZERO at every non-interior
+    // position, so the output is again a zero-padded map.  EPI_BIAS_BF16 / EPI_BIAS_RELU_BF16 / EPI_BIAS_ADD_RELU_BF16 only.
+    int conv2d = 0;
+    const int32_t* tile_pitch = nullptr;
+    const int32_t* tile_row0 = nullptr;
+    int conv_F = 0;
 };
 
 int gemm_bf16(const GemmDesc& d, cudaStream_t st);
