@@ -30,7 +30,7 @@ int fbank_run(const int16_t* pcm, const int64_t* seg_offset_dev, const int64_t* 
               int n_bins, int subtract_mean, float* out, cudaStream_t st);
 
 constexpr int kEmbDimDefault = 256, kEmbBins = 80, kEmbPooled = 5120;  // the width is a property of the loaded model (seg_1 rows): 256 for WeSpeaker ResNet34
-constexpr int kEmbMaxFramesPerGroup = 8192;  // fbank frames per forward batch (bounds the im2col workspace: 80 * frames * 288 bf16)
+constexpr int kEmbMaxFramesPerGroup = 32768;  // fbank frames per forward batch (bounds the im2col workspace: 80 * frames * 288 bf16)
 
 struct ConvW {
     int c_in, c_out, k, stride, K;  // K = GEMM inner size (k*k*c_in, conv1: 16)
