@@ -285,6 +285,7 @@ static int emb_gemm(const __nv_bfloat16* A, const __nv_bfloat16* in, const EmbLe
     g.N = c.c_out;
     g.epilogue = epi; g.out = out; g.ldc = c.c_out; g.bias = c.b; g.resid_bf16 = resid;
     g.tile_pitch = lv.d_pitch; g.tile_row0 = lv.d_row0; g.conv_F = lv.F;
+    g.bn = c.c_out <= 64 ? 64 : 128;
     if (A) {
         g.A = A; g.a_row_stride = c.K; g.W = c.w; g.ldw = c.K; g.K = c.K; g.conv2d = 3;
     } else if (c.c_in == 32) {

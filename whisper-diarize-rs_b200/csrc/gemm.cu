@@ -172,12 +172,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            // CONV: the pitch of a tile's map comes from global memory; it is fetched one tile ahead so that its latency never sits
+            // between two tiles' loads
+            int pitch_next = ((CONV == 1 || CONV == 2) && blockIdx.x < p.total_tiles) ? p.tile_pitch[(blockIdx.x / p.splits) / p.n_tiles] : 0;
             for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
                 const int t = w / p.splits, sp = w - t * p.splits;
                 const int m_tile = t / p.n_tiles, n_tile = t - m_tile * p.n_tiles;
                 const int batch = m_tile / p.tiles_per_batch, mt = m_tile - batch * p.tiles_per_batch;
                 const int kb0 = sp * p.kb_per_split, kb1 = min(num_kb, kb0 + p.kb_per_split);
-                const int pitch = (CONV == 1 || CONV == 2) ? p.tile_pitch[m_tile] : 0;
+                const int pitch = pitch_next;
+                if ((CONV == 1 || CONV == 2) && w + (int)gridDim.x < p.total_tiles) pitch_next = p.tile_pitch[((w + (int)gridDim.x) / p.splits) / p.n_tiles];
                 for (int kb = kb0; kb < kb1; kb++) {
                     if (prefetched > 0) prefetched--;  // requested in the prologue: this stage is armed and both tiles are in flight
                     else {
@@ -267,6 +271,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 // operands that do not depend on the accumulator are fetched before waiting for it
                 float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.bias && col_ok) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+                uint2 rres[8];  // EPI_BIAS_ADD_RELU_BF16: the residual's four bf16 of every row this lane stores
+                if (EPI == EPI_BIAS_ADD_RELU_BF16) {
+#pragma unroll
+                    for (int it = 0; it < 8; it++) {
+                        const int row = it * 4 + rsub;
+                        rres[it] = make_uint2(0u, 0u);
+                        if (mt * kBM + q * 32 + row < p.rows_per_batch && col_ok) rres[it] = *reinterpret_cast<const uint2*>(p.resid_bf16 + c_base + (int64_t)row * p.ldc + n);
+                    }
+                }
                 float4 extra[8];
                 if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_GELU_POS_F32) {
 #pragma unroll
@@ -340,7 +353,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         } else if (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_QKV_BF16 || EPI == EPI_BIAS_RELU_BF16 ||
                                    EPI == EPI_BIAS_ADD_RELU_BF16) {
                             if (EPI == EPI_BIAS_ADD_RELU_BF16) {
-                                const uint2 rr = *reinterpret_cast<const uint2*>(p.resid_bf16 + off);
+                                const uint2 rr = rres[it];
                                 const float2 r0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.x));
                                 const float2 r1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr.y));
                                 v.x += r0.x; v.y += r0.y; v.z += r1.x; v.w += r1.y;
@@ -471,9 +484,9 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
     g_last_bn = BN;
     WDR_REQUIRE(d.split_k >= 1, "split_k must be >= 1");
     if (d.epilogue == EPI_BIAS_GELU_SPLIT) WDR_REQUIRE(d.dual_a && d.split_k == 1 && d.bn == 64 && d.bias && d.split_stride > 0, "EPI_BIAS_GELU_SPLIT is the decoder fc1 GEMM (dual-A, BN=64, no split-K)");
-    else if (d.split_k > 1 || d.bn == 64 || d.dual_a) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 / dual-A are plain fp32-partial GEMMs (EPI_F32, no bias)");
+    else if (d.split_k > 1 || (d.bn == 64 && !d.conv2d) || d.dual_a) WDR_REQUIRE(d.epilogue == EPI_F32 && (d.split_k == 1 || !d.bias), "split-K / BN=64 / dual-A are plain fp32-partial GEMMs (EPI_F32, no bias)");
     if (d.conv2d) {
-        WDR_REQUIRE(d.conv2d >= 1 && d.conv2d <= 3 && d.tile_pitch && d.tile_row0 && d.conv_F > 0 && d.n_batch == 1 && !d.dual_a && d.split_k == 1 && d.bn != 64,
+        WDR_REQUIRE(d.conv2d >= 1 && d.conv2d <= 3 && d.tile_pitch && d.tile_row0 && d.conv_F > 0 && d.n_batch == 1 && !d.dual_a && d.split_k == 1,
                     "conv2d GEMMs are single-batch plain-tile GEMMs with per-tile map tables");
         WDR_REQUIRE(d.epilogue == EPI_BIAS_BF16 || d.epilogue == EPI_BIAS_RELU_BF16 || d.epilogue == EPI_BIAS_ADD_RELU_BF16, "conv2d epilogues: bias / bias+ReLU / bias+residual+ReLU");
         WDR_REQUIRE(d.rows_per_batch % kBM == 0, "padded maps are blocks of whole 128-row tiles");
@@ -550,6 +563,20 @@ int gemm_bf16(const GemmDesc& d, cudaStream_t st) {
             case EPI_HEADS_BF16: return launch_gemm<256, 4, EPI_HEADS_BF16>(ta, tb, p, st);
             default: break;
         }
+    }
+    if (d.conv2d && BN == 64) {  // N <= 64: half the B rows and half the MMA width of a 128-wide tile whose upper columns would be padding
+#define WDR_CONV64_CASE(E) \
+        case E: return d.conv2d == 1 ? launch_gemm<64, 7, E, false, 1>(ta, tb, p, st) : d.conv2d == 2 ? launch_gemm<64, 7, E, false, 2>(ta, tb, p, st) \
+                                                                                       : launch_gemm<64, 7, E, false, 3>(ta, tb, p, st);
+        switch (d.epilogue) {
+            WDR_CONV64_CASE(EPI_BIAS_BF16)
+            WDR_CONV64_CASE(EPI_BIAS_RELU_BF16)
+            case EPI_BIAS_ADD_RELU_BF16: WDR_REQUIRE(d.resid_bf16, "resid_bf16 missing");
+                return d.conv2d == 1 ? launch_gemm<64, 7, EPI_BIAS_ADD_RELU_BF16, false, 1>(ta, tb, p, st) : d.conv2d == 2 ? launch_gemm<64, 7, EPI_BIAS_ADD_RELU_BF16, false, 2>(ta, tb, p, st)
+                                                                                                           : launch_gemm<64, 7, EPI_BIAS_ADD_RELU_BF16, false, 3>(ta, tb, p, st);
+            default: break;
+        }
+#undef WDR_CONV64_CASE
     }
     if (d.conv2d) {
 #define WDR_CONV_CASE(E) \
