@@ -375,11 +375,11 @@ def run_diarize(args):
                 "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": int(pcm.nbytes + cat.nbytes), "d2h_bytes_per_step": int(E.nbytes + 60 * 589 * 7 * 4),
                         "api": "host.diarize: wdr_seg_get_segments + wdr_emb_compute_batch_i16 + wdr_cosine_matrix + wdr_cluster_leader (host pointers)"},
                 "gpu_launches": int(launches), "clocks": clocks, "stages": stages, "fbank_kernel": fb,
-                "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05): the 36 convolutions of the ResNet34 embedding stage as GEMMs over a materialised im2col "
-                                                          "(CUDA events around the GEMM launches only)",
+                "roofline": {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05): the 36 convolutions of the ResNet34 embedding stage — 29 as implicit GEMMs over the zero-padded "
+                                                          "activation maps, the stem and the stride-2 ones over a gathered operand (CUDA events around the GEMM launches only)",
                              "achieved": ach_gemm, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach_gemm / tf_peak, "traffic": None,
                              "algorithmic_gflop_per_step": flops / 1e9, "gemm_ms": gemm_ms, "im2col_gather_ms": gather_ms,
-                             "whole_stage": {"achieved": ach, "frac": ach / tf_peak, "note": "whole embedding call incl. fbank, im2col gathers, H2D / D2H"}}}
+                             "whole_stage": {"achieved": ach, "frac": ach / tf_peak, "note": "whole embedding call incl. fbank, operand gathers of the stem / stride-2 stages, H2D / D2H"}}}
         if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only
             cpu_threads = claim_cpu_threads()
             t_seg, t_emb = diar_cpu(pcm, 2, 4)
