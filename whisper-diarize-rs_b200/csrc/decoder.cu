@@ -648,16 +648,16 @@ constexpr int kDtwpMaxT = 256;  // longest teacher-forced sequence (sot, lang, n
 // (row stride 65: conflict-free for "lane = key" and "lane = column" accesses alike); one warp per query.
 __global__ void __launch_bounds__(256)
 dtwp_self_attn_kernel(const float* __restrict__ qkv /* [M][3d] */, const float* __restrict__ b_qkv, const int32_t* __restrict__ row_off,
-                      const int32_t* __restrict__ T, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off) {
+                      const int32_t* __restrict__ T, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off, int cap_T /* >= every T_b: sizes the shared arrays */) {
     extern __shared__ float sm[];
     const int hh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int T_b = T[b];
     if (T_b <= 0) return;
     const int64_t r0 = row_off[b];
     float* Ks = sm;                       // [T_b][65]
-    float* Vs = Ks + kDtwpMaxT * 65;      // [T_b][65]
-    float* qs = Vs + kDtwpMaxT * 65;      // [8][64]
-    float* ps = qs + 8 * 64;              // [8][kDtwpMaxT]
+    float* Vs = Ks + cap_T * 65;          // [T_b][65]
+    float* qs = Vs + cap_T * 65;          // [8][64]
+    float* ps = qs + 8 * 64;              // [8][cap_T]
     for (int e = tid; e < T_b * 64; e += 256) {
         const int t = e >> 6, c = e & 63;
         const float* src = qkv + (r0 + t) * 3 * (int64_t)d + hh * 64 + c;
@@ -667,7 +667,7 @@ dtwp_self_attn_kernel(const float* __restrict__ qkv /* [M][3d] */, const float* 
     }
     __syncthreads();
     float* q = qs + warp * 64;
-    float* p = ps + warp * kDtwpMaxT;
+    float* p = ps + warp * cap_T;
     for (int i = warp; i < T_b; i += 8) {
         const float* src = qkv + (r0 + i) * 3 * (int64_t)d + hh * 64;
         q[lane] = src[lane] + b_qkv[hh * 64 + lane];
@@ -1802,12 +1802,17 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
     WDR_CUDA_TRY(cudaMemcpyAsync(pw.row_off, row_off.data(), sizeof(int32_t) * kDecMaxWindows, cudaMemcpyHostToDevice, st));
     WDR_CUDA_TRY(cudaStreamSynchronize(st));  // the staging vectors die with this frame
     static DeviceOnce attr_once;
-    const int smem_self = (int)sizeof(float) * (2 * kDtwpMaxT * 65 + 8 * 64 + 8 * kDtwpMaxT);
+    // shared arrays sized by this batch's longest sequence, not by the 256-token bound: at ~130 tokens three CTAs fit an SM instead of one
+    const int smem_self_max = (int)sizeof(float) * (2 * kDtwpMaxT * 65 + 8 * 64 + 8 * kDtwpMaxT);
+    int cap_T = 8;
+    for (int b = 0; b < B; b++) cap_T = std::max(cap_T, (int)T_host[b]);
+    cap_T = (cap_T + 7) / 8 * 8;
+    const int smem_self = (int)sizeof(float) * (2 * cap_T * 65 + 8 * 64 + 8 * cap_T);
     const int smem_cross = (int)sizeof(float) * (kDtwpQB * 64 + kDtwpQB * kDtwpPStride);
     const int smem_cross_mma = (int)sizeof(float) * (kDtwpQB * kMqQPitch + kDtwpQB * kMqPitch);
     static const bool cross_ffma = getenv("WDR_DTWP_FFMA") != nullptr;  // A/B knob: the fp32-FMA kernel instead of the tensor-core one
     WDR_CUDA_TRY(per_device_once(attr_once, [&] {
-        cudaError_t e = cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self);
+        cudaError_t e = cudaFuncSetAttribute(dtwp_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_self_max);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(dtwp_cross_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross_mma);
         return e != cudaSuccess ? e : cudaFuncSetAttribute(dtwp_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cross);
     }));
@@ -1834,7 +1839,7 @@ int decoder_dtw_pass(const wdr_context* ctx, DecoderWorkspace& ws, DtwPassWorksp
         if ((rc = packed_gemm(pw.h, M, Mc, e.w_qkv, 3 * d, d, pw.part, st, prof)) != WDR_OK) return rc;
         {
             ProfScope ps(prof, KC_DECODER, st);
-            dtwp_self_attn_kernel<<<dim3(H, B), 256, smem_self, st>>>(pw.part, e.b_qkv, pw.row_off, ws.aw_T, d, pw.att, Mc * d);
+            dtwp_self_attn_kernel<<<dim3(H, B), 256, smem_self, st>>>(pw.part, e.b_qkv, pw.row_off, ws.aw_T, d, pw.att, Mc * d, cap_T);
             WDR_LAUNCH_CHECK();
         }
         if ((rc = packed_gemm(pw.att, M, Mc, e.w_o, d, d, pw.part, st, prof)) != WDR_OK) return rc;
