@@ -193,7 +193,9 @@ dec_ln_kernel(float* __restrict__ x, const float* __restrict__ part, int n_split
 // each chunk from shared memory.  The new position's k / v never make the global round trip: they are patched into the chunk that
 // holds them.  Scores: lane = key position (one fmaf chain in column order); softmax by warp shuffles; P V: lane = two adjacent
 // columns, one fmaf chain in position order.
-constexpr int kSelfMaxHeadsPerCta = 1;
+// Four heads (warps) per CTA: with one-warp CTAs the 2400 CTA launches of a 120-window large-v3 batch (16 per SM, one after the other)
+// were themselves a large part of the kernel's ~16 us floor (ncu, L2-warm, pos 110: 16.6 us).
+constexpr int kSelfMaxHeadsPerCta = 4;
 __device__ __forceinline__ int64_t self_k_off(int t, int c) { return (int64_t)(t >> 5) * 2048 + (c >> 3) * 256 + (t & 31) * 8 + (c & 7); }
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
@@ -203,18 +205,22 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 // ANC = beam search / fallback rows (history read through the ancestry table); the greedy instantiation carries none of that code.
 template <bool ANC>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(kSelfMaxHeadsPerCta * 32)
 dec_self_attn_kernel(const float* __restrict__ part, int n_splits, int64_t split_stride, const float* __restrict__ b_qkv,
                      __half* __restrict__ sk, __half* __restrict__ sv, const int32_t* __restrict__ pos_ptr, int pos, int d, __nv_bfloat16* __restrict__ att, int64_t lo_off,
                      const DecWinState* __restrict__ win /* decode: skip finished windows */, const int32_t* __restrict__ t_limit /* forced pass: window length */,
                      const int32_t* __restrict__ anc /* beam search: [rows][anc_ld = 448] row that holds position t of this row's history; null = own row */,
                      int anc_ld) {
-    __shared__ __align__(16) unsigned char ring[2][4096];
-    __shared__ __align__(16) float q[64];
-    __shared__ float p[kDecSeqCap];
-    __shared__ int32_t as_[ANC ? kDecSeqCap : 1];
-    const int lane = threadIdx.x;
-    const int hh = blockIdx.x, b = blockIdx.y;
+    __shared__ __align__(16) unsigned char ring_[kSelfMaxHeadsPerCta][2][4096];
+    __shared__ __align__(16) float q_[kSelfMaxHeadsPerCta][64];
+    __shared__ float p_[kSelfMaxHeadsPerCta][kDecSeqCap];
+    __shared__ int32_t as__[ANC ? kSelfMaxHeadsPerCta : 1][ANC ? kDecSeqCap : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int hh = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
+    unsigned char (*ring)[4096] = ring_[warp];
+    float* q = q_[warp];
+    float* p = p_[warp];
+    int32_t* as_ = as__[ANC ? warp : 0];
     pdl_launch_dependents();
     pdl_wait();
     pos = load_pos(pos_ptr, pos);
