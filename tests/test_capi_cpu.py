@@ -29,6 +29,39 @@ def test_library_exports_every_declared_symbol(wdr):
     assert not missing, f"declared in include/*.h but not exported: {missing}"
 
 
+def test_library_carries_blackwell_tensor_and_tma_code(wdr):
+    """The hot kernels are what they claim to be: the SASS of the built library holds tcgen05 MMAs (UTCHMMA) with TMEM loads (LDTM), TMA
+    tensor loads (UTMALDG), the warp-level MMAs of the multi-query cross-attention (HMMA), async global -> shared copies (LDGSTS) and packed
+    fp32 FMAs (FFMA2) — and was built for sm_100a."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "-sass", wdr.lib_path()], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    per_kernel = {}
+    cur = None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            per_kernel[cur] = set()
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur:
+            per_kernel[cur].add(m.group(1))
+
+    def has(kernel_substr, op):
+        return any(kernel_substr in k and op in ops for k, ops in per_kernel.items())
+
+    assert has("gemm_bf16_kernel", "UTCHMMA") and has("gemm_bf16_kernel", "UTMALDG") and has("gemm_bf16_kernel", "LDTM")
+    assert has("encoder_attention_kernel", "UTCHMMA") and has("encoder_attention_kernel", "LDTM")
+    assert has("dtwp_cross_attn_mma_kernel", "HMMA") and has("dec_cross_attn_rows_mma_kernel", "HMMA")
+    assert has("dec_self_attn_kernel", "LDGSTS")
+    assert has("dtwp_cross_attn_kernel", "FFMA2")
+
+
 def test_version_and_shape_helpers(wdr):
     assert "sm_100a" in wdr.version()
     assert wdr.mel_n_len(480000) == 6000 and wdr.mel_n_len(0) == 3000

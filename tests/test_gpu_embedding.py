@@ -1,5 +1,5 @@
 """GPU parity of the speaker-embedding path (reference src/transcribe.rs:343, 466-467) through the C ABI:
-Kaldi fbank -> WeSpeaker ResNet34 (tcgen05 GEMMs over im2col, bf16 activations) -> TSTP -> Linear, against oracle/resnet.py
+Kaldi fbank -> WeSpeaker ResNet34 (tcgen05 GEMMs — implicit GEMMs over zero-padded activation maps —, bf16 activations) -> TSTP -> Linear, against oracle/resnet.py
 (fp32 activations, the same bf16-rounded folded weights).
 
 Tolerance: the library keeps activations in bf16 between the 36 convolutions, the oracle in fp32, so the embedding agrees to bf16
