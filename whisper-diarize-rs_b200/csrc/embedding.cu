@@ -27,7 +27,7 @@
 namespace wdr {
 
 int fbank_run(const int16_t* pcm, const int64_t* seg_offset_dev, const int64_t* feat_offset_dev, const std::vector<int64_t>& seg_offset_host,
-              int n_bins, int subtract_mean, float* out, cudaStream_t st);
+              int n_bins, int subtract_mean, float* out, cudaStream_t st, const int64_t* seg_end_dev, const std::vector<int64_t>* seg_end_host);
 
 constexpr int kEmbDimDefault = 256, kEmbBins = 80, kEmbPooled = 5120;  // the width is a property of the loaded model (seg_1 rows): 256 for WeSpeaker ResNet34
 constexpr int kEmbMaxFramesPerGroup = 32768;  // fbank frames per forward batch (bounds the im2col workspace: 80 * frames * 288 bf16)
@@ -570,18 +570,19 @@ static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector
             fo[k + 1] = fo[k] + wdr_fbank_frames((int)(seg_off[s + 1] - seg_off[s]));
         }
         struct { float* p; } feats, emb;
-        struct { int64_t* p; } d_so, d_fo;
+        struct { int64_t* p; } d_so, d_fo, d_se;
         int rc;
         {
             DevArena& A = m->scratch;
             const size_t need = DevArena::padded(sizeof(float) * frames * kEmbBins) + DevArena::padded(sizeof(float) * g * m->emb_dim) +
-                                2 * DevArena::padded(sizeof(int64_t) * (g + 2)) + DevArena::padded(sizeof(int32_t) * 4 * g) +
+                                3 * DevArena::padded(sizeof(int64_t) * (g + 2)) + DevArena::padded(sizeof(int32_t) * 4 * g) +
                                 DevArena::padded(sizeof(int64_t) * 5 * (g + 1)) + DevArena::padded(sizeof(float) * g * kEmbPooled);
             if ((rc = A.reserve(need)) != WDR_OK) return rc;
             feats.p = A.take<float>((size_t)frames * kEmbBins);
             emb.p = A.take<float>((size_t)g * m->emb_dim);
             d_fo.p = A.take<int64_t>((size_t)g + 2);
             d_so.p = A.take<int64_t>((size_t)g + 2);
+            d_se.p = A.take<int64_t>((size_t)g + 2);
         }
         WDR_CUDA_TRY(cudaMemcpyAsync(d_fo.p, fo.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
         if (contiguous) {
@@ -590,24 +591,18 @@ static int emb_compute_dev(wdr_emb* m, const int16_t* pcm_dev, const std::vector
             s2[g] = seg_off[live[i0 + g - 1] + 1];
             WDR_CUDA_TRY(cudaMemcpyAsync(d_so.p, s2.data(), sizeof(int64_t) * (g + 1), cudaMemcpyHostToDevice, st));
             WDR_CUDA_TRY(cudaStreamSynchronize(st));
-            rc = fbank_run(pcm_dev, d_so.p, d_fo.p, s2, kEmbBins, 1, feats.p, st);
+            rc = fbank_run(pcm_dev, d_so.p, d_fo.p, s2, kEmbBins, 1, feats.p, st, nullptr, nullptr);
             if (rc != WDR_OK) return rc;
         } else {
-            // one fbank launch per contiguous run
-            int k0 = 0;
-            while (k0 < g) {
-                int k1 = k0 + 1;
-                while (k1 < g && seg_off[live[i0 + k1]] == seg_off[live[i0 + k1 - 1] + 1]) k1++;
-                std::vector<int64_t> s2((size_t)(k1 - k0) + 1);
-                for (int k = k0; k < k1; k++) s2[k - k0] = seg_off[live[i0 + k]];
-                s2[k1 - k0] = seg_off[live[i0 + k1 - 1] + 1];
-                WDR_CUDA_TRY(cudaMemcpyAsync(d_so.p, s2.data(), sizeof(int64_t) * s2.size(), cudaMemcpyHostToDevice, st));
-                WDR_CUDA_TRY(cudaStreamSynchronize(st));
-                rc = fbank_run(pcm_dev, d_so.p, d_fo.p + k0, s2, kEmbBins, 1, feats.p, st);
-                if (rc != WDR_OK) return rc;
-                WDR_CUDA_TRY(cudaStreamSynchronize(st));  // d_so is reused by the next run
-                k0 = k1;
-            }
+            // segments that are not back to back in pcm (the short ones in between were skipped): explicit [start, end) pairs, ONE launch
+            // (round 1 launched the fbank once per contiguous run — 39 launch pairs and stream synchronisations per 10 min recording)
+            std::vector<int64_t> s2((size_t)g), e2((size_t)g);
+            for (int k = 0; k < g; k++) { s2[k] = seg_off[live[i0 + k]]; e2[k] = seg_off[live[i0 + k] + 1]; }
+            WDR_CUDA_TRY(cudaMemcpyAsync(d_so.p, s2.data(), sizeof(int64_t) * g, cudaMemcpyHostToDevice, st));
+            WDR_CUDA_TRY(cudaMemcpyAsync(d_se.p, e2.data(), sizeof(int64_t) * g, cudaMemcpyHostToDevice, st));
+            WDR_CUDA_TRY(cudaStreamSynchronize(st));
+            rc = fbank_run(pcm_dev, d_so.p, d_fo.p, s2, kEmbBins, 1, feats.p, st, d_se.p, &e2);
+            if (rc != WDR_OK) return rc;
         }
         {
             int32_t* tab_T = m->scratch.take<int32_t>((size_t)4 * g);

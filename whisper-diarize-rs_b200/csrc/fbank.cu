@@ -39,8 +39,8 @@ static FbankTables g_fb[16];  // per device
 
 // grid: (cta index within the launch); cta_map[blockIdx.x] = {segment, first frame}
 __global__ void __launch_bounds__(kFbThreads, 2)
-fbank_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ seg_offset, const int64_t* __restrict__ feat_offset,
-             const int2* __restrict__ cta_map, const float* __restrict__ window_g, const cpx* __restrict__ tw512_g,
+fbank_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ seg_offset, const int64_t* __restrict__ seg_end /* null: segment s ends where s + 1 starts */,
+             const int64_t* __restrict__ feat_offset, const int2* __restrict__ cta_map, const float* __restrict__ window_g, const cpx* __restrict__ tw512_g,
              const float* __restrict__ fw, const int4* __restrict__ frow, int n_bins, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);
@@ -54,7 +54,7 @@ fbank_kernel(const int16_t* __restrict__ pcm, const int64_t* __restrict__ seg_of
     const int2 cm = cta_map[blockIdx.x];
     const int seg = cm.x, frame0 = cm.y;
     const int64_t s_begin = seg_offset[seg];
-    const int n = (int)(seg_offset[seg + 1] - s_begin);
+    const int n = (int)((seg_end ? seg_end[seg] : seg_offset[seg + 1]) - s_begin);
     const int T = (n < FB_FLEN) ? 0 : 1 + (n - FB_FLEN) / FB_SHIFT;
     const int frames_here = min(FB_FRAMES_PER_CTA, T - frame0);
     if (frames_here <= 0) return;
@@ -182,16 +182,18 @@ static int fbank_tables(int n_bins, FbankTables** out_tab) {
     return WDR_OK;
 }
 
-// seg_offset_host: n_segments+1 sample offsets (host copy, used to build the CTA map).
+// seg_offset_host: n_segments+1 sample offsets (host copy, used to build the CTA map).  seg_end_dev / seg_end_host (both or neither):
+// segments that are NOT back to back in pcm — segment s then spans [seg_offset[s], seg_end[s]) and seg_offset_host holds n_segments starts.
 int fbank_run(const int16_t* pcm, const int64_t* seg_offset_dev, const int64_t* feat_offset_dev,
-              const std::vector<int64_t>& seg_offset_host, int n_bins, int subtract_mean, float* out, cudaStream_t st) {
+              const std::vector<int64_t>& seg_offset_host, int n_bins, int subtract_mean, float* out, cudaStream_t st,
+              const int64_t* seg_end_dev, const std::vector<int64_t>* seg_end_host) {
     FbankTables* tab = nullptr;
     int rc = fbank_tables(n_bins, &tab);
     if (rc != WDR_OK) return rc;
-    const int n_segments = (int)seg_offset_host.size() - 1;
+    const int n_segments = seg_end_host ? (int)seg_end_host->size() : (int)seg_offset_host.size() - 1;
     std::vector<int2> map;
     for (int s = 0; s < n_segments; s++) {
-        const int64_t n = seg_offset_host[s + 1] - seg_offset_host[s];
+        const int64_t n = (seg_end_host ? (*seg_end_host)[s] : seg_offset_host[s + 1]) - seg_offset_host[s];
         const int T = n < FB_FLEN ? 0 : (int)(1 + (n - FB_FLEN) / FB_SHIFT);
         for (int f = 0; f < T; f += FB_FRAMES_PER_CTA) map.push_back(make_int2(s, f));
     }
@@ -199,7 +201,7 @@ int fbank_run(const int16_t* pcm, const int64_t* seg_offset_dev, const int64_t* 
     int2* d_map = nullptr;
     WDR_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_map), sizeof(int2) * map.size(), st));
     WDR_CUDA_TRY(cudaMemcpyAsync(d_map, map.data(), sizeof(int2) * map.size(), cudaMemcpyHostToDevice, st));
-    fbank_kernel<<<(unsigned)map.size(), kFbThreads, kFbSmemBytes, st>>>(pcm, seg_offset_dev, feat_offset_dev, d_map, tab->d_window,
+    fbank_kernel<<<(unsigned)map.size(), kFbThreads, kFbSmemBytes, st>>>(pcm, seg_offset_dev, seg_end_dev, feat_offset_dev, d_map, tab->d_window,
                                                                          tab->d_tw512, tab->d_fw, tab->d_frow, n_bins, out);
     WDR_LAUNCH_CHECK();
     WDR_CUDA_TRY(cudaFreeAsync(d_map, st));
@@ -235,7 +237,7 @@ extern "C" int wdr_kaldi_fbank_i16(const int16_t* pcm, int n, int n_bins, int su
     WDR_CUDA_TRY(cudaMemcpy(d_in.p, pcm, sizeof(int16_t) * (size_t)n, cudaMemcpyHostToDevice));
     WDR_CUDA_TRY(cudaMemcpy(d_off.p, offs, sizeof(offs), cudaMemcpyHostToDevice));
     std::vector<int64_t> so = {0, n};
-    rc = fbank_run(d_in.p, d_off.p, d_off.p + 2, so, n_bins, subtract_mean, d_out.p, 0);
+    rc = fbank_run(d_in.p, d_off.p, d_off.p + 2, so, n_bins, subtract_mean, d_out.p, 0, nullptr, nullptr);
     if (rc != WDR_OK) return rc;
     WDR_CUDA_TRY(cudaMemcpy(out, d_out.p, sizeof(float) * (size_t)T * n_bins, cudaMemcpyDeviceToHost));
     return T;
@@ -254,7 +256,7 @@ extern "C" int wdr_kaldi_fbank_batch_i16_dev(const int16_t* pcm, const int64_t* 
     std::vector<int64_t> so(n_segments + 1);
     WDR_CUDA_TRY(cudaMemcpyAsync(so.data(), seg_offset, sizeof(int64_t) * (n_segments + 1), cudaMemcpyDeviceToHost, st));
     WDR_CUDA_TRY(cudaStreamSynchronize(st));
-    return fbank_run(pcm, seg_offset, feat_offset, so, n_bins, subtract_mean, out, st);
+    return fbank_run(pcm, seg_offset, feat_offset, so, n_bins, subtract_mean, out, st, nullptr, nullptr);
 }
 
 extern "C" int wdr_signal_energy(const float* pcm, int n, int half_window, float* out) {
